@@ -1,0 +1,207 @@
+"""ctypes binding of libcatchb200.so (include/catch_b200.h).  Fails loudly when the library is
+missing or when a call returns an error -- there is no CPU fallback on the product path."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libcatchb200.so')
+
+
+class CatchB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libcatchb200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class HybParams(C.Structure):
+    _fields_ = [('mismatches', C.c_int32), ('lcf_thres', C.c_int32),
+                ('island_of_exact_match', C.c_int32), ('cover_extension', C.c_int32),
+                ('k', C.c_int32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [('ms_h2d', C.c_double), ('ms_pack', C.c_double), ('ms_seed_index', C.c_double),
+                ('ms_scan_count', C.c_double), ('ms_scan_emit', C.c_double), ('ms_merge', C.c_double),
+                ('ms_universe', C.c_double), ('ms_greedy', C.c_double), ('ms_d2h', C.c_double),
+                ('ms_total', C.c_double),
+                ('n_seed_entries', C.c_int64), ('n_seed_lookups', C.c_int64),
+                ('n_candidate_hits', C.c_int64), ('n_raw_ranges', C.c_int64),
+                ('n_intervals', C.c_int64), ('n_picks', C.c_int64), ('n_kernel_launches', C.c_int64),
+                ('bytes_algorithmic', C.c_int64), ('reserved', C.c_int64 * 8)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_ if n != 'reserved'}
+
+
+# every symbol include/catch_b200.h declares
+EXPORTED_SYMBOLS = [
+    'cb_init', 'cb_destroy', 'cb_last_error', 'cb_version',
+    'cb_upload_targets', 'cb_targets_free', 'cb_upload_probes', 'cb_probes_free',
+    'cb_coverage', 'cb_cover_free', 'cb_cover_num_intervals', 'cb_cover_export',
+    'cb_setcover', 'cb_minhash_neardup', 'cb_hamming_neardup',
+]
+
+_lib = None
+
+
+def load():
+    """Load the shared library (no CUDA call is made here)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "catch_b200: %s is missing. Build it with `python -c 'import __graft_entry__ as g; "
+            "g.build()'` or `make -C catch_b200/csrc`. There is no CPU fallback." % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+    L.cb_version.restype = C.c_char_p
+    L.cb_init.argtypes = [C.c_int, C.POINTER(vp)]
+    L.cb_destroy.argtypes = [vp]
+    L.cb_destroy.restype = None
+    L.cb_last_error.argtypes = [vp]
+    L.cb_last_error.restype = C.c_char_p
+    L.cb_upload_targets.argtypes = [vp, vp, vp, i64, vp, i32, vp, i32, C.POINTER(vp), C.POINTER(Stats)]
+    L.cb_targets_free.argtypes = [vp]
+    L.cb_targets_free.restype = None
+    L.cb_upload_probes.argtypes = [vp, vp, vp, i64, vp, i32, C.POINTER(vp), C.POINTER(Stats)]
+    L.cb_probes_free.argtypes = [vp]
+    L.cb_probes_free.restype = None
+    L.cb_coverage.argtypes = [vp, vp, vp, C.POINTER(HybParams), vp, vp, C.POINTER(vp), C.POINTER(Stats)]
+    L.cb_cover_free.argtypes = [vp]
+    L.cb_cover_free.restype = None
+    L.cb_cover_num_intervals.argtypes = [vp]
+    L.cb_cover_num_intervals.restype = i64
+    L.cb_cover_export.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.cb_setcover.argtypes = [vp, vp, vp, vp, vp, C.POINTER(i64), C.POINTER(Stats)]
+    L.cb_minhash_neardup.argtypes = [vp, vp, vp, i64, vp, vp, i32, i32, i32, C.c_double, vp, C.POINTER(Stats)]
+    L.cb_hamming_neardup.argtypes = [vp, vp, vp, i64, vp, i32, i32, i32, vp, C.POINTER(Stats)]
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    return a.ctypes.data if a is not None else None
+
+
+class Context:
+    """One cb_ctx (one CUDA device, one stream).  Not thread-safe, as in the reference where a
+    filter instance is not re-entrant (probe.py:820-832)."""
+
+    def __init__(self, device_id=None):
+        self.L = load()
+        if device_id is None:
+            device_id = int(os.environ.get('LOCAL_RANK', os.environ.get('CB_DEVICE', '0')))
+        self.device_id = device_id
+        h = C.c_void_p()
+        rc = self.L.cb_init(device_id, C.byref(h))
+        self.h = h
+        if rc != 0:
+            msg = self.L.cb_last_error(h).decode() if h else 'cb_init failed'
+            raise CatchB200Error(rc, msg)
+
+    def close(self):
+        if getattr(self, 'h', None):
+            self.L.cb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise CatchB200Error(rc, self.L.cb_last_error(self.h).decode())
+
+    # ---- packing
+    def upload_targets(self, ascii_u8, seq_off, seq_genome, n_genomes, lut, bits):
+        out, st = C.c_void_p(), Stats()
+        self._check(self.L.cb_upload_targets(self.h, _ptr(ascii_u8), _ptr(seq_off), len(seq_off) - 1,
+                                             _ptr(seq_genome), n_genomes, _ptr(lut), bits,
+                                             C.byref(out), C.byref(st)))
+        return Handle(self.L.cb_targets_free, out), st
+
+    def upload_probes(self, ascii_u8, probe_off, lut, bits):
+        out, st = C.c_void_p(), Stats()
+        self._check(self.L.cb_upload_probes(self.h, _ptr(ascii_u8), _ptr(probe_off), len(probe_off) - 1,
+                                            _ptr(lut), bits, C.byref(out), C.byref(st)))
+        return Handle(self.L.cb_probes_free, out), st
+
+    # ---- stage A
+    def coverage(self, probes, targets, mismatches, lcf_thres, island, cover_extension, k,
+                 seed_off, seed_pos):
+        hp = HybParams(mismatches, lcf_thres, island, cover_extension, k)
+        out, st = C.c_void_p(), Stats()
+        self._check(self.L.cb_coverage(self.h, probes.h, targets.h, C.byref(hp), _ptr(seed_off),
+                                       _ptr(seed_pos), C.byref(out), C.byref(st)))
+        return Handle(self.L.cb_cover_free, out), st
+
+    def cover_export(self, cover):
+        n = self.L.cb_cover_num_intervals(cover.h)
+        pid = np.zeros(n, dtype=np.int64)
+        gen = np.zeros(n, dtype=np.int32)
+        start = np.zeros(n, dtype=np.int64)
+        end = np.zeros(n, dtype=np.int64)
+        self._check(self.L.cb_cover_export(self.h, cover.h, _ptr(pid), _ptr(gen), _ptr(start), _ptr(end)))
+        return pid, gen, start, end
+
+    # ---- stage B
+    def setcover(self, cover, n_probes, ranks=None, universe_p=None):
+        sel = np.zeros(max(n_probes, 1), dtype=np.int64)
+        n, st = C.c_int64(), Stats()
+        self._check(self.L.cb_setcover(self.h, cover.h, _ptr(ranks), _ptr(universe_p), _ptr(sel),
+                                       C.byref(n), C.byref(st)))
+        return sel[:n.value].copy(), st
+
+    # ---- near-duplicate filter
+    def minhash_neardup(self, ascii_u8, probe_off, a, b, n_tables, k_concat, kmer_size, dist_thres):
+        n = len(probe_off) - 1
+        keep = np.zeros(max(n, 1), dtype=np.uint8)
+        st = Stats()
+        self._check(self.L.cb_minhash_neardup(self.h, _ptr(ascii_u8), _ptr(probe_off), n, _ptr(a), _ptr(b),
+                                              n_tables, k_concat, kmer_size, float(dist_thres), _ptr(keep),
+                                              C.byref(st)))
+        return keep[:n], st
+
+    def hamming_neardup(self, ascii_u8, probe_off, positions, n_tables, k_concat, dist_thres):
+        n = len(probe_off) - 1
+        keep = np.zeros(max(n, 1), dtype=np.uint8)
+        st = Stats()
+        self._check(self.L.cb_hamming_neardup(self.h, _ptr(ascii_u8), _ptr(probe_off), n, _ptr(positions),
+                                              n_tables, k_concat, int(dist_thres), _ptr(keep), C.byref(st)))
+        return keep[:n], st
+
+
+class Handle:
+    """Owns an opaque device object and frees it with the matching cb_*_free."""
+
+    def __init__(self, free_fn, h):
+        self._free = free_fn
+        self.h = h
+
+    def free(self):
+        if self.h:
+            self._free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+_default_ctx = None
+
+
+def default_context():
+    """Process-wide context, created on first use (never at import time, so forking before the
+    first filter call stays safe)."""
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context()
+    return _default_ctx

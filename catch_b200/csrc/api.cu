@@ -1,0 +1,304 @@
+// C ABI of libcatchb200.so (see include/catch_b200.h): context, packing (uploads), exports and
+// the thin wrappers around the stage implementations.
+#include <algorithm>
+#include <cstring>
+
+#include "internal.cuh"
+
+static int upload_common_lut(cb_ctx *ctx, const uint8_t lut[256], int bits, DevBuf<uint8_t> &d_lut)
+{
+    if (bits < 1 || bits > CB_MAX_SYMBOL_BITS) return cb_fail(ctx, CB_ERR_ARG, "bits must be in [1, 8]");
+    for (int i = 0; i < 256; i++)
+        if (bits < 8 && (lut[i] >> bits)) return cb_fail(ctx, CB_ERR_ARG, "lut code does not fit in `bits`");
+    CB_CUDA(ctx, d_lut.alloc(256));
+    CB_CUDA(ctx, cudaMemcpyAsync(d_lut.p, lut, 256, cudaMemcpyHostToDevice, ctx->stream));
+    return CB_OK;
+}
+
+extern "C" {
+
+const char *cb_version(void) { return "catch_b200 0.1 sm_100a"; }
+
+int cb_init(int device_id, cb_ctx **out)
+{
+    if (!out) return CB_ERR_ARG;
+    *out = nullptr;
+    cb_ctx *ctx = new cb_ctx();
+    ctx->device = device_id;
+    cudaError_t e = cudaSetDevice(device_id);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    cudaDeviceProp prop;
+    if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device_id);
+    if (e != cudaSuccess) {
+        // keep the context alive so the caller can read the message, but mark it unusable
+        ctx->err = std::string("cb_init: ") + cudaGetErrorString(e);
+        *out = ctx;
+        return CB_ERR_CUDA;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    if (prop.major < 10) {
+        ctx->err = "cb_init: this library is built for sm_100a (Blackwell) only";
+        *out = ctx;
+        return CB_ERR_UNSUPPORTED;
+    }
+    *out = ctx;
+    return CB_OK;
+}
+
+void cb_destroy(cb_ctx *ctx)
+{
+    if (!ctx) return;
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *cb_last_error(cb_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int cb_upload_targets(cb_ctx *ctx, const uint8_t *ascii, const int64_t *seq_off, int64_t n_seqs,
+                      const int32_t *seq_genome, int32_t n_genomes, const uint8_t lut[256], int32_t bits,
+                      cb_targets **out, cb_stats *stats)
+{
+    if (!ctx || !out || !lut || n_seqs < 0 || n_genomes < 0) return cb_fail(ctx, CB_ERR_ARG, "bad argument");
+    if (n_seqs > 0 && (!seq_off || !seq_genome)) return cb_fail(ctx, CB_ERR_ARG, "null sequence table");
+    *out = nullptr;
+    if (stats) memset(stats, 0, sizeof *stats);
+    ctx->launches = 0;
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int64_t T = n_seqs ? seq_off[n_seqs] - seq_off[0] : 0;
+    if (T > 0 && !ascii) return cb_fail(ctx, CB_ERR_ARG, "null ascii");
+
+    cb_targets *t = new cb_targets();
+    struct Guard { cb_targets *t; ~Guard() { if (t) cb_targets_free(t); } } guard{t};
+    t->ctx = ctx;
+    t->bits = bits;
+    t->n_seqs = n_seqs;
+    t->n_genomes = n_genomes;
+    t->total_bases = T;
+    memcpy(t->lut, lut, 256);
+    // host tables: target coordinate of each sequence, universe layout
+    t->h_seq_start.resize((size_t)n_seqs + 1);
+    t->h_genome_len.assign((size_t)n_genomes, 0);
+    std::vector<int64_t> seq_in_genome((size_t)n_seqs, 0);
+    for (int64_t i = 0; i < n_seqs; i++) {
+        const int64_t len = seq_off[i + 1] - seq_off[i];
+        if (len < 0) return cb_fail(ctx, CB_ERR_ARG, "seq_off not monotone");
+        const int32_t g = seq_genome[i];
+        if (g < 0 || g >= n_genomes || (i > 0 && g < seq_genome[i - 1]))
+            return cb_fail(ctx, CB_ERR_ARG, "seq_genome must be non-decreasing and < n_genomes");
+        t->h_seq_start[(size_t)i] = seq_off[i] - seq_off[0];
+        seq_in_genome[(size_t)i] = t->h_genome_len[(size_t)g];      // length_so_far, set_cover_filter.py:418,453
+        t->h_genome_len[(size_t)g] += len;
+    }
+    t->h_seq_start[(size_t)n_seqs] = T;
+    t->h_ubase.resize((size_t)n_genomes + 1);
+    uint64_t ub = 0;
+    for (int32_t g = 0; g < n_genomes; g++) {
+        t->h_ubase[(size_t)g] = (uint32_t)ub;
+        ub = (ub + (uint64_t)t->h_genome_len[(size_t)g] + 1 + 63) & ~63ull;    // >= 1 spare bit, 64-aligned
+        if (ub >= 0xffffff00ull) return cb_fail(ctx, CB_ERR_UNSUPPORTED, "target group exceeds 2^32 universe bits");
+    }
+    t->h_ubase[(size_t)n_genomes] = (uint32_t)ub;
+    t->universe_bits = (int64_t)ub;
+    std::vector<uint32_t> h_seq_ubase((size_t)n_seqs);
+    for (int64_t i = 0; i < n_seqs; i++)
+        h_seq_ubase[(size_t)i] = t->h_ubase[(size_t)seq_genome[i]] + (uint32_t)seq_in_genome[(size_t)i];
+
+    int64_t pw = (T + CB_FRONT_PAD + 63) / 64 + CB_TILE_WORDS + CB_BACK_PAD_WORDS;
+    pw = (pw + 1) & ~1ll;
+    t->plane_words = pw;
+    EventTimer t_all(st), t_h2d(st), t_pack(st);
+    t_all.start();
+    CB_CUDA(ctx, cudaMalloc((void **)&t->d_planes, sizeof(uint64_t) * (size_t)pw * (size_t)bits));
+    CB_CUDA(ctx, cudaMalloc((void **)&t->d_seq_start, sizeof(int64_t) * (size_t)(n_seqs + 1)));
+    CB_CUDA(ctx, cudaMalloc((void **)&t->d_seq_genome, sizeof(int32_t) * (size_t)(n_seqs + 1)));
+    CB_CUDA(ctx, cudaMalloc((void **)&t->d_seq_ubase, sizeof(uint32_t) * (size_t)(n_seqs + 1)));
+    CB_CUDA(ctx, cudaMalloc((void **)&t->d_ubase, sizeof(uint32_t) * (size_t)(n_genomes + 1)));
+    DevBuf<uint8_t> d_ascii, d_lut;
+    CB_TRY(upload_common_lut(ctx, lut, bits, d_lut));
+    CB_CUDA(ctx, d_ascii.alloc((size_t)T));
+    t_h2d.start();
+    if (T) CB_CUDA(ctx, cudaMemcpyAsync(d_ascii.p, ascii + seq_off[0], (size_t)T, cudaMemcpyHostToDevice, st));
+    CB_CUDA(ctx, cudaMemcpyAsync(t->d_seq_start, t->h_seq_start.data(), sizeof(int64_t) * (size_t)(n_seqs + 1), cudaMemcpyHostToDevice, st));
+    if (n_seqs) {
+        CB_CUDA(ctx, cudaMemcpyAsync(t->d_seq_genome, seq_genome, sizeof(int32_t) * (size_t)n_seqs, cudaMemcpyHostToDevice, st));
+        CB_CUDA(ctx, cudaMemcpyAsync(t->d_seq_ubase, h_seq_ubase.data(), sizeof(uint32_t) * (size_t)n_seqs, cudaMemcpyHostToDevice, st));
+    }
+    CB_CUDA(ctx, cudaMemcpyAsync(t->d_ubase, t->h_ubase.data(), sizeof(uint32_t) * (size_t)(n_genomes + 1), cudaMemcpyHostToDevice, st));
+    t_h2d.stop();
+    t_pack.start();
+    CB_TRY(cb_launch_pack_targets(ctx, d_ascii.p, T, d_lut.p, bits, t->d_planes, pw));
+    t_pack.stop();
+    t_all.stop();
+    CB_CUDA(ctx, cudaStreamSynchronize(st));
+    if (stats) {
+        stats->ms_h2d = t_h2d.ms();
+        stats->ms_pack = t_pack.ms();
+        stats->ms_total = t_all.ms();
+        stats->n_kernel_launches = ctx->launches;
+    }
+    guard.t = nullptr;
+    *out = t;
+    return CB_OK;
+}
+
+void cb_targets_free(cb_targets *t)
+{
+    if (!t) return;
+    cudaFree(t->d_planes);
+    cudaFree(t->d_seq_start);
+    cudaFree(t->d_seq_genome);
+    cudaFree(t->d_seq_ubase);
+    cudaFree(t->d_ubase);
+    delete t;
+}
+
+int cb_upload_probes(cb_ctx *ctx, const uint8_t *ascii, const int64_t *probe_off, int64_t n_probes,
+                     const uint8_t lut[256], int32_t bits, cb_probes **out, cb_stats *stats)
+{
+    if (!ctx || !out || !lut || n_probes < 0) return cb_fail(ctx, CB_ERR_ARG, "bad argument");
+    if (n_probes > 0 && (!probe_off || !ascii)) return cb_fail(ctx, CB_ERR_ARG, "null probe table");
+    if (n_probes >= 0xfffffff0ll) return cb_fail(ctx, CB_ERR_UNSUPPORTED, "too many probes");
+    *out = nullptr;
+    if (stats) memset(stats, 0, sizeof *stats);
+    ctx->launches = 0;
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    int max_len = 0;
+    for (int64_t i = 0; i < n_probes; i++) {
+        const int64_t len = probe_off[i + 1] - probe_off[i];
+        if (len < 0) return cb_fail(ctx, CB_ERR_ARG, "probe_off not monotone");
+        if (len > CB_MAX_PROBE_LEN) return cb_fail(ctx, CB_ERR_UNSUPPORTED, "probe longer than CB_MAX_PROBE_LEN (256)");
+        if (len > max_len) max_len = (int)len;
+    }
+    cb_probes *p = new cb_probes();
+    struct Guard { cb_probes *p; ~Guard() { if (p) cb_probes_free(p); } } guard{p};
+    p->ctx = ctx;
+    p->bits = bits;
+    p->n_probes = n_probes;
+    p->max_len = max_len;
+    p->nw = max_len ? (max_len + 63) / 64 : 1;
+    memcpy(p->lut, lut, 256);
+    const int64_t total = n_probes ? probe_off[n_probes] - probe_off[0] : 0;
+    EventTimer t_all(st), t_h2d(st), t_pack(st);
+    t_all.start();
+    CB_CUDA(ctx, cudaMalloc((void **)&p->d_words, sizeof(uint64_t) * (size_t)(n_probes ? n_probes : 1) * (size_t)bits * (size_t)p->nw));
+    CB_CUDA(ctx, cudaMalloc((void **)&p->d_len, sizeof(int32_t) * (size_t)(n_probes ? n_probes : 1)));
+    DevBuf<uint8_t> d_ascii, d_lut;
+    DevBuf<int64_t> d_off;
+    CB_TRY(upload_common_lut(ctx, lut, bits, d_lut));
+    CB_CUDA(ctx, d_ascii.alloc((size_t)total));
+    CB_CUDA(ctx, d_off.alloc((size_t)n_probes + 1));
+    t_h2d.start();
+    if (n_probes) {
+        std::vector<int64_t> rel((size_t)n_probes + 1);
+        for (int64_t i = 0; i <= n_probes; i++) rel[(size_t)i] = probe_off[i] - probe_off[0];
+        if (total) CB_CUDA(ctx, cudaMemcpyAsync(d_ascii.p, ascii + probe_off[0], (size_t)total, cudaMemcpyHostToDevice, st));
+        CB_CUDA(ctx, cudaMemcpyAsync(d_off.p, rel.data(), sizeof(int64_t) * (size_t)(n_probes + 1), cudaMemcpyHostToDevice, st));
+        CB_CUDA(ctx, cudaStreamSynchronize(st));    // `rel` goes out of scope
+    }
+    t_h2d.stop();
+    t_pack.start();
+    CB_TRY(cb_launch_pack_probes(ctx, d_ascii.p, d_off.p, n_probes, d_lut.p, bits, p->nw, p->d_words, p->d_len));
+    t_pack.stop();
+    t_all.stop();
+    CB_CUDA(ctx, cudaStreamSynchronize(st));
+    if (stats) {
+        stats->ms_h2d = t_h2d.ms();
+        stats->ms_pack = t_pack.ms();
+        stats->ms_total = t_all.ms();
+        stats->n_kernel_launches = ctx->launches;
+    }
+    guard.p = nullptr;
+    *out = p;
+    return CB_OK;
+}
+
+void cb_probes_free(cb_probes *p)
+{
+    if (!p) return;
+    cudaFree(p->d_words);
+    cudaFree(p->d_len);
+    delete p;
+}
+
+int cb_coverage(cb_ctx *ctx, const cb_probes *probes, const cb_targets *targets, const cb_hyb_params *params,
+                const int64_t *seed_off, const int32_t *seed_pos, cb_cover **out, cb_stats *stats)
+{
+    if (!ctx) return CB_ERR_ARG;
+    if (stats) memset(stats, 0, sizeof *stats);
+    ctx->launches = 0;
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    return cb_coverage_impl(ctx, probes, targets, params, seed_off, seed_pos, out, stats);
+}
+
+void cb_cover_free(cb_cover *c)
+{
+    if (!c) return;
+    cudaFree(c->d_iv_off);
+    cudaFree(c->d_iv);
+    cudaFree(c->d_ubase);
+    delete c;
+}
+
+int64_t cb_cover_num_intervals(const cb_cover *c) { return c ? c->n_intervals : 0; }
+
+int cb_cover_export(cb_ctx *ctx, const cb_cover *c, int64_t *probe_id, int32_t *genome, int64_t *start, int64_t *end)
+{
+    if (!ctx || !c) return cb_fail(ctx, CB_ERR_ARG, "null argument");
+    const int64_t E = c->n_intervals, P = c->n_probes;
+    if (E == 0) return CB_OK;
+    if (!probe_id || !genome || !start || !end) return cb_fail(ctx, CB_ERR_ARG, "null output array");
+    std::vector<int64_t> off((size_t)P + 1);
+    std::vector<uint2> iv((size_t)E);
+    CB_CUDA(ctx, cudaMemcpyAsync(off.data(), c->d_iv_off, sizeof(int64_t) * (size_t)(P + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    CB_CUDA(ctx, cudaMemcpyAsync(iv.data(), c->d_iv, sizeof(uint2) * (size_t)E, cudaMemcpyDeviceToHost, ctx->stream));
+    CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const std::vector<uint32_t> &ub = c->h_ubase;
+    for (int64_t p = 0; p < P; p++)
+        for (int64_t i = off[(size_t)p]; i < off[(size_t)p + 1]; i++) {
+            const uint32_t s = iv[(size_t)i].x, e = iv[(size_t)i].y;
+            const int32_t g = (int32_t)(std::upper_bound(ub.begin(), ub.end(), s) - ub.begin()) - 1;
+            probe_id[i] = p;
+            genome[i] = g;
+            start[i] = (int64_t)s - (int64_t)ub[(size_t)g];
+            end[i] = (int64_t)e - (int64_t)ub[(size_t)g];
+        }
+    return CB_OK;
+}
+
+int cb_setcover(cb_ctx *ctx, const cb_cover *cover, const int32_t *ranks, const double *universe_p,
+                int64_t *sel_ids, int64_t *n_sel, cb_stats *stats)
+{
+    if (!ctx) return CB_ERR_ARG;
+    if (stats) memset(stats, 0, sizeof *stats);
+    ctx->launches = 0;
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    return cb_setcover_impl(ctx, cover, ranks, universe_p, sel_ids, n_sel, stats);
+}
+
+int cb_minhash_neardup(cb_ctx *ctx, const uint8_t *ascii, const int64_t *probe_off, int64_t n_probes,
+                       const uint32_t *a, const uint32_t *b, int32_t n_tables, int32_t k_concat,
+                       int32_t kmer_size, double dist_thres, uint8_t *keep, cb_stats *stats)
+{
+    if (!ctx) return CB_ERR_ARG;
+    if (stats) memset(stats, 0, sizeof *stats);
+    ctx->launches = 0;
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    return cb_minhash_neardup_impl(ctx, ascii, probe_off, n_probes, a, b, n_tables, k_concat, kmer_size,
+                                   dist_thres, keep, stats);
+}
+
+int cb_hamming_neardup(cb_ctx *ctx, const uint8_t *ascii, const int64_t *probe_off, int64_t n_probes,
+                       const int32_t *positions, int32_t n_tables, int32_t k_concat, int32_t dist_thres,
+                       uint8_t *keep, cb_stats *stats)
+{
+    if (!ctx) return CB_ERR_ARG;
+    if (stats) memset(stats, 0, sizeof *stats);
+    ctx->launches = 0;
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    return cb_hamming_neardup_impl(ctx, ascii, probe_off, n_probes, positions, n_tables, k_concat,
+                                   dist_thres, keep, stats);
+}
+
+}  // extern "C"

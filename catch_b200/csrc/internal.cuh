@@ -1,0 +1,168 @@
+// Internal declarations shared by the translation units of libcatchb200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/catch_b200.h"
+
+// ---------------------------------------------------------------------------------------
+// Device data layout
+//
+// Sequences are held as bit planes ("bit-sliced"): plane w, bit i = bit w of the symbol code
+// of base i.  Two bases differ iff any plane differs, so the mismatch mask of a probe against
+// a target window is OR_w (probe_plane_w XOR window_plane_w): one XOR+OR per plane per 64
+// bases, for any alphabet size (2 planes for ACGT, 3 with N, up to 8 for arbitrary bytes).
+//
+// Targets: all sequences of a group back to back; target coordinate g is stored at bit
+// (g + CB_FRONT_PAD) of every plane so windows that hang off the left end read zeros.
+// Probes: probe p owns planes*NW consecutive words, [plane][word], NW = ceil(maxlen/64).
+// Universe coordinates: genome u owns bits [ubase[u], ubase[u]+genome_len[u]) of the universe
+// bit set; ubase is 64-aligned and leaves >= 1 unused bit between genomes so intervals of
+// different genomes never touch.
+// ---------------------------------------------------------------------------------------
+#define CB_FRONT_PAD 256          // bits of zeros in front of target position 0
+#define CB_BACK_PAD_WORDS 8       // zero words after the last base
+#define CB_TILE 1024              // target positions per scan tile
+#define CB_TILE_WORDS ((CB_TILE + 2 * CB_FRONT_PAD) / 64 + 2)   // staged words per plane (even)
+
+struct cb_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t launches = 0;         // kernels launched since the counter was last reset
+};
+
+struct cb_targets {
+    cb_ctx *ctx = nullptr;
+    int bits = 0;
+    int64_t n_seqs = 0;
+    int32_t n_genomes = 0;
+    int64_t total_bases = 0;       // T
+    int64_t plane_words = 0;       // words per plane (even)
+    uint64_t *d_planes = nullptr;  // [bits][plane_words]
+    int64_t *d_seq_start = nullptr;    // [n_seqs+1] target coordinate of each sequence
+    int32_t *d_seq_genome = nullptr;   // [n_seqs]
+    uint32_t *d_seq_ubase = nullptr;   // [n_seqs] universe bit of the sequence's first base
+    uint32_t *d_ubase = nullptr;       // [n_genomes+1] universe bit of each genome's first base
+    std::vector<int64_t> h_seq_start;
+    std::vector<uint32_t> h_ubase;     // [n_genomes+1]
+    std::vector<int64_t> h_genome_len; // [n_genomes]
+    int64_t universe_bits = 0;         // total bits (multiple of 64)
+    uint8_t lut[256];
+};
+
+struct cb_probes {
+    cb_ctx *ctx = nullptr;
+    int bits = 0;
+    int64_t n_probes = 0;
+    int nw = 0;                        // words per plane per probe
+    int max_len = 0;
+    uint64_t *d_words = nullptr;       // [n_probes][bits][nw]
+    int32_t *d_len = nullptr;          // [n_probes]
+    uint8_t lut[256];
+};
+
+struct cb_cover {
+    cb_ctx *ctx = nullptr;
+    int64_t n_probes = 0;
+    int32_t n_genomes = 0;
+    int64_t n_intervals = 0;
+    int64_t universe_bits = 0;
+    uint32_t max_interval_len = 0;
+    int64_t *d_iv_off = nullptr;       // [n_probes+1]
+    uint2 *d_iv = nullptr;             // [n_intervals] (start, end) universe coordinates, sorted per probe
+    uint32_t *d_ubase = nullptr;       // [n_genomes+1] (own copy)
+    std::vector<uint32_t> h_ubase;
+    std::vector<int64_t> h_genome_len;
+};
+
+// ---------------------------------------------------------------------------------------
+// Error handling
+// ---------------------------------------------------------------------------------------
+#define CB_CUDA(ctx, call)                                                                   \
+    do {                                                                                     \
+        cudaError_t e__ = (call);                                                            \
+        if (e__ != cudaSuccess) {                                                            \
+            char buf__[512];                                                                 \
+            snprintf(buf__, sizeof buf__, "%s:%d: %s failed: %s", __FILE__, __LINE__, #call, \
+                     cudaGetErrorString(e__));                                               \
+            (ctx)->err = buf__;                                                              \
+            return CB_ERR_CUDA;                                                              \
+        }                                                                                    \
+    } while (0)
+
+#define CB_TRY(expr)                \
+    do {                            \
+        int r__ = (expr);           \
+        if (r__ != CB_OK) return r__; \
+    } while (0)
+
+static inline int cb_fail(cb_ctx *ctx, int code, const char *msg)
+{
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+// RAII device buffer tied to a stream-ordered context (plain cudaMalloc/cudaFree).
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    DevBuf() {}
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t count)
+    {
+        if (p) { cudaFree(p); p = nullptr; }
+        n = count;
+        return cudaMalloc((void **)&p, (count ? count : 1) * sizeof(T));
+    }
+    T *release() { T *q = p; p = nullptr; return q; }
+};
+
+struct EventTimer {
+    cudaEvent_t a = nullptr, b = nullptr;
+    cudaStream_t s;
+    explicit EventTimer(cudaStream_t st) : s(st) { cudaEventCreate(&a); cudaEventCreate(&b); }
+    ~EventTimer() { cudaEventDestroy(a); cudaEventDestroy(b); }
+    void start() { cudaEventRecord(a, s); }
+    // records the end event; the value is read later with ms() after a sync
+    void stop() { cudaEventRecord(b, s); }
+    double ms() { float f = 0; cudaEventSynchronize(b); cudaEventElapsedTime(&f, a, b); return f; }
+};
+
+// ---------------------------------------------------------------------------------------
+// Launchers implemented in the .cu files
+// ---------------------------------------------------------------------------------------
+// scan.cu
+int cb_exclusive_scan_u32_to_i64(cb_ctx *ctx, const uint32_t *d_in, int64_t *d_out, int64_t n,
+                                 int64_t *h_total);
+// d_out has n+1 entries: d_out[i] = sum of d_in[0..i), d_out[n] = total.
+
+// pack.cu
+int cb_launch_pack_targets(cb_ctx *ctx, const uint8_t *d_ascii, int64_t total, const uint8_t *d_lut,
+                           int bits, uint64_t *d_planes, int64_t plane_words);
+int cb_launch_pack_probes(cb_ctx *ctx, const uint8_t *d_ascii, const int64_t *d_off, int64_t n_probes,
+                          const uint8_t *d_lut, int bits, int nw, uint64_t *d_words, int32_t *d_len);
+
+// coverage.cu
+int cb_coverage_impl(cb_ctx *ctx, const cb_probes *probes, const cb_targets *targets,
+                     const cb_hyb_params *params, const int64_t *seed_off, const int32_t *seed_pos,
+                     cb_cover **out, cb_stats *stats);
+
+// setcover.cu
+int cb_setcover_impl(cb_ctx *ctx, const cb_cover *cover, const int32_t *ranks, const double *universe_p,
+                     int64_t *sel_ids, int64_t *n_sel, cb_stats *stats);
+
+// neardup.cu
+int cb_minhash_neardup_impl(cb_ctx *ctx, const uint8_t *ascii, const int64_t *probe_off, int64_t n_probes,
+                            const uint32_t *a, const uint32_t *b, int32_t n_tables, int32_t k_concat,
+                            int32_t kmer_size, double dist_thres, uint8_t *keep, cb_stats *stats);
+int cb_hamming_neardup_impl(cb_ctx *ctx, const uint8_t *ascii, const int64_t *probe_off, int64_t n_probes,
+                            const int32_t *positions, int32_t n_tables, int32_t k_concat,
+                            int32_t dist_thres, uint8_t *keep, cb_stats *stats);

@@ -1,0 +1,97 @@
+// K1: ASCII -> bit planes.  Replaces the per-hit str -> np.array('U1') conversion of the
+// reference (probe.py:1074) and Probe.from_str (probe.py:344): every sequence is packed once.
+// A warp packs 64 bases at a time: each lane loads two bytes (coalesced), maps them through the
+// 256-entry code table in shared memory, and one __ballot_sync per plane yields 32 bits of that
+// plane directly.
+#include "internal.cuh"
+
+namespace {
+
+constexpr int PACK_THREADS = 256;
+
+__global__ void __launch_bounds__(PACK_THREADS)
+pack_targets_kernel(const uint8_t *__restrict__ ascii, int64_t total, const uint8_t *__restrict__ lut,
+                    int bits, uint64_t *__restrict__ planes, int64_t plane_words)
+{
+    __shared__ uint8_t s_lut[256];
+    s_lut[threadIdx.x & 255] = lut[threadIdx.x & 255];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * PACK_THREADS + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * PACK_THREADS) >> 5;
+    const int64_t n_words = (total + 63) >> 6;
+    for (int64_t w = warp; w < n_words; w += n_warps) {
+        const int64_t g0 = w << 6;
+        const int64_t i0 = g0 + lane, i1 = g0 + 32 + lane;
+        const unsigned c0 = i0 < total ? s_lut[ascii[i0]] : 0u;
+        const unsigned c1 = i1 < total ? s_lut[ascii[i1]] : 0u;
+        for (int b = 0; b < bits; b++) {
+            const unsigned lo = __ballot_sync(0xffffffffu, (c0 >> b) & 1u);
+            const unsigned hi = __ballot_sync(0xffffffffu, (c1 >> b) & 1u);
+            if (lane == b)
+                planes[(int64_t)b * plane_words + (CB_FRONT_PAD >> 6) + w] =
+                    ((uint64_t)hi << 32) | (uint64_t)lo;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(PACK_THREADS)
+pack_probes_kernel(const uint8_t *__restrict__ ascii, const int64_t *__restrict__ off, int64_t n_probes,
+                   const uint8_t *__restrict__ lut, int bits, int nw, uint64_t *__restrict__ words,
+                   int32_t *__restrict__ lens)
+{
+    __shared__ uint8_t s_lut[256];
+    s_lut[threadIdx.x & 255] = lut[threadIdx.x & 255];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * PACK_THREADS + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * PACK_THREADS) >> 5;
+    for (int64_t p = warp; p < n_probes; p += n_warps) {
+        const int64_t beg = off[p];
+        const int len = (int)(off[p + 1] - beg);
+        if (lane == 0) lens[p] = len;
+        uint64_t *dst = words + p * (int64_t)bits * nw;
+        for (int w = 0; w < nw; w++) {
+            const int j0 = w * 64 + lane, j1 = j0 + 32;
+            const unsigned c0 = j0 < len ? s_lut[ascii[beg + j0]] : 0u;
+            const unsigned c1 = j1 < len ? s_lut[ascii[beg + j1]] : 0u;
+            for (int b = 0; b < bits; b++) {
+                const unsigned lo = __ballot_sync(0xffffffffu, (c0 >> b) & 1u);
+                const unsigned hi = __ballot_sync(0xffffffffu, (c1 >> b) & 1u);
+                if (lane == b) dst[b * nw + w] = ((uint64_t)hi << 32) | (uint64_t)lo;
+            }
+        }
+    }
+}
+
+}  // namespace
+
+int cb_launch_pack_targets(cb_ctx *ctx, const uint8_t *d_ascii, int64_t total, const uint8_t *d_lut,
+                           int bits, uint64_t *d_planes, int64_t plane_words)
+{
+    CB_CUDA(ctx, cudaMemsetAsync(d_planes, 0, sizeof(uint64_t) * (size_t)bits * (size_t)plane_words, ctx->stream));
+    if (total == 0) return CB_OK;
+    int64_t n_words = (total + 63) >> 6;
+    int64_t blocks = (n_words * 32 + PACK_THREADS - 1) / PACK_THREADS;
+    int64_t cap = (int64_t)ctx->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    pack_targets_kernel<<<(unsigned)blocks, PACK_THREADS, 0, ctx->stream>>>(d_ascii, total, d_lut, bits,
+                                                                            d_planes, plane_words);
+    ctx->launches++;
+    CB_CUDA(ctx, cudaGetLastError());
+    return CB_OK;
+}
+
+int cb_launch_pack_probes(cb_ctx *ctx, const uint8_t *d_ascii, const int64_t *d_off, int64_t n_probes,
+                          const uint8_t *d_lut, int bits, int nw, uint64_t *d_words, int32_t *d_len)
+{
+    if (n_probes == 0) return CB_OK;
+    int64_t blocks = (n_probes * 32 + PACK_THREADS - 1) / PACK_THREADS;
+    int64_t cap = (int64_t)ctx->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    pack_probes_kernel<<<(unsigned)blocks, PACK_THREADS, 0, ctx->stream>>>(d_ascii, d_off, n_probes, d_lut,
+                                                                           bits, nw, d_words, d_len);
+    ctx->launches++;
+    CB_CUDA(ctx, cudaGetLastError());
+    return CB_OK;
+}

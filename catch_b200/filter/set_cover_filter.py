@@ -1,0 +1,207 @@
+"""SetCoverFilter on the device: the drop-in for catch/filter/set_cover_filter.py:195-930.
+
+Same constructor, attributes and `_filter(input, target_genomes_grouped)` contract as the
+reference (:199-213, :902-930): for every grouping it computes which bases of the grouping's
+target genomes each candidate probe covers (stage A, reference `_make_sets` :359-470), then picks
+probes by greedy multi-universe set cover (stage B, `set_cover.approx_multiuniverse`), and
+returns the SAME Probe objects it was given, in the order the reference would emit them.
+
+Host work kept here on purpose: the seed choice (it replays numpy's global RNG exactly as the
+reference consumes it), duplicate handling, ranks/universe_p bookkeeping and the Python-set
+ordering of the output.  Everything else is in libcatchb200.so; there is no CPU fallback.
+"""
+import logging
+import pickle
+import time
+
+import numpy as np
+
+from catch_b200 import _lib
+from catch_b200 import coverage as cov
+from catch_b200.filter.base_filter import BaseFilter
+from catch_b200.utils import seq_io
+
+logger = logging.getLogger(__name__)
+
+
+def set_max_num_processes_for_set_cover_instances(max_num_processes=8):
+    """Interface compatibility (set_cover_filter.py:66-80); groupings are solved on the GPU one
+    after the other, no process pool exists."""
+    global _sc_max_num_processes
+    _sc_max_num_processes = max_num_processes
+
+
+set_max_num_processes_for_set_cover_instances()
+
+_RC = str.maketrans('ACGT', 'TGCA')
+
+
+def _reverse_complement(s):
+    # rc_map.get(b, b): anything outside ACGT maps to itself (set_cover_filter.py:514-520)
+    return s[::-1].translate(_RC)
+
+
+class SetCoverFilter(BaseFilter):
+    def __init__(self, mismatches, lcf_thres, island_of_exact_match=0, mismatches_tolerant=None,
+                 lcf_thres_tolerant=None, island_of_exact_match_tolerant=None,
+                 custom_cover_range_fn=None, custom_cover_range_tolerant_fn=None, identify=False,
+                 avoided_genomes=[], coverage=1.0, cover_extension=0, kmer_probe_map_k=20,
+                 kmer_probe_map_use_native_dict=False):
+        if custom_cover_range_fn is not None or custom_cover_range_tolerant_fn is not None:
+            # the reference loads an arbitrary Python predicate (set_cover_filter.py:296-299);
+            # that cannot run inside a CUDA kernel
+            raise NotImplementedError("custom hybridization functions are Python callables and "
+                                      "are not supported by the device implementation")
+        self.mismatches = mismatches
+        self.lcf_thres = lcf_thres
+        self.island_of_exact_match = island_of_exact_match
+        # reference keeps callables here; the device path carries the parameters instead
+        self.cover_range_fn = ('lcf', mismatches, lcf_thres, island_of_exact_match)
+        if not mismatches_tolerant:
+            mismatches_tolerant = mismatches
+        if not lcf_thres_tolerant:
+            lcf_thres_tolerant = lcf_thres
+        if not island_of_exact_match_tolerant:
+            island_of_exact_match_tolerant = island_of_exact_match
+        self.mismatches_tolerant = mismatches_tolerant
+        self.lcf_thres_tolerant = lcf_thres_tolerant
+        self.island_of_exact_match_tolerant = island_of_exact_match_tolerant
+        self.cover_range_tolerant_fn = ('lcf', mismatches_tolerant, lcf_thres_tolerant,
+                                        island_of_exact_match_tolerant)
+        if identify:
+            if (coverage <= 1.0 and coverage >= 0.25) or (coverage > 1 and coverage >= 5000):
+                logger.warning("Identification is enabled but the required coverage is high; "
+                               "generally coverage should be small when performing identification")
+        self.identify = identify
+        self.avoided_genomes = avoided_genomes
+        self.coverage = coverage
+        self.cover_extension = cover_extension
+        self.kmer_probe_map_k = kmer_probe_map_k
+        self.kmer_probe_map_use_native_dict = kmer_probe_map_use_native_dict
+        self.requires_probe_groupings = True
+        self._force_num_processes = None       # accepted and ignored (tests set it)
+        self._ctx = None
+        self.last_stats = []                   # one dict per grouping of the last _filter call
+
+    # ------------------------------------------------------------------ helpers
+    def _context(self):
+        if self._ctx is None:
+            self._ctx = _lib.default_context()
+        return self._ctx
+
+    def _make_universe_p(self, target_genomes):
+        """set_cover_filter.py:761-792."""
+        if self.coverage <= 1.0:
+            return np.full(len(target_genomes), float(self.coverage), dtype=np.float64)
+        p = np.empty(len(target_genomes), dtype=np.float64)
+        for j, g in enumerate(target_genomes):
+            size = g.size()
+            p[j] = float(min(self.coverage, size)) / size
+        return p
+
+    def _tolerant_bp_covered(self, ctx, probe_strs, sequences):
+        """Sum over `sequences` and their reverse complements of the bp each probe covers under
+        the tolerant parameters (set_cover_filter.py:472-529): ranges merged per sequence, no
+        cover extension.  Each sequence and each reverse complement is packed as its own
+        'genome' so merging stays per sequence."""
+        seqs = []
+        for s in sequences:
+            seqs.append([s])
+            seqs.append([_reverse_complement(s)])
+        group = cov.PackedGroup(ctx, probe_strs, seqs)
+        try:
+            cover, st, _, _ = cov.compute_cover(ctx, group, probe_strs, self.mismatches_tolerant,
+                                                self.lcf_thres_tolerant,
+                                                self.island_of_exact_match_tolerant, 0,
+                                                self.kmer_probe_map_k)
+            pid, _, start, end = ctx.cover_export(cover)
+            cover.free()
+        finally:
+            group.free()
+        bp = np.zeros(len(probe_strs), dtype=np.int64)
+        if len(pid):
+            np.add.at(bp, pid, end - start)
+        return bp
+
+    def _make_ranks(self, ctx, probe_strs, target_genomes_grouped):
+        """set_cover_filter.py:614-735.  Returns None when every probe has the same rank."""
+        if not self.identify and len(self.avoided_genomes) == 0:
+            return None
+        n = len(probe_strs)
+        rep = cov.dedup_map(probe_strs)
+        first = np.zeros(n, dtype=np.int64)
+        second = np.zeros(n, dtype=np.int64)
+        if self.identify:
+            hits = np.zeros(n, dtype=np.int64)
+            for genomes in target_genomes_grouped:
+                seqs = [s for g in genomes for s in g.seqs]
+                bp = self._tolerant_bp_covered(ctx, probe_strs, seqs)
+                hits += (bp >= 1)
+            second = hits
+        avoided_bp = np.zeros(n, dtype=np.int64)
+        for path in self.avoided_genomes:
+            seqs = list(seq_io.iterate_fasta(path))
+            avoided_bp += self._tolerant_bp_covered(ctx, probe_strs, seqs)
+        if rep is not None:
+            # dicts keyed by sequence: all duplicates share the values of their representative
+            rep = np.asarray(rep)
+            second = second[rep]
+            avoided_bp = avoided_bp[rep]
+        mask = avoided_bp > 0
+        first[mask] = 1
+        second = np.where(mask, avoided_bp, second)
+        tuples = sorted(set(zip(first.tolist(), second.tolist())))
+        idx = {t: i for i, t in enumerate(tuples)}
+        return np.array([idx[(a, b)] for a, b in zip(first.tolist(), second.tolist())], dtype=np.int32)
+
+    # ------------------------------------------------------------------ the filter
+    def _filter(self, input, target_genomes_grouped):
+        ctx = self._context()
+        self.last_stats = []
+        selected = []
+        for group_i, (possible_probes, target_genomes) in enumerate(zip(input, target_genomes_grouped)):
+            possible_probes = list(possible_probes)
+            t0 = time.perf_counter()
+            stats = {'group': group_i, 'n_probes': len(possible_probes),
+                     'target_bp': sum(g.size() for g in target_genomes)}
+            if len(possible_probes) == 0:                       # set_cover_filter.py:393-394
+                selected.append([])
+                self.last_stats.append(stats)
+                continue
+            probe_strs = [p.seq_str for p in possible_probes]
+            logger.info("Computing coverage of %d probes in %d genomes (group %d of %d)",
+                        len(probe_strs), len(target_genomes), group_i + 1, len(input))
+            group = cov.PackedGroup(ctx, probe_strs, target_genomes)
+            try:
+                cover, st_a, k, mode = cov.compute_cover(
+                    ctx, group, probe_strs, self.mismatches, self.lcf_thres,
+                    self.island_of_exact_match, self.cover_extension, self.kmer_probe_map_k)
+            finally:
+                group.free()
+            try:
+                ranks = self._make_ranks(ctx, probe_strs, target_genomes_grouped)
+                universe_p = self._make_universe_p(target_genomes)
+                picks, st_b = ctx.setcover(cover, len(probe_strs), ranks, universe_p)
+            finally:
+                cover.free()
+            if ranks is not None:
+                n_bad = int(np.sum(ranks[picks] > 0))
+                if n_bad > 0:
+                    logger.warning("Group %d: forced to choose %d less-than-ideal probe%s",
+                                   group_i + 1, n_bad, '' if n_bad == 1 else 's')
+            # The reference returns a Python set of ids from a Pool worker and iterates it
+            # (set_cover_filter.py:893-900, :926): same elements, CPython set order after a
+            # pickle round trip.  Reproduce it with the real thing.
+            chosen = set()
+            for i in picks.tolist():
+                chosen.add(i)
+            chosen = pickle.loads(pickle.dumps(chosen))
+            selected.append([possible_probes[i] for i in chosen])
+            stats.update(seed_mode=mode, k=k, bits=group.bits, h2d_bytes=group.h2d_bytes,
+                         d2h_bytes=int(picks.nbytes), picks=picks,
+                         upload_targets=group.st_targets.as_dict(),
+                         upload_probes=group.st_probes.as_dict(),
+                         coverage=st_a.as_dict(), setcover=st_b.as_dict(),
+                         wall_s=time.perf_counter() - t0)
+            self.last_stats.append(stats)
+        return selected

@@ -1,0 +1,159 @@
+/*
+ * catch_b200.h -- C ABI of libcatchb200.so, the sm_100a implementation of the CATCH
+ * probe-coverage + set-cover + near-duplicate hot path.
+ *
+ * The reference (broadinstitute/catch) is pure Python and has no FFI; this header is the
+ * boundary a maintainer would bind with ctypes from the reference's filter classes
+ * (see INTEGRATION.md).  Each entry point names the reference code it replaces
+ * (paths relative to the reference tree).
+ *
+ * Conventions: every function returns 0 on success and a negative cb_status on error;
+ * cb_last_error(ctx) gives the message.  Handles are opaque and released with the matching
+ * *_free call.  Calls are synchronous (they return after the context's stream has been
+ * synchronised) and a cb_ctx must only be used from one host thread at a time.
+ * Host pointers are plain caller-owned memory; nothing here takes or returns torch types.
+ */
+#ifndef CATCH_B200_H
+#define CATCH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cb_ctx cb_ctx;
+typedef struct cb_targets cb_targets;
+typedef struct cb_probes cb_probes;
+typedef struct cb_cover cb_cover;
+
+enum cb_status {
+    CB_OK = 0,
+    CB_ERR_CUDA = -1,        /* a CUDA runtime call failed */
+    CB_ERR_ARG = -2,         /* invalid argument */
+    CB_ERR_UNSUPPORTED = -3, /* outside the supported envelope */
+    CB_ERR_NOMEM = -4,
+    CB_ERR_STATE = -5,       /* e.g. set cover could not reach the requested coverage */
+    CB_ERR_COMM = -6         /* NCCL failure */
+};
+
+/* Limits of the device kernels. */
+#define CB_MAX_PROBE_LEN 256     /* bases per probe */
+#define CB_MAX_SYMBOL_BITS 8     /* bit planes per base */
+#define CB_MAX_MISMATCHES 31
+
+/* Hybridisation model parameters: probe.py:1274-1346
+ * probe_covers_sequence_by_longest_common_substring(mismatches, lcf_thres, island). */
+typedef struct {
+    int32_t mismatches;
+    int32_t lcf_thres;
+    int32_t island_of_exact_match;
+    int32_t cover_extension;     /* filter/set_cover_filter.py:429-432 */
+    int32_t k;                   /* seed (k-mer) length of the probe map, probe.py:507-577 */
+} cb_hyb_params;
+
+/* Per-call timings (CUDA events on the context's stream, milliseconds) and counters. */
+typedef struct {
+    double ms_h2d;               /* host->device copies inside the call */
+    double ms_pack;              /* ASCII -> bit-plane packing */
+    double ms_seed_index;        /* K2 */
+    double ms_scan_count;        /* K3, counting pass */
+    double ms_scan_emit;         /* K3, emitting pass */
+    double ms_merge;             /* K4 */
+    double ms_universe;          /* K5 + gain initialisation */
+    double ms_greedy;            /* K6-K8 persistent greedy kernel */
+    double ms_d2h;
+    double ms_total;             /* wall time of the call on the device timeline */
+    int64_t n_seed_entries;
+    int64_t n_seed_lookups;      /* target positions looked up */
+    int64_t n_candidate_hits;    /* bucket entries examined */
+    int64_t n_raw_ranges;        /* cover ranges emitted before merging */
+    int64_t n_intervals;         /* merged (probe, genome) intervals */
+    int64_t n_picks;
+    int64_t n_kernel_launches;
+    int64_t bytes_algorithmic;   /* DESIGN.md formula, for the roofline */
+    int64_t reserved[8];
+} cb_stats;
+
+/* ---- context --------------------------------------------------------------------- */
+int cb_init(int device_id, cb_ctx **out);
+void cb_destroy(cb_ctx *ctx);
+const char *cb_last_error(cb_ctx *ctx);
+/* Library build identification ("catch_b200 <version> sm_100a"). */
+const char *cb_version(void);
+
+/* ---- packing (K1) ------------------------------------------------------------------
+ * Replaces the per-hit str -> np.array('U1') conversions of probe.py:1074 and
+ * Probe.from_str (probe.py:344): sequences go to the device once, as `bits` bit planes
+ * per base.  `lut` maps every input byte to a code < 2^bits; two bases match iff their
+ * codes are equal (plain character equality, utils/longest_common_substring.py:110, so the
+ * host must give distinct codes to distinct characters, 'N' included).
+ *
+ * Targets: `n_seqs` sequences concatenated in `ascii`, sequence i at
+ * [seq_off[i], seq_off[i+1]).  seq_genome[i] (non-decreasing, 0..n_genomes-1) is the genome
+ * ("universe", filter/set_cover_filter.py:414-416) the sequence belongs to. */
+int cb_upload_targets(cb_ctx *ctx, const uint8_t *ascii, const int64_t *seq_off, int64_t n_seqs,
+                      const int32_t *seq_genome, int32_t n_genomes, const uint8_t lut[256],
+                      int32_t bits, cb_targets **out, cb_stats *stats);
+void cb_targets_free(cb_targets *t);
+
+/* Probes: probe i is ascii[probe_off[i] .. probe_off[i+1]), at most CB_MAX_PROBE_LEN. */
+int cb_upload_probes(cb_ctx *ctx, const uint8_t *ascii, const int64_t *probe_off, int64_t n_probes,
+                     const uint8_t lut[256], int32_t bits, cb_probes **out, cb_stats *stats);
+void cb_probes_free(cb_probes *p);
+
+/* ---- stage A: coverage (K2-K4) -----------------------------------------------------
+ * Replaces SetCoverFilter._make_sets (filter/set_cover_filter.py:359-470), i.e.
+ * probe.SharedKmerProbeMap.construct (probe.py:684-763) + open_probe_finding_pool +
+ * find_probe_covers_in_sequence over every target sequence (probe.py:1008-1271) with the
+ * predicate of probe.py:1328-1344, followed by the +-cover_extension / clip / genome-offset
+ * step (:429-439) and interval.IntervalSet merging (:462-466).
+ *
+ * seed_off/seed_pos: CSR over probes of the DISTINCT seed start positions, ascending within
+ * a probe.  The host generates them (pigeonhole rule or a replay of numpy's legacy RNG,
+ * probe.py:356-504) because they depend on host RNG state. */
+int cb_coverage(cb_ctx *ctx, const cb_probes *probes, const cb_targets *targets,
+                const cb_hyb_params *params, const int64_t *seed_off, const int32_t *seed_pos,
+                cb_cover **out, cb_stats *stats);
+void cb_cover_free(cb_cover *c);
+
+/* Number of merged (probe, genome, start, end) intervals held by a cover. */
+int64_t cb_cover_num_intervals(const cb_cover *c);
+/* Copy them out, sorted by (probe, genome, start); start/end are genome coordinates
+ * (positions of all sequences of the genome laid end to end, :438-439).  Arrays are
+ * caller-allocated with cb_cover_num_intervals() entries. */
+int cb_cover_export(cb_ctx *ctx, const cb_cover *c, int64_t *probe_id, int32_t *genome,
+                    int64_t *start, int64_t *end);
+
+/* ---- stage B: greedy multi-universe set cover (K5-K8) -------------------------------
+ * Replaces set_cover.approx_multiuniverse(sets, costs=1, universe_p, ranks,
+ * use_intervalsets=True) (utils/set_cover.py:147-615) as called from
+ * filter/set_cover_filter.py:136-142.
+ * ranks: one int32 per probe or NULL (all equal).  universe_p: one double per genome or NULL
+ * (1.0).  sel_ids: caller-allocated, capacity n_probes; filled in PICK ORDER. */
+int cb_setcover(cb_ctx *ctx, const cb_cover *cover, const int32_t *ranks, const double *universe_p,
+                int64_t *sel_ids, int64_t *n_sel, cb_stats *stats);
+
+/* ---- near-duplicate filter (K9-K12) --------------------------------------------------
+ * Replaces NearDuplicateFilter._filter (filter/near_duplicate_filter.py:47-103) with
+ * lsh.NearNeighborLookup (utils/lsh.py:239-320).  `probes` are the DISTINCT probes in
+ * priority order (multiplicity descending, stable; :61-66).  keep[i] = 1 iff probe i is kept.
+ *
+ * MinHash family (utils/lsh.py:74-148, N=1, use_fast_str_hash=True under PYTHONHASHSEED=0):
+ * a/b hold n_tables*k_concat drawn parameters, function f of table t at index t*k_concat+f.
+ * The inner string hash is CPython's SipHash-1-3 with a zero key over the k-mer's bytes, so
+ * this entry point needs the probes' ASCII (passed again here). */
+int cb_minhash_neardup(cb_ctx *ctx, const uint8_t *ascii, const int64_t *probe_off, int64_t n_probes,
+                       const uint32_t *a, const uint32_t *b, int32_t n_tables, int32_t k_concat,
+                       int32_t kmer_size, double dist_thres, uint8_t *keep, cb_stats *stats);
+
+/* Hamming family (utils/lsh.py:16-45): positions holds n_tables*k_concat sampled indices;
+ * all probes must have the same length. */
+int cb_hamming_neardup(cb_ctx *ctx, const uint8_t *ascii, const int64_t *probe_off, int64_t n_probes,
+                       const int32_t *positions, int32_t n_tables, int32_t k_concat,
+                       int32_t dist_thres, uint8_t *keep, cb_stats *stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CATCH_B200_H */

@@ -1,0 +1,109 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.  Needs a B200."""
+import random
+
+import numpy as np
+import pytest
+
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle():
+    from oracle import oracle
+    return oracle
+
+
+def _device_quads(ctx, probe_strs, genomes, params, k=None):
+    from catch_b200 import coverage as cov
+    group = cov.PackedGroup(ctx, probe_strs, genomes)
+    cover, st, k, mode = cov.compute_cover(ctx, group, probe_strs, params['mismatches'], params['lcf_thres'],
+                                           params['island_of_exact_match'], params['cover_extension'],
+                                           params['kmer_probe_map_k'])
+    pid, gen, s, e = ctx.cover_export(cover)
+    group.free()
+    quads = np.stack([pid, gen.astype(np.int64), s, e], axis=1) if len(pid) else np.zeros((0, 4), np.int64)
+    return quads, cover, st
+
+
+@pytest.mark.parametrize('case', range(24))
+def test_coverage_and_setcover_match_oracle(ctx, case):
+    O = _oracle()
+    alphabet = 'ACGT' if case % 4 else 'ACGTRYKMSW'
+    groups, cands, params = helpers.random_case(case, alphabet=alphabet)
+    for probe_strs, genomes in zip(cands, groups):
+        if not probe_strs:
+            continue
+        seed = 1000 + case
+        np.random.seed(seed)
+        k, seeds, _ = O.choose_seeds(probe_strs, params['mismatches'], params['lcf_thres'],
+                                     min_k=params['kmer_probe_map_k'], k=params['kmer_probe_map_k'])
+        sm = O.SeedMap(probe_strs, seeds, k)
+        want = O.make_sets_quads(sm, genomes, params['mismatches'], params['lcf_thres'],
+                                 params['island_of_exact_match'], params['cover_extension'])
+        np.random.seed(seed)
+        got, cover, st = _device_quads(ctx, probe_strs, genomes, params)
+        assert got.shape == want.shape, (got.shape, want.shape)
+        assert np.array_equal(got, want)
+        # stage B on the same cover, both modes of the greedy kernel
+        cov_p = params['coverage']
+        if cov_p <= 1.0:
+            up = np.full(len(genomes), float(cov_p))
+        else:
+            up = np.array([float(min(cov_p, sum(map(len, g)))) / sum(map(len, g)) for g in genomes])
+        want_picks = O.set_cover_quads(want, len(probe_strs), len(genomes), None, up, None)
+        picks, st_b = ctx.setcover(cover, len(probe_strs), None, up)
+        assert picks.tolist() == want_picks
+        cover.free()
+
+
+@pytest.mark.parametrize('case', range(12))
+def test_filter_end_to_end_matches_oracle(ctx, case):
+    """SetCoverFilter.filter() vs the oracle's restatement of the reference filter, including
+    the order of the returned probes."""
+    O = _oracle()
+    from catch_b200 import probe
+    from catch_b200.filter.set_cover_filter import SetCoverFilter
+    groups, cands, params = helpers.random_case(100 + case)
+    genomes = helpers.to_genomes(groups)
+    probes = [[probe.Probe.from_str(s) for s in c] for c in cands]
+    f = SetCoverFilter(**params)
+    np.random.seed(7 + case)
+    random.seed(7 + case)
+    out = f.filter(probes, genomes, input_is_grouped=True)
+    np.random.seed(7 + case)
+    random.seed(7 + case)
+    want = O.set_cover_filter(cands, groups, params['mismatches'], params['lcf_thres'],
+                              params['island_of_exact_match'], params['coverage'],
+                              params['cover_extension'], params['kmer_probe_map_k'])
+    for g, (o, w) in enumerate(zip(out, want)):
+        ids = {id(p): i for i, p in enumerate(probes[g])}
+        assert [ids[id(p)] for p in o] == w
+
+
+def test_ranks_and_full_mode(ctx):
+    """Ranks (set_cover.py:349,491,522-526) and the p<1 clamp on a shared cover."""
+    O = _oracle()
+    rng = random.Random(5)
+    groups, cands, params = helpers.random_case(3)
+    probe_strs, genomes = cands[0], groups[0]
+    np.random.seed(11)
+    got, cover, _ = _device_quads(ctx, probe_strs, genomes, params)
+    for trial in range(6):
+        ranks = np.array([rng.choice([0, 0, 1, 5]) for _ in probe_strs], dtype=np.int32)
+        up = np.array([rng.choice([1.0, 0.9, 0.5, 0.1]) if trial % 2 else 1.0 for _ in genomes])
+        want = O.set_cover_quads(got, len(probe_strs), len(genomes), None, up, ranks)
+        picks, _ = ctx.setcover(cover, len(probe_strs), ranks, up)
+        assert picks.tolist() == want
+    cover.free()
+
+
+def test_empty_inputs(ctx):
+    from catch_b200 import probe
+    from catch_b200.filter.set_cover_filter import SetCoverFilter
+    f = SetCoverFilter(0, 20)
+    assert f.filter([[]], [[]], input_is_grouped=True) == [[]]
+    # a sequence shorter than k yields no coverage (probe.py:1204-1212)
+    g = helpers.to_genomes([[['ACGTACGTAC']]])
+    p = [[probe.Probe.from_str('ACGTACGTACGTACGTACGTACGTA')]]
+    assert f.filter(p, g, input_is_grouped=True) == [[]]
