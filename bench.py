@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""Benchmark of the SetCoverFilter hot path (BASELINE.json metric: candidate-probe x target-bp / s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload zika] [--impl reference]
+
+A step is one pass of the hot path (stage A coverage + stage B greedy set cover) over one batch
+of synthetic genomes.  Two numbers per run:
+  value : inputs already packed and resident in HBM when the timed region starts (device
+          timeline, CUDA events on the library's stream);
+  e2e   : the same metric through the plugin call a user makes, SetCoverFilter.filter(), with
+          host Probe/Genome objects; host packing, host->device copies, both stages and the
+          device->host read of the selection are all inside the timed region.
+The CPU oracle (oracle/) is executed only for `cpu_baseline` and `--impl reference`.
+"""
+import argparse
+import json
+import os
+import random
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from tests import helpers  # noqa: E402  (synthetic generators of SURVEY.md section 8d)
+
+RNG_SEED = 7
+
+WORKLOADS = {
+    # name: (n_genomes, genome_len, divergence, generator seed, probe_length, probe_stride, filter kwargs)
+    'plumbing': dict(n_genomes=20, length=5000, div=0.03, seed=1, pl=75, ps=50,
+                     scf=dict(mismatches=0, lcf_thres=75, cover_extension=0),
+                     desc='config 1: 20 x 5 kb, -pl 75 -m 0 -e 0'),
+    'zika': dict(n_genomes=500, length=11000, div=0.03, seed=2, pl=75, ps=50,
+                 scf=dict(mismatches=2, lcf_thres=60, cover_extension=50),
+                 desc='config 2 (Zika-scale): 500 x 11 kb, -pl 75 -m 2 -l 60 -e 50'),
+}
+
+
+def make_workload(name, n_genomes=None):
+    w = dict(WORKLOADS[name])
+    if n_genomes is not None:
+        w['n_genomes'] = n_genomes
+    seqs = helpers.synthetic_genomes(w['n_genomes'], w['length'], w['div'], w['seed'])
+    cands = helpers.tile_candidates(seqs, w['pl'], w['ps'])
+    cands = list(dict.fromkeys(cands))          # DuplicateFilter upstream of SetCoverFilter
+    w['seqs'] = seqs
+    w['cands'] = cands
+    w['pairs'] = len(cands) * sum(len(s) for s in seqs)
+    return w
+
+
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[4:8]):
+                if v.lower().startswith('active'):
+                    reasons.add(nm)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': mx,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+# ------------------------------------------------------------------------------------------
+def run_reference_arm(args, rank, world):
+    """`--impl reference`: the CPU restatement of the reference path (oracle port -- the reference
+    itself is Python and does not travel to the GPU box) on the host cores, bounded sample."""
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    w = make_workload(args.workload, n_genomes=args.cpu_sample_genomes)
+    threads = O.num_threads()
+    groups = [[[s] for s in w['seqs']]]
+
+    def step():
+        np.random.seed(RNG_SEED)
+        random.seed(RNG_SEED)
+        t0 = time.perf_counter()
+        O.set_cover_filter([w['cands']], groups, w['scf']['mismatches'], w['scf']['lcf_thres'], 0, 1.0,
+                           w['scf']['cover_extension'], 20, n_threads=threads)
+        return time.perf_counter() - t0
+
+    for _ in range(args.warmup):
+        step()
+    times = [step() for _ in range(args.steps)]
+    t = sum(times) / len(times)
+    v = w['pairs'] / t
+    sample = 'first %d genomes of %s (P=%d, T=%d bp)' % (w['n_genomes'], args.workload, len(w['cands']),
+                                                          sum(map(len, w['seqs'])))
+    print(json.dumps({
+        'impl': 'reference', 'metric': 'candidate-probe x target-bp / s through SetCoverFilter',
+        'value': v, 'unit': 'pairs/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': t * 1e3, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+        'dtype': 'u8', 'data': 'synthetic',
+        'config': {'workload': WORKLOADS[args.workload]['desc'], 'sample': sample},
+        'cpu_baseline': {'value': v, 'unit': 'pairs/s', 'cores': threads, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': v, 'unit': 'pairs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }))
+
+
+def cpu_baseline(args):
+    from oracle import oracle as O
+    w = make_workload(args.workload, n_genomes=args.cpu_sample_genomes)
+    threads = O.num_threads()
+    np.random.seed(RNG_SEED)
+    random.seed(RNG_SEED)
+    t0 = time.perf_counter()
+    O.set_cover_filter([w['cands']], [[[s] for s in w['seqs']]], w['scf']['mismatches'],
+                       w['scf']['lcf_thres'], 0, 1.0, w['scf']['cover_extension'], 20, n_threads=threads)
+    t = time.perf_counter() - t0
+    return {'value': w['pairs'] / t, 'unit': 'pairs/s', 'cores': threads, 'kind': 'port',
+            'sample': 'first %d genomes of %s (P=%d, T=%d bp), %.1f s; stage A on %d threads, stage B on 1 '
+                      '(as the reference: one process per grouping)' % (
+                          w['n_genomes'], args.workload, len(w['cands']), sum(map(len, w['seqs'])), t, threads)}
+
+
+# ------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--workload', default='zika', choices=sorted(WORKLOADS))
+    ap.add_argument('--cpu-sample-genomes', type=int, default=60)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'b200' and not os.environ.get('CB_BENCH_PROFILING'):
+        args.warmup = max(args.warmup, 3)      # timing rule: at least 3 warm-up steps
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+
+    if args.impl == 'reference':
+        run_reference_arm(args, rank, world)
+        return
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('gloo')      # plumbing only: barrier + max-over-ranks of the timings
+
+    from catch_b200 import _lib, probe
+    from catch_b200 import coverage as cov
+    from catch_b200.filter.set_cover_filter import SetCoverFilter
+
+    w = make_workload(args.workload)
+    ctx = _lib.Context(local_rank)
+    genomes = helpers.to_genomes([[[s] for s in w['seqs']]])
+    probes = [[probe.Probe.from_str(s) for s in w['cands']]]
+    scf = SetCoverFilter(**w['scf'])
+    scf._ctx = ctx
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    # ---- e2e: the plugin call with host objects
+    def e2e_step():
+        np.random.seed(RNG_SEED)
+        random.seed(RNG_SEED)
+        ctx.flush_l2()
+        t0 = time.perf_counter()
+        out = scf.filter(probes, genomes, input_is_grouped=True)
+        return time.perf_counter() - t0, out
+
+    # ---- resident: inputs packed in HBM before the timed region
+    group = cov.PackedGroup(ctx, w['cands'], genomes[0])
+
+    def resident_step():
+        np.random.seed(RNG_SEED)
+        ctx.flush_l2()
+        cover, st_a, k, mode = cov.compute_cover(ctx, group, w['cands'], w['scf']['mismatches'],
+                                                 w['scf']['lcf_thres'], 0, w['scf']['cover_extension'], 20)
+        picks, st_b = ctx.setcover(cover, len(w['cands']), None, None)
+        cover.free()
+        return st_a, st_b, picks
+
+    for _ in range(args.warmup):
+        resident_step()
+        e2e_step()
+
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    res = [resident_step() for _ in range(args.steps)]
+    e2e = [e2e_step() for _ in range(args.steps)]
+    barrier()
+    clocks = sampler.stop()
+
+    ms_res = [a.ms_total + b.ms_total for a, b, _ in res]
+    t_res = float(np.mean(ms_res)) / 1e3
+    t_e2e = float(np.mean([t for t, _ in e2e]))
+    if dist is not None:
+        import torch
+        t = torch.tensor([t_res, t_e2e], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_res, t_e2e = t.tolist()
+    st_a, st_b, picks = res[-1]
+    launches = int(st_a.n_kernel_launches + st_b.n_kernel_launches)
+
+    # ---- roofline of the dominant kernel
+    kern = {
+        'scan_kernel (K3, count+emit)': (st_a.ms_scan_count + st_a.ms_scan_emit),
+        'greedy_kernel (K6-K8)': st_b.ms_greedy,
+        'merge_kernel (K4)': st_a.ms_merge,
+        'seed_index (K2)': st_a.ms_seed_index,
+    }
+    dom = max(kern, key=kern.get)
+    P, T = len(w['cands']), sum(len(s) for s in w['seqs'])
+    E, S = int(st_a.n_intervals), int(st_b.n_picks)
+    bits = group.bits
+    if dom.startswith('scan'):
+        # per pass  T*bits/8 (target planes) + hits*8 (index entries) + hits*nw*bits*8 (probe words)
+        #            + raw*8 (emitted ranges, emit pass only); two passes
+        nw = (w['pl'] + 63) // 64
+        per_pass = T * bits / 8 + st_a.n_candidate_hits * (8 + nw * bits * 8)
+        alg_bytes = 2 * per_pass + st_a.n_raw_ranges * 8
+        dur = kern[dom] / 1e3
+    elif dom.startswith('greedy'):
+        # S*P*4 (gain vector per pick) + E*16 (index items touched at least once) + 2*U/8
+        alg_bytes = S * P * 4 + E * 16 + 2 * (T / 8)
+        dur = kern[dom] / 1e3
+    else:
+        alg_bytes = st_a.n_raw_ranges * 16
+        dur = kern[dom] / 1e3
+    peak, peak_src = measured_peak_gbs()
+    achieved = alg_bytes / dur / 1e9 if dur > 0 else 0.0
+    roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+                'kernel_ms': {k: round(v, 3) for k, v in kern.items()},
+                'note': 'latency/issue-bound integer path; see DESIGN.md'}
+
+    out = {
+        'metric': 'candidate-probe x target-bp / s through SetCoverFilter',
+        'value': w['pairs'] / t_res, 'unit': 'pairs/s', 'n_gpus': world, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': t_res * 1e3, 'higher_is_better': True,
+        'scaling': 'strong', 'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
+        'config': {'workload': w['desc'], 'P': P, 'T_bp': T, 'pairs': w['pairs'], 'intervals': E,
+                   'picks': S, 'l2': 'flushed between steps (256 MiB memset)',
+                   'parallelism': 'single GPU' if world == 1 else 'replicas'},
+        'e2e': {'value': w['pairs'] / t_e2e, 'unit': 'pairs/s', 'ms_per_step': t_e2e * 1e3,
+                'h2d_bytes_per_step': int(scf.last_stats[0]['h2d_bytes']),
+                'd2h_bytes_per_step': int(scf.last_stats[0]['d2h_bytes'])},
+        'gpu_launches': launches * args.steps * 2,
+        'clocks': clocks,
+        'roofline': roofline,
+        'stages_ms': {'coverage': st_a.as_dict(), 'setcover': st_b.as_dict()},
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            out['cpu_baseline'] = cpu_baseline(args)
+        print(json.dumps(out))
+    group.free()
+
+
+if __name__ == '__main__':
+    main()

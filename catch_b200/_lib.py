@@ -37,7 +37,7 @@ class Stats(C.Structure):
 
 # every symbol include/catch_b200.h declares
 EXPORTED_SYMBOLS = [
-    'cb_init', 'cb_destroy', 'cb_last_error', 'cb_version',
+    'cb_init', 'cb_destroy', 'cb_last_error', 'cb_version', 'cb_flush_l2',
     'cb_upload_targets', 'cb_targets_free', 'cb_upload_probes', 'cb_probes_free',
     'cb_coverage', 'cb_cover_free', 'cb_cover_num_intervals', 'cb_cover_export',
     'cb_setcover', 'cb_minhash_neardup', 'cb_hamming_neardup',
@@ -63,6 +63,7 @@ def load():
     L.cb_destroy.restype = None
     L.cb_last_error.argtypes = [vp]
     L.cb_last_error.restype = C.c_char_p
+    L.cb_flush_l2.argtypes = [vp]
     L.cb_upload_targets.argtypes = [vp, vp, vp, i64, vp, i32, vp, i32, C.POINTER(vp), C.POINTER(Stats)]
     L.cb_targets_free.argtypes = [vp]
     L.cb_targets_free.restype = None
@@ -116,6 +117,9 @@ class Context:
     def _check(self, rc):
         if rc != 0:
             raise CatchB200Error(rc, self.L.cb_last_error(self.h).decode())
+
+    def flush_l2(self):
+        self._check(self.L.cb_flush_l2(self.h))
 
     # ---- packing
     def upload_targets(self, ascii_u8, seq_off, seq_genome, n_genomes, lut, bits):

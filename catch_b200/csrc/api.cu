@@ -48,11 +48,23 @@ int cb_init(int device_id, cb_ctx **out)
 void cb_destroy(cb_ctx *ctx)
 {
     if (!ctx) return;
+    if (ctx->flush_buf) cudaFree(ctx->flush_buf);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 
 const char *cb_last_error(cb_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int cb_flush_l2(cb_ctx *ctx)
+{
+    if (!ctx) return CB_ERR_ARG;
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t bytes = 256ull << 20;
+    if (!ctx->flush_buf) CB_CUDA(ctx, cudaMalloc(&ctx->flush_buf, bytes));
+    CB_CUDA(ctx, cudaMemsetAsync(ctx->flush_buf, (int)(++ctx->flush_val & 0xff), bytes, ctx->stream));
+    CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return CB_OK;
+}
 
 int cb_upload_targets(cb_ctx *ctx, const uint8_t *ascii, const int64_t *seq_off, int64_t n_seqs,
                       const int32_t *seq_genome, int32_t n_genomes, const uint8_t lut[256], int32_t bits,

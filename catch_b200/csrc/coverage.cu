@@ -4,15 +4,29 @@
 //   probe.py:356-504,684-763   seed-map construction  -> seed_index_* kernels (bucketed hash CSR)
 //   probe.py:1008-1119         _find_probe_covers_in_subsequence -> scan_kernel
 //   utils/longest_common_substring.py:59-159 k_lcf_around_anchor -> anchored_extend (bit scans)
-//   probe.py:1328-1344         lcf() predicate -> inside process_hit
+//   probe.py:1328-1344         lcf() predicate -> inside run_owner_task
 //   utils/interval.py:288-316  merge_overlapping, filter/set_cover_filter.py:429-439,462-466
 //                              -> emitted ranges are extended/clipped/offset at emit time and
 //                                 merged per probe by merge_kernel
 //
 // Semantics kept bit for bit: a (probe, diagonal) pair is examined iff one of the probe's
 // SELECTED seeds matches the target exactly at an in-bounds position; every matching seed gives
-// its own anchored range; ranges are unioned.  One thread owns a (probe, diagonal): the thread
-// that arrived through the smallest matching seed; it walks the remaining seeds of the probe.
+// its own anchored range; ranges are unioned.
+//
+// How the scan is organised (one CTA per tile of CB_TILE target positions, persistent grid):
+//   1. the tile's bit planes (+ halo) are staged into shared memory by the TMA engine
+//      (cp.async.bulk + mbarrier);
+//   2. one seed-index lookup per target position gives a bucket of candidate (probe, seed) hits;
+//      a block-wide prefix sum spreads the hits evenly over the threads;
+//   3. per hit: mismatch mask M of the whole alignment = OR over planes of (probe XOR window);
+//      the set of selected seeds of that probe that match exactly and in bounds on this diagonal
+//      is A = runs_of_k_zeros(M) & seed_mask(probe), computed with log2(k) shift-AND steps.
+//      The hit that came through the LOWEST bit of A owns the diagonal; all others stop here;
+//   4. owners are compacted into a shared-memory queue and processed densely (no divergence
+//      between owners and non-owners): for every seed of A that starts a new mismatch-free run
+//      (seeds in one run give identical ranges) the anchored extension is evaluated with
+//      ffs/clz on the mask, and the resulting range is appended, warp-aggregated, to a global
+//      list that is later bucketed by probe.
 #include <cstring>
 
 #include "internal.cuh"
@@ -22,6 +36,10 @@ namespace {
 constexpr int SCAN_THREADS = 256;
 constexpr int POS_PER_THREAD = CB_TILE / SCAN_THREADS;
 constexpr int TW = CB_TILE_WORDS;
+constexpr int HITS_PER_THREAD = 4;
+constexpr int QUEUE_CAP = 2048;
+constexpr int QUEUE_FLUSH = QUEUE_CAP - SCAN_THREADS * HITS_PER_THREAD;
+constexpr int MAX_LOCAL_REC = 4;
 
 struct ScanParams {
     // targets
@@ -32,28 +50,28 @@ struct ScanParams {
     int64_t n_seqs;
     const int64_t *seq_start;
     const uint32_t *seq_ubase;
-    // probes
-    const uint64_t *pwords;
+    // probes: record = bits*NW plane words followed by NW words of seed mask
+    const uint64_t *precs;
+    int prec_words;
     const int32_t *plen;
-    // seeds (CSR, ascending within a probe)
-    const uint32_t *seed_off;
-    const uint8_t *seed_pos;
     // seed index
     const int64_t *bucket_off;
     const uint64_t *entries;
     uint32_t bucket_mask;
     // hybridisation model
     int m, lcf, island, ext, k;
-    // output
-    uint32_t *rec_count;          // count pass: ranges per probe
-    const int64_t *rec_off;       // emit pass
-    uint32_t *rec_cursor;
-    uint64_t *rec;
+    // output: global range list (probe, start, end, -) + per-probe counts
+    uint4 *rec;
+    unsigned long long rec_cap;
+    unsigned long long *rec_cursor;
+    uint32_t *rec_count;
     // scheduling / stats
     int64_t n_tiles;
     unsigned long long *tile_counter;
     unsigned long long *stat_hits;
     unsigned long long *stat_lookups;
+    unsigned long long *stat_owners;
+    int count_only;               // 1: only count candidate hits (capacity pre-pass)
 };
 
 // ---------------------------------------------------------------------------------------
@@ -103,6 +121,57 @@ __device__ __forceinline__ void clear_bit(uint64_t (&M)[NW], int b)
 #pragma unroll
     for (int w = 0; w < NW; w++)
         if ((b >> 6) == w) M[w] &= ~(1ull << (b & 63));
+}
+
+template <int NW>
+__device__ __forceinline__ bool test_bit(const uint64_t (&M)[NW], int b)
+{
+    uint64_t v = 0;
+#pragma unroll
+    for (int w = 0; w < NW; w++)
+        if ((b >> 6) == w) v = M[w];
+    return (v >> (b & 63)) & 1ull;
+}
+
+// R = X >> n over NW words (bit j of R = bit j+n of X), 0 <= n < 64*NW
+template <int NW>
+__device__ __forceinline__ void shr_multi(const uint64_t (&X)[NW], int n, uint64_t (&R)[NW])
+{
+    const int ws = n >> 6, bs = n & 63;
+#pragma unroll
+    for (int w = 0; w < NW; w++) {
+        uint64_t lo = 0, hi = 0;
+#pragma unroll
+        for (int v = 0; v < NW; v++) {
+            if (v == w + ws) lo = X[v];
+            if (v == w + ws + 1) hi = X[v];
+        }
+        R[w] = bs ? ((lo >> bs) | (hi << (64 - bs))) : lo;
+    }
+}
+
+// C[s] = 1 iff Z[s .. s+k) are all ones (runs of k ones), by doubling: log2(k) shift-AND steps
+template <int NW>
+__device__ __forceinline__ void runs_of_k(const uint64_t (&Z)[NW], int k, uint64_t (&C)[NW])
+{
+    uint64_t D[NW], T[NW];
+#pragma unroll
+    for (int w = 0; w < NW; w++) { D[w] = Z[w]; C[w] = ~0ull; }
+    int off = 0;
+    for (int len = 1; len <= k; len <<= 1) {
+        // D = runs of `len` ones
+        if (k & len) {
+            shr_multi<NW>(D, off, T);
+#pragma unroll
+            for (int w = 0; w < NW; w++) C[w] &= T[w];
+            off += len;
+        }
+        if ((len << 1) <= k) {
+            shr_multi<NW>(D, len, T);
+#pragma unroll
+            for (int w = 0; w < NW; w++) D[w] &= T[w];
+        }
+    }
 }
 
 __device__ __forceinline__ uint64_t mix64(uint64_t h, uint64_t v)
@@ -156,21 +225,35 @@ __device__ __forceinline__ uint64_t kmer_hash(int bits, int k, Reader rd)
 // ---------------------------------------------------------------------------------------
 // K2: seed index.  Entry = probe << 32 | pos << 24 | tag24.
 // ---------------------------------------------------------------------------------------
-__global__ void seed_expand_kernel(const uint32_t *__restrict__ seed_off, int64_t n_probes,
-                                   uint32_t *__restrict__ entry_probe)
+// one warp per probe: expands the seed CSR into per-entry probe ids and builds the probe's
+// seed mask (the last NW words of its record)
+__global__ void seed_expand_kernel(const uint32_t *__restrict__ seed_off, const uint8_t *__restrict__ seed_pos,
+                                   int64_t n_probes, uint32_t *__restrict__ entry_probe,
+                                   uint64_t *__restrict__ precs, int prec_words, int nw)
 {
-    // one warp per probe writes the probe id of each of its seed entries
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t p = warp; p < n_probes; p += n_warps)
-        for (uint32_t e = seed_off[p] + lane; e < seed_off[p + 1]; e += 32) entry_probe[e] = (uint32_t)p;
+    for (int64_t p = warp; p < n_probes; p += n_warps) {
+        uint64_t mask[4] = {0, 0, 0, 0};
+        for (uint32_t e = seed_off[p] + lane; e < seed_off[p + 1]; e += 32) {
+            entry_probe[e] = (uint32_t)p;
+            const int s = seed_pos[e];
+            mask[s >> 6] |= 1ull << (s & 63);
+        }
+#pragma unroll
+        for (int w = 0; w < 4; w++) {
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) mask[w] |= __shfl_xor_sync(0xffffffffu, mask[w], o);
+        }
+        if (lane < nw) precs[p * (int64_t)prec_words + (prec_words - nw) + lane] = mask[lane];
+    }
 }
 
 template <bool SCATTER>
 __global__ void seed_index_kernel(const uint32_t *__restrict__ entry_probe,
                                   const uint8_t *__restrict__ seed_pos, int64_t n_entries,
-                                  const uint64_t *__restrict__ pwords, int bits, int nw, int k,
+                                  const uint64_t *__restrict__ precs, int prec_words, int bits, int nw, int k,
                                   uint32_t bucket_mask, uint32_t *__restrict__ bucket_count,
                                   const int64_t *__restrict__ bucket_off, uint32_t *__restrict__ cursor,
                                   uint64_t *__restrict__ entries)
@@ -179,7 +262,7 @@ __global__ void seed_index_kernel(const uint32_t *__restrict__ entry_probe,
          e += (int64_t)gridDim.x * blockDim.x) {
         const uint32_t p = entry_probe[e];
         const int pos = seed_pos[e];
-        const uint64_t *pw = pwords + (int64_t)p * bits * nw;
+        const uint64_t *pw = precs + (int64_t)p * prec_words;
         const uint64_t h = kmer_hash(bits, k, [&](int b, int o) { return read64_bounded(pw + b * nw, nw, pos + o); });
         const uint32_t bucket = (uint32_t)h & bucket_mask;
         if (!SCATTER) {
@@ -189,6 +272,18 @@ __global__ void seed_index_kernel(const uint32_t *__restrict__ entry_probe,
             entries[bucket_off[bucket] + slot] =
                 ((uint64_t)p << 32) | ((uint64_t)pos << 24) | (uint64_t)(h >> 40);
         }
+    }
+}
+
+// copies the packed probe planes into the records (seed mask is filled by seed_expand_kernel)
+__global__ void build_precs_kernel(const uint64_t *__restrict__ pwords, int64_t n_probes, int plane_words,
+                                   int prec_words, uint64_t *__restrict__ precs)
+{
+    const int64_t n = n_probes * plane_words;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = i / plane_words;
+        const int w = (int)(i % plane_words);
+        precs[p * prec_words + w] = pwords[i];
     }
 }
 
@@ -229,7 +324,7 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
 
 // utils/longest_common_substring.py:59-159 on bit masks.  M: mismatch mask of the alignment,
 // valid for probe positions [a, b); anchor [s, s+k) is mismatch free.  Returns the length and
-// writes the start (probe coordinate); bef0/aft0 give the exact-match extents for the island test.
+// writes the start (probe coordinate); exact_len is the 0-mismatch extent for the island test.
 template <int NW>
 __device__ __forceinline__ int anchored_extend(const uint64_t (&M)[NW], int a, int b, int s, int k, int m,
                                                int &start, int &exact_len)
@@ -246,13 +341,13 @@ __device__ __forceinline__ int anchored_extend(const uint64_t (&M)[NW], int a, i
     const int after_full = b - (s + k);
     int n_right = 0;
     for (int j = 0; j <= m; j++) {
-        const int pos = lowest_set(MR);
+        const int pos = lowest_set<NW>(MR);
         if (pos < 0) break;
         const uint64_t v = (uint64_t)(pos - (s + k));
 #pragma unroll
         for (int q = 0; q < 4; q++)
             if ((j >> 3) == q) aft[q] |= v << ((j & 7) * 8);
-        clear_bit(MR, pos);
+        clear_bit<NW>(MR, pos);
         n_right++;
     }
     auto after = [&](int j) -> int {
@@ -267,68 +362,81 @@ __device__ __forceinline__ int anchored_extend(const uint64_t (&M)[NW], int a, i
     int bef0 = 0;
     for (int i = 0; i <= m; i++) {
         // before[i]: distance to the (i+1)-th mismatch on the left, else everything to `a` (:140-146)
-        const int hp = highest_set(ML);
+        const int hp = highest_set<NW>(ML);
         const int bef = hp >= 0 ? (s - 1 - hp) : (s - a);
         if (i == 0) bef0 = bef;
         const int tot = bef + k + after(m - i);
         if (tot > best_len) { best_len = tot; best_start = s - bef; }     // strict '>' (:154)
         if (hp < 0) break;       // further i: same `before`, `after` can only shrink
-        clear_bit(ML, hp);
+        clear_bit<NW>(ML, hp);
     }
     start = best_start;
     exact_len = bef0 + k + after(0);
     return best_len;
 }
 
-template <int NW, bool EMIT>
-__device__ __forceinline__ void process_hit(const ScanParams &P, const uint64_t *s_tile, int64_t t0, int64_t g,
-                                            int64_t qs, int64_t qe, uint32_t q_ubase, uint32_t p, int pos)
+// Mismatch mask of probe p aligned at target coordinate d, clipped to the sequence [qs, qe),
+// and the mask A of its selected seeds that match exactly and in bounds on this diagonal.
+template <int NW>
+__device__ __forceinline__ void align_probe(const ScanParams &P, const uint64_t *s_tile, int64_t t0, int64_t d,
+                                            int64_t qs, int64_t qe, uint32_t p, int L, uint64_t (&M)[NW],
+                                            uint64_t (&A)[NW], int &a, int &bnd)
 {
-    const int L = P.plen[p];
-    const int k = P.k;
-    const int64_t d = g - pos;                       // target coordinate of probe position 0
     const int off = (int)(d - t0) + CB_FRONT_PAD;    // bit offset in the staged tile
-    uint64_t M[NW];
+    const uint64_t *pw = P.precs + (int64_t)p * P.prec_words;
 #pragma unroll
     for (int w = 0; w < NW; w++) M[w] = 0ull;
-    const uint64_t *pw = P.pwords + (int64_t)p * P.bits * NW;
     for (int b = 0; b < P.bits; b++) {
 #pragma unroll
         for (int w = 0; w < NW; w++) M[w] |= __ldg(pw + b * NW + w) ^ read64(s_tile + b * TW, off + 64 * w);
     }
     // probe.py:1075-1094: the alignment is clipped to the sequence on both sides
-    const int a = (int)max((int64_t)0, qs - d);
-    const int bnd = (int)min((int64_t)L, qe - d);
-    if (any_in_range<NW>(M, pos, pos + k)) return;   // bucket/tag collision: k-mer differs
+    a = (int)max((int64_t)0, qs - d);
+    bnd = (int)min((int64_t)L, qe - d);
+    uint64_t Z[NW];
+#pragma unroll
+    for (int w = 0; w < NW; w++) Z[w] = ~M[w] & range_word(a, bnd, w);
+    runs_of_k<NW>(Z, P.k, A);
+#pragma unroll
+    for (int w = 0; w < NW; w++) A[w] &= __ldg(pw + P.bits * NW + w);
+}
 
-    // ownership: the smallest in-bounds, exactly matching seed of this probe on this diagonal
-    uint32_t e = P.seed_off[p];
-    const uint32_t se = P.seed_off[p + 1];
-    for (; e < se; e++) {
-        const int s = P.seed_pos[e];
-        if (s >= pos) break;
-        if (s >= a && s + k <= bnd && !any_in_range<NW>(M, s, s + k)) return;
-    }
+struct OutRec { uint32_t s, e; };
+
+// Owner of a (probe, diagonal): evaluate the anchored extension for every matching seed that
+// starts a new mismatch-free run; returns the number of ranges written to `out`.
+template <int NW>
+__device__ __forceinline__ int run_owner_task(const ScanParams &P, const uint64_t (&M)[NW], uint64_t (&A)[NW],
+                                              int a, int bnd, int L, int64_t d, int64_t qs, int64_t qe,
+                                              uint32_t q_ubase, uint32_t p, OutRec (&out)[MAX_LOCAL_REC])
+{
+    const int k = P.k;
     const int64_t qlen = qe - qs;
     int thres = P.lcf;                                // probe.py:1332
     if (L < thres) thres = L;
     if (qlen < (int64_t)thres) thres = (int)qlen;
-
     uint32_t cur_s = 0, cur_e = 0;
     bool have = false;
-    uint32_t n_out = 0;
+    int n_out = 0;
     auto flush = [&]() {
-        if (EMIT) {
-            const uint32_t slot = atomicAdd(&P.rec_cursor[p], 1u);
-            P.rec[P.rec_off[p] + slot] = ((uint64_t)cur_s << 32) | (uint64_t)cur_e;
-        } else {
-            n_out++;
+        if (n_out < MAX_LOCAL_REC) {
+            out[n_out].s = cur_s;
+            out[n_out].e = cur_e;
+        } else {                                      // rare: spill straight to the global list
+            const unsigned long long slot = atomicAdd(P.rec_cursor, 1ull);
+            if (slot < P.rec_cap) P.rec[slot] = make_uint4(p, cur_s, cur_e, 0u);
         }
+        n_out++;
     };
-    for (; e < se; e++) {
-        const int s = P.seed_pos[e];
-        if (!(s >= a && s + k <= bnd)) continue;
-        if (any_in_range<NW>(M, s, s + k)) continue;
+    int prev_s = -1;
+    for (;;) {
+        const int s = lowest_set<NW>(A);
+        if (s < 0) break;
+        clear_bit<NW>(A, s);
+        // seeds inside one mismatch-free run see the same mismatches on both sides and give the
+        // same range; only the first seed of a run is evaluated
+        if (prev_s >= 0 && !any_in_range<NW>(M, prev_s + k, s)) { prev_s = s; continue; }
+        prev_s = s;
         int start, exact_len;
         const int len = anchored_extend<NW>(M, a, bnd, s, k, P.m, start, exact_len);
         if (len < thres) continue;
@@ -355,10 +463,10 @@ __device__ __forceinline__ void process_hit(const ScanParams &P, const uint64_t 
         }
     }
     if (have) flush();
-    if (!EMIT && n_out) atomicAdd(&P.rec_count[p], n_out);
+    return n_out;
 }
 
-template <int NW, bool EMIT>
+template <int NW>
 __global__ void __launch_bounds__(SCAN_THREADS)
 scan_kernel(const ScanParams P)
 {
@@ -368,7 +476,9 @@ scan_kernel(const ScanParams P)
     __shared__ uint32_t s_cum[CB_TILE + 1];
     __shared__ uint32_t s_tag[CB_TILE];
     __shared__ uint32_t s_seq[CB_TILE];
+    __shared__ uint64_t s_queue[QUEUE_CAP];        // owner tasks: j << 40 | pos << 32 | probe
     __shared__ uint32_t s_warp[SCAN_THREADS / 32];
+    __shared__ uint32_t s_qcount;
     __shared__ long long s_tile_id;
     __shared__ long long s_qrange[2];
 
@@ -377,10 +487,11 @@ scan_kernel(const ScanParams P)
     if (tid == 0) {
         mbar_init(&s_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        s_qcount = 0;
     }
     __syncthreads();
     uint32_t phase = 0;
-    unsigned long long local_hits = 0, local_lookups = 0;
+    unsigned long long local_hits = 0, local_lookups = 0, local_owners = 0;
 
     for (;;) {
         if (tid == 0) s_tile_id = (long long)atomicAdd(P.tile_counter, 1ull);
@@ -469,26 +580,119 @@ scan_kernel(const ScanParams P)
         __syncthreads();
         const uint32_t total = s_cum[CB_TILE];
         local_hits += (tid == 0) ? total : 0;
+        if (P.count_only) continue;
 
-        // ---- phase 2: candidate hits, spread evenly over the block
-        for (uint32_t h = tid; h < total; h += SCAN_THREADS) {
-            int lo = 0, hi = CB_TILE;                // largest j with s_cum[j] <= h
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (s_cum[mid] <= h) lo = mid; else hi = mid;
+        // ---- phase 2: candidate hits in chunks; owners are queued, the queue is drained densely
+        for (uint32_t base = 0; base < total; base += SCAN_THREADS * HITS_PER_THREAD) {
+            const uint32_t h0 = base + tid * HITS_PER_THREAD;
+            // warp-uniform guard: the whole warp enters or skips, lanes past `total` are predicated
+            if (base + (uint32_t)(tid & ~31) * HITS_PER_THREAD < total) {
+                int j = 0;
+                if (h0 < total) {
+                    int lo = 0, hi = CB_TILE;            // largest j with s_cum[j] <= h0
+                    while (hi - lo > 1) {
+                        const int mid = (lo + hi) >> 1;
+                        if (s_cum[mid] <= h0) lo = mid; else hi = mid;
+                    }
+                    j = lo;
+                }
+#pragma unroll
+                for (int u = 0; u < HITS_PER_THREAD; u++) {
+                    const uint32_t h = h0 + u;
+                    bool owner = false;
+                    uint64_t task = 0;
+                    if (h < total) {
+                        while (s_cum[j + 1] <= h) j++;
+                        const uint64_t ent = __ldg(P.entries + (int64_t)s_begin_lo[j] + (h - s_cum[j]));
+                        if ((uint32_t)(ent & 0xffffffull) == s_tag[j]) {
+                            const uint32_t p = (uint32_t)(ent >> 32);
+                            const int pos = (int)((ent >> 24) & 0xff);
+                            const uint32_t q = s_seq[j];
+                            const int L = P.plen[p];
+                            uint64_t M[NW], A[NW];
+                            int a, bnd;
+                            align_probe<NW>(P, s_tile, t0, t0 + j - pos, P.seq_start[q], P.seq_start[q + 1], p, L,
+                                            M, A, a, bnd);
+                            // A has bit `pos` set unless the bucket/tag matched a different k-mer
+                            owner = lowest_set<NW>(A) == pos;
+                            task = ((uint64_t)j << 40) | ((uint64_t)pos << 32) | (uint64_t)p;
+                        }
+                    }
+                    __syncwarp();
+                    const unsigned owners = __ballot_sync(0xffffffffu, owner);
+                    if (owners) {                        // warp-aggregated push
+                        uint32_t qb = 0;
+                        if (lane == 0) qb = atomicAdd(&s_qcount, (uint32_t)__popc(owners));
+                        qb = __shfl_sync(0xffffffffu, qb, 0);
+                        if (owner) s_queue[qb + __popc(owners & ((1u << lane) - 1u))] = task;
+                    }
+                }
             }
-            const int j = lo;
-            const uint64_t ent = __ldg(P.entries + (int64_t)s_begin_lo[j] + (h - s_cum[j]));
-            if ((uint32_t)(ent & 0xffffffull) != s_tag[j]) continue;
-            const uint32_t q = s_seq[j];
-            process_hit<NW, EMIT>(P, s_tile, t0, t0 + j, P.seq_start[q], P.seq_start[q + 1], P.seq_ubase[q],
-                                  (uint32_t)(ent >> 32), (int)((ent >> 24) & 0xff));
+            __syncthreads();
+            const uint32_t qn = s_qcount;
+            const bool last = base + SCAN_THREADS * HITS_PER_THREAD >= total;
+            if (qn > (uint32_t)QUEUE_FLUSH || (last && qn > 0)) {
+                for (uint32_t tb = 0; tb < qn; tb += SCAN_THREADS) {
+                    const uint32_t ti = tb + tid;
+                    OutRec out[MAX_LOCAL_REC];
+                    int n_out = 0;
+                    uint32_t p = 0;
+                    if (ti < qn) {
+                        const uint64_t task = s_queue[ti];
+                        const int j = (int)(task >> 40);
+                        const int pos = (int)((task >> 32) & 0xff);
+                        p = (uint32_t)task;
+                        const uint32_t q = s_seq[j];
+                        const int64_t qs = P.seq_start[q], qe = P.seq_start[q + 1];
+                        const int L = P.plen[p];
+                        const int64_t d = t0 + j - pos;
+                        uint64_t M[NW], A[NW];
+                        int a, bnd;
+                        align_probe<NW>(P, s_tile, t0, d, qs, qe, p, L, M, A, a, bnd);
+                        n_out = run_owner_task<NW>(P, M, A, a, bnd, L, d, qs, qe, P.seq_ubase[q], p, out);
+                        if (n_out) atomicAdd(&P.rec_count[p], (uint32_t)n_out);
+                        local_owners++;
+                    }
+                    // warp-aggregated append of the (up to MAX_LOCAL_REC) ranges held in registers
+                    const int n_loc = n_out < MAX_LOCAL_REC ? n_out : MAX_LOCAL_REC;
+                    int incl = n_loc;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl += t;
+                    }
+                    const int wtotal = __shfl_sync(0xffffffffu, incl, 31);
+                    if (wtotal) {
+                        unsigned long long wb = 0;
+                        if (lane == 0) wb = atomicAdd(P.rec_cursor, (unsigned long long)wtotal);
+                        wb = __shfl_sync(0xffffffffu, wb, 0) + (unsigned long long)(incl - n_loc);
+#pragma unroll
+                        for (int r = 0; r < MAX_LOCAL_REC; r++)
+                            if (r < n_loc && wb + r < P.rec_cap) P.rec[wb + r] = make_uint4(p, out[r].s, out[r].e, 0u);
+                    }
+                }
+                __syncthreads();
+                if (tid == 0) s_qcount = 0;
+                __syncthreads();
+            }
         }
         __syncthreads();                              // tile + scan arrays are reused by the next tile
     }
-    if (!EMIT) {
-        if (local_hits) atomicAdd(P.stat_hits, local_hits);
-        if (local_lookups) atomicAdd(P.stat_lookups, local_lookups);
+    if (local_hits) atomicAdd(P.stat_hits, local_hits);
+    if (local_lookups) atomicAdd(P.stat_lookups, local_lookups);
+    if (local_owners) atomicAdd(P.stat_owners, local_owners);
+}
+
+// bucket the global range list by probe: rec_sorted[rec_off[p] + slot] = (start << 32 | end)
+__global__ void scatter_by_probe_kernel(const uint4 *__restrict__ rec, unsigned long long n,
+                                        const int64_t *__restrict__ rec_off, uint32_t *__restrict__ cursor,
+                                        uint64_t *__restrict__ rec_sorted)
+{
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint4 r = rec[i];
+        const uint32_t slot = atomicAdd(&cursor[r.x], 1u);
+        rec_sorted[rec_off[r.x] + slot] = ((uint64_t)r.y << 32) | (uint64_t)r.z;
     }
 }
 
@@ -624,22 +828,21 @@ __global__ void compact_kernel(const int64_t *__restrict__ rec_off, const uint64
 }
 
 template <int NW>
-int launch_scan(cb_ctx *ctx, const ScanParams &P, bool emit, int grid)
+int launch_scan(cb_ctx *ctx, const ScanParams &P, int grid)
 {
-    if (emit) scan_kernel<NW, true><<<grid, SCAN_THREADS, 0, ctx->stream>>>(P);
-    else scan_kernel<NW, false><<<grid, SCAN_THREADS, 0, ctx->stream>>>(P);
+    scan_kernel<NW><<<grid, SCAN_THREADS, 0, ctx->stream>>>(P);
     ctx->launches++;
     CB_CUDA(ctx, cudaGetLastError());
     return CB_OK;
 }
 
-int launch_scan_nw(cb_ctx *ctx, int nw, const ScanParams &P, bool emit, int grid)
+int launch_scan_nw(cb_ctx *ctx, int nw, const ScanParams &P, int grid)
 {
     switch (nw) {
-    case 1: return launch_scan<1>(ctx, P, emit, grid);
-    case 2: return launch_scan<2>(ctx, P, emit, grid);
-    case 3: return launch_scan<3>(ctx, P, emit, grid);
-    case 4: return launch_scan<4>(ctx, P, emit, grid);
+    case 1: return launch_scan<1>(ctx, P, grid);
+    case 2: return launch_scan<2>(ctx, P, grid);
+    case 3: return launch_scan<3>(ctx, P, grid);
+    case 4: return launch_scan<4>(ctx, P, grid);
     }
     return cb_fail(ctx, CB_ERR_UNSUPPORTED, "probe longer than CB_MAX_PROBE_LEN");
 }
@@ -677,20 +880,17 @@ int cb_coverage_impl(cb_ctx *ctx, const cb_probes *probes, const cb_targets *tar
     CB_CUDA(ctx, cudaMalloc((void **)&cov->d_iv_off, sizeof(int64_t) * (size_t)(P + 1)));
 
     const int64_t n_entries = P ? seed_off[P] : 0;
-    bool empty = (P == 0 || targets->total_bases == 0 || n_entries == 0);
-    if (!empty) {
-        // validate + narrow the seed CSR on the host
-        if (n_entries >= (int64_t)0xffffffffll) return cb_fail(ctx, CB_ERR_UNSUPPORTED, "too many seed entries");
-    }
+    const bool empty = (P == 0 || targets->total_bases == 0 || n_entries == 0);
     if (empty) {
         CB_CUDA(ctx, cudaMemsetAsync(cov->d_iv_off, 0, sizeof(int64_t) * (size_t)(P + 1), st));
         CB_CUDA(ctx, cudaStreamSynchronize(st));
-        if (stats) memset(stats, 0, sizeof *stats);
         guard.c = nullptr;
         *out = cov;
         return CB_OK;
     }
+    if (n_entries >= (int64_t)0xffffffffll) return cb_fail(ctx, CB_ERR_UNSUPPORTED, "too many seed entries");
 
+    // validate + narrow the seed CSR on the host
     std::vector<uint32_t> h_soff((size_t)P + 1);
     std::vector<uint8_t> h_spos((size_t)n_entries);
     for (int64_t p = 0; p <= P; p++) h_soff[(size_t)p] = (uint32_t)seed_off[p];
@@ -705,20 +905,23 @@ int cb_coverage_impl(cb_ctx *ctx, const cb_probes *probes, const cb_targets *tar
             prev = s;
         }
     }
+    const int nw = probes->nw, bits = probes->bits;
+    const int plane_words = bits * nw, prec_words = plane_words + nw;
     DevBuf<uint32_t> d_soff, d_eprobe, d_bcount, d_bcursor;
     DevBuf<uint8_t> d_spos;
     DevBuf<int64_t> d_boff;
-    DevBuf<uint64_t> d_entries;
-    DevBuf<unsigned long long> d_ctr;        // [0] tile counter, [1] hits, [2] lookups
+    DevBuf<uint64_t> d_entries, d_precs;
+    DevBuf<unsigned long long> d_ctr;        // [0] tile counter, [1] hits, [2] lookups, [3] owners, [4] range cursor
     CB_CUDA(ctx, d_soff.alloc((size_t)P + 1));
     CB_CUDA(ctx, d_spos.alloc((size_t)n_entries));
     CB_CUDA(ctx, d_eprobe.alloc((size_t)n_entries));
     CB_CUDA(ctx, d_entries.alloc((size_t)n_entries));
-    CB_CUDA(ctx, d_ctr.alloc(4));
+    CB_CUDA(ctx, d_precs.alloc((size_t)P * (size_t)prec_words));
+    CB_CUDA(ctx, d_ctr.alloc(8));
     CB_CUDA(ctx, cudaMemcpyAsync(d_soff.p, h_soff.data(), sizeof(uint32_t) * (size_t)(P + 1), cudaMemcpyHostToDevice, st));
     CB_CUDA(ctx, cudaMemcpyAsync(d_spos.p, h_spos.data(), (size_t)n_entries, cudaMemcpyHostToDevice, st));
 
-    // ---- K2 seed index
+    // ---- K2 seed index (+ probe records with their seed masks)
     t_idx.start();
     int64_t nb = 1024;
     while (nb < 2 * n_entries) nb <<= 1;
@@ -728,42 +931,38 @@ int cb_coverage_impl(cb_ctx *ctx, const cb_probes *probes, const cb_targets *tar
     CB_CUDA(ctx, cudaMemsetAsync(d_bcount.p, 0, sizeof(uint32_t) * (size_t)nb, st));
     CB_CUDA(ctx, cudaMemsetAsync(d_bcursor.p, 0, sizeof(uint32_t) * (size_t)nb, st));
     const int wide = ctx->sm_count * 8;
-    seed_expand_kernel<<<wide, 256, 0, st>>>(d_soff.p, P, d_eprobe.p);
-    seed_index_kernel<false><<<wide, 256, 0, st>>>(d_eprobe.p, d_spos.p, n_entries, probes->d_words, probes->bits,
-                                                   probes->nw, hp->k, (uint32_t)(nb - 1), d_bcount.p, nullptr,
-                                                   nullptr, nullptr);
-    ctx->launches += 2;
+    build_precs_kernel<<<wide, 256, 0, st>>>(probes->d_words, P, plane_words, prec_words, d_precs.p);
+    seed_expand_kernel<<<wide, 256, 0, st>>>(d_soff.p, d_spos.p, P, d_eprobe.p, d_precs.p, prec_words, nw);
+    seed_index_kernel<false><<<wide, 256, 0, st>>>(d_eprobe.p, d_spos.p, n_entries, d_precs.p, prec_words, bits, nw,
+                                                   hp->k, (uint32_t)(nb - 1), d_bcount.p, nullptr, nullptr, nullptr);
+    ctx->launches += 3;
     CB_CUDA(ctx, cudaGetLastError());
     CB_TRY(cb_exclusive_scan_u32_to_i64(ctx, d_bcount.p, d_boff.p, nb, nullptr));
-    seed_index_kernel<true><<<wide, 256, 0, st>>>(d_eprobe.p, d_spos.p, n_entries, probes->d_words, probes->bits,
-                                                  probes->nw, hp->k, (uint32_t)(nb - 1), nullptr, d_boff.p,
-                                                  d_bcursor.p, d_entries.p);
+    seed_index_kernel<true><<<wide, 256, 0, st>>>(d_eprobe.p, d_spos.p, n_entries, d_precs.p, prec_words, bits, nw,
+                                                  hp->k, (uint32_t)(nb - 1), nullptr, d_boff.p, d_bcursor.p,
+                                                  d_entries.p);
     ctx->launches++;
     CB_CUDA(ctx, cudaGetLastError());
     t_idx.stop();
 
-    // ---- K3 count pass
     DevBuf<uint32_t> d_rcount, d_rcursor;
     DevBuf<int64_t> d_roff;
     CB_CUDA(ctx, d_rcount.alloc((size_t)P));
     CB_CUDA(ctx, d_rcursor.alloc((size_t)P));
     CB_CUDA(ctx, d_roff.alloc((size_t)P + 1));
-    CB_CUDA(ctx, cudaMemsetAsync(d_rcount.p, 0, sizeof(uint32_t) * (size_t)P, st));
-    CB_CUDA(ctx, cudaMemsetAsync(d_rcursor.p, 0, sizeof(uint32_t) * (size_t)P, st));
-    CB_CUDA(ctx, cudaMemsetAsync(d_ctr.p, 0, sizeof(unsigned long long) * 4, st));
 
     ScanParams sp;
+    memset(&sp, 0, sizeof sp);
     sp.planes = targets->d_planes;
     sp.plane_words = targets->plane_words;
-    sp.bits = targets->bits;
+    sp.bits = bits;
     sp.total_bases = targets->total_bases;
     sp.n_seqs = targets->n_seqs;
     sp.seq_start = targets->d_seq_start;
     sp.seq_ubase = targets->d_seq_ubase;
-    sp.pwords = probes->d_words;
+    sp.precs = d_precs.p;
+    sp.prec_words = prec_words;
     sp.plen = probes->d_len;
-    sp.seed_off = d_soff.p;
-    sp.seed_pos = d_spos.p;
     sp.bucket_off = d_boff.p;
     sp.entries = d_entries.p;
     sp.bucket_mask = (uint32_t)(nb - 1);
@@ -773,57 +972,87 @@ int cb_coverage_impl(cb_ctx *ctx, const cb_probes *probes, const cb_targets *tar
     sp.ext = hp->cover_extension;
     sp.k = hp->k;
     sp.rec_count = d_rcount.p;
-    sp.rec_off = nullptr;
-    sp.rec_cursor = d_rcursor.p;
-    sp.rec = nullptr;
     sp.n_tiles = (targets->total_bases + CB_TILE - 1) / CB_TILE;
     sp.tile_counter = d_ctr.p;
     sp.stat_hits = d_ctr.p + 1;
     sp.stat_lookups = d_ctr.p + 2;
-    int64_t grid64 = sp.n_tiles < (int64_t)ctx->sm_count * 4 ? sp.n_tiles : (int64_t)ctx->sm_count * 4;
+    sp.stat_owners = d_ctr.p + 3;
+    sp.rec_cursor = d_ctr.p + 4;
+    int per_sm = 4;
+    if (const char *e = getenv("CB_SCAN_BLOCKS_PER_SM")) per_sm = atoi(e) > 0 ? atoi(e) : per_sm;
+    int64_t grid64 = sp.n_tiles < (int64_t)ctx->sm_count * per_sm ? sp.n_tiles : (int64_t)ctx->sm_count * per_sm;
     const int grid = (int)grid64;
 
+    // ---- K3 pre-pass: upper bound on the number of candidate hits (sizes the range list)
+    unsigned long long h_ctr[8];
     t_cnt.start();
-    CB_TRY(launch_scan_nw(ctx, probes->nw, sp, false, grid));
+    CB_CUDA(ctx, cudaMemsetAsync(d_ctr.p, 0, sizeof(unsigned long long) * 8, st));
+    sp.count_only = 1;
+    CB_TRY(launch_scan_nw(ctx, nw, sp, grid));
     t_cnt.stop();
-    int64_t n_raw = 0;
-    CB_TRY(cb_exclusive_scan_u32_to_i64(ctx, d_rcount.p, d_roff.p, P, &n_raw));
-    if (n_raw >= (int64_t)0x7fffffff00ll) return cb_fail(ctx, CB_ERR_UNSUPPORTED, "too many cover ranges");
+    CB_CUDA(ctx, cudaMemcpyAsync(h_ctr, d_ctr.p, sizeof h_ctr, cudaMemcpyDeviceToHost, st));
+    CB_CUDA(ctx, cudaStreamSynchronize(st));
+    const unsigned long long hits_ub = h_ctr[1];
+    // a diagonal is emitted once, by its lowest matching seed: expect about hits / seeds-per-probe
+    // ranges; start with twice that and fall back to the hard bound if it overflows
+    const double seeds_per_probe = (double)n_entries / (double)P;
+    unsigned long long cap = (unsigned long long)(2.0 * (double)hits_ub / (seeds_per_probe > 1.0 ? seeds_per_probe : 1.0)) + 4096;
+    if (cap > hits_ub + 4096) cap = hits_ub + 4096;
 
-    // ---- K3 emit pass
-    DevBuf<uint64_t> d_rec;
-    CB_CUDA(ctx, d_rec.alloc((size_t)n_raw));
-    CB_CUDA(ctx, cudaMemsetAsync(d_ctr.p, 0, sizeof(unsigned long long), st));    // tile counter only
-    sp.rec_off = d_roff.p;
-    sp.rec = d_rec.p;
+    // ---- K3 scan
+    DevBuf<uint4> d_rec;
+    unsigned long long n_raw = 0;
     t_emit.start();
-    CB_TRY(launch_scan_nw(ctx, probes->nw, sp, true, grid));
+    for (int attempt = 0; attempt < 2; attempt++) {
+        CB_CUDA(ctx, d_rec.alloc((size_t)cap));
+        CB_CUDA(ctx, cudaMemsetAsync(d_rcount.p, 0, sizeof(uint32_t) * (size_t)P, st));
+        CB_CUDA(ctx, cudaMemsetAsync(d_ctr.p, 0, sizeof(unsigned long long) * 8, st));
+        sp.count_only = 0;
+        sp.rec = d_rec.p;
+        sp.rec_cap = cap;
+        CB_TRY(launch_scan_nw(ctx, nw, sp, grid));
+        CB_CUDA(ctx, cudaMemcpyAsync(h_ctr, d_ctr.p, sizeof h_ctr, cudaMemcpyDeviceToHost, st));
+        CB_CUDA(ctx, cudaStreamSynchronize(st));
+        n_raw = h_ctr[4];
+        if (n_raw <= cap) break;
+        if (attempt == 1) return cb_fail(ctx, CB_ERR_STATE, "range list overflow after retry");
+        cap = hits_ub + 4096;
+    }
     t_emit.stop();
+    if (n_raw >= 0xfffffff0ull * 16ull) return cb_fail(ctx, CB_ERR_UNSUPPORTED, "too many cover ranges");
 
-    // ---- K4 merge
+    // ---- bucket by probe, K4 merge
+    t_merge.start();
+    int64_t n_raw_chk = 0;
+    CB_TRY(cb_exclusive_scan_u32_to_i64(ctx, d_rcount.p, d_roff.p, P, &n_raw_chk));
+    if ((unsigned long long)n_raw_chk != n_raw) return cb_fail(ctx, CB_ERR_STATE, "range count mismatch");
+    DevBuf<uint64_t> d_sorted;
     DevBuf<uint32_t> d_nmerged, d_maxlen;
+    CB_CUDA(ctx, d_sorted.alloc((size_t)n_raw));
     CB_CUDA(ctx, d_nmerged.alloc((size_t)P));
     CB_CUDA(ctx, d_maxlen.alloc(1));
+    CB_CUDA(ctx, cudaMemsetAsync(d_rcursor.p, 0, sizeof(uint32_t) * (size_t)P, st));
     CB_CUDA(ctx, cudaMemsetAsync(d_maxlen.p, 0, sizeof(uint32_t), st));
-    t_merge.start();
+    if (n_raw) {
+        scatter_by_probe_kernel<<<wide, 256, 0, st>>>(d_rec.p, n_raw, d_roff.p, d_rcursor.p, d_sorted.p);
+        ctx->launches++;
+    }
     {
         int64_t g = P < (int64_t)ctx->sm_count * 16 ? P : (int64_t)ctx->sm_count * 16;
-        merge_kernel<<<(unsigned)g, MERGE_THREADS, 0, st>>>(d_roff.p, d_rec.p, P, d_nmerged.p, d_maxlen.p);
+        merge_kernel<<<(unsigned)g, MERGE_THREADS, 0, st>>>(d_roff.p, d_sorted.p, P, d_nmerged.p, d_maxlen.p);
         ctx->launches++;
         CB_CUDA(ctx, cudaGetLastError());
     }
     int64_t n_iv = 0;
     CB_TRY(cb_exclusive_scan_u32_to_i64(ctx, d_nmerged.p, cov->d_iv_off, P, &n_iv));
     CB_CUDA(ctx, cudaMalloc((void **)&cov->d_iv, sizeof(uint2) * (size_t)(n_iv ? n_iv : 1)));
-    compact_kernel<<<wide, 256, 0, st>>>(d_roff.p, d_rec.p, cov->d_iv_off, P, cov->d_iv);
+    compact_kernel<<<wide, 256, 0, st>>>(d_roff.p, d_sorted.p, cov->d_iv_off, P, cov->d_iv);
     ctx->launches++;
     CB_CUDA(ctx, cudaGetLastError());
     t_merge.stop();
     t_all.stop();
     cov->n_intervals = n_iv;
 
-    unsigned long long h_ctr[4];
-    CB_CUDA(ctx, cudaMemcpyAsync(h_ctr, d_ctr.p, sizeof h_ctr, cudaMemcpyDeviceToHost, st));
     CB_CUDA(ctx, cudaMemcpyAsync(&cov->max_interval_len, d_maxlen.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CB_CUDA(ctx, cudaStreamSynchronize(st));
     if (stats) {
@@ -835,9 +1064,10 @@ int cb_coverage_impl(cb_ctx *ctx, const cb_probes *probes, const cb_targets *tar
         stats->n_seed_entries = n_entries;
         stats->n_seed_lookups = (int64_t)h_ctr[2];
         stats->n_candidate_hits = (int64_t)h_ctr[1];
-        stats->n_raw_ranges = n_raw;
+        stats->n_raw_ranges = (int64_t)n_raw;
         stats->n_intervals = n_iv;
         stats->n_kernel_launches = ctx->launches;
+        stats->reserved[0] = (int64_t)h_ctr[3];     // diagonals owned (anchored extensions run)
     }
     guard.c = nullptr;
     *out = cov;

@@ -34,6 +34,8 @@ struct cb_ctx {
     cudaStream_t stream = nullptr;
     std::string err;
     int64_t launches = 0;         // kernels launched since the counter was last reset
+    void *flush_buf = nullptr;    // cb_flush_l2 scratch
+    unsigned flush_val = 0;
 };
 
 struct cb_targets {

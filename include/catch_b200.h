@@ -81,6 +81,9 @@ void cb_destroy(cb_ctx *ctx);
 const char *cb_last_error(cb_ctx *ctx);
 /* Library build identification ("catch_b200 <version> sm_100a"). */
 const char *cb_version(void);
+/* Benchmark hygiene: overwrite a buffer larger than the L2 cache (256 MiB) so the next call
+ * starts with a cold L2. */
+int cb_flush_l2(cb_ctx *ctx);
 
 /* ---- packing (K1) ------------------------------------------------------------------
  * Replaces the per-hit str -> np.array('U1') conversions of probe.py:1074 and
