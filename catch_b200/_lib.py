@@ -32,14 +32,16 @@ class Stats(C.Structure):
                 ('bytes_algorithmic', C.c_int64), ('reserved', C.c_int64 * 8)]
 
     def as_dict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_ if n != 'reserved'}
+        d = {n: getattr(self, n) for n, _ in self._fields_ if n != 'reserved'}
+        d['reserved'] = list(self.reserved)
+        return d
 
 
 # every symbol include/catch_b200.h declares
 EXPORTED_SYMBOLS = [
     'cb_init', 'cb_destroy', 'cb_last_error', 'cb_version', 'cb_flush_l2',
     'cb_upload_targets', 'cb_targets_free', 'cb_upload_probes', 'cb_probes_free',
-    'cb_coverage', 'cb_cover_free', 'cb_cover_num_intervals', 'cb_cover_export',
+    'cb_coverage', 'cb_cover_free', 'cb_cover_num_intervals', 'cb_cover_export', 'cb_cover_import',
     'cb_setcover', 'cb_minhash_neardup', 'cb_hamming_neardup',
 ]
 
@@ -76,6 +78,7 @@ def load():
     L.cb_cover_num_intervals.argtypes = [vp]
     L.cb_cover_num_intervals.restype = i64
     L.cb_cover_export.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.cb_cover_import.argtypes = [vp, i64, i32, vp, i64, vp, vp, vp, vp, C.POINTER(vp)]
     L.cb_setcover.argtypes = [vp, vp, vp, vp, vp, C.POINTER(i64), C.POINTER(Stats)]
     L.cb_minhash_neardup.argtypes = [vp, vp, vp, i64, vp, vp, i32, i32, i32, C.c_double, vp, C.POINTER(Stats)]
     L.cb_hamming_neardup.argtypes = [vp, vp, vp, i64, vp, i32, i32, i32, vp, C.POINTER(Stats)]
@@ -152,6 +155,20 @@ class Context:
         end = np.zeros(n, dtype=np.int64)
         self._check(self.L.cb_cover_export(self.h, cover.h, _ptr(pid), _ptr(gen), _ptr(start), _ptr(end)))
         return pid, gen, start, end
+
+    def cover_import(self, n_probes, genome_len, probe_id, genome, start, end):
+        """Cover from host intervals (flat form of approx_multiuniverse's `sets`)."""
+        gl = np.ascontiguousarray(genome_len, dtype=np.int64)
+        pid = np.ascontiguousarray(probe_id, dtype=np.int64)
+        gen = np.ascontiguousarray(genome, dtype=np.int32)
+        s = np.ascontiguousarray(start, dtype=np.int64)
+        e = np.ascontiguousarray(end, dtype=np.int64)
+        out = C.c_void_p()
+        self._check(self.L.cb_cover_import(self.h, n_probes, len(gl), _ptr(gl) if len(gl) else None, len(pid),
+                                           _ptr(pid) if len(pid) else None, _ptr(gen) if len(pid) else None,
+                                           _ptr(s) if len(pid) else None, _ptr(e) if len(pid) else None,
+                                           C.byref(out)))
+        return Handle(self.L.cb_cover_free, out)
 
     # ---- stage B
     def setcover(self, cover, n_probes, ranks=None, universe_p=None):

@@ -12,25 +12,25 @@ def _concat_ascii(strs):
     off = np.zeros(n + 1, dtype=np.int64)
     if n:
         np.cumsum(np.fromiter((len(s) for s in strs), dtype=np.int64, count=n), out=off[1:])
-    buf = np.frombuffer(''.join(strs).encode('latin-1'), dtype=np.uint8)
-    if buf.size != off[-1]:
+    raw = ''.join(strs).encode('latin-1')
+    if len(raw) != off[-1]:
         raise ValueError("sequences must contain single-byte characters only")
-    if buf.size == 0:
-        buf = np.zeros(1, dtype=np.uint8)
-    return buf, off
+    buf = np.frombuffer(raw if raw else b'\0', dtype=np.uint8)
+    return buf, off, raw
 
 
-def make_alphabet(*byte_arrays):
+_ACGT = bytes(b'ACGT')
+
+
+def make_alphabet(*byte_buffers):
     """Code table for the bit-plane packing: distinct bytes -> dense codes.  Two bases match
     iff their bytes are equal (utils/longest_common_substring.py:110), so any injective code
     works; ACGT-only input gets 2 planes, ACGT+N 3, arbitrary test alphabets up to 8."""
-    present = np.zeros(256, dtype=bool)
-    for a in byte_arrays:
-        if a.size:
-            present |= np.bincount(a, minlength=256).astype(bool)
-    for c in b'ACGT':
-        present[c] = True
-    symbols = np.flatnonzero(present)
+    present = set(_ACGT)
+    for buf in byte_buffers:
+        # strip the four common bases at C speed; what is left (usually nothing) is small
+        present.update(bytes(buf).translate(None, _ACGT))
+    symbols = np.array(sorted(present), dtype=np.intp)
     lut = np.zeros(256, dtype=np.uint8)
     lut[symbols] = np.arange(len(symbols), dtype=np.uint8)
     bits = max(1, int(np.ceil(np.log2(len(symbols)))))
@@ -50,9 +50,9 @@ class PackedGroup:
                 seq_genome.append(j)
         self.n_genomes = len(genomes)
         self.target_bases = sum(len(s) for s in seqs)
-        p_buf, self.probe_off = _concat_ascii(probe_strs)
-        t_buf, seq_off = _concat_ascii(seqs)
-        lut, bits = make_alphabet(p_buf[:self.probe_off[-1]], t_buf[:seq_off[-1]])
+        p_buf, self.probe_off, p_raw = _concat_ascii(probe_strs)
+        t_buf, seq_off, t_raw = _concat_ascii(seqs)
+        lut, bits = make_alphabet(p_raw, t_raw)
         self.bits = bits
         sg = np.array(seq_genome if seq_genome else [0], dtype=np.int32)
         self.targets, self.st_targets = ctx.upload_targets(t_buf, seq_off, sg, self.n_genomes, lut, bits)
@@ -65,27 +65,23 @@ class PackedGroup:
 
 
 def seeds_to_csr(seeds, rep=None):
-    """[n, s] seed draws -> CSR of distinct ascending positions per probe.  `rep[i]` (optional)
-    redirects the draws of list index i to another index (duplicates collapse onto the last
-    occurrence, see SetCoverFilter._dedup_map)."""
+    """[n, s] seed draws -> CSR for cb_coverage (set semantics on the device, so repeats are
+    passed through untouched).  `rep[i]` (optional) redirects the draws of list index i to another
+    index: duplicates collapse onto their last occurrence, see dedup_map."""
     n = seeds.shape[0]
     if n == 0:
         return np.zeros(1, dtype=np.int64), np.zeros(1, dtype=np.int32)
     if rep is None:
-        srt = np.sort(seeds, axis=1)
-        keep = np.ones(srt.shape, dtype=bool)
-        keep[:, 1:] = srt[:, 1:] != srt[:, :-1]
-        counts = keep.sum(axis=1)
-        off = np.zeros(n + 1, dtype=np.int64)
-        np.cumsum(counts, out=off[1:])
-        pos = np.ascontiguousarray(srt[keep], dtype=np.int32)
+        s = seeds.shape[1]
+        off = np.arange(n + 1, dtype=np.int64) * s
+        pos = np.ascontiguousarray(seeds, dtype=np.int32).reshape(-1)
     else:
-        merged = [set() for _ in range(n)]
+        merged = [[] for _ in range(n)]
         for i in range(n):
-            merged[rep[i]].update(int(x) for x in seeds[i])
+            merged[rep[i]].extend(int(x) for x in seeds[i])
         off = np.zeros(n + 1, dtype=np.int64)
         off[1:] = np.cumsum([len(m) for m in merged])
-        pos = np.array([x for m in merged for x in sorted(m)], dtype=np.int32)
+        pos = np.array([x for m in merged for x in m], dtype=np.int32)
     if pos.size == 0:
         pos = np.zeros(1, dtype=np.int32)
     return off, pos
@@ -95,11 +91,11 @@ def dedup_map(probe_strs):
     """For every list index the LAST index holding the same sequence
     (filter/set_cover_filter.py:408-412: probe_id[p] = id overwrites earlier duplicates, and the
     k-mer map is keyed by sequence, probe.py:324-329).  Returns None when all are distinct."""
+    if len(set(probe_strs)) == len(probe_strs):
+        return None
     last = {}
     for i, s in enumerate(probe_strs):
         last[s] = i
-    if len(last) == len(probe_strs):
-        return None
     return [last[s] for s in probe_strs]
 
 
@@ -114,3 +110,16 @@ def compute_cover(ctx, group, probe_strs, mismatches, lcf_thres, island, cover_e
     cover, st = ctx.coverage(group.probes, group.targets, mismatches, lcf_thres, island,
                              cover_extension, k, seed_off, seed_pos)
     return cover, st, k, mode
+
+
+def cover_with_seeds(ctx, group, seeds_per_probe, k, mismatches, lcf_thres, island, cover_extension):
+    """Stage A with explicitly given seed positions (a list of position lists, one per probe):
+    the device counterpart of probe.find_probe_covers_in_sequence over a prebuilt
+    kmer_probe_map (probe.py:1122)."""
+    n = len(seeds_per_probe)
+    off = np.zeros(n + 1, dtype=np.int64)
+    off[1:] = np.cumsum([len(x) for x in seeds_per_probe])
+    flat = [int(x) for sl in seeds_per_probe for x in sl]
+    pos = np.array(flat if flat else [0], dtype=np.int32)
+    return ctx.coverage(group.probes, group.targets, mismatches, lcf_thres, island, cover_extension, k,
+                        off, pos)

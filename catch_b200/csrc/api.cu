@@ -279,6 +279,16 @@ int cb_cover_export(cb_ctx *ctx, const cb_cover *c, int64_t *probe_id, int32_t *
     return CB_OK;
 }
 
+int cb_cover_import(cb_ctx *ctx, int64_t n_probes, int32_t n_genomes, const int64_t *genome_len,
+                    int64_t n_intervals, const int64_t *probe_id, const int32_t *genome,
+                    const int64_t *start, const int64_t *end, cb_cover **out)
+{
+    if (!ctx) return CB_ERR_ARG;
+    ctx->launches = 0;
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    return cb_cover_import_impl(ctx, n_probes, n_genomes, genome_len, n_intervals, probe_id, genome, start, end, out);
+}
+
 int cb_setcover(cb_ctx *ctx, const cb_cover *cover, const int32_t *ranks, const double *universe_p,
                 int64_t *sel_ids, int64_t *n_sel, cb_stats *stats)
 {

@@ -225,28 +225,59 @@ __device__ __forceinline__ uint64_t kmer_hash(int bits, int k, Reader rd)
 // ---------------------------------------------------------------------------------------
 // K2: seed index.  Entry = probe << 32 | pos << 24 | tag24.
 // ---------------------------------------------------------------------------------------
-// one warp per probe: expands the seed CSR into per-entry probe ids and builds the probe's
-// seed mask (the last NW words of its record)
-__global__ void seed_expand_kernel(const uint32_t *__restrict__ seed_off, const uint8_t *__restrict__ seed_pos,
-                                   int64_t n_probes, uint32_t *__restrict__ entry_probe,
-                                   uint64_t *__restrict__ precs, int prec_words, int nw)
+// Seed positions arrive as a CSR that may hold repeats in any order (the reference draws with
+// replacement and keeps a set, probe.py:393-398).  One warp per probe ORs them into the probe's
+// seed mask (the last NW words of its record) and counts the distinct positions.
+__global__ void seed_mask_kernel(const int64_t *__restrict__ seed_off, const uint8_t *__restrict__ seed_pos,
+                                 const int32_t *__restrict__ plen, int k, int64_t n_probes,
+                                 uint64_t *__restrict__ precs, int prec_words, int nw,
+                                 uint32_t *__restrict__ n_distinct, int *__restrict__ bad)
 {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t p = warp; p < n_probes; p += n_warps) {
         uint64_t mask[4] = {0, 0, 0, 0};
-        for (uint32_t e = seed_off[p] + lane; e < seed_off[p + 1]; e += 32) {
-            entry_probe[e] = (uint32_t)p;
+        const int limit = plen[p] - k;             // last admissible seed start
+        for (int64_t e = seed_off[p] + lane; e < seed_off[p + 1]; e += 32) {
             const int s = seed_pos[e];
-            mask[s >> 6] |= 1ull << (s & 63);
+            if (s > limit) { *bad = 1; continue; }
+#pragma unroll
+            for (int w = 0; w < 4; w++)
+                if ((s >> 6) == w) mask[w] |= 1ull << (s & 63);
         }
+        uint32_t c = 0;
 #pragma unroll
         for (int w = 0; w < 4; w++) {
 #pragma unroll
             for (int o = 16; o >= 1; o >>= 1) mask[w] |= __shfl_xor_sync(0xffffffffu, mask[w], o);
+            c += __popcll(mask[w]);
         }
-        if (lane < nw) precs[p * (int64_t)prec_words + (prec_words - nw) + lane] = mask[lane];
+#pragma unroll
+        for (int w = 0; w < 4; w++)
+            if (lane == w && w < nw) precs[p * (int64_t)prec_words + (prec_words - nw) + w] = mask[w];
+        if (lane == 0) n_distinct[p] = c;
+    }
+}
+
+// one thread per probe lists its distinct seed positions (ascending) as index entries
+__global__ void seed_expand_kernel(const uint64_t *__restrict__ precs, int prec_words, int nw, int64_t n_probes,
+                                   const int64_t *__restrict__ entry_off, uint32_t *__restrict__ entry_probe,
+                                   uint8_t *__restrict__ entry_pos)
+{
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_probes;
+         p += (int64_t)gridDim.x * blockDim.x) {
+        int64_t o = entry_off[p];
+        for (int w = 0; w < nw; w++) {
+            uint64_t m = precs[p * (int64_t)prec_words + (prec_words - nw) + w];
+            while (m) {
+                const int b = __ffsll((long long)m) - 1;
+                m &= m - 1;
+                entry_probe[o] = (uint32_t)p;
+                entry_pos[o] = (uint8_t)(w * 64 + b);
+                o++;
+            }
+        }
     }
 }
 
@@ -879,8 +910,8 @@ int cb_coverage_impl(cb_ctx *ctx, const cb_probes *probes, const cb_targets *tar
                                  cudaMemcpyDeviceToDevice, st));
     CB_CUDA(ctx, cudaMalloc((void **)&cov->d_iv_off, sizeof(int64_t) * (size_t)(P + 1)));
 
-    const int64_t n_entries = P ? seed_off[P] : 0;
-    const bool empty = (P == 0 || targets->total_bases == 0 || n_entries == 0);
+    const int64_t n_raw_seeds = P ? seed_off[P] - seed_off[0] : 0;
+    const bool empty = (P == 0 || targets->total_bases == 0 || n_raw_seeds == 0);
     if (empty) {
         CB_CUDA(ctx, cudaMemsetAsync(cov->d_iv_off, 0, sizeof(int64_t) * (size_t)(P + 1), st));
         CB_CUDA(ctx, cudaStreamSynchronize(st));
@@ -888,41 +919,62 @@ int cb_coverage_impl(cb_ctx *ctx, const cb_probes *probes, const cb_targets *tar
         *out = cov;
         return CB_OK;
     }
-    if (n_entries >= (int64_t)0xffffffffll) return cb_fail(ctx, CB_ERR_UNSUPPORTED, "too many seed entries");
-
-    // validate + narrow the seed CSR on the host
-    std::vector<uint32_t> h_soff((size_t)P + 1);
-    std::vector<uint8_t> h_spos((size_t)n_entries);
-    for (int64_t p = 0; p <= P; p++) h_soff[(size_t)p] = (uint32_t)seed_off[p];
-    for (int64_t p = 0; p < P; p++) {
-        if (seed_off[p + 1] < seed_off[p]) return cb_fail(ctx, CB_ERR_ARG, "seed_off not monotone");
-        int prev = -1;
-        for (int64_t e = seed_off[p]; e < seed_off[p + 1]; e++) {
-            const int s = seed_pos[e];
-            if (s <= prev) return cb_fail(ctx, CB_ERR_ARG, "seed positions must be distinct and ascending per probe");
-            if (s < 0 || s > 255) return cb_fail(ctx, CB_ERR_ARG, "seed position out of range");
+    // narrow the seed positions to bytes (range-checked here, against the probe length on the device)
+    std::vector<uint8_t> h_spos((size_t)n_raw_seeds);
+    std::vector<int64_t> h_soff((size_t)P + 1);
+    for (int64_t p = 0; p <= P; p++) {
+        h_soff[(size_t)p] = seed_off[p] - seed_off[0];
+        if (p && seed_off[p] < seed_off[p - 1]) return cb_fail(ctx, CB_ERR_ARG, "seed_off not monotone");
+    }
+    {
+        const int32_t *sp0 = seed_pos + seed_off[0];
+        int bad = 0;
+        for (int64_t e = 0; e < n_raw_seeds; e++) {
+            const int32_t s = sp0[e];
+            bad |= (s < 0) | (s >= CB_MAX_PROBE_LEN);
             h_spos[(size_t)e] = (uint8_t)s;
-            prev = s;
         }
+        if (bad) return cb_fail(ctx, CB_ERR_ARG, "seed position out of range");
     }
     const int nw = probes->nw, bits = probes->bits;
     const int plane_words = bits * nw, prec_words = plane_words + nw;
-    DevBuf<uint32_t> d_soff, d_eprobe, d_bcount, d_bcursor;
-    DevBuf<uint8_t> d_spos;
-    DevBuf<int64_t> d_boff;
+    DevBuf<uint32_t> d_eprobe, d_bcount, d_bcursor, d_ndist;
+    DevBuf<uint8_t> d_spos, d_epos;
+    DevBuf<int64_t> d_boff, d_soff, d_eoff;
     DevBuf<uint64_t> d_entries, d_precs;
+    DevBuf<int> d_bad;
     DevBuf<unsigned long long> d_ctr;        // [0] tile counter, [1] hits, [2] lookups, [3] owners, [4] range cursor
     CB_CUDA(ctx, d_soff.alloc((size_t)P + 1));
-    CB_CUDA(ctx, d_spos.alloc((size_t)n_entries));
-    CB_CUDA(ctx, d_eprobe.alloc((size_t)n_entries));
-    CB_CUDA(ctx, d_entries.alloc((size_t)n_entries));
+    CB_CUDA(ctx, d_spos.alloc((size_t)n_raw_seeds));
+    CB_CUDA(ctx, d_ndist.alloc((size_t)P));
+    CB_CUDA(ctx, d_eoff.alloc((size_t)P + 1));
     CB_CUDA(ctx, d_precs.alloc((size_t)P * (size_t)prec_words));
+    CB_CUDA(ctx, d_bad.alloc(1));
     CB_CUDA(ctx, d_ctr.alloc(8));
-    CB_CUDA(ctx, cudaMemcpyAsync(d_soff.p, h_soff.data(), sizeof(uint32_t) * (size_t)(P + 1), cudaMemcpyHostToDevice, st));
-    CB_CUDA(ctx, cudaMemcpyAsync(d_spos.p, h_spos.data(), (size_t)n_entries, cudaMemcpyHostToDevice, st));
+    CB_CUDA(ctx, cudaMemsetAsync(d_bad.p, 0, sizeof(int), st));
+    CB_CUDA(ctx, cudaMemcpyAsync(d_soff.p, h_soff.data(), sizeof(int64_t) * (size_t)(P + 1), cudaMemcpyHostToDevice, st));
+    CB_CUDA(ctx, cudaMemcpyAsync(d_spos.p, h_spos.data(), (size_t)n_raw_seeds, cudaMemcpyHostToDevice, st));
 
     // ---- K2 seed index (+ probe records with their seed masks)
     t_idx.start();
+    const int wide = ctx->sm_count * 8;
+    build_precs_kernel<<<wide, 256, 0, st>>>(probes->d_words, P, plane_words, prec_words, d_precs.p);
+    seed_mask_kernel<<<wide, 256, 0, st>>>(d_soff.p, d_spos.p, probes->d_len, hp->k, P, d_precs.p, prec_words, nw,
+                                           d_ndist.p, d_bad.p);
+    ctx->launches += 2;
+    CB_CUDA(ctx, cudaGetLastError());
+    int64_t n_entries = 0;
+    CB_TRY(cb_exclusive_scan_u32_to_i64(ctx, d_ndist.p, d_eoff.p, P, &n_entries));
+    {
+        int h_bad = 0;
+        CB_CUDA(ctx, cudaMemcpyAsync(&h_bad, d_bad.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CB_CUDA(ctx, cudaStreamSynchronize(st));
+        if (h_bad) return cb_fail(ctx, CB_ERR_ARG, "seed position + k exceeds the probe length");
+    }
+    if (n_entries >= (int64_t)0xffffffffll) return cb_fail(ctx, CB_ERR_UNSUPPORTED, "too many seed entries");
+    CB_CUDA(ctx, d_eprobe.alloc((size_t)n_entries));
+    CB_CUDA(ctx, d_epos.alloc((size_t)n_entries));
+    CB_CUDA(ctx, d_entries.alloc((size_t)n_entries));
     int64_t nb = 1024;
     while (nb < 2 * n_entries) nb <<= 1;
     CB_CUDA(ctx, d_bcount.alloc((size_t)nb));
@@ -930,15 +982,13 @@ int cb_coverage_impl(cb_ctx *ctx, const cb_probes *probes, const cb_targets *tar
     CB_CUDA(ctx, d_boff.alloc((size_t)nb + 1));
     CB_CUDA(ctx, cudaMemsetAsync(d_bcount.p, 0, sizeof(uint32_t) * (size_t)nb, st));
     CB_CUDA(ctx, cudaMemsetAsync(d_bcursor.p, 0, sizeof(uint32_t) * (size_t)nb, st));
-    const int wide = ctx->sm_count * 8;
-    build_precs_kernel<<<wide, 256, 0, st>>>(probes->d_words, P, plane_words, prec_words, d_precs.p);
-    seed_expand_kernel<<<wide, 256, 0, st>>>(d_soff.p, d_spos.p, P, d_eprobe.p, d_precs.p, prec_words, nw);
-    seed_index_kernel<false><<<wide, 256, 0, st>>>(d_eprobe.p, d_spos.p, n_entries, d_precs.p, prec_words, bits, nw,
+    seed_expand_kernel<<<wide, 256, 0, st>>>(d_precs.p, prec_words, nw, P, d_eoff.p, d_eprobe.p, d_epos.p);
+    seed_index_kernel<false><<<wide, 256, 0, st>>>(d_eprobe.p, d_epos.p, n_entries, d_precs.p, prec_words, bits, nw,
                                                    hp->k, (uint32_t)(nb - 1), d_bcount.p, nullptr, nullptr, nullptr);
-    ctx->launches += 3;
+    ctx->launches += 2;
     CB_CUDA(ctx, cudaGetLastError());
     CB_TRY(cb_exclusive_scan_u32_to_i64(ctx, d_bcount.p, d_boff.p, nb, nullptr));
-    seed_index_kernel<true><<<wide, 256, 0, st>>>(d_eprobe.p, d_spos.p, n_entries, d_precs.p, prec_words, bits, nw,
+    seed_index_kernel<true><<<wide, 256, 0, st>>>(d_eprobe.p, d_epos.p, n_entries, d_precs.p, prec_words, bits, nw,
                                                   hp->k, (uint32_t)(nb - 1), nullptr, d_boff.p, d_bcursor.p,
                                                   d_entries.p);
     ctx->launches++;
@@ -1069,6 +1119,92 @@ int cb_coverage_impl(cb_ctx *ctx, const cb_probes *probes, const cb_targets *tar
         stats->n_kernel_launches = ctx->launches;
         stats->reserved[0] = (int64_t)h_ctr[3];     // diagonals owned (anchored extensions run)
     }
+    guard.c = nullptr;
+    *out = cov;
+    return CB_OK;
+}
+
+
+// Cover from host intervals: same bucket-by-probe + merge path as the scan output.
+int cb_cover_import_impl(cb_ctx *ctx, int64_t P, int32_t NG, const int64_t *genome_len, int64_t n,
+                         const int64_t *probe_id, const int32_t *genome, const int64_t *start,
+                         const int64_t *end, cb_cover **out)
+{
+    if (!out || P < 0 || NG < 0 || n < 0) return cb_fail(ctx, CB_ERR_ARG, "bad argument");
+    if (NG > 0 && !genome_len) return cb_fail(ctx, CB_ERR_ARG, "null genome_len");
+    if (n > 0 && (!probe_id || !genome || !start || !end)) return cb_fail(ctx, CB_ERR_ARG, "null interval array");
+    cudaStream_t st = ctx->stream;
+    cb_cover *cov = new cb_cover();
+    struct Guard { cb_cover *c; ~Guard() { if (c) cb_cover_free(c); } } guard{cov};
+    cov->ctx = ctx;
+    cov->n_probes = P;
+    cov->n_genomes = NG;
+    cov->h_ubase.resize((size_t)NG + 1);
+    cov->h_genome_len.assign(genome_len, genome_len + NG);
+    uint64_t ub = 0;
+    for (int32_t g = 0; g < NG; g++) {
+        if (genome_len[g] < 0) return cb_fail(ctx, CB_ERR_ARG, "negative genome length");
+        cov->h_ubase[(size_t)g] = (uint32_t)ub;
+        ub = (ub + (uint64_t)genome_len[g] + 1 + 63) & ~63ull;
+        if (ub >= 0xffffff00ull) return cb_fail(ctx, CB_ERR_UNSUPPORTED, "universe exceeds 2^32 bits");
+    }
+    cov->h_ubase[(size_t)NG] = (uint32_t)ub;
+    cov->universe_bits = (int64_t)ub;
+    std::vector<uint4> h_rec((size_t)n);
+    std::vector<uint32_t> h_count((size_t)P, 0u);
+    for (int64_t i = 0; i < n; i++) {
+        if (probe_id[i] < 0 || probe_id[i] >= P || genome[i] < 0 || genome[i] >= NG || start[i] < 0 ||
+            end[i] < start[i] || end[i] > genome_len[genome[i]])
+            return cb_fail(ctx, CB_ERR_ARG, "interval out of range");
+        const uint32_t b = cov->h_ubase[(size_t)genome[i]];
+        h_rec[(size_t)i] = make_uint4((uint32_t)probe_id[i], b + (uint32_t)start[i], b + (uint32_t)end[i], 0u);
+        if (end[i] > start[i]) h_count[(size_t)probe_id[i]]++;
+        else h_rec[(size_t)i].x = 0xffffffffu;            // empty interval: dropped
+    }
+    // compact away empty intervals on the host
+    size_t m = 0;
+    for (size_t i = 0; i < (size_t)n; i++) if (h_rec[i].x != 0xffffffffu) h_rec[m++] = h_rec[i];
+    CB_CUDA(ctx, cudaMalloc((void **)&cov->d_ubase, sizeof(uint32_t) * (size_t)(NG + 1)));
+    CB_CUDA(ctx, cudaMemcpyAsync(cov->d_ubase, cov->h_ubase.data(), sizeof(uint32_t) * (size_t)(NG + 1), cudaMemcpyHostToDevice, st));
+    CB_CUDA(ctx, cudaMalloc((void **)&cov->d_iv_off, sizeof(int64_t) * (size_t)(P + 1)));
+    if (P == 0 || m == 0) {
+        CB_CUDA(ctx, cudaMemsetAsync(cov->d_iv_off, 0, sizeof(int64_t) * (size_t)(P + 1), st));
+        CB_CUDA(ctx, cudaStreamSynchronize(st));
+        guard.c = nullptr;
+        *out = cov;
+        return CB_OK;
+    }
+    DevBuf<uint4> d_rec;
+    DevBuf<uint32_t> d_rcount, d_rcursor, d_nmerged, d_maxlen;
+    DevBuf<int64_t> d_roff;
+    DevBuf<uint64_t> d_sorted;
+    CB_CUDA(ctx, d_rec.alloc(m));
+    CB_CUDA(ctx, d_rcount.alloc((size_t)P));
+    CB_CUDA(ctx, d_rcursor.alloc((size_t)P));
+    CB_CUDA(ctx, d_roff.alloc((size_t)P + 1));
+    CB_CUDA(ctx, d_sorted.alloc(m));
+    CB_CUDA(ctx, d_nmerged.alloc((size_t)P));
+    CB_CUDA(ctx, d_maxlen.alloc(1));
+    CB_CUDA(ctx, cudaMemcpyAsync(d_rec.p, h_rec.data(), sizeof(uint4) * m, cudaMemcpyHostToDevice, st));
+    CB_CUDA(ctx, cudaMemcpyAsync(d_rcount.p, h_count.data(), sizeof(uint32_t) * (size_t)P, cudaMemcpyHostToDevice, st));
+    CB_CUDA(ctx, cudaMemsetAsync(d_rcursor.p, 0, sizeof(uint32_t) * (size_t)P, st));
+    CB_CUDA(ctx, cudaMemsetAsync(d_maxlen.p, 0, sizeof(uint32_t), st));
+    CB_TRY(cb_exclusive_scan_u32_to_i64(ctx, d_rcount.p, d_roff.p, P, nullptr));
+    const int wide = ctx->sm_count * 8;
+    scatter_by_probe_kernel<<<wide, 256, 0, st>>>(d_rec.p, (unsigned long long)m, d_roff.p, d_rcursor.p, d_sorted.p);
+    int64_t g = P < (int64_t)ctx->sm_count * 16 ? P : (int64_t)ctx->sm_count * 16;
+    merge_kernel<<<(unsigned)g, MERGE_THREADS, 0, st>>>(d_roff.p, d_sorted.p, P, d_nmerged.p, d_maxlen.p);
+    ctx->launches += 2;
+    CB_CUDA(ctx, cudaGetLastError());
+    int64_t n_iv = 0;
+    CB_TRY(cb_exclusive_scan_u32_to_i64(ctx, d_nmerged.p, cov->d_iv_off, P, &n_iv));
+    CB_CUDA(ctx, cudaMalloc((void **)&cov->d_iv, sizeof(uint2) * (size_t)(n_iv ? n_iv : 1)));
+    compact_kernel<<<wide, 256, 0, st>>>(d_roff.p, d_sorted.p, cov->d_iv_off, P, cov->d_iv);
+    ctx->launches++;
+    CB_CUDA(ctx, cudaGetLastError());
+    cov->n_intervals = n_iv;
+    CB_CUDA(ctx, cudaMemcpyAsync(&cov->max_interval_len, d_maxlen.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CB_CUDA(ctx, cudaStreamSynchronize(st));
     guard.c = nullptr;
     *out = cov;
     return CB_OK;

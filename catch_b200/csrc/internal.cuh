@@ -157,6 +157,10 @@ int cb_coverage_impl(cb_ctx *ctx, const cb_probes *probes, const cb_targets *tar
                      const cb_hyb_params *params, const int64_t *seed_off, const int32_t *seed_pos,
                      cb_cover **out, cb_stats *stats);
 
+int cb_cover_import_impl(cb_ctx *ctx, int64_t n_probes, int32_t n_genomes, const int64_t *genome_len,
+                         int64_t n_intervals, const int64_t *probe_id, const int32_t *genome,
+                         const int64_t *start, const int64_t *end, cb_cover **out);
+
 // setcover.cu
 int cb_setcover_impl(cb_ctx *ctx, const cb_cover *cover, const int32_t *ranks, const double *universe_p,
                      int64_t *sel_ids, int64_t *n_sel, cb_stats *stats);

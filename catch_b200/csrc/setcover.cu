@@ -18,15 +18,11 @@
 //     bits in the overlap; overlapping intervals are found through an index of intervals bucketed
 //     by start position (64-position blocks).
 //   full (some p_u < 1): gains are recomputed from U for every probe at every pick.
-#include <cooperative_groups.h>
-
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
 
 #include "internal.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace {
 
@@ -61,21 +57,9 @@ struct GreedyParams {
     long long *sel;                // [n_probes] picks in order
     long long *n_sel;
     int *status;
+    unsigned long long *barrier;   // grid barrier arrival counter
+    unsigned long long *phase_ns;  // [4] time CTA 0 spent in: argmax, barrier, delta, barrier
 };
-
-__device__ __forceinline__ uint32_t popcount_range(const unsigned long long *U, uint32_t s, uint32_t e)
-{
-    if (s >= e) return 0;
-    const uint32_t w0 = s >> 6, w1 = (e - 1) >> 6;
-    uint32_t c = 0;
-    for (uint32_t w = w0; w <= w1; w++) {
-        unsigned long long m = ~0ull;
-        if (w == w0) m &= ~0ull << (s & 63);
-        if (w == w1) m &= ~0ull >> (63 - ((e - 1) & 63));
-        c += __popcll(U[w] & m);
-    }
-    return c;
-}
 
 // ---- K5: universe = union of all intervals
 __global__ void universe_build_kernel(const uint2 *__restrict__ iv, int64_t n, unsigned long long *U)
@@ -147,6 +131,8 @@ __global__ void block_index_kernel(const int64_t *__restrict__ iv_off, const uin
     }
 }
 
+__device__ __forceinline__ uint32_t popcount_range_cg(const unsigned long long *U, uint32_t s, uint32_t e);
+
 // initial gains: sum over (probe, genome) of min(left_u, |s_u & U_u|)
 __device__ __forceinline__ void recompute_gains(const GreedyParams &G, int64_t gtid, int64_t gsize)
 {
@@ -159,10 +145,10 @@ __device__ __forceinline__ void recompute_gains(const GreedyParams &G, int64_t g
             long long c = 0;
             while (i < e && G.iv_genome[i] == u) {
                 const uint2 r = G.iv[i];
-                c += popcount_range(G.U, r.x, r.y);
+                c += popcount_range_cg(G.U, r.x, r.y);
                 i++;
             }
-            long long left = G.u_size[u] - G.uncoverable[u];
+            long long left = __ldcg(&G.u_size[u]) - G.uncoverable[u];
             if (left < 0) left = 0;
             total += (uint32_t)(c < left ? c : left);
         }
@@ -186,21 +172,65 @@ __global__ void gains_init_kernel(const int64_t *__restrict__ iv_off, const uint
     }
 }
 
+// ---- grid-wide barrier for the persistent kernel: monotone arrival counter, one arrival per
+// CTA, volatile polling (no fence inside the loop), one fence after.  Mutable global data is read with
+// __ldcg / atomics (L2), so no L1 invalidation is needed after the barrier.
+__device__ __forceinline__ void grid_barrier(unsigned long long *counter, unsigned long long &target)
+{
+    __syncthreads();
+    target += gridDim.x;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1ull);
+        while (*(volatile unsigned long long *)counter < target) { }
+        __threadfence();
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__device__ __forceinline__ uint32_t popcount_range_cg(const unsigned long long *U, uint32_t s, uint32_t e)
+{
+    if (s >= e) return 0;
+    const uint32_t w0 = s >> 6, w1 = (e - 1) >> 6;
+    uint32_t c = 0;
+    for (uint32_t w = w0; w <= w1; w++) {
+        unsigned long long m = ~0ull;
+        if (w == w0) m &= ~0ull << (s & 63);
+        if (w == w1) m &= ~0ull >> (63 - ((e - 1) & 63));
+        c += __popcll(__ldcg(U + w) & m);
+    }
+    return c;
+}
+
 // ---- the persistent greedy kernel
 __global__ void __launch_bounds__(GREEDY_THREADS)
 greedy_kernel(const GreedyParams G)
 {
-    cg::grid_group grid = cg::this_grid();
     __shared__ unsigned long long s_key[GREEDY_THREADS / 32];
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t gsize = (int64_t)gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t gwarp = gtid >> 5, n_gwarps = gsize >> 5;
 
     int cur_rank = 0;
     long long n_picks = 0;
     long long prev = -1;
-    const int nb_slots = (int)((2 * (int64_t)G.max_len) >> 6) + 2;
+    unsigned long long bar_target = 0;
+    unsigned long long t_phase[4] = {0, 0, 0, 0}, t_last = 0;
+    const bool timing = (gtid == 0);
+    if (timing) t_last = globaltimer_ns();
+    auto lap = [&](int i) {
+        if (timing) {
+            const unsigned long long t = globaltimer_ns();
+            t_phase[i] += t - t_last;
+            t_last = t;
+        }
+    };
 
     for (unsigned it = 0;; it++) {
         // ---- apply the previous pick: U -= s (K8), count what it newly covered
@@ -225,19 +255,19 @@ greedy_kernel(const GreedyParams G)
             }
         }
         if (G.full_mode) {
-            grid.sync();
+            grid_barrier(G.barrier, bar_target);
             if (gtid == 0) G.n_left[(it + 1) & 1] = 0;
             recompute_gains(G, gtid, gsize);
             unsigned cnt = 0;
             for (int64_t u = gtid; u < G.n_genomes; u += gsize)
-                if (G.u_size[u] - G.uncoverable[u] > 0) cnt++;
+                if (__ldcg(&G.u_size[u]) - G.uncoverable[u] > 0) cnt++;
             if (cnt) atomicAdd(&G.n_left[it & 1], cnt);
-            grid.sync();
+            grid_barrier(G.barrier, bar_target);
         }
         // ---- K7 argmax over the current rank: max gain, smallest id
         unsigned long long best = 0;
         for (int64_t p = gtid; p < G.n_probes; p += gsize) {
-            const uint32_t g = G.gain[p];
+            const uint32_t g = __ldcg(&G.gain[p]);
             if (g && G.rank_idx[p] == (uint32_t)cur_rank) {
                 const unsigned long long key = ((unsigned long long)g << 32) | (unsigned long long)(0xffffffffu - (uint32_t)p);
                 best = key > best ? key : best;
@@ -259,12 +289,14 @@ greedy_kernel(const GreedyParams G)
             }
             if (lane == 0 && best) atomicMax(&G.key[it & 1], best);
         }
-        grid.sync();
+        lap(0);
+        grid_barrier(G.barrier, bar_target);
+        lap(1);
 
         // ---- decide
-        const bool done = G.full_mode ? (G.n_left[it & 1] == 0) : (*G.remaining == 0ull);
+        const bool done = G.full_mode ? (__ldcg(&G.n_left[it & 1]) == 0) : (__ldcg(G.remaining) == 0ull);
         if (done) break;
-        const unsigned long long key = G.key[it & 1];
+        const unsigned long long key = __ldcg(&G.key[it & 1]);
         if (gtid == 0) G.key[(it + 1) & 1] = 0ull;
         if (key == 0ull) {                      // nothing in this rank covers anything needed (:522-526)
             cur_rank++;
@@ -273,7 +305,7 @@ greedy_kernel(const GreedyParams G)
                 if (gtid == 0) *G.status = CB_ERR_STATE;
                 break;
             }
-            grid.sync();
+            grid_barrier(G.barrier, bar_target);
             continue;
         }
         const long long w = (long long)(0xffffffffu - (uint32_t)(key & 0xffffffffull));
@@ -281,31 +313,93 @@ greedy_kernel(const GreedyParams G)
         n_picks++;
         prev = w;
 
-        // ---- K6 (incremental): take the winner's still-uncovered bits out of every overlapping interval
+        // ---- K6 (incremental): take the winner's still-uncovered bits out of every overlapping
+        // interval.  Intervals are indexed by the 64-position block of their start, blocks are
+        // consecutive in blk_items, so the candidates of one winner interval are ONE contiguous
+        // range of items; a CTA takes a winner interval, its threads stride over the range.
         if (!G.full_mode) {
             const int64_t i0 = G.iv_off[w], i1 = G.iv_off[w + 1];
-            const int64_t n_tasks = (i1 - i0) * nb_slots;
-            for (int64_t t = gwarp; t < n_tasks; t += n_gwarps) {
-                const uint2 r = G.iv[i0 + t / nb_slots];
-                const int slot = (int)(t % nb_slots);
+            for (int64_t i = i0 + blockIdx.x; i < i1; i += gridDim.x) {
+                uint2 r = G.iv[i];
+                // narrow the winner interval to the span of its still-uncovered bits; most late
+                // picks re-cover ground in most genomes and need no gain update there at all
+                {
+                    uint32_t first = 0xffffffffu, last = 0;
+                    if (r.x < r.y) {
+                        const uint32_t w0 = r.x >> 6, w1 = (r.y - 1) >> 6;
+                        for (uint32_t w = w0; w <= w1; w++) {
+                            unsigned long long m = ~0ull;
+                            if (w == w0) m &= ~0ull << (r.x & 63);
+                            if (w == w1) m &= ~0ull >> (63 - ((r.y - 1) & 63));
+                            const unsigned long long v = __ldcg(G.U + w) & m;
+                            if (v) {
+                                if (first == 0xffffffffu) first = (w << 6) + (uint32_t)__ffsll((long long)v) - 1u;
+                                last = (w << 6) + 63u - (uint32_t)__clzll((long long)v);
+                            }
+                        }
+                    }
+                    if (first == 0xffffffffu) continue;
+                    r.x = first;
+                    r.y = last + 1u;
+                }
                 const int64_t lo_pos = (int64_t)r.x - (int64_t)G.max_len + 1;
                 const int64_t b_lo = (lo_pos > 0 ? lo_pos : 0) >> 6;
-                const int64_t b_hi = ((int64_t)r.y - 1) >> 6;
-                const int64_t b = b_lo + slot;
-                if (b > b_hi || b >= G.n_blocks) continue;
-                for (int64_t x = G.blk_off[b] + lane; x < G.blk_off[b + 1]; x += 32) {
-                    const uint4 item = G.blk_items[x];
-                    const uint32_t os = max(item.x, r.x), oe = min(item.y, r.y);
-                    if (os < oe) {
-                        const uint32_t dlt = popcount_range(G.U, os, oe);
-                        if (dlt) atomicSub(&G.gain[item.z], dlt);
+                int64_t b_hi = ((int64_t)r.y - 1) >> 6;
+                if (b_hi >= G.n_blocks) b_hi = G.n_blocks - 1;
+                const int64_t x0 = G.blk_off[b_lo], x1 = G.blk_off[b_hi + 1];
+                // all item loads of a batch are issued before any is consumed (memory-level
+                // parallelism: the phase is a chain of dependent DRAM/L2 round trips otherwise)
+                constexpr int BATCH = 4;
+                for (int64_t xb = x0 + threadIdx.x; xb < x1; xb += (int64_t)GREEDY_THREADS * BATCH) {
+                    uint4 item[BATCH];
+#pragma unroll
+                    for (int u = 0; u < BATCH; u++) {
+                        const int64_t x = xb + (int64_t)u * GREEDY_THREADS;
+                        item[u] = x < x1 ? __ldg(G.blk_items + x) : make_uint4(0u, 0u, 0u, 0u);
+                    }
+                    uint32_t os[BATCH], oe[BATCH];
+                    unsigned long long w0v[BATCH], w1v[BATCH], w2v[BATCH];
+#pragma unroll
+                    for (int u = 0; u < BATCH; u++) {
+                        os[u] = max(item[u].x, r.x);
+                        oe[u] = min(item[u].y, r.y);
+                        w0v[u] = w1v[u] = w2v[u] = 0ull;
+                        if (os[u] < oe[u]) {
+                            // overlaps are at most max_len long; the common case spans <= 3 words
+                            const uint32_t wa = os[u] >> 6, wb = (oe[u] - 1) >> 6;
+                            w0v[u] = __ldcg(G.U + wa);
+                            if (wb > wa) w1v[u] = __ldcg(G.U + wa + 1);
+                            if (wb > wa + 1) w2v[u] = __ldcg(G.U + wa + 2);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < BATCH; u++) {
+                        if (os[u] < oe[u]) {
+                            const uint32_t wa = os[u] >> 6, wb = (oe[u] - 1) >> 6;
+                            uint32_t dlt;
+                            if (wb <= wa + 2) {
+                                const unsigned long long mlo = ~0ull << (os[u] & 63);
+                                const unsigned long long mhi = ~0ull >> (63 - ((oe[u] - 1) & 63));
+                                if (wb == wa) dlt = __popcll(w0v[u] & mlo & mhi);
+                                else if (wb == wa + 1) dlt = __popcll(w0v[u] & mlo) + __popcll(w1v[u] & mhi);
+                                else dlt = __popcll(w0v[u] & mlo) + __popcll(w1v[u]) + __popcll(w2v[u] & mhi);
+                            } else {
+                                dlt = popcount_range_cg(G.U, os[u], oe[u]);
+                            }
+                            if (dlt) atomicSub(&G.gain[item[u].z], dlt);
+                        }
                     }
                 }
             }
         }
-        grid.sync();
+        lap(2);
+        grid_barrier(G.barrier, bar_target);
+        lap(3);
     }
-    if (gtid == 0) *G.n_sel = n_picks;
+    if (gtid == 0) {
+        *G.n_sel = n_picks;
+        for (int i = 0; i < 4; i++) G.phase_ns[i] = t_phase[i];
+    }
 }
 
 }  // namespace
@@ -329,7 +423,7 @@ int cb_setcover_impl(cb_ctx *ctx, const cb_cover *cover, const int32_t *ranks, c
     const int wide = ctx->sm_count * 8;
     const int64_t u_words = cover->universe_bits >> 6;
 
-    DevBuf<unsigned long long> d_U, d_key, d_remaining;
+    DevBuf<unsigned long long> d_U, d_key, d_remaining, d_barrier;
     DevBuf<long long> d_usize, d_uncov, d_sel, d_nsel;
     DevBuf<uint32_t> d_gain, d_rank, d_ivg, d_bcount, d_bcursor;
     DevBuf<unsigned int> d_nleft;
@@ -390,6 +484,8 @@ int cb_setcover_impl(cb_ctx *ctx, const cb_cover *cover, const int32_t *ranks, c
     CB_CUDA(ctx, cudaMemsetAsync(d_nleft.p, 0, sizeof(unsigned int) * 2, st));
     CB_CUDA(ctx, d_status.alloc(1));
     CB_CUDA(ctx, cudaMemsetAsync(d_status.p, 0, sizeof(int), st));
+    CB_CUDA(ctx, d_barrier.alloc(8));
+    CB_CUDA(ctx, cudaMemsetAsync(d_barrier.p, 0, sizeof(unsigned long long) * 8, st));
 
     GreedyParams G;
     memset(&G, 0, sizeof G);
@@ -414,6 +510,8 @@ int cb_setcover_impl(cb_ctx *ctx, const cb_cover *cover, const int32_t *ranks, c
     G.sel = d_sel.p;
     G.n_sel = d_nsel.p;
     G.status = d_status.p;
+    G.barrier = d_barrier.p;
+    G.phase_ns = d_barrier.p + 1;
 
     if (full_mode) {
         CB_CUDA(ctx, d_ivg.alloc((size_t)E));
@@ -458,6 +556,8 @@ int cb_setcover_impl(cb_ctx *ctx, const cb_cover *cover, const int32_t *ranks, c
 
     long long h_nsel = 0;
     int h_status = 0;
+    unsigned long long h_phase[4] = {0, 0, 0, 0};
+    CB_CUDA(ctx, cudaMemcpyAsync(h_phase, d_barrier.p + 1, sizeof h_phase, cudaMemcpyDeviceToHost, st));
     CB_CUDA(ctx, cudaMemcpyAsync(&h_nsel, d_nsel.p, sizeof h_nsel, cudaMemcpyDeviceToHost, st));
     CB_CUDA(ctx, cudaMemcpyAsync(&h_status, d_status.p, sizeof h_status, cudaMemcpyDeviceToHost, st));
     CB_CUDA(ctx, cudaStreamSynchronize(st));
@@ -475,6 +575,7 @@ int cb_setcover_impl(cb_ctx *ctx, const cb_cover *cover, const int32_t *ranks, c
         stats->n_picks = h_nsel;
         stats->n_intervals = E;
         stats->n_kernel_launches = ctx->launches;
+        for (int i = 0; i < 4; i++) stats->reserved[i] = (int64_t)h_phase[i];   // ns: argmax, barrier, delta, barrier
     }
     return CB_OK;
 }

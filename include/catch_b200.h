@@ -112,9 +112,10 @@ void cb_probes_free(cb_probes *p);
  * predicate of probe.py:1328-1344, followed by the +-cover_extension / clip / genome-offset
  * step (:429-439) and interval.IntervalSet merging (:462-466).
  *
- * seed_off/seed_pos: CSR over probes of the DISTINCT seed start positions, ascending within
- * a probe.  The host generates them (pigeonhole rule or a replay of numpy's legacy RNG,
- * probe.py:356-504) because they depend on host RNG state. */
+ * seed_off/seed_pos: CSR over probes of the selected seed start positions.  Set semantics, as in
+ * the reference (probe.py:398): a position may repeat and the order is free; every position must
+ * satisfy pos + k <= len(probe).  The host generates them (pigeonhole rule or a replay of
+ * numpy's legacy RNG, probe.py:356-504) because they depend on host RNG state. */
 int cb_coverage(cb_ctx *ctx, const cb_probes *probes, const cb_targets *targets,
                 const cb_hyb_params *params, const int64_t *seed_off, const int32_t *seed_pos,
                 cb_cover **out, cb_stats *stats);
@@ -127,6 +128,15 @@ int64_t cb_cover_num_intervals(const cb_cover *c);
  * caller-allocated with cb_cover_num_intervals() entries. */
 int cb_cover_export(cb_ctx *ctx, const cb_cover *c, int64_t *probe_id, int32_t *genome,
                     int64_t *start, int64_t *end);
+
+/* Build a cover from host-side intervals instead of cb_coverage (the `sets` argument of
+ * set_cover.approx_multiuniverse, utils/set_cover.py:147, in flat form): interval i says probe
+ * probe_id[i] covers [start[i], end[i]) of genome genome[i].  Intervals may come in any order and
+ * may overlap; they are merged per (probe, genome) like interval.IntervalSet does.
+ * genome_len[g] bounds the coordinates of genome g. */
+int cb_cover_import(cb_ctx *ctx, int64_t n_probes, int32_t n_genomes, const int64_t *genome_len,
+                    int64_t n_intervals, const int64_t *probe_id, const int32_t *genome,
+                    const int64_t *start, const int64_t *end, cb_cover **out);
 
 /* ---- stage B: greedy multi-universe set cover (K5-K8) -------------------------------
  * Replaces set_cover.approx_multiuniverse(sets, costs=1, universe_p, ranks,

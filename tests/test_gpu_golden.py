@@ -1,0 +1,133 @@
+"""The CUDA path (through the C ABI) against golden vectors produced by the reference itself:
+the input/output pairs of the reference's own unit tests and seeded random cases
+(tests/golden/*.json.gz, written by tests/golden/make_golden.py).  Needs a B200."""
+import os
+import random
+import tempfile
+
+import numpy as np
+import pytest
+
+from tests import golden_io, helpers
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def ref_tests():
+    return golden_io.load('reference_tests.json.gz')
+
+
+@pytest.fixture(scope='module')
+def rnd_cases():
+    return golden_io.load('random_cases.json.gz')
+
+
+def test_find_probe_covers_in_sequence(ctx, ref_tests):
+    """tests/test_probe.py scans: toy A-Z alphabets, N, probes overhanging either end,
+    len(seq) < k, random planted probes -- exact (start, end) lists per probe."""
+    from catch_b200 import coverage as cov
+    n = 0
+    for r in ref_tests['scan']:
+        if not r['merge']:
+            continue          # merge_overlapping=False is only used by the adapter filter (out of scope)
+        group = cov.PackedGroup(ctx, r['probes'], [[r['seq']]])
+        cover, st = cov.cover_with_seeds(ctx, group, r['seeds'], r['k'], r['m'], r['lcf'], r['island'], 0)
+        pid, gen, s, e = ctx.cover_export(cover)
+        got = {}
+        for p, a, b in zip(pid.tolist(), s.tolist(), e.tolist()):
+            got.setdefault(r['probes'][p], []).append([a, b])
+        cover.free()
+        group.free()
+        assert got == r['out'], (r['probes'], r['seq'][:80])
+        n += 1
+    assert n >= 80
+
+
+def test_approx_multiuniverse(ctx, ref_tests):
+    """utils/tests/test_set_cover.py instances with unit costs (the only costs SetCoverFilter
+    ever passes, filter/set_cover_filter.py:759) through cb_cover_import + cb_setcover."""
+    n = 0
+    for r in ref_tests['setcover']:
+        quads, n_sets, n_u, costs, up, ranks, set_ids = golden_io.setcover_case_to_quads(r)
+        if costs is not None and any(c != 1 for c in costs):
+            continue
+        q = np.array(quads, dtype=np.int64).reshape(-1, 4)
+        glen = np.zeros(n_u, dtype=np.int64)
+        for u in range(n_u):
+            sel = q[q[:, 1] == u]
+            glen[u] = sel[:, 3].max() if len(sel) else 0
+        cover = ctx.cover_import(n_sets, glen, q[:, 0], q[:, 1], q[:, 2], q[:, 3])
+        picks, _ = ctx.setcover(cover, n_sets,
+                                None if ranks is None else np.array(ranks, dtype=np.int32),
+                                None if up is None else np.array(up, dtype=np.float64))
+        cover.free()
+        assert sorted(set_ids[p] for p in picks.tolist()) == r['out'], r
+        n += 1
+    assert n >= 15
+
+
+def _run_scf(ctx, r):
+    from catch_b200 import probe
+    from catch_b200.filter.set_cover_filter import SetCoverFilter
+    a = dict(r['args'])
+    tmp = []
+    try:
+        paths = []
+        for seqs in r.get('avoided', []):
+            f = tempfile.NamedTemporaryFile('w', suffix='.fasta', delete=False)
+            for i, s in enumerate(seqs):
+                f.write('>s%d\n%s\n' % (i, s))
+            f.close()
+            tmp.append(f.name)
+            paths.append(f.name)
+        filt = SetCoverFilter(avoided_genomes=paths, **a)
+        filt._ctx = ctx
+        probes = [[probe.Probe.from_str(s) for s in g] for g in r['probes']]
+        genomes = helpers.to_genomes(r['genomes'])
+        np.random.seed(r['seed'])
+        random.seed(r['seed'])
+        out = filt.filter(probes, genomes, input_is_grouped=True)
+        got = []
+        for gi, go in zip(probes, out):
+            ids = {id(p): i for i, p in enumerate(gi)}
+            got.append([ids[id(p)] for p in go])
+        return got
+    finally:
+        for t in tmp:
+            os.unlink(t)
+
+
+def test_set_cover_filter_reference_tests(ctx, ref_tests):
+    """filter/tests/test_set_cover_filter.py: every recorded SetCoverFilter.filter call (coverage
+    fraction / bp, cover_extension, identify, avoided genomes, empty input), selected probes in
+    the reference's output order."""
+    assert len(ref_tests['scf']) >= 100
+    for r in ref_tests['scf']:
+        assert _run_scf(ctx, r) == r['out'], r['args']
+
+
+def test_set_cover_filter_random(ctx, rnd_cases):
+    for r in rnd_cases['scf']:
+        assert _run_scf(ctx, r) == r['out'], r['args']
+
+
+def test_config1_fingerprint(ctx):
+    """BASELINE config 1 (20 x 5 kb, -pl 75 -m 0 -e 0): candidates -> DuplicateFilter ->
+    SetCoverFilter must give the reference's probe set (md5 of the sorted sequences)."""
+    import hashlib
+    from catch_b200 import probe
+    from catch_b200.filter.duplicate_filter import DuplicateFilter
+    from catch_b200.filter.set_cover_filter import SetCoverFilter
+    want = golden_io.load('config1.json.gz')
+    seqs = helpers.synthetic_genomes(20, 5000, 0.03, seed=1)
+    cands = [probe.Probe.from_str(s) for s in helpers.tile_candidates(seqs, 75, 50)]
+    assert len(cands) == want['n_candidates']
+    genomes = helpers.to_genomes([[[s] for s in seqs]])
+    probes = DuplicateFilter().filter([cands], genomes, input_is_grouped=True)
+    f = SetCoverFilter(mismatches=0, lcf_thres=75, cover_extension=0)
+    f._ctx = ctx
+    out = f.filter(probes, genomes, input_is_grouped=True)
+    final = list(set(p for g in out for p in g))
+    assert len(final) == want['n_final']
+    assert hashlib.md5('\n'.join(sorted(p.seq_str for p in final)).encode()).hexdigest() == want['md5_sorted']

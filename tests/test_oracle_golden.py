@@ -1,0 +1,117 @@
+"""The CPU oracle against golden vectors produced by the reference itself: the input/output pairs
+exercised by the reference's own unit tests (tests/golden/reference_tests.json.gz) and seeded
+random cases pushed through the reference (tests/golden/random_cases.json.gz).  CPU only."""
+import random
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests import golden_io
+
+
+@pytest.fixture(scope='module')
+def ref_tests():
+    return golden_io.load('reference_tests.json.gz')
+
+
+@pytest.fixture(scope='module')
+def rnd_cases():
+    return golden_io.load('random_cases.json.gz')
+
+
+def test_k_lcf_around_anchor_kats(ref_tests):
+    """utils/tests/test_longest_common_substring.py: the 25 (len, start) KATs."""
+    assert len(ref_tests['lcs']) >= 25
+    for r in ref_tests['lcs']:
+        assert list(O.k_lcf_around_anchor(r['a'], r['b'], r['s'], r['e'], r['k'])) == r['out'], r
+
+
+def test_lcf_predicate_kats(ref_tests):
+    """tests/test_probe.py:410-508 probe_covers_sequence_by_longest_common_substring KATs."""
+    assert len(ref_tests['lcf']) >= 10
+    for r in ref_tests['lcf']:
+        got = O.lcf_cover(r['p'], r['s'], r['ks'], r['ke'], r['fpl'], r['fsl'], r['m'], r['lcf'], r['island'])
+        assert (None if got is None else list(got)) == r['out'], r
+
+
+def test_find_probe_covers_in_sequence(ref_tests):
+    """tests/test_probe.py:519-941: every find_probe_covers_in_sequence call the tests make with
+    the default hybridisation model (A-Z alphabets, N, probes longer than the sequence, ...)."""
+    assert len(ref_tests['scan']) >= 100
+    for r in ref_tests['scan']:
+        sm = O.SeedMap(r['probes'], r['seeds'], r['k'])
+        got = O.find_probe_covers_in_sequence(sm, r['seq'], r['m'], r['lcf'], r['island'],
+                                              merge_overlapping=r['merge'])
+        got = {r['probes'][i]: [list(x) for x in v] for i, v in got.items()}
+        assert got == r['out']
+
+
+def test_approx_multiuniverse(ref_tests):
+    """utils/tests/test_set_cover.py: ranks, float costs, partial cover, multi-universe,
+    sets / arrays / interval sets (all expressed as intervals)."""
+    assert len(ref_tests['setcover']) >= 40
+    for r in ref_tests['setcover']:
+        quads, n_sets, n_u, costs, up, ranks, set_ids = golden_io.setcover_case_to_quads(r)
+        picks = O.set_cover_quads(np.array(quads, dtype=np.int64).reshape(-1, 4), n_sets, n_u, costs, up, ranks)
+        assert sorted(set_ids[p] for p in picks) == r['out'], r
+
+
+def _avoid_supported(r):
+    return not r['avoided'] and not r['args']['identify']
+
+
+def test_set_cover_filter_reference_tests(ref_tests):
+    """filter/tests/test_set_cover_filter.py: SetCoverFilter.filter inputs/outputs (cases without
+    identify / avoided genomes, which the oracle's filter wrapper does not model)."""
+    n = 0
+    for r in ref_tests['scf']:
+        if not _avoid_supported(r):
+            continue
+        a = r['args']
+        np.random.seed(r['seed'])
+        random.seed(r['seed'])
+        got = O.set_cover_filter(r['probes'], r['genomes'], a['mismatches'], a['lcf_thres'],
+                                 a['island_of_exact_match'], a['coverage'], a['cover_extension'],
+                                 a['kmer_probe_map_k'])
+        assert got == r['out'], a
+        n += 1
+    assert n >= 50
+
+
+def test_set_cover_filter_random(rnd_cases):
+    for r in rnd_cases['scf']:
+        a = r['args']
+        np.random.seed(r['seed'])
+        random.seed(r['seed'])
+        got = O.set_cover_filter(r['probes'], r['genomes'], a['mismatches'], a['lcf_thres'],
+                                 a['island_of_exact_match'], a['coverage'], a['cover_extension'],
+                                 a['kmer_probe_map_k'])
+        assert got == r['out']
+
+
+def _ndf(r):
+    random.seed(r['seed'])
+    if r['kind'] == 'minhash':
+        return O.near_duplicate_minhash(r['probes'], r['dist_thres'], r['kmer_size'], r['k'], r['reporting_prob'])
+    return O.near_duplicate_hamming(r['probes'], r['dist_thres'], r['dim'], r['k'], r['reporting_prob'])
+
+
+def test_near_duplicate_filter(ref_tests, rnd_cases):
+    """filter/tests/test_near_duplicate_filter.py inputs + random cases; fixtures were generated
+    under PYTHONHASHSEED=0, so the kept probes AND their order must match."""
+    for r in ref_tests['ndf'] + rnd_cases['ndf']:
+        got = _ndf(r)
+        # list(set_of_probes) order depends on the interpreter's str hash seed; compare as the
+        # reference would under PYTHONHASHSEED=0 when that is how this process runs, else as sets
+        import os
+        if os.environ.get('PYTHONHASHSEED') == '0':
+            assert got == r['out']
+        else:
+            assert sorted(got) == sorted(r['out'])
+
+
+def test_cpython_str_hash(rnd_cases):
+    """abs(hash(str)) under PYTHONHASHSEED=0 == SipHash-1-3, zero key (utils/lsh.py:103)."""
+    for s, h in rnd_cases['hash']:
+        assert O.abs_pyhash(s) == h
