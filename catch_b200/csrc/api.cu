@@ -15,6 +15,8 @@ static int upload_common_lut(cb_ctx *ctx, const uint8_t lut[256], int bits, DevB
     return CB_OK;
 }
 
+thread_local cudaStream_t cb_tls_stream = nullptr;
+
 extern "C" {
 
 const char *cb_version(void) { return "catch_b200 0.1 sm_100a"; }
@@ -36,6 +38,13 @@ int cb_init(int device_id, cb_ctx **out)
         return CB_ERR_CUDA;
     }
     ctx->sm_count = prop.multiProcessorCount;
+    {   // keep freed blocks in the stream-ordered pool instead of returning them to the driver
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device_id) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     if (prop.major < 10) {
         ctx->err = "cb_init: this library is built for sm_100a (Blackwell) only";
         *out = ctx;
@@ -59,6 +68,7 @@ int cb_flush_l2(cb_ctx *ctx)
 {
     if (!ctx) return CB_ERR_ARG;
     CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cb_tls_stream = ctx->stream;
     const size_t bytes = 256ull << 20;
     if (!ctx->flush_buf) CB_CUDA(ctx, cudaMalloc(&ctx->flush_buf, bytes));
     CB_CUDA(ctx, cudaMemsetAsync(ctx->flush_buf, (int)(++ctx->flush_val & 0xff), bytes, ctx->stream));
@@ -76,6 +86,7 @@ int cb_upload_targets(cb_ctx *ctx, const uint8_t *ascii, const int64_t *seq_off,
     if (stats) memset(stats, 0, sizeof *stats);
     ctx->launches = 0;
     CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cb_tls_stream = ctx->stream;
     cudaStream_t st = ctx->stream;
     const int64_t T = n_seqs ? seq_off[n_seqs] - seq_off[0] : 0;
     if (T > 0 && !ascii) return cb_fail(ctx, CB_ERR_ARG, "null ascii");
@@ -121,11 +132,11 @@ int cb_upload_targets(cb_ctx *ctx, const uint8_t *ascii, const int64_t *seq_off,
     t->plane_words = pw;
     EventTimer t_all(st), t_h2d(st), t_pack(st);
     t_all.start();
-    CB_CUDA(ctx, cudaMalloc((void **)&t->d_planes, sizeof(uint64_t) * (size_t)pw * (size_t)bits));
-    CB_CUDA(ctx, cudaMalloc((void **)&t->d_seq_start, sizeof(int64_t) * (size_t)(n_seqs + 1)));
-    CB_CUDA(ctx, cudaMalloc((void **)&t->d_seq_genome, sizeof(int32_t) * (size_t)(n_seqs + 1)));
-    CB_CUDA(ctx, cudaMalloc((void **)&t->d_seq_ubase, sizeof(uint32_t) * (size_t)(n_seqs + 1)));
-    CB_CUDA(ctx, cudaMalloc((void **)&t->d_ubase, sizeof(uint32_t) * (size_t)(n_genomes + 1)));
+    CB_CUDA(ctx, cb_dev_alloc(st, (void **)&t->d_planes, sizeof(uint64_t) * (size_t)pw * (size_t)bits));
+    CB_CUDA(ctx, cb_dev_alloc(st, (void **)&t->d_seq_start, sizeof(int64_t) * (size_t)(n_seqs + 1)));
+    CB_CUDA(ctx, cb_dev_alloc(st, (void **)&t->d_seq_genome, sizeof(int32_t) * (size_t)(n_seqs + 1)));
+    CB_CUDA(ctx, cb_dev_alloc(st, (void **)&t->d_seq_ubase, sizeof(uint32_t) * (size_t)(n_seqs + 1)));
+    CB_CUDA(ctx, cb_dev_alloc(st, (void **)&t->d_ubase, sizeof(uint32_t) * (size_t)(n_genomes + 1)));
     DevBuf<uint8_t> d_ascii, d_lut;
     CB_TRY(upload_common_lut(ctx, lut, bits, d_lut));
     CB_CUDA(ctx, d_ascii.alloc((size_t)T));
@@ -157,11 +168,12 @@ int cb_upload_targets(cb_ctx *ctx, const uint8_t *ascii, const int64_t *seq_off,
 void cb_targets_free(cb_targets *t)
 {
     if (!t) return;
-    cudaFree(t->d_planes);
-    cudaFree(t->d_seq_start);
-    cudaFree(t->d_seq_genome);
-    cudaFree(t->d_seq_ubase);
-    cudaFree(t->d_ubase);
+    cudaStream_t st = t->ctx->stream;
+    cb_dev_free(st, t->d_planes);
+    cb_dev_free(st, t->d_seq_start);
+    cb_dev_free(st, t->d_seq_genome);
+    cb_dev_free(st, t->d_seq_ubase);
+    cb_dev_free(st, t->d_ubase);
     delete t;
 }
 
@@ -175,6 +187,7 @@ int cb_upload_probes(cb_ctx *ctx, const uint8_t *ascii, const int64_t *probe_off
     if (stats) memset(stats, 0, sizeof *stats);
     ctx->launches = 0;
     CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cb_tls_stream = ctx->stream;
     cudaStream_t st = ctx->stream;
     int max_len = 0;
     for (int64_t i = 0; i < n_probes; i++) {
@@ -194,8 +207,8 @@ int cb_upload_probes(cb_ctx *ctx, const uint8_t *ascii, const int64_t *probe_off
     const int64_t total = n_probes ? probe_off[n_probes] - probe_off[0] : 0;
     EventTimer t_all(st), t_h2d(st), t_pack(st);
     t_all.start();
-    CB_CUDA(ctx, cudaMalloc((void **)&p->d_words, sizeof(uint64_t) * (size_t)(n_probes ? n_probes : 1) * (size_t)bits * (size_t)p->nw));
-    CB_CUDA(ctx, cudaMalloc((void **)&p->d_len, sizeof(int32_t) * (size_t)(n_probes ? n_probes : 1)));
+    CB_CUDA(ctx, cb_dev_alloc(st, (void **)&p->d_words, sizeof(uint64_t) * (size_t)(n_probes ? n_probes : 1) * (size_t)bits * (size_t)p->nw));
+    CB_CUDA(ctx, cb_dev_alloc(st, (void **)&p->d_len, sizeof(int32_t) * (size_t)(n_probes ? n_probes : 1)));
     DevBuf<uint8_t> d_ascii, d_lut;
     DevBuf<int64_t> d_off;
     CB_TRY(upload_common_lut(ctx, lut, bits, d_lut));
@@ -229,8 +242,8 @@ int cb_upload_probes(cb_ctx *ctx, const uint8_t *ascii, const int64_t *probe_off
 void cb_probes_free(cb_probes *p)
 {
     if (!p) return;
-    cudaFree(p->d_words);
-    cudaFree(p->d_len);
+    cb_dev_free(p->ctx->stream, p->d_words);
+    cb_dev_free(p->ctx->stream, p->d_len);
     delete p;
 }
 
@@ -241,15 +254,16 @@ int cb_coverage(cb_ctx *ctx, const cb_probes *probes, const cb_targets *targets,
     if (stats) memset(stats, 0, sizeof *stats);
     ctx->launches = 0;
     CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cb_tls_stream = ctx->stream;
     return cb_coverage_impl(ctx, probes, targets, params, seed_off, seed_pos, out, stats);
 }
 
 void cb_cover_free(cb_cover *c)
 {
     if (!c) return;
-    cudaFree(c->d_iv_off);
-    cudaFree(c->d_iv);
-    cudaFree(c->d_ubase);
+    cb_dev_free(c->ctx->stream, c->d_iv_off);
+    cb_dev_free(c->ctx->stream, c->d_iv);
+    cb_dev_free(c->ctx->stream, c->d_ubase);
     delete c;
 }
 
@@ -286,6 +300,7 @@ int cb_cover_import(cb_ctx *ctx, int64_t n_probes, int32_t n_genomes, const int6
     if (!ctx) return CB_ERR_ARG;
     ctx->launches = 0;
     CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cb_tls_stream = ctx->stream;
     return cb_cover_import_impl(ctx, n_probes, n_genomes, genome_len, n_intervals, probe_id, genome, start, end, out);
 }
 
@@ -296,6 +311,7 @@ int cb_setcover(cb_ctx *ctx, const cb_cover *cover, const int32_t *ranks, const 
     if (stats) memset(stats, 0, sizeof *stats);
     ctx->launches = 0;
     CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cb_tls_stream = ctx->stream;
     return cb_setcover_impl(ctx, cover, ranks, universe_p, sel_ids, n_sel, stats);
 }
 
@@ -307,6 +323,7 @@ int cb_minhash_neardup(cb_ctx *ctx, const uint8_t *ascii, const int64_t *probe_o
     if (stats) memset(stats, 0, sizeof *stats);
     ctx->launches = 0;
     CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cb_tls_stream = ctx->stream;
     return cb_minhash_neardup_impl(ctx, ascii, probe_off, n_probes, a, b, n_tables, k_concat, kmer_size,
                                    dist_thres, keep, stats);
 }
@@ -319,6 +336,7 @@ int cb_hamming_neardup(cb_ctx *ctx, const uint8_t *ascii, const int64_t *probe_o
     if (stats) memset(stats, 0, sizeof *stats);
     ctx->launches = 0;
     CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cb_tls_stream = ctx->stream;
     return cb_hamming_neardup_impl(ctx, ascii, probe_off, n_probes, positions, n_tables, k_concat,
                                    dist_thres, keep, stats);
 }

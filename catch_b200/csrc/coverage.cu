@@ -905,10 +905,10 @@ int cb_coverage_impl(cb_ctx *ctx, const cb_probes *probes, const cb_targets *tar
     cov->h_ubase = targets->h_ubase;
     cov->h_genome_len = targets->h_genome_len;
     struct Guard { cb_cover *c; ~Guard() { if (c) cb_cover_free(c); } } guard{cov};
-    CB_CUDA(ctx, cudaMalloc((void **)&cov->d_ubase, sizeof(uint32_t) * (size_t)(targets->n_genomes + 1)));
+    CB_CUDA(ctx, cb_dev_alloc(st, (void **)&cov->d_ubase, sizeof(uint32_t) * (size_t)(targets->n_genomes + 1)));
     CB_CUDA(ctx, cudaMemcpyAsync(cov->d_ubase, targets->d_ubase, sizeof(uint32_t) * (size_t)(targets->n_genomes + 1),
                                  cudaMemcpyDeviceToDevice, st));
-    CB_CUDA(ctx, cudaMalloc((void **)&cov->d_iv_off, sizeof(int64_t) * (size_t)(P + 1)));
+    CB_CUDA(ctx, cb_dev_alloc(st, (void **)&cov->d_iv_off, sizeof(int64_t) * (size_t)(P + 1)));
 
     const int64_t n_raw_seeds = P ? seed_off[P] - seed_off[0] : 0;
     const bool empty = (P == 0 || targets->total_bases == 0 || n_raw_seeds == 0);
@@ -1095,7 +1095,7 @@ int cb_coverage_impl(cb_ctx *ctx, const cb_probes *probes, const cb_targets *tar
     }
     int64_t n_iv = 0;
     CB_TRY(cb_exclusive_scan_u32_to_i64(ctx, d_nmerged.p, cov->d_iv_off, P, &n_iv));
-    CB_CUDA(ctx, cudaMalloc((void **)&cov->d_iv, sizeof(uint2) * (size_t)(n_iv ? n_iv : 1)));
+    CB_CUDA(ctx, cb_dev_alloc(st, (void **)&cov->d_iv, sizeof(uint2) * (size_t)(n_iv ? n_iv : 1)));
     compact_kernel<<<wide, 256, 0, st>>>(d_roff.p, d_sorted.p, cov->d_iv_off, P, cov->d_iv);
     ctx->launches++;
     CB_CUDA(ctx, cudaGetLastError());
@@ -1164,9 +1164,9 @@ int cb_cover_import_impl(cb_ctx *ctx, int64_t P, int32_t NG, const int64_t *geno
     // compact away empty intervals on the host
     size_t m = 0;
     for (size_t i = 0; i < (size_t)n; i++) if (h_rec[i].x != 0xffffffffu) h_rec[m++] = h_rec[i];
-    CB_CUDA(ctx, cudaMalloc((void **)&cov->d_ubase, sizeof(uint32_t) * (size_t)(NG + 1)));
+    CB_CUDA(ctx, cb_dev_alloc(st, (void **)&cov->d_ubase, sizeof(uint32_t) * (size_t)(NG + 1)));
     CB_CUDA(ctx, cudaMemcpyAsync(cov->d_ubase, cov->h_ubase.data(), sizeof(uint32_t) * (size_t)(NG + 1), cudaMemcpyHostToDevice, st));
-    CB_CUDA(ctx, cudaMalloc((void **)&cov->d_iv_off, sizeof(int64_t) * (size_t)(P + 1)));
+    CB_CUDA(ctx, cb_dev_alloc(st, (void **)&cov->d_iv_off, sizeof(int64_t) * (size_t)(P + 1)));
     if (P == 0 || m == 0) {
         CB_CUDA(ctx, cudaMemsetAsync(cov->d_iv_off, 0, sizeof(int64_t) * (size_t)(P + 1), st));
         CB_CUDA(ctx, cudaStreamSynchronize(st));
@@ -1198,7 +1198,7 @@ int cb_cover_import_impl(cb_ctx *ctx, int64_t P, int32_t NG, const int64_t *geno
     CB_CUDA(ctx, cudaGetLastError());
     int64_t n_iv = 0;
     CB_TRY(cb_exclusive_scan_u32_to_i64(ctx, d_nmerged.p, cov->d_iv_off, P, &n_iv));
-    CB_CUDA(ctx, cudaMalloc((void **)&cov->d_iv, sizeof(uint2) * (size_t)(n_iv ? n_iv : 1)));
+    CB_CUDA(ctx, cb_dev_alloc(st, (void **)&cov->d_iv, sizeof(uint2) * (size_t)(n_iv ? n_iv : 1)));
     compact_kernel<<<wide, 256, 0, st>>>(d_roff.p, d_sorted.p, cov->d_iv_off, P, cov->d_iv);
     ctx->launches++;
     CB_CUDA(ctx, cudaGetLastError());

@@ -109,7 +109,21 @@ static inline int cb_fail(cb_ctx *ctx, int code, const char *msg)
     return code;
 }
 
-// RAII device buffer tied to a stream-ordered context (plain cudaMalloc/cudaFree).
+// Device memory comes from CUDA's stream-ordered allocator (cudaMallocAsync on the context's
+// stream; the pool keeps freed blocks, see cb_init), so the many short-lived work buffers of a
+// call cost no cudaMalloc/cudaFree round trips and no implicit device synchronisation.
+extern thread_local cudaStream_t cb_tls_stream;     // stream of the context serving this thread's call
+
+static inline cudaError_t cb_dev_alloc(cudaStream_t st, void **p, size_t bytes)
+{
+    return cudaMallocAsync(p, bytes ? bytes : 1, st);
+}
+static inline void cb_dev_free(cudaStream_t st, void *p)
+{
+    if (p) cudaFreeAsync(p, st);
+}
+
+// RAII work buffer, freed in stream order when it goes out of scope.
 template <typename T>
 struct DevBuf {
     T *p = nullptr;
@@ -117,12 +131,13 @@ struct DevBuf {
     DevBuf() {}
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
-    ~DevBuf() { if (p) cudaFree(p); }
+    ~DevBuf() { cb_dev_free(cb_tls_stream, p); }
     cudaError_t alloc(size_t count)
     {
-        if (p) { cudaFree(p); p = nullptr; }
+        cb_dev_free(cb_tls_stream, p);
+        p = nullptr;
         n = count;
-        return cudaMalloc((void **)&p, (count ? count : 1) * sizeof(T));
+        return cb_dev_alloc(cb_tls_stream, (void **)&p, count * sizeof(T));
     }
     T *release() { T *q = p; p = nullptr; return q; }
 };
