@@ -41,16 +41,24 @@ WORKLOADS = {
 }
 
 
-def make_workload(name, n_genomes=None):
+def make_workload(name, n_genomes=None, n_groups=1):
+    """n_groups independent groupings of the named shape (generator seeds seed, seed+1, ...):
+    one grouping per GPU in the multi-GPU runs (weak scaling over independent set-cover instances,
+    the V-All structure of many taxa)."""
     w = dict(WORKLOADS[name])
     if n_genomes is not None:
         w['n_genomes'] = n_genomes
-    seqs = helpers.synthetic_genomes(w['n_genomes'], w['length'], w['div'], w['seed'])
-    cands = helpers.tile_candidates(seqs, w['pl'], w['ps'])
-    cands = list(dict.fromkeys(cands))          # DuplicateFilter upstream of SetCoverFilter
-    w['seqs'] = seqs
-    w['cands'] = cands
-    w['pairs'] = len(cands) * sum(len(s) for s in seqs)
+    w['groups_seqs'], w['groups_cands'] = [], []
+    pairs = 0
+    for g in range(n_groups):
+        seqs = helpers.synthetic_genomes(w['n_genomes'], w['length'], w['div'], w['seed'] + g)
+        cands = helpers.tile_candidates(seqs, w['pl'], w['ps'])
+        cands = list(dict.fromkeys(cands))          # DuplicateFilter upstream of SetCoverFilter
+        w['groups_seqs'].append(seqs)
+        w['groups_cands'].append(cands)
+        pairs += len(cands) * sum(len(s) for s in seqs)
+    w['seqs'], w['cands'] = w['groups_seqs'][0], w['groups_cands'][0]
+    w['pairs'] = pairs
     return w
 
 
@@ -143,7 +151,7 @@ def run_reference_arm(args, rank, world):
     print(json.dumps({
         'impl': 'reference', 'metric': 'candidate-probe x target-bp / s through SetCoverFilter',
         'value': v, 'unit': 'pairs/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': t * 1e3, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+        'ms_per_step': t * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'u8', 'data': 'synthetic',
         'config': {'workload': WORKLOADS[args.workload]['desc'], 'sample': sample},
         'cpu_baseline': {'value': v, 'unit': 'pairs/s', 'cores': threads, 'kind': 'port', 'sample': sample},
@@ -191,25 +199,32 @@ def main():
 
     dist = None
     if world > 1:
+        import torch
         import torch.distributed as dist
-        dist.init_process_group('gloo')      # plumbing only: barrier + max-over-ranks of the timings
+        torch.cuda.set_device(local_rank)
+        # plumbing only: barrier, max-over-ranks of the timings (NCCL), exchange of the selected
+        # ids between ranks (gloo, a few KB of Python objects)
+        dist.init_process_group('cpu:gloo,cuda:nccl')
 
     from catch_b200 import _lib, probe
     from catch_b200 import coverage as cov
     from catch_b200.filter.set_cover_filter import SetCoverFilter
 
-    w = make_workload(args.workload)
+    w = make_workload(args.workload, n_groups=world)
     ctx = _lib.Context(local_rank)
-    genomes = helpers.to_genomes([[[s] for s in w['seqs']]])
-    probes = [[probe.Probe.from_str(s) for s in w['cands']]]
+    genomes = helpers.to_genomes([[[s] for s in seqs] for seqs in w['groups_seqs']])
+    probes = [[probe.Probe.from_str(s) for s in c] for c in w['groups_cands']]
     scf = SetCoverFilter(**w['scf'])
     scf._ctx = ctx
+    my_group = rank if world > 1 else 0          # equal-size groupings: assign_groups gives g -> rank g
 
     def barrier():
         if dist is not None:
-            dist.barrier()
+            import torch
+            dist.barrier(device_ids=[local_rank])
+            torch.cuda.synchronize()
 
-    # ---- e2e: the plugin call with host objects
+    # ---- e2e: the plugin call with host objects (all groupings in, all selections out)
     def e2e_step():
         np.random.seed(RNG_SEED)
         random.seed(RNG_SEED)
@@ -218,15 +233,17 @@ def main():
         out = scf.filter(probes, genomes, input_is_grouped=True)
         return time.perf_counter() - t0, out
 
-    # ---- resident: inputs packed in HBM before the timed region
-    group = cov.PackedGroup(ctx, w['cands'], genomes[0])
+    # ---- resident: this rank's grouping packed in HBM before the timed region
+    my_cands = w['groups_cands'][my_group]
+    group = cov.PackedGroup(ctx, my_cands, genomes[my_group])
 
     def resident_step():
         np.random.seed(RNG_SEED)
         ctx.flush_l2()
-        cover, st_a, k, mode = cov.compute_cover(ctx, group, w['cands'], w['scf']['mismatches'],
-                                                 w['scf']['lcf_thres'], 0, w['scf']['cover_extension'], 20)
-        picks, st_b = ctx.setcover(cover, len(w['cands']), None, None)
+        plan = cov.SeedPlan(my_cands, w['scf']['mismatches'], w['scf']['lcf_thres'], 20)
+        cover, st_a = cov.compute_cover(ctx, group, plan, w['scf']['mismatches'], w['scf']['lcf_thres'], 0,
+                                        w['scf']['cover_extension'])
+        picks, st_b = ctx.setcover(cover, len(my_cands), None, None)
         cover.free()
         return st_a, st_b, picks
 
@@ -238,6 +255,7 @@ def main():
     barrier()
     sampler.start()
     res = [resident_step() for _ in range(args.steps)]
+    barrier()
     e2e = [e2e_step() for _ in range(args.steps)]
     barrier()
     clocks = sampler.stop()
@@ -247,11 +265,14 @@ def main():
     t_e2e = float(np.mean([t for t, _ in e2e]))
     if dist is not None:
         import torch
-        t = torch.tensor([t_res, t_e2e], dtype=torch.float64)
+        t = torch.tensor([t_res, t_e2e], dtype=torch.float64, device='cuda')
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_res, t_e2e = t.tolist()
     st_a, st_b, picks = res[-1]
-    launches = int(st_a.n_kernel_launches + st_b.n_kernel_launches)
+    launches = sum(int(a.n_kernel_launches + b.n_kernel_launches) for a, b, _ in res)
+    ls = scf.last_stats[my_group]
+    launches += args.steps * int(ls['upload_targets']['n_kernel_launches'] + ls['upload_probes']['n_kernel_launches'] +
+                                 ls['coverage']['n_kernel_launches'] + ls['setcover']['n_kernel_launches'])
 
     # ---- roofline of the dominant kernel
     kern = {
@@ -261,7 +282,7 @@ def main():
         'seed_index (K2)': st_a.ms_seed_index,
     }
     dom = max(kern, key=kern.get)
-    P, T = len(w['cands']), sum(len(s) for s in w['seqs'])
+    P, T = len(my_cands), sum(len(s) for s in w['groups_seqs'][my_group])
     E, S = int(st_a.n_intervals), int(st_b.n_picks)
     bits = group.bits
     if dom.startswith('scan'):
@@ -289,14 +310,16 @@ def main():
         'metric': 'candidate-probe x target-bp / s through SetCoverFilter',
         'value': w['pairs'] / t_res, 'unit': 'pairs/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': t_res * 1e3, 'higher_is_better': True,
-        'scaling': 'strong', 'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
-        'config': {'workload': w['desc'], 'P': P, 'T_bp': T, 'pairs': w['pairs'], 'intervals': E,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
+        'config': {'workload': w['desc'] + ('' if world == 1 else ' x %d independent groupings' % world),
+                   'P_per_group': P, 'T_bp_per_group': T, 'pairs': w['pairs'], 'intervals': E,
                    'picks': S, 'l2': 'flushed between steps (256 MiB memset)',
-                   'parallelism': 'single GPU' if world == 1 else 'replicas'},
+                   'parallelism': 'single GPU' if world == 1 else
+                   'one grouping per GPU (independent set-cover instances), no data-path collective'},
         'e2e': {'value': w['pairs'] / t_e2e, 'unit': 'pairs/s', 'ms_per_step': t_e2e * 1e3,
-                'h2d_bytes_per_step': int(scf.last_stats[0]['h2d_bytes']),
-                'd2h_bytes_per_step': int(scf.last_stats[0]['d2h_bytes'])},
-        'gpu_launches': launches * args.steps * 2,
+                'h2d_bytes_per_step': int(scf.last_stats[my_group]['h2d_bytes']) * world,
+                'd2h_bytes_per_step': int(scf.last_stats[my_group]['d2h_bytes']) * world},
+        'gpu_launches': launches * world,
         'clocks': clocks,
         'roofline': roofline,
         'stages_ms': {'coverage': st_a.as_dict(), 'setcover': st_b.as_dict()},
@@ -306,6 +329,9 @@ def main():
             out['cpu_baseline'] = cpu_baseline(args)
         print(json.dumps(out))
     group.free()
+    if dist is not None:
+        dist.barrier(device_ids=[local_rank])
+        dist.destroy_process_group()
 
 
 if __name__ == '__main__':

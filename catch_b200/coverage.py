@@ -99,17 +99,24 @@ def dedup_map(probe_strs):
     return [last[s] for s in probe_strs]
 
 
-def compute_cover(ctx, group, probe_strs, mismatches, lcf_thres, island, cover_extension,
-                  kmer_probe_map_k):
-    """Stage A for one packed group.  Returns (cover handle, stats, k, mode)."""
-    lengths = np.diff(group.probe_off)
-    k, seeds, mode = probe_mod.choose_seed_positions(lengths, mismatches, lcf_thres,
-                                                     min_k=kmer_probe_map_k, k=kmer_probe_map_k)
-    rep = dedup_map(probe_strs)
-    seed_off, seed_pos = seeds_to_csr(np.asarray(seeds), rep)
-    cover, st = ctx.coverage(group.probes, group.targets, mismatches, lcf_thres, island,
-                             cover_extension, k, seed_off, seed_pos)
-    return cover, st, k, mode
+class SeedPlan:
+    """The seed choice for one probe list: drawn on the host (it consumes numpy's global RNG
+    exactly like probe.construct_kmer_probe_map_to_find_probe_covers, probe.py:507-577), then
+    handed to cb_coverage as a CSR.  Drawing is separate from the device call so that a rank
+    which does not own a grouping can still advance the RNG stream identically."""
+
+    def __init__(self, probe_strs, mismatches, lcf_thres, kmer_probe_map_k):
+        lengths = np.fromiter((len(s) for s in probe_strs), dtype=np.int64, count=len(probe_strs))
+        self.k, seeds, self.mode = probe_mod.choose_seed_positions(
+            lengths, mismatches, lcf_thres, min_k=kmer_probe_map_k, k=kmer_probe_map_k)
+        self.rep = dedup_map(probe_strs)
+        self.seed_off, self.seed_pos = seeds_to_csr(np.asarray(seeds), self.rep)
+
+
+def compute_cover(ctx, group, plan, mismatches, lcf_thres, island, cover_extension):
+    """Stage A for one packed group with a drawn SeedPlan.  Returns (cover handle, stats)."""
+    return ctx.coverage(group.probes, group.targets, mismatches, lcf_thres, island, cover_extension,
+                        plan.k, plan.seed_off, plan.seed_pos)
 
 
 def cover_with_seeds(ctx, group, seeds_per_probe, k, mismatches, lcf_thres, island, cover_extension):

@@ -18,6 +18,7 @@ import numpy as np
 
 from catch_b200 import _lib
 from catch_b200 import coverage as cov
+from catch_b200 import parallel
 from catch_b200.filter.base_filter import BaseFilter
 from catch_b200.utils import seq_io
 
@@ -99,7 +100,7 @@ class SetCoverFilter(BaseFilter):
             p[j] = float(min(self.coverage, size)) / size
         return p
 
-    def _tolerant_bp_covered(self, ctx, probe_strs, sequences):
+    def _tolerant_bp_covered(self, ctx, probe_strs, plan, sequences):
         """Sum over `sequences` and their reverse complements of the bp each probe covers under
         the tolerant parameters (set_cover_filter.py:472-529): ranges merged per sequence, no
         cover extension.  Each sequence and each reverse complement is packed as its own
@@ -110,10 +111,8 @@ class SetCoverFilter(BaseFilter):
             seqs.append([_reverse_complement(s)])
         group = cov.PackedGroup(ctx, probe_strs, seqs)
         try:
-            cover, st, _, _ = cov.compute_cover(ctx, group, probe_strs, self.mismatches_tolerant,
-                                                self.lcf_thres_tolerant,
-                                                self.island_of_exact_match_tolerant, 0,
-                                                self.kmer_probe_map_k)
+            cover, st = cov.compute_cover(ctx, group, plan, self.mismatches_tolerant,
+                                          self.lcf_thres_tolerant, self.island_of_exact_match_tolerant, 0)
             pid, _, start, end = ctx.cover_export(cover)
             cover.free()
         finally:
@@ -123,28 +122,29 @@ class SetCoverFilter(BaseFilter):
             np.add.at(bp, pid, end - start)
         return bp
 
-    def _make_ranks(self, ctx, probe_strs, target_genomes_grouped):
-        """set_cover_filter.py:614-735.  Returns None when every probe has the same rank."""
-        if not self.identify and len(self.avoided_genomes) == 0:
-            return None
+    def _needs_ranks(self):
+        return bool(self.identify) or len(self.avoided_genomes) > 0
+
+    def _make_ranks(self, ctx, probe_strs, plan, target_genomes_grouped):
+        """set_cover_filter.py:614-735.  `plan` is the tolerant seed plan: the reference builds ONE
+        k-mer map per call (:672-681) and scans every grouping / avoided genome with it."""
         n = len(probe_strs)
-        rep = cov.dedup_map(probe_strs)
         first = np.zeros(n, dtype=np.int64)
         second = np.zeros(n, dtype=np.int64)
         if self.identify:
             hits = np.zeros(n, dtype=np.int64)
             for genomes in target_genomes_grouped:
                 seqs = [s for g in genomes for s in g.seqs]
-                bp = self._tolerant_bp_covered(ctx, probe_strs, seqs)
+                bp = self._tolerant_bp_covered(ctx, probe_strs, plan, seqs)
                 hits += (bp >= 1)
             second = hits
         avoided_bp = np.zeros(n, dtype=np.int64)
         for path in self.avoided_genomes:
             seqs = list(seq_io.iterate_fasta(path))
-            avoided_bp += self._tolerant_bp_covered(ctx, probe_strs, seqs)
-        if rep is not None:
+            avoided_bp += self._tolerant_bp_covered(ctx, probe_strs, plan, seqs)
+        if plan.rep is not None:
             # dicts keyed by sequence: all duplicates share the values of their representative
-            rep = np.asarray(rep)
+            rep = np.asarray(plan.rep)
             second = second[rep]
             avoided_bp = avoided_bp[rep]
         mask = avoided_bp > 0
@@ -156,52 +156,79 @@ class SetCoverFilter(BaseFilter):
 
     # ------------------------------------------------------------------ the filter
     def _filter(self, input, target_genomes_grouped):
-        ctx = self._context()
-        self.last_stats = []
-        selected = []
+        self.last_stats = [None] * len(input)
+        # multi-GPU: groupings are independent instances; each rank solves the ones it owns
+        rank, world_size, _ = parallel.world()
+        sharded = parallel.active()
+        sizes = [len(p) * max(1, sum(g.size() for g in tg)) for p, tg in zip(input, target_genomes_grouped)]
+        owner = parallel.assign_groups(sizes, world_size) if sharded else [rank] * len(input)
+        local = {}
         for group_i, (possible_probes, target_genomes) in enumerate(zip(input, target_genomes_grouped)):
             possible_probes = list(possible_probes)
-            t0 = time.perf_counter()
-            stats = {'group': group_i, 'n_probes': len(possible_probes),
-                     'target_bp': sum(g.size() for g in target_genomes)}
-            if len(possible_probes) == 0:                       # set_cover_filter.py:393-394
-                selected.append([])
-                self.last_stats.append(stats)
-                continue
             probe_strs = [p.seq_str for p in possible_probes]
-            logger.info("Computing coverage of %d probes in %d genomes (group %d of %d)",
-                        len(probe_strs), len(target_genomes), group_i + 1, len(input))
-            group = cov.PackedGroup(ctx, probe_strs, target_genomes)
-            try:
-                cover, st_a, k, mode = cov.compute_cover(
-                    ctx, group, probe_strs, self.mismatches, self.lcf_thres,
-                    self.island_of_exact_match, self.cover_extension, self.kmer_probe_map_k)
-            finally:
-                group.free()
-            try:
-                ranks = self._make_ranks(ctx, probe_strs, target_genomes_grouped)
-                universe_p = self._make_universe_p(target_genomes)
-                picks, st_b = ctx.setcover(cover, len(probe_strs), ranks, universe_p)
-            finally:
-                cover.free()
-            if ranks is not None:
-                n_bad = int(np.sum(ranks[picks] > 0))
-                if n_bad > 0:
-                    logger.warning("Group %d: forced to choose %d less-than-ideal probe%s",
-                                   group_i + 1, n_bad, '' if n_bad == 1 else 's')
-            # The reference returns a Python set of ids from a Pool worker and iterates it
-            # (set_cover_filter.py:893-900, :926): same elements, CPython set order after a
-            # pickle round trip.  Reproduce it with the real thing.
-            chosen = set()
-            for i in picks.tolist():
-                chosen.add(i)
-            chosen = pickle.loads(pickle.dumps(chosen))
+            # The seed draws consume numpy's global RNG per grouping, in grouping order, first for
+            # _make_sets and then for _make_ranks (set_cover_filter.py:824-827); every rank replays
+            # all of them so that a sharded run sees the same stream as a single process.
+            plan = plan_tol = None
+            if probe_strs:
+                plan = cov.SeedPlan(probe_strs, self.mismatches, self.lcf_thres, self.kmer_probe_map_k)
+                if self._needs_ranks():
+                    plan_tol = cov.SeedPlan(probe_strs, self.mismatches_tolerant, self.lcf_thres_tolerant,
+                                            self.kmer_probe_map_k)
+            if owner[group_i] != rank:
+                continue
+            local[group_i] = self._select_for_group(group_i, len(input), probe_strs, plan, plan_tol,
+                                                    target_genomes, target_genomes_grouped)
+        chosen_per_group = parallel.exchange_group_results(local, owner, rank) if sharded else \
+            [local[i] for i in range(len(input))]
+        selected = []
+        for possible_probes, chosen in zip(input, chosen_per_group):
+            possible_probes = list(possible_probes)
             selected.append([possible_probes[i] for i in chosen])
-            stats.update(seed_mode=mode, k=k, bits=group.bits, h2d_bytes=group.h2d_bytes,
-                         d2h_bytes=int(picks.nbytes), picks=picks,
-                         upload_targets=group.st_targets.as_dict(),
-                         upload_probes=group.st_probes.as_dict(),
-                         coverage=st_a.as_dict(), setcover=st_b.as_dict(),
-                         wall_s=time.perf_counter() - t0)
-            self.last_stats.append(stats)
         return selected
+
+    def _select_for_group(self, group_i, n_groups, probe_strs, plan, plan_tol, target_genomes,
+                          target_genomes_grouped):
+        """Indices (into the grouping's probe list) of the selected probes, in the reference's
+        output order."""
+        ctx = self._context()
+        t0 = time.perf_counter()
+        stats = {'group': group_i, 'n_probes': len(probe_strs),
+                 'target_bp': sum(g.size() for g in target_genomes)}
+        self.last_stats[group_i] = stats
+        if len(probe_strs) == 0:                            # set_cover_filter.py:393-394
+            return []
+        logger.info("Computing coverage of %d probes in %d genomes (group %d of %d)",
+                    len(probe_strs), len(target_genomes), group_i + 1, n_groups)
+        group = cov.PackedGroup(ctx, probe_strs, target_genomes)
+        try:
+            cover, st_a = cov.compute_cover(ctx, group, plan, self.mismatches, self.lcf_thres,
+                                            self.island_of_exact_match, self.cover_extension)
+        finally:
+            group.free()
+        try:
+            ranks = self._make_ranks(ctx, probe_strs, plan_tol, target_genomes_grouped) \
+                if plan_tol is not None else None
+            universe_p = self._make_universe_p(target_genomes)
+            picks, st_b = ctx.setcover(cover, len(probe_strs), ranks, universe_p)
+        finally:
+            cover.free()
+        if ranks is not None:
+            n_bad = int(np.sum(ranks[picks] > 0))
+            if n_bad > 0:
+                logger.warning("Group %d: forced to choose %d less-than-ideal probe%s",
+                               group_i + 1, n_bad, '' if n_bad == 1 else 's')
+        # The reference returns a Python set of ids from a Pool worker and iterates it
+        # (set_cover_filter.py:893-900, :926): same elements, CPython set order after a
+        # pickle round trip.  Reproduce it with the real thing.
+        chosen = set()
+        for i in picks.tolist():
+            chosen.add(i)
+        chosen = pickle.loads(pickle.dumps(chosen))
+        stats.update(seed_mode=plan.mode, k=plan.k, bits=group.bits, h2d_bytes=group.h2d_bytes,
+                     d2h_bytes=int(picks.nbytes), picks=picks,
+                     upload_targets=group.st_targets.as_dict(),
+                     upload_probes=group.st_probes.as_dict(),
+                     coverage=st_a.as_dict(), setcover=st_b.as_dict(),
+                     wall_s=time.perf_counter() - t0)
+        return list(chosen)

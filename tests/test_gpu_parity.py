@@ -17,9 +17,9 @@ def _oracle():
 def _device_quads(ctx, probe_strs, genomes, params, k=None):
     from catch_b200 import coverage as cov
     group = cov.PackedGroup(ctx, probe_strs, genomes)
-    cover, st, k, mode = cov.compute_cover(ctx, group, probe_strs, params['mismatches'], params['lcf_thres'],
-                                           params['island_of_exact_match'], params['cover_extension'],
-                                           params['kmer_probe_map_k'])
+    plan = cov.SeedPlan(probe_strs, params['mismatches'], params['lcf_thres'], params['kmer_probe_map_k'])
+    cover, st = cov.compute_cover(ctx, group, plan, params['mismatches'], params['lcf_thres'],
+                                  params['island_of_exact_match'], params['cover_extension'])
     pid, gen, s, e = ctx.cover_export(cover)
     group.free()
     quads = np.stack([pid, gen.astype(np.int64), s, e], axis=1) if len(pid) else np.zeros((0, 4), np.int64)

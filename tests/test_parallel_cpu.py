@@ -1,0 +1,91 @@
+"""Host-side multi-GPU logic on CPU: world_size-2 gloo process group, device work replaced by a
+stub (no CUDA call is made).  Checks that groupings are partitioned, that every rank ends with the
+complete result, and that the RNG stream a rank sees does not depend on which groupings it owns."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_assign_groups_is_deterministic_and_balanced():
+    from catch_b200 import parallel
+    sizes = [5, 100, 7, 90, 3, 60, 60]
+    own = parallel.assign_groups(sizes, 3)
+    assert own == parallel.assign_groups(sizes, 3)
+    load = [sum(s for s, o in zip(sizes, own) if o == r) for r in range(3)]
+    assert sum(load) == sum(sizes) and max(load) <= 120 and min(load) >= 100
+    assert parallel.assign_groups(sizes, 1) == [0] * len(sizes)
+    assert parallel.assign_groups([], 4) == []
+
+
+def _worker(rank, world_size, port, out_path):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world_size), LOCAL_RANK=str(rank),
+                      MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    sys.path.insert(0, ROOT)
+    import random
+    import torch.distributed as dist
+    from catch_b200 import probe
+    from catch_b200.filter.set_cover_filter import SetCoverFilter
+    from tests import helpers
+    dist.init_process_group('gloo', rank=rank, world_size=world_size)
+    computed = []
+
+    def fake_select(self, group_i, n_groups, probe_strs, plan, plan_tol, target_genomes, all_genomes):
+        computed.append(group_i)
+        # deterministic stand-in for the device result: depends on the drawn seeds
+        return [int(x) % max(1, len(probe_strs)) for x in plan.seed_pos[:3]]
+
+    SetCoverFilter._select_for_group = fake_select
+    rng = random.Random(5)
+    groups = [helpers.random_groups(rng, n_groups=1)[0] for _ in range(5)]
+    cands = [helpers.tile_candidates([s for g in gens for s in g], 30, 10) for gens in groups]
+    probes = [[probe.Probe.from_str(s) for s in c] for c in cands]
+    f = SetCoverFilter(mismatches=1, lcf_thres=20)          # random seed mode: consumes np.random
+    np.random.seed(3)
+    out = f.filter(probes, helpers.to_genomes(groups), input_is_grouped=True)
+    after = int(np.random.randint(0, 1 << 30))
+    np.save(out_path, np.array([computed, [[p.seq_str for p in g] for g in out], after], dtype=object),
+            allow_pickle=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+@pytest.mark.parametrize('world_size', [1, 2])
+def test_group_sharding_over_gloo(tmp_path, world_size):
+    import multiprocessing as mp
+    ctxm = mp.get_context('spawn')
+    port = _free_port()
+    paths = [str(tmp_path / ('r%d.npy' % r)) for r in range(world_size)]
+    procs = [ctxm.Process(target=_worker, args=(r, world_size, port, paths[r])) for r in range(world_size)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    res = [np.load(p, allow_pickle=True) for p in paths]
+    all_computed = sorted(g for r in res for g in r[0])
+    assert all_computed == [0, 1, 2, 3, 4]                    # every grouping exactly once
+    for r in res[1:]:
+        assert r[1] == res[0][1]                              # every rank has the full result
+        assert r[2] == res[0][2]                              # and saw the same RNG stream
+    # world size must not change the result or the stream either
+    ref_path = tmp_path / 'single.npy'
+    if world_size > 1:
+        p = ctxm.Process(target=_worker, args=(0, 1, _free_port(), str(ref_path)))
+        p.start()
+        p.join(180)
+        assert p.exitcode == 0
+        single = np.load(str(ref_path), allow_pickle=True)
+        assert single[1] == res[0][1] and single[2] == res[0][2]
