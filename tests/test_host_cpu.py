@@ -1,0 +1,111 @@
+"""Host-side logic that needs no GPU: C-ABI exports, candidate tiling, seed rule, FASTA I/O, CLI parser."""
+import ctypes
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    """libcatchb200.so loads (no CUDA call) and exports every function include/catch_b200.h declares."""
+    from catch_b200 import _lib
+    hdr = open(os.path.join(ROOT, 'include', 'catch_b200.h')).read()
+    declared = sorted(set(re.findall(r'\b(cb_[a-z0-9_]+)\s*\(', hdr)) - {'cb_status'})
+    assert len(declared) >= 16
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert sorted(_lib.EXPORTED_SYMBOLS) == declared
+    assert b'sm_100a' in _lib.load().cb_version()
+
+
+def test_no_oracle_on_product_path():
+    """Nothing under catch_b200/ or bin/ may import the oracle."""
+    for base in ('catch_b200', 'bin'):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, base)):
+            for f in files:
+                if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                    text = open(os.path.join(dirpath, f)).read()
+                    assert 'oracle' not in text.lower(), os.path.join(dirpath, f)
+
+
+def test_pigeonhole_rule():
+    """probe.py:473-491 (pinned by the reference's tests/test_probe.py:270-335)."""
+    from catch_b200 import probe
+    assert probe.pigeonhole_kmer_length(100, 0, 20) == 100
+    assert probe.pigeonhole_kmer_length(100, 2, 20) == 25      # k < 50, divides 100
+    assert probe.pigeonhole_kmer_length(100, 3, 20) == 25
+    assert probe.pigeonhole_kmer_length(75, 2, 20) == 25
+    with pytest.raises(probe.PigeonholeRequiresTooSmallKmerSizeError):
+        probe.pigeonhole_kmer_length(100, 5, 20)              # would need k < 20
+    k, seeds, mode = probe.choose_seed_positions([75] * 3, 0, 75)
+    assert (k, mode) == (75, 'pigeonhole') and seeds.tolist() == [[0]] * 3
+    k, seeds, mode = probe.choose_seed_positions([100] * 2, 2, 100)
+    assert (k, mode) == (25, 'pigeonhole') and seeds.tolist() == [[0, 25, 50, 75]] * 2
+    np.random.seed(0)
+    k, seeds, mode = probe.choose_seed_positions([75, 75, 60], 2, 60)
+    assert (k, mode) == (20, 'random') and seeds.shape == (3, 20)
+    assert seeds[:2].max() <= 55 and seeds[2].max() <= 40
+
+
+def test_candidate_tiling_and_n_handling():
+    from catch_b200.filter import candidate_probes as cp
+    seq = 'ACGT' * 10 + 'A'            # 41 nt
+    ps = [p.seq_str for p in cp.make_candidate_probes_from_sequence(seq, 10, 5)]
+    assert ps[0] == seq[:10] and ps[-1] == seq[-10:] and len(ps) == 7 + 1
+    with_n = 'ACGTACGTAC' + 'NN' + 'GTGTGTGTGT' + 'CCCC'
+    got = [p.seq_str for p in cp.make_candidate_probes_from_sequence(with_n, 10, 4)]
+    assert all('NN' not in s for s in got)
+    assert 'ACGTACGTAC' in got and 'GTGTGTGTGT' in got       # flanking probes
+    with pytest.raises(ValueError):
+        cp.make_candidate_probes_from_sequence('ACGT', 10, 5)
+    assert [p.seq_str for p in cp.make_candidate_probes_from_sequence('ACGTAC', 10, 5, allow_small_seqs=5)] == ['ACGTAC']
+
+
+def test_fasta_round_trip(tmp_path):
+    from catch_b200 import probe
+    from catch_b200.utils import seq_io
+    fn = tmp_path / 'in.fasta'
+    fn.write_text('>a desc\nacgtRy-\nNNac\n\n>b\nTTTT\n')
+    m = seq_io.read_fasta(str(fn))
+    assert list(m.items()) == [('a desc', 'ACGTNNNNAC'), ('b', 'TTTT')]
+    gs = seq_io.read_genomes_from_fasta(str(fn))
+    assert [g.seqs for g in gs] == [['ACGTNNNNAC'], ['TTTT']] and gs[0].size() == 10
+    out = tmp_path / 'out.fasta'
+    p = probe.Probe.from_str('ACGTACGT')
+    seq_io.write_probe_fasta([p], str(out))
+    import hashlib
+    assert out.read_text() == '>probe_%s\nACGTACGT\n' % hashlib.sha224(b'ACGTACGT').hexdigest()[-10:]
+
+
+def test_cli_parser_matches_reference_defaults():
+    sys.path.insert(0, os.path.join(ROOT, 'bin'))
+    import design
+    a = design.init_and_parse_args('basic', ['x.fasta', '-o', 'out.fasta'])
+    assert (a.probe_length, a.probe_stride, a.mismatches, a.cover_extension, a.coverage) == (100, 50, 0, 0, 1.0)
+    assert a.filter_with_lsh_minhash is None and a.lcf_thres is None
+    b = design.init_and_parse_args('large', ['x.fasta', 'y.fasta', '-o', 'o.fa', '-pl', '75', '-c', '300'])
+    assert (b.mismatches, b.cover_extension, b.filter_with_lsh_minhash, b.probe_length, b.coverage) == \
+        (5, 50, 0.6, 75, 300)
+    with pytest.raises(SystemExit):
+        design.init_and_parse_args('basic', ['x.fasta', '-o', 'o', '-c', '1.5'])
+
+
+def test_filters_fail_loudly_without_a_gpu():
+    """No CPU fallback: with no usable device the filter raises instead of computing elsewhere."""
+    from catch_b200 import _lib, probe
+    from catch_b200.filter.set_cover_filter import SetCoverFilter
+    from tests import helpers
+    try:
+        _lib.Context(0)
+    except _lib.CatchB200Error:
+        f = SetCoverFilter(0, 12, kmer_probe_map_k=5)
+        with pytest.raises(_lib.CatchB200Error):
+            f.filter([[probe.Probe.from_str('ACGTACGTACGT')]], helpers.to_genomes([[['ACGTACGTACGTACGT']]]),
+                     input_is_grouped=True)
+    with pytest.raises(NotImplementedError):
+        SetCoverFilter(0, 10, custom_cover_range_fn=('x.py', 'f'))
