@@ -8,6 +8,7 @@ with one all_gather over torch.distributed -- no collective on the data path.  W
 process (no RANK in the environment) everything below is a no-op.
 """
 import os
+import sys
 
 
 def world():
@@ -32,9 +33,10 @@ def assign_groups(sizes, world_size):
 
 
 def _dist():
-    try:
-        import torch.distributed as dist
-    except ImportError:
+    # A process group can only be initialised if the launcher already imported torch.distributed;
+    # never import torch from here (seconds of start-up a single-GPU run does not need).
+    dist = sys.modules.get('torch.distributed')
+    if dist is None:
         return None
     return dist if dist.is_available() and dist.is_initialized() else None
 

@@ -104,3 +104,26 @@ def synthetic_genomes(n_genomes, length, div, seed):
         g = np.where(mask, (anc + shift) % 4, anc)
         out.append(letters[g].tobytes().decode())
     return out
+
+
+INFLUENZA_SEGMENTS = [2341, 2341, 2233, 1778, 1565, 1413, 1027, 890]
+
+
+def synthetic_influenza(n_genomes, seed, n_clades=10, clade_div=0.08, strain_div=0.02):
+    """segmented genomes, one ancestor per segment, two-level
+    divergence (clades, then strains).  Returns a list of genomes, each a list of 8 segment strings."""
+    rng = np.random.default_rng(seed)
+    letters = np.frombuffer(b'ACGT', dtype=np.uint8)
+
+    def diverge(anc, div):
+        mask = rng.random(len(anc)) < div
+        shift = rng.integers(1, 4, len(anc))
+        return np.where(mask, (anc + shift) % 4, anc)
+
+    ancestors = [rng.integers(0, 4, L) for L in INFLUENZA_SEGMENTS]
+    clades = [[diverge(a, clade_div) for a in ancestors] for _ in range(n_clades)]
+    genomes = []
+    for i in range(n_genomes):
+        c = clades[i % n_clades]
+        genomes.append([letters[diverge(seg, strain_div)].tobytes().decode() for seg in c])
+    return genomes
