@@ -27,6 +27,7 @@
 //      (seeds in one run give identical ranges) the anchored extension is evaluated with
 //      ffs/clz on the mask, and the resulting range is appended, warp-aggregated, to a global
 //      list that is later bucketed by probe.
+#include <cstdlib>
 #include <cstring>
 
 #include "internal.cuh"
@@ -432,6 +433,158 @@ __device__ __forceinline__ void align_probe(const ScanParams &P, const uint64_t 
     for (int w = 0; w < NW; w++) A[w] &= __ldg(pw + P.bits * NW + w);
 }
 
+// ---------------------------------------------------------------------------------------
+// Fast path for probes of up to 128 bases (NW == 2) and a compile-time seed length KC: masks are
+// two scalar 64-bit registers, every shift amount of the run detection is a constant.
+// ---------------------------------------------------------------------------------------
+struct U128 { uint64_t lo, hi; };
+
+__device__ __forceinline__ U128 shr128(U128 x, int n)      // n is a compile-time constant after unrolling
+{
+    U128 r;
+    if (n == 0) return x;
+    if (n < 64) { r.lo = (x.lo >> n) | (x.hi << (64 - n)); r.hi = x.hi >> n; }
+    else if (n == 64) { r.lo = x.hi; r.hi = 0; }
+    else if (n < 128) { r.lo = x.hi >> (n - 64); r.hi = 0; }
+    else { r.lo = 0; r.hi = 0; }
+    return r;
+}
+
+template <int KC>
+__device__ __forceinline__ U128 runs_of_k_const(U128 Z)
+{
+    U128 D = Z, C;
+    C.lo = ~0ull; C.hi = ~0ull;
+    int off = 0;
+#pragma unroll
+    for (int len = 1; len <= KC; len <<= 1) {
+        if (KC & len) {
+            const U128 t = shr128(D, off);
+            C.lo &= t.lo; C.hi &= t.hi;
+            off += len;
+        }
+        if ((len << 1) <= KC) {
+            const U128 t = shr128(D, len);
+            D.lo &= t.lo; D.hi &= t.hi;
+        }
+    }
+    return C;
+}
+
+// bits [a, b) of a 128-bit mask, 0 <= a <= b <= 128
+__device__ __forceinline__ U128 range128(int a, int b)
+{
+    U128 r;
+    const uint64_t ge_lo = a < 64 ? (~0ull << a) : 0ull;
+    const uint64_t ge_hi = a <= 64 ? ~0ull : (~0ull << (a - 64));
+    const uint64_t lt_lo = b >= 64 ? ~0ull : ((1ull << b) - 1ull);
+    const uint64_t lt_hi = b <= 64 ? 0ull : (b >= 128 ? ~0ull : ((1ull << (b - 64)) - 1ull));
+    r.lo = ge_lo & lt_lo;
+    r.hi = ge_hi & lt_hi;
+    return r;
+}
+
+template <int KC>
+__device__ __forceinline__ void align_probe_fast(const ScanParams &P, const uint64_t *s_tile, int64_t t0, int64_t d,
+                                                 int64_t qs, int64_t qe, uint32_t p, int L, U128 &M, U128 &A,
+                                                 int &a, int &bnd)
+{
+    const int off = (int)(d - t0) + CB_FRONT_PAD;
+    const int idx = off >> 6, sh = off & 63;
+    const ulonglong2 *pr = reinterpret_cast<const ulonglong2 *>(P.precs + (int64_t)p * P.prec_words);
+    M.lo = 0ull;
+    M.hi = 0ull;
+    for (int b = 0; b < P.bits; b++) {
+        const ulonglong2 pw = __ldg(pr + b);
+        const uint64_t *t = s_tile + b * TW + idx;
+        const uint64_t s0 = t[0], s1 = t[1], s2 = t[2];
+        // 64-bit funnel shifts; (x << (63 - sh)) << 1 is x << (64 - sh) without the sh == 0 hazard
+        const uint64_t w0 = (s0 >> sh) | ((s1 << (63 - sh)) << 1);
+        const uint64_t w1 = (s1 >> sh) | ((s2 << (63 - sh)) << 1);
+        M.lo |= pw.x ^ w0;
+        M.hi |= pw.y ^ w1;
+    }
+    const ulonglong2 seeds = __ldg(pr + P.bits);
+    a = (int)max((int64_t)0, qs - d);
+    bnd = (int)min((int64_t)L, qe - d);
+    const U128 R = range128(a, bnd);
+    U128 Z;
+    Z.lo = ~M.lo & R.lo;
+    Z.hi = ~M.hi & R.hi;
+    const U128 C = runs_of_k_const<KC>(Z);
+    A.lo = C.lo & seeds.x;
+    A.hi = C.hi & seeds.y;
+}
+
+// is bit `pos` the lowest set bit of A?
+__device__ __forceinline__ bool lowest_is(U128 A, int pos)
+{
+    const uint64_t below = pos < 64 ? (A.lo & ((1ull << pos) - 1ull))
+                                    : (A.lo | (A.hi & ((1ull << (pos - 64)) - 1ull)));
+    const uint64_t bit = pos < 64 ? (A.lo >> pos) : (A.hi >> (pos - 64));
+    return below == 0ull && (bit & 1ull);
+}
+
+__device__ __forceinline__ int ffs128(U128 x)
+{
+    return x.lo ? (__ffsll((long long)x.lo) - 1) : (x.hi ? (64 + __ffsll((long long)x.hi) - 1) : -1);
+}
+__device__ __forceinline__ int fls128(U128 x)
+{
+    return x.hi ? (127 - __clzll((long long)x.hi)) : (x.lo ? (63 - __clzll((long long)x.lo)) : -1);
+}
+__device__ __forceinline__ void clear128(U128 &x, int b)
+{
+    if (b < 64) x.lo &= ~(1ull << b); else x.hi &= ~(1ull << (b - 64));
+}
+
+// anchored extension (utils/longest_common_substring.py:59-159) on scalar 128-bit masks.
+// ML / MR: mismatches strictly left of the anchor / at or right of its end, already clipped to [a, b).
+__device__ __forceinline__ int anchored_extend_fast(U128 ML, U128 MR, int a, int b, int s, int k, int m,
+                                                    int &start, int &exact_len)
+{
+    // after[j] packed one byte each (distances < 128)
+    uint64_t aft[4] = {0, 0, 0, 0};
+    const int after_full = b - (s + k);
+    int n_right = 0;
+    for (int j = 0; j <= m; j++) {
+        const int pos = ffs128(MR);
+        if (pos < 0) break;
+        const uint64_t v = (uint64_t)(pos - (s + k));
+        if (j < 8) aft[0] |= v << (j * 8);
+        else {
+#pragma unroll
+            for (int q = 1; q < 4; q++)
+                if ((j >> 3) == q) aft[q] |= v << ((j & 7) * 8);
+        }
+        clear128(MR, pos);
+        n_right++;
+    }
+    auto after = [&](int j) -> int {
+        if (j >= n_right) return after_full;
+        uint64_t word = aft[0];
+        if (j >= 8) {
+#pragma unroll
+            for (int q = 1; q < 4; q++)
+                if ((j >> 3) == q) word = aft[q];
+        }
+        return (int)((word >> ((j & 7) * 8)) & 0xffull);
+    };
+    int best_len = -1, best_start = -1, bef0 = 0;
+    for (int i = 0; i <= m; i++) {
+        const int hp = fls128(ML);
+        const int bef = hp >= 0 ? (s - 1 - hp) : (s - a);
+        if (i == 0) bef0 = bef;
+        const int tot = bef + k + after(m - i);
+        if (tot > best_len) { best_len = tot; best_start = s - bef; }     // strict '>' (:154)
+        if (hp < 0) break;
+        clear128(ML, hp);
+    }
+    start = best_start;
+    exact_len = bef0 + k + after(0);
+    return best_len;
+}
+
 struct OutRec { uint32_t s, e; };
 
 // Owner of a (probe, diagonal): evaluate the anchored extension for every matching seed that
@@ -451,8 +604,9 @@ __device__ __forceinline__ int run_owner_task(const ScanParams &P, const uint64_
     int n_out = 0;
     auto flush = [&]() {
         if (n_out < MAX_LOCAL_REC) {
-            out[n_out].s = cur_s;
-            out[n_out].e = cur_e;
+#pragma unroll
+            for (int r = 0; r < MAX_LOCAL_REC; r++)
+                if (r == n_out) { out[r].s = cur_s; out[r].e = cur_e; }
         } else {                                      // rare: spill straight to the global list
             const unsigned long long slot = atomicAdd(P.rec_cursor, 1ull);
             if (slot < P.rec_cap) P.rec[slot] = make_uint4(p, cur_s, cur_e, 0u);
@@ -497,7 +651,80 @@ __device__ __forceinline__ int run_owner_task(const ScanParams &P, const uint64_
     return n_out;
 }
 
-template <int NW>
+// Fast-path owner: one anchored extension per mismatch-free run that holds a matching seed.
+// All seeds of A below the first mismatch (or the clip boundary) to the right of the current seed
+// lie in the same run -- a seed overlapping that mismatch would not be in A -- and give the same
+// range, so they are dropped together.
+template <int KC>
+__device__ __forceinline__ int run_owner_task_fast(const ScanParams &P, U128 M, U128 A, int a, int bnd, int L,
+                                                   int64_t d, int64_t qs, int64_t qe, uint32_t q_ubase, uint32_t p,
+                                                   OutRec (&out)[MAX_LOCAL_REC])
+{
+    const int64_t qlen = qe - qs;
+    int thres = P.lcf;                                // probe.py:1332
+    if (L < thres) thres = L;
+    if (qlen < (int64_t)thres) thres = (int)qlen;
+    const U128 R = range128(a, bnd);
+    U128 mism;
+    mism.lo = M.lo & R.lo;
+    mism.hi = M.hi & R.hi;
+    uint32_t cur_s = 0, cur_e = 0;
+    bool have = false;
+    int n_out = 0;
+    auto flush = [&]() {
+        if (n_out < MAX_LOCAL_REC) {
+#pragma unroll
+            for (int r = 0; r < MAX_LOCAL_REC; r++)
+                if (r == n_out) { out[r].s = cur_s; out[r].e = cur_e; }
+        } else {
+            const unsigned long long slot = atomicAdd(P.rec_cursor, 1ull);
+            if (slot < P.rec_cap) P.rec[slot] = make_uint4(p, cur_s, cur_e, 0u);
+        }
+        n_out++;
+    };
+    while (A.lo | A.hi) {
+        const int s = ffs128(A);
+        const U128 right = range128(s + KC, 128);
+        U128 MR;
+        MR.lo = mism.lo & right.lo;
+        MR.hi = mism.hi & right.hi;
+        int run_end = ffs128(MR);
+        if (run_end < 0) run_end = bnd;
+        const U128 gone = range128(0, run_end);
+        A.lo &= ~gone.lo;
+        A.hi &= ~gone.hi;
+        const U128 left = range128(0, s);
+        U128 ML;
+        ML.lo = mism.lo & left.lo;
+        ML.hi = mism.hi & left.hi;
+        int start, exact_len;
+        const int len = anchored_extend_fast(ML, MR, a, bnd, s, KC, P.m, start, exact_len);
+        if (len < thres) continue;
+        if (P.island > 0) {                           // probe.py:1335-1342
+            const int ex = (P.m == 0) ? len : exact_len;
+            if (ex < P.island) continue;
+        }
+        int64_t rs = d + start - qs, re = rs + len;   // filter/set_cover_filter.py:429-439
+        rs -= P.ext;
+        re += P.ext;
+        if (rs < 0) rs = 0;
+        if (re > qlen) re = qlen;
+        const uint32_t us = q_ubase + (uint32_t)rs, ue = q_ubase + (uint32_t)re;
+        if (have && us <= cur_e && ue >= cur_s) {
+            cur_s = min(cur_s, us);
+            cur_e = max(cur_e, ue);
+        } else {
+            if (have) flush();
+            cur_s = us;
+            cur_e = ue;
+            have = true;
+        }
+    }
+    if (have) flush();
+    return n_out;
+}
+
+template <int NW, int KC>
 __global__ void __launch_bounds__(SCAN_THREADS)
 scan_kernel(const ScanParams P)
 {
@@ -640,12 +867,19 @@ scan_kernel(const ScanParams P)
                             const int pos = (int)((ent >> 24) & 0xff);
                             const uint32_t q = s_seq[j];
                             const int L = P.plen[p];
-                            uint64_t M[NW], A[NW];
                             int a, bnd;
-                            align_probe<NW>(P, s_tile, t0, t0 + j - pos, P.seq_start[q], P.seq_start[q + 1], p, L,
-                                            M, A, a, bnd);
                             // A has bit `pos` set unless the bucket/tag matched a different k-mer
-                            owner = lowest_set<NW>(A) == pos;
+                            if constexpr (NW == 2 && KC > 0) {
+                                U128 M, A;
+                                align_probe_fast<KC>(P, s_tile, t0, t0 + j - pos, P.seq_start[q], P.seq_start[q + 1],
+                                                     p, L, M, A, a, bnd);
+                                owner = lowest_is(A, pos);
+                            } else {
+                                uint64_t M[NW], A[NW];
+                                align_probe<NW>(P, s_tile, t0, t0 + j - pos, P.seq_start[q], P.seq_start[q + 1], p,
+                                                L, M, A, a, bnd);
+                                owner = lowest_set<NW>(A) == pos;
+                            }
                             task = ((uint64_t)j << 40) | ((uint64_t)pos << 32) | (uint64_t)p;
                         }
                     }
@@ -677,10 +911,16 @@ scan_kernel(const ScanParams P)
                         const int64_t qs = P.seq_start[q], qe = P.seq_start[q + 1];
                         const int L = P.plen[p];
                         const int64_t d = t0 + j - pos;
-                        uint64_t M[NW], A[NW];
                         int a, bnd;
-                        align_probe<NW>(P, s_tile, t0, d, qs, qe, p, L, M, A, a, bnd);
-                        n_out = run_owner_task<NW>(P, M, A, a, bnd, L, d, qs, qe, P.seq_ubase[q], p, out);
+                        if constexpr (NW == 2 && KC > 0) {
+                            U128 M, A;
+                            align_probe_fast<KC>(P, s_tile, t0, d, qs, qe, p, L, M, A, a, bnd);
+                            n_out = run_owner_task_fast<KC>(P, M, A, a, bnd, L, d, qs, qe, P.seq_ubase[q], p, out);
+                        } else {
+                            uint64_t M[NW], A[NW];
+                            align_probe<NW>(P, s_tile, t0, d, qs, qe, p, L, M, A, a, bnd);
+                            n_out = run_owner_task<NW>(P, M, A, a, bnd, L, d, qs, qe, P.seq_ubase[q], p, out);
+                        }
                         if (n_out) atomicAdd(&P.rec_count[p], (uint32_t)n_out);
                         local_owners++;
                     }
@@ -858,10 +1098,10 @@ __global__ void compact_kernel(const int64_t *__restrict__ rec_off, const uint64
     }
 }
 
-template <int NW>
+template <int NW, int KC>
 int launch_scan(cb_ctx *ctx, const ScanParams &P, int grid)
 {
-    scan_kernel<NW><<<grid, SCAN_THREADS, 0, ctx->stream>>>(P);
+    scan_kernel<NW, KC><<<grid, SCAN_THREADS, 0, ctx->stream>>>(P);
     ctx->launches++;
     CB_CUDA(ctx, cudaGetLastError());
     return CB_OK;
@@ -869,11 +1109,24 @@ int launch_scan(cb_ctx *ctx, const ScanParams &P, int grid)
 
 int launch_scan_nw(cb_ctx *ctx, int nw, const ScanParams &P, int grid)
 {
+    const bool generic = getenv("CB_SCAN_GENERIC") != nullptr;     // testing: force the generic path
+    if (nw == 2 && !generic) {
+        // specialised seed lengths: the random-mode default (20) and the pigeonhole lengths of
+        // 75/100-nt probes (probe.py:473-491)
+        switch (P.k) {
+        case 20: return launch_scan<2, 20>(ctx, P, grid);
+        case 25: return launch_scan<2, 25>(ctx, P, grid);
+        case 50: return launch_scan<2, 50>(ctx, P, grid);
+        case 75: return launch_scan<2, 75>(ctx, P, grid);
+        case 100: return launch_scan<2, 100>(ctx, P, grid);
+        default: break;
+        }
+    }
     switch (nw) {
-    case 1: return launch_scan<1>(ctx, P, grid);
-    case 2: return launch_scan<2>(ctx, P, grid);
-    case 3: return launch_scan<3>(ctx, P, grid);
-    case 4: return launch_scan<4>(ctx, P, grid);
+    case 1: return launch_scan<1, 0>(ctx, P, grid);
+    case 2: return launch_scan<2, 0>(ctx, P, grid);
+    case 3: return launch_scan<3, 0>(ctx, P, grid);
+    case 4: return launch_scan<4, 0>(ctx, P, grid);
     }
     return cb_fail(ctx, CB_ERR_UNSUPPORTED, "probe longer than CB_MAX_PROBE_LEN");
 }

@@ -107,3 +107,34 @@ def test_empty_inputs(ctx):
     g = helpers.to_genomes([[['ACGTACGTAC']]])
     p = [[probe.Probe.from_str('ACGTACGTACGTACGTACGTACGTA')]]
     assert f.filter(p, g, input_is_grouped=True) == [[]]
+
+
+@pytest.mark.parametrize('pl,m,lcf', [(75, 0, 75), (100, 0, 100), (75, 2, 75), (100, 2, 100), (100, 1, 100),
+                                      (75, 3, 60), (100, 5, 30), (128, 2, 50), (120, 4, 120)])
+def test_fast_path_probe_lengths(ctx, pl, m, lcf):
+    """Probes of 65..128 nt take the specialised 128-bit scan path for k in {20,25,50,75,100} and
+    the generic one otherwise; both must reproduce the oracle's intervals exactly (N, multi-sequence
+    genomes, probes hanging off both ends, cover extension)."""
+    O = _oracle()
+    rng = random.Random(pl * 100 + m)
+    groups = helpers.random_groups(rng, n_groups=1, anc_len=(400, 900), max_genomes=8)
+    genomes = groups[0]
+    seqs = [s for g in genomes for s in g]
+    probe_strs = [x for x in dict.fromkeys(helpers.tile_candidates(seqs, pl, 20)) if len(x) >= 20]
+    # probes that overhang: built from sequence ends plus random tails
+    for s in seqs[:4]:
+        if len(s) >= 40:
+            tail = ''.join(rng.choice('ACGT') for _ in range(pl - 40))
+            probe_strs.append((tail + s[:40])[:pl])
+            probe_strs.append((s[-40:] + tail)[:pl])
+    params = dict(mismatches=m, lcf_thres=lcf, island_of_exact_match=rng.choice([0, 0, 15]),
+                  cover_extension=rng.choice([0, 50]), kmer_probe_map_k=20)
+    np.random.seed(pl + m)
+    k, seeds, mode = O.choose_seeds(probe_strs, m, lcf, min_k=20, k=20)
+    sm = O.SeedMap(probe_strs, seeds, k)
+    want = O.make_sets_quads(sm, genomes, m, lcf, params['island_of_exact_match'], params['cover_extension'])
+    np.random.seed(pl + m)
+    got, cover, st = _device_quads(ctx, probe_strs, genomes, params)
+    cover.free()
+    assert len(want) > 0
+    assert np.array_equal(got, want), (k, mode)
