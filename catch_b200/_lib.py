@@ -41,6 +41,7 @@ class Stats(C.Structure):
 EXPORTED_SYMBOLS = [
     'cb_init', 'cb_destroy', 'cb_last_error', 'cb_version', 'cb_flush_l2',
     'cb_upload_targets', 'cb_targets_free', 'cb_upload_probes', 'cb_probes_free',
+    'cb_probes_have_duplicates', 'cb_mt19937_randint',
     'cb_coverage', 'cb_cover_free', 'cb_cover_num_intervals', 'cb_cover_export', 'cb_cover_import',
     'cb_setcover', 'cb_minhash_neardup', 'cb_hamming_neardup',
 ]
@@ -72,6 +73,8 @@ def load():
     L.cb_upload_probes.argtypes = [vp, vp, vp, i64, vp, i32, C.POINTER(vp), C.POINTER(Stats)]
     L.cb_probes_free.argtypes = [vp]
     L.cb_probes_free.restype = None
+    L.cb_probes_have_duplicates.argtypes = [vp, vp, C.POINTER(i32)]
+    L.cb_mt19937_randint.argtypes = [vp, C.POINTER(i32), C.c_uint32, i64, vp]
     L.cb_coverage.argtypes = [vp, vp, vp, C.POINTER(HybParams), vp, vp, C.POINTER(vp), C.POINTER(Stats)]
     L.cb_cover_free.argtypes = [vp]
     L.cb_cover_free.restype = None
@@ -137,6 +140,11 @@ class Context:
         self._check(self.L.cb_upload_probes(self.h, _ptr(ascii_u8), _ptr(probe_off), len(probe_off) - 1,
                                             _ptr(lut), bits, C.byref(out), C.byref(st)))
         return Handle(self.L.cb_probes_free, out), st
+
+    def probes_have_duplicates(self, probes):
+        flag = C.c_int32()
+        self._check(self.L.cb_probes_have_duplicates(self.h, probes.h, C.byref(flag)))
+        return bool(flag.value)
 
     # ---- stage A
     def coverage(self, probes, targets, mismatches, lcf_thres, island, cover_extension, k,
@@ -226,3 +234,21 @@ def default_context():
     if _default_ctx is None:
         _default_ctx = Context()
     return _default_ctx
+
+
+def legacy_randint(bound, shape):
+    """np.random.randint(0, bound, size=shape) on numpy's legacy global stream, generated by the
+    library's MT19937 replay (same values, same final state, a fraction of the time)."""
+    L = load()
+    name, key, pos, has_gauss, cached = np.random.get_state()
+    if name != 'MT19937':
+        return np.random.randint(0, bound, size=shape)
+    key = np.ascontiguousarray(key, dtype=np.uint32).copy()
+    n = int(np.prod(shape))
+    out = np.empty(n, dtype=np.int32)
+    p = C.c_int32(int(pos))
+    rc = L.cb_mt19937_randint(key.ctypes.data, C.byref(p), int(bound), n, out.ctypes.data)
+    if rc != 0:
+        raise CatchB200Error(rc, 'cb_mt19937_randint')
+    np.random.set_state((name, key, p.value, has_gauss, cached))
+    return out.reshape(shape)

@@ -105,11 +105,14 @@ class SeedPlan:
     handed to cb_coverage as a CSR.  Drawing is separate from the device call so that a rank
     which does not own a grouping can still advance the RNG stream identically."""
 
-    def __init__(self, probe_strs, mismatches, lcf_thres, kmer_probe_map_k):
-        lengths = np.fromiter((len(s) for s in probe_strs), dtype=np.int64, count=len(probe_strs))
+    def __init__(self, probe_strs, mismatches, lcf_thres, kmer_probe_map_k, lengths=None, may_have_dups=True):
+        if lengths is None:
+            lengths = np.fromiter((len(s) for s in probe_strs), dtype=np.int64, count=len(probe_strs))
         self.k, seeds, self.mode = probe_mod.choose_seed_positions(
-            lengths, mismatches, lcf_thres, min_k=kmer_probe_map_k, k=kmer_probe_map_k)
-        self.rep = dedup_map(probe_strs)
+            lengths, mismatches, lcf_thres, min_k=kmer_probe_map_k, k=kmer_probe_map_k,
+            randint=_lib.legacy_randint)
+        # may_have_dups=False: the device already established that all probes are distinct
+        self.rep = dedup_map(probe_strs) if may_have_dups else None
         self.seed_off, self.seed_pos = seeds_to_csr(np.asarray(seeds), self.rep)
 
 

@@ -247,6 +247,60 @@ void cb_probes_free(cb_probes *p)
     delete p;
 }
 
+// ---- MT19937 replay (host only) -----------------------------------------------------------
+static inline void mt19937_gen(uint32_t *mt)
+{
+    const uint32_t UPPER = 0x80000000u, LOWER = 0x7fffffffu, MATRIX_A = 0x9908b0dfu;
+    int kk;
+    uint32_t y;
+    for (kk = 0; kk < 624 - 397; kk++) {
+        y = (mt[kk] & UPPER) | (mt[kk + 1] & LOWER);
+        mt[kk] = mt[kk + 397] ^ (y >> 1) ^ ((y & 1u) ? MATRIX_A : 0u);
+    }
+    for (; kk < 623; kk++) {
+        y = (mt[kk] & UPPER) | (mt[kk + 1] & LOWER);
+        mt[kk] = mt[kk + (397 - 624)] ^ (y >> 1) ^ ((y & 1u) ? MATRIX_A : 0u);
+    }
+    y = (mt[623] & UPPER) | (mt[0] & LOWER);
+    mt[623] = mt[396] ^ (y >> 1) ^ ((y & 1u) ? MATRIX_A : 0u);
+}
+
+int cb_mt19937_randint(uint32_t *key, int32_t *pos, uint32_t bound, int64_t n, int32_t *out)
+{
+    if (!key || !pos || !out || bound == 0 || n < 0 || *pos < 0 || *pos > 624) return CB_ERR_ARG;
+    const uint32_t rng = bound - 1;            // inclusive upper value
+    if (rng == 0) {                            // numpy draws nothing when the range is a single value
+        for (int64_t i = 0; i < n; i++) out[i] = 0;
+        return CB_OK;
+    }
+    uint32_t mask = rng;
+    mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+    int p = *pos;
+    for (int64_t i = 0; i < n; i++) {
+        uint32_t val;
+        do {
+            if (p == 624) { mt19937_gen(key); p = 0; }
+            uint32_t y = key[p++];
+            y ^= (y >> 11);
+            y ^= (y << 7) & 0x9d2c5680u;
+            y ^= (y << 15) & 0xefc60000u;
+            y ^= (y >> 18);
+            val = y & mask;
+        } while (val > rng);
+        out[i] = (int32_t)val;
+    }
+    *pos = p;
+    return CB_OK;
+}
+
+int cb_probes_have_duplicates(cb_ctx *ctx, const cb_probes *probes, int32_t *has_dup)
+{
+    if (!ctx || !probes || !has_dup) return cb_fail(ctx, CB_ERR_ARG, "null argument");
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cb_tls_stream = ctx->stream;
+    return cb_probes_have_duplicates_impl(ctx, probes, has_dup);
+}
+
 int cb_coverage(cb_ctx *ctx, const cb_probes *probes, const cb_targets *targets, const cb_hyb_params *params,
                 const int64_t *seed_off, const int32_t *seed_pos, cb_cover **out, cb_stats *stats)
 {

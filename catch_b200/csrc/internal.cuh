@@ -167,6 +167,8 @@ int cb_launch_pack_targets(cb_ctx *ctx, const uint8_t *d_ascii, int64_t total, c
 int cb_launch_pack_probes(cb_ctx *ctx, const uint8_t *d_ascii, const int64_t *d_off, int64_t n_probes,
                           const uint8_t *d_lut, int bits, int nw, uint64_t *d_words, int32_t *d_len);
 
+int cb_probes_have_duplicates_impl(cb_ctx *ctx, const cb_probes *probes, int32_t *has_dup);
+
 // coverage.cu
 int cb_coverage_impl(cb_ctx *ctx, const cb_probes *probes, const cb_targets *targets,
                      const cb_hyb_params *params, const int64_t *seed_off, const int32_t *seed_pos,

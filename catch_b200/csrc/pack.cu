@@ -95,3 +95,57 @@ int cb_launch_pack_probes(cb_ctx *ctx, const uint8_t *d_ascii, const int64_t *d_
     CB_CUDA(ctx, cudaGetLastError());
     return CB_OK;
 }
+
+
+// ---- duplicate detection: 64-bit hash of every packed probe into an open-addressing table
+namespace {
+__global__ void dup_probe_kernel(const uint64_t *__restrict__ words, const int32_t *__restrict__ lens,
+                                 int64_t n_probes, int wpp, unsigned long long *__restrict__ table,
+                                 uint32_t mask, int *__restrict__ flag)
+{
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_probes;
+         p += (int64_t)gridDim.x * blockDim.x) {
+        unsigned long long h = 0x9E3779B97F4A7C15ull ^ (unsigned long long)lens[p];
+        for (int w = 0; w < wpp; w++) {
+            h ^= words[p * wpp + w];
+            h *= 0xBF58476D1CE4E5B9ull;
+            h ^= h >> 31;
+        }
+        if (h == 0ull) h = 1ull;
+        uint32_t slot = (uint32_t)(h >> 13) & mask;
+        for (;;) {
+            const unsigned long long prev = atomicCAS(&table[slot], 0ull, h);
+            if (prev == 0ull) break;
+            if (prev == h) { *flag = 1; break; }
+            slot = (slot + 1) & mask;
+        }
+    }
+}
+}  // namespace
+
+int cb_probes_have_duplicates_impl(cb_ctx *ctx, const cb_probes *probes, int32_t *has_dup)
+{
+    *has_dup = 0;
+    const int64_t P = probes->n_probes;
+    if (P < 2) return CB_OK;
+    int64_t cap = 1024;
+    while (cap < 2 * P) cap <<= 1;
+    DevBuf<unsigned long long> table;
+    DevBuf<int> flag;
+    CB_CUDA(ctx, table.alloc((size_t)cap));
+    CB_CUDA(ctx, flag.alloc(1));
+    CB_CUDA(ctx, cudaMemsetAsync(table.p, 0, sizeof(unsigned long long) * (size_t)cap, ctx->stream));
+    CB_CUDA(ctx, cudaMemsetAsync(flag.p, 0, sizeof(int), ctx->stream));
+    int64_t blocks = (P + PACK_THREADS - 1) / PACK_THREADS;
+    if (blocks > (int64_t)ctx->sm_count * 16) blocks = (int64_t)ctx->sm_count * 16;
+    dup_probe_kernel<<<(unsigned)blocks, PACK_THREADS, 0, ctx->stream>>>(probes->d_words, probes->d_len, P,
+                                                                        probes->bits * probes->nw, table.p,
+                                                                        (uint32_t)(cap - 1), flag.p);
+    ctx->launches++;
+    CB_CUDA(ctx, cudaGetLastError());
+    int h = 0;
+    CB_CUDA(ctx, cudaMemcpyAsync(&h, flag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *has_dup = h;
+    return CB_OK;
+}

@@ -44,6 +44,7 @@ struct GreedyParams {
     // incremental mode
     const int64_t *blk_off;        // [n_blocks+1]
     const uint4 *blk_items;        // (start, end, probe, -)
+    const uint2 *ivx;              // per interval: [x0, x1) range of blk_items that can overlap it
     int64_t n_blocks;
     uint32_t max_len;
     unsigned long long *remaining; // total uncovered bits still to cover
@@ -59,6 +60,12 @@ struct GreedyParams {
     int *status;
     unsigned long long *barrier;   // grid barrier arrival counter
     unsigned long long *phase_ns;  // [4] time CTA 0 spent in: argmax, barrier, delta, barrier
+    // candidate list of the incremental kernel
+    uint32_t *list;                // probes whose gain was >= tau when the list was built
+    uint32_t *list_n;
+    uint32_t list_cap;
+    unsigned long long *pub;       // [0] sequence number, [1] message (kind << 32 | probe)
+    unsigned long long *ctr;       // [0] list rebuilds, [1] picks served from a list
 };
 
 // ---- K5: universe = union of all intervals
@@ -132,6 +139,21 @@ __global__ void block_index_kernel(const int64_t *__restrict__ iv_off, const uin
 }
 
 __device__ __forceinline__ uint32_t popcount_range_cg(const unsigned long long *U, uint32_t s, uint32_t e);
+
+// per interval: the contiguous range of indexed items whose start lies in
+// (start - max_len, end), i.e. every interval that can overlap it
+__global__ void item_range_kernel(const uint2 *__restrict__ iv, int64_t n, const int64_t *__restrict__ blk_off,
+                                  int64_t n_blocks, uint32_t max_len, uint2 *__restrict__ ivx)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint2 r = iv[i];
+        const int64_t lo_pos = (int64_t)r.x - (int64_t)max_len + 1;
+        const int64_t b_lo = (lo_pos > 0 ? lo_pos : 0) >> 6;
+        int64_t b_hi = ((int64_t)r.y - 1) >> 6;
+        if (b_hi >= n_blocks) b_hi = n_blocks - 1;
+        ivx[i] = make_uint2((uint32_t)blk_off[b_lo], (uint32_t)blk_off[b_hi + 1]);
+    }
+}
 
 // initial gains: sum over (probe, genome) of min(left_u, |s_u & U_u|)
 __device__ __forceinline__ void recompute_gains(const GreedyParams &G, int64_t gtid, int64_t gsize)
@@ -402,6 +424,305 @@ greedy_kernel(const GreedyParams G)
     }
 }
 
+
+constexpr int APPLY_WORDS = 64;          // winner intervals up to 64 words are staged in shared memory
+
+// apply() for a winner interval longer than APPLY_WORDS*64 positions: same work against L2
+__device__ __forceinline__ void apply_long_interval(const GreedyParams &G, uint2 r, uint2 xr)
+{
+    for (int64_t x = (int64_t)xr.x + threadIdx.x; x < (int64_t)xr.y; x += GREEDY_THREADS) {
+        const uint4 item = __ldg(G.blk_items + x);
+        const uint32_t os = max(item.x, r.x), oe = min(item.y, r.y);
+        if (os < oe) {
+            const uint32_t dlt = popcount_range_cg(G.U, os, oe);
+            if (dlt) atomicSub(&G.gain[item.z], dlt);
+        }
+    }
+    __syncthreads();
+    const uint32_t w0 = r.x >> 6, w1 = (r.y - 1) >> 6;
+    uint32_t c = 0;
+    for (uint32_t wd = w0 + threadIdx.x; wd <= w1; wd += GREEDY_THREADS) {
+        unsigned long long m = ~0ull;
+        if (wd == w0) m &= ~0ull << (r.x & 63);
+        if (wd == w1) m &= ~0ull >> (63 - ((r.y - 1) & 63));
+        const unsigned long long old = atomicAnd(&G.U[wd], ~m);
+        c += __popcll(old & m);
+    }
+    if (c) atomicAdd(G.remaining, (unsigned long long)(-(long long)c));
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------
+// Incremental greedy, one grid-wide rendezvous per pick.
+//
+//   apply(w):  a CTA takes a winner interval: (1) narrow it to the span of its still-uncovered
+//              bits, (2) for every indexed interval overlapping that span subtract the uncovered
+//              bits in the overlap from the owner's gain, (3) __syncthreads, (4) clear the bits.
+//              The bits a CTA reads in (2) lie inside ITS winner interval and winner intervals
+//              are disjoint, so (2) and (4) of different CTAs never interfere: no grid barrier
+//              between "update gains" and "clear U".
+//   pick:      gains only ever decrease.  When a candidate list is built, it holds every probe of
+//              the current rank with gain >= tau; all other probes stay below tau for ever.  As
+//              long as the best CURRENT gain inside the list is >= tau it is the global maximum
+//              (ties broken by the id embedded in the key), so CTA 0 alone finds the next winner
+//              from the list after all CTAs have arrived, and publishes it; the others spin on the
+//              published sequence number.  When the list's best falls below tau the list is
+//              rebuilt with a full argmax + collect pass.
+// ---------------------------------------------------------------------------------------
+constexpr unsigned long long MSG_WINNER = 1, MSG_REBUILD = 2, MSG_DONE = 3;
+
+__device__ __forceinline__ void arrive_only(unsigned long long *counter, unsigned long long &target)
+{
+    __syncthreads();
+    target += gridDim.x;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1ull);
+    }
+}
+
+__global__ void __launch_bounds__(GREEDY_THREADS)
+greedy_inc_kernel(const GreedyParams G)
+{
+    __shared__ unsigned long long s_key[GREEDY_THREADS / 32];
+    __shared__ unsigned long long s_msg;
+    __shared__ unsigned long long s_u[APPLY_WORDS];
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t gsize = (int64_t)gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    int cur_rank = 0;
+    long long n_picks = 0;
+    unsigned long long bar_target = 0, seq = 0, n_rebuilds = 0, n_listed = 0;
+    uint32_t tau = 1;
+    int band_shift = 4;                 // list threshold = gmax - gmax >> band_shift
+    unsigned rb = 0;                    // rebuild counter: selects the argmax slot
+    bool need_rebuild = true;
+    long long w = -1;
+    unsigned long long t_phase[4] = {0, 0, 0, 0}, t_last = 0;
+    const bool timing = (gtid == 0);
+    if (timing) t_last = globaltimer_ns();
+    auto lap = [&](int i) {
+        if (timing) {
+            const unsigned long long t = globaltimer_ns();
+            t_phase[i] += t - t_last;
+            t_last = t;
+        }
+    };
+    auto block_max = [&](unsigned long long best) -> unsigned long long {
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            const unsigned long long t = __shfl_xor_sync(0xffffffffu, best, o);
+            best = t > best ? t : best;
+        }
+        if (lane == 0) s_key[warp] = best;
+        __syncthreads();
+        best = lane < GREEDY_THREADS / 32 ? s_key[lane] : 0ull;
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            const unsigned long long t = __shfl_xor_sync(0xffffffffu, best, o);
+            best = t > best ? t : best;
+        }
+        __syncthreads();
+        return best;                    // valid in every thread of warp 0 (and all warps: same reduction)
+    };
+
+    for (unsigned it = 0;; it++) {
+        if (need_rebuild) {
+            // ---- full argmax over the current rank
+            unsigned long long best = 0;
+            for (int64_t p = gtid; p < G.n_probes; p += gsize) {
+                const uint32_t g = __ldcg(&G.gain[p]);
+                if (g && G.rank_idx[p] == (uint32_t)cur_rank) {
+                    const unsigned long long key = ((unsigned long long)g << 32) | (unsigned long long)(0xffffffffu - (uint32_t)p);
+                    best = key > best ? key : best;
+                }
+            }
+            best = block_max(best);
+            const unsigned slot_k = rb & 1u;
+            rb++;
+            if (threadIdx.x == 0 && best) atomicMax(&G.key[slot_k], best);
+            if (gtid == 0) *G.list_n = 0;
+            grid_barrier(G.barrier, bar_target);
+            if (__ldcg(G.remaining) == 0ull) break;
+            const unsigned long long key = __ldcg(&G.key[slot_k]);
+            if (gtid == 0) G.key[slot_k ^ 1u] = 0ull;
+            if (key == 0ull) {                  // rank exhausted (:522-526)
+                cur_rank++;
+                if (cur_rank >= G.n_ranks) {
+                    if (gtid == 0) *G.status = CB_ERR_STATE;
+                    break;
+                }
+                grid_barrier(G.barrier, bar_target);
+                continue;
+            }
+            w = (long long)(0xffffffffu - (uint32_t)(key & 0xffffffffull));
+            const uint32_t gmax = (uint32_t)(key >> 32);
+            // ---- collect the candidate list: everything within a band below the maximum
+            for (;;) {
+                const uint32_t band = gmax >> band_shift;
+                tau = gmax - band;
+                if (tau < 1u) tau = 1u;
+                for (int64_t p = gtid; p < G.n_probes; p += gsize) {
+                    const uint32_t g = __ldcg(&G.gain[p]);
+                    if (g >= tau && G.rank_idx[p] == (uint32_t)cur_rank) {
+                        const uint32_t slot = atomicAdd(G.list_n, 1u);
+                        if (slot < G.list_cap) G.list[slot] = (uint32_t)p;
+                    }
+                }
+                grid_barrier(G.barrier, bar_target);
+                const uint32_t n = __ldcg(G.list_n);
+                if (n <= G.list_cap) {
+                    // aim for a few hundred candidates: widen the band when the list is short
+                    if (n < G.list_cap / 16 && band_shift > 1) band_shift--;
+                    break;
+                }
+                // too many candidates: everyone has read n; empty the list and narrow the band
+                grid_barrier(G.barrier, bar_target);
+                if (gtid == 0) *G.list_n = 0;
+                grid_barrier(G.barrier, bar_target);
+                if (band == 0u) {
+                    // more than list_cap probes tie at the maximum: run without a list
+                    // (the empty list forces a full argmax for every pick)
+                    tau = 0xffffffffu;
+                    break;
+                }
+                band_shift++;
+            }
+            need_rebuild = false;
+            n_rebuilds++;
+            lap(0);
+        }
+
+        // ---- apply the pick w
+        if (gtid == 0) G.sel[n_picks] = w;
+        n_picks++;
+        {
+            const int64_t i0 = G.iv_off[w], i1 = G.iv_off[w + 1];
+            for (int64_t i = i0 + blockIdx.x; i < i1; i += gridDim.x) {
+                const uint2 r = G.iv[i];
+                const uint2 xr = G.ivx[i];
+                if (r.x >= r.y) continue;
+                const uint32_t w0 = r.x >> 6, w1 = (r.y - 1) >> 6;
+                const uint32_t nwords = w1 - w0 + 1;
+                if (nwords > (uint32_t)APPLY_WORDS) {         // very long interval: L2 path (CTA-uniform)
+                    apply_long_interval(G, r, xr);
+                    continue;
+                }
+                // the winner interval's still-uncovered bits, staged in shared memory: they are what
+                // every overlap is counted against AND exactly what has to be cleared afterwards
+                unsigned long long mine = 0ull;
+                if (threadIdx.x < nwords) {
+                    unsigned long long m = ~0ull;
+                    const uint32_t wd = w0 + threadIdx.x;
+                    if (wd == w0) m &= ~0ull << (r.x & 63);
+                    if (wd == w1) m &= ~0ull >> (63 - ((r.y - 1) & 63));
+                    mine = __ldcg(G.U + wd) & m;
+                    s_u[threadIdx.x] = mine;
+                }
+                // candidate items are fetched while the bits are in flight
+                constexpr int BATCH = 4;
+                const int64_t x0 = xr.x, x1 = xr.y;
+                uint4 item[BATCH];
+#pragma unroll
+                for (int u = 0; u < BATCH; u++) {
+                    const int64_t x = x0 + threadIdx.x + (int64_t)u * GREEDY_THREADS;
+                    item[u] = x < x1 ? __ldg(G.blk_items + x) : make_uint4(0u, 0u, 0u, 0u);
+                }
+                const int any = __syncthreads_or(mine != 0ull);
+                if (any) {
+                    int64_t xb = x0 + threadIdx.x;
+                    for (;;) {
+#pragma unroll
+                        for (int u = 0; u < BATCH; u++) {
+                            const uint32_t os = max(item[u].x, r.x), oe = min(item[u].y, r.y);
+                            if (os < oe) {
+                                const uint32_t wa = (os >> 6) - w0, wb = ((oe - 1) >> 6) - w0;
+                                uint32_t dlt = 0;
+                                for (uint32_t q = wa; q <= wb; q++) {
+                                    unsigned long long m = ~0ull;
+                                    if (q == wa) m &= ~0ull << (os & 63);
+                                    if (q == wb) m &= ~0ull >> (63 - ((oe - 1) & 63));
+                                    dlt += __popcll(s_u[q] & m);
+                                }
+                                if (dlt) atomicSub(&G.gain[item[u].z], dlt);
+                            }
+                        }
+                        xb += (int64_t)GREEDY_THREADS * BATCH;
+                        if (xb - threadIdx.x >= x1) break;          // CTA-uniform
+#pragma unroll
+                        for (int u = 0; u < BATCH; u++) {
+                            const int64_t x = xb + (int64_t)u * GREEDY_THREADS;
+                            item[u] = x < x1 ? __ldg(G.blk_items + x) : make_uint4(0u, 0u, 0u, 0u);
+                        }
+                    }
+                    // clear exactly the bits that were set (nobody else touches this range)
+                    if (mine) {
+                        atomicAnd(&G.U[w0 + threadIdx.x], ~mine);
+                        atomicAdd(G.remaining, (unsigned long long)(-(long long)__popcll(mine)));
+                    }
+                }
+                __syncthreads();                             // s_u is reused by the next interval
+            }
+        }
+        lap(2);
+
+        // ---- rendezvous: everyone arrives, CTA 0 picks from the list and publishes
+        arrive_only(G.barrier, bar_target);
+        seq++;
+        if (blockIdx.x == 0) {
+            if (threadIdx.x == 0) {
+                while (*(volatile unsigned long long *)G.barrier < bar_target) { }
+                __threadfence();
+            }
+            __syncthreads();
+            const uint32_t n = __ldcg(G.list_n);
+            unsigned long long best = 0;
+            for (uint32_t i = threadIdx.x; i < n; i += GREEDY_THREADS) {
+                const uint32_t p = G.list[i];
+                const uint32_t g = __ldcg(&G.gain[p]);
+                if (g) {
+                    const unsigned long long key = ((unsigned long long)g << 32) | (unsigned long long)(0xffffffffu - p);
+                    best = key > best ? key : best;
+                }
+            }
+            best = block_max(best);
+            if (threadIdx.x == 0) {
+                unsigned long long msg;
+                if (__ldcg(G.remaining) == 0ull) msg = MSG_DONE << 32;
+                else if ((uint32_t)(best >> 32) >= tau) msg = (MSG_WINNER << 32) | (unsigned long long)(0xffffffffu - (uint32_t)(best & 0xffffffffull));
+                else msg = MSG_REBUILD << 32;
+                G.pub[1] = msg;
+                __threadfence();
+                *(volatile unsigned long long *)G.pub = seq;
+                s_msg = msg;
+            }
+            __syncthreads();
+        } else {
+            if (threadIdx.x == 0) {
+                while (*(volatile unsigned long long *)G.pub < seq) { }
+                __threadfence();
+                s_msg = *(volatile unsigned long long *)(G.pub + 1);
+            }
+            __syncthreads();
+        }
+        const unsigned long long msg = s_msg;
+        __syncthreads();
+        lap(3);
+        const unsigned long long kind = msg >> 32;
+        if (kind == MSG_DONE) break;
+        if (kind == MSG_REBUILD) { need_rebuild = true; continue; }
+        w = (long long)(uint32_t)(msg & 0xffffffffull);
+        n_listed++;
+    }
+    if (gtid == 0) {
+        *G.n_sel = n_picks;
+        for (int i = 0; i < 4; i++) G.phase_ns[i] = t_phase[i];
+        G.ctr[0] = n_rebuilds;
+        G.ctr[1] = n_listed;
+    }
+}
+
 }  // namespace
 
 int cb_setcover_impl(cb_ctx *ctx, const cb_cover *cover, const int32_t *ranks, const double *universe_p,
@@ -423,13 +744,15 @@ int cb_setcover_impl(cb_ctx *ctx, const cb_cover *cover, const int32_t *ranks, c
     const int wide = ctx->sm_count * 8;
     const int64_t u_words = cover->universe_bits >> 6;
 
-    DevBuf<unsigned long long> d_U, d_key, d_remaining, d_barrier;
+    DevBuf<unsigned long long> d_U, d_key, d_remaining, d_barrier, d_pub;
+    DevBuf<uint32_t> d_list;
     DevBuf<long long> d_usize, d_uncov, d_sel, d_nsel;
     DevBuf<uint32_t> d_gain, d_rank, d_ivg, d_bcount, d_bcursor;
     DevBuf<unsigned int> d_nleft;
     DevBuf<int> d_status;
     DevBuf<int64_t> d_boff;
     DevBuf<uint4> d_items;
+    DevBuf<uint2> d_ivx;
     CB_CUDA(ctx, d_U.alloc((size_t)u_words + 1));
     CB_CUDA(ctx, cudaMemsetAsync(d_U.p, 0, sizeof(unsigned long long) * ((size_t)u_words + 1), st));
     CB_CUDA(ctx, d_usize.alloc((size_t)NG));
@@ -512,6 +835,16 @@ int cb_setcover_impl(cb_ctx *ctx, const cb_cover *cover, const int32_t *ranks, c
     G.status = d_status.p;
     G.barrier = d_barrier.p;
     G.phase_ns = d_barrier.p + 1;
+    const uint32_t list_cap = 4096;
+    CB_CUDA(ctx, d_list.alloc(list_cap + 1));
+    CB_CUDA(ctx, d_pub.alloc(8));
+    CB_CUDA(ctx, cudaMemsetAsync(d_pub.p, 0, sizeof(unsigned long long) * 8, st));
+    CB_CUDA(ctx, cudaMemsetAsync(d_list.p, 0, sizeof(uint32_t) * (list_cap + 1), st));
+    G.list = d_list.p;
+    G.list_n = d_list.p + list_cap;
+    G.list_cap = list_cap;
+    G.pub = d_pub.p;
+    G.ctr = d_pub.p + 4;
 
     if (full_mode) {
         CB_CUDA(ctx, d_ivg.alloc((size_t)E));
@@ -532,16 +865,24 @@ int cb_setcover_impl(cb_ctx *ctx, const cb_cover *cover, const int32_t *ranks, c
         block_index_kernel<true><<<wide, 256, 0, st>>>(cover->d_iv_off, cover->d_iv, P, nullptr, d_boff.p, d_bcursor.p, d_items.p);
         gains_init_kernel<<<wide, 256, 0, st>>>(cover->d_iv_off, cover->d_iv, P, d_gain.p);
         ctx->launches += 2;
+        if (E >= 0xfffffff0ll) return cb_fail(ctx, CB_ERR_UNSUPPORTED, "more than 2^32 intervals in one grouping");
+        CB_CUDA(ctx, d_ivx.alloc((size_t)E));
+        item_range_kernel<<<wide, 256, 0, st>>>(cover->d_iv, E, d_boff.p, n_blocks, cover->max_interval_len, d_ivx.p);
+        ctx->launches++;
         G.blk_off = d_boff.p;
         G.blk_items = d_items.p;
         G.n_blocks = n_blocks;
+        G.ivx = d_ivx.p;
     }
     CB_CUDA(ctx, cudaGetLastError());
     t_uni.stop();
 
     // ---- persistent cooperative launch: as many co-resident blocks as the device allows
+    const bool legacy = full_mode || (getenv("CB_GREEDY_LEGACY") && getenv("CB_GREEDY_LEGACY")[0] == '1');
+    void *kernel = legacy ? (void *)greedy_kernel : (void *)greedy_inc_kernel;
     int per_sm = 0;
-    CB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, greedy_kernel, GREEDY_THREADS, 0));
+    if (legacy) CB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, greedy_kernel, GREEDY_THREADS, 0));
+    else CB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, greedy_inc_kernel, GREEDY_THREADS, 0));
     if (per_sm < 1) return cb_fail(ctx, CB_ERR_CUDA, "greedy kernel does not fit on an SM");
     int want = 2;
     if (const char *e = getenv("CB_GREEDY_BLOCKS_PER_SM")) want = atoi(e) > 0 ? atoi(e) : want;
@@ -549,15 +890,16 @@ int cb_setcover_impl(cb_ctx *ctx, const cb_cover *cover, const int32_t *ranks, c
     const int grid = per_sm * ctx->sm_count;
     void *args[] = {(void *)&G};
     t_greedy.start();
-    CB_CUDA(ctx, cudaLaunchCooperativeKernel((void *)greedy_kernel, dim3(grid), dim3(GREEDY_THREADS), args, 0, st));
+    CB_CUDA(ctx, cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(GREEDY_THREADS), args, 0, st));
     ctx->launches++;
     t_greedy.stop();
     t_all.stop();
 
     long long h_nsel = 0;
     int h_status = 0;
-    unsigned long long h_phase[4] = {0, 0, 0, 0};
+    unsigned long long h_phase[4] = {0, 0, 0, 0}, h_ctr[2] = {0, 0};
     CB_CUDA(ctx, cudaMemcpyAsync(h_phase, d_barrier.p + 1, sizeof h_phase, cudaMemcpyDeviceToHost, st));
+    CB_CUDA(ctx, cudaMemcpyAsync(h_ctr, d_pub.p + 4, sizeof h_ctr, cudaMemcpyDeviceToHost, st));
     CB_CUDA(ctx, cudaMemcpyAsync(&h_nsel, d_nsel.p, sizeof h_nsel, cudaMemcpyDeviceToHost, st));
     CB_CUDA(ctx, cudaMemcpyAsync(&h_status, d_status.p, sizeof h_status, cudaMemcpyDeviceToHost, st));
     CB_CUDA(ctx, cudaStreamSynchronize(st));
@@ -575,7 +917,9 @@ int cb_setcover_impl(cb_ctx *ctx, const cb_cover *cover, const int32_t *ranks, c
         stats->n_picks = h_nsel;
         stats->n_intervals = E;
         stats->n_kernel_launches = ctx->launches;
-        for (int i = 0; i < 4; i++) stats->reserved[i] = (int64_t)h_phase[i];   // ns: argmax, barrier, delta, barrier
+        for (int i = 0; i < 4; i++) stats->reserved[i] = (int64_t)h_phase[i];   // ns: argmax/rebuild, barrier, apply, rendezvous
+        stats->reserved[4] = (int64_t)h_ctr[0];      // candidate-list rebuilds
+        stats->reserved[5] = (int64_t)h_ctr[1];      // picks served from a list
     }
     return CB_OK;
 }

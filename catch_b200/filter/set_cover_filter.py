@@ -169,15 +169,23 @@ class SetCoverFilter(BaseFilter):
             # The seed draws consume numpy's global RNG per grouping, in grouping order, first for
             # _make_sets and then for _make_ranks (set_cover_filter.py:824-827); every rank replays
             # all of them so that a sharded run sees the same stream as a single process.
+            mine = owner[group_i] == rank
+            group = None
+            lengths, dups = None, True
+            if mine and probe_strs:
+                group = cov.PackedGroup(self._context(), probe_strs, target_genomes)
+                lengths = np.diff(group.probe_off)
+                dups = self._context().probes_have_duplicates(group.probes)
             plan = plan_tol = None
             if probe_strs:
-                plan = cov.SeedPlan(probe_strs, self.mismatches, self.lcf_thres, self.kmer_probe_map_k)
+                plan = cov.SeedPlan(probe_strs, self.mismatches, self.lcf_thres, self.kmer_probe_map_k,
+                                    lengths=lengths, may_have_dups=dups and mine)
                 if self._needs_ranks():
                     plan_tol = cov.SeedPlan(probe_strs, self.mismatches_tolerant, self.lcf_thres_tolerant,
-                                            self.kmer_probe_map_k)
-            if owner[group_i] != rank:
+                                            self.kmer_probe_map_k, lengths=lengths, may_have_dups=dups and mine)
+            if not mine:
                 continue
-            local[group_i] = self._select_for_group(group_i, len(input), probe_strs, plan, plan_tol,
+            local[group_i] = self._select_for_group(group_i, len(input), probe_strs, group, plan, plan_tol,
                                                     target_genomes, target_genomes_grouped)
         chosen_per_group = parallel.exchange_group_results(local, owner, rank) if sharded else \
             [local[i] for i in range(len(input))]
@@ -187,7 +195,7 @@ class SetCoverFilter(BaseFilter):
             selected.append([possible_probes[i] for i in chosen])
         return selected
 
-    def _select_for_group(self, group_i, n_groups, probe_strs, plan, plan_tol, target_genomes,
+    def _select_for_group(self, group_i, n_groups, probe_strs, group, plan, plan_tol, target_genomes,
                           target_genomes_grouped):
         """Indices (into the grouping's probe list) of the selected probes, in the reference's
         output order."""
@@ -200,7 +208,6 @@ class SetCoverFilter(BaseFilter):
             return []
         logger.info("Computing coverage of %d probes in %d genomes (group %d of %d)",
                     len(probe_strs), len(target_genomes), group_i + 1, n_groups)
-        group = cov.PackedGroup(ctx, probe_strs, target_genomes)
         try:
             cover, st_a = cov.compute_cover(ctx, group, plan, self.mismatches, self.lcf_thres,
                                             self.island_of_exact_match, self.cover_extension)

@@ -110,7 +110,8 @@ def pigeonhole_kmer_length(probe_length, mismatches, min_k):
     return k
 
 
-def choose_seed_positions(lengths, mismatches, lcf_thres, min_k=20, k=20, num_kmers_per_probe=20):
+def choose_seed_positions(lengths, mismatches, lcf_thres, min_k=20, k=20, num_kmers_per_probe=20,
+                          randint=None):
     """Seed start positions for every probe of a list, as the reference would select them.
 
     Args:
@@ -124,7 +125,8 @@ def choose_seed_positions(lengths, mismatches, lcf_thres, min_k=20, k=20, num_km
     k < min_k (:574-577).  Random mode draws, per probe in list order,
     np.random.choice(L - k + 1, size=20, replace=True) from numpy's legacy global stream
     (probe.py:386-398).  For a run of probes of equal length that is the same stream as one
-    np.random.randint(0, L - k + 1, size=(run, 20)) call, which is what is used here.
+    np.random.randint(0, L - k + 1, size=(run, 20)) call, which is what is used here; `randint`
+    may supply a faster generator of the same stream (catch_b200._lib.legacy_randint).
     """
     lengths = np.asarray(lengths, dtype=np.int64)
     n = len(lengths)
@@ -148,5 +150,8 @@ def choose_seed_positions(lengths, mismatches, lcf_thres, min_k=20, k=20, num_km
     ends = np.concatenate((change, [n]))
     for s, e in zip(starts, ends):
         span = int(lengths[s]) - k + 1
-        seeds[s:e] = np.random.randint(0, span, size=(e - s, num_kmers_per_probe))
+        if randint is None:
+            seeds[s:e] = np.random.randint(0, span, size=(e - s, num_kmers_per_probe))
+        else:
+            seeds[s:e] = randint(span, (e - s, num_kmers_per_probe))
     return k, seeds, 'random'

@@ -105,6 +105,18 @@ int cb_upload_probes(cb_ctx *ctx, const uint8_t *ascii, const int64_t *probe_off
                      const uint8_t lut[256], int32_t bits, cb_probes **out, cb_stats *stats);
 void cb_probes_free(cb_probes *p);
 
+/* 1 in *has_dup if two probes may have the same sequence (decided from a 64-bit hash of the
+ * packed probe: equal sequences always report 1, distinct ones almost never).  Lets the host skip
+ * its duplicate bookkeeping (filter/set_cover_filter.py:408-412) in the common duplicate-free case. */
+int cb_probes_have_duplicates(cb_ctx *ctx, const cb_probes *probes, int32_t *has_dup);
+
+/* Host-side helper (no device work): continue numpy's legacy MT19937 stream exactly as
+ * RandomState.randint(0, bound, size=n) / np.random.choice(bound, n) would (masked rejection
+ * sampling on 32-bit outputs, numpy/random/src/distributions/distributions.c), so the seed draws of
+ * probe.py:393-396 can be replayed without per-probe Python overhead.  key[624]/pos are the state
+ * from np.random.get_state() and are updated in place. */
+int cb_mt19937_randint(uint32_t *key, int32_t *pos, uint32_t bound, int64_t n, int32_t *out);
+
 /* ---- stage A: coverage (K2-K4) -----------------------------------------------------
  * Replaces SetCoverFilter._make_sets (filter/set_cover_filter.py:359-470), i.e.
  * probe.SharedKmerProbeMap.construct (probe.py:684-763) + open_probe_finding_pool +

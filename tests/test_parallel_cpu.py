@@ -34,12 +34,30 @@ def _worker(rank, world_size, port, out_path):
     dist.init_process_group('gloo', rank=rank, world_size=world_size)
     computed = []
 
-    def fake_select(self, group_i, n_groups, probe_strs, plan, plan_tol, target_genomes, all_genomes):
+    def fake_select(self, group_i, n_groups, probe_strs, group, plan, plan_tol, target_genomes, all_genomes):
         computed.append(group_i)
         # deterministic stand-in for the device result: depends on the drawn seeds
         return [int(x) % max(1, len(probe_strs)) for x in plan.seed_pos[:3]]
 
     SetCoverFilter._select_for_group = fake_select
+
+    # no device in this test: stand-ins for the packed group and the context
+    from catch_b200 import coverage as cov
+
+    class FakeGroup:
+        def __init__(self, ctx, probe_strs, genomes):
+            self.probe_off = np.concatenate(([0], np.cumsum([len(s) for s in probe_strs]))).astype(np.int64)
+            self.probes = None
+
+        def free(self):
+            pass
+
+    class FakeCtx:
+        def probes_have_duplicates(self, probes):
+            return True
+
+    cov.PackedGroup = FakeGroup
+    SetCoverFilter._context = lambda self: FakeCtx()
     rng = random.Random(5)
     groups = [helpers.random_groups(rng, n_groups=1)[0] for _ in range(5)]
     cands = [helpers.tile_candidates([s for g in gens for s in g], 30, 10) for gens in groups]
