@@ -185,6 +185,9 @@ def main():
     ap.add_argument('--workload', default='zika', choices=sorted(WORKLOADS))
     ap.add_argument('--cpu-sample-genomes', type=int, default=60)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--shard', default='groups', choices=['groups', 'probes'],
+                    help='multi-GPU mode: one grouping per GPU (weak scaling, default) or the probes of ONE '
+                         'grouping split over the GPUs with an NCCL all-gather of the coverage (strong scaling)')
     args = ap.parse_args()
     if args.impl == 'b200' and not os.environ.get('CB_BENCH_PROFILING'):
         args.warmup = max(args.warmup, 3)      # timing rule: at least 3 warm-up steps
@@ -210,13 +213,15 @@ def main():
     from catch_b200 import coverage as cov
     from catch_b200.filter.set_cover_filter import SetCoverFilter
 
-    w = make_workload(args.workload, n_groups=world)
+    strong = world > 1 and args.shard == 'probes'
+    os.environ['CB_SHARD'] = args.shard
+    w = make_workload(args.workload, n_groups=1 if strong else world)
     ctx = _lib.Context(local_rank)
     genomes = helpers.to_genomes([[[s] for s in seqs] for seqs in w['groups_seqs']])
     probes = [[probe.Probe.from_str(s) for s in c] for c in w['groups_cands']]
     scf = SetCoverFilter(**w['scf'])
     scf._ctx = ctx
-    my_group = rank if world > 1 else 0          # equal-size groupings: assign_groups gives g -> rank g
+    my_group = rank if (world > 1 and not strong) else 0     # equal-size groupings: assign_groups gives g -> rank g
 
     def barrier():
         if dist is not None:
@@ -233,16 +238,34 @@ def main():
         out = scf.filter(probes, genomes, input_is_grouped=True)
         return time.perf_counter() - t0, out
 
-    # ---- resident: this rank's grouping packed in HBM before the timed region
+    # ---- resident: this rank's grouping (or its block of the probes) packed in HBM before the timed region
     my_cands = w['groups_cands'][my_group]
-    group = cov.PackedGroup(ctx, my_cands, genomes[my_group])
+    if strong:
+        from catch_b200 import parallel
+        parallel.ensure_comm(ctx)
+        lo, hi = parallel.shard_bounds(len(my_cands), world, rank)
+        group = cov.PackedGroup(ctx, my_cands[lo:hi], genomes[my_group])
+    else:
+        lo, hi = 0, len(my_cands)
+        group = cov.PackedGroup(ctx, my_cands, genomes[my_group])
 
     def resident_step():
         np.random.seed(RNG_SEED)
         ctx.flush_l2()
         plan = cov.SeedPlan(my_cands, w['scf']['mismatches'], w['scf']['lcf_thres'], 20)
-        cover, st_a = cov.compute_cover(ctx, group, plan, w['scf']['mismatches'], w['scf']['lcf_thres'], 0,
-                                        w['scf']['cover_extension'])
+        if strong:
+            t0 = time.perf_counter()
+            so = np.ascontiguousarray(plan.seed_off[lo:hi + 1] - plan.seed_off[lo])
+            sp = np.ascontiguousarray(plan.seed_pos[plan.seed_off[lo]:max(plan.seed_off[hi], plan.seed_off[lo] + 1)])
+            local, st_a = ctx.coverage(group.probes, group.targets, w['scf']['mismatches'], w['scf']['lcf_thres'], 0,
+                                       w['scf']['cover_extension'], plan.k, so, sp)
+            tg = time.perf_counter()
+            cover = ctx.cover_allgather(local, lo, len(my_cands))
+            st_a.ms_total += (time.perf_counter() - tg) * 1e3        # the exchange is part of the step
+            local.free()
+        else:
+            cover, st_a = cov.compute_cover(ctx, group, plan, w['scf']['mismatches'], w['scf']['lcf_thres'], 0,
+                                            w['scf']['cover_extension'])
         picks, st_b = ctx.setcover(cover, len(my_cands), None, None)
         cover.free()
         return st_a, st_b, picks
@@ -310,12 +333,14 @@ def main():
         'metric': 'candidate-probe x target-bp / s through SetCoverFilter',
         'value': w['pairs'] / t_res, 'unit': 'pairs/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': t_res * 1e3, 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
-        'config': {'workload': w['desc'] + ('' if world == 1 else ' x %d independent groupings' % world),
+        'scaling': 'strong' if strong else 'weak', 'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
+        'config': {'workload': w['desc'] + ('' if (world == 1 or strong) else ' x %d independent groupings' % world),
                    'P_per_group': P, 'T_bp_per_group': T, 'pairs': w['pairs'], 'intervals': E,
                    'picks': S, 'l2': 'flushed between steps (256 MiB memset)',
                    'parallelism': 'single GPU' if world == 1 else
-                   'one grouping per GPU (independent set-cover instances), no data-path collective'},
+                   ('probes of one grouping split over the GPUs, NCCL all-gather of the coverage, greedy replicated'
+                    if strong else
+                    'one grouping per GPU (independent set-cover instances), no data-path collective')},
         'e2e': {'value': w['pairs'] / t_e2e, 'unit': 'pairs/s', 'ms_per_step': t_e2e * 1e3,
                 'h2d_bytes_per_step': int(scf.last_stats[my_group]['h2d_bytes']) * world,
                 'd2h_bytes_per_step': int(scf.last_stats[my_group]['d2h_bytes']) * world},

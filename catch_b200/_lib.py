@@ -44,6 +44,7 @@ EXPORTED_SYMBOLS = [
     'cb_probes_have_duplicates', 'cb_mt19937_randint',
     'cb_coverage', 'cb_cover_free', 'cb_cover_num_intervals', 'cb_cover_export', 'cb_cover_import',
     'cb_setcover', 'cb_minhash_neardup', 'cb_hamming_neardup',
+    'cb_comm_unique_id', 'cb_comm_init', 'cb_comm_destroy', 'cb_cover_allgather',
 ]
 
 _lib = None
@@ -82,6 +83,10 @@ def load():
     L.cb_cover_num_intervals.restype = i64
     L.cb_cover_export.argtypes = [vp, vp, vp, vp, vp, vp]
     L.cb_cover_import.argtypes = [vp, i64, i32, vp, i64, vp, vp, vp, vp, C.POINTER(vp)]
+    L.cb_comm_unique_id.argtypes = [vp, vp]
+    L.cb_comm_init.argtypes = [vp, vp, i32, i32]
+    L.cb_comm_destroy.argtypes = [vp]
+    L.cb_cover_allgather.argtypes = [vp, vp, i64, i64, C.POINTER(vp)]
     L.cb_setcover.argtypes = [vp, vp, vp, vp, vp, C.POINTER(i64), C.POINTER(Stats)]
     L.cb_minhash_neardup.argtypes = [vp, vp, vp, i64, vp, vp, i32, i32, i32, C.c_double, vp, C.POINTER(Stats)]
     L.cb_hamming_neardup.argtypes = [vp, vp, vp, i64, vp, i32, i32, i32, vp, C.POINTER(Stats)]
@@ -176,6 +181,22 @@ class Context:
                                            _ptr(pid) if len(pid) else None, _ptr(gen) if len(pid) else None,
                                            _ptr(s) if len(pid) else None, _ptr(e) if len(pid) else None,
                                            C.byref(out)))
+        return Handle(self.L.cb_cover_free, out)
+
+    # ---- multi-GPU (probe sharding inside a grouping)
+    def comm_unique_id(self):
+        buf = (C.c_uint8 * 128)()
+        self._check(self.L.cb_comm_unique_id(self.h, buf))
+        return bytes(buf)
+
+    def comm_init(self, unique_id, rank, n_ranks):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        self._check(self.L.cb_comm_init(self.h, buf, rank, n_ranks))
+        self.comm_ready = True
+
+    def cover_allgather(self, local_cover, probe_lo, n_probes_total):
+        out = C.c_void_p()
+        self._check(self.L.cb_cover_allgather(self.h, local_cover.h, probe_lo, n_probes_total, C.byref(out)))
         return Handle(self.L.cb_cover_free, out)
 
     # ---- stage B

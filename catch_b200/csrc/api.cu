@@ -57,6 +57,7 @@ int cb_init(int device_id, cb_ctx **out)
 void cb_destroy(cb_ctx *ctx)
 {
     if (!ctx) return;
+    cb_comm_destroy(ctx);
     if (ctx->flush_buf) cudaFree(ctx->flush_buf);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

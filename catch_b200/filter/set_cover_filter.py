@@ -11,6 +11,7 @@ reference consumes it), duplicate handling, ranks/universe_p bookkeeping and the
 ordering of the output.  Everything else is in libcatchb200.so; there is no CPU fallback.
 """
 import logging
+import os
 import pickle
 import time
 
@@ -157,9 +158,13 @@ class SetCoverFilter(BaseFilter):
     # ------------------------------------------------------------------ the filter
     def _filter(self, input, target_genomes_grouped):
         self.last_stats = [None] * len(input)
-        # multi-GPU: groupings are independent instances; each rank solves the ones it owns
+        # multi-GPU: groupings are independent instances and are sharded over the ranks; when there
+        # are fewer groupings than ranks, the PROBES of each grouping are sharded instead and the
+        # per-probe coverage is all-gathered (parallel.ensure_comm / cb_cover_allgather)
         rank, world_size, _ = parallel.world()
         sharded = parallel.active()
+        if sharded and self._shard_probes(len(input), world_size):
+            return self._filter_probe_sharded(input, target_genomes_grouped, rank, world_size)
         sizes = [len(p) * max(1, sum(g.size() for g in tg)) for p, tg in zip(input, target_genomes_grouped)]
         owner = parallel.assign_groups(sizes, world_size) if sharded else [rank] * len(input)
         local = {}
@@ -193,6 +198,58 @@ class SetCoverFilter(BaseFilter):
         for possible_probes, chosen in zip(input, chosen_per_group):
             possible_probes = list(possible_probes)
             selected.append([possible_probes[i] for i in chosen])
+        return selected
+
+    def _shard_probes(self, n_groups, world_size):
+        mode = os.environ.get('CB_SHARD', 'auto')
+        if mode == 'groups' or self._needs_ranks():
+            return False
+        return mode == 'probes' or n_groups < world_size
+
+    def _filter_probe_sharded(self, input, target_genomes_grouped, rank, world_size):
+        """Every rank works on every grouping: stage A on its block of the probes, all-gather of the
+        coverage over NCCL, then the (identical) greedy selection on every rank."""
+        ctx = self._context()
+        parallel.ensure_comm(ctx)
+        selected = []
+        for group_i, (possible_probes, target_genomes) in enumerate(zip(input, target_genomes_grouped)):
+            possible_probes = list(possible_probes)
+            probe_strs = [p.seq_str for p in possible_probes]
+            t0 = time.perf_counter()
+            stats = {'group': group_i, 'n_probes': len(probe_strs), 'shard': 'probes',
+                     'target_bp': sum(g.size() for g in target_genomes)}
+            self.last_stats[group_i] = stats
+            if not probe_strs:
+                selected.append([])
+                continue
+            plan = cov.SeedPlan(probe_strs, self.mismatches, self.lcf_thres, self.kmer_probe_map_k)
+            lo, hi = parallel.shard_bounds(len(probe_strs), world_size, rank)
+            group = cov.PackedGroup(ctx, probe_strs[lo:hi], target_genomes)
+            try:
+                so = plan.seed_off[lo:hi + 1] - plan.seed_off[lo]
+                sp = plan.seed_pos[plan.seed_off[lo]:max(plan.seed_off[hi], plan.seed_off[lo] + 1)]
+                local, st_a = ctx.coverage(group.probes, group.targets, self.mismatches, self.lcf_thres,
+                                           self.island_of_exact_match, self.cover_extension, plan.k,
+                                           np.ascontiguousarray(so), np.ascontiguousarray(sp))
+            finally:
+                group.free()
+            try:
+                cover = ctx.cover_allgather(local, lo, len(probe_strs))
+            finally:
+                local.free()
+            try:
+                picks, st_b = ctx.setcover(cover, len(probe_strs), None, self._make_universe_p(target_genomes))
+            finally:
+                cover.free()
+            chosen = set()
+            for i in picks.tolist():
+                chosen.add(i)
+            chosen = pickle.loads(pickle.dumps(chosen))
+            selected.append([possible_probes[i] for i in chosen])
+            stats.update(seed_mode=plan.mode, k=plan.k, bits=group.bits, h2d_bytes=group.h2d_bytes,
+                         d2h_bytes=int(picks.nbytes), picks=picks, upload_targets=group.st_targets.as_dict(),
+                         upload_probes=group.st_probes.as_dict(), coverage=st_a.as_dict(),
+                         setcover=st_b.as_dict(), wall_s=time.perf_counter() - t0)
         return selected
 
     def _select_for_group(self, group_i, n_groups, probe_strs, group, plan, plan_tol, target_genomes,

@@ -63,3 +63,24 @@ def active():
     """True when running under an initialised multi-rank process group."""
     dist = _dist()
     return dist is not None and dist.get_world_size() > 1
+
+
+def shard_bounds(n, world_size, rank):
+    """Contiguous block [lo, hi) of n items owned by `rank` (sizes differ by at most one)."""
+    base, extra = divmod(n, world_size)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def ensure_comm(ctx):
+    """Join the NCCL communicator of libcatchb200 (once per context): rank 0 creates the unique
+    id, torch.distributed carries the 128 bytes to the other ranks."""
+    if getattr(ctx, 'comm_ready', False):
+        return
+    dist = _dist()
+    if dist is None:
+        raise RuntimeError("probe sharding needs an initialised torch.distributed process group")
+    rank, world_size = dist.get_rank(), dist.get_world_size()
+    box = [ctx.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    ctx.comm_init(box[0], rank, world_size)

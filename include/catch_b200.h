@@ -159,6 +159,19 @@ int cb_cover_import(cb_ctx *ctx, int64_t n_probes, int32_t n_genomes, const int6
 int cb_setcover(cb_ctx *ctx, const cb_cover *cover, const int32_t *ranks, const double *universe_p,
                 int64_t *sel_ids, int64_t *n_sel, cb_stats *stats);
 
+/* ---- multi-GPU: probe sharding inside one grouping ------------------------------------------
+ * One process per GPU.  Rank 0 obtains an NCCL unique id, the host distributes the 128 bytes to all
+ * ranks (any side channel), every rank joins with cb_comm_init.  Each rank then runs cb_coverage
+ * on ALL targets of the grouping and its own contiguous block of probes
+ * [probe_lo, probe_lo + local_n), and cb_cover_allgather assembles the full cover on every rank
+ * (NCCL broadcasts over NVLink; the only exchange step of the path).  cb_setcover on that cover
+ * gives the same picks on every rank. */
+int cb_comm_unique_id(cb_ctx *ctx, uint8_t out[128]);
+int cb_comm_init(cb_ctx *ctx, const uint8_t id[128], int32_t rank, int32_t n_ranks);
+int cb_comm_destroy(cb_ctx *ctx);
+int cb_cover_allgather(cb_ctx *ctx, const cb_cover *local, int64_t probe_lo, int64_t n_probes_total,
+                       cb_cover **out);
+
 /* ---- near-duplicate filter (K9-K12) --------------------------------------------------
  * Replaces NearDuplicateFilter._filter (filter/near_duplicate_filter.py:47-103) with
  * lsh.NearNeighborLookup (utils/lsh.py:239-320).  `probes` are the DISTINCT probes in
