@@ -322,12 +322,23 @@ def main():
     else:
         alg_bytes = st_a.n_raw_ranges * 16
         dur = kern[dom] / 1e3
+    # measured DRAM traffic of the same kernel on the same workload (one `ncu --set full` capture,
+    # profiles/traffic_r01.json); None for other workloads
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'traffic_r01.json')) as f:
+            tj = json.load(f)
+        if tj.get('workload') == args.workload:
+            traffic = tj['dram_bytes_per_launch'].get('scan_kernel' if dom.startswith('scan') else 'greedy_kernel')
+    except Exception:
+        pass
     peak, peak_src = measured_peak_gbs()
     achieved = alg_bytes / dur / 1e9 if dur > 0 else 0.0
     roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+                'frac': achieved / peak, 'traffic': traffic, 'algorithmic_bytes': alg_bytes, 'peak_source': peak_src,
                 'kernel_ms': {k: round(v, 3) for k, v in kern.items()},
-                'note': 'latency/issue-bound integer path; see DESIGN.md'}
+                'note': 'integer path bound by instruction issue (scan) and by per-pick latency (greedy), not by HBM: '
+                        'operands of a grouping are L2-resident; see DESIGN.md section 5 and profiles/README_r01.md'}
 
     out = {
         'metric': 'candidate-probe x target-bp / s through SetCoverFilter',
