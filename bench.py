@@ -309,11 +309,11 @@ def main():
     E, S = int(st_a.n_intervals), int(st_b.n_picks)
     bits = group.bits
     if dom.startswith('scan'):
-        # per pass  T*bits/8 (target planes) + hits*8 (index entries) + hits*nw*bits*8 (probe words)
-        #            + raw*8 (emitted ranges, emit pass only); two passes
+        # T*planes/8 (target planes) + hits*8 (index entries) + hits*(planes+1)*nw*8
+        # (probe record incl. seed mask) + ranges*16 (emitted ranges); the count-only pre-pass re-reads
+        # the target planes once more
         nw = (w['pl'] + 63) // 64
-        per_pass = T * bits / 8 + st_a.n_candidate_hits * (8 + nw * bits * 8)
-        alg_bytes = 2 * per_pass + st_a.n_raw_ranges * 8
+        alg_bytes = 2 * T * bits / 8 + st_a.n_candidate_hits * (8 + (bits + 1) * nw * 8) + st_a.n_raw_ranges * 16
         dur = kern[dom] / 1e3
     elif dom.startswith('greedy'):
         # S*P*4 (gain vector per pick) + E*16 (index items touched at least once) + 2*U/8
