@@ -358,7 +358,9 @@ def main():
         'gpu_launches': launches * world,
         'clocks': clocks,
         'roofline': roofline,
-        'stages_ms': {'coverage': st_a.as_dict(), 'setcover': st_b.as_dict()},
+        'stages_ms': {'coverage': st_a.as_dict(), 'setcover': st_b.as_dict(),
+                      'e2e_host': {k: round(v, 2) for k, v in scf.last_stats[my_group].get('host_ms', {}).items()},
+                      'e2e_group_wall_ms': round(scf.last_stats[my_group].get('wall_s', 0) * 1e3, 2)},
     }
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:

@@ -277,18 +277,23 @@ int cb_mt19937_randint(uint32_t *key, int32_t *pos, uint32_t bound, int64_t n, i
     uint32_t mask = rng;
     mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
     int p = *pos;
-    for (int64_t i = 0; i < n; i++) {
-        uint32_t val;
-        do {
-            if (p == 624) { mt19937_gen(key); p = 0; }
-            uint32_t y = key[p++];
+    int64_t i = 0;
+    while (i < n) {
+        if (p == 624) { mt19937_gen(key); p = 0; }
+        // rejection sampling over the rest of the current block; the accept is branch-free
+        // (write, then advance only if the value is in range)
+        int j = p;
+        for (; j < 624 && i < n; j++) {
+            uint32_t y = key[j];
             y ^= (y >> 11);
             y ^= (y << 7) & 0x9d2c5680u;
             y ^= (y << 15) & 0xefc60000u;
             y ^= (y >> 18);
-            val = y & mask;
-        } while (val > rng);
-        out[i] = (int32_t)val;
+            const uint32_t val = y & mask;
+            out[i] = (int32_t)val;
+            i += (val <= rng);
+        }
+        p = j;
     }
     *pos = p;
     return CB_OK;

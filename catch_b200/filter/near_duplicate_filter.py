@@ -11,7 +11,9 @@ the Python-set order of the result (:103).  The MinHash inner hash is CPython's 
 reference this is only reproducible under PYTHONHASHSEED=0, which is what the device implements
 (SipHash-1-3 with a zero key).
 """
+import collections
 import math
+import operator
 import random
 
 import numpy as np
@@ -46,22 +48,25 @@ class NearDuplicateFilter(BaseFilter):
         raise NotImplementedError
 
     def _filter(self, input):
-        # multiplicity, descending, stable in first-occurrence order (:61-66)
-        occurrences = {}
-        for p in input:
-            occurrences[p] = occurrences.get(p, 0) + 1
-        order = [p for p, _ in sorted(occurrences.items(), key=lambda kv: kv[1], reverse=True)]
+        # multiplicity, descending, stable in first-occurrence order (:61-66).  Counting runs on the
+        # sequence strings (C speed); the objects returned are the first-seen Probe of each sequence,
+        # as with the reference's dict keyed by Probe.
+        input = list(input)
+        strs = [p.seq_str for p in input]
+        occurrences = collections.Counter(strs)
+        order = [s for s, _ in sorted(occurrences.items(), key=operator.itemgetter(1), reverse=True)]
         if not order:
             # the reference still builds the lookup (and draws its parameters) for empty input
             self._draw_only()
             return []
-        buf, off, _ = cov._concat_ascii([p.seq_str for p in order])
+        first_seen = dict(zip(reversed(strs), reversed(input)))
+        buf, off, _ = cov._concat_ascii(order)
         keep, st = self._draw_and_run(self._context(), buf, off)
         self.last_stats = st.as_dict()
         to_include = set()
-        for p, k in zip(order, keep.tolist()):
+        for s, k in zip(order, keep.tolist()):
             if k:
-                to_include.add(p)
+                to_include.add(first_seen[s])
         return list(to_include)                                   # :103
 
 

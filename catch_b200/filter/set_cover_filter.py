@@ -177,10 +177,20 @@ class SetCoverFilter(BaseFilter):
             mine = owner[group_i] == rank
             group = None
             lengths, dups = None, True
+            host_ms = {}
+            t_mark = time.perf_counter()
+
+            def mark(name):
+                nonlocal t_mark
+                now = time.perf_counter()
+                host_ms[name] = host_ms.get(name, 0.0) + (now - t_mark) * 1e3
+                t_mark = now
             if mine and probe_strs:
                 group = cov.PackedGroup(self._context(), probe_strs, target_genomes)
+                mark('pack_and_upload')
                 lengths = np.diff(group.probe_off)
                 dups = self._context().probes_have_duplicates(group.probes)
+                mark('duplicate_check')
             plan = plan_tol = None
             if probe_strs:
                 plan = cov.SeedPlan(probe_strs, self.mismatches, self.lcf_thres, self.kmer_probe_map_k,
@@ -188,6 +198,8 @@ class SetCoverFilter(BaseFilter):
                 if self._needs_ranks():
                     plan_tol = cov.SeedPlan(probe_strs, self.mismatches_tolerant, self.lcf_thres_tolerant,
                                             self.kmer_probe_map_k, lengths=lengths, may_have_dups=dups and mine)
+                mark('seed_plan')
+            self._host_ms = host_ms
             if not mine:
                 continue
             local[group_i] = self._select_for_group(group_i, len(input), probe_strs, group, plan, plan_tol,
@@ -294,5 +306,5 @@ class SetCoverFilter(BaseFilter):
                      upload_targets=group.st_targets.as_dict(),
                      upload_probes=group.st_probes.as_dict(),
                      coverage=st_a.as_dict(), setcover=st_b.as_dict(),
-                     wall_s=time.perf_counter() - t0)
+                     wall_s=time.perf_counter() - t0, host_ms=dict(getattr(self, '_host_ms', {})))
         return list(chosen)

@@ -138,3 +138,45 @@ def test_fast_path_probe_lengths(ctx, pl, m, lcf):
     cover.free()
     assert len(want) > 0
     assert np.array_equal(got, want), (k, mode)
+
+
+@pytest.mark.parametrize('pl,m,lcf,alphabet', [
+    (150, 3, 100, 'ACGT'), (200, 0, 200, 'ACGT'), (256, 8, 120, 'ACGT'), (190, 10, 60, 'ACGTN'),
+    (64, 1, 40, 'ACGT'), (129, 2, 129, 'ACGT'),
+    (90, 2, 50, 'ABCDEFGHIJKLMNOPQRSTUVWXYZ'), (40, 1, 30, 'ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789')])
+def test_generic_path_long_probes_and_wide_alphabets(ctx, pl, m, lcf, alphabet):
+    """Probes up to CB_MAX_PROBE_LEN (3-4 mask words) and alphabets needing 5-6 bit planes take the
+    generic multi-word path; intervals must still match the oracle exactly."""
+    O = _oracle()
+    rng = random.Random(pl + 7 * m)
+    groups = helpers.random_groups(rng, alphabet=alphabet, n_groups=1, anc_len=(600, 1200), max_genomes=6,
+                                   with_n=('N' in alphabet or len(alphabet) > 4))
+    genomes = groups[0]
+    seqs = [s for g in genomes for s in g]
+    probe_strs = [x for x in dict.fromkeys(helpers.tile_candidates(seqs, pl, 37)) if len(x) >= 20]
+    params = dict(mismatches=m, lcf_thres=lcf, island_of_exact_match=rng.choice([0, 12]),
+                  cover_extension=rng.choice([0, 30]), kmer_probe_map_k=20)
+    np.random.seed(pl)
+    k, seeds, mode = O.choose_seeds(probe_strs, m, lcf, min_k=20, k=20)
+    sm = O.SeedMap(probe_strs, seeds, k)
+    want = O.make_sets_quads(sm, genomes, m, lcf, params['island_of_exact_match'], params['cover_extension'])
+    np.random.seed(pl)
+    got, cover, st = _device_quads(ctx, probe_strs, genomes, params)
+    assert len(want) > 0
+    assert np.array_equal(got, want), (k, mode)
+    up = np.full(len(genomes), 1.0)
+    assert ctx.setcover(cover, len(probe_strs), None, up)[0].tolist() == \
+        O.set_cover_quads(want, len(probe_strs), len(genomes), None, up, None)
+    cover.free()
+
+
+def test_limits_are_reported(ctx):
+    """Outside the supported envelope the library says so instead of computing something else."""
+    from catch_b200 import _lib, probe
+    from catch_b200.filter.set_cover_filter import SetCoverFilter
+    g = helpers.to_genomes([[['ACGT' * 100]]])
+    with pytest.raises(_lib.CatchB200Error):          # probe longer than 256 nt
+        SetCoverFilter(0, 300, kmer_probe_map_k=20).filter([[probe.Probe.from_str('ACGT' * 75)]], g,
+                                                           input_is_grouped=True)
+    with pytest.raises(_lib.CatchB200Error):          # more than 31 mismatches
+        SetCoverFilter(40, 30).filter([[probe.Probe.from_str('ACGT' * 25)]], g, input_is_grouped=True)
