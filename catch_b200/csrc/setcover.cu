@@ -65,7 +65,10 @@ struct GreedyParams {
     uint32_t *list_n;
     uint32_t list_cap;
     unsigned long long *pub;       // [0] sequence number, [1] message (kind << 32 | probe)
-    unsigned long long *ctr;       // [0] list rebuilds, [1] picks served from a list
+    unsigned long long *ctr;       // [0] list rebuilds, [1] picks served from a list / rounds, [2] active candidates summed over rounds
+    // parallel-rounds kernel
+    unsigned long long *mark;      // [u_words+1] highest key among the active candidates touching the word
+    uint32_t *flag;                // [list_cap] conflict flag of active candidate a in the current round
 };
 
 // ---- K5: universe = union of all intervals
@@ -452,6 +455,76 @@ __device__ __forceinline__ void apply_long_interval(const GreedyParams &G, uint2
     __syncthreads();
 }
 
+// apply() for ONE winner interval, by one CTA: stage the interval's still-uncovered bits in shared
+// memory, subtract the uncovered bits of every overlap from the gain of the overlapping interval's
+// probe, then clear exactly the staged bits.  CTA-uniform (contains __syncthreads).
+__device__ __forceinline__ void apply_interval(const GreedyParams &G, int64_t i, unsigned long long *s_u)
+{
+    const uint2 r = G.iv[i];
+    const uint2 xr = G.ivx[i];
+    if (r.x >= r.y) return;
+    const uint32_t w0 = r.x >> 6, w1 = (r.y - 1) >> 6;
+    const uint32_t nwords = w1 - w0 + 1;
+    if (nwords > (uint32_t)APPLY_WORDS) {         // very long interval: L2 path (CTA-uniform)
+        apply_long_interval(G, r, xr);
+        return;
+    }
+    // the winner interval's still-uncovered bits, staged in shared memory: they are what
+    // every overlap is counted against AND exactly what has to be cleared afterwards
+    unsigned long long mine = 0ull;
+    if (threadIdx.x < nwords) {
+        unsigned long long m = ~0ull;
+        const uint32_t wd = w0 + threadIdx.x;
+        if (wd == w0) m &= ~0ull << (r.x & 63);
+        if (wd == w1) m &= ~0ull >> (63 - ((r.y - 1) & 63));
+        mine = __ldcg(G.U + wd) & m;
+        s_u[threadIdx.x] = mine;
+    }
+    // candidate items are fetched while the bits are in flight
+    constexpr int BATCH = 4;
+    const int64_t x0 = xr.x, x1 = xr.y;
+    uint4 item[BATCH];
+#pragma unroll
+    for (int u = 0; u < BATCH; u++) {
+        const int64_t x = x0 + threadIdx.x + (int64_t)u * GREEDY_THREADS;
+        item[u] = x < x1 ? __ldg(G.blk_items + x) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    const int any = __syncthreads_or(mine != 0ull);
+    if (any) {
+        int64_t xb = x0 + threadIdx.x;
+        for (;;) {
+#pragma unroll
+            for (int u = 0; u < BATCH; u++) {
+                const uint32_t os = max(item[u].x, r.x), oe = min(item[u].y, r.y);
+                if (os < oe) {
+                    const uint32_t wa = (os >> 6) - w0, wb = ((oe - 1) >> 6) - w0;
+                    uint32_t dlt = 0;
+                    for (uint32_t q = wa; q <= wb; q++) {
+                        unsigned long long m = ~0ull;
+                        if (q == wa) m &= ~0ull << (os & 63);
+                        if (q == wb) m &= ~0ull >> (63 - ((oe - 1) & 63));
+                        dlt += __popcll(s_u[q] & m);
+                    }
+                    if (dlt) atomicSub(&G.gain[item[u].z], dlt);
+                }
+            }
+            xb += (int64_t)GREEDY_THREADS * BATCH;
+            if (xb - threadIdx.x >= x1) break;          // CTA-uniform
+#pragma unroll
+            for (int u = 0; u < BATCH; u++) {
+                const int64_t x = xb + (int64_t)u * GREEDY_THREADS;
+                item[u] = x < x1 ? __ldg(G.blk_items + x) : make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+        // clear exactly the bits that were set (nobody else touches this range)
+        if (mine) {
+            atomicAnd(&G.U[w0 + threadIdx.x], ~mine);
+            atomicAdd(G.remaining, (unsigned long long)(-(long long)__popcll(mine)));
+        }
+    }
+    __syncthreads();                             // s_u is reused by the next interval
+}
+
 // ---------------------------------------------------------------------------------------
 // Incremental greedy, one grid-wide rendezvous per pick.
 //
@@ -599,71 +672,7 @@ greedy_inc_kernel(const GreedyParams G)
         n_picks++;
         {
             const int64_t i0 = G.iv_off[w], i1 = G.iv_off[w + 1];
-            for (int64_t i = i0 + blockIdx.x; i < i1; i += gridDim.x) {
-                const uint2 r = G.iv[i];
-                const uint2 xr = G.ivx[i];
-                if (r.x >= r.y) continue;
-                const uint32_t w0 = r.x >> 6, w1 = (r.y - 1) >> 6;
-                const uint32_t nwords = w1 - w0 + 1;
-                if (nwords > (uint32_t)APPLY_WORDS) {         // very long interval: L2 path (CTA-uniform)
-                    apply_long_interval(G, r, xr);
-                    continue;
-                }
-                // the winner interval's still-uncovered bits, staged in shared memory: they are what
-                // every overlap is counted against AND exactly what has to be cleared afterwards
-                unsigned long long mine = 0ull;
-                if (threadIdx.x < nwords) {
-                    unsigned long long m = ~0ull;
-                    const uint32_t wd = w0 + threadIdx.x;
-                    if (wd == w0) m &= ~0ull << (r.x & 63);
-                    if (wd == w1) m &= ~0ull >> (63 - ((r.y - 1) & 63));
-                    mine = __ldcg(G.U + wd) & m;
-                    s_u[threadIdx.x] = mine;
-                }
-                // candidate items are fetched while the bits are in flight
-                constexpr int BATCH = 4;
-                const int64_t x0 = xr.x, x1 = xr.y;
-                uint4 item[BATCH];
-#pragma unroll
-                for (int u = 0; u < BATCH; u++) {
-                    const int64_t x = x0 + threadIdx.x + (int64_t)u * GREEDY_THREADS;
-                    item[u] = x < x1 ? __ldg(G.blk_items + x) : make_uint4(0u, 0u, 0u, 0u);
-                }
-                const int any = __syncthreads_or(mine != 0ull);
-                if (any) {
-                    int64_t xb = x0 + threadIdx.x;
-                    for (;;) {
-#pragma unroll
-                        for (int u = 0; u < BATCH; u++) {
-                            const uint32_t os = max(item[u].x, r.x), oe = min(item[u].y, r.y);
-                            if (os < oe) {
-                                const uint32_t wa = (os >> 6) - w0, wb = ((oe - 1) >> 6) - w0;
-                                uint32_t dlt = 0;
-                                for (uint32_t q = wa; q <= wb; q++) {
-                                    unsigned long long m = ~0ull;
-                                    if (q == wa) m &= ~0ull << (os & 63);
-                                    if (q == wb) m &= ~0ull >> (63 - ((oe - 1) & 63));
-                                    dlt += __popcll(s_u[q] & m);
-                                }
-                                if (dlt) atomicSub(&G.gain[item[u].z], dlt);
-                            }
-                        }
-                        xb += (int64_t)GREEDY_THREADS * BATCH;
-                        if (xb - threadIdx.x >= x1) break;          // CTA-uniform
-#pragma unroll
-                        for (int u = 0; u < BATCH; u++) {
-                            const int64_t x = xb + (int64_t)u * GREEDY_THREADS;
-                            item[u] = x < x1 ? __ldg(G.blk_items + x) : make_uint4(0u, 0u, 0u, 0u);
-                        }
-                    }
-                    // clear exactly the bits that were set (nobody else touches this range)
-                    if (mine) {
-                        atomicAnd(&G.U[w0 + threadIdx.x], ~mine);
-                        atomicAdd(G.remaining, (unsigned long long)(-(long long)__popcll(mine)));
-                    }
-                }
-                __syncthreads();                             // s_u is reused by the next interval
-            }
+            for (int64_t i = i0 + blockIdx.x; i < i1; i += gridDim.x) apply_interval(G, i, s_u);
         }
         lap(2);
 
@@ -723,6 +732,345 @@ greedy_inc_kernel(const GreedyParams G)
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Incremental greedy in PARALLEL ROUNDS (every p_u == 1).
+//
+// Sequential greedy picks the probe with the largest key = (gain, smallest id) again and again.
+// Call two probes in conflict when they share a still-uncovered universe bit.  A probe whose key
+// is larger than the key of every probe it conflicts with ("local maximum") keeps its gain until
+// it is picked -- a conflicting neighbour would have to become the global maximum first, and it
+// cannot while the probe is there -- and it IS picked in the end, because nobody else can cover
+// its bits before it.  So all local maxima can be applied at once: the selected SET and every
+// probe's gain at pick time are those of the sequential loop.  Keys at pick time are strictly
+// decreasing along the sequential pick sequence, therefore sorting the picks by that key (done
+// by the host part of cb_setcover) restores the sequential pick ORDER (utils/set_cover.py:
+// 393-433, 483-526 -- the order matters because the reference builds its result set by .add()
+// in pick order).
+//
+// Local maxima are searched among the candidate list only: it holds every probe (of the current
+// rank) with gain >= tau, i.e. a prefix of the global key order, so every probe with a larger
+// key than a list member is itself in the list.  Per round, three phases separated by grid
+// barriers:
+//   mark:   every active candidate writes atomicMax(mark[w], key) for each universe word w in
+//           which one of its intervals still has uncovered bits (one thread per interval);
+//   check:  a candidate is accepted iff mark[w] == its key in all of those words (conflicts are
+//           detected at word granularity: false conflicts only postpone a pick);
+//   apply:  marks are reset; the intervals of ALL accepted probes are spread over the CTAs and
+//           applied as in the one-pick kernel (accepted probes share no word with uncovered bits,
+//           so their staged bit ranges are disjoint).
+// The active candidates and the winners are compacted redundantly by every CTA into its own
+// shared memory (same inputs, same deterministic scan), which saves a barrier and all counters.
+// ---------------------------------------------------------------------------------------
+constexpr int PAR_LIST_CAP = 4096;          // upper limit of the candidate list (a runtime cap <= this is used)
+
+template <typename F>
+__device__ __forceinline__ void for_each_word(uint2 r, F f)
+{
+    if (r.x >= r.y) return;
+    const uint32_t w0 = r.x >> 6, w1 = (r.y - 1) >> 6;
+    for (uint32_t w = w0; w <= w1; w++) {
+        unsigned long long m = ~0ull;
+        if (w == w0) m &= ~0ull << (r.x & 63);
+        if (w == w1) m &= ~0ull >> (63 - ((r.y - 1) & 63));
+        f(w, m);
+    }
+}
+
+__global__ void __launch_bounds__(GREEDY_THREADS)
+greedy_par_kernel(const GreedyParams G)
+{
+    __shared__ unsigned long long s_key[GREEDY_THREADS / 32];
+    __shared__ unsigned long long s_u[APPLY_WORDS];
+    __shared__ uint32_t s_part[GREEDY_THREADS / 32];
+    extern __shared__ uint32_t s_dyn[];
+    // per CTA, list_cap entries each: active candidates (probe, gain, first interval, exclusive prefix
+    // of the interval counts) and the winners among them (first interval, prefix)
+    uint32_t *s_p = s_dyn, *s_g = s_p + G.list_cap, *s_i0 = s_g + G.list_cap, *s_base = s_i0 + G.list_cap,
+             *s_wi0 = s_base + G.list_cap + 1, *s_wbase = s_wi0 + G.list_cap;
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t gsize = (int64_t)gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int NWARP = GREEDY_THREADS / 32;
+    constexpr int PER = PAR_LIST_CAP / GREEDY_THREADS;
+    // exclusive prefix of v over the CTA (thread order); adds the CTA total to `total`
+    auto block_scan = [&](uint32_t v, uint32_t &total) -> uint32_t {
+        uint32_t inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        __syncthreads();                 // s_part may still be read from the previous scan
+        if (lane == 31) s_part[warp] = inc;
+        __syncthreads();
+        uint32_t before = 0, all = 0;
+#pragma unroll
+        for (int q = 0; q < NWARP; q++) {
+            const uint32_t t = s_part[q];
+            if (q < warp) before += t;
+            all += t;
+        }
+        total += all;
+        return before + inc - v;
+    };
+
+    int cur_rank = 0;
+    long long n_picks = 0;
+    unsigned long long bar_target = 0, n_rebuilds = 0, n_rounds = 0, n_active_sum = 0;
+    uint32_t tau = 1;
+    int band_shift = 4;
+    unsigned rb = 0;
+    bool need_rebuild = true;
+    unsigned long long t_phase[4] = {0, 0, 0, 0}, t_last = 0;
+    const bool timing = (gtid == 0);
+    if (timing) t_last = globaltimer_ns();
+    auto lap = [&](int i) {
+        if (timing) {
+            const unsigned long long t = globaltimer_ns();
+            t_phase[i] += t - t_last;
+            t_last = t;
+        }
+    };
+    auto block_max = [&](unsigned long long best) -> unsigned long long {
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            const unsigned long long t = __shfl_xor_sync(0xffffffffu, best, o);
+            best = t > best ? t : best;
+        }
+        if (lane == 0) s_key[warp] = best;
+        __syncthreads();
+        best = lane < NWARP ? s_key[lane] : 0ull;
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            const unsigned long long t = __shfl_xor_sync(0xffffffffu, best, o);
+            best = t > best ? t : best;
+        }
+        __syncthreads();
+        return best;
+    };
+
+    for (;;) {
+        if (need_rebuild) {
+            // ---- full argmax over the current rank, then the candidate list (band below the maximum)
+            unsigned long long best = 0;
+            for (int64_t p = gtid; p < G.n_probes; p += gsize) {
+                const uint32_t g = __ldcg(&G.gain[p]);
+                if (g && G.rank_idx[p] == (uint32_t)cur_rank) {
+                    const unsigned long long key = ((unsigned long long)g << 32) | (unsigned long long)(0xffffffffu - (uint32_t)p);
+                    best = key > best ? key : best;
+                }
+            }
+            best = block_max(best);
+            const unsigned slot_k = rb & 1u;
+            rb++;
+            if (threadIdx.x == 0 && best) atomicMax(&G.key[slot_k], best);
+            if (gtid == 0) *G.list_n = 0;
+            grid_barrier(G.barrier, bar_target);
+            if (__ldcg(G.remaining) == 0ull) break;
+            const unsigned long long key = __ldcg(&G.key[slot_k]);
+            if (gtid == 0) G.key[slot_k ^ 1u] = 0ull;
+            if (key == 0ull) {                  // rank exhausted (:522-526)
+                cur_rank++;
+                if (cur_rank >= G.n_ranks) {
+                    if (gtid == 0) *G.status = CB_ERR_STATE;
+                    break;
+                }
+                grid_barrier(G.barrier, bar_target);
+                continue;
+            }
+            const uint32_t wmax = 0xffffffffu - (uint32_t)(key & 0xffffffffull);
+            const uint32_t gmax = (uint32_t)(key >> 32);
+            for (;;) {
+                const uint32_t band = gmax >> band_shift;
+                tau = gmax - band;
+                if (tau < 1u) tau = 1u;
+                for (int64_t p = gtid; p < G.n_probes; p += gsize) {
+                    const uint32_t g = __ldcg(&G.gain[p]);
+                    if (g >= tau && G.rank_idx[p] == (uint32_t)cur_rank) {
+                        const uint32_t slot = atomicAdd(G.list_n, 1u);
+                        if (slot < G.list_cap) G.list[slot] = (uint32_t)p;
+                    }
+                }
+                grid_barrier(G.barrier, bar_target);
+                const uint32_t n = __ldcg(G.list_n);
+                if (n <= G.list_cap) {
+                    if (n < G.list_cap / 8 && band_shift > 1) band_shift--;
+                    break;
+                }
+                // too many candidates: everyone has read n; narrow the band and collect again.  When
+                // even the ties at the maximum overflow the list, run this round with the argmax alone.
+                grid_barrier(G.barrier, bar_target);
+                if (gtid == 0) {
+                    if (band == 0u) { G.list[0] = wmax; *G.list_n = 1u; }
+                    else *G.list_n = 0;
+                }
+                grid_barrier(G.barrier, bar_target);
+                if (band == 0u) { tau = gmax; break; }
+                band_shift++;
+            }
+            need_rebuild = false;
+            n_rebuilds++;
+            lap(0);
+        }
+
+        // ---- active candidates: list entries whose gain is still >= tau.  Every CTA derives the
+        // same compact arrays in its own shared memory (gains are stable until the next apply), so
+        // no global list, counter or extra barrier is needed.
+        const uint32_t n_list = min(__ldcg(G.list_n), G.list_cap);
+        uint32_t n_act = 0;
+        {
+            uint32_t pv[PER], gv[PER];
+#pragma unroll
+            for (int u = 0; u < PER; u++) {
+                const uint32_t c = (uint32_t)u * GREEDY_THREADS + threadIdx.x;
+                pv[u] = c < n_list ? __ldcg(&G.list[c]) : 0xffffffffu;
+            }
+#pragma unroll
+            for (int u = 0; u < PER; u++) gv[u] = pv[u] != 0xffffffffu ? __ldcg(&G.gain[pv[u]]) : 0u;
+#pragma unroll
+            for (int u = 0; u < PER; u++) {
+                if ((uint32_t)u * GREEDY_THREADS >= n_list) break;          // CTA-uniform
+                const bool act = gv[u] >= tau && pv[u] != 0xffffffffu;
+                const uint32_t before = n_act;
+                const uint32_t pos = before + block_scan(act ? 1u : 0u, n_act);
+                if (act) { s_p[pos] = pv[u]; s_g[pos] = gv[u]; }
+            }
+            __syncthreads();
+        }
+        if (n_act == 0u) {                       // the list is used up
+            need_rebuild = true;
+            continue;
+        }
+        uint32_t total_pairs = 0;
+        {
+            uint32_t i0v[PER], cntv[PER];
+#pragma unroll
+            for (int u = 0; u < PER; u++) {
+                const uint32_t a = (uint32_t)u * GREEDY_THREADS + threadIdx.x;
+                i0v[u] = cntv[u] = 0;
+                if (a < n_act) {
+                    const uint32_t p = s_p[a];
+                    const int64_t x = G.iv_off[p], y = G.iv_off[p + 1];
+                    i0v[u] = (uint32_t)x;
+                    cntv[u] = (uint32_t)(y - x);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < PER; u++) {
+                if ((uint32_t)u * GREEDY_THREADS >= n_act) break;           // CTA-uniform
+                const uint32_t a = (uint32_t)u * GREEDY_THREADS + threadIdx.x;
+                const uint32_t before = total_pairs;
+                const uint32_t pos = before + block_scan(cntv[u], total_pairs);
+                if (a < n_act) { s_i0[a] = i0v[u]; s_base[a] = pos; }
+            }
+            if (threadIdx.x == 0) s_base[n_act] = total_pairs;
+            // the conflict flags of the previous round have been read by everybody (barrier since)
+            if (blockIdx.x == 0)
+                for (uint32_t a = threadIdx.x; a < G.list_cap; a += GREEDY_THREADS) G.flag[a] = 0u;
+            __syncthreads();
+        }
+        auto pair_of = [&](uint32_t f, uint32_t &a) -> int64_t {
+            uint32_t lo = 0, hi = n_act;
+            while (hi - lo > 1) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (s_base[mid] <= f) lo = mid; else hi = mid;
+            }
+            a = lo;
+            return (int64_t)s_i0[lo] + (f - s_base[lo]);
+        };
+        auto key_of = [&](uint32_t a) -> unsigned long long {
+            return ((unsigned long long)s_g[a] << 32) | (unsigned long long)(0xffffffffu - s_p[a]);
+        };
+
+        // ---- mark: one thread per (candidate, interval)
+        for (int64_t f = gtid; f < (int64_t)total_pairs; f += gsize) {
+            uint32_t a;
+            const int64_t i = pair_of((uint32_t)f, a);
+            const unsigned long long key = key_of(a);
+            for_each_word(G.iv[i], [&](uint32_t w, unsigned long long m) {
+                if (__ldcg(G.U + w) & m) atomicMax(&G.mark[w], key);
+            });
+        }
+        grid_barrier(G.barrier, bar_target);
+
+        // ---- check
+        for (int64_t f = gtid; f < (int64_t)total_pairs; f += gsize) {
+            uint32_t a;
+            const int64_t i = pair_of((uint32_t)f, a);
+            const unsigned long long key = key_of(a);
+            bool conflict = false;
+            for_each_word(G.iv[i], [&](uint32_t w, unsigned long long m) {
+                if ((__ldcg(G.U + w) & m) && __ldcg(G.mark + w) != key) conflict = true;
+            });
+            if (conflict) G.flag[a] = 1u;
+        }
+        grid_barrier(G.barrier, bar_target);
+
+        // ---- winners = active candidates without a conflict (same compaction in every CTA)
+        uint32_t n_win = 0;
+        {
+            uint32_t fl[PER];
+#pragma unroll
+            for (int u = 0; u < PER; u++) {
+                const uint32_t a = (uint32_t)u * GREEDY_THREADS + threadIdx.x;
+                fl[u] = a < n_act ? __ldcg(&G.flag[a]) : 1u;
+            }
+            uint32_t wsum = 0;
+#pragma unroll
+            for (int u = 0; u < PER; u++) {
+                if ((uint32_t)u * GREEDY_THREADS >= n_act) break;           // CTA-uniform
+                const uint32_t a = (uint32_t)u * GREEDY_THREADS + threadIdx.x;
+                const bool win = fl[u] == 0u;
+                const uint32_t cnt = win ? s_base[a + 1] - s_base[a] : 0u;
+                const uint32_t before_n = n_win, before_s = wsum;
+                const uint32_t j = before_n + block_scan(win ? 1u : 0u, n_win);
+                const uint32_t base = before_s + block_scan(cnt, wsum);
+                if (win) {
+                    s_wi0[j] = s_i0[a];
+                    s_wbase[j] = base;
+                    if (blockIdx.x == 0) G.sel[n_picks + j] = (long long)key_of(a);
+                }
+            }
+            if (threadIdx.x == 0) s_wbase[n_win] = wsum;
+            __syncthreads();
+        }
+        lap(1);
+        n_rounds++;
+        n_active_sum += n_act;
+        n_picks += n_win;
+
+        // ---- reset the marks of this round
+        for (int64_t f = gtid; f < (int64_t)total_pairs; f += gsize) {
+            uint32_t a;
+            const int64_t i = pair_of((uint32_t)f, a);
+            for_each_word(G.iv[i], [&](uint32_t w, unsigned long long) { G.mark[w] = 0ull; });
+        }
+        // ---- apply every accepted probe: (winner, interval) pairs are dealt round-robin to the CTAs
+        {
+            const uint32_t total = s_wbase[n_win];
+            for (uint32_t f = blockIdx.x; f < total; f += gridDim.x) {
+                uint32_t lo = 0, hi = n_win;
+                while (hi - lo > 1) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (s_wbase[mid] <= f) lo = mid; else hi = mid;
+                }
+                apply_interval(G, (int64_t)s_wi0[lo] + (f - s_wbase[lo]), s_u);
+            }
+        }
+        lap(2);
+        grid_barrier(G.barrier, bar_target);
+        lap(3);
+        if (__ldcg(G.remaining) == 0ull) break;
+    }
+    if (gtid == 0) {
+        *G.n_sel = n_picks;
+        for (int i = 0; i < 4; i++) G.phase_ns[i] = t_phase[i];
+        G.ctr[0] = n_rebuilds;
+        G.ctr[1] = n_rounds;
+        G.ctr[2] = n_active_sum;
+    }
+}
+
 }  // namespace
 
 int cb_setcover_impl(cb_ctx *ctx, const cb_cover *cover, const int32_t *ranks, const double *universe_p,
@@ -744,8 +1092,8 @@ int cb_setcover_impl(cb_ctx *ctx, const cb_cover *cover, const int32_t *ranks, c
     const int wide = ctx->sm_count * 8;
     const int64_t u_words = cover->universe_bits >> 6;
 
-    DevBuf<unsigned long long> d_U, d_key, d_remaining, d_barrier, d_pub;
-    DevBuf<uint32_t> d_list;
+    DevBuf<unsigned long long> d_U, d_key, d_remaining, d_barrier, d_pub, d_mark;
+    DevBuf<uint32_t> d_list, d_winners;
     DevBuf<long long> d_usize, d_uncov, d_sel, d_nsel;
     DevBuf<uint32_t> d_gain, d_rank, d_ivg, d_bcount, d_bcursor;
     DevBuf<unsigned int> d_nleft;
@@ -835,7 +1183,17 @@ int cb_setcover_impl(cb_ctx *ctx, const cb_cover *cover, const int32_t *ranks, c
     G.status = d_status.p;
     G.barrier = d_barrier.p;
     G.phase_ns = d_barrier.p + 1;
-    const uint32_t list_cap = 4096;
+    // which kernel: parallel rounds (default), one pick per rendezvous ("inc"), or the two-barrier
+    // kernel that recomputes clamped gains ("legacy"; the only one that handles p_u < 1)
+    const char *mode_env = getenv("CB_GREEDY");
+    const bool legacy = full_mode || (mode_env && !strcmp(mode_env, "legacy")) ||
+                        (getenv("CB_GREEDY_LEGACY") && getenv("CB_GREEDY_LEGACY")[0] == '1');
+    const bool par = !legacy && !(mode_env && !strcmp(mode_env, "inc"));
+    uint32_t list_cap = par ? (uint32_t)PAR_LIST_CAP : 4096u;
+    if (const char *e = getenv("CB_GREEDY_LIST_CAP")) {
+        const int v = atoi(e);
+        if (v >= 1 && (uint32_t)v <= list_cap) list_cap = (uint32_t)v;
+    }
     CB_CUDA(ctx, d_list.alloc(list_cap + 1));
     CB_CUDA(ctx, d_pub.alloc(8));
     CB_CUDA(ctx, cudaMemsetAsync(d_pub.p, 0, sizeof(unsigned long long) * 8, st));
@@ -845,6 +1203,14 @@ int cb_setcover_impl(cb_ctx *ctx, const cb_cover *cover, const int32_t *ranks, c
     G.list_cap = list_cap;
     G.pub = d_pub.p;
     G.ctr = d_pub.p + 4;
+    if (par) {
+        CB_CUDA(ctx, d_mark.alloc((size_t)u_words + 1));
+        CB_CUDA(ctx, cudaMemsetAsync(d_mark.p, 0, sizeof(unsigned long long) * ((size_t)u_words + 1), st));
+        CB_CUDA(ctx, d_winners.alloc(list_cap));
+        CB_CUDA(ctx, cudaMemsetAsync(d_winners.p, 0, sizeof(uint32_t) * list_cap, st));
+        G.mark = d_mark.p;
+        G.flag = d_winners.p;
+    }
 
     if (full_mode) {
         CB_CUDA(ctx, d_ivg.alloc((size_t)E));
@@ -878,10 +1244,15 @@ int cb_setcover_impl(cb_ctx *ctx, const cb_cover *cover, const int32_t *ranks, c
     t_uni.stop();
 
     // ---- persistent cooperative launch: as many co-resident blocks as the device allows
-    const bool legacy = full_mode || (getenv("CB_GREEDY_LEGACY") && getenv("CB_GREEDY_LEGACY")[0] == '1');
-    void *kernel = legacy ? (void *)greedy_kernel : (void *)greedy_inc_kernel;
+    void *kernel = legacy ? (void *)greedy_kernel : par ? (void *)greedy_par_kernel : (void *)greedy_inc_kernel;
     int per_sm = 0;
+    size_t dyn_smem = 0;
     if (legacy) CB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, greedy_kernel, GREEDY_THREADS, 0));
+    else if (par) {
+        dyn_smem = sizeof(uint32_t) * (6 * (size_t)list_cap + 2);
+        CB_CUDA(ctx, cudaFuncSetAttribute(greedy_par_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+        CB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, greedy_par_kernel, GREEDY_THREADS, dyn_smem));
+    }
     else CB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, greedy_inc_kernel, GREEDY_THREADS, 0));
     if (per_sm < 1) return cb_fail(ctx, CB_ERR_CUDA, "greedy kernel does not fit on an SM");
     int want = 2;
@@ -890,14 +1261,14 @@ int cb_setcover_impl(cb_ctx *ctx, const cb_cover *cover, const int32_t *ranks, c
     const int grid = per_sm * ctx->sm_count;
     void *args[] = {(void *)&G};
     t_greedy.start();
-    CB_CUDA(ctx, cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(GREEDY_THREADS), args, 0, st));
+    CB_CUDA(ctx, cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(GREEDY_THREADS), args, dyn_smem, st));
     ctx->launches++;
     t_greedy.stop();
     t_all.stop();
 
     long long h_nsel = 0;
     int h_status = 0;
-    unsigned long long h_phase[4] = {0, 0, 0, 0}, h_ctr[2] = {0, 0};
+    unsigned long long h_phase[4] = {0, 0, 0, 0}, h_ctr[3] = {0, 0, 0};
     CB_CUDA(ctx, cudaMemcpyAsync(h_phase, d_barrier.p + 1, sizeof h_phase, cudaMemcpyDeviceToHost, st));
     CB_CUDA(ctx, cudaMemcpyAsync(h_ctr, d_pub.p + 4, sizeof h_ctr, cudaMemcpyDeviceToHost, st));
     CB_CUDA(ctx, cudaMemcpyAsync(&h_nsel, d_nsel.p, sizeof h_nsel, cudaMemcpyDeviceToHost, st));
@@ -908,6 +1279,21 @@ int cb_setcover_impl(cb_ctx *ctx, const cb_cover *cover, const int32_t *ranks, c
         static_assert(sizeof(long long) == sizeof(int64_t), "int64");
         CB_CUDA(ctx, cudaMemcpyAsync(sel_ids, d_sel.p, sizeof(int64_t) * (size_t)h_nsel, cudaMemcpyDeviceToHost, st));
         CB_CUDA(ctx, cudaStreamSynchronize(st));
+        if (par) {
+            // the kernel reports each pick's key at pick time, (gain << 32) | (2^32-1 - id), in no
+            // particular order inside a round; the sequential loop picks rank by rank and, inside a
+            // rank, in strictly decreasing key order (see greedy_par_kernel)
+            uint64_t *keys = reinterpret_cast<uint64_t *>(sel_ids);
+            auto id_of = [](uint64_t k) { return (int64_t)(0xffffffffu - (uint32_t)(k & 0xffffffffull)); };
+            if (n_ranks > 1)
+                std::sort(keys, keys + h_nsel, [&](uint64_t a, uint64_t b) {
+                    const uint32_t ra = h_rank[(size_t)id_of(a)], rb = h_rank[(size_t)id_of(b)];
+                    return ra != rb ? ra < rb : a > b;
+                });
+            else
+                std::sort(keys, keys + h_nsel, [](uint64_t a, uint64_t b) { return a > b; });
+            for (long long i = 0; i < h_nsel; i++) sel_ids[i] = id_of(keys[i]);
+        }
     }
     *n_sel = h_nsel;
     if (stats) {
@@ -919,7 +1305,8 @@ int cb_setcover_impl(cb_ctx *ctx, const cb_cover *cover, const int32_t *ranks, c
         stats->n_kernel_launches = ctx->launches;
         for (int i = 0; i < 4; i++) stats->reserved[i] = (int64_t)h_phase[i];   // ns: argmax/rebuild, barrier, apply, rendezvous
         stats->reserved[4] = (int64_t)h_ctr[0];      // candidate-list rebuilds
-        stats->reserved[5] = (int64_t)h_ctr[1];      // picks served from a list
+        stats->reserved[5] = (int64_t)h_ctr[1];      // picks served from a list (inc) / rounds (par)
+        stats->reserved[6] = (int64_t)h_ctr[2];      // active candidates summed over the rounds (par)
     }
     return CB_OK;
 }

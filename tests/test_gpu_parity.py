@@ -180,3 +180,60 @@ def test_limits_are_reported(ctx):
                                                            input_is_grouped=True)
     with pytest.raises(_lib.CatchB200Error):          # more than 31 mismatches
         SetCoverFilter(40, 30).filter([[probe.Probe.from_str('ACGT' * 25)]], g, input_is_grouped=True)
+
+
+@pytest.mark.parametrize('mode,cap', [('par', None), ('par', '1'), ('par', '3'), ('inc', None), ('legacy', None)])
+def test_greedy_kernels_agree_with_oracle(ctx, monkeypatch, mode, cap):
+    """The three greedy kernels (parallel rounds, one pick per rendezvous, recompute-everything) give
+    the oracle's pick SEQUENCE; a tiny candidate list forces the overflow and rebuild paths of the
+    parallel-rounds kernel."""
+    O = _oracle()
+    monkeypatch.setenv('CB_GREEDY', mode)
+    if cap:
+        monkeypatch.setenv('CB_GREEDY_LIST_CAP', cap)
+    rng = random.Random(17)
+    for case in (1, 2, 5, 7, 9):
+        groups, cands, params = helpers.random_case(case)
+        probe_strs, genomes = cands[0], groups[0]
+        if not probe_strs:
+            continue
+        np.random.seed(3)
+        got, cover, _ = _device_quads(ctx, probe_strs, genomes, params)
+        for ranks in (None, np.array([rng.choice([0, 0, 2, 7]) for _ in probe_strs], dtype=np.int32)):
+            want = O.set_cover_quads(got, len(probe_strs), len(genomes), None, None, ranks)
+            picks, st = ctx.setcover(cover, len(probe_strs), ranks, None)
+            assert picks.tolist() == want
+        cover.free()
+
+
+def test_parallel_rounds_at_scale(ctx, monkeypatch):
+    """Size-independent check at a size the oracle would take minutes for: the parallel-rounds
+    kernel and the one-pick-per-rendezvous kernel give the same pick sequence, and the selection
+    covers every universe bit."""
+    from catch_b200 import coverage as cov
+    seqs = helpers.synthetic_genomes(120, 6000, 0.03, seed=5)
+    cands = list(dict.fromkeys(helpers.tile_candidates(seqs, 75, 25)))
+    group = cov.PackedGroup(ctx, cands, [[s] for s in seqs])
+    np.random.seed(7)
+    plan = cov.SeedPlan(cands, 2, 60, 20)
+    cover, _ = cov.compute_cover(ctx, group, plan, 2, 60, 0, 50)
+    group.free()
+    res = {}
+    for mode in ('par', 'inc'):
+        monkeypatch.setenv('CB_GREEDY', mode)
+        res[mode], st = ctx.setcover(cover, len(cands), None, None)
+    assert len(res['par']) > 50
+    assert res['par'].tolist() == res['inc'].tolist()
+    pid, gen, s, e = ctx.cover_export(cover)
+    cover.free()
+    chosen = np.zeros(len(cands), dtype=bool)
+    chosen[res['par']] = True
+    L = 6000
+    allc = np.zeros(len(seqs) * L + 1, dtype=np.int32)
+    selc = np.zeros(len(seqs) * L + 1, dtype=np.int32)
+    np.add.at(allc, gen * L + s, 1)
+    np.add.at(allc, gen * L + e, -1)
+    m = chosen[pid]
+    np.add.at(selc, gen[m] * L + s[m], 1)
+    np.add.at(selc, gen[m] * L + e[m], -1)
+    assert np.array_equal(np.cumsum(allc) > 0, np.cumsum(selc) > 0)
