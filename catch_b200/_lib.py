@@ -40,8 +40,9 @@ class Stats(C.Structure):
 # every symbol include/catch_b200.h declares
 EXPORTED_SYMBOLS = [
     'cb_init', 'cb_destroy', 'cb_last_error', 'cb_version', 'cb_flush_l2',
-    'cb_upload_targets', 'cb_targets_free', 'cb_upload_probes', 'cb_probes_free',
-    'cb_probes_have_duplicates', 'cb_mt19937_randint',
+    'cb_upload_targets', 'cb_targets_free', 'cb_upload_probes', 'cb_probes_free', 'cb_upload_group',
+    'cb_probes_have_duplicates', 'cb_mt19937_randint', 'cb_mt19937_randint_begin', 'cb_mt19937_randint_end',
+    'cb_split_lengths',
     'cb_coverage', 'cb_cover_free', 'cb_cover_num_intervals', 'cb_cover_export', 'cb_cover_import',
     'cb_setcover', 'cb_minhash_neardup', 'cb_hamming_neardup',
     'cb_comm_unique_id', 'cb_comm_init', 'cb_comm_destroy', 'cb_cover_allgather',
@@ -73,8 +74,14 @@ def load():
     L.cb_targets_free.restype = None
     L.cb_upload_probes.argtypes = [vp, vp, vp, i64, vp, i32, C.POINTER(vp), C.POINTER(Stats)]
     L.cb_probes_free.argtypes = [vp]
+    L.cb_upload_group.argtypes = [vp, vp, i64, vp, i64, i32, vp, vp, i64, vp, i32, vp, C.POINTER(i32),
+                                  C.POINTER(vp), C.POINTER(vp), C.POINTER(Stats)]
     L.cb_probes_free.restype = None
     L.cb_probes_have_duplicates.argtypes = [vp, vp, C.POINTER(i32)]
+    L.cb_mt19937_randint_begin.argtypes = [vp, C.POINTER(i32), C.c_uint32, i64, vp]
+    L.cb_mt19937_randint_begin.restype = vp
+    L.cb_mt19937_randint_end.argtypes = [vp]
+    L.cb_split_lengths.argtypes = [vp, i64, i64, i32, vp]
     L.cb_mt19937_randint.argtypes = [vp, C.POINTER(i32), C.c_uint32, i64, vp]
     L.cb_coverage.argtypes = [vp, vp, vp, C.POINTER(HybParams), vp, vp, C.POINTER(vp), C.POINTER(Stats)]
     L.cb_cover_free.argtypes = [vp]
@@ -145,6 +152,18 @@ class Context:
         self._check(self.L.cb_upload_probes(self.h, _ptr(ascii_u8), _ptr(probe_off), len(probe_off) - 1,
                                             _ptr(lut), bits, C.byref(out), C.byref(st)))
         return Handle(self.L.cb_probes_free, out), st
+
+    def upload_group(self, probes_raw, n_probes, targets_raw, seq_off, seq_genome, n_genomes, probe_off=None,
+                     sep=10):
+        """cb_upload_group: `probes_raw` is a bytes object holding the probes separated by `sep`
+        (or back to back with explicit `probe_off`).  Returns (probes, targets, lengths, bits, stats)."""
+        p_out, t_out, st, bits = C.c_void_p(), C.c_void_p(), Stats(), C.c_int32()
+        lens = np.zeros(max(n_probes, 1), dtype=np.int32)
+        self._check(self.L.cb_upload_group(self.h, probes_raw, len(probes_raw), _ptr(probe_off), n_probes, sep,
+                                           targets_raw, _ptr(seq_off), len(seq_off) - 1, _ptr(seq_genome), n_genomes,
+                                           _ptr(lens), C.byref(bits), C.byref(p_out), C.byref(t_out), C.byref(st)))
+        return (Handle(self.L.cb_probes_free, p_out), Handle(self.L.cb_targets_free, t_out), lens[:n_probes],
+                bits.value, st)
 
     def probes_have_duplicates(self, probes):
         flag = C.c_int32()
@@ -257,6 +276,14 @@ def default_context():
     return _default_ctx
 
 
+def split_lengths(raw, n, sep=10):
+    """Lengths of the n strings joined with `sep` into the bytes object `raw`; None when the
+    separator also occurs inside a string."""
+    lens = np.zeros(max(n, 1), dtype=np.int32)
+    rc = load().cb_split_lengths(raw, len(raw), n, sep, lens.ctypes.data)
+    return lens[:n] if rc == 0 else None
+
+
 def legacy_randint(bound, shape):
     """np.random.randint(0, bound, size=shape) on numpy's legacy global stream, generated by the
     library's MT19937 replay (same values, same final state, a fraction of the time)."""
@@ -273,3 +300,33 @@ def legacy_randint(bound, shape):
         raise CatchB200Error(rc, 'cb_mt19937_randint')
     np.random.set_state((name, key, p.value, has_gauss, cached))
     return out.reshape(shape)
+
+
+class PendingRandint:
+    """legacy_randint running on the library's worker thread: result() waits for it, advances
+    numpy's global state and returns the draws.  Nothing else may use np.random in between."""
+
+    def __init__(self, bound, shape):
+        self.L = load()
+        self.shape = shape
+        st = np.random.get_state()
+        self.sync = None
+        if st[0] != 'MT19937':
+            self.sync = np.random.randint(0, bound, size=shape)
+            return
+        self.name, key, pos, self.has_gauss, self.cached = st
+        self.key = np.ascontiguousarray(key, dtype=np.uint32).copy()
+        self.out = np.empty(int(np.prod(shape)), dtype=np.int32)
+        self.pos = C.c_int32(int(pos))
+        self.job = self.L.cb_mt19937_randint_begin(self.key.ctypes.data, C.byref(self.pos), int(bound),
+                                                   self.out.size, self.out.ctypes.data)
+
+    def result(self):
+        if self.sync is not None:
+            return self.sync
+        rc = self.L.cb_mt19937_randint_end(self.job)
+        self.job = None
+        if rc != 0:
+            raise CatchB200Error(rc, 'cb_mt19937_randint')
+        np.random.set_state((self.name, self.key, self.pos.value, self.has_gauss, self.cached))
+        return self.out.reshape(self.shape)

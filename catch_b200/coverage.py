@@ -19,28 +19,21 @@ def _concat_ascii(strs):
     return buf, off, raw
 
 
-_ACGT = bytes(b'ACGT')
-
-
-def make_alphabet(*byte_buffers):
-    """Code table for the bit-plane packing: distinct bytes -> dense codes.  Two bases match
-    iff their bytes are equal (utils/longest_common_substring.py:110), so any injective code
-    works; ACGT-only input gets 2 planes, ACGT+N 3, arbitrary test alphabets up to 8."""
-    present = set(_ACGT)
-    for buf in byte_buffers:
-        # strip the four common bases at C speed; what is left (usually nothing) is small
-        present.update(bytes(buf).translate(None, _ACGT))
-    symbols = np.array(sorted(present), dtype=np.intp)
-    lut = np.zeros(256, dtype=np.uint8)
-    lut[symbols] = np.arange(len(symbols), dtype=np.uint8)
-    bits = max(1, int(np.ceil(np.log2(len(symbols)))))
-    return lut, bits
+def join_probes(probe_strs):
+    """The probes as one newline-separated bytes object (the form cb_upload_group takes)."""
+    try:
+        return '\n'.join(probe_strs).encode('latin-1')
+    except UnicodeEncodeError:
+        raise ValueError("sequences must contain single-byte characters only")
 
 
 class PackedGroup:
-    """Probes + targets of one grouping, resident on the device."""
+    """Probes + targets of one grouping, resident on the device (one cb_upload_group call: both
+    host->device copies, the code table derived on the device, both packings)."""
 
-    def __init__(self, ctx, probe_strs, genomes):
+    def __init__(self, ctx, probe_strs, genomes, p_raw=None):
+        """`p_raw`: the probes already joined with newlines and encoded (join_probes), if the
+        caller has them."""
         self.ctx = ctx
         self.n_probes = len(probe_strs)
         seqs, seq_genome = [], []
@@ -49,15 +42,31 @@ class PackedGroup:
                 seqs.append(s)
                 seq_genome.append(j)
         self.n_genomes = len(genomes)
-        self.target_bases = sum(len(s) for s in seqs)
-        p_buf, self.probe_off, p_raw = _concat_ascii(probe_strs)
-        t_buf, seq_off, t_raw = _concat_ascii(seqs)
-        lut, bits = make_alphabet(p_raw, t_raw)
-        self.bits = bits
+        _, seq_off, t_raw = _concat_ascii(seqs)
+        self.target_bases = int(seq_off[-1])
         sg = np.array(seq_genome if seq_genome else [0], dtype=np.int32)
-        self.targets, self.st_targets = ctx.upload_targets(t_buf, seq_off, sg, self.n_genomes, lut, bits)
-        self.probes, self.st_probes = ctx.upload_probes(p_buf, self.probe_off, lut, bits)
-        self.h2d_bytes = int(self.probe_off[-1] + seq_off[-1])
+        # probes go over as ONE newline-joined buffer; the library finds the boundaries, so no
+        # per-probe length pass is needed on the host
+        if p_raw is None:
+            p_raw = join_probes(probe_strs)
+        try:
+            self.probes, self.targets, self.probe_len, self.bits, st = ctx.upload_group(
+                p_raw, self.n_probes, t_raw, seq_off, sg, self.n_genomes)
+        except _lib.CatchB200Error as e:
+            if e.code != -2 or 'separator' not in str(e):
+                raise
+            # a probe contains the separator byte itself: pass explicit offsets instead
+            _, off, p_raw = _concat_ascii(probe_strs)
+            self.probes, self.targets, self.probe_len, self.bits, st = ctx.upload_group(
+                p_raw, self.n_probes, t_raw, seq_off, sg, self.n_genomes, probe_off=off)
+        self.st_targets, self.st_probes = st, _lib.Stats()
+        self.h2d_bytes = int(len(p_raw) + len(t_raw))
+
+    @property
+    def probe_off(self):
+        off = np.zeros(self.n_probes + 1, dtype=np.int64)
+        np.cumsum(self.probe_len, out=off[1:])
+        return off
 
     def free(self):
         self.targets.free()
@@ -99,18 +108,37 @@ def dedup_map(probe_strs):
     return [last[s] for s in probe_strs]
 
 
+def draw_seeds(lengths, mismatches, lcf_thres, kmer_probe_map_k, background=False):
+    """(k, seeds, mode) for probes of the given lengths; consumes numpy's global RNG in random
+    mode.  Only needs the lengths.  With background=True the generator may run on the library's
+    worker thread while the caller packs and uploads the sequences; `seeds` is then a pending
+    object until finish_draw() is applied (nothing else may touch np.random in between)."""
+    return probe_mod.choose_seed_positions(lengths, mismatches, lcf_thres, min_k=kmer_probe_map_k,
+                                           k=kmer_probe_map_k, randint=_lib.legacy_randint,
+                                           randint_async=_lib.PendingRandint if background else None)
+
+
+def finish_draw(drawn):
+    k, seeds, mode = drawn
+    if hasattr(seeds, 'result'):
+        seeds = seeds.result()
+    return k, seeds, mode
+
+
 class SeedPlan:
     """The seed choice for one probe list: drawn on the host (it consumes numpy's global RNG
     exactly like probe.construct_kmer_probe_map_to_find_probe_covers, probe.py:507-577), then
     handed to cb_coverage as a CSR.  Drawing is separate from the device call so that a rank
     which does not own a grouping can still advance the RNG stream identically."""
 
-    def __init__(self, probe_strs, mismatches, lcf_thres, kmer_probe_map_k, lengths=None, may_have_dups=True):
-        if lengths is None:
-            lengths = np.fromiter((len(s) for s in probe_strs), dtype=np.int64, count=len(probe_strs))
-        self.k, seeds, self.mode = probe_mod.choose_seed_positions(
-            lengths, mismatches, lcf_thres, min_k=kmer_probe_map_k, k=kmer_probe_map_k,
-            randint=_lib.legacy_randint)
+    def __init__(self, probe_strs, mismatches, lcf_thres, kmer_probe_map_k, lengths=None, may_have_dups=True,
+                 drawn=None):
+        """`drawn`: the result of draw_seeds() when the draw was done ahead of time."""
+        if drawn is None:
+            if lengths is None:
+                lengths = np.fromiter(map(len, probe_strs), dtype=np.int64, count=len(probe_strs))
+            drawn = draw_seeds(lengths, mismatches, lcf_thres, kmer_probe_map_k)
+        self.k, seeds, self.mode = drawn
         # may_have_dups=False: the device already established that all probes are distinct
         self.rep = dedup_map(probe_strs) if may_have_dups else None
         self.seed_off, self.seed_pos = seeds_to_csr(np.asarray(seeds), self.rep)

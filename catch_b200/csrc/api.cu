@@ -2,6 +2,7 @@
 // the thin wrappers around the stage implementations.
 #include <algorithm>
 #include <cstring>
+#include <thread>
 
 #include "internal.cuh"
 
@@ -13,6 +14,152 @@ static int upload_common_lut(cb_ctx *ctx, const uint8_t lut[256], int bits, DevB
     CB_CUDA(ctx, d_lut.alloc(256));
     CB_CUDA(ctx, cudaMemcpyAsync(d_lut.p, lut, 256, cudaMemcpyHostToDevice, ctx->stream));
     return CB_OK;
+}
+
+// ---- staging and packing shared by cb_upload_targets / cb_upload_probes / cb_upload_group
+extern "C" void cb_targets_free(cb_targets *t);
+extern "C" void cb_probes_free(cb_probes *p);
+
+// host tables (sequence starts, universe layout), allocations and the host->device copy of the
+// bytes; *out is allocated here and owned by the caller from then on
+static int targets_stage(cb_ctx *ctx, const uint8_t *ascii, const int64_t *seq_off, int64_t n_seqs,
+                         const int32_t *seq_genome, int32_t n_genomes, cb_targets **out, DevBuf<uint8_t> &d_ascii)
+{
+    if (n_seqs < 0 || n_genomes < 0) return cb_fail(ctx, CB_ERR_ARG, "bad argument");
+    if (n_seqs > 0 && (!seq_off || !seq_genome)) return cb_fail(ctx, CB_ERR_ARG, "null sequence table");
+    cudaStream_t st = ctx->stream;
+    const int64_t T = n_seqs ? seq_off[n_seqs] - seq_off[0] : 0;
+    if (T > 0 && !ascii) return cb_fail(ctx, CB_ERR_ARG, "null ascii");
+    cb_targets *t = new cb_targets();
+    *out = t;
+    t->ctx = ctx;
+    t->n_seqs = n_seqs;
+    t->n_genomes = n_genomes;
+    t->total_bases = T;
+    t->h_seq_start.resize((size_t)n_seqs + 1);
+    t->h_genome_len.assign((size_t)n_genomes, 0);
+    std::vector<int64_t> seq_in_genome((size_t)n_seqs, 0);
+    for (int64_t i = 0; i < n_seqs; i++) {
+        const int64_t len = seq_off[i + 1] - seq_off[i];
+        if (len < 0) return cb_fail(ctx, CB_ERR_ARG, "seq_off not monotone");
+        const int32_t g = seq_genome[i];
+        if (g < 0 || g >= n_genomes || (i > 0 && g < seq_genome[i - 1]))
+            return cb_fail(ctx, CB_ERR_ARG, "seq_genome must be non-decreasing and < n_genomes");
+        t->h_seq_start[(size_t)i] = seq_off[i] - seq_off[0];
+        seq_in_genome[(size_t)i] = t->h_genome_len[(size_t)g];      // length_so_far, set_cover_filter.py:418,453
+        t->h_genome_len[(size_t)g] += len;
+    }
+    t->h_seq_start[(size_t)n_seqs] = T;
+    t->h_ubase.resize((size_t)n_genomes + 1);
+    uint64_t ub = 0;
+    for (int32_t g = 0; g < n_genomes; g++) {
+        t->h_ubase[(size_t)g] = (uint32_t)ub;
+        ub = (ub + (uint64_t)t->h_genome_len[(size_t)g] + 1 + 63) & ~63ull;    // >= 1 spare bit, 64-aligned
+        if (ub >= 0xffffff00ull) return cb_fail(ctx, CB_ERR_UNSUPPORTED, "target group exceeds 2^32 universe bits");
+    }
+    t->h_ubase[(size_t)n_genomes] = (uint32_t)ub;
+    t->universe_bits = (int64_t)ub;
+    std::vector<uint32_t> h_seq_ubase((size_t)n_seqs);
+    for (int64_t i = 0; i < n_seqs; i++)
+        h_seq_ubase[(size_t)i] = t->h_ubase[(size_t)seq_genome[i]] + (uint32_t)seq_in_genome[(size_t)i];
+
+    int64_t pw = (T + CB_FRONT_PAD + 63) / 64 + CB_TILE_WORDS + CB_BACK_PAD_WORDS;
+    pw = (pw + 1) & ~1ll;
+    t->plane_words = pw;
+    CB_CUDA(ctx, cb_dev_alloc(st, (void **)&t->d_seq_start, sizeof(int64_t) * (size_t)(n_seqs + 1)));
+    CB_CUDA(ctx, cb_dev_alloc(st, (void **)&t->d_seq_genome, sizeof(int32_t) * (size_t)(n_seqs + 1)));
+    CB_CUDA(ctx, cb_dev_alloc(st, (void **)&t->d_seq_ubase, sizeof(uint32_t) * (size_t)(n_seqs + 1)));
+    CB_CUDA(ctx, cb_dev_alloc(st, (void **)&t->d_ubase, sizeof(uint32_t) * (size_t)(n_genomes + 1)));
+    CB_CUDA(ctx, d_ascii.alloc((size_t)T));
+    if (T) CB_CUDA(ctx, cudaMemcpyAsync(d_ascii.p, ascii + seq_off[0], (size_t)T, cudaMemcpyHostToDevice, st));
+    CB_CUDA(ctx, cudaMemcpyAsync(t->d_seq_start, t->h_seq_start.data(), sizeof(int64_t) * (size_t)(n_seqs + 1), cudaMemcpyHostToDevice, st));
+    if (n_seqs) {
+        CB_CUDA(ctx, cudaMemcpyAsync(t->d_seq_genome, seq_genome, sizeof(int32_t) * (size_t)n_seqs, cudaMemcpyHostToDevice, st));
+        CB_CUDA(ctx, cudaMemcpyAsync(t->d_seq_ubase, h_seq_ubase.data(), sizeof(uint32_t) * (size_t)n_seqs, cudaMemcpyHostToDevice, st));
+    }
+    CB_CUDA(ctx, cudaMemcpyAsync(t->d_ubase, t->h_ubase.data(), sizeof(uint32_t) * (size_t)(n_genomes + 1), cudaMemcpyHostToDevice, st));
+    CB_CUDA(ctx, cudaStreamSynchronize(st));      // h_seq_ubase goes out of scope
+    return CB_OK;
+}
+
+static int targets_pack(cb_ctx *ctx, cb_targets *t, const uint8_t *d_ascii, const uint8_t lut[256], int bits)
+{
+    DevBuf<uint8_t> d_lut;
+    CB_TRY(upload_common_lut(ctx, lut, bits, d_lut));
+    t->bits = bits;
+    memcpy(t->lut, lut, 256);
+    CB_CUDA(ctx, cb_dev_alloc(ctx->stream, (void **)&t->d_planes, sizeof(uint64_t) * (size_t)t->plane_words * (size_t)bits));
+    return cb_launch_pack_targets(ctx, d_ascii, t->total_bases, d_lut.p, bits, t->d_planes, t->plane_words);
+}
+
+// Probes either with explicit offsets (probe_off != NULL) or as one buffer of `bytes` bytes in
+// which consecutive probes are separated by one `sep` byte (offsets found here with memchr).
+static int probes_stage(cb_ctx *ctx, const uint8_t *ascii, int64_t bytes, const int64_t *probe_off, int64_t n_probes,
+                        int sep, int32_t *len_out, cb_probes **out, DevBuf<uint8_t> &d_ascii, DevBuf<int64_t> &d_off)
+{
+    if (n_probes < 0) return cb_fail(ctx, CB_ERR_ARG, "bad argument");
+    if (n_probes > 0 && !ascii && (probe_off ? probe_off[n_probes] > probe_off[0] : bytes > 0))
+        return cb_fail(ctx, CB_ERR_ARG, "null probe bytes");
+    if (n_probes >= 0xfffffff0ll) return cb_fail(ctx, CB_ERR_UNSUPPORTED, "too many probes");
+    cudaStream_t st = ctx->stream;
+    std::vector<int64_t> rel((size_t)n_probes + 1, 0);
+    int64_t total = 0;
+    const int gap = probe_off ? 0 : 1;
+    if (probe_off) {
+        for (int64_t i = 0; i <= n_probes; i++) rel[(size_t)i] = probe_off[i] - probe_off[0];
+        total = rel[(size_t)n_probes];
+        ascii = ascii ? ascii + probe_off[0] : ascii;
+    } else if (n_probes > 0) {
+        if (sep < 0 || sep > 255 || bytes < n_probes - 1) return cb_fail(ctx, CB_ERR_ARG, "bad separator / size");
+        const uint8_t *q = ascii, *end = ascii + bytes;
+        for (int64_t i = 0; i < n_probes; i++) {
+            rel[(size_t)i] = q - ascii;
+            const uint8_t *hit = (q < end) ? (const uint8_t *)memchr(q, sep, (size_t)(end - q)) : nullptr;
+            if (i + 1 < n_probes) {
+                if (!hit) return cb_fail(ctx, CB_ERR_ARG, "fewer separators than probes");
+                q = hit + 1;
+            } else if (hit) {
+                return cb_fail(ctx, CB_ERR_ARG, "separator byte occurs inside a probe");
+            }
+        }
+        rel[(size_t)n_probes] = bytes + 1;          // as if a separator followed the last probe
+        total = bytes;
+    }
+    int max_len = 0;
+    for (int64_t i = 0; i < n_probes; i++) {
+        const int64_t len = rel[(size_t)i + 1] - rel[(size_t)i] - gap;
+        if (len < 0) return cb_fail(ctx, CB_ERR_ARG, "probe_off not monotone");
+        if (len > CB_MAX_PROBE_LEN) return cb_fail(ctx, CB_ERR_UNSUPPORTED, "probe longer than CB_MAX_PROBE_LEN (256)");
+        if (len > max_len) max_len = (int)len;
+        if (len_out) len_out[i] = (int32_t)len;
+    }
+    cb_probes *p = new cb_probes();
+    *out = p;
+    p->ctx = ctx;
+    p->n_probes = n_probes;
+    p->max_len = max_len;
+    p->nw = max_len ? (max_len + 63) / 64 : 1;
+    CB_CUDA(ctx, cb_dev_alloc(st, (void **)&p->d_len, sizeof(int32_t) * (size_t)(n_probes ? n_probes : 1)));
+    CB_CUDA(ctx, d_ascii.alloc((size_t)total));
+    CB_CUDA(ctx, d_off.alloc((size_t)n_probes + 1));
+    if (n_probes) {
+        if (total) CB_CUDA(ctx, cudaMemcpyAsync(d_ascii.p, ascii, (size_t)total, cudaMemcpyHostToDevice, st));
+        CB_CUDA(ctx, cudaMemcpyAsync(d_off.p, rel.data(), sizeof(int64_t) * (size_t)(n_probes + 1), cudaMemcpyHostToDevice, st));
+        CB_CUDA(ctx, cudaStreamSynchronize(st));    // `rel` goes out of scope
+    }
+    return CB_OK;
+}
+
+static int probes_pack(cb_ctx *ctx, cb_probes *p, const uint8_t *d_ascii, const int64_t *d_off, int gap,
+                       const uint8_t lut[256], int bits)
+{
+    DevBuf<uint8_t> d_lut;
+    CB_TRY(upload_common_lut(ctx, lut, bits, d_lut));
+    p->bits = bits;
+    memcpy(p->lut, lut, 256);
+    CB_CUDA(ctx, cb_dev_alloc(ctx->stream, (void **)&p->d_words,
+                              sizeof(uint64_t) * (size_t)(p->n_probes ? p->n_probes : 1) * (size_t)bits * (size_t)p->nw));
+    return cb_launch_pack_probes(ctx, d_ascii, d_off, gap, p->n_probes, d_lut.p, bits, p->nw, p->d_words, p->d_len);
 }
 
 thread_local cudaStream_t cb_tls_stream = nullptr;
@@ -81,77 +228,23 @@ int cb_upload_targets(cb_ctx *ctx, const uint8_t *ascii, const int64_t *seq_off,
                       const int32_t *seq_genome, int32_t n_genomes, const uint8_t lut[256], int32_t bits,
                       cb_targets **out, cb_stats *stats)
 {
-    if (!ctx || !out || !lut || n_seqs < 0 || n_genomes < 0) return cb_fail(ctx, CB_ERR_ARG, "bad argument");
-    if (n_seqs > 0 && (!seq_off || !seq_genome)) return cb_fail(ctx, CB_ERR_ARG, "null sequence table");
+    if (!ctx || !out || !lut) return cb_fail(ctx, CB_ERR_ARG, "bad argument");
     *out = nullptr;
     if (stats) memset(stats, 0, sizeof *stats);
     ctx->launches = 0;
     CB_CUDA(ctx, cudaSetDevice(ctx->device));
     cb_tls_stream = ctx->stream;
     cudaStream_t st = ctx->stream;
-    const int64_t T = n_seqs ? seq_off[n_seqs] - seq_off[0] : 0;
-    if (T > 0 && !ascii) return cb_fail(ctx, CB_ERR_ARG, "null ascii");
-
-    cb_targets *t = new cb_targets();
-    struct Guard { cb_targets *t; ~Guard() { if (t) cb_targets_free(t); } } guard{t};
-    t->ctx = ctx;
-    t->bits = bits;
-    t->n_seqs = n_seqs;
-    t->n_genomes = n_genomes;
-    t->total_bases = T;
-    memcpy(t->lut, lut, 256);
-    // host tables: target coordinate of each sequence, universe layout
-    t->h_seq_start.resize((size_t)n_seqs + 1);
-    t->h_genome_len.assign((size_t)n_genomes, 0);
-    std::vector<int64_t> seq_in_genome((size_t)n_seqs, 0);
-    for (int64_t i = 0; i < n_seqs; i++) {
-        const int64_t len = seq_off[i + 1] - seq_off[i];
-        if (len < 0) return cb_fail(ctx, CB_ERR_ARG, "seq_off not monotone");
-        const int32_t g = seq_genome[i];
-        if (g < 0 || g >= n_genomes || (i > 0 && g < seq_genome[i - 1]))
-            return cb_fail(ctx, CB_ERR_ARG, "seq_genome must be non-decreasing and < n_genomes");
-        t->h_seq_start[(size_t)i] = seq_off[i] - seq_off[0];
-        seq_in_genome[(size_t)i] = t->h_genome_len[(size_t)g];      // length_so_far, set_cover_filter.py:418,453
-        t->h_genome_len[(size_t)g] += len;
-    }
-    t->h_seq_start[(size_t)n_seqs] = T;
-    t->h_ubase.resize((size_t)n_genomes + 1);
-    uint64_t ub = 0;
-    for (int32_t g = 0; g < n_genomes; g++) {
-        t->h_ubase[(size_t)g] = (uint32_t)ub;
-        ub = (ub + (uint64_t)t->h_genome_len[(size_t)g] + 1 + 63) & ~63ull;    // >= 1 spare bit, 64-aligned
-        if (ub >= 0xffffff00ull) return cb_fail(ctx, CB_ERR_UNSUPPORTED, "target group exceeds 2^32 universe bits");
-    }
-    t->h_ubase[(size_t)n_genomes] = (uint32_t)ub;
-    t->universe_bits = (int64_t)ub;
-    std::vector<uint32_t> h_seq_ubase((size_t)n_seqs);
-    for (int64_t i = 0; i < n_seqs; i++)
-        h_seq_ubase[(size_t)i] = t->h_ubase[(size_t)seq_genome[i]] + (uint32_t)seq_in_genome[(size_t)i];
-
-    int64_t pw = (T + CB_FRONT_PAD + 63) / 64 + CB_TILE_WORDS + CB_BACK_PAD_WORDS;
-    pw = (pw + 1) & ~1ll;
-    t->plane_words = pw;
     EventTimer t_all(st), t_h2d(st), t_pack(st);
     t_all.start();
-    CB_CUDA(ctx, cb_dev_alloc(st, (void **)&t->d_planes, sizeof(uint64_t) * (size_t)pw * (size_t)bits));
-    CB_CUDA(ctx, cb_dev_alloc(st, (void **)&t->d_seq_start, sizeof(int64_t) * (size_t)(n_seqs + 1)));
-    CB_CUDA(ctx, cb_dev_alloc(st, (void **)&t->d_seq_genome, sizeof(int32_t) * (size_t)(n_seqs + 1)));
-    CB_CUDA(ctx, cb_dev_alloc(st, (void **)&t->d_seq_ubase, sizeof(uint32_t) * (size_t)(n_seqs + 1)));
-    CB_CUDA(ctx, cb_dev_alloc(st, (void **)&t->d_ubase, sizeof(uint32_t) * (size_t)(n_genomes + 1)));
-    DevBuf<uint8_t> d_ascii, d_lut;
-    CB_TRY(upload_common_lut(ctx, lut, bits, d_lut));
-    CB_CUDA(ctx, d_ascii.alloc((size_t)T));
+    cb_targets *t = nullptr;
+    struct Guard { cb_targets **t; ~Guard() { if (*t) cb_targets_free(*t); } } guard{&t};
+    DevBuf<uint8_t> d_ascii;
     t_h2d.start();
-    if (T) CB_CUDA(ctx, cudaMemcpyAsync(d_ascii.p, ascii + seq_off[0], (size_t)T, cudaMemcpyHostToDevice, st));
-    CB_CUDA(ctx, cudaMemcpyAsync(t->d_seq_start, t->h_seq_start.data(), sizeof(int64_t) * (size_t)(n_seqs + 1), cudaMemcpyHostToDevice, st));
-    if (n_seqs) {
-        CB_CUDA(ctx, cudaMemcpyAsync(t->d_seq_genome, seq_genome, sizeof(int32_t) * (size_t)n_seqs, cudaMemcpyHostToDevice, st));
-        CB_CUDA(ctx, cudaMemcpyAsync(t->d_seq_ubase, h_seq_ubase.data(), sizeof(uint32_t) * (size_t)n_seqs, cudaMemcpyHostToDevice, st));
-    }
-    CB_CUDA(ctx, cudaMemcpyAsync(t->d_ubase, t->h_ubase.data(), sizeof(uint32_t) * (size_t)(n_genomes + 1), cudaMemcpyHostToDevice, st));
+    CB_TRY(targets_stage(ctx, ascii, seq_off, n_seqs, seq_genome, n_genomes, &t, d_ascii));
     t_h2d.stop();
     t_pack.start();
-    CB_TRY(cb_launch_pack_targets(ctx, d_ascii.p, T, d_lut.p, bits, t->d_planes, pw));
+    CB_TRY(targets_pack(ctx, t, d_ascii.p, lut, bits));
     t_pack.stop();
     t_all.stop();
     CB_CUDA(ctx, cudaStreamSynchronize(st));
@@ -161,8 +254,8 @@ int cb_upload_targets(cb_ctx *ctx, const uint8_t *ascii, const int64_t *seq_off,
         stats->ms_total = t_all.ms();
         stats->n_kernel_launches = ctx->launches;
     }
-    guard.t = nullptr;
     *out = t;
+    t = nullptr;
     return CB_OK;
 }
 
@@ -181,51 +274,24 @@ void cb_targets_free(cb_targets *t)
 int cb_upload_probes(cb_ctx *ctx, const uint8_t *ascii, const int64_t *probe_off, int64_t n_probes,
                      const uint8_t lut[256], int32_t bits, cb_probes **out, cb_stats *stats)
 {
-    if (!ctx || !out || !lut || n_probes < 0) return cb_fail(ctx, CB_ERR_ARG, "bad argument");
-    if (n_probes > 0 && (!probe_off || !ascii)) return cb_fail(ctx, CB_ERR_ARG, "null probe table");
-    if (n_probes >= 0xfffffff0ll) return cb_fail(ctx, CB_ERR_UNSUPPORTED, "too many probes");
+    if (!ctx || !out || !lut) return cb_fail(ctx, CB_ERR_ARG, "bad argument");
     *out = nullptr;
     if (stats) memset(stats, 0, sizeof *stats);
     ctx->launches = 0;
     CB_CUDA(ctx, cudaSetDevice(ctx->device));
     cb_tls_stream = ctx->stream;
     cudaStream_t st = ctx->stream;
-    int max_len = 0;
-    for (int64_t i = 0; i < n_probes; i++) {
-        const int64_t len = probe_off[i + 1] - probe_off[i];
-        if (len < 0) return cb_fail(ctx, CB_ERR_ARG, "probe_off not monotone");
-        if (len > CB_MAX_PROBE_LEN) return cb_fail(ctx, CB_ERR_UNSUPPORTED, "probe longer than CB_MAX_PROBE_LEN (256)");
-        if (len > max_len) max_len = (int)len;
-    }
-    cb_probes *p = new cb_probes();
-    struct Guard { cb_probes *p; ~Guard() { if (p) cb_probes_free(p); } } guard{p};
-    p->ctx = ctx;
-    p->bits = bits;
-    p->n_probes = n_probes;
-    p->max_len = max_len;
-    p->nw = max_len ? (max_len + 63) / 64 : 1;
-    memcpy(p->lut, lut, 256);
-    const int64_t total = n_probes ? probe_off[n_probes] - probe_off[0] : 0;
     EventTimer t_all(st), t_h2d(st), t_pack(st);
     t_all.start();
-    CB_CUDA(ctx, cb_dev_alloc(st, (void **)&p->d_words, sizeof(uint64_t) * (size_t)(n_probes ? n_probes : 1) * (size_t)bits * (size_t)p->nw));
-    CB_CUDA(ctx, cb_dev_alloc(st, (void **)&p->d_len, sizeof(int32_t) * (size_t)(n_probes ? n_probes : 1)));
-    DevBuf<uint8_t> d_ascii, d_lut;
+    cb_probes *p = nullptr;
+    struct Guard { cb_probes **p; ~Guard() { if (*p) cb_probes_free(*p); } } guard{&p};
+    DevBuf<uint8_t> d_ascii;
     DevBuf<int64_t> d_off;
-    CB_TRY(upload_common_lut(ctx, lut, bits, d_lut));
-    CB_CUDA(ctx, d_ascii.alloc((size_t)total));
-    CB_CUDA(ctx, d_off.alloc((size_t)n_probes + 1));
     t_h2d.start();
-    if (n_probes) {
-        std::vector<int64_t> rel((size_t)n_probes + 1);
-        for (int64_t i = 0; i <= n_probes; i++) rel[(size_t)i] = probe_off[i] - probe_off[0];
-        if (total) CB_CUDA(ctx, cudaMemcpyAsync(d_ascii.p, ascii + probe_off[0], (size_t)total, cudaMemcpyHostToDevice, st));
-        CB_CUDA(ctx, cudaMemcpyAsync(d_off.p, rel.data(), sizeof(int64_t) * (size_t)(n_probes + 1), cudaMemcpyHostToDevice, st));
-        CB_CUDA(ctx, cudaStreamSynchronize(st));    // `rel` goes out of scope
-    }
+    CB_TRY(probes_stage(ctx, ascii, 0, probe_off, n_probes, -1, nullptr, &p, d_ascii, d_off));
     t_h2d.stop();
     t_pack.start();
-    CB_TRY(cb_launch_pack_probes(ctx, d_ascii.p, d_off.p, n_probes, d_lut.p, bits, p->nw, p->d_words, p->d_len));
+    CB_TRY(probes_pack(ctx, p, d_ascii.p, d_off.p, 0, lut, bits));
     t_pack.stop();
     t_all.stop();
     CB_CUDA(ctx, cudaStreamSynchronize(st));
@@ -235,8 +301,77 @@ int cb_upload_probes(cb_ctx *ctx, const uint8_t *ascii, const int64_t *probe_off
         stats->ms_total = t_all.ms();
         stats->n_kernel_launches = ctx->launches;
     }
-    guard.p = nullptr;
     *out = p;
+    p = nullptr;
+    return CB_OK;
+}
+
+int cb_upload_group(cb_ctx *ctx, const uint8_t *probes_ascii, int64_t probes_bytes, const int64_t *probe_off,
+                    int64_t n_probes, int32_t sep, const uint8_t *targets_ascii, const int64_t *seq_off,
+                    int64_t n_seqs, const int32_t *seq_genome, int32_t n_genomes, int32_t *probe_len_out,
+                    int32_t *bits_out, cb_probes **probes_out, cb_targets **targets_out, cb_stats *stats)
+{
+    if (!ctx || !probes_out || !targets_out) return cb_fail(ctx, CB_ERR_ARG, "bad argument");
+    *probes_out = nullptr;
+    *targets_out = nullptr;
+    if (stats) memset(stats, 0, sizeof *stats);
+    ctx->launches = 0;
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cb_tls_stream = ctx->stream;
+    cudaStream_t st = ctx->stream;
+    EventTimer t_all(st), t_h2d(st), t_pack(st);
+    t_all.start();
+    cb_probes *p = nullptr;
+    cb_targets *t = nullptr;
+    struct Guard {
+        cb_probes **p; cb_targets **t;
+        ~Guard() { if (*p) cb_probes_free(*p); if (*t) cb_targets_free(*t); }
+    } guard{&p, &t};
+    DevBuf<uint8_t> d_pascii, d_tascii;
+    DevBuf<int64_t> d_off;
+    DevBuf<uint32_t> d_present;
+    t_h2d.start();
+    CB_TRY(targets_stage(ctx, targets_ascii, seq_off, n_seqs, seq_genome, n_genomes, &t, d_tascii));
+    CB_TRY(probes_stage(ctx, probes_ascii, probes_bytes, probe_off, n_probes, probe_off ? -1 : sep, probe_len_out,
+                        &p, d_pascii, d_off));
+    t_h2d.stop();
+    t_pack.start();
+    // code table: the distinct bytes of both buffers (ACGT always) get dense codes in byte order,
+    // found on the device since the bytes are there anyway
+    CB_CUDA(ctx, d_present.alloc(512));
+    CB_CUDA(ctx, cudaMemsetAsync(d_present.p, 0, sizeof(uint32_t) * 512, st));
+    const int64_t pbytes = probe_off ? (n_probes ? probe_off[n_probes] - probe_off[0] : 0) : probes_bytes;
+    CB_TRY(cb_launch_byte_presence(ctx, d_pascii.p, pbytes, d_present.p));
+    CB_TRY(cb_launch_byte_presence(ctx, d_tascii.p, t->total_bases, d_present.p + 256));
+    uint32_t h_present[512];
+    CB_CUDA(ctx, cudaMemcpyAsync(h_present, d_present.p, sizeof h_present, cudaMemcpyDeviceToHost, st));
+    CB_CUDA(ctx, cudaStreamSynchronize(st));
+    if (!probe_off && sep >= 0 && sep < 256) h_present[sep] = 0;          // separators are not symbols
+    uint8_t lut[256];
+    memset(lut, 0, sizeof lut);
+    int n_sym = 0;
+    for (int c = 0; c < 256; c++) {
+        const bool here = h_present[c] || h_present[256 + c] || c == 'A' || c == 'C' || c == 'G' || c == 'T';
+        if (here) lut[c] = (uint8_t)n_sym++;
+    }
+    int bits = 1;
+    while ((1 << bits) < n_sym) bits++;
+    CB_TRY(targets_pack(ctx, t, d_tascii.p, lut, bits));
+    CB_TRY(probes_pack(ctx, p, d_pascii.p, d_off.p, probe_off ? 0 : 1, lut, bits));
+    t_pack.stop();
+    t_all.stop();
+    CB_CUDA(ctx, cudaStreamSynchronize(st));
+    if (bits_out) *bits_out = bits;
+    if (stats) {
+        stats->ms_h2d = t_h2d.ms();
+        stats->ms_pack = t_pack.ms();
+        stats->ms_total = t_all.ms();
+        stats->n_kernel_launches = ctx->launches;
+    }
+    *probes_out = p;
+    *targets_out = t;
+    p = nullptr;
+    t = nullptr;
     return CB_OK;
 }
 
@@ -297,6 +432,47 @@ int cb_mt19937_randint(uint32_t *key, int32_t *pos, uint32_t bound, int64_t n, i
     }
     *pos = p;
     return CB_OK;
+}
+
+// The same replay on a native thread, so the host can pack and upload sequences meanwhile (no
+// Python thread, no GIL hand-over): begin returns at once, end joins and returns the status.
+struct cb_rng_job {
+    std::thread th;
+    int rc = CB_OK;
+};
+
+cb_rng_job *cb_mt19937_randint_begin(uint32_t *key, int32_t *pos, uint32_t bound, int64_t n, int32_t *out)
+{
+    cb_rng_job *job = new cb_rng_job();
+    job->th = std::thread([=]() { job->rc = cb_mt19937_randint(key, pos, bound, n, out); });
+    return job;
+}
+
+int cb_mt19937_randint_end(cb_rng_job *job)
+{
+    if (!job) return CB_ERR_ARG;
+    if (job->th.joinable()) job->th.join();
+    const int rc = job->rc;
+    delete job;
+    return rc;
+}
+
+int cb_split_lengths(const uint8_t *buf, int64_t bytes, int64_t n, int32_t sep, int32_t *len_out)
+{
+    if (n < 0 || bytes < 0 || sep < 0 || sep > 255 || (n > 0 && !len_out) || (bytes > 0 && !buf)) return CB_ERR_ARG;
+    const uint8_t *q = buf, *end = buf + bytes;
+    for (int64_t i = 0; i < n; i++) {
+        const uint8_t *hit = (q < end) ? (const uint8_t *)memchr(q, sep, (size_t)(end - q)) : nullptr;
+        if (i + 1 < n) {
+            if (!hit) return CB_ERR_ARG;
+            len_out[i] = (int32_t)(hit - q);
+            q = hit + 1;
+        } else {
+            if (hit) return CB_ERR_ARG;
+            len_out[i] = (int32_t)(end - q);
+        }
+    }
+    return (n == 0 && bytes > 0) ? CB_ERR_ARG : CB_OK;
 }
 
 int cb_probes_have_duplicates(cb_ctx *ctx, const cb_probes *probes, int32_t *has_dup)

@@ -166,8 +166,9 @@ int cb_exclusive_scan_u32_to_i64(cb_ctx *ctx, const uint32_t *d_in, int64_t *d_o
 // pack.cu
 int cb_launch_pack_targets(cb_ctx *ctx, const uint8_t *d_ascii, int64_t total, const uint8_t *d_lut,
                            int bits, uint64_t *d_planes, int64_t plane_words);
-int cb_launch_pack_probes(cb_ctx *ctx, const uint8_t *d_ascii, const int64_t *d_off, int64_t n_probes,
+int cb_launch_pack_probes(cb_ctx *ctx, const uint8_t *d_ascii, const int64_t *d_off, int gap, int64_t n_probes,
                           const uint8_t *d_lut, int bits, int nw, uint64_t *d_words, int32_t *d_len);
+int cb_launch_byte_presence(cb_ctx *ctx, const uint8_t *d_buf, int64_t n, uint32_t *d_present);
 
 int cb_probes_have_duplicates_impl(cb_ctx *ctx, const cb_probes *probes, int32_t *has_dup);
 

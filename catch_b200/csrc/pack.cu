@@ -36,7 +36,7 @@ pack_targets_kernel(const uint8_t *__restrict__ ascii, int64_t total, const uint
 }
 
 __global__ void __launch_bounds__(PACK_THREADS)
-pack_probes_kernel(const uint8_t *__restrict__ ascii, const int64_t *__restrict__ off, int64_t n_probes,
+pack_probes_kernel(const uint8_t *__restrict__ ascii, const int64_t *__restrict__ off, int gap, int64_t n_probes,
                    const uint8_t *__restrict__ lut, int bits, int nw, uint64_t *__restrict__ words,
                    int32_t *__restrict__ lens)
 {
@@ -48,7 +48,7 @@ pack_probes_kernel(const uint8_t *__restrict__ ascii, const int64_t *__restrict_
     const int64_t n_warps = ((int64_t)gridDim.x * PACK_THREADS) >> 5;
     for (int64_t p = warp; p < n_probes; p += n_warps) {
         const int64_t beg = off[p];
-        const int len = (int)(off[p + 1] - beg);
+        const int len = (int)(off[p + 1] - beg) - gap;      // gap: separator bytes between probes
         if (lane == 0) lens[p] = len;
         uint64_t *dst = words + p * (int64_t)bits * nw;
         for (int w = 0; w < nw; w++) {
@@ -82,20 +82,64 @@ int cb_launch_pack_targets(cb_ctx *ctx, const uint8_t *d_ascii, int64_t total, c
     return CB_OK;
 }
 
-int cb_launch_pack_probes(cb_ctx *ctx, const uint8_t *d_ascii, const int64_t *d_off, int64_t n_probes,
+int cb_launch_pack_probes(cb_ctx *ctx, const uint8_t *d_ascii, const int64_t *d_off, int gap, int64_t n_probes,
                           const uint8_t *d_lut, int bits, int nw, uint64_t *d_words, int32_t *d_len)
 {
     if (n_probes == 0) return CB_OK;
     int64_t blocks = (n_probes * 32 + PACK_THREADS - 1) / PACK_THREADS;
     int64_t cap = (int64_t)ctx->sm_count * 16;
     if (blocks > cap) blocks = cap;
-    pack_probes_kernel<<<(unsigned)blocks, PACK_THREADS, 0, ctx->stream>>>(d_ascii, d_off, n_probes, d_lut,
+    pack_probes_kernel<<<(unsigned)blocks, PACK_THREADS, 0, ctx->stream>>>(d_ascii, d_off, gap, n_probes, d_lut,
                                                                            bits, nw, d_words, d_len);
     ctx->launches++;
     CB_CUDA(ctx, cudaGetLastError());
     return CB_OK;
 }
 
+
+// ---- which byte values occur (for the code table): per-CTA 256-entry presence in shared memory
+namespace {
+__global__ void __launch_bounds__(PACK_THREADS)
+byte_presence_kernel(const uint8_t *__restrict__ buf, int64_t n, uint32_t *__restrict__ present)
+{
+    __shared__ uint32_t s_present[256];
+    s_present[threadIdx.x] = 0u;
+    __syncthreads();
+    const int64_t tid = (int64_t)blockIdx.x * PACK_THREADS + threadIdx.x, nthr = (int64_t)gridDim.x * PACK_THREADS;
+    // 16 bytes per load once the pointer is aligned; the ragged head and tail byte-wise
+    const int64_t head = min(n, (int64_t)((16 - ((uintptr_t)buf & 15)) & 15));
+    const int64_t n_vec = (n - head) >> 4;
+    const uint4 *v = reinterpret_cast<const uint4 *>(buf + head);
+    uint32_t last = 0xffffffffu;
+    for (int64_t i = tid; i < n_vec; i += nthr) {
+        const uint4 q = v[i];
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (w[j] == last) continue;                 // runs of the same 4 bytes are common
+            last = w[j];
+#pragma unroll
+            for (int b = 0; b < 4; b++) s_present[(w[j] >> (8 * b)) & 0xffu] = 1u;
+        }
+    }
+    for (int64_t i = tid; i < head; i += nthr) s_present[buf[i]] = 1u;
+    for (int64_t i = head + (n_vec << 4) + tid; i < n; i += nthr) s_present[buf[i]] = 1u;
+    __syncthreads();
+    if (s_present[threadIdx.x]) present[threadIdx.x] = 1u;
+}
+}  // namespace
+
+int cb_launch_byte_presence(cb_ctx *ctx, const uint8_t *d_buf, int64_t n, uint32_t *d_present)
+{
+    if (n <= 0) return CB_OK;
+    int64_t blocks = (n / 16 + PACK_THREADS - 1) / PACK_THREADS;
+    if (blocks < 1) blocks = 1;
+    if (blocks > (int64_t)ctx->sm_count * 8) blocks = (int64_t)ctx->sm_count * 8;
+    byte_presence_kernel<<<(unsigned)blocks, PACK_THREADS, 0, ctx->stream>>>(d_buf, n, d_present);
+    ctx->launches++;
+    CB_CUDA(ctx, cudaGetLastError());
+    return CB_OK;
+}
 
 // ---- duplicate detection: 64-bit hash of every packed probe into an open-addressing table
 namespace {

@@ -185,19 +185,38 @@ class SetCoverFilter(BaseFilter):
                 now = time.perf_counter()
                 host_ms[name] = host_ms.get(name, 0.0) + (now - t_mark) * 1e3
                 t_mark = now
+            drawn = drawn_tol = None
             if mine and probe_strs:
-                group = cov.PackedGroup(self._context(), probe_strs, target_genomes)
-                mark('pack_and_upload')
-                lengths = np.diff(group.probe_off)
-                dups = self._context().probes_have_duplicates(group.probes)
-                mark('duplicate_check')
+                p_raw = cov.join_probes(probe_strs)
+                lengths = _lib.split_lengths(p_raw, len(probe_strs))
+                mark('join')
+                if lengths is not None:
+                    # the seed draw needs only the lengths: it runs on the library's worker thread
+                    # while the sequences are copied to the device and packed.  The tolerant draw
+                    # (ranks) continues the same stream, so it follows once the first has finished.
+                    drawn = cov.draw_seeds(lengths, self.mismatches, self.lcf_thres, self.kmer_probe_map_k,
+                                           background=True)
+                try:
+                    group = cov.PackedGroup(self._context(), probe_strs, target_genomes, p_raw=p_raw)
+                    mark('pack_and_upload')
+                    dups = self._context().probes_have_duplicates(group.probes)
+                    mark('duplicate_check')
+                finally:
+                    if drawn is not None:
+                        drawn = cov.finish_draw(drawn)
+                if drawn is not None and self._needs_ranks():
+                    drawn_tol = cov.draw_seeds(lengths, self.mismatches_tolerant, self.lcf_thres_tolerant,
+                                               self.kmer_probe_map_k)
+                lengths = group.probe_len
+                mark('seed_draw_wait')
             plan = plan_tol = None
             if probe_strs:
                 plan = cov.SeedPlan(probe_strs, self.mismatches, self.lcf_thres, self.kmer_probe_map_k,
-                                    lengths=lengths, may_have_dups=dups and mine)
+                                    lengths=lengths, may_have_dups=dups and mine, drawn=drawn)
                 if self._needs_ranks():
                     plan_tol = cov.SeedPlan(probe_strs, self.mismatches_tolerant, self.lcf_thres_tolerant,
-                                            self.kmer_probe_map_k, lengths=lengths, may_have_dups=dups and mine)
+                                            self.kmer_probe_map_k, lengths=lengths, may_have_dups=dups and mine,
+                                            drawn=drawn_tol)
                 mark('seed_plan')
             self._host_ms = host_ms
             if not mine:

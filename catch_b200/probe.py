@@ -111,7 +111,7 @@ def pigeonhole_kmer_length(probe_length, mismatches, min_k):
 
 
 def choose_seed_positions(lengths, mismatches, lcf_thres, min_k=20, k=20, num_kmers_per_probe=20,
-                          randint=None):
+                          randint=None, randint_async=None):
     """Seed start positions for every probe of a list, as the reference would select them.
 
     Args:
@@ -126,7 +126,9 @@ def choose_seed_positions(lengths, mismatches, lcf_thres, min_k=20, k=20, num_km
     np.random.choice(L - k + 1, size=20, replace=True) from numpy's legacy global stream
     (probe.py:386-398).  For a run of probes of equal length that is the same stream as one
     np.random.randint(0, L - k + 1, size=(run, 20)) call, which is what is used here; `randint`
-    may supply a faster generator of the same stream (catch_b200._lib.legacy_randint).
+    may supply a faster generator of the same stream (catch_b200._lib.legacy_randint);
+    `randint_async(bound, shape)` may start that generator in the background, in which case
+    `seeds` is returned as a pending object with a result() method (single-length lists only).
     """
     lengths = np.asarray(lengths, dtype=np.int64)
     n = len(lengths)
@@ -143,6 +145,10 @@ def choose_seed_positions(lengths, mismatches, lcf_thres, min_k=20, k=20, num_km
             pass
     if np.any(lengths < k):
         raise ValueError("k is larger than the length of a probe")
+    if randint_async is not None and not differ:
+        # one run of equal lengths = one generator call, which may run in the background:
+        # the third element is then an object whose result() yields the [n, s] draws
+        return k, randint_async(L0 - k + 1, (n, num_kmers_per_probe)), 'random'
     seeds = np.empty((n, num_kmers_per_probe), dtype=np.int32)
     # runs of equal length, in list order
     change = np.flatnonzero(np.diff(lengths)) + 1

@@ -105,6 +105,32 @@ int cb_upload_probes(cb_ctx *ctx, const uint8_t *ascii, const int64_t *probe_off
                      const uint8_t lut[256], int32_t bits, cb_probes **out, cb_stats *stats);
 void cb_probes_free(cb_probes *p);
 
+/* Both uploads of one grouping in a single call, with the code table derived on the device: the
+ * distinct bytes of the two buffers (A, C, G, T always included) get dense codes in byte order,
+ * *bits_out = ceil(log2(#symbols)) planes.  This is what SetCoverFilter._filter does per grouping
+ * before _make_sets (filter/set_cover_filter.py:359-470 receives str sequences; here they are
+ * packed once).
+ * Probes come either with explicit offsets (probe_off != NULL, probes_bytes/sep ignored) or as ONE
+ * buffer of probes_bytes bytes in which consecutive probes are separated by a single `sep` byte
+ * (what '\n'.join(...) produces; no trailing separator); the offsets are then found here, which
+ * spares the host a per-probe length pass.  CB_ERR_ARG if the number of separators is not
+ * n_probes - 1.  probe_len_out (nullable) receives the n_probes probe lengths. */
+int cb_upload_group(cb_ctx *ctx, const uint8_t *probes_ascii, int64_t probes_bytes, const int64_t *probe_off,
+                    int64_t n_probes, int32_t sep, const uint8_t *targets_ascii, const int64_t *seq_off,
+                    int64_t n_seqs, const int32_t *seq_genome, int32_t n_genomes, int32_t *probe_len_out,
+                    int32_t *bits_out, cb_probes **probes_out, cb_targets **targets_out, cb_stats *stats);
+
+/* The same on a native worker thread: _begin returns immediately, _end waits for the draw and
+ * returns its status.  key/pos/out must stay valid and untouched in between.  Lets the caller
+ * overlap the (host-only) seed draw with cb_upload_group. */
+typedef struct cb_rng_job cb_rng_job;
+cb_rng_job *cb_mt19937_randint_begin(uint32_t *key, int32_t *pos, uint32_t bound, int64_t n, int32_t *out);
+int cb_mt19937_randint_end(cb_rng_job *job);
+
+/* Host-side helper (no device work): lengths of the n strings held in `buf`, consecutive strings
+ * separated by one `sep` byte (see cb_upload_group).  CB_ERR_ARG unless exactly n-1 separators occur. */
+int cb_split_lengths(const uint8_t *buf, int64_t bytes, int64_t n, int32_t sep, int32_t *len_out);
+
 /* 1 in *has_dup if two probes may have the same sequence (decided from a 64-bit hash of the
  * packed probe: equal sequences always report 1, distinct ones almost never).  Lets the host skip
  * its duplicate bookkeeping (filter/set_cover_filter.py:408-412) in the common duplicate-free case. */

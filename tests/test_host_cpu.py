@@ -109,3 +109,36 @@ def test_filters_fail_loudly_without_a_gpu():
                      input_is_grouped=True)
     with pytest.raises(NotImplementedError):
         SetCoverFilter(0, 10, custom_cover_range_fn=('x.py', 'f'))
+
+
+def test_mt19937_replay_matches_numpy_sync_and_background():
+    """cb_mt19937_randint (and its worker-thread variant) continue numpy's legacy stream exactly:
+    same draws as np.random.randint and the same generator state afterwards (probe.py:393-396)."""
+    from catch_b200 import _lib
+    for bound, shape, seed in [(56, (1000, 20), 7), (81, (333, 20), 1), (1, (5, 20), 2), (64, (700, 20), 3),
+                               (2, (10, 3), 4)]:
+        np.random.seed(seed)
+        np.random.randint(0, 10, size=17)             # start from a position inside a block
+        state0 = np.random.get_state()
+        want = np.random.randint(0, bound, size=shape)
+        after = int(np.random.randint(0, 1 << 30))
+        np.random.set_state(state0)
+        got = _lib.legacy_randint(bound, shape)
+        assert np.array_equal(got, want)
+        assert int(np.random.randint(0, 1 << 30)) == after
+        np.random.set_state(state0)
+        pending = _lib.PendingRandint(bound, shape)
+        got = pending.result()
+        assert np.array_equal(got, want)
+        assert int(np.random.randint(0, 1 << 30)) == after
+
+
+def test_split_lengths():
+    from catch_b200 import _lib
+    strs = ['ACGT', '', 'A', 'GGGTTT', '']
+    raw = '\n'.join(strs).encode()
+    assert _lib.split_lengths(raw, len(strs)).tolist() == [len(s) for s in strs]
+    assert _lib.split_lengths(raw, len(strs) + 1) is None
+    assert _lib.split_lengths(raw, len(strs) - 1) is None
+    assert _lib.split_lengths(b'', 0).tolist() == []
+    assert _lib.split_lengths(b'', 1).tolist() == [0]

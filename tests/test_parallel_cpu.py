@@ -45,8 +45,8 @@ def _worker(rank, world_size, port, out_path):
     from catch_b200 import coverage as cov
 
     class FakeGroup:
-        def __init__(self, ctx, probe_strs, genomes):
-            self.probe_off = np.concatenate(([0], np.cumsum([len(s) for s in probe_strs]))).astype(np.int64)
+        def __init__(self, ctx, probe_strs, genomes, p_raw=None):
+            self.probe_len = np.array([len(s) for s in probe_strs], dtype=np.int32)
             self.probes = None
 
         def free(self):
