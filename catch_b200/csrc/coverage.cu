@@ -854,6 +854,10 @@ scan_kernel(const ScanParams P)
                     }
                     j = lo;
                 }
+                // the HITS_PER_THREAD alignments of a thread are independent instruction chains: they are
+                // all evaluated before any result is pushed, so the scheduler can interleave them
+                bool owner_v[HITS_PER_THREAD];
+                uint64_t task_v[HITS_PER_THREAD];
 #pragma unroll
                 for (int u = 0; u < HITS_PER_THREAD; u++) {
                     const uint32_t h = h0 + u;
@@ -883,13 +887,27 @@ scan_kernel(const ScanParams P)
                             task = ((uint64_t)j << 40) | ((uint64_t)pos << 32) | (uint64_t)p;
                         }
                     }
-                    __syncwarp();
-                    const unsigned owners = __ballot_sync(0xffffffffu, owner);
-                    if (owners) {                        // warp-aggregated push
-                        uint32_t qb = 0;
-                        if (lane == 0) qb = atomicAdd(&s_qcount, (uint32_t)__popc(owners));
-                        qb = __shfl_sync(0xffffffffu, qb, 0);
-                        if (owner) s_queue[qb + __popc(owners & ((1u << lane) - 1u))] = task;
+                    owner_v[u] = owner;
+                    task_v[u] = task;
+                }
+                __syncwarp();
+                // one warp-aggregated push for all of them
+                unsigned ow[HITS_PER_THREAD];
+                uint32_t n_push = 0;
+#pragma unroll
+                for (int u = 0; u < HITS_PER_THREAD; u++) {
+                    ow[u] = __ballot_sync(0xffffffffu, owner_v[u]);
+                    n_push += __popc(ow[u]);
+                }
+                if (n_push) {
+                    uint32_t qb = 0;
+                    if (lane == 0) qb = atomicAdd(&s_qcount, n_push);
+                    qb = __shfl_sync(0xffffffffu, qb, 0);
+                    uint32_t before = 0;
+#pragma unroll
+                    for (int u = 0; u < HITS_PER_THREAD; u++) {
+                        if (owner_v[u]) s_queue[qb + before + __popc(ow[u] & ((1u << lane) - 1u))] = task_v[u];
+                        before += __popc(ow[u]);
                     }
                 }
             }
