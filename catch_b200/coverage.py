@@ -5,6 +5,11 @@ import numpy as np
 from catch_b200 import _lib
 from catch_b200 import probe as probe_mod
 
+try:                                    # host-side glue built next to libcatchb200.so (csrc/fastpack.c)
+    from catch_b200 import _fastpack
+except ImportError:                     # pure-Python gathering below does the same, slower
+    _fastpack = None
+
 
 def _concat_ascii(strs):
     """(uint8 array of all bytes, int64 offsets) for a list of str."""
@@ -19,21 +24,29 @@ def _concat_ascii(strs):
     return buf, off, raw
 
 
-def join_probes(probe_strs):
-    """The probes as one newline-separated bytes object (the form cb_upload_group takes)."""
+def gather_probes(probes):
+    """(bytes of all sequences back to back, int32 lengths) for a list of Probe objects (or str).
+    One C pass over the list when the _fastpack helper is built."""
+    n = len(probes)
+    if _fastpack is not None:
+        data, lens = _fastpack.gather(probes, 'seq_str')
+        return data, np.frombuffer(lens, dtype=np.int32, count=n)
+    strs = [p if isinstance(p, str) else p.seq_str for p in probes]
+    lens = np.fromiter(map(len, strs), dtype=np.int32, count=n)
     try:
-        return '\n'.join(probe_strs).encode('latin-1')
+        data = ''.join(strs).encode('latin-1')
     except UnicodeEncodeError:
         raise ValueError("sequences must contain single-byte characters only")
+    return data, lens
 
 
 class PackedGroup:
     """Probes + targets of one grouping, resident on the device (one cb_upload_group call: both
     host->device copies, the code table derived on the device, both packings)."""
 
-    def __init__(self, ctx, probe_strs, genomes, p_raw=None):
-        """`p_raw`: the probes already joined with newlines and encoded (join_probes), if the
-        caller has them."""
+    def __init__(self, ctx, probe_strs, genomes, gathered=None):
+        """`probe_strs`: list of str (or of objects with .seq_str).  `gathered`: the result of
+        gather_probes() on it, if the caller already has that."""
         self.ctx = ctx
         self.n_probes = len(probe_strs)
         seqs, seq_genome = [], []
@@ -45,20 +58,11 @@ class PackedGroup:
         _, seq_off, t_raw = _concat_ascii(seqs)
         self.target_bases = int(seq_off[-1])
         sg = np.array(seq_genome if seq_genome else [0], dtype=np.int32)
-        # probes go over as ONE newline-joined buffer; the library finds the boundaries, so no
-        # per-probe length pass is needed on the host
-        if p_raw is None:
-            p_raw = join_probes(probe_strs)
-        try:
-            self.probes, self.targets, self.probe_len, self.bits, st = ctx.upload_group(
-                p_raw, self.n_probes, t_raw, seq_off, sg, self.n_genomes)
-        except _lib.CatchB200Error as e:
-            if e.code != -2 or 'separator' not in str(e):
-                raise
-            # a probe contains the separator byte itself: pass explicit offsets instead
-            _, off, p_raw = _concat_ascii(probe_strs)
-            self.probes, self.targets, self.probe_len, self.bits, st = ctx.upload_group(
-                p_raw, self.n_probes, t_raw, seq_off, sg, self.n_genomes, probe_off=off)
+        p_raw, lens = gathered if gathered is not None else gather_probes(probe_strs)
+        off = np.zeros(self.n_probes + 1, dtype=np.int64)
+        np.cumsum(lens, out=off[1:])
+        self.probes, self.targets, self.probe_len, self.bits, st = ctx.upload_group(
+            p_raw, self.n_probes, t_raw, seq_off, sg, self.n_genomes, probe_off=off)
         self.st_targets, self.st_probes = st, _lib.Stats()
         self.h2d_bytes = int(len(p_raw) + len(t_raw))
 

@@ -43,6 +43,29 @@ def _reverse_complement(s):
     return s[::-1].translate(_RC)
 
 
+class _LazyStrs:
+    """The seq_str of every probe of a list, materialised on first use: the common path (no
+    duplicates, no ranks) never needs the Python strings, only the gathered bytes."""
+
+    def __init__(self, probes):
+        self._probes = probes
+        self._strs = None
+
+    def _get(self):
+        if self._strs is None:
+            self._strs = [p.seq_str for p in self._probes]
+        return self._strs
+
+    def __len__(self):
+        return len(self._probes)
+
+    def __iter__(self):
+        return iter(self._get())
+
+    def __getitem__(self, i):
+        return self._get()[i]
+
+
 class SetCoverFilter(BaseFilter):
     def __init__(self, mismatches, lcf_thres, island_of_exact_match=0, mismatches_tolerant=None,
                  lcf_thres_tolerant=None, island_of_exact_match_tolerant=None,
@@ -170,7 +193,8 @@ class SetCoverFilter(BaseFilter):
         local = {}
         for group_i, (possible_probes, target_genomes) in enumerate(zip(input, target_genomes_grouped)):
             possible_probes = list(possible_probes)
-            probe_strs = [p.seq_str for p in possible_probes]
+            n_probes = len(possible_probes)
+            probe_strs = _LazyStrs(possible_probes)
             # The seed draws consume numpy's global RNG per grouping, in grouping order, first for
             # _make_sets and then for _make_ranks (set_cover_filter.py:824-827); every rank replays
             # all of them so that a sharded run sees the same stream as a single process.
@@ -186,31 +210,29 @@ class SetCoverFilter(BaseFilter):
                 host_ms[name] = host_ms.get(name, 0.0) + (now - t_mark) * 1e3
                 t_mark = now
             drawn = drawn_tol = None
-            if mine and probe_strs:
-                p_raw = cov.join_probes(probe_strs)
-                lengths = _lib.split_lengths(p_raw, len(probe_strs))
-                mark('join')
-                if lengths is not None:
-                    # the seed draw needs only the lengths: it runs on the library's worker thread
-                    # while the sequences are copied to the device and packed.  The tolerant draw
-                    # (ranks) continues the same stream, so it follows once the first has finished.
-                    drawn = cov.draw_seeds(lengths, self.mismatches, self.lcf_thres, self.kmer_probe_map_k,
-                                           background=True)
+            if n_probes:
+                gathered = cov.gather_probes(possible_probes)
+                lengths = gathered[1]
+                mark('gather')
+            if mine and n_probes:
+                # the seed draw needs only the lengths: it runs on the library's worker thread
+                # while the sequences are copied to the device and packed.  The tolerant draw
+                # (ranks) continues the same stream, so it follows once the first has finished.
+                drawn = cov.draw_seeds(lengths, self.mismatches, self.lcf_thres, self.kmer_probe_map_k,
+                                       background=True)
                 try:
-                    group = cov.PackedGroup(self._context(), probe_strs, target_genomes, p_raw=p_raw)
+                    group = cov.PackedGroup(self._context(), possible_probes, target_genomes, gathered=gathered)
                     mark('pack_and_upload')
                     dups = self._context().probes_have_duplicates(group.probes)
                     mark('duplicate_check')
                 finally:
-                    if drawn is not None:
-                        drawn = cov.finish_draw(drawn)
-                if drawn is not None and self._needs_ranks():
+                    drawn = cov.finish_draw(drawn)
+                if self._needs_ranks():
                     drawn_tol = cov.draw_seeds(lengths, self.mismatches_tolerant, self.lcf_thres_tolerant,
                                                self.kmer_probe_map_k)
-                lengths = group.probe_len
                 mark('seed_draw_wait')
             plan = plan_tol = None
-            if probe_strs:
+            if n_probes:
                 plan = cov.SeedPlan(probe_strs, self.mismatches, self.lcf_thres, self.kmer_probe_map_k,
                                     lengths=lengths, may_have_dups=dups and mine, drawn=drawn)
                 if self._needs_ranks():

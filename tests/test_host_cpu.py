@@ -142,3 +142,29 @@ def test_split_lengths():
     assert _lib.split_lengths(raw, len(strs) - 1) is None
     assert _lib.split_lengths(b'', 0).tolist() == []
     assert _lib.split_lengths(b'', 1).tolist() == [0]
+
+
+def test_gather_probes_c_helper_matches_python():
+    """_fastpack.gather (one C pass over the Probe list) gives the bytes and lengths that the plain
+    Python join would; wide characters are rejected like the Python path rejects them."""
+    from catch_b200 import coverage as cov
+    from catch_b200 import probe
+    assert cov._fastpack is not None, "catch_b200/_fastpack.so is not built"
+    strs = ['ACGT', '', 'N' * 300, 'ACGTNRYK', 'A']
+    for items in (strs, [probe.Probe.from_str(s) for s in strs], tuple(strs), []):
+        data, lens = cov.gather_probes(items)
+        assert data == ''.join(strs[:len(items)]).encode() and lens.tolist() == [len(s) for s in strs[:len(items)]]
+    saved, cov._fastpack = cov._fastpack, None
+    try:
+        data2, lens2 = cov.gather_probes([probe.Probe.from_str(s) for s in strs])
+    finally:
+        cov._fastpack = saved
+    assert data2 == ''.join(strs).encode() and lens2.tolist() == [len(s) for s in strs]
+    for bad in (['ACΔT'], [probe.Probe.from_str('A\U0001F600')]):
+        with pytest.raises(ValueError):
+            cov.gather_probes(bad)
+    with pytest.raises((TypeError, AttributeError)):
+        cov._fastpack.gather([1, 2], 'seq_str')
+    # latin-1 characters are single bytes and pass through
+    data, lens = cov.gather_probes(['A\xe9'])
+    assert data == b'A\xe9' and lens.tolist() == [2]

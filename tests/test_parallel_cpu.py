@@ -45,7 +45,7 @@ def _worker(rank, world_size, port, out_path):
     from catch_b200 import coverage as cov
 
     class FakeGroup:
-        def __init__(self, ctx, probe_strs, genomes, p_raw=None):
+        def __init__(self, ctx, probe_strs, genomes, gathered=None):
             self.probe_len = np.array([len(s) for s in probe_strs], dtype=np.int32)
             self.probes = None
 
