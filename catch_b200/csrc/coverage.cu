@@ -35,10 +35,13 @@
 namespace {
 
 constexpr int SCAN_THREADS = 256;
+#ifndef SCAN_MIN_BLOCKS
+#define SCAN_MIN_BLOCKS 4
+#endif
 constexpr int POS_PER_THREAD = CB_TILE / SCAN_THREADS;
 constexpr int TW = CB_TILE_WORDS;
 constexpr int HITS_PER_THREAD = 4;
-constexpr int QUEUE_CAP = 2048;
+constexpr int QUEUE_CAP = 1536;           // 12 KB: keeps the CTA under 32 KB so four fit beside a large L1
 constexpr int QUEUE_FLUSH = QUEUE_CAP - SCAN_THREADS * HITS_PER_THREAD;
 constexpr int MAX_LOCAL_REC = 4;
 
@@ -725,7 +728,7 @@ __device__ __forceinline__ int run_owner_task_fast(const ScanParams &P, U128 M, 
 }
 
 template <int NW, int KC>
-__global__ void __launch_bounds__(SCAN_THREADS)
+__global__ void __launch_bounds__(SCAN_THREADS, SCAN_MIN_BLOCKS)
 scan_kernel(const ScanParams P)
 {
     __shared__ __align__(128) uint64_t s_tile[CB_MAX_SYMBOL_BITS * TW];

@@ -732,6 +732,103 @@ greedy_inc_kernel(const GreedyParams G)
     }
 }
 
+// apply() for ONE winner interval by ONE WARP (parallel-rounds kernel: thousands of winner intervals
+// per round, each a short dependent chain of loads, so many of them must be in flight per SM).
+// Same work as apply_interval; `s_uw` is the warp's private APPLY_WORDS-word staging area.
+__device__ __forceinline__ void apply_interval_warp(const GreedyParams &G, int64_t i, unsigned long long *s_uw, int lane)
+{
+    const uint2 r = G.iv[i];
+    const uint2 xr = G.ivx[i];
+    if (r.x >= r.y) return;
+    const uint32_t w0 = r.x >> 6, w1 = (r.y - 1) >> 6;
+    const uint32_t nwords = w1 - w0 + 1;
+    const int64_t x0 = xr.x, x1 = xr.y;
+    if (nwords > (uint32_t)APPLY_WORDS) {          // very long interval: count against L2, no staging
+        for (int64_t x = x0 + lane; x < x1; x += 32) {
+            const uint4 item = __ldg(G.blk_items + x);
+            const uint32_t os = max(item.x, r.x), oe = min(item.y, r.y);
+            if (os < oe) {
+                const uint32_t dlt = popcount_range_cg(G.U, os, oe);
+                if (dlt) atomicSub(&G.gain[item.z], dlt);
+            }
+        }
+        __syncwarp();
+        uint32_t c = 0;
+        for (uint32_t wd = w0 + lane; wd <= w1; wd += 32) {
+            unsigned long long m = ~0ull;
+            if (wd == w0) m &= ~0ull << (r.x & 63);
+            if (wd == w1) m &= ~0ull >> (63 - ((r.y - 1) & 63));
+            const unsigned long long old = atomicAnd(&G.U[wd], ~m);
+            c += __popcll(old & m);
+        }
+        if (c) atomicAdd(G.remaining, (unsigned long long)(-(long long)c));
+        __syncwarp();
+        return;
+    }
+    unsigned long long mine[APPLY_WORDS / 32];
+#pragma unroll
+    for (int h = 0; h < APPLY_WORDS / 32; h++) {
+        const uint32_t q = (uint32_t)lane + 32u * h;
+        mine[h] = 0ull;
+        if (q < nwords) {
+            unsigned long long m = ~0ull;
+            const uint32_t wd = w0 + q;
+            if (wd == w0) m &= ~0ull << (r.x & 63);
+            if (wd == w1) m &= ~0ull >> (63 - ((r.y - 1) & 63));
+            mine[h] = __ldcg(G.U + wd) & m;
+            s_uw[q] = mine[h];
+        }
+    }
+    constexpr int BATCH = 8;
+    uint4 item[BATCH];
+#pragma unroll
+    for (int u = 0; u < BATCH; u++) {
+        const int64_t x = x0 + lane + (int64_t)u * 32;
+        item[u] = x < x1 ? __ldg(G.blk_items + x) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    bool have = false;
+#pragma unroll
+    for (int h = 0; h < APPLY_WORDS / 32; h++) have |= mine[h] != 0ull;
+    if (!__any_sync(0xffffffffu, have)) return;    // everything here is covered already (also orders s_uw)
+    int64_t xb = x0 + lane;
+    for (;;) {
+#pragma unroll
+        for (int u = 0; u < BATCH; u++) {
+            const uint32_t os = max(item[u].x, r.x), oe = min(item[u].y, r.y);
+            if (os < oe) {
+                const uint32_t wa = (os >> 6) - w0, wb = ((oe - 1) >> 6) - w0;
+                uint32_t dlt = 0;
+                for (uint32_t q = wa; q <= wb; q++) {
+                    unsigned long long m = ~0ull;
+                    if (q == wa) m &= ~0ull << (os & 63);
+                    if (q == wb) m &= ~0ull >> (63 - ((oe - 1) & 63));
+                    dlt += __popcll(s_uw[q] & m);
+                }
+                if (dlt) atomicSub(&G.gain[item[u].z], dlt);
+            }
+        }
+        xb += 32 * BATCH;
+        if (xb - lane >= x1) break;                 // warp-uniform
+#pragma unroll
+        for (int u = 0; u < BATCH; u++) {
+            const int64_t x = xb + (int64_t)u * 32;
+            item[u] = x < x1 ? __ldg(G.blk_items + x) : make_uint4(0u, 0u, 0u, 0u);
+        }
+    }
+    // clear exactly the bits that were set (nobody else touches them)
+    uint32_t c = 0;
+#pragma unroll
+    for (int h = 0; h < APPLY_WORDS / 32; h++)
+        if (mine[h]) {
+            atomicAnd(&G.U[w0 + lane + 32u * h], ~mine[h]);
+            c += __popcll(mine[h]);
+        }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0 && c) atomicAdd(G.remaining, (unsigned long long)(-(long long)c));
+    __syncwarp();                                   // s_uw is reused by the warp's next interval
+}
+
 // ---------------------------------------------------------------------------------------
 // Incremental greedy in PARALLEL ROUNDS (every p_u == 1).
 //
@@ -776,11 +873,11 @@ __device__ __forceinline__ void for_each_word(uint2 r, F f)
     }
 }
 
-__global__ void __launch_bounds__(GREEDY_THREADS)
+__global__ void __launch_bounds__(GREEDY_THREADS, 3)
 greedy_par_kernel(const GreedyParams G)
 {
     __shared__ unsigned long long s_key[GREEDY_THREADS / 32];
-    __shared__ unsigned long long s_u[APPLY_WORDS];
+    __shared__ unsigned long long s_u[(GREEDY_THREADS / 32) * APPLY_WORDS];   // one staging area per warp
     __shared__ uint32_t s_part[GREEDY_THREADS / 32];
     extern __shared__ uint32_t s_dyn[];
     // per CTA, list_cap entries each: active candidates (probe, gain, first interval, exclusive prefix
@@ -1048,13 +1145,13 @@ greedy_par_kernel(const GreedyParams G)
         // ---- apply every accepted probe: (winner, interval) pairs are dealt round-robin to the CTAs
         {
             const uint32_t total = s_wbase[n_win];
-            for (uint32_t f = blockIdx.x; f < total; f += gridDim.x) {
+            for (uint32_t f = (uint32_t)warp * gridDim.x + blockIdx.x; f < total; f += gridDim.x * NWARP) {
                 uint32_t lo = 0, hi = n_win;
                 while (hi - lo > 1) {
                     const uint32_t mid = (lo + hi) >> 1;
                     if (s_wbase[mid] <= f) lo = mid; else hi = mid;
                 }
-                apply_interval(G, (int64_t)s_wi0[lo] + (f - s_wbase[lo]), s_u);
+                apply_interval_warp(G, (int64_t)s_wi0[lo] + (f - s_wbase[lo]), s_u + warp * APPLY_WORDS, lane);
             }
         }
         lap(2);
@@ -1189,10 +1286,10 @@ int cb_setcover_impl(cb_ctx *ctx, const cb_cover *cover, const int32_t *ranks, c
     const bool legacy = full_mode || (mode_env && !strcmp(mode_env, "legacy")) ||
                         (getenv("CB_GREEDY_LEGACY") && getenv("CB_GREEDY_LEGACY")[0] == '1');
     const bool par = !legacy && !(mode_env && !strcmp(mode_env, "inc"));
-    uint32_t list_cap = par ? (uint32_t)PAR_LIST_CAP : 4096u;
+    uint32_t list_cap = par ? 2048u : 4096u;          // par: <= PAR_LIST_CAP; 2048 leaves room for 3 CTAs per SM
     if (const char *e = getenv("CB_GREEDY_LIST_CAP")) {
         const int v = atoi(e);
-        if (v >= 1 && (uint32_t)v <= list_cap) list_cap = (uint32_t)v;
+        if (v >= 1 && (uint32_t)v <= (par ? (uint32_t)PAR_LIST_CAP : 4096u)) list_cap = (uint32_t)v;
     }
     CB_CUDA(ctx, d_list.alloc(list_cap + 1));
     CB_CUDA(ctx, d_pub.alloc(8));
@@ -1255,7 +1352,7 @@ int cb_setcover_impl(cb_ctx *ctx, const cb_cover *cover, const int32_t *ranks, c
     }
     else CB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, greedy_inc_kernel, GREEDY_THREADS, 0));
     if (per_sm < 1) return cb_fail(ctx, CB_ERR_CUDA, "greedy kernel does not fit on an SM");
-    int want = 2;
+    int want = par ? 3 : 2;
     if (const char *e = getenv("CB_GREEDY_BLOCKS_PER_SM")) want = atoi(e) > 0 ? atoi(e) : want;
     if (per_sm > want) per_sm = want;
     const int grid = per_sm * ctx->sm_count;
