@@ -41,9 +41,10 @@ class Stats(C.Structure):
 EXPORTED_SYMBOLS = [
     'cb_init', 'cb_destroy', 'cb_last_error', 'cb_version', 'cb_flush_l2',
     'cb_upload_targets', 'cb_targets_free', 'cb_upload_probes', 'cb_probes_free', 'cb_upload_group',
-    'cb_probes_have_duplicates', 'cb_mt19937_randint', 'cb_mt19937_randint_begin', 'cb_mt19937_randint_end',
+    'cb_probes_have_duplicates', 'cb_mt19937_randint', 'cb_mt19937_randint_u8', 'cb_mt19937_randint_begin',
+    'cb_mt19937_randint_end',
     'cb_split_lengths',
-    'cb_coverage', 'cb_cover_free', 'cb_cover_num_intervals', 'cb_cover_export', 'cb_cover_import',
+    'cb_coverage', 'cb_coverage_uniform', 'cb_cover_free', 'cb_cover_num_intervals', 'cb_cover_export', 'cb_cover_import',
     'cb_setcover', 'cb_minhash_neardup', 'cb_hamming_neardup',
     'cb_comm_unique_id', 'cb_comm_init', 'cb_comm_destroy', 'cb_cover_allgather',
 ]
@@ -78,12 +79,14 @@ def load():
                                   C.POINTER(vp), C.POINTER(vp), C.POINTER(Stats)]
     L.cb_probes_free.restype = None
     L.cb_probes_have_duplicates.argtypes = [vp, vp, C.POINTER(i32)]
-    L.cb_mt19937_randint_begin.argtypes = [vp, C.POINTER(i32), C.c_uint32, i64, vp]
+    L.cb_mt19937_randint_u8.argtypes = [vp, C.POINTER(i32), C.c_uint32, i64, vp]
+    L.cb_mt19937_randint_begin.argtypes = [vp, C.POINTER(i32), C.c_uint32, i64, vp, i32]
     L.cb_mt19937_randint_begin.restype = vp
     L.cb_mt19937_randint_end.argtypes = [vp]
     L.cb_split_lengths.argtypes = [vp, i64, i64, i32, vp]
     L.cb_mt19937_randint.argtypes = [vp, C.POINTER(i32), C.c_uint32, i64, vp]
     L.cb_coverage.argtypes = [vp, vp, vp, C.POINTER(HybParams), vp, vp, C.POINTER(vp), C.POINTER(Stats)]
+    L.cb_coverage_uniform.argtypes = [vp, vp, vp, C.POINTER(HybParams), vp, i32, C.POINTER(vp), C.POINTER(Stats)]
     L.cb_cover_free.argtypes = [vp]
     L.cb_cover_free.restype = None
     L.cb_cover_num_intervals.argtypes = [vp]
@@ -103,6 +106,9 @@ def load():
 
 def _ptr(a):
     return a.ctypes.data if a is not None else None
+
+
+_ONE_BYTE = np.zeros(1, dtype=np.uint8)
 
 
 class Context:
@@ -177,6 +183,16 @@ class Context:
         out, st = C.c_void_p(), Stats()
         self._check(self.L.cb_coverage(self.h, probes.h, targets.h, C.byref(hp), _ptr(seed_off),
                                        _ptr(seed_pos), C.byref(out), C.byref(st)))
+        return Handle(self.L.cb_cover_free, out), st
+
+    def coverage_uniform(self, probes, targets, mismatches, lcf_thres, island, cover_extension, k, seeds_u8):
+        """cb_coverage_uniform: `seeds_u8` is a C-contiguous uint8 [n_probes, s] matrix."""
+        hp = HybParams(mismatches, lcf_thres, island, cover_extension, k)
+        out, st = C.c_void_p(), Stats()
+        s = seeds_u8.shape[1] if seeds_u8.ndim == 2 else 0
+        self._check(self.L.cb_coverage_uniform(self.h, probes.h, targets.h, C.byref(hp),
+                                               seeds_u8.ctypes.data if seeds_u8.size else _ONE_BYTE.ctypes.data, s,
+                                               C.byref(out), C.byref(st)))
         return Handle(self.L.cb_cover_free, out), st
 
     def cover_export(self, cover):
@@ -284,18 +300,25 @@ def split_lengths(raw, n, sep=10):
     return lens[:n] if rc == 0 else None
 
 
+def _small(bound):
+    return np.uint8 if bound <= 256 else np.int32
+
+
 def legacy_randint(bound, shape):
     """np.random.randint(0, bound, size=shape) on numpy's legacy global stream, generated by the
-    library's MT19937 replay (same values, same final state, a fraction of the time)."""
+    library's MT19937 replay (same values, same final state, a fraction of the time).  Values come
+    back as uint8 when bound <= 256 (seed positions), else int32."""
     L = load()
     name, key, pos, has_gauss, cached = np.random.get_state()
+    dt = _small(bound)
     if name != 'MT19937':
-        return np.random.randint(0, bound, size=shape)
+        return np.random.randint(0, bound, size=shape).astype(dt)
     key = np.ascontiguousarray(key, dtype=np.uint32).copy()
     n = int(np.prod(shape))
-    out = np.empty(n, dtype=np.int32)
+    out = np.empty(n, dtype=dt)
     p = C.c_int32(int(pos))
-    rc = L.cb_mt19937_randint(key.ctypes.data, C.byref(p), int(bound), n, out.ctypes.data)
+    fn = L.cb_mt19937_randint_u8 if dt is np.uint8 else L.cb_mt19937_randint
+    rc = fn(key.ctypes.data, C.byref(p), int(bound), n, out.ctypes.data)
     if rc != 0:
         raise CatchB200Error(rc, 'cb_mt19937_randint')
     np.random.set_state((name, key, p.value, has_gauss, cached))
@@ -311,15 +334,16 @@ class PendingRandint:
         self.shape = shape
         st = np.random.get_state()
         self.sync = None
+        dt = _small(bound)
         if st[0] != 'MT19937':
-            self.sync = np.random.randint(0, bound, size=shape)
+            self.sync = np.random.randint(0, bound, size=shape).astype(dt)
             return
         self.name, key, pos, self.has_gauss, self.cached = st
         self.key = np.ascontiguousarray(key, dtype=np.uint32).copy()
-        self.out = np.empty(int(np.prod(shape)), dtype=np.int32)
+        self.out = np.empty(int(np.prod(shape)), dtype=dt)
         self.pos = C.c_int32(int(pos))
         self.job = self.L.cb_mt19937_randint_begin(self.key.ctypes.data, C.byref(self.pos), int(bound),
-                                                   self.out.size, self.out.ctypes.data)
+                                                   self.out.size, self.out.ctypes.data, self.out.itemsize)
 
     def result(self):
         if self.sync is not None:

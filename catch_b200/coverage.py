@@ -145,11 +145,35 @@ class SeedPlan:
         self.k, seeds, self.mode = drawn
         # may_have_dups=False: the device already established that all probes are distinct
         self.rep = dedup_map(probe_strs) if may_have_dups else None
-        self.seed_off, self.seed_pos = seeds_to_csr(np.asarray(seeds), self.rep)
+        seeds = np.asarray(seeds)
+        # Without duplicates every probe has the same number of draws: the dense byte matrix goes to
+        # cb_coverage_uniform as it is.  With duplicates the draws of a sequence's copies are merged
+        # (the k-mer map is keyed by sequence) and the general CSR form is needed.
+        self.uniform = None
+        self._seeds = seeds
+        self._csr = None
+        if self.rep is None and seeds.ndim == 2 and seeds.size and int(seeds.max(initial=0)) < 256:
+            self.uniform = np.ascontiguousarray(seeds, dtype=np.uint8)
+
+    def _get_csr(self):
+        if self._csr is None:
+            self._csr = seeds_to_csr(self._seeds, self.rep)
+        return self._csr
+
+    @property
+    def seed_off(self):
+        return self._get_csr()[0]
+
+    @property
+    def seed_pos(self):
+        return self._get_csr()[1]
 
 
 def compute_cover(ctx, group, plan, mismatches, lcf_thres, island, cover_extension):
     """Stage A for one packed group with a drawn SeedPlan.  Returns (cover handle, stats)."""
+    if plan.uniform is not None:
+        return ctx.coverage_uniform(group.probes, group.targets, mismatches, lcf_thres, island, cover_extension,
+                                    plan.k, plan.uniform)
     return ctx.coverage(group.probes, group.targets, mismatches, lcf_thres, island, cover_extension,
                         plan.k, plan.seed_off, plan.seed_pos)
 

@@ -401,7 +401,10 @@ static inline void mt19937_gen(uint32_t *mt)
     mt[623] = mt[396] ^ (y >> 1) ^ ((y & 1u) ? MATRIX_A : 0u);
 }
 
-int cb_mt19937_randint(uint32_t *key, int32_t *pos, uint32_t bound, int64_t n, int32_t *out)
+}  // extern "C"
+
+template <typename T>
+static int mt19937_randint_t(uint32_t *key, int32_t *pos, uint32_t bound, int64_t n, T *out)
 {
     if (!key || !pos || !out || bound == 0 || n < 0 || *pos < 0 || *pos > 624) return CB_ERR_ARG;
     const uint32_t rng = bound - 1;            // inclusive upper value
@@ -425,13 +428,26 @@ int cb_mt19937_randint(uint32_t *key, int32_t *pos, uint32_t bound, int64_t n, i
             y ^= (y << 15) & 0xefc60000u;
             y ^= (y >> 18);
             const uint32_t val = y & mask;
-            out[i] = (int32_t)val;
+            out[i] = (T)val;
             i += (val <= rng);
         }
         p = j;
     }
     *pos = p;
     return CB_OK;
+}
+
+extern "C" {
+
+int cb_mt19937_randint(uint32_t *key, int32_t *pos, uint32_t bound, int64_t n, int32_t *out)
+{
+    return mt19937_randint_t<int32_t>(key, pos, bound, n, out);
+}
+
+int cb_mt19937_randint_u8(uint32_t *key, int32_t *pos, uint32_t bound, int64_t n, uint8_t *out)
+{
+    if (bound > 256) return CB_ERR_ARG;
+    return mt19937_randint_t<uint8_t>(key, pos, bound, n, out);
 }
 
 // The same replay on a native thread, so the host can pack and upload sequences meanwhile (no
@@ -441,10 +457,16 @@ struct cb_rng_job {
     int rc = CB_OK;
 };
 
-cb_rng_job *cb_mt19937_randint_begin(uint32_t *key, int32_t *pos, uint32_t bound, int64_t n, int32_t *out)
+cb_rng_job *cb_mt19937_randint_begin(uint32_t *key, int32_t *pos, uint32_t bound, int64_t n, void *out,
+                                     int32_t elem_size)
 {
     cb_rng_job *job = new cb_rng_job();
-    job->th = std::thread([=]() { job->rc = cb_mt19937_randint(key, pos, bound, n, out); });
+    if (elem_size == 1)
+        job->th = std::thread([=]() { job->rc = cb_mt19937_randint_u8(key, pos, bound, n, (uint8_t *)out); });
+    else if (elem_size == 4)
+        job->th = std::thread([=]() { job->rc = cb_mt19937_randint(key, pos, bound, n, (int32_t *)out); });
+    else
+        job->rc = CB_ERR_ARG;
     return job;
 }
 
@@ -491,7 +513,19 @@ int cb_coverage(cb_ctx *ctx, const cb_probes *probes, const cb_targets *targets,
     ctx->launches = 0;
     CB_CUDA(ctx, cudaSetDevice(ctx->device));
     cb_tls_stream = ctx->stream;
-    return cb_coverage_impl(ctx, probes, targets, params, seed_off, seed_pos, out, stats);
+    return cb_coverage_impl(ctx, probes, targets, params, seed_off, seed_pos, nullptr, 0, out, stats);
+}
+
+int cb_coverage_uniform(cb_ctx *ctx, const cb_probes *probes, const cb_targets *targets, const cb_hyb_params *params,
+                        const uint8_t *seed_pos, int32_t seeds_per_probe, cb_cover **out, cb_stats *stats)
+{
+    if (!ctx) return CB_ERR_ARG;
+    if (!seed_pos) return cb_fail(ctx, CB_ERR_ARG, "null seed positions");
+    if (stats) memset(stats, 0, sizeof *stats);
+    ctx->launches = 0;
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cb_tls_stream = ctx->stream;
+    return cb_coverage_impl(ctx, probes, targets, params, nullptr, nullptr, seed_pos, seeds_per_probe, out, stats);
 }
 
 void cb_cover_free(cb_cover *c)

@@ -232,7 +232,9 @@ __device__ __forceinline__ uint64_t kmer_hash(int bits, int k, Reader rd)
 // Seed positions arrive as a CSR that may hold repeats in any order (the reference draws with
 // replacement and keeps a set, probe.py:393-398).  One warp per probe ORs them into the probe's
 // seed mask (the last NW words of its record) and counts the distinct positions.
-__global__ void seed_mask_kernel(const int64_t *__restrict__ seed_off, const uint8_t *__restrict__ seed_pos,
+// seed_off == nullptr: every probe has exactly `uniform` positions, probe p at [p*uniform, (p+1)*uniform).
+__global__ void seed_mask_kernel(const int64_t *__restrict__ seed_off, int uniform,
+                                 const uint8_t *__restrict__ seed_pos,
                                  const int32_t *__restrict__ plen, int k, int64_t n_probes,
                                  uint64_t *__restrict__ precs, int prec_words, int nw,
                                  uint32_t *__restrict__ n_distinct, int *__restrict__ bad)
@@ -243,7 +245,8 @@ __global__ void seed_mask_kernel(const int64_t *__restrict__ seed_off, const uin
     for (int64_t p = warp; p < n_probes; p += n_warps) {
         uint64_t mask[4] = {0, 0, 0, 0};
         const int limit = plen[p] - k;             // last admissible seed start
-        for (int64_t e = seed_off[p] + lane; e < seed_off[p + 1]; e += 32) {
+        const int64_t e0 = seed_off ? seed_off[p] : p * uniform, e1 = seed_off ? seed_off[p + 1] : e0 + uniform;
+        for (int64_t e = e0 + lane; e < e1; e += 32) {
             const int s = seed_pos[e];
             if (s > limit) { *bad = 1; continue; }
 #pragma unroll
@@ -1156,9 +1159,12 @@ int launch_scan_nw(cb_ctx *ctx, int nw, const ScanParams &P, int grid)
 
 int cb_coverage_impl(cb_ctx *ctx, const cb_probes *probes, const cb_targets *targets,
                      const cb_hyb_params *hp, const int64_t *seed_off, const int32_t *seed_pos,
-                     cb_cover **out, cb_stats *stats)
+                     const uint8_t *seed_pos_u8, int32_t seeds_per_probe, cb_cover **out, cb_stats *stats)
 {
     if (!probes || !targets || !hp || !out) return cb_fail(ctx, CB_ERR_ARG, "null argument");
+    const bool uniform = seed_pos_u8 != nullptr;        // [n_probes][seeds_per_probe] bytes, no CSR
+    if (uniform ? seeds_per_probe < 0 : (probes->n_probes > 0 && (!seed_off || !seed_pos)))
+        return cb_fail(ctx, CB_ERR_ARG, "bad seed arguments");
     if (probes->bits != targets->bits || memcmp(probes->lut, targets->lut, 256) != 0)
         return cb_fail(ctx, CB_ERR_ARG, "probes and targets were packed with different alphabets");
     if (hp->mismatches < 0 || hp->mismatches > CB_MAX_MISMATCHES)
@@ -1184,7 +1190,7 @@ int cb_coverage_impl(cb_ctx *ctx, const cb_probes *probes, const cb_targets *tar
                                  cudaMemcpyDeviceToDevice, st));
     CB_CUDA(ctx, cb_dev_alloc(st, (void **)&cov->d_iv_off, sizeof(int64_t) * (size_t)(P + 1)));
 
-    const int64_t n_raw_seeds = P ? seed_off[P] - seed_off[0] : 0;
+    const int64_t n_raw_seeds = !P ? 0 : uniform ? P * (int64_t)seeds_per_probe : seed_off[P] - seed_off[0];
     const bool empty = (P == 0 || targets->total_bases == 0 || n_raw_seeds == 0);
     if (empty) {
         CB_CUDA(ctx, cudaMemsetAsync(cov->d_iv_off, 0, sizeof(int64_t) * (size_t)(P + 1), st));
@@ -1193,14 +1199,17 @@ int cb_coverage_impl(cb_ctx *ctx, const cb_probes *probes, const cb_targets *tar
         *out = cov;
         return CB_OK;
     }
-    // narrow the seed positions to bytes (range-checked here, against the probe length on the device)
-    std::vector<uint8_t> h_spos((size_t)n_raw_seeds);
-    std::vector<int64_t> h_soff((size_t)P + 1);
-    for (int64_t p = 0; p <= P; p++) {
-        h_soff[(size_t)p] = seed_off[p] - seed_off[0];
-        if (p && seed_off[p] < seed_off[p - 1]) return cb_fail(ctx, CB_ERR_ARG, "seed_off not monotone");
-    }
-    {
+    // CSR form: narrow the seed positions to bytes (range-checked here, against the probe length on
+    // the device).  Uniform form: the caller's bytes go to the device as they are.
+    std::vector<uint8_t> h_spos;
+    std::vector<int64_t> h_soff;
+    if (!uniform) {
+        h_spos.resize((size_t)n_raw_seeds);
+        h_soff.resize((size_t)P + 1);
+        for (int64_t p = 0; p <= P; p++) {
+            h_soff[(size_t)p] = seed_off[p] - seed_off[0];
+            if (p && seed_off[p] < seed_off[p - 1]) return cb_fail(ctx, CB_ERR_ARG, "seed_off not monotone");
+        }
         const int32_t *sp0 = seed_pos + seed_off[0];
         int bad = 0;
         for (int64_t e = 0; e < n_raw_seeds; e++) {
@@ -1218,7 +1227,7 @@ int cb_coverage_impl(cb_ctx *ctx, const cb_probes *probes, const cb_targets *tar
     DevBuf<uint64_t> d_entries, d_precs;
     DevBuf<int> d_bad;
     DevBuf<unsigned long long> d_ctr;        // [0] tile counter, [1] hits, [2] lookups, [3] owners, [4] range cursor
-    CB_CUDA(ctx, d_soff.alloc((size_t)P + 1));
+    if (!uniform) CB_CUDA(ctx, d_soff.alloc((size_t)P + 1));
     CB_CUDA(ctx, d_spos.alloc((size_t)n_raw_seeds));
     CB_CUDA(ctx, d_ndist.alloc((size_t)P));
     CB_CUDA(ctx, d_eoff.alloc((size_t)P + 1));
@@ -1226,14 +1235,15 @@ int cb_coverage_impl(cb_ctx *ctx, const cb_probes *probes, const cb_targets *tar
     CB_CUDA(ctx, d_bad.alloc(1));
     CB_CUDA(ctx, d_ctr.alloc(8));
     CB_CUDA(ctx, cudaMemsetAsync(d_bad.p, 0, sizeof(int), st));
-    CB_CUDA(ctx, cudaMemcpyAsync(d_soff.p, h_soff.data(), sizeof(int64_t) * (size_t)(P + 1), cudaMemcpyHostToDevice, st));
-    CB_CUDA(ctx, cudaMemcpyAsync(d_spos.p, h_spos.data(), (size_t)n_raw_seeds, cudaMemcpyHostToDevice, st));
+    if (!uniform)
+        CB_CUDA(ctx, cudaMemcpyAsync(d_soff.p, h_soff.data(), sizeof(int64_t) * (size_t)(P + 1), cudaMemcpyHostToDevice, st));
+    CB_CUDA(ctx, cudaMemcpyAsync(d_spos.p, uniform ? seed_pos_u8 : h_spos.data(), (size_t)n_raw_seeds, cudaMemcpyHostToDevice, st));
 
     // ---- K2 seed index (+ probe records with their seed masks)
     t_idx.start();
     const int wide = ctx->sm_count * 8;
     build_precs_kernel<<<wide, 256, 0, st>>>(probes->d_words, P, plane_words, prec_words, d_precs.p);
-    seed_mask_kernel<<<wide, 256, 0, st>>>(d_soff.p, d_spos.p, probes->d_len, hp->k, P, d_precs.p, prec_words, nw,
+    seed_mask_kernel<<<wide, 256, 0, st>>>(uniform ? nullptr : d_soff.p, (int)seeds_per_probe, d_spos.p, probes->d_len, hp->k, P, d_precs.p, prec_words, nw,
                                            d_ndist.p, d_bad.p);
     ctx->launches += 2;
     CB_CUDA(ctx, cudaGetLastError());
@@ -1319,8 +1329,8 @@ int cb_coverage_impl(cb_ctx *ctx, const cb_probes *probes, const cb_targets *tar
     const unsigned long long hits_ub = h_ctr[1];
     // a diagonal is emitted once, by its lowest matching seed: expect about hits / seeds-per-probe
     // ranges; start with twice that and fall back to the hard bound if it overflows
-    const double seeds_per_probe = (double)n_entries / (double)P;
-    unsigned long long cap = (unsigned long long)(2.0 * (double)hits_ub / (seeds_per_probe > 1.0 ? seeds_per_probe : 1.0)) + 4096;
+    const double distinct_per_probe = (double)n_entries / (double)P;
+    unsigned long long cap = (unsigned long long)(2.0 * (double)hits_ub / (distinct_per_probe > 1.0 ? distinct_per_probe : 1.0)) + 4096;
     if (cap > hits_ub + 4096) cap = hits_ub + 4096;
 
     // ---- K3 scan

@@ -175,7 +175,7 @@ int cb_probes_have_duplicates_impl(cb_ctx *ctx, const cb_probes *probes, int32_t
 // coverage.cu
 int cb_coverage_impl(cb_ctx *ctx, const cb_probes *probes, const cb_targets *targets,
                      const cb_hyb_params *params, const int64_t *seed_off, const int32_t *seed_pos,
-                     cb_cover **out, cb_stats *stats);
+                     const uint8_t *seed_pos_u8, int32_t seeds_per_probe, cb_cover **out, cb_stats *stats);
 
 int cb_cover_import_impl(cb_ctx *ctx, int64_t n_probes, int32_t n_genomes, const int64_t *genome_len,
                          int64_t n_intervals, const int64_t *probe_id, const int32_t *genome,

@@ -149,7 +149,7 @@ def choose_seed_positions(lengths, mismatches, lcf_thres, min_k=20, k=20, num_km
         # one run of equal lengths = one generator call, which may run in the background:
         # the third element is then an object whose result() yields the [n, s] draws
         return k, randint_async(L0 - k + 1, (n, num_kmers_per_probe)), 'random'
-    seeds = np.empty((n, num_kmers_per_probe), dtype=np.int32)
+    seeds = np.empty((n, num_kmers_per_probe), dtype=np.int32 if int(lengths.max()) - k + 1 > 256 else np.uint8)
     # runs of equal length, in list order
     change = np.flatnonzero(np.diff(lengths)) + 1
     starts = np.concatenate(([0], change))

@@ -124,7 +124,8 @@ int cb_upload_group(cb_ctx *ctx, const uint8_t *probes_ascii, int64_t probes_byt
  * returns its status.  key/pos/out must stay valid and untouched in between.  Lets the caller
  * overlap the (host-only) seed draw with cb_upload_group. */
 typedef struct cb_rng_job cb_rng_job;
-cb_rng_job *cb_mt19937_randint_begin(uint32_t *key, int32_t *pos, uint32_t bound, int64_t n, int32_t *out);
+cb_rng_job *cb_mt19937_randint_begin(uint32_t *key, int32_t *pos, uint32_t bound, int64_t n, void *out,
+                                     int32_t elem_size /* 4: int32 output, 1: uint8 output */);
 int cb_mt19937_randint_end(cb_rng_job *job);
 
 /* Host-side helper (no device work): lengths of the n strings held in `buf`, consecutive strings
@@ -142,6 +143,8 @@ int cb_probes_have_duplicates(cb_ctx *ctx, const cb_probes *probes, int32_t *has
  * probe.py:393-396 can be replayed without per-probe Python overhead.  key[624]/pos are the state
  * from np.random.get_state() and are updated in place. */
 int cb_mt19937_randint(uint32_t *key, int32_t *pos, uint32_t bound, int64_t n, int32_t *out);
+/* Same draws stored as bytes (bound <= 256): the form cb_coverage_uniform takes. */
+int cb_mt19937_randint_u8(uint32_t *key, int32_t *pos, uint32_t bound, int64_t n, uint8_t *out);
 
 /* ---- stage A: coverage (K2-K4) -----------------------------------------------------
  * Replaces SetCoverFilter._make_sets (filter/set_cover_filter.py:359-470), i.e.
@@ -157,6 +160,12 @@ int cb_mt19937_randint(uint32_t *key, int32_t *pos, uint32_t bound, int64_t n, i
 int cb_coverage(cb_ctx *ctx, const cb_probes *probes, const cb_targets *targets,
                 const cb_hyb_params *params, const int64_t *seed_off, const int32_t *seed_pos,
                 cb_cover **out, cb_stats *stats);
+/* Same as cb_coverage when every probe has the same number of seed positions (the reference's
+ * random mode draws 20 per probe, probe.py:393-396; pigeonhole mode gives L/k per probe):
+ * seed_pos is a dense [n_probes][seeds_per_probe] byte matrix, no offsets, no host-side narrowing. */
+int cb_coverage_uniform(cb_ctx *ctx, const cb_probes *probes, const cb_targets *targets,
+                        const cb_hyb_params *params, const uint8_t *seed_pos, int32_t seeds_per_probe,
+                        cb_cover **out, cb_stats *stats);
 void cb_cover_free(cb_cover *c);
 
 /* Number of merged (probe, genome, start, end) intervals held by a cover. */
