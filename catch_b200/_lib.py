@@ -39,7 +39,7 @@ class Stats(C.Structure):
 
 # every symbol include/catch_b200.h declares
 EXPORTED_SYMBOLS = [
-    'cb_init', 'cb_destroy', 'cb_last_error', 'cb_version', 'cb_flush_l2',
+    'cb_init', 'cb_destroy', 'cb_last_error', 'cb_version', 'cb_flush_l2', 'cb_host_buffer',
     'cb_upload_targets', 'cb_targets_free', 'cb_upload_probes', 'cb_probes_free', 'cb_upload_group',
     'cb_probes_have_duplicates', 'cb_mt19937_randint', 'cb_mt19937_randint_u8', 'cb_mt19937_randint_begin',
     'cb_mt19937_randint_end',
@@ -70,6 +70,7 @@ def load():
     L.cb_last_error.argtypes = [vp]
     L.cb_last_error.restype = C.c_char_p
     L.cb_flush_l2.argtypes = [vp]
+    L.cb_host_buffer.argtypes = [vp, i32, i64, C.POINTER(vp)]
     L.cb_upload_targets.argtypes = [vp, vp, vp, i64, vp, i32, vp, i32, C.POINTER(vp), C.POINTER(Stats)]
     L.cb_targets_free.argtypes = [vp]
     L.cb_targets_free.restype = None
@@ -120,6 +121,7 @@ class Context:
         if device_id is None:
             device_id = int(os.environ.get('LOCAL_RANK', os.environ.get('CB_DEVICE', '0')))
         self.device_id = device_id
+        self._pinned_addr, self._pinned_cap = {}, {}
         h = C.c_void_p()
         rc = self.L.cb_init(device_id, C.byref(h))
         self.h = h
@@ -141,6 +143,17 @@ class Context:
     def _check(self, rc):
         if rc != 0:
             raise CatchB200Error(rc, self.L.cb_last_error(self.h).decode())
+
+    def host_buffer(self, slot, nbytes):
+        """(address, capacity) of the context's page-locked staging buffer `slot`, grown to hold
+        at least nbytes."""
+        cap = self._pinned_cap.get(slot, 0)
+        if nbytes > cap or slot not in self._pinned_addr:
+            out = C.c_void_p()
+            self._check(self.L.cb_host_buffer(self.h, slot, max(int(nbytes), 1), C.byref(out)))
+            self._pinned_addr[slot] = out.value
+            self._pinned_cap[slot] = max(int(nbytes), 1)
+        return self._pinned_addr[slot], self._pinned_cap[slot]
 
     def flush_l2(self):
         self._check(self.L.cb_flush_l2(self.h))
@@ -165,7 +178,10 @@ class Context:
         (or back to back with explicit `probe_off`).  Returns (probes, targets, lengths, bits, stats)."""
         p_out, t_out, st, bits = C.c_void_p(), C.c_void_p(), Stats(), C.c_int32()
         lens = np.zeros(max(n_probes, 1), dtype=np.int32)
-        self._check(self.L.cb_upload_group(self.h, probes_raw, len(probes_raw), _ptr(probe_off), n_probes, sep,
+        # probes_raw / targets_raw: bytes objects, or integer addresses of staged host memory
+        # (then probe_off gives the size)
+        p_bytes = len(probes_raw) if isinstance(probes_raw, (bytes, bytearray)) else int(probe_off[-1])
+        self._check(self.L.cb_upload_group(self.h, probes_raw, p_bytes, _ptr(probe_off), n_probes, sep,
                                            targets_raw, _ptr(seq_off), len(seq_off) - 1, _ptr(seq_genome), n_genomes,
                                            _ptr(lens), C.byref(bits), C.byref(p_out), C.byref(t_out), C.byref(st)))
         return (Handle(self.L.cb_probes_free, p_out), Handle(self.L.cb_targets_free, t_out), lens[:n_probes],
@@ -344,6 +360,12 @@ class PendingRandint:
         self.pos = C.c_int32(int(pos))
         self.job = self.L.cb_mt19937_randint_begin(self.key.ctypes.data, C.byref(self.pos), int(bound),
                                                    self.out.size, self.out.ctypes.data, self.out.itemsize)
+
+    def cancel(self):
+        """Wait for the worker and drop its output; numpy's state stays as it was."""
+        if self.sync is None and self.job is not None:
+            self.L.cb_mt19937_randint_end(self.job)
+            self.job = None
 
     def result(self):
         if self.sync is not None:

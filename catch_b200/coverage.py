@@ -24,6 +24,21 @@ def _concat_ascii(strs):
     return buf, off, raw
 
 
+def gather_staged(ctx, slot, items):
+    """Gather the sequences of `items` (str or objects with .seq_str) straight into the context's
+    page-locked staging buffer `slot`.  Returns (address, int32 lengths, total bytes), or None when
+    the C helper is not built (callers then use gather_probes)."""
+    if _fastpack is None or not hasattr(ctx, 'host_buffer'):
+        return None
+    n = len(items)
+    addr, cap = ctx.host_buffer(slot, 0)
+    total, lens = _fastpack.gather_into(items, 'seq_str', addr, cap)
+    if total > cap:
+        addr, cap = ctx.host_buffer(slot, total)
+        total, lens = _fastpack.gather_into(items, 'seq_str', addr, cap)
+    return addr, np.frombuffer(lens, dtype=np.int32, count=n), total
+
+
 def gather_probes(probes):
     """(bytes of all sequences back to back, int32 lengths) for a list of Probe objects (or str).
     One C pass over the list when the _fastpack helper is built."""
@@ -55,16 +70,27 @@ class PackedGroup:
                 seqs.append(s)
                 seq_genome.append(j)
         self.n_genomes = len(genomes)
-        _, seq_off, t_raw = _concat_ascii(seqs)
-        self.target_bases = int(seq_off[-1])
         sg = np.array(seq_genome if seq_genome else [0], dtype=np.int32)
-        p_raw, lens = gathered if gathered is not None else gather_probes(probe_strs)
+        staged_t = gather_staged(ctx, 1, seqs)
+        if staged_t is not None:
+            t_raw, t_lens, t_total = staged_t
+            seq_off = np.zeros(len(seqs) + 1, dtype=np.int64)
+            np.cumsum(t_lens, out=seq_off[1:])
+        else:
+            _, seq_off, t_raw = _concat_ascii(seqs)
+            t_total = len(t_raw)
+        self.target_bases = int(seq_off[-1])
+        if gathered is None:
+            gathered = gather_staged(ctx, 0, probe_strs)
+            if gathered is None:
+                gathered = gather_probes(probe_strs)
+        p_raw, lens = gathered[0], gathered[1]
         off = np.zeros(self.n_probes + 1, dtype=np.int64)
         np.cumsum(lens, out=off[1:])
         self.probes, self.targets, self.probe_len, self.bits, st = ctx.upload_group(
             p_raw, self.n_probes, t_raw, seq_off, sg, self.n_genomes, probe_off=off)
         self.st_targets, self.st_probes = st, _lib.Stats()
-        self.h2d_bytes = int(len(p_raw) + len(t_raw))
+        self.h2d_bytes = int(off[-1]) + int(t_total)
 
     @property
     def probe_off(self):
@@ -122,6 +148,13 @@ def draw_seeds(lengths, mismatches, lcf_thres, kmer_probe_map_k, background=Fals
                                            randint_async=_lib.PendingRandint if background else None)
 
 
+def cancel_draw(drawn):
+    """Drop a background draw (made on a guess that turned out wrong) without consuming the RNG."""
+    seeds = drawn[1]
+    if hasattr(seeds, 'cancel'):
+        seeds.cancel()
+
+
 def finish_draw(drawn):
     k, seeds, mode = drawn
     if hasattr(seeds, 'result'):
@@ -152,7 +185,8 @@ class SeedPlan:
         self.uniform = None
         self._seeds = seeds
         self._csr = None
-        if self.rep is None and seeds.ndim == 2 and seeds.size and int(seeds.max(initial=0)) < 256:
+        if self.rep is None and seeds.ndim == 2 and seeds.size and \
+                (seeds.dtype == np.uint8 or int(seeds.max(initial=0)) < 256):
             self.uniform = np.ascontiguousarray(seeds, dtype=np.uint8)
 
     def _get_csr(self):

@@ -206,11 +206,31 @@ void cb_destroy(cb_ctx *ctx)
     if (!ctx) return;
     cb_comm_destroy(ctx);
     if (ctx->flush_buf) cudaFree(ctx->flush_buf);
+    for (int i = 0; i < 2; i++)
+        if (ctx->pinned[i]) cudaFreeHost(ctx->pinned[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 
 const char *cb_last_error(cb_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int cb_host_buffer(cb_ctx *ctx, int32_t slot, int64_t bytes, void **out)
+{
+    if (!ctx || !out || slot < 0 || slot > 1 || bytes < 0) return cb_fail(ctx, CB_ERR_ARG, "bad argument");
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if ((size_t)bytes > ctx->pinned_bytes[slot]) {
+        // the previous buffer may still feed an asynchronous copy
+        CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->pinned[slot]) CB_CUDA(ctx, cudaFreeHost(ctx->pinned[slot]));
+        ctx->pinned[slot] = nullptr;
+        ctx->pinned_bytes[slot] = 0;
+        size_t want = (size_t)bytes + ((size_t)bytes >> 2) + 4096;      // headroom: sizes drift between groupings
+        CB_CUDA(ctx, cudaHostAlloc(&ctx->pinned[slot], want, cudaHostAllocDefault));
+        ctx->pinned_bytes[slot] = want;
+    }
+    *out = ctx->pinned[slot];
+    return CB_OK;
+}
 
 int cb_flush_l2(cb_ctx *ctx)
 {

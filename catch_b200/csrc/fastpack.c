@@ -10,12 +10,18 @@
 #include <string.h>
 
 /* gather(seq, attr) -> (bytes data, bytes lengths_int32)
+ * gather_into(seq, attr, address, capacity) -> (int total_bytes, bytes lengths_int32)
  * Every item is either a str or an object whose attribute `attr` is a str.  Raises ValueError
- * when a string holds characters above U+00FF (not representable as one byte per base). */
-static PyObject *gather(PyObject *self, PyObject *args)
+ * when a string holds characters above U+00FF (not representable as one byte per base).
+ * gather_into copies into caller-owned memory (the library's pinned staging buffer) instead of a
+ * new bytes object; when total_bytes exceeds the capacity nothing is copied and the caller
+ * retries with a larger buffer. */
+static PyObject *gather_impl(PyObject *args, int into)
 {
     PyObject *seq_in, *attr;
-    if (!PyArg_ParseTuple(args, "OU", &seq_in, &attr)) return NULL;
+    unsigned long long address = 0, capacity = 0;
+    if (into ? !PyArg_ParseTuple(args, "OUKK", &seq_in, &attr, &address, &capacity)
+             : !PyArg_ParseTuple(args, "OU", &seq_in, &attr)) return NULL;
     PyObject *seq = PySequence_Fast(seq_in, "expected a sequence of probes");
     if (!seq) return NULL;
     const Py_ssize_t n = PySequence_Fast_GET_SIZE(seq);
@@ -55,12 +61,14 @@ static PyObject *gather(PyObject *self, PyObject *args)
         total += (size_t)len;
     }
     {
-        /* pass 2: copy into a bytes object of the final size */
-        PyObject *data = PyBytes_FromStringAndSize(NULL, (Py_ssize_t)total);
+        /* pass 2: copy into a bytes object of the final size, or into the caller's buffer */
+        PyObject *data = into ? PyLong_FromUnsignedLongLong((unsigned long long)total)
+                              : PyBytes_FromStringAndSize(NULL, (Py_ssize_t)total);
         if (!data) goto fail;
-        char *dst = PyBytes_AS_STRING(data);
+        char *dst = into ? (char *)(uintptr_t)address : PyBytes_AS_STRING(data);
+        const int copy = !into || total <= (size_t)capacity;
         for (Py_ssize_t i = 0; i < n; i++) {
-            memcpy(dst, PyUnicode_1BYTE_DATA(strs[i]), (size_t)lens[i]);
+            if (copy) memcpy(dst, PyUnicode_1BYTE_DATA(strs[i]), (size_t)lens[i]);
             dst += lens[i];
             Py_DECREF(strs[i]);
         }
@@ -79,8 +87,13 @@ fail:
     return NULL;
 }
 
+static PyObject *gather(PyObject *self, PyObject *args) { return gather_impl(args, 0); }
+static PyObject *gather_into(PyObject *self, PyObject *args) { return gather_impl(args, 1); }
+
 static PyMethodDef methods[] = {
     {"gather", gather, METH_VARARGS, "gather(seq, attr) -> (bytes data, bytes int32 lengths)"},
+    {"gather_into", gather_into, METH_VARARGS,
+     "gather_into(seq, attr, address, capacity) -> (int total_bytes, bytes int32 lengths)"},
     {NULL, NULL, 0, NULL}};
 
 static struct PyModuleDef moddef = {PyModuleDef_HEAD_INIT, "_fastpack", NULL, -1, methods};

@@ -210,16 +210,40 @@ class SetCoverFilter(BaseFilter):
                 host_ms[name] = host_ms.get(name, 0.0) + (now - t_mark) * 1e3
                 t_mark = now
             drawn = drawn_tol = None
+            guess = None
+            if mine and n_probes:
+                # The seed draw needs only the probe lengths and runs on the library's worker thread
+                # while the sequences are gathered, copied to the device and packed.  It is started
+                # on the guess that all probes are as long as the first (candidate probes are);
+                # if the gathered lengths say otherwise the guess is dropped -- a background draw
+                # only touches numpy's RNG state when it is accepted -- and the draw is redone.
+                guess = len(possible_probes[0].seq_str)
+                try:
+                    drawn = cov.draw_seeds(np.full(n_probes, guess, dtype=np.int32), self.mismatches,
+                                           self.lcf_thres, self.kmer_probe_map_k, background=True)
+                except ValueError:          # e.g. k longer than the first probe: decided on the real lengths
+                    drawn = None
             if n_probes:
-                gathered = cov.gather_probes(possible_probes)
+                # sequences of the whole list in one buffer (straight into page-locked staging memory
+                # when this rank is going to upload them)
+                try:
+                    gathered = cov.gather_staged(self._context(), 0, possible_probes) if mine else None
+                    if gathered is None:
+                        gathered = cov.gather_probes(possible_probes)
+                except BaseException:
+                    if drawn is not None:
+                        cov.cancel_draw(drawn)
+                    raise
                 lengths = gathered[1]
+                if mine and (drawn is None or not bool(np.all(lengths == guess))):
+                    if drawn is not None:
+                        cov.cancel_draw(drawn)
+                    drawn = cov.draw_seeds(lengths, self.mismatches, self.lcf_thres, self.kmer_probe_map_k,
+                                           background=True)
                 mark('gather')
             if mine and n_probes:
-                # the seed draw needs only the lengths: it runs on the library's worker thread
-                # while the sequences are copied to the device and packed.  The tolerant draw
-                # (ranks) continues the same stream, so it follows once the first has finished.
-                drawn = cov.draw_seeds(lengths, self.mismatches, self.lcf_thres, self.kmer_probe_map_k,
-                                       background=True)
+                # The tolerant draw (ranks) continues the same stream, so it follows once the first
+                # has finished.
                 try:
                     group = cov.PackedGroup(self._context(), possible_probes, target_genomes, gathered=gathered)
                     mark('pack_and_upload')

@@ -85,6 +85,12 @@ const char *cb_version(void);
  * starts with a cold L2. */
 int cb_flush_l2(cb_ctx *ctx);
 
+/* Page-locked host staging memory owned by the context: slot 0 or 1, at least `bytes` bytes, valid
+ * until the next cb_host_buffer call for the same slot with a larger size (or cb_destroy).  Filling
+ * the sequences straight into it lets the uploads below run as true asynchronous DMA instead of
+ * going through the driver's bounce buffer. */
+int cb_host_buffer(cb_ctx *ctx, int32_t slot, int64_t bytes, void **out);
+
 /* ---- packing (K1) ------------------------------------------------------------------
  * Replaces the per-hit str -> np.array('U1') conversions of probe.py:1074 and
  * Probe.from_str (probe.py:344): sequences go to the device once, as `bits` bit planes

@@ -168,3 +168,15 @@ def test_gather_probes_c_helper_matches_python():
     # latin-1 characters are single bytes and pass through
     data, lens = cov.gather_probes(['A\xe9'])
     assert data == b'A\xe9' and lens.tolist() == [2]
+
+
+def test_background_draw_can_be_cancelled_without_touching_the_rng():
+    from catch_b200 import coverage as cov
+    np.random.seed(11)
+    before = np.random.get_state()[1].copy()
+    drawn = cov.draw_seeds(np.full(5000, 75, dtype=np.int32), 2, 60, 20, background=True)
+    cov.cancel_draw(drawn)
+    assert np.array_equal(np.random.get_state()[1], before)
+    k, seeds, mode = cov.finish_draw(cov.draw_seeds(np.full(5000, 75, dtype=np.int32), 2, 60, 20, background=True))
+    np.random.seed(11)
+    assert mode == 'random' and np.array_equal(seeds, np.random.randint(0, 56, size=(5000, 20)))
