@@ -1029,19 +1029,67 @@ __device__ __forceinline__ void bitonic_sort(uint64_t *a, uint32_t n)
     }
 }
 
+// Warp merge of a sorted list a[0..n): overlapping or touching ranges (utils/interval.py:304-314:
+// start <= curr_end) are united; the result is written in place at the front of g (g may alias a).
+// Returns the number of merged ranges (valid in every lane); local_max tracks the longest range.
+__device__ __forceinline__ uint32_t warp_merge_sorted(const uint64_t *a, uint64_t *g, uint32_t n, int lane,
+                                                      uint32_t &local_max)
+{
+    uint32_t carry_max = 0, carry_gs = 0, n_out = 0;
+    for (uint32_t base = 0; base < n; base += 32) {
+        const uint32_t idx = base + lane;
+        const bool valid = idx < n;
+        const uint64_t r = valid ? a[idx] : ~0ull;
+        const uint32_t s = (uint32_t)(r >> 32), e = valid ? (uint32_t)r : 0u;
+        const uint64_t rn = (idx + 1 < n) ? a[idx + 1] : ~0ull;     // next start (lookahead)
+        const uint32_t s_next = (uint32_t)(rn >> 32);
+        // exclusive running max of the ends
+        uint32_t inc = e;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc = max(inc, t);
+        }
+        inc = max(inc, carry_max);
+        uint32_t exc = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (lane == 0) exc = carry_max;
+        const bool head = valid && (idx == 0 || s > exc);
+        // start of the group each element belongs to
+        uint32_t gs = head ? s : 0u;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, gs, o);
+            if (lane >= o) gs = max(gs, t);
+        }
+        gs = max(gs, carry_gs);
+        const bool tail = valid && (idx + 1 == n || s_next > inc);
+        const unsigned tails = __ballot_sync(0xffffffffu, tail);
+        __syncwarp();
+        if (tail) {
+            const uint32_t k = n_out + __popc(tails & ((1u << lane) - 1u));
+            // k <= idx, and every element at index <= base+31 is already in registers
+            g[k] = ((uint64_t)gs << 32) | (uint64_t)inc;
+            local_max = max(local_max, inc - gs);
+        }
+        n_out += __popc(tails);
+        carry_max = __shfl_sync(0xffffffffu, inc, 31);
+        carry_gs = __shfl_sync(0xffffffffu, gs, 31);
+        __syncwarp();
+    }
+    return n_out;
+}
+
+// Probes with more than MERGE_WARP_CAP ranges: one block per probe (see above).
 __global__ void __launch_bounds__(MERGE_THREADS)
 merge_kernel(const int64_t *__restrict__ rec_off, uint64_t *__restrict__ rec, int64_t n_probes,
-             uint32_t *__restrict__ n_merged, uint32_t *__restrict__ max_len)
+             uint32_t *__restrict__ n_merged, uint32_t *__restrict__ max_len, uint32_t min_n)
 {
     __shared__ uint64_t s_rec[MERGE_SMEM_CAP];
     uint32_t local_max = 0;
     for (int64_t p = blockIdx.x; p < n_probes; p += gridDim.x) {
         const int64_t o0 = rec_off[p];
         const uint32_t n = (uint32_t)(rec_off[p + 1] - o0);
-        if (n == 0) {
-            if (threadIdx.x == 0) n_merged[p] = 0;
-            continue;
-        }
+        if (n < min_n) continue;                    // done by merge_warp_kernel (block-uniform)
         uint64_t *g = rec + o0;
         uint64_t *a = g;
         const bool in_smem = n <= MERGE_SMEM_CAP;
@@ -1051,51 +1099,9 @@ merge_kernel(const int64_t *__restrict__ rec_off, uint64_t *__restrict__ rec, in
         }
         __syncthreads();
         if (n > 1) bitonic_sort(a, n);
-        // merge by warp 0; output is written in place at the front of the probe's slice
         if (threadIdx.x < 32) {
-            const int lane = threadIdx.x;
-            uint32_t carry_max = 0, carry_gs = 0, n_out = 0;
-            for (uint32_t base = 0; base < n; base += 32) {
-                const uint32_t idx = base + lane;
-                const bool valid = idx < n;
-                const uint64_t r = valid ? a[idx] : ~0ull;
-                const uint32_t s = (uint32_t)(r >> 32), e = valid ? (uint32_t)r : 0u;
-                const uint64_t rn = (idx + 1 < n) ? a[idx + 1] : ~0ull;     // next start (lookahead)
-                const uint32_t s_next = (uint32_t)(rn >> 32);
-                // exclusive running max of the ends
-                uint32_t inc = e;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-                    if (lane >= o) inc = max(inc, t);
-                }
-                inc = max(inc, carry_max);
-                uint32_t exc = __shfl_up_sync(0xffffffffu, inc, 1);
-                if (lane == 0) exc = carry_max;
-                const bool head = valid && (idx == 0 || s > exc);
-                // start of the group each element belongs to
-                uint32_t gs = head ? s : 0u;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t t = __shfl_up_sync(0xffffffffu, gs, o);
-                    if (lane >= o) gs = max(gs, t);
-                }
-                gs = max(gs, carry_gs);
-                const bool tail = valid && (idx + 1 == n || s_next > inc);
-                const unsigned tails = __ballot_sync(0xffffffffu, tail);
-                __syncwarp();
-                if (tail) {
-                    const uint32_t k = n_out + __popc(tails & ((1u << lane) - 1u));
-                    // k <= idx, and every element at index <= base+31 is already in registers
-                    g[k] = ((uint64_t)gs << 32) | (uint64_t)inc;
-                    local_max = max(local_max, inc - gs);
-                }
-                n_out += __popc(tails);
-                carry_max = __shfl_sync(0xffffffffu, inc, 31);
-                carry_gs = __shfl_sync(0xffffffffu, gs, 31);
-                __syncwarp();
-            }
-            if (lane == 0) n_merged[p] = n_out;
+            const uint32_t n_out = warp_merge_sorted(a, g, n, threadIdx.x, local_max);
+            if (threadIdx.x == 0) n_merged[p] = n_out;
         }
         __syncthreads();
     }
@@ -1104,6 +1110,64 @@ merge_kernel(const int64_t *__restrict__ rec_off, uint64_t *__restrict__ rec, in
         for (int o = 16; o >= 1; o >>= 1) local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, o));
         if (threadIdx.x == 0 && local_max) atomicMax(max_len, local_max);
     }
+}
+
+// Probes with at most MERGE_WARP_CAP ranges (all of them in the usual one-range-per-genome case):
+// one WARP per probe, the same normalised bitonic network in the warp's slice of shared memory
+// with __syncwarp between the steps -- no block barrier anywhere, eight probes in flight per CTA.
+constexpr int MERGE_WARP_CAP = 512;
+constexpr int MERGE_WARPS = 8;
+
+__global__ void __launch_bounds__(MERGE_WARPS * 32)
+merge_warp_kernel(const int64_t *__restrict__ rec_off, uint64_t *__restrict__ rec, int64_t n_probes,
+                  uint32_t *__restrict__ n_merged, uint32_t *__restrict__ max_len, unsigned int *__restrict__ n_large)
+{
+    __shared__ uint64_t s_all[MERGE_WARPS * MERGE_WARP_CAP];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint64_t *a = s_all + warp * MERGE_WARP_CAP;
+    uint32_t local_max = 0, large = 0;
+    for (int64_t p = (int64_t)blockIdx.x * MERGE_WARPS + warp; p < n_probes; p += (int64_t)gridDim.x * MERGE_WARPS) {
+        const int64_t o0 = rec_off[p];
+        const uint32_t n = (uint32_t)(rec_off[p + 1] - o0);
+        if (n == 0) {
+            if (lane == 0) n_merged[p] = 0;
+            continue;
+        }
+        if (n > (uint32_t)MERGE_WARP_CAP) { large = 1; continue; }
+        uint64_t *g = rec + o0;
+        for (uint32_t i = lane; i < n; i += 32) a[i] = g[i];
+        __syncwarp();
+        uint32_t n2 = 1;
+        while (n2 < n) n2 <<= 1;
+        for (uint32_t size = 2; size <= n2; size <<= 1) {
+            for (uint32_t t = lane; t < n2 / 2; t += 32) {
+                const uint32_t blk = t / (size / 2), o = t % (size / 2);
+                const uint32_t i = blk * size + o, j = blk * size + size - 1 - o;
+                if (j < n) {
+                    const uint64_t x = a[i], y = a[j];
+                    if (x > y) { a[i] = y; a[j] = x; }
+                }
+            }
+            __syncwarp();
+            for (uint32_t stride = size / 4; stride >= 1; stride >>= 1) {
+                for (uint32_t t = lane; t < n2 / 2; t += 32) {
+                    const uint32_t i = (t / stride) * stride * 2 + (t % stride), j = i + stride;
+                    if (j < n) {
+                        const uint64_t x = a[i], y = a[j];
+                        if (x > y) { a[i] = y; a[j] = x; }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        const uint32_t n_out = warp_merge_sorted(a, g, n, lane, local_max);
+        if (lane == 0) n_merged[p] = n_out;
+        __syncwarp();
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, o));
+    if (lane == 0 && local_max) atomicMax(max_len, local_max);
+    if (lane == 0 && large) atomicOr(n_large, 1u);
 }
 
 __global__ void compact_kernel(const int64_t *__restrict__ rec_off, const uint64_t *__restrict__ rec,
@@ -1120,6 +1184,34 @@ __global__ void compact_kernel(const int64_t *__restrict__ rec_off, const uint64
             iv[dst + i] = make_uint2((uint32_t)(r >> 32), (uint32_t)r);
         }
     }
+}
+
+// K4 launcher: warp-per-probe kernel first; the block-per-probe kernel only if some probe has
+// more than MERGE_WARP_CAP ranges.
+int launch_merge(cb_ctx *ctx, const int64_t *d_roff, uint64_t *d_sorted, int64_t P, uint32_t *d_nmerged, uint32_t *d_maxlen)
+{
+    cudaStream_t st = ctx->stream;
+    DevBuf<unsigned int> d_large;
+    CB_CUDA(ctx, d_large.alloc(1));
+    CB_CUDA(ctx, cudaMemsetAsync(d_large.p, 0, sizeof(unsigned int), st));
+    int64_t g = (P + MERGE_WARPS - 1) / MERGE_WARPS;
+    const int64_t cap = (int64_t)ctx->sm_count * 16;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    merge_warp_kernel<<<(unsigned)g, MERGE_WARPS * 32, 0, st>>>(d_roff, d_sorted, P, d_nmerged, d_maxlen, d_large.p);
+    ctx->launches++;
+    CB_CUDA(ctx, cudaGetLastError());
+    unsigned int h_large = 0;
+    CB_CUDA(ctx, cudaMemcpyAsync(&h_large, d_large.p, sizeof h_large, cudaMemcpyDeviceToHost, st));
+    CB_CUDA(ctx, cudaStreamSynchronize(st));
+    if (h_large) {
+        int64_t gb = P < (int64_t)ctx->sm_count * 8 ? P : (int64_t)ctx->sm_count * 8;
+        merge_kernel<<<(unsigned)gb, MERGE_THREADS, 0, st>>>(d_roff, d_sorted, P, d_nmerged, d_maxlen,
+                                                            (uint32_t)MERGE_WARP_CAP + 1u);
+        ctx->launches++;
+        CB_CUDA(ctx, cudaGetLastError());
+    }
+    return CB_OK;
 }
 
 template <int NW, int KC>
@@ -1371,12 +1463,7 @@ int cb_coverage_impl(cb_ctx *ctx, const cb_probes *probes, const cb_targets *tar
         scatter_by_probe_kernel<<<wide, 256, 0, st>>>(d_rec.p, n_raw, d_roff.p, d_rcursor.p, d_sorted.p);
         ctx->launches++;
     }
-    {
-        int64_t g = P < (int64_t)ctx->sm_count * 16 ? P : (int64_t)ctx->sm_count * 16;
-        merge_kernel<<<(unsigned)g, MERGE_THREADS, 0, st>>>(d_roff.p, d_sorted.p, P, d_nmerged.p, d_maxlen.p);
-        ctx->launches++;
-        CB_CUDA(ctx, cudaGetLastError());
-    }
+    CB_TRY(launch_merge(ctx, d_roff.p, d_sorted.p, P, d_nmerged.p, d_maxlen.p));
     int64_t n_iv = 0;
     CB_TRY(cb_exclusive_scan_u32_to_i64(ctx, d_nmerged.p, cov->d_iv_off, P, &n_iv));
     CB_CUDA(ctx, cb_dev_alloc(st, (void **)&cov->d_iv, sizeof(uint2) * (size_t)(n_iv ? n_iv : 1)));
@@ -1476,9 +1563,8 @@ int cb_cover_import_impl(cb_ctx *ctx, int64_t P, int32_t NG, const int64_t *geno
     CB_TRY(cb_exclusive_scan_u32_to_i64(ctx, d_rcount.p, d_roff.p, P, nullptr));
     const int wide = ctx->sm_count * 8;
     scatter_by_probe_kernel<<<wide, 256, 0, st>>>(d_rec.p, (unsigned long long)m, d_roff.p, d_rcursor.p, d_sorted.p);
-    int64_t g = P < (int64_t)ctx->sm_count * 16 ? P : (int64_t)ctx->sm_count * 16;
-    merge_kernel<<<(unsigned)g, MERGE_THREADS, 0, st>>>(d_roff.p, d_sorted.p, P, d_nmerged.p, d_maxlen.p);
-    ctx->launches += 2;
+    ctx->launches++;
+    CB_TRY(launch_merge(ctx, d_roff.p, d_sorted.p, P, d_nmerged.p, d_maxlen.p));
     CB_CUDA(ctx, cudaGetLastError());
     int64_t n_iv = 0;
     CB_TRY(cb_exclusive_scan_u32_to_i64(ctx, d_nmerged.p, cov->d_iv_off, P, &n_iv));

@@ -237,3 +237,27 @@ def test_parallel_rounds_at_scale(ctx, monkeypatch):
     np.add.at(selc, gen[m] * L + s[m], 1)
     np.add.at(selc, gen[m] * L + e[m], -1)
     assert np.array_equal(np.cumsum(allc) > 0, np.cumsum(selc) > 0)
+
+
+def test_merge_paths_small_and_large_range_lists(ctx):
+    """Probes with a handful of ranges take the warp-per-probe merge, probes with more than 512
+    ranges (here: ~700 near-identical genomes) the block-per-probe merge; both against the oracle."""
+    O = _oracle()
+    rng = random.Random(23)
+    anc = ''.join(rng.choice('ACGT') for _ in range(260))
+    anc_b = ''.join(rng.choice('ACGT') for _ in range(260))
+    genomes = [[helpers.mutate(rng, anc, 0.01)] for _ in range(700)] + \
+              [[helpers.mutate(rng, anc_b, 0.01)] for _ in range(4)]
+    probe_strs = list(dict.fromkeys(helpers.tile_candidates([g[0] for g in genomes[:6] + genomes[-2:]], 60, 20)))
+    params = dict(mismatches=3, lcf_thres=40, island_of_exact_match=0, cover_extension=5, kmer_probe_map_k=15)
+    np.random.seed(5)
+    k, seeds, _ = O.choose_seeds(probe_strs, 3, 40, min_k=15, k=15)
+    want = O.make_sets_quads(O.SeedMap(probe_strs, seeds, k), genomes, 3, 40, 0, 5)
+    np.random.seed(5)
+    got, cover, st = _device_quads(ctx, probe_strs, genomes, params)
+    counts = np.bincount(want[:, 0], minlength=len(probe_strs))
+    assert counts.max() > 512 and counts.min() < 512
+    assert np.array_equal(got, want)
+    picks, _ = ctx.setcover(cover, len(probe_strs), None, None)
+    assert picks.tolist() == O.set_cover_quads(want, len(probe_strs), len(genomes))
+    cover.free()
