@@ -69,6 +69,7 @@ struct GreedyParams {
     // parallel-rounds kernel
     unsigned long long *mark;      // [u_words+1] highest key among the active candidates touching the word
     uint32_t *flag;                // [list_cap] conflict flag of active candidate a in the current round
+    uint32_t *hist;                // [2][64] level histograms of the list rebuilds, alternating
 };
 
 // ---- K5: universe = union of all intervals
@@ -789,7 +790,8 @@ __device__ __forceinline__ void apply_interval_warp(const GreedyParams &G, int64
     bool have = false;
 #pragma unroll
     for (int h = 0; h < APPLY_WORDS / 32; h++) have |= mine[h] != 0ull;
-    if (!__any_sync(0xffffffffu, have)) return;    // everything here is covered already (also orders s_uw)
+    __syncwarp();                                   // the staged words are read by the other lanes below
+    if (!__any_sync(0xffffffffu, have)) return;    // everything here is covered already
     int64_t xb = x0 + lane;
     for (;;) {
 #pragma unroll
@@ -858,6 +860,8 @@ __device__ __forceinline__ void apply_interval_warp(const GreedyParams &G, int64
 // The active candidates and the winners are compacted redundantly by every CTA into its own
 // shared memory (same inputs, same deterministic scan), which saves a barrier and all counters.
 // ---------------------------------------------------------------------------------------
+constexpr int PAR_GAIN_LEVELS = 14;
+constexpr int PAR_ID_LEVELS = 33;
 constexpr int PAR_LIST_CAP = 4096;          // upper limit of the candidate list (a runtime cap <= this is used)
 
 template <typename F>
@@ -879,6 +883,7 @@ greedy_par_kernel(const GreedyParams G)
     __shared__ unsigned long long s_key[GREEDY_THREADS / 32];
     __shared__ unsigned long long s_u[(GREEDY_THREADS / 32) * APPLY_WORDS];   // one staging area per warp
     __shared__ uint32_t s_part[GREEDY_THREADS / 32];
+    __shared__ uint32_t s_hist[64];                  // level histogram of a list rebuild
     extern __shared__ uint32_t s_dyn[];
     // per CTA, list_cap entries each: active candidates (probe, gain, first interval, exclusive prefix
     // of the interval counts) and the winners among them (first interval, prefix)
@@ -915,7 +920,6 @@ greedy_par_kernel(const GreedyParams G)
     long long n_picks = 0;
     unsigned long long bar_target = 0, n_rebuilds = 0, n_rounds = 0, n_active_sum = 0;
     uint32_t tau = 1;
-    int band_shift = 4;
     unsigned rb = 0;
     bool need_rebuild = true;
     unsigned long long t_phase[4] = {0, 0, 0, 0}, t_last = 0;
@@ -977,34 +981,76 @@ greedy_par_kernel(const GreedyParams G)
             }
             const uint32_t wmax = 0xffffffffu - (uint32_t)(key & 0xffffffffull);
             const uint32_t gmax = (uint32_t)(key >> 32);
-            for (;;) {
-                const uint32_t band = gmax >> band_shift;
-                tau = gmax - band;
-                if (tau < 1u) tau = 1u;
-                for (int64_t p = gtid; p < G.n_probes; p += gsize) {
-                    const uint32_t g = __ldcg(&G.gain[p]);
-                    if (g >= tau && G.rank_idx[p] == (uint32_t)cur_rank) {
-                        const uint32_t slot = atomicAdd(G.list_n, 1u);
-                        if (slot < G.list_cap) G.list[slot] = (uint32_t)p;
+            // ---- choose the list threshold from a histogram, so that the list holds as many of the
+            // top candidates as fit: gain levels tau_0 = 1, tau_s = gmax - (gmax >> s) (s = 1..12),
+            // tau_13 = gmax; and, should more probes than fit TIE at gmax, id levels
+            // "id < ceil(P / 2^j)" among those ties.  Either way the list is a prefix of the key order.
+            auto tau_of = [&](int lv) -> uint32_t {
+                if (lv == 0) return 1u;
+                if (lv >= PAR_GAIN_LEVELS - 1) return gmax;
+                const uint32_t t = gmax - (gmax >> lv);
+                return t < 1u ? 1u : t;
+            };
+            // id levels halve the span from the smallest tied id (wmax) to the end: sequential greedy
+            // consumes ties from the low ids upwards, so the remaining ones sit in [wmax, P)
+            auto idthr_of = [&](int j) -> unsigned long long {
+                const unsigned long long span = (unsigned long long)G.n_probes - (unsigned long long)wmax;
+                return (unsigned long long)wmax + ((span + (1ull << j) - 1ull) >> j);
+            };
+            if (threadIdx.x < 64) s_hist[threadIdx.x] = 0u;
+            __syncthreads();
+            for (int64_t p = gtid; p < G.n_probes; p += gsize) {
+                const uint32_t g = __ldcg(&G.gain[p]);
+                if (g && G.rank_idx[p] == (uint32_t)cur_rank) {
+                    int lv = PAR_GAIN_LEVELS - 1;
+                    while (lv > 0 && g < tau_of(lv)) lv--;          // largest level the probe qualifies for
+                    atomicAdd(&s_hist[lv], 1u);
+                    if (g == gmax) {
+                        int j = 0;
+                        while (j + 1 < PAR_ID_LEVELS && (unsigned long long)p < idthr_of(j + 1)) j++;
+                        atomicAdd(&s_hist[PAR_GAIN_LEVELS + j], 1u);
                     }
                 }
-                grid_barrier(G.barrier, bar_target);
-                const uint32_t n = __ldcg(G.list_n);
-                if (n <= G.list_cap) {
-                    if (n < G.list_cap / 8 && band_shift > 1) band_shift--;
-                    break;
-                }
-                // too many candidates: everyone has read n; narrow the band and collect again.  When
-                // even the ties at the maximum overflow the list, run this round with the argmax alone.
-                grid_barrier(G.barrier, bar_target);
-                if (gtid == 0) {
-                    if (band == 0u) { G.list[0] = wmax; *G.list_n = 1u; }
-                    else *G.list_n = 0;
-                }
-                grid_barrier(G.barrier, bar_target);
-                if (band == 0u) { tau = gmax; break; }
-                band_shift++;
             }
+            __syncthreads();
+            uint32_t *hist_now = G.hist + 64 * slot_k, *hist_next = G.hist + 64 * (slot_k ^ 1u);
+            if (threadIdx.x < 64 && s_hist[threadIdx.x]) atomicAdd(&hist_now[threadIdx.x], s_hist[threadIdx.x]);
+            grid_barrier(G.barrier, bar_target);
+            if (gtid < 64) hist_next[gtid] = 0u;                    // last read one rebuild ago
+            uint32_t id_thr = 0xffffffffu;
+            {
+                // counts are suffix sums: a probe at level lv also qualifies for every wider level
+                uint32_t c = 0;
+                int pick = -1;
+                for (int lv = PAR_GAIN_LEVELS - 1; lv >= 0; lv--) {
+                    c += __ldcg(&hist_now[lv]);
+                    if (c <= G.list_cap) pick = lv; else break;
+                }
+                if (pick >= 0) {
+                    tau = tau_of(pick);
+                } else {                                            // more ties at gmax than the list holds
+                    tau = gmax;
+                    c = 0;
+                    int pj = -1;
+                    for (int j = PAR_ID_LEVELS - 1; j >= 0; j--) {
+                        c += __ldcg(&hist_now[PAR_GAIN_LEVELS + j]);
+                        if (c <= G.list_cap) pj = j; else break;
+                    }
+                    // the smallest tied id is wmax; an id level that holds no tie at all (or none that
+                    // fits) leaves the argmax alone in the list
+                    unsigned long long thr = pj >= 0 ? idthr_of(pj) : 0ull;
+                    if (thr <= (unsigned long long)wmax) thr = (unsigned long long)wmax + 1ull;
+                    id_thr = thr > 0xffffffffull ? 0xffffffffu : (uint32_t)thr;
+                }
+            }
+            for (int64_t p = gtid; p < G.n_probes; p += gsize) {
+                const uint32_t g = __ldcg(&G.gain[p]);
+                if (g >= tau && (uint32_t)p < id_thr && G.rank_idx[p] == (uint32_t)cur_rank) {
+                    const uint32_t slot = atomicAdd(G.list_n, 1u);
+                    if (slot < G.list_cap) G.list[slot] = (uint32_t)p;      // always true, by the counts
+                }
+            }
+            grid_barrier(G.barrier, bar_target);
             need_rebuild = false;
             n_rebuilds++;
             lap(0);
@@ -1303,10 +1349,11 @@ int cb_setcover_impl(cb_ctx *ctx, const cb_cover *cover, const int32_t *ranks, c
     if (par) {
         CB_CUDA(ctx, d_mark.alloc((size_t)u_words + 1));
         CB_CUDA(ctx, cudaMemsetAsync(d_mark.p, 0, sizeof(unsigned long long) * ((size_t)u_words + 1), st));
-        CB_CUDA(ctx, d_winners.alloc(list_cap));
-        CB_CUDA(ctx, cudaMemsetAsync(d_winners.p, 0, sizeof(uint32_t) * list_cap, st));
+        CB_CUDA(ctx, d_winners.alloc(list_cap + 128));
+        CB_CUDA(ctx, cudaMemsetAsync(d_winners.p, 0, sizeof(uint32_t) * (list_cap + 128), st));
         G.mark = d_mark.p;
         G.flag = d_winners.p;
+        G.hist = d_winners.p + list_cap;
     }
 
     if (full_mode) {

@@ -261,3 +261,29 @@ def test_merge_paths_small_and_large_range_lists(ctx):
     picks, _ = ctx.setcover(cover, len(probe_strs), None, None)
     assert picks.tolist() == O.set_cover_quads(want, len(probe_strs), len(genomes))
     cover.free()
+
+
+def test_parallel_rounds_tie_heavy_regime(ctx, monkeypatch):
+    """Exact-match parameters (m=0, lcf = probe length) make thousands of probes tie at the same small
+    gain and nearly every probe gets picked: the regime that exercises the histogram-chosen list
+    threshold, the id-level tie handling and many winners per round.  The parallel-rounds kernel must
+    give the one-pick kernel's sequence, every time."""
+    from catch_b200 import coverage as cov
+    gens = helpers.synthetic_influenza(40, seed=3)
+    seqs = [seg for g in gens for seg in g]
+    cands = list(dict.fromkeys(helpers.tile_candidates(seqs, 100, 50)))
+    group = cov.PackedGroup(ctx, cands, [[s] for s in seqs])
+    np.random.seed(7)
+    plan = cov.SeedPlan(cands, 0, 100, 20)
+    assert plan.mode == 'pigeonhole'
+    cover, _ = cov.compute_cover(ctx, group, plan, 0, 100, 0, 50)
+    group.free()
+    monkeypatch.setenv('CB_GREEDY', 'inc')
+    want, _ = ctx.setcover(cover, len(cands), None, None)
+    assert len(want) > 1000
+    for cap in ('64', '2048', '2048'):
+        monkeypatch.setenv('CB_GREEDY', 'par')
+        monkeypatch.setenv('CB_GREEDY_LIST_CAP', cap)
+        got, st = ctx.setcover(cover, len(cands), None, None)
+        assert got.tolist() == want.tolist()
+    cover.free()

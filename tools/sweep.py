@@ -73,6 +73,7 @@ def main():
                 'e2e_ms': round(dt * 1e3, 2), 'device_ms': round(dev_ms, 2), 'scan_ms': round(scan_ms, 2),
                 'merge_ms': round(ca['ms_merge'], 2), 'greedy_ms': round(cb['ms_greedy'], 2),
                 'hits': ca['n_candidate_hits'], 'intervals': ca['n_intervals'], 'picks': cb['n_picks'],
+                'greedy_rounds': cb['reserved'][5], 'greedy_rebuilds': cb['reserved'][4],
                 'scan_operand_GBps': round(operand / (scan_ms / 1e3) / 1e9, 1) if scan_ms > 0 else None,
                 'scan_operand_frac_of_hbm_peak': round(operand / (scan_ms / 1e3) / 1e9 / peak, 3) if scan_ms > 0 else None,
             }), flush=True)
