@@ -1,5 +1,7 @@
 """Host side of stage A: packs a group's probes and target genomes, replays the seed choice,
 and drives cb_coverage / cb_setcover.  Everything numeric happens in libcatchb200.so."""
+import itertools
+
 import numpy as np
 
 from catch_b200 import _lib
@@ -64,13 +66,13 @@ class PackedGroup:
         gather_probes() on it, if the caller already has that."""
         self.ctx = ctx
         self.n_probes = len(probe_strs)
-        seqs, seq_genome = [], []
-        for j, g in enumerate(genomes):
-            for s in (g.seqs if hasattr(g, 'seqs') else g):
-                seqs.append(s)
-                seq_genome.append(j)
+        # sequences of all genomes in order, and the genome each belongs to (no per-sequence Python loop:
+        # an influenza-shaped grouping has 40 000 single-sequence genomes)
+        seq_lists = [g.seqs if hasattr(g, 'seqs') else g for g in genomes]
         self.n_genomes = len(genomes)
-        sg = np.array(seq_genome if seq_genome else [0], dtype=np.int32)
+        counts = np.fromiter(map(len, seq_lists), dtype=np.int64, count=self.n_genomes)
+        seqs = list(itertools.chain.from_iterable(seq_lists))
+        sg = np.repeat(np.arange(self.n_genomes, dtype=np.int32), counts) if len(seqs) else np.zeros(1, np.int32)
         staged_t = gather_staged(ctx, 1, seqs)
         if staged_t is not None:
             t_raw, t_lens, t_total = staged_t

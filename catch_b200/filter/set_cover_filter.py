@@ -188,8 +188,11 @@ class SetCoverFilter(BaseFilter):
         sharded = parallel.active()
         if sharded and self._shard_probes(len(input), world_size):
             return self._filter_probe_sharded(input, target_genomes_grouped, rank, world_size)
-        sizes = [len(p) * max(1, sum(g.size() for g in tg)) for p, tg in zip(input, target_genomes_grouped)]
-        owner = parallel.assign_groups(sizes, world_size) if sharded else [rank] * len(input)
+        if sharded:
+            sizes = [len(p) * max(1, sum(g.size() for g in tg)) for p, tg in zip(input, target_genomes_grouped)]
+            owner = parallel.assign_groups(sizes, world_size)
+        else:
+            owner = [rank] * len(input)
         local = {}
         for group_i, (possible_probes, target_genomes) in enumerate(zip(input, target_genomes_grouped)):
             possible_probes = list(possible_probes)
@@ -336,7 +339,7 @@ class SetCoverFilter(BaseFilter):
         ctx = self._context()
         t0 = time.perf_counter()
         stats = {'group': group_i, 'n_probes': len(probe_strs),
-                 'target_bp': sum(g.size() for g in target_genomes)}
+                 'target_bp': group.target_bases if group is not None else sum(g.size() for g in target_genomes)}
         self.last_stats[group_i] = stats
         if len(probe_strs) == 0:                            # set_cover_filter.py:393-394
             return []

@@ -180,3 +180,14 @@ def test_background_draw_can_be_cancelled_without_touching_the_rng():
     k, seeds, mode = cov.finish_draw(cov.draw_seeds(np.full(5000, 75, dtype=np.int32), 2, 60, 20, background=True))
     np.random.seed(11)
     assert mode == 'random' and np.array_equal(seeds, np.random.randint(0, 56, size=(5000, 20)))
+
+
+def test_gather_large_input_takes_the_threaded_copy():
+    """More than 8 MB in total: pass 2 of the gather runs on several threads with the GIL released."""
+    from catch_b200 import coverage as cov
+    rng = np.random.default_rng(1)
+    strs = [''.join('ACGT'[i] for i in rng.integers(0, 4, int(n))) for n in rng.integers(50_000, 150_000, 120)]
+    strs += ['', 'N', 'ACGT' * 3]
+    assert sum(map(len, strs)) > (8 << 20)
+    data, lens = cov.gather_probes(strs)
+    assert data == ''.join(strs).encode() and lens.tolist() == [len(s) for s in strs]
