@@ -45,7 +45,7 @@ EXPORTED_SYMBOLS = [
     'cb_mt19937_randint_end',
     'cb_split_lengths',
     'cb_coverage', 'cb_coverage_uniform', 'cb_cover_free', 'cb_cover_num_intervals', 'cb_cover_export', 'cb_cover_import',
-    'cb_setcover', 'cb_minhash_neardup', 'cb_hamming_neardup',
+    'cb_setcover', 'cb_minhash_neardup', 'cb_hamming_neardup', 'cb_neardup_filter',
     'cb_comm_unique_id', 'cb_comm_init', 'cb_comm_destroy', 'cb_cover_allgather',
 ]
 
@@ -100,6 +100,8 @@ def load():
     L.cb_cover_allgather.argtypes = [vp, vp, i64, i64, C.POINTER(vp)]
     L.cb_setcover.argtypes = [vp, vp, vp, vp, vp, C.POINTER(i64), C.POINTER(Stats)]
     L.cb_minhash_neardup.argtypes = [vp, vp, vp, i64, vp, vp, i32, i32, i32, C.c_double, vp, C.POINTER(Stats)]
+    L.cb_neardup_filter.argtypes = [vp, vp, vp, i64, i32, vp, vp, vp, i32, i32, i32, C.c_double, vp, C.POINTER(i64),
+                                    C.POINTER(i64), C.POINTER(Stats)]
     L.cb_hamming_neardup.argtypes = [vp, vp, vp, i64, vp, i32, i32, i32, vp, C.POINTER(Stats)]
     _lib = L
     return L
@@ -267,6 +269,19 @@ class Context:
                                               n_tables, k_concat, kmer_size, float(dist_thres), _ptr(keep),
                                               C.byref(st)))
         return keep[:n], st
+
+    def neardup_filter(self, raw, probe_off, family, a, b, positions, n_tables, k_concat, kmer_size, dist_thres):
+        """cb_neardup_filter on the whole probe list (duplicates included).  `raw`: bytes object or the
+        address of staged host memory holding the sequences back to back.  Returns (list indices of
+        the first occurrence of every kept sequence in priority order, number of distinct sequences,
+        stats)."""
+        n = len(probe_off) - 1
+        kept = np.zeros(max(n, 1), dtype=np.int64)
+        nk, nd, st = C.c_int64(), C.c_int64(), Stats()
+        self._check(self.L.cb_neardup_filter(self.h, raw, _ptr(probe_off), n, family, _ptr(a), _ptr(b),
+                                             _ptr(positions), n_tables, k_concat, kmer_size, float(dist_thres),
+                                             _ptr(kept), C.byref(nk), C.byref(nd), C.byref(st)))
+        return kept[:nk.value].copy(), nd.value, st
 
     def hamming_neardup(self, ascii_u8, probe_off, positions, n_tables, k_concat, dist_thres):
         n = len(probe_off) - 1

@@ -618,6 +618,20 @@ int cb_minhash_neardup(cb_ctx *ctx, const uint8_t *ascii, const int64_t *probe_o
                                    dist_thres, keep, stats);
 }
 
+int cb_neardup_filter(cb_ctx *ctx, const uint8_t *ascii, const int64_t *probe_off, int64_t n_probes, int32_t family,
+                      const uint32_t *a, const uint32_t *b, const int32_t *positions, int32_t n_tables,
+                      int32_t k_concat, int32_t kmer_size, double dist_thres, int64_t *kept_first_idx,
+                      int64_t *n_kept, int64_t *n_distinct, cb_stats *stats)
+{
+    if (!ctx) return CB_ERR_ARG;
+    if (stats) memset(stats, 0, sizeof *stats);
+    ctx->launches = 0;
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cb_tls_stream = ctx->stream;
+    return cb_neardup_filter_impl(ctx, ascii, probe_off, n_probes, family, a, b, positions, n_tables, k_concat,
+                                  kmer_size, dist_thres, kept_first_idx, n_kept, n_distinct, stats);
+}
+
 int cb_hamming_neardup(cb_ctx *ctx, const uint8_t *ascii, const int64_t *probe_off, int64_t n_probes,
                        const int32_t *positions, int32_t n_tables, int32_t k_concat, int32_t dist_thres,
                        uint8_t *keep, cb_stats *stats)

@@ -191,6 +191,10 @@ int cb_setcover_impl(cb_ctx *ctx, const cb_cover *cover, const int32_t *ranks, c
 int cb_minhash_neardup_impl(cb_ctx *ctx, const uint8_t *ascii, const int64_t *probe_off, int64_t n_probes,
                             const uint32_t *a, const uint32_t *b, int32_t n_tables, int32_t k_concat,
                             int32_t kmer_size, double dist_thres, uint8_t *keep, cb_stats *stats);
+int cb_neardup_filter_impl(cb_ctx *ctx, const uint8_t *ascii, const int64_t *probe_off, int64_t n, int32_t family,
+                           const uint32_t *pa, const uint32_t *pb, const int32_t *positions, int32_t n_tables,
+                           int32_t k_concat, int32_t kmer, double dist_thres, int64_t *kept_first_idx,
+                           int64_t *n_kept, int64_t *n_distinct_out, cb_stats *stats);
 int cb_hamming_neardup_impl(cb_ctx *ctx, const uint8_t *ascii, const int64_t *probe_off, int64_t n_probes,
                             const int32_t *positions, int32_t n_tables, int32_t k_concat,
                             int32_t dist_thres, uint8_t *keep, cb_stats *stats);

@@ -370,29 +370,17 @@ __global__ void finish_kernel(const uint8_t *__restrict__ state, int64_t n, uint
         keep[i] = state[i] == 1;
 }
 
-int neardup_common(cb_ctx *ctx, const uint8_t *ascii, const int64_t *probe_off, int64_t P, int family,
-                   const uint32_t *pa, const uint32_t *pb, const int32_t *positions, int n_tables, int k_concat,
-                   int kmer, double dist_thres, uint8_t *keep, cb_stats *stats)
+// Host-side checks shared by the entry points: per-probe lengths -> relative offsets and k-mer
+// offsets; symbol table for the exact k-mer codes of the MinHash family.
+int neardup_tables(cb_ctx *ctx, int64_t P, int family, int kmer, const int32_t *positions, int n_fn,
+                   const std::vector<int64_t> &h_off, std::vector<int64_t> &h_koff, const bool present[256],
+                   uint8_t lut[256], int &cbits)
 {
-    if (P < 0 || n_tables < 1 || k_concat < 1 || !keep) return cb_fail(ctx, CB_ERR_ARG, "bad argument");
-    if (P == 0) return CB_OK;
-    if (!ascii || !probe_off) return cb_fail(ctx, CB_ERR_ARG, "null probe table");
-    if (P >= 0xfffffff0ll) return cb_fail(ctx, CB_ERR_UNSUPPORTED, "too many probes");
-    cudaStream_t st = ctx->stream;
-    const int n_fn = n_tables * k_concat;
-    const int64_t base = probe_off[0];
-    const int64_t total = probe_off[P] - base;
-    const int wide = ctx->sm_count * 8;
-    EventTimer t_all(st), t_sig(st), t_rounds(st);
-
-    // host-side checks and tables
-    std::vector<int64_t> h_off((size_t)P + 1), h_koff((size_t)P + 1, 0);
-    bool present[256] = {false};
-    int L0 = (int)(probe_off[1] - probe_off[0]);
+    h_koff.assign((size_t)P + 1, 0);
+    const int L0 = P ? (int)(h_off[1] - h_off[0]) : 0;
     for (int64_t p = 0; p < P; p++) {
-        const int64_t len = probe_off[p + 1] - probe_off[p];
+        const int64_t len = h_off[(size_t)p + 1] - h_off[(size_t)p];
         if (len < 0 || len > ND_MAX_LEN) return cb_fail(ctx, CB_ERR_UNSUPPORTED, "probe length outside [0, 256]");
-        h_off[(size_t)p] = probe_off[p] - base;
         if (family == 0) {
             if (len < kmer) return cb_fail(ctx, CB_ERR_ARG, "kmer_size exceeds a probe's length (utils/lsh.py:117)");
             h_koff[(size_t)p + 1] = h_koff[(size_t)p] + (len - kmer + 1);
@@ -400,12 +388,10 @@ int neardup_common(cb_ctx *ctx, const uint8_t *ascii, const int64_t *probe_off, 
             return cb_fail(ctx, CB_ERR_ARG, "Hamming family needs probes of one length (utils/lsh.py:30)");
         }
     }
-    h_off[(size_t)P] = total;
-    uint8_t lut[256] = {0};
-    int cbits = 1;
+    memset(lut, 0, 256);
+    cbits = 1;
     if (family == 0) {
         if (kmer < 1) return cb_fail(ctx, CB_ERR_ARG, "kmer_size must be positive");
-        for (int64_t i = 0; i < total; i++) present[ascii[base + i]] = true;
         int n_sym = 0;
         for (int c = 0; c < 256; c++) if (present[c]) lut[c] = (uint8_t)n_sym++;
         while ((1 << cbits) < n_sym) cbits++;
@@ -415,19 +401,31 @@ int neardup_common(cb_ctx *ctx, const uint8_t *ascii, const int64_t *probe_off, 
         for (int f = 0; f < n_fn; f++)
             if (positions[f] < 0 || positions[f] >= L0) return cb_fail(ctx, CB_ERR_ARG, "sampled position out of range");
     }
+    return CB_OK;
+}
 
+// The device pipeline on P distinct probes in priority order whose bytes are already on the device
+// (d_ascii, relative offsets h_off).  keep[i] (host) = 1 iff probe i is kept.
+int neardup_run(cb_ctx *ctx, const uint8_t *d_ascii_in, const std::vector<int64_t> &h_off,
+                const std::vector<int64_t> &h_koff, const uint8_t lut[256], int cbits, int64_t P, int family,
+                const uint32_t *pa, const uint32_t *pb, const int32_t *positions, int n_tables, int k_concat,
+                int kmer, double dist_thres, uint8_t *keep, cb_stats *stats)
+{
+    cudaStream_t st = ctx->stream;
+    const int n_fn = n_tables * k_concat;
+    const int wide = ctx->sm_count * 8;
+    EventTimer t_all(st), t_sig(st), t_rounds(st);
     t_all.start();
-    DevBuf<uint8_t> d_ascii, d_lut, d_state, d_keep;
+    struct { const uint8_t *p; } d_ascii{d_ascii_in};
+    DevBuf<uint8_t> d_lut, d_state, d_keep;
     DevBuf<int64_t> d_off, d_koff, d_boff;
     DevBuf<uint32_t> d_X, d_kcnt, d_pa, d_pb, d_sig, d_pg, d_bsize, d_grpmin, d_inccount, d_inclist, d_checked;
     DevBuf<int32_t> d_pos;
     DevBuf<uint64_t> d_kset;
     DevBuf<unsigned long long> d_ctr;
-    CB_CUDA(ctx, d_ascii.alloc((size_t)total));
     CB_CUDA(ctx, d_off.alloc((size_t)P + 1));
     CB_CUDA(ctx, d_sig.alloc((size_t)P * n_fn));
     CB_CUDA(ctx, d_ctr.alloc(2));
-    CB_CUDA(ctx, cudaMemcpyAsync(d_ascii.p, ascii + base, (size_t)total, cudaMemcpyHostToDevice, st));
     CB_CUDA(ctx, cudaMemcpyAsync(d_off.p, h_off.data(), sizeof(int64_t) * (size_t)(P + 1), cudaMemcpyHostToDevice, st));
 
     t_sig.start();
@@ -529,9 +527,9 @@ int neardup_common(cb_ctx *ctx, const uint8_t *ascii, const int64_t *probe_off, 
     CB_CUDA(ctx, cudaMemcpyAsync(keep, d_keep.p, (size_t)P, cudaMemcpyDeviceToHost, st));
     CB_CUDA(ctx, cudaStreamSynchronize(st));
     if (stats) {
-        stats->ms_seed_index = t_sig.ms();       // signatures + buckets
-        stats->ms_greedy = t_rounds.ms();        // decision rounds
-        stats->ms_total = t_all.ms();
+        stats->ms_seed_index += t_sig.ms();      // signatures + buckets
+        stats->ms_greedy += t_rounds.ms();       // decision rounds
+        stats->ms_total += t_all.ms();
         stats->n_picks = rounds;
         stats->n_candidate_hits = (int64_t)h_ctr[1];   // exact distance evaluations
         stats->n_kernel_launches = ctx->launches;
@@ -539,7 +537,245 @@ int neardup_common(cb_ctx *ctx, const uint8_t *ascii, const int64_t *probe_off, 
     return CB_OK;
 }
 
+// cb_minhash_neardup / cb_hamming_neardup: the caller passes the DISTINCT probes in priority order.
+int neardup_common(cb_ctx *ctx, const uint8_t *ascii, const int64_t *probe_off, int64_t P, int family,
+                   const uint32_t *pa, const uint32_t *pb, const int32_t *positions, int n_tables, int k_concat,
+                   int kmer, double dist_thres, uint8_t *keep, cb_stats *stats)
+{
+    if (P < 0 || n_tables < 1 || k_concat < 1 || !keep) return cb_fail(ctx, CB_ERR_ARG, "bad argument");
+    if (P == 0) return CB_OK;
+    if (!ascii || !probe_off) return cb_fail(ctx, CB_ERR_ARG, "null probe table");
+    if (P >= 0xfffffff0ll) return cb_fail(ctx, CB_ERR_UNSUPPORTED, "too many probes");
+    const int64_t base = probe_off[0];
+    const int64_t total = probe_off[P] - base;
+    std::vector<int64_t> h_off((size_t)P + 1), h_koff;
+    for (int64_t p = 0; p <= P; p++) h_off[(size_t)p] = probe_off[p] - base;
+    bool present[256] = {false};
+    if (family == 0)
+        for (int64_t i = 0; i < total; i++) present[ascii[base + i]] = true;
+    uint8_t lut[256];
+    int cbits = 1;
+    CB_TRY(neardup_tables(ctx, P, family, kmer, positions, n_tables * k_concat, h_off, h_koff, present, lut, cbits));
+    DevBuf<uint8_t> d_ascii;
+    CB_CUDA(ctx, d_ascii.alloc((size_t)total));
+    CB_CUDA(ctx, cudaMemcpyAsync(d_ascii.p, ascii + base, (size_t)total, cudaMemcpyHostToDevice, ctx->stream));
+    return neardup_run(ctx, d_ascii.p, h_off, h_koff, lut, cbits, P, family, pa, pb, positions, n_tables, k_concat,
+                       kmer, dist_thres, keep, stats);
+}
+
+
+// ---------------------------------------------------------------------------------------
+// Exact-duplicate grouping on the device (filter/near_duplicate_filter.py:61-66: occurrences[p] += 1
+// over Probe objects that hash and compare by sequence).  Probes are packed to bit planes first, so
+// two probes are the same sequence iff their lengths and packed words are equal.
+// An open-addressing table holds, per distinct sequence, the SMALLEST list index carrying it:
+// a probe walks its probe sequence until it finds a free slot (claims it) or a slot whose occupant
+// is the same sequence (atomicMin of the index).  Slots never change their sequence class, so all
+// probes of a class end in the same slot whatever the interleaving.
+// ---------------------------------------------------------------------------------------
+constexpr uint32_t GRP_EMPTY = 0xffffffffu;
+
+__device__ __forceinline__ uint64_t hash_packed(const uint64_t *w, int wpp, int len)
+{
+    uint64_t h = 0x9E3779B97F4A7C15ull ^ (uint64_t)len;
+    for (int i = 0; i < wpp; i++) {
+        h ^= w[i];
+        h *= 0xBF58476D1CE4E5B9ull;
+        h ^= h >> 31;
+    }
+    return h;
+}
+
+__device__ __forceinline__ bool same_packed(const uint64_t *words, const int32_t *lens, int wpp, int64_t a, int64_t b)
+{
+    if (lens[a] != lens[b]) return false;
+    const uint64_t *x = words + a * wpp, *y = words + b * wpp;
+    for (int i = 0; i < wpp; i++)
+        if (x[i] != y[i]) return false;
+    return true;
+}
+
+template <bool INSERT>
+__global__ void group_kernel(const uint64_t *__restrict__ words, const int32_t *__restrict__ lens, int64_t n, int wpp,
+                             uint32_t *table, uint32_t mask, uint32_t *__restrict__ count, uint32_t *__restrict__ is_rep)
+{
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t slot = (uint32_t)(hash_packed(words + p * wpp, wpp, lens[p]) >> 17) & mask;
+        for (;;) {
+            uint32_t cur = __ldcg(&table[slot]);
+            if (INSERT && cur == GRP_EMPTY) {
+                cur = atomicCAS(&table[slot], GRP_EMPTY, (uint32_t)p);
+                if (cur == GRP_EMPTY) break;                       // claimed
+            }
+            if (cur != GRP_EMPTY && same_packed(words, lens, wpp, p, (int64_t)cur)) {
+                if (INSERT) atomicMin(&table[slot], (uint32_t)p);
+                else {
+                    atomicAdd(&count[cur], 1u);                    // cur is the class's first occurrence now
+                    is_rep[p] = cur == (uint32_t)p ? 1u : 0u;
+                }
+                break;
+            }
+            slot = (slot + 1) & mask;
+        }
+    }
+}
+
+__global__ void group_compact_kernel(const uint32_t *__restrict__ is_rep, const int64_t *__restrict__ pos,
+                                     const uint32_t *__restrict__ count, int64_t n, uint32_t *__restrict__ first_idx,
+                                     uint32_t *__restrict__ mult)
+{
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x)
+        if (is_rep[p]) {
+            first_idx[pos[p]] = (uint32_t)p;
+            mult[pos[p]] = count[p];
+        }
+}
+
+// bytes of the chosen probes, back to back in the given order: one warp per probe
+__global__ void gather_bytes_kernel(const uint8_t *__restrict__ src, const int64_t *__restrict__ src_off,
+                                    const int64_t *__restrict__ dst_off, int64_t n, uint8_t *__restrict__ dst)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t p = warp; p < n; p += n_warps) {
+        const int64_t a = src_off[p], b = dst_off[p];
+        const int len = (int)(dst_off[p + 1] - b);
+        for (int i = lane; i < len; i += 32) dst[b + i] = src[a + i];
+    }
+}
+
 }  // namespace
+
+// Whole near-duplicate filter for one probe list WITH its duplicates, in list order: grouping of
+// identical sequences, priority order (multiplicity descending, first occurrence ascending --
+// Python's stable sorted(..., reverse=True) over a dict in insertion order), LSH filter.
+int cb_neardup_filter_impl(cb_ctx *ctx, const uint8_t *ascii, const int64_t *probe_off, int64_t n, int32_t family,
+                           const uint32_t *pa, const uint32_t *pb, const int32_t *positions, int32_t n_tables,
+                           int32_t k_concat, int32_t kmer, double dist_thres, int64_t *kept_first_idx,
+                           int64_t *n_kept, int64_t *n_distinct_out, cb_stats *stats)
+{
+    if (n < 0 || n_tables < 1 || k_concat < 1 || !kept_first_idx || !n_kept) return cb_fail(ctx, CB_ERR_ARG, "bad argument");
+    *n_kept = 0;
+    if (n_distinct_out) *n_distinct_out = 0;
+    if (n == 0) return CB_OK;
+    if (!ascii || !probe_off) return cb_fail(ctx, CB_ERR_ARG, "null probe table");
+    if (n >= 0xfffffff0ll) return cb_fail(ctx, CB_ERR_UNSUPPORTED, "too many probes");
+    if (family == 0 ? (!pa || !pb) : !positions) return cb_fail(ctx, CB_ERR_ARG, "null hash parameters");
+    cudaStream_t st = ctx->stream;
+    const int wide = ctx->sm_count * 8;
+    const int64_t base = probe_off[0], total = probe_off[n] - base;
+    int max_len = 0;
+    std::vector<int64_t> rel((size_t)n + 1);
+    for (int64_t i = 0; i <= n; i++) rel[(size_t)i] = probe_off[i] - base;
+    for (int64_t i = 0; i < n; i++) {
+        const int64_t len = rel[(size_t)i + 1] - rel[(size_t)i];
+        if (len < 0 || len > ND_MAX_LEN) return cb_fail(ctx, CB_ERR_UNSUPPORTED, "probe length outside [0, 256]");
+        if (len > max_len) max_len = (int)len;
+    }
+    EventTimer t_grp(st);
+    t_grp.start();
+    // ---- bytes and offsets to the device, symbol table, bit planes
+    DevBuf<uint8_t> d_ascii, d_lut;
+    DevBuf<int64_t> d_off, d_pos;
+    DevBuf<uint32_t> d_present, d_table, d_count, d_isrep, d_first, d_mult;
+    DevBuf<uint64_t> d_words;
+    DevBuf<int32_t> d_len;
+    CB_CUDA(ctx, d_ascii.alloc((size_t)total));
+    CB_CUDA(ctx, d_off.alloc((size_t)n + 1));
+    CB_CUDA(ctx, d_present.alloc(256));
+    CB_CUDA(ctx, cudaMemsetAsync(d_present.p, 0, sizeof(uint32_t) * 256, st));
+    if (total) CB_CUDA(ctx, cudaMemcpyAsync(d_ascii.p, ascii + base, (size_t)total, cudaMemcpyHostToDevice, st));
+    CB_CUDA(ctx, cudaMemcpyAsync(d_off.p, rel.data(), sizeof(int64_t) * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
+    CB_TRY(cb_launch_byte_presence(ctx, d_ascii.p, total, d_present.p));
+    uint32_t h_present[256];
+    CB_CUDA(ctx, cudaMemcpyAsync(h_present, d_present.p, sizeof h_present, cudaMemcpyDeviceToHost, st));
+    CB_CUDA(ctx, cudaStreamSynchronize(st));
+    bool present[256];
+    uint8_t pack_lut[256];
+    memset(pack_lut, 0, sizeof pack_lut);
+    int n_sym = 0;
+    for (int c = 0; c < 256; c++) {
+        present[c] = h_present[c] != 0;
+        if (present[c]) pack_lut[c] = (uint8_t)n_sym++;
+    }
+    int bits = 1;
+    while ((1 << bits) < n_sym) bits++;
+    const int nw = max_len ? (max_len + 63) / 64 : 1, wpp = bits * nw;
+    CB_CUDA(ctx, d_lut.alloc(256));
+    CB_CUDA(ctx, cudaMemcpyAsync(d_lut.p, pack_lut, 256, cudaMemcpyHostToDevice, st));
+    CB_CUDA(ctx, d_words.alloc((size_t)n * (size_t)wpp));
+    CB_CUDA(ctx, d_len.alloc((size_t)n));
+    CB_TRY(cb_launch_pack_probes(ctx, d_ascii.p, d_off.p, 0, n, d_lut.p, bits, nw, d_words.p, d_len.p));
+    // ---- grouping
+    int64_t cap = 1024;
+    while (cap < 2 * n) cap <<= 1;
+    CB_CUDA(ctx, d_table.alloc((size_t)cap));
+    CB_CUDA(ctx, d_count.alloc((size_t)n));
+    CB_CUDA(ctx, d_isrep.alloc((size_t)n));
+    CB_CUDA(ctx, d_pos.alloc((size_t)n + 1));
+    CB_CUDA(ctx, cudaMemsetAsync(d_table.p, 0xff, sizeof(uint32_t) * (size_t)cap, st));
+    CB_CUDA(ctx, cudaMemsetAsync(d_count.p, 0, sizeof(uint32_t) * (size_t)n, st));
+    group_kernel<true><<<wide, ND_THREADS, 0, st>>>(d_words.p, d_len.p, n, wpp, d_table.p, (uint32_t)(cap - 1), nullptr, nullptr);
+    group_kernel<false><<<wide, ND_THREADS, 0, st>>>(d_words.p, d_len.p, n, wpp, d_table.p, (uint32_t)(cap - 1), d_count.p, d_isrep.p);
+    ctx->launches += 2;
+    CB_CUDA(ctx, cudaGetLastError());
+    int64_t D = 0;
+    CB_TRY(cb_exclusive_scan_u32_to_i64(ctx, d_isrep.p, d_pos.p, n, &D));
+    CB_CUDA(ctx, d_first.alloc((size_t)D));
+    CB_CUDA(ctx, d_mult.alloc((size_t)D));
+    group_compact_kernel<<<wide, ND_THREADS, 0, st>>>(d_isrep.p, d_pos.p, d_count.p, n, d_first.p, d_mult.p);
+    ctx->launches++;
+    CB_CUDA(ctx, cudaGetLastError());
+    std::vector<uint32_t> h_first((size_t)D), h_mult((size_t)D);
+    CB_CUDA(ctx, cudaMemcpyAsync(h_first.data(), d_first.p, sizeof(uint32_t) * (size_t)D, cudaMemcpyDeviceToHost, st));
+    CB_CUDA(ctx, cudaMemcpyAsync(h_mult.data(), d_mult.p, sizeof(uint32_t) * (size_t)D, cudaMemcpyDeviceToHost, st));
+    CB_CUDA(ctx, cudaStreamSynchronize(st));
+    if (n_distinct_out) *n_distinct_out = D;
+    // ---- priority order: multiplicity descending, first occurrence ascending (the distinct entries
+    // arrive in first-occurrence order, so a stable counting sort by multiplicity does it)
+    uint32_t max_mult = 0;
+    for (int64_t i = 0; i < D; i++) max_mult = std::max(max_mult, h_mult[(size_t)i]);
+    std::vector<int64_t> start((size_t)max_mult + 2, 0);
+    for (int64_t i = 0; i < D; i++) start[(size_t)(max_mult - h_mult[(size_t)i]) + 1]++;
+    for (size_t c = 1; c < start.size(); c++) start[c] += start[c - 1];
+    std::vector<uint32_t> ordered((size_t)D);                      // list index of the k-th probe in priority order
+    for (int64_t i = 0; i < D; i++) ordered[(size_t)start[(size_t)(max_mult - h_mult[(size_t)i])]++] = h_first[(size_t)i];
+    std::vector<int64_t> h_src((size_t)D), h_off((size_t)D + 1), h_koff;
+    h_off[0] = 0;
+    for (int64_t k = 0; k < D; k++) {
+        const uint32_t i = ordered[(size_t)k];
+        h_src[(size_t)k] = rel[i];
+        h_off[(size_t)k + 1] = h_off[(size_t)k] + (rel[(size_t)i + 1] - rel[i]);
+    }
+    uint8_t lut[256];
+    int cbits = 1;
+    CB_TRY(neardup_tables(ctx, D, family, kmer, positions, n_tables * k_concat, h_off, h_koff, present, lut, cbits));
+    DevBuf<uint8_t> d_ord;
+    DevBuf<int64_t> d_src, d_dst;
+    CB_CUDA(ctx, d_ord.alloc((size_t)h_off[(size_t)D]));
+    CB_CUDA(ctx, d_src.alloc((size_t)D));
+    CB_CUDA(ctx, d_dst.alloc((size_t)D + 1));
+    CB_CUDA(ctx, cudaMemcpyAsync(d_src.p, h_src.data(), sizeof(int64_t) * (size_t)D, cudaMemcpyHostToDevice, st));
+    CB_CUDA(ctx, cudaMemcpyAsync(d_dst.p, h_off.data(), sizeof(int64_t) * (size_t)(D + 1), cudaMemcpyHostToDevice, st));
+    gather_bytes_kernel<<<wide, ND_THREADS, 0, st>>>(d_ascii.p, d_src.p, d_dst.p, D, d_ord.p);
+    ctx->launches++;
+    CB_CUDA(ctx, cudaGetLastError());
+    t_grp.stop();
+    std::vector<uint8_t> keep((size_t)D, 0);
+    CB_TRY(neardup_run(ctx, d_ord.p, h_off, h_koff, lut, cbits, D, family, pa, pb, positions, n_tables, k_concat, kmer,
+                       dist_thres, keep.data(), stats));
+    int64_t nk = 0;
+    for (int64_t k = 0; k < D; k++)
+        if (keep[(size_t)k]) kept_first_idx[nk++] = (int64_t)ordered[(size_t)k];
+    *n_kept = nk;
+    if (stats) {
+        stats->ms_pack = t_grp.ms();             // upload, packing, grouping, ordering, gather
+        stats->ms_total += stats->ms_pack;
+        stats->n_intervals = D;                  // distinct sequences
+    }
+    return CB_OK;
+}
 
 int cb_minhash_neardup_impl(cb_ctx *ctx, const uint8_t *ascii, const int64_t *probe_off, int64_t n_probes,
                             const uint32_t *a, const uint32_t *b, int32_t n_tables, int32_t k_concat,

@@ -5,15 +5,13 @@ kmer_size=10)` :163, `NearDuplicateFilterWithHammingDistance(dist_thres, probe_l
 `.reporting_prob` are read and mutated by callers).  `_filter(input)` keeps the highest-multiplicity
 probe of every LSH-connected neighbourhood exactly as the reference's sequential loop does (:47-103).
 
-Host work kept here: multiplicity ordering (:61-66), drawing the hash-function parameters from
-Python's `random` in the reference's call order (utils/lsh.py:28,95-96,224,284-287) and rebuilding
-the Python-set order of the result (:103).  The MinHash inner hash is CPython's str hash; like the
-reference this is only reproducible under PYTHONHASHSEED=0, which is what the device implements
-(SipHash-1-3 with a zero key).
+Host work kept here: drawing the hash-function parameters from Python's `random` in the reference's
+call order (utils/lsh.py:28,95-96,224,284-287) and rebuilding the Python-set order of the result
+(:103).  Grouping identical sequences and the multiplicity ordering (:61-66) run in the library.
+The MinHash inner hash is CPython's str hash; like the reference this is only reproducible under
+PYTHONHASHSEED=0, which is what the device implements (SipHash-1-3 with a zero key).
 """
-import collections
 import math
-import operator
 import random
 
 import numpy as np
@@ -44,29 +42,33 @@ class NearDuplicateFilter(BaseFilter):
             self._ctx = _lib.default_context()
         return self._ctx
 
-    def _draw_and_run(self, ctx, buf, off):
+    def _draw_and_run(self, ctx, raw, off, lens):
         raise NotImplementedError
 
     def _filter(self, input):
-        # multiplicity, descending, stable in first-occurrence order (:61-66).  Counting runs on the
-        # sequence strings (C speed); the objects returned are the first-seen Probe of each sequence,
-        # as with the reference's dict keyed by Probe.
+        """One library call per probe list: the sequences (duplicates included, list order) are gathered
+        into one buffer; grouping by sequence, the multiplicity ordering (:61-66), the LSH tables and
+        the sequential keep/drop loop (:81-96) all run in cb_neardup_filter.  It returns, in priority
+        order, the list index of the first occurrence of every kept sequence -- the Probe object the
+        reference's dict keyed by Probe keeps."""
         input = list(input)
-        strs = [p.seq_str for p in input]
-        occurrences = collections.Counter(strs)
-        order = [s for s, _ in sorted(occurrences.items(), key=operator.itemgetter(1), reverse=True)]
-        if not order:
+        if not input:
             # the reference still builds the lookup (and draws its parameters) for empty input
             self._draw_only()
             return []
-        first_seen = dict(zip(reversed(strs), reversed(input)))
-        buf, off, _ = cov._concat_ascii(order)
-        keep, st = self._draw_and_run(self._context(), buf, off)
+        ctx = self._context()
+        gathered = cov.gather_staged(ctx, 0, input)
+        if gathered is None:
+            gathered = cov.gather_probes(input)
+        raw, lens = gathered[0], gathered[1]
+        off = np.zeros(len(input) + 1, dtype=np.int64)
+        np.cumsum(lens, out=off[1:])
+        kept, n_distinct, st = self._draw_and_run(ctx, raw, off, lens)
         self.last_stats = st.as_dict()
+        self.last_stats['n_distinct'] = n_distinct
         to_include = set()
-        for s, k in zip(order, keep.tolist()):
-            if k:
-                to_include.add(first_seen[s])
+        for i in kept.tolist():
+            to_include.add(input[i])
         return list(to_include)                                   # :103
 
 
@@ -85,11 +87,11 @@ class NearDuplicateFilterWithHammingDistance(NearDuplicateFilter):
     def _draw_only(self):
         self._params()
 
-    def _draw_and_run(self, ctx, buf, off):
+    def _draw_and_run(self, ctx, raw, off, lens):
         n_tab, pos = self._params()
-        if np.any(np.diff(off) != self.probe_length):
+        if np.any(lens != self.probe_length):
             raise AssertionError("all probes must have length %d" % self.probe_length)    # utils/lsh.py:30
-        return ctx.hamming_neardup(buf, off, pos, n_tab, self.k, self.dist_thres)
+        return ctx.neardup_filter(raw, off, 1, None, None, pos, n_tab, self.k, 0, self.dist_thres)
 
 
 class NearDuplicateFilterWithMinHash(NearDuplicateFilter):
@@ -110,8 +112,8 @@ class NearDuplicateFilterWithMinHash(NearDuplicateFilter):
     def _draw_only(self):
         self._params()
 
-    def _draw_and_run(self, ctx, buf, off):
+    def _draw_and_run(self, ctx, raw, off, lens):
         n_tab, a, b = self._params()
-        if np.any(np.diff(off) < self.kmer_size):
+        if np.any(lens < self.kmer_size):
             raise AssertionError("kmer_size exceeds the length of a probe")               # utils/lsh.py:117
-        return ctx.minhash_neardup(buf, off, a, b, n_tab, self.k, self.kmer_size, self.dist_thres)
+        return ctx.neardup_filter(raw, off, 0, a, b, None, n_tab, self.k, self.kmer_size, self.dist_thres)

@@ -232,6 +232,18 @@ int cb_hamming_neardup(cb_ctx *ctx, const uint8_t *ascii, const int64_t *probe_o
                        const int32_t *positions, int32_t n_tables, int32_t k_concat,
                        int32_t dist_thres, uint8_t *keep, cb_stats *stats);
 
+/* The whole of NearDuplicateFilter._filter (filter/near_duplicate_filter.py:47-103) for one probe
+ * list WITH its duplicates, in list order: identical sequences are grouped on the device
+ * (occurrences[p] += 1, :61-63), the distinct ones are ranked by multiplicity descending and first
+ * occurrence ascending (the stable sorted(..., reverse=True) of :64-66), and the LSH filter above
+ * runs on them.  family: 0 = MinHash (a, b, kmer_size used), 1 = Hamming (positions used).
+ * kept_first_idx (caller-allocated, capacity n_probes) receives, in priority order, the list index
+ * of the FIRST occurrence of every kept sequence -- the Probe object the reference's dict keeps. */
+int cb_neardup_filter(cb_ctx *ctx, const uint8_t *ascii, const int64_t *probe_off, int64_t n_probes,
+                      int32_t family, const uint32_t *a, const uint32_t *b, const int32_t *positions,
+                      int32_t n_tables, int32_t k_concat, int32_t kmer_size, double dist_thres,
+                      int64_t *kept_first_idx, int64_t *n_kept, int64_t *n_distinct, cb_stats *stats);
+
 #ifdef __cplusplus
 }
 #endif
