@@ -194,14 +194,22 @@ class SetCoverFilter(BaseFilter):
         else:
             owner = [rank] * len(input)
         local = {}
+        pending_sends = []
         for group_i, (possible_probes, target_genomes) in enumerate(zip(input, target_genomes_grouped)):
+            # The seed draws consume numpy's global RNG per grouping, in grouping order, first for
+            # _make_sets and then for _make_ranks (set_cover_filter.py:824-827).  In a sharded run the
+            # RNG state is a token that travels along the groupings from owner to owner, so that every
+            # grouping sees the stream of a single-process run while a rank only ever touches the
+            # groupings it owns.
+            mine = owner[group_i] == rank
+            if sharded:
+                if not mine:
+                    continue
+                if group_i > 0 and owner[group_i - 1] != rank:
+                    parallel.rng_recv(owner[group_i - 1])
             possible_probes = list(possible_probes)
             n_probes = len(possible_probes)
             probe_strs = _LazyStrs(possible_probes)
-            # The seed draws consume numpy's global RNG per grouping, in grouping order, first for
-            # _make_sets and then for _make_ranks (set_cover_filter.py:824-827); every rank replays
-            # all of them so that a sharded run sees the same stream as a single process.
-            mine = owner[group_i] == rank
             group = None
             lengths, dups = None, True
             host_ms = {}
@@ -267,11 +275,16 @@ class SetCoverFilter(BaseFilter):
                                             self.kmer_probe_map_k, lengths=lengths, may_have_dups=dups and mine,
                                             drawn=drawn_tol)
                 mark('seed_plan')
+            if sharded and group_i + 1 < len(input) and owner[group_i + 1] != rank:
+                pending_sends.append(parallel.rng_isend(owner[group_i + 1]))     # all draws of this grouping are done
             self._host_ms = host_ms
-            if not mine:
-                continue
             local[group_i] = self._select_for_group(group_i, len(input), probe_strs, group, plan, plan_tol,
                                                     target_genomes, target_genomes_grouped)
+        if sharded:
+            for req, _buf in pending_sends:
+                req.wait()
+            if len(input):
+                parallel.rng_broadcast(owner[-1])         # everyone ends where a single process would
         chosen_per_group = parallel.exchange_group_results(local, owner, rank) if sharded else \
             [local[i] for i in range(len(input))]
         selected = []

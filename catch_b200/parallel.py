@@ -59,6 +59,55 @@ def exchange_group_results(local, owner, rank):
     return [merged[i] for i in range(n)]
 
 
+# ---- numpy's global RNG state as a token passed along the groupings ------------------------------
+# The seed draws of grouping g continue the stream where grouping g-1 left it (the reference draws
+# them one grouping after the other in the main process, set_cover_filter.py:824-827).  Instead of
+# every rank replaying every grouping's draws, the state travels: the owner of grouping g receives
+# it from the owner of g-1, draws, and sends it on before it starts the device work.
+def _state_tensor():
+    import numpy as np
+    torch = sys.modules['torch']
+    name, key, pos, has_gauss, cached = np.random.get_state()
+    if name != 'MT19937':
+        raise RuntimeError("numpy's legacy global RNG is expected to be MT19937")
+    t = torch.empty(627, dtype=torch.int64)
+    t[:624] = torch.from_numpy(key.astype(np.int64))
+    t[624], t[625] = int(pos), int(has_gauss)
+    t[626] = int(np.array([cached], dtype=np.float64).view(np.int64)[0])
+    return t
+
+
+def _set_state_from(t):
+    import numpy as np
+    a = t.numpy()
+    cached = float(np.array([a[626]], dtype=np.int64).view(np.float64)[0])
+    np.random.set_state(('MT19937', a[:624].astype(np.uint32), int(a[624]), int(a[625]), cached))
+
+
+def rng_recv(src):
+    """Block until the RNG state arrives from rank `src` and install it."""
+    dist, torch = _dist(), sys.modules['torch']
+    t = torch.empty(627, dtype=torch.int64)
+    dist.recv(t, src=src)
+    _set_state_from(t)
+
+
+def rng_isend(dst):
+    """Send the current RNG state to rank `dst` without waiting; returns (request, tensor): keep
+    both alive and wait() on the request before the process group is torn down."""
+    t = _state_tensor()
+    return _dist().isend(t, dst=dst), t
+
+
+def rng_broadcast(src):
+    """Everyone ends with the state rank `src` holds."""
+    dist, torch = _dist(), sys.modules['torch']
+    t = _state_tensor() if dist.get_rank() == src else torch.empty(627, dtype=torch.int64)
+    dist.broadcast(t, src=src)
+    if dist.get_rank() != src:
+        _set_state_from(t)
+
+
 def active():
     """True when running under an initialised multi-rank process group."""
     dist = _dist()

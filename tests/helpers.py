@@ -127,3 +127,25 @@ def synthetic_influenza(n_genomes, seed, n_clades=10, clade_div=0.08, strain_div
         c = clades[i % n_clades]
         genomes.append([letters[diverge(seg, strain_div)].tobytes().decode() for seg in c])
     return genomes
+
+
+def synthetic_taxa(n_taxa, genomes_per_taxon, seed=4, n_clades=10, clade_div=0.08, strain_div=0.02,
+                   length_range=(10000, 30001)):
+    """SURVEY.md section 8(d) config 4 (V-All shape): independent taxa, each with its own ancestor of
+    a random length in [10 kb, 30 kb] and two-level divergence (clades, then strains) as in config 3.
+    Returns a list of groups, each a list of genome strings (one sequence per genome)."""
+    rng = np.random.default_rng(seed)
+    letters = np.frombuffer(b'ACGT', dtype=np.uint8)
+
+    def diverge(anc, div):
+        mask = rng.random(len(anc)) < div
+        shift = rng.integers(1, 4, len(anc))
+        return np.where(mask, (anc + shift) % 4, anc)
+
+    groups = []
+    for _ in range(n_taxa):
+        anc = rng.integers(0, 4, int(rng.integers(*length_range)))
+        clades = [diverge(anc, clade_div) for _ in range(n_clades)]
+        groups.append([letters[diverge(clades[i % n_clades], strain_div)].tobytes().decode()
+                       for i in range(genomes_per_taxon)])
+    return groups
