@@ -41,6 +41,15 @@ def gather_staged(ctx, slot, items):
     return addr, np.frombuffer(lens, dtype=np.int32, count=n), total
 
 
+def probe_lengths(probes):
+    """int32 lengths of the sequences of `probes` (str or objects with .seq_str), nothing copied."""
+    n = len(probes)
+    if _fastpack is not None:
+        _, lens = _fastpack.lengths(probes, 'seq_str')
+        return np.frombuffer(lens, dtype=np.int32, count=n)
+    return np.fromiter((len(p if isinstance(p, str) else p.seq_str) for p in probes), dtype=np.int32, count=n)
+
+
 def gather_probes(probes):
     """(bytes of all sequences back to back, int32 lengths) for a list of Probe objects (or str).
     One C pass over the list when the _fastpack helper is built."""

@@ -45,8 +45,9 @@ static PyObject *gather_impl(PyObject *args, int into)
 {
     PyObject *seq_in, *attr;
     unsigned long long address = 0, capacity = 0;
-    if (into ? !PyArg_ParseTuple(args, "OUKK", &seq_in, &attr, &address, &capacity)
-             : !PyArg_ParseTuple(args, "OU", &seq_in, &attr)) return NULL;
+    if (into == 1 ? !PyArg_ParseTuple(args, "OUKK", &seq_in, &attr, &address, &capacity)
+                  : !PyArg_ParseTuple(args, "OU", &seq_in, &attr)) return NULL;
+    if (into == 2) capacity = 0;                /* lengths only: behaves like gather_into with no room */
     PyObject *seq = PySequence_Fast(seq_in, "expected a sequence of probes");
     if (!seq) return NULL;
     const Py_ssize_t n = PySequence_Fast_GET_SIZE(seq);
@@ -91,7 +92,7 @@ static PyObject *gather_impl(PyObject *args, int into)
                               : PyBytes_FromStringAndSize(NULL, (Py_ssize_t)total);
         if (!data) goto fail;
         char *dst = into ? (char *)(uintptr_t)address : PyBytes_AS_STRING(data);
-        const int copy = !into || total <= (size_t)capacity;
+        const int copy = !into || (into == 1 && total <= (size_t)capacity);
         const void **srcs = NULL;
         if (copy && total >= PAR_COPY_MIN_BYTES && n >= 2 * PAR_COPY_THREADS)
             srcs = (const void **)malloc(sizeof(void *) * (size_t)n);
@@ -143,9 +144,11 @@ fail:
 
 static PyObject *gather(PyObject *self, PyObject *args) { return gather_impl(args, 0); }
 static PyObject *gather_into(PyObject *self, PyObject *args) { return gather_impl(args, 1); }
+static PyObject *lengths(PyObject *self, PyObject *args) { return gather_impl(args, 2); }
 
 static PyMethodDef methods[] = {
     {"gather", gather, METH_VARARGS, "gather(seq, attr) -> (bytes data, bytes int32 lengths)"},
+    {"lengths", lengths, METH_VARARGS, "lengths(seq, attr) -> (int total_bytes, bytes int32 lengths); nothing is copied"},
     {"gather_into", gather_into, METH_VARARGS,
      "gather_into(seq, attr, address, capacity) -> (int total_bytes, bytes int32 lengths)"},
     {NULL, NULL, 0, NULL}};

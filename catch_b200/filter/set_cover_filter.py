@@ -13,6 +13,7 @@ ordering of the output.  Everything else is in libcatchb200.so; there is no CPU 
 import logging
 import os
 import pickle
+import threading
 import time
 
 import numpy as np
@@ -64,6 +65,65 @@ class _LazyStrs:
 
     def __getitem__(self, i):
         return self._get()[i]
+
+
+class _DrawChain:
+    """Seed draws of a group-sharded run.  numpy's global RNG state is a token that travels along the
+    groupings in order: the owner of grouping g receives it from the owner of g-1, makes the draws of
+    g (first for _make_sets, then the tolerant ones for _make_ranks, set_cover_filter.py:824-827) and
+    passes it on.  That chain is inherently sequential, so it runs on its own thread, decoupled from
+    the uploads and device work of the rank's groupings: a rank that is busy on the GPU must not
+    hold up the owners of the groupings that follow.  Only this thread touches np.random while the
+    chain is running."""
+
+    def __init__(self, flt, input, owner, rank):
+        self.flt, self.owner, self.rank, self.n_groups = flt, owner, rank, len(input)
+        self.mine = [g for g in range(len(input)) if owner[g] == rank]
+        # lengths first, on the calling thread and on all ranks at once, so that a hop of the chain
+        # is nothing but the draw itself
+        self.lengths = {g: cov.probe_lengths(input[g] if isinstance(input[g], (list, tuple)) else list(input[g]))
+                        for g in self.mine}
+        self.events = {g: threading.Event() for g in self.mine}
+        self.results, self.sends, self.error = {}, [], None
+        self.thread = threading.Thread(target=self._run, name='cb-draw-chain', daemon=True)
+        self.thread.start()
+
+    def _run(self):
+        flt = self.flt
+        for g in self.mine:
+            try:
+                if g > 0 and self.owner[g - 1] != self.rank:
+                    parallel.rng_recv(self.owner[g - 1])
+                drawn = drawn_tol = None
+                lens = self.lengths[g]
+                try:
+                    if len(lens):
+                        drawn = cov.draw_seeds(lens, flt.mismatches, flt.lcf_thres, flt.kmer_probe_map_k)
+                        if flt._needs_ranks():
+                            drawn_tol = cov.draw_seeds(lens, flt.mismatches_tolerant, flt.lcf_thres_tolerant,
+                                                       flt.kmer_probe_map_k)
+                finally:
+                    # the token moves on even if this grouping's parameters are rejected, so that the
+                    # other ranks are not left waiting
+                    if g + 1 < self.n_groups and self.owner[g + 1] != self.rank:
+                        self.sends.append(parallel.rng_isend(self.owner[g + 1]))
+                self.results[g] = (drawn, drawn_tol)
+            except BaseException as e:
+                self.error = e
+            self.events[g].set()
+
+    def get(self, g):
+        self.events[g].wait()
+        if self.error is not None:
+            raise self.error
+        return self.results.pop(g)
+
+    def finish(self):
+        self.thread.join()
+        for req, _buf in self.sends:
+            req.wait()
+        if self.n_groups:
+            parallel.rng_broadcast(self.owner[-1])            # everyone ends where a single process would
 
 
 class SetCoverFilter(BaseFilter):
@@ -194,19 +254,15 @@ class SetCoverFilter(BaseFilter):
         else:
             owner = [rank] * len(input)
         local = {}
-        pending_sends = []
+        chain = _DrawChain(self, input, owner, rank) if sharded else None
         for group_i, (possible_probes, target_genomes) in enumerate(zip(input, target_genomes_grouped)):
-            # The seed draws consume numpy's global RNG per grouping, in grouping order, first for
-            # _make_sets and then for _make_ranks (set_cover_filter.py:824-827).  In a sharded run the
-            # RNG state is a token that travels along the groupings from owner to owner, so that every
-            # grouping sees the stream of a single-process run while a rank only ever touches the
-            # groupings it owns.
+            # The seed draws consume numpy's global RNG per grouping, in grouping order
+            # (set_cover_filter.py:824-827).  A sharded run gets them from the draw chain (every
+            # grouping sees the stream of a single-process run, a rank only touches the groupings it
+            # owns); a single process draws here, in the background of the upload.
             mine = owner[group_i] == rank
-            if sharded:
-                if not mine:
-                    continue
-                if group_i > 0 and owner[group_i - 1] != rank:
-                    parallel.rng_recv(owner[group_i - 1])
+            if sharded and not mine:
+                continue
             possible_probes = list(possible_probes)
             n_probes = len(possible_probes)
             probe_strs = _LazyStrs(possible_probes)
@@ -222,7 +278,9 @@ class SetCoverFilter(BaseFilter):
                 t_mark = now
             drawn = drawn_tol = None
             guess = None
-            if mine and n_probes:
+            if sharded:
+                drawn, drawn_tol = chain.get(group_i)
+            elif n_probes:
                 # The seed draw needs only the probe lengths and runs on the library's worker thread
                 # while the sequences are gathered, copied to the device and packed.  It is started
                 # on the guess that all probes are as long as the first (candidate probes are);
@@ -246,7 +304,7 @@ class SetCoverFilter(BaseFilter):
                         cov.cancel_draw(drawn)
                     raise
                 lengths = gathered[1]
-                if mine and (drawn is None or not bool(np.all(lengths == guess))):
+                if not sharded and (drawn is None or not bool(np.all(lengths == guess))):
                     if drawn is not None:
                         cov.cancel_draw(drawn)
                     drawn = cov.draw_seeds(lengths, self.mismatches, self.lcf_thres, self.kmer_probe_map_k,
@@ -261,8 +319,9 @@ class SetCoverFilter(BaseFilter):
                     dups = self._context().probes_have_duplicates(group.probes)
                     mark('duplicate_check')
                 finally:
-                    drawn = cov.finish_draw(drawn)
-                if self._needs_ranks():
+                    if not sharded:
+                        drawn = cov.finish_draw(drawn)
+                if self._needs_ranks() and not sharded:
                     drawn_tol = cov.draw_seeds(lengths, self.mismatches_tolerant, self.lcf_thres_tolerant,
                                                self.kmer_probe_map_k)
                 mark('seed_draw_wait')
@@ -275,16 +334,11 @@ class SetCoverFilter(BaseFilter):
                                             self.kmer_probe_map_k, lengths=lengths, may_have_dups=dups and mine,
                                             drawn=drawn_tol)
                 mark('seed_plan')
-            if sharded and group_i + 1 < len(input) and owner[group_i + 1] != rank:
-                pending_sends.append(parallel.rng_isend(owner[group_i + 1]))     # all draws of this grouping are done
             self._host_ms = host_ms
             local[group_i] = self._select_for_group(group_i, len(input), probe_strs, group, plan, plan_tol,
                                                     target_genomes, target_genomes_grouped)
         if sharded:
-            for req, _buf in pending_sends:
-                req.wait()
-            if len(input):
-                parallel.rng_broadcast(owner[-1])         # everyone ends where a single process would
+            chain.finish()
         chosen_per_group = parallel.exchange_group_results(local, owner, rank) if sharded else \
             [local[i] for i in range(len(input))]
         selected = []
