@@ -41,7 +41,8 @@ class Stats(C.Structure):
 EXPORTED_SYMBOLS = [
     'cb_init', 'cb_destroy', 'cb_last_error', 'cb_version', 'cb_flush_l2', 'cb_host_buffer',
     'cb_upload_targets', 'cb_targets_free', 'cb_upload_probes', 'cb_probes_free', 'cb_upload_group',
-    'cb_probes_have_duplicates', 'cb_mt19937_randint', 'cb_mt19937_randint_u8', 'cb_mt19937_randint_begin',
+    'cb_probes_have_duplicates', 'cb_mt19937_randint', 'cb_mt19937_randint_scalar', 'cb_mt19937_randint_u8',
+    'cb_mt19937_randint_begin',
     'cb_mt19937_randint_end',
     'cb_split_lengths',
     'cb_coverage', 'cb_coverage_uniform', 'cb_cover_free', 'cb_cover_num_intervals', 'cb_cover_export', 'cb_cover_import',
@@ -80,6 +81,7 @@ def load():
                                   C.POINTER(vp), C.POINTER(vp), C.POINTER(Stats)]
     L.cb_probes_free.restype = None
     L.cb_probes_have_duplicates.argtypes = [vp, vp, C.POINTER(i32)]
+    L.cb_mt19937_randint_scalar.argtypes = [vp, C.POINTER(i32), C.c_uint32, i64, vp]
     L.cb_mt19937_randint_u8.argtypes = [vp, C.POINTER(i32), C.c_uint32, i64, vp]
     L.cb_mt19937_randint_begin.argtypes = [vp, C.POINTER(i32), C.c_uint32, i64, vp, i32]
     L.cb_mt19937_randint_begin.restype = vp

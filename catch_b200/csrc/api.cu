@@ -2,7 +2,6 @@
 // the thin wrappers around the stage implementations.
 #include <algorithm>
 #include <cstring>
-#include <thread>
 
 #include "internal.cuh"
 
@@ -403,101 +402,7 @@ void cb_probes_free(cb_probes *p)
     delete p;
 }
 
-// ---- MT19937 replay (host only) -----------------------------------------------------------
-static inline void mt19937_gen(uint32_t *mt)
-{
-    const uint32_t UPPER = 0x80000000u, LOWER = 0x7fffffffu, MATRIX_A = 0x9908b0dfu;
-    int kk;
-    uint32_t y;
-    for (kk = 0; kk < 624 - 397; kk++) {
-        y = (mt[kk] & UPPER) | (mt[kk + 1] & LOWER);
-        mt[kk] = mt[kk + 397] ^ (y >> 1) ^ ((y & 1u) ? MATRIX_A : 0u);
-    }
-    for (; kk < 623; kk++) {
-        y = (mt[kk] & UPPER) | (mt[kk + 1] & LOWER);
-        mt[kk] = mt[kk + (397 - 624)] ^ (y >> 1) ^ ((y & 1u) ? MATRIX_A : 0u);
-    }
-    y = (mt[623] & UPPER) | (mt[0] & LOWER);
-    mt[623] = mt[396] ^ (y >> 1) ^ ((y & 1u) ? MATRIX_A : 0u);
-}
-
-}  // extern "C"
-
-template <typename T>
-static int mt19937_randint_t(uint32_t *key, int32_t *pos, uint32_t bound, int64_t n, T *out)
-{
-    if (!key || !pos || !out || bound == 0 || n < 0 || *pos < 0 || *pos > 624) return CB_ERR_ARG;
-    const uint32_t rng = bound - 1;            // inclusive upper value
-    if (rng == 0) {                            // numpy draws nothing when the range is a single value
-        for (int64_t i = 0; i < n; i++) out[i] = 0;
-        return CB_OK;
-    }
-    uint32_t mask = rng;
-    mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
-    int p = *pos;
-    int64_t i = 0;
-    while (i < n) {
-        if (p == 624) { mt19937_gen(key); p = 0; }
-        // rejection sampling over the rest of the current block; the accept is branch-free
-        // (write, then advance only if the value is in range)
-        int j = p;
-        for (; j < 624 && i < n; j++) {
-            uint32_t y = key[j];
-            y ^= (y >> 11);
-            y ^= (y << 7) & 0x9d2c5680u;
-            y ^= (y << 15) & 0xefc60000u;
-            y ^= (y >> 18);
-            const uint32_t val = y & mask;
-            out[i] = (T)val;
-            i += (val <= rng);
-        }
-        p = j;
-    }
-    *pos = p;
-    return CB_OK;
-}
-
-extern "C" {
-
-int cb_mt19937_randint(uint32_t *key, int32_t *pos, uint32_t bound, int64_t n, int32_t *out)
-{
-    return mt19937_randint_t<int32_t>(key, pos, bound, n, out);
-}
-
-int cb_mt19937_randint_u8(uint32_t *key, int32_t *pos, uint32_t bound, int64_t n, uint8_t *out)
-{
-    if (bound > 256) return CB_ERR_ARG;
-    return mt19937_randint_t<uint8_t>(key, pos, bound, n, out);
-}
-
-// The same replay on a native thread, so the host can pack and upload sequences meanwhile (no
-// Python thread, no GIL hand-over): begin returns at once, end joins and returns the status.
-struct cb_rng_job {
-    std::thread th;
-    int rc = CB_OK;
-};
-
-cb_rng_job *cb_mt19937_randint_begin(uint32_t *key, int32_t *pos, uint32_t bound, int64_t n, void *out,
-                                     int32_t elem_size)
-{
-    cb_rng_job *job = new cb_rng_job();
-    if (elem_size == 1)
-        job->th = std::thread([=]() { job->rc = cb_mt19937_randint_u8(key, pos, bound, n, (uint8_t *)out); });
-    else if (elem_size == 4)
-        job->th = std::thread([=]() { job->rc = cb_mt19937_randint(key, pos, bound, n, (int32_t *)out); });
-    else
-        job->rc = CB_ERR_ARG;
-    return job;
-}
-
-int cb_mt19937_randint_end(cb_rng_job *job)
-{
-    if (!job) return CB_ERR_ARG;
-    if (job->th.joinable()) job->th.join();
-    const int rc = job->rc;
-    delete job;
-    return rc;
-}
+// (the MT19937 replay, cb_mt19937_*, lives in rng.cpp: host-only code with an AVX-512 path)
 
 int cb_split_lengths(const uint8_t *buf, int64_t bytes, int64_t n, int32_t sep, int32_t *len_out)
 {

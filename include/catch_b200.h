@@ -149,6 +149,9 @@ int cb_probes_have_duplicates(cb_ctx *ctx, const cb_probes *probes, int32_t *has
  * probe.py:393-396 can be replayed without per-probe Python overhead.  key[624]/pos are the state
  * from np.random.get_state() and are updated in place. */
 int cb_mt19937_randint(uint32_t *key, int32_t *pos, uint32_t bound, int64_t n, int32_t *out);
+/* The portable (non-SIMD) loop of the same function: identical output; exported so that both code
+ * paths can be compared on one machine. */
+int cb_mt19937_randint_scalar(uint32_t *key, int32_t *pos, uint32_t bound, int64_t n, int32_t *out);
 /* Same draws stored as bytes (bound <= 256): the form cb_coverage_uniform takes. */
 int cb_mt19937_randint_u8(uint32_t *key, int32_t *pos, uint32_t bound, int64_t n, uint8_t *out);
 
