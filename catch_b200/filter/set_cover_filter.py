@@ -263,7 +263,8 @@ class SetCoverFilter(BaseFilter):
             mine = owner[group_i] == rank
             if sharded and not mine:
                 continue
-            possible_probes = list(possible_probes)
+            if not isinstance(possible_probes, (list, tuple)):
+                possible_probes = list(possible_probes)
             n_probes = len(possible_probes)
             probe_strs = _LazyStrs(possible_probes)
             group = None
@@ -343,7 +344,8 @@ class SetCoverFilter(BaseFilter):
             [local[i] for i in range(len(input))]
         selected = []
         for possible_probes, chosen in zip(input, chosen_per_group):
-            possible_probes = list(possible_probes)
+            if not isinstance(possible_probes, (list, tuple)):
+                possible_probes = list(possible_probes)
             selected.append([possible_probes[i] for i in chosen])
         return selected
 
