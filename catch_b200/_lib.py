@@ -46,7 +46,7 @@ EXPORTED_SYMBOLS = [
     'cb_mt19937_randint_end',
     'cb_split_lengths',
     'cb_coverage', 'cb_coverage_uniform', 'cb_cover_free', 'cb_cover_num_intervals', 'cb_cover_export', 'cb_cover_import',
-    'cb_setcover', 'cb_minhash_neardup', 'cb_hamming_neardup', 'cb_neardup_filter',
+    'cb_setcover', 'cb_minhash_neardup', 'cb_hamming_neardup', 'cb_neardup_filter', 'cb_group_duplicates',
     'cb_comm_unique_id', 'cb_comm_init', 'cb_comm_destroy', 'cb_cover_allgather',
 ]
 
@@ -104,6 +104,7 @@ def load():
     L.cb_minhash_neardup.argtypes = [vp, vp, vp, i64, vp, vp, i32, i32, i32, C.c_double, vp, C.POINTER(Stats)]
     L.cb_neardup_filter.argtypes = [vp, vp, vp, i64, i32, vp, vp, vp, i32, i32, i32, C.c_double, vp, C.POINTER(i64),
                                     C.POINTER(i64), C.POINTER(Stats)]
+    L.cb_group_duplicates.argtypes = [vp, vp, vp, i64, vp, vp, C.POINTER(i64), C.POINTER(Stats)]
     L.cb_hamming_neardup.argtypes = [vp, vp, vp, i64, vp, i32, i32, i32, vp, C.POINTER(Stats)]
     _lib = L
     return L
@@ -284,6 +285,17 @@ class Context:
                                              _ptr(positions), n_tables, k_concat, kmer_size, float(dist_thres),
                                              _ptr(kept), C.byref(nk), C.byref(nd), C.byref(st)))
         return kept[:nk.value].copy(), nd.value, st
+
+    def group_duplicates(self, raw, probe_off):
+        """cb_group_duplicates: (first-occurrence index, multiplicity) of every distinct sequence, in
+        order of first occurrence."""
+        n = len(probe_off) - 1
+        first = np.zeros(max(n, 1), dtype=np.int64)
+        count = np.zeros(max(n, 1), dtype=np.int32)
+        nd, st = C.c_int64(), Stats()
+        self._check(self.L.cb_group_duplicates(self.h, raw, _ptr(probe_off), n, _ptr(first), _ptr(count),
+                                               C.byref(nd), C.byref(st)))
+        return first[:nd.value], count[:nd.value], st
 
     def hamming_neardup(self, ascii_u8, probe_off, positions, n_tables, k_concat, dist_thres):
         n = len(probe_off) - 1

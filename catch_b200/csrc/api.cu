@@ -537,6 +537,17 @@ int cb_neardup_filter(cb_ctx *ctx, const uint8_t *ascii, const int64_t *probe_of
                                   kmer_size, dist_thres, kept_first_idx, n_kept, n_distinct, stats);
 }
 
+int cb_group_duplicates(cb_ctx *ctx, const uint8_t *ascii, const int64_t *probe_off, int64_t n_probes,
+                        int64_t *first_idx, int32_t *count, int64_t *n_distinct, cb_stats *stats)
+{
+    if (!ctx) return CB_ERR_ARG;
+    if (stats) memset(stats, 0, sizeof *stats);
+    ctx->launches = 0;
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cb_tls_stream = ctx->stream;
+    return cb_group_duplicates_impl(ctx, ascii, probe_off, n_probes, first_idx, count, n_distinct, stats);
+}
+
 int cb_hamming_neardup(cb_ctx *ctx, const uint8_t *ascii, const int64_t *probe_off, int64_t n_probes,
                        const int32_t *positions, int32_t n_tables, int32_t k_concat, int32_t dist_thres,
                        uint8_t *keep, cb_stats *stats)

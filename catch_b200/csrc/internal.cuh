@@ -195,6 +195,8 @@ int cb_neardup_filter_impl(cb_ctx *ctx, const uint8_t *ascii, const int64_t *pro
                            const uint32_t *pa, const uint32_t *pb, const int32_t *positions, int32_t n_tables,
                            int32_t k_concat, int32_t kmer, double dist_thres, int64_t *kept_first_idx,
                            int64_t *n_kept, int64_t *n_distinct_out, cb_stats *stats);
+int cb_group_duplicates_impl(cb_ctx *ctx, const uint8_t *ascii, const int64_t *probe_off, int64_t n,
+                             int64_t *first_idx, int32_t *count, int64_t *n_distinct, cb_stats *stats);
 int cb_hamming_neardup_impl(cb_ctx *ctx, const uint8_t *ascii, const int64_t *probe_off, int64_t n_probes,
                             const int32_t *positions, int32_t n_tables, int32_t k_concat,
                             int32_t dist_thres, uint8_t *keep, cb_stats *stats);

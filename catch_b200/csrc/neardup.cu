@@ -647,57 +647,54 @@ __global__ void gather_bytes_kernel(const uint8_t *__restrict__ src, const int64
 
 }  // namespace
 
-// Whole near-duplicate filter for one probe list WITH its duplicates, in list order: grouping of
-// identical sequences, priority order (multiplicity descending, first occurrence ascending --
-// Python's stable sorted(..., reverse=True) over a dict in insertion order), LSH filter.
-int cb_neardup_filter_impl(cb_ctx *ctx, const uint8_t *ascii, const int64_t *probe_off, int64_t n, int32_t family,
-                           const uint32_t *pa, const uint32_t *pb, const int32_t *positions, int32_t n_tables,
-                           int32_t k_concat, int32_t kmer, double dist_thres, int64_t *kept_first_idx,
-                           int64_t *n_kept, int64_t *n_distinct_out, cb_stats *stats)
+// Identical sequences of one probe list grouped on the device.  On return `first`/`mult` hold, for every
+// distinct sequence in order of first occurrence, the list index of that occurrence and the number
+// of occurrences; the bytes stay on the device for the caller.
+struct GroupResult {
+    DevBuf<uint8_t> d_ascii;
+    std::vector<int64_t> rel;              // [n+1] offsets relative to the first probe
+    std::vector<uint32_t> first, mult;     // [n_distinct]
+    bool present[256];
+    double ms = 0;
+};
+
+static int group_identical(cb_ctx *ctx, const uint8_t *ascii, const int64_t *probe_off, int64_t n, GroupResult &R)
 {
-    if (n < 0 || n_tables < 1 || k_concat < 1 || !kept_first_idx || !n_kept) return cb_fail(ctx, CB_ERR_ARG, "bad argument");
-    *n_kept = 0;
-    if (n_distinct_out) *n_distinct_out = 0;
-    if (n == 0) return CB_OK;
-    if (!ascii || !probe_off) return cb_fail(ctx, CB_ERR_ARG, "null probe table");
-    if (n >= 0xfffffff0ll) return cb_fail(ctx, CB_ERR_UNSUPPORTED, "too many probes");
-    if (family == 0 ? (!pa || !pb) : !positions) return cb_fail(ctx, CB_ERR_ARG, "null hash parameters");
     cudaStream_t st = ctx->stream;
     const int wide = ctx->sm_count * 8;
     const int64_t base = probe_off[0], total = probe_off[n] - base;
     int max_len = 0;
-    std::vector<int64_t> rel((size_t)n + 1);
-    for (int64_t i = 0; i <= n; i++) rel[(size_t)i] = probe_off[i] - base;
+    R.rel.resize((size_t)n + 1);
+    for (int64_t i = 0; i <= n; i++) R.rel[(size_t)i] = probe_off[i] - base;
     for (int64_t i = 0; i < n; i++) {
-        const int64_t len = rel[(size_t)i + 1] - rel[(size_t)i];
+        const int64_t len = R.rel[(size_t)i + 1] - R.rel[(size_t)i];
         if (len < 0 || len > ND_MAX_LEN) return cb_fail(ctx, CB_ERR_UNSUPPORTED, "probe length outside [0, 256]");
         if (len > max_len) max_len = (int)len;
     }
     EventTimer t_grp(st);
     t_grp.start();
     // ---- bytes and offsets to the device, symbol table, bit planes
-    DevBuf<uint8_t> d_ascii, d_lut;
+    DevBuf<uint8_t> d_lut;
     DevBuf<int64_t> d_off, d_pos;
     DevBuf<uint32_t> d_present, d_table, d_count, d_isrep, d_first, d_mult;
     DevBuf<uint64_t> d_words;
     DevBuf<int32_t> d_len;
-    CB_CUDA(ctx, d_ascii.alloc((size_t)total));
+    CB_CUDA(ctx, R.d_ascii.alloc((size_t)total));
     CB_CUDA(ctx, d_off.alloc((size_t)n + 1));
     CB_CUDA(ctx, d_present.alloc(256));
     CB_CUDA(ctx, cudaMemsetAsync(d_present.p, 0, sizeof(uint32_t) * 256, st));
-    if (total) CB_CUDA(ctx, cudaMemcpyAsync(d_ascii.p, ascii + base, (size_t)total, cudaMemcpyHostToDevice, st));
-    CB_CUDA(ctx, cudaMemcpyAsync(d_off.p, rel.data(), sizeof(int64_t) * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
-    CB_TRY(cb_launch_byte_presence(ctx, d_ascii.p, total, d_present.p));
+    if (total) CB_CUDA(ctx, cudaMemcpyAsync(R.d_ascii.p, ascii + base, (size_t)total, cudaMemcpyHostToDevice, st));
+    CB_CUDA(ctx, cudaMemcpyAsync(d_off.p, R.rel.data(), sizeof(int64_t) * (size_t)(n + 1), cudaMemcpyHostToDevice, st));
+    CB_TRY(cb_launch_byte_presence(ctx, R.d_ascii.p, total, d_present.p));
     uint32_t h_present[256];
     CB_CUDA(ctx, cudaMemcpyAsync(h_present, d_present.p, sizeof h_present, cudaMemcpyDeviceToHost, st));
     CB_CUDA(ctx, cudaStreamSynchronize(st));
-    bool present[256];
     uint8_t pack_lut[256];
     memset(pack_lut, 0, sizeof pack_lut);
     int n_sym = 0;
     for (int c = 0; c < 256; c++) {
-        present[c] = h_present[c] != 0;
-        if (present[c]) pack_lut[c] = (uint8_t)n_sym++;
+        R.present[c] = h_present[c] != 0;
+        if (R.present[c]) pack_lut[c] = (uint8_t)n_sym++;
     }
     int bits = 1;
     while ((1 << bits) < n_sym) bits++;
@@ -706,7 +703,7 @@ int cb_neardup_filter_impl(cb_ctx *ctx, const uint8_t *ascii, const int64_t *pro
     CB_CUDA(ctx, cudaMemcpyAsync(d_lut.p, pack_lut, 256, cudaMemcpyHostToDevice, st));
     CB_CUDA(ctx, d_words.alloc((size_t)n * (size_t)wpp));
     CB_CUDA(ctx, d_len.alloc((size_t)n));
-    CB_TRY(cb_launch_pack_probes(ctx, d_ascii.p, d_off.p, 0, n, d_lut.p, bits, nw, d_words.p, d_len.p));
+    CB_TRY(cb_launch_pack_probes(ctx, R.d_ascii.p, d_off.p, 0, n, d_lut.p, bits, nw, d_words.p, d_len.p));
     // ---- grouping
     int64_t cap = 1024;
     while (cap < 2 * n) cap <<= 1;
@@ -727,10 +724,69 @@ int cb_neardup_filter_impl(cb_ctx *ctx, const uint8_t *ascii, const int64_t *pro
     group_compact_kernel<<<wide, ND_THREADS, 0, st>>>(d_isrep.p, d_pos.p, d_count.p, n, d_first.p, d_mult.p);
     ctx->launches++;
     CB_CUDA(ctx, cudaGetLastError());
-    std::vector<uint32_t> h_first((size_t)D), h_mult((size_t)D);
-    CB_CUDA(ctx, cudaMemcpyAsync(h_first.data(), d_first.p, sizeof(uint32_t) * (size_t)D, cudaMemcpyDeviceToHost, st));
-    CB_CUDA(ctx, cudaMemcpyAsync(h_mult.data(), d_mult.p, sizeof(uint32_t) * (size_t)D, cudaMemcpyDeviceToHost, st));
+    R.first.resize((size_t)D);
+    R.mult.resize((size_t)D);
+    CB_CUDA(ctx, cudaMemcpyAsync(R.first.data(), d_first.p, sizeof(uint32_t) * (size_t)D, cudaMemcpyDeviceToHost, st));
+    CB_CUDA(ctx, cudaMemcpyAsync(R.mult.data(), d_mult.p, sizeof(uint32_t) * (size_t)D, cudaMemcpyDeviceToHost, st));
+    t_grp.stop();
     CB_CUDA(ctx, cudaStreamSynchronize(st));
+    R.ms = t_grp.ms();
+    return CB_OK;
+}
+
+// DuplicateFilter on the device (filter/duplicate_filter.py:20-26: list(OrderedDict.fromkeys(input))):
+// first occurrence of every distinct sequence, in list order, with its multiplicity.
+int cb_group_duplicates_impl(cb_ctx *ctx, const uint8_t *ascii, const int64_t *probe_off, int64_t n,
+                             int64_t *first_idx, int32_t *count, int64_t *n_distinct, cb_stats *stats)
+{
+    if (n < 0 || !n_distinct || (n > 0 && !first_idx)) return cb_fail(ctx, CB_ERR_ARG, "bad argument");
+    *n_distinct = 0;
+    if (n == 0) return CB_OK;
+    if (!ascii || !probe_off) return cb_fail(ctx, CB_ERR_ARG, "null probe table");
+    if (n >= 0xfffffff0ll) return cb_fail(ctx, CB_ERR_UNSUPPORTED, "too many probes");
+    GroupResult R;
+    CB_TRY(group_identical(ctx, ascii, probe_off, n, R));
+    const int64_t D = (int64_t)R.first.size();
+    for (int64_t i = 0; i < D; i++) {
+        first_idx[i] = (int64_t)R.first[(size_t)i];
+        if (count) count[i] = (int32_t)R.mult[(size_t)i];
+    }
+    *n_distinct = D;
+    if (stats) {
+        stats->ms_pack = R.ms;
+        stats->ms_total = R.ms;
+        stats->n_intervals = D;
+        stats->n_kernel_launches = ctx->launches;
+    }
+    return CB_OK;
+}
+
+// Whole near-duplicate filter for one probe list WITH its duplicates, in list order: grouping of
+// identical sequences, priority order (multiplicity descending, first occurrence ascending --
+// Python's stable sorted(..., reverse=True) over a dict in insertion order), LSH filter.
+int cb_neardup_filter_impl(cb_ctx *ctx, const uint8_t *ascii, const int64_t *probe_off, int64_t n, int32_t family,
+                           const uint32_t *pa, const uint32_t *pb, const int32_t *positions, int32_t n_tables,
+                           int32_t k_concat, int32_t kmer, double dist_thres, int64_t *kept_first_idx,
+                           int64_t *n_kept, int64_t *n_distinct_out, cb_stats *stats)
+{
+    if (n < 0 || n_tables < 1 || k_concat < 1 || !kept_first_idx || !n_kept) return cb_fail(ctx, CB_ERR_ARG, "bad argument");
+    *n_kept = 0;
+    if (n_distinct_out) *n_distinct_out = 0;
+    if (n == 0) return CB_OK;
+    if (!ascii || !probe_off) return cb_fail(ctx, CB_ERR_ARG, "null probe table");
+    if (n >= 0xfffffff0ll) return cb_fail(ctx, CB_ERR_UNSUPPORTED, "too many probes");
+    if (family == 0 ? (!pa || !pb) : !positions) return cb_fail(ctx, CB_ERR_ARG, "null hash parameters");
+    cudaStream_t st = ctx->stream;
+    const int wide = ctx->sm_count * 8;
+    GroupResult R;
+    CB_TRY(group_identical(ctx, ascii, probe_off, n, R));
+    const int64_t D = (int64_t)R.first.size();
+    const std::vector<uint32_t> &h_first = R.first, &h_mult = R.mult;
+    const std::vector<int64_t> &rel = R.rel;
+    const bool *present = R.present;
+    DevBuf<uint8_t> &d_ascii = R.d_ascii;
+    EventTimer t_grp(st);
+    t_grp.start();
     if (n_distinct_out) *n_distinct_out = D;
     // ---- priority order: multiplicity descending, first occurrence ascending (the distinct entries
     // arrive in first-occurrence order, so a stable counting sort by multiplicity does it)
@@ -770,7 +826,7 @@ int cb_neardup_filter_impl(cb_ctx *ctx, const uint8_t *ascii, const int64_t *pro
         if (keep[(size_t)k]) kept_first_idx[nk++] = (int64_t)ordered[(size_t)k];
     *n_kept = nk;
     if (stats) {
-        stats->ms_pack = t_grp.ms();             // upload, packing, grouping, ordering, gather
+        stats->ms_pack = R.ms + t_grp.ms();      // upload, packing, grouping; ordering, gather
         stats->ms_total += stats->ms_pack;
         stats->n_intervals = D;                  // distinct sequences
     }

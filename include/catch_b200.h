@@ -235,6 +235,14 @@ int cb_hamming_neardup(cb_ctx *ctx, const uint8_t *ascii, const int64_t *probe_o
                        const int32_t *positions, int32_t n_tables, int32_t k_concat,
                        int32_t dist_thres, uint8_t *keep, cb_stats *stats);
 
+/* DuplicateFilter._filter (filter/duplicate_filter.py:20-26, list(OrderedDict.fromkeys(input))) and
+ * the multiplicity count of NearDuplicateFilter (:61-63) on the device: identical sequences of the
+ * probe list are grouped (exact comparison of the packed bit planes).  first_idx / count
+ * (caller-allocated, capacity n_probes; count may be NULL) receive, for every distinct sequence in
+ * order of first occurrence, the list index of that occurrence and the number of occurrences. */
+int cb_group_duplicates(cb_ctx *ctx, const uint8_t *ascii, const int64_t *probe_off, int64_t n_probes,
+                        int64_t *first_idx, int32_t *count, int64_t *n_distinct, cb_stats *stats);
+
 /* The whole of NearDuplicateFilter._filter (filter/near_duplicate_filter.py:47-103) for one probe
  * list WITH its duplicates, in list order: identical sequences are grouped on the device
  * (occurrences[p] += 1, :61-63), the distinct ones are ranked by multiplicity descending and first

@@ -287,3 +287,26 @@ def test_parallel_rounds_tie_heavy_regime(ctx, monkeypatch):
         got, st = ctx.setcover(cover, len(cands), None, None)
         assert got.tolist() == want.tolist()
     cover.free()
+
+
+def test_duplicate_filter_matches_ordered_dict(ctx):
+    """DuplicateFilter on the device == list(OrderedDict.fromkeys(input)) (duplicate_filter.py:20-26):
+    first occurrences, input order, the same Probe objects; mixed lengths, N, one-symbol alphabets."""
+    from collections import OrderedDict
+    from catch_b200 import probe
+    from catch_b200.filter.duplicate_filter import DuplicateFilter
+    rng = random.Random(3)
+    f = DuplicateFilter()
+    f._ctx = ctx
+    for alphabet, n, lens in (('ACGT', 5000, (20, 21, 40)), ('ACGTN', 3000, (75,)), ('A', 50, (1, 2, 3)),
+                              ('ACGTRYKM', 2000, (100, 130, 256))):
+        pool = [''.join(rng.choice(alphabet) for _ in range(rng.choice(lens))) for _ in range(max(2, n // 4))]
+        probes = [probe.Probe.from_str(rng.choice(pool)) for _ in range(n)]
+        got = f.filter(probes)
+        want = list(OrderedDict.fromkeys(probes))
+        assert len(got) == len(want) and all(a is b for a, b in zip(got, want))
+    assert f.filter([]) == []
+    # grouped input goes through BaseFilter's per-grouping loop
+    probes = [probe.Probe.from_str(s) for s in ('ACGT', 'ACGT', 'AC', 'ACGT', 'AC', 'T')]
+    out = f.filter([probes, probes[2:]], input_is_grouped=True)
+    assert [[p.seq_str for p in g] for g in out] == [['ACGT', 'AC', 'T'], ['AC', 'ACGT', 'T']]
