@@ -208,6 +208,18 @@ def main():
         # plumbing only: barrier, max-over-ranks of the timings (NCCL), exchange of the selected
         # ids between ranks (gloo, a few KB of Python objects)
         dist.init_process_group('cpu:gloo,cuda:nccl')
+        # NCCL announces its version on stdout when the communicator is first used; the contract is ONE
+        # JSON line on stdout, so the first collective runs with fd 1 pointed at stderr
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.barrier(device_ids=[local_rank])
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     from catch_b200 import _lib, probe
     from catch_b200 import coverage as cov
