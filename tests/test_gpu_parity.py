@@ -310,3 +310,61 @@ def test_duplicate_filter_matches_ordered_dict(ctx):
     probes = [probe.Probe.from_str(s) for s in ('ACGT', 'ACGT', 'AC', 'ACGT', 'AC', 'T')]
     out = f.filter([probes, probes[2:]], input_is_grouped=True)
     assert [[p.seq_str for p in g] for g in out] == [['ACGT', 'AC', 'T'], ['AC', 'ACGT', 'T']]
+
+
+def test_baseline_config2_full_size_properties(ctx, monkeypatch):
+    """BASELINE config 2 at its full size (500 x 11 kb, -pl 75 -m 2 -l 60 -e 50; the oracle would need
+    minutes): size-independent properties of the result.  (1) the parallel-rounds kernel gives the
+    one-pick kernel's pick sequence; (2) the selection covers every universe bit that any candidate
+    covers; (3) the picks are distinct and gains at pick time never increase along the sequence;
+    (4) SetCoverFilter.filter() on host objects returns exactly those probes."""
+    from catch_b200 import coverage as cov
+    from catch_b200 import probe
+    from catch_b200.filter.set_cover_filter import SetCoverFilter
+    seqs = helpers.synthetic_genomes(500, 11000, 0.03, seed=2)
+    cands = list(dict.fromkeys(helpers.tile_candidates(seqs, 75, 50)))
+    group = cov.PackedGroup(ctx, cands, [[s] for s in seqs])
+    np.random.seed(7)
+    plan = cov.SeedPlan(cands, 2, 60, 20)
+    cover, st = cov.compute_cover(ctx, group, plan, 2, 60, 0, 50)
+    group.free()
+    picks = {}
+    for mode in ('par', 'inc'):
+        monkeypatch.setenv('CB_GREEDY', mode)
+        picks[mode], _ = ctx.setcover(cover, len(cands), None, None)
+    monkeypatch.delenv('CB_GREEDY')
+    assert picks['par'].tolist() == picks['inc'].tolist()
+    sel = picks['par']
+    assert len(set(sel.tolist())) == len(sel) > 100
+    pid, gen, s, e = ctx.cover_export(cover)
+    cover.free()
+    L = 11000
+    lo, hi = gen * L + s, gen * L + e
+
+    def covered(mask):
+        n = len(seqs) * L + 1
+        d = np.bincount(lo[mask], minlength=n) - np.bincount(hi[mask], minlength=n)
+        return np.cumsum(d)[:-1] > 0
+    chosen = np.zeros(len(cands), dtype=bool)
+    chosen[sel] = True
+    universe = covered(np.ones(len(pid), dtype=bool))
+    assert np.array_equal(universe, covered(chosen[pid]))
+    # gain of every pick at the time it is picked: new bits it adds, replayed on the host
+    done = np.zeros(len(seqs) * L, dtype=bool)
+    order = np.argsort(pid, kind='stable')
+    starts = np.searchsorted(pid[order], np.arange(len(cands) + 1))
+    prev = None
+    for p in sel.tolist():
+        gain = 0
+        for i in order[starts[p]:starts[p + 1]]:
+            seg = done[lo[i]:hi[i]]
+            gain += int(seg.size - seg.sum())
+            seg[:] = True
+        assert gain > 0 and (prev is None or gain <= prev)
+        prev = gain
+    f = SetCoverFilter(mismatches=2, lcf_thres=60, cover_extension=50)
+    f._ctx = ctx
+    np.random.seed(7)
+    out = f.filter([[probe.Probe.from_str(c) for c in cands]], helpers.to_genomes([[[x] for x in seqs]]),
+                   input_is_grouped=True)
+    assert sorted(p.seq_str for p in out[0]) == sorted(cands[i] for i in sel.tolist())
