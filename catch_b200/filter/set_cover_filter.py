@@ -438,7 +438,9 @@ class SetCoverFilter(BaseFilter):
         for i in picks.tolist():
             chosen.add(i)
         chosen = pickle.loads(pickle.dumps(chosen))
-        stats.update(seed_mode=plan.mode, k=plan.k, bits=group.bits, h2d_bytes=group.h2d_bytes,
+        seed_bytes = int(plan.uniform.nbytes) if plan.uniform is not None else \
+            int(plan.seed_pos.nbytes + plan.seed_off.nbytes)
+        stats.update(seed_mode=plan.mode, k=plan.k, bits=group.bits, h2d_bytes=group.h2d_bytes + seed_bytes,
                      d2h_bytes=int(picks.nbytes), picks=picks,
                      upload_targets=group.st_targets.as_dict(),
                      upload_probes=group.st_probes.as_dict(),
