@@ -46,7 +46,7 @@ EXPORTED_SYMBOLS = [
     'cb_mt19937_randint_end',
     'cb_split_lengths',
     'cb_coverage', 'cb_coverage_uniform', 'cb_cover_free', 'cb_cover_num_intervals', 'cb_cover_export', 'cb_cover_import',
-    'cb_setcover', 'cb_minhash_neardup', 'cb_hamming_neardup', 'cb_neardup_filter', 'cb_group_duplicates',
+    'cb_setcover', 'cb_setcover_costs', 'cb_minhash_neardup', 'cb_hamming_neardup', 'cb_neardup_filter', 'cb_group_duplicates',
     'cb_comm_unique_id', 'cb_comm_init', 'cb_comm_destroy', 'cb_cover_allgather',
 ]
 
@@ -101,6 +101,7 @@ def load():
     L.cb_comm_destroy.argtypes = [vp]
     L.cb_cover_allgather.argtypes = [vp, vp, i64, i64, C.POINTER(vp)]
     L.cb_setcover.argtypes = [vp, vp, vp, vp, vp, C.POINTER(i64), C.POINTER(Stats)]
+    L.cb_setcover_costs.argtypes = [vp, vp, vp, vp, vp, vp, C.POINTER(i64), C.POINTER(Stats)]
     L.cb_minhash_neardup.argtypes = [vp, vp, vp, i64, vp, vp, i32, i32, i32, C.c_double, vp, C.POINTER(Stats)]
     L.cb_neardup_filter.argtypes = [vp, vp, vp, i64, i32, vp, vp, vp, i32, i32, i32, C.c_double, vp, C.POINTER(i64),
                                     C.POINTER(i64), C.POINTER(Stats)]
@@ -256,11 +257,16 @@ class Context:
         return Handle(self.L.cb_cover_free, out)
 
     # ---- stage B
-    def setcover(self, cover, n_probes, ranks=None, universe_p=None):
+    def setcover(self, cover, n_probes, ranks=None, universe_p=None, costs=None):
         sel = np.zeros(max(n_probes, 1), dtype=np.int64)
         n, st = C.c_int64(), Stats()
-        self._check(self.L.cb_setcover(self.h, cover.h, _ptr(ranks), _ptr(universe_p), _ptr(sel),
-                                       C.byref(n), C.byref(st)))
+        if costs is not None:
+            costs = np.ascontiguousarray(costs, dtype=np.float64)
+            self._check(self.L.cb_setcover_costs(self.h, cover.h, _ptr(costs), _ptr(ranks), _ptr(universe_p),
+                                                 _ptr(sel), C.byref(n), C.byref(st)))
+        else:
+            self._check(self.L.cb_setcover(self.h, cover.h, _ptr(ranks), _ptr(universe_p), _ptr(sel),
+                                           C.byref(n), C.byref(st)))
         return sel[:n.value].copy(), st
 
     # ---- near-duplicate filter

@@ -507,7 +507,18 @@ int cb_setcover(cb_ctx *ctx, const cb_cover *cover, const int32_t *ranks, const 
     ctx->launches = 0;
     CB_CUDA(ctx, cudaSetDevice(ctx->device));
     cb_tls_stream = ctx->stream;
-    return cb_setcover_impl(ctx, cover, ranks, universe_p, sel_ids, n_sel, stats);
+    return cb_setcover_impl(ctx, cover, nullptr, ranks, universe_p, sel_ids, n_sel, stats);
+}
+
+int cb_setcover_costs(cb_ctx *ctx, const cb_cover *cover, const double *costs, const int32_t *ranks,
+                      const double *universe_p, int64_t *sel_ids, int64_t *n_sel, cb_stats *stats)
+{
+    if (!ctx) return CB_ERR_ARG;
+    if (stats) memset(stats, 0, sizeof *stats);
+    ctx->launches = 0;
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cb_tls_stream = ctx->stream;
+    return cb_setcover_impl(ctx, cover, costs, ranks, universe_p, sel_ids, n_sel, stats);
 }
 
 int cb_minhash_neardup(cb_ctx *ctx, const uint8_t *ascii, const int64_t *probe_off, int64_t n_probes,

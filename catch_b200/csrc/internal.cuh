@@ -184,8 +184,8 @@ int cb_cover_import_impl(cb_ctx *ctx, int64_t n_probes, int32_t n_genomes, const
                          const int64_t *start, const int64_t *end, cb_cover **out);
 
 // setcover.cu
-int cb_setcover_impl(cb_ctx *ctx, const cb_cover *cover, const int32_t *ranks, const double *universe_p,
-                     int64_t *sel_ids, int64_t *n_sel, cb_stats *stats);
+int cb_setcover_impl(cb_ctx *ctx, const cb_cover *cover, const double *costs, const int32_t *ranks,
+                     const double *universe_p, int64_t *sel_ids, int64_t *n_sel, cb_stats *stats);
 
 // neardup.cu
 int cb_minhash_neardup_impl(cb_ctx *ctx, const uint8_t *ascii, const int64_t *probe_off, int64_t n_probes,

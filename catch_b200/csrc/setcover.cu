@@ -68,6 +68,8 @@ struct GreedyParams {
     unsigned long long *ctr;       // [0] list rebuilds, [1] picks served from a list / rounds, [2] active candidates summed over rounds
     // parallel-rounds kernel
     unsigned long long *mark;      // [u_words+1] highest key among the active candidates touching the word
+    const double *costs;           // [n_probes] or nullptr (all 1): two-barrier kernel only
+    uint32_t *idmin;               // [2] smallest id among the sets at the minimum ratio (cost mode)
     uint32_t *flag;                // [list_cap] conflict flag of active candidate a in the current round
     uint32_t *hist;                // [2][64] level histograms of the list rebuilds, alternating
 };
@@ -290,12 +292,21 @@ greedy_kernel(const GreedyParams G)
             if (cnt) atomicAdd(&G.n_left[it & 1], cnt);
             grid_barrier(G.barrier, bar_target);
         }
-        // ---- K7 argmax over the current rank: max gain, smallest id
+        // ---- K7 argmax over the current rank: max gain, smallest id.  With costs (set_cover.py:426:
+        // ratio = float(cost) / gain, strict '<' over ascending ids) the key of this first pass is the
+        // ratio alone -- the bitwise complement of its order-preserving integer image, so that the
+        // LARGEST key is the smallest ratio; the smallest id at that ratio is found in a second pass.
+        auto ratio_key = [&](int64_t p, uint32_t g) -> unsigned long long {
+            const long long b = __double_as_longlong(G.costs[p] / (double)g);
+            const unsigned long long u = (unsigned long long)b ^ ((unsigned long long)(b >> 63) | 0x8000000000000000ull);
+            return ~u;
+        };
         unsigned long long best = 0;
         for (int64_t p = gtid; p < G.n_probes; p += gsize) {
             const uint32_t g = __ldcg(&G.gain[p]);
             if (g && G.rank_idx[p] == (uint32_t)cur_rank) {
-                const unsigned long long key = ((unsigned long long)g << 32) | (unsigned long long)(0xffffffffu - (uint32_t)p);
+                const unsigned long long key = G.costs ? ratio_key(p, g)
+                    : (((unsigned long long)g << 32) | (unsigned long long)(0xffffffffu - (uint32_t)p));
                 best = key > best ? key : best;
             }
         }
@@ -323,7 +334,10 @@ greedy_kernel(const GreedyParams G)
         const bool done = G.full_mode ? (__ldcg(&G.n_left[it & 1]) == 0) : (__ldcg(G.remaining) == 0ull);
         if (done) break;
         const unsigned long long key = __ldcg(&G.key[it & 1]);
-        if (gtid == 0) G.key[(it + 1) & 1] = 0ull;
+        if (gtid == 0) {
+            G.key[(it + 1) & 1] = 0ull;
+            if (G.costs) G.idmin[(it + 1) & 1] = 0xffffffffu;     // also when the rank advances below
+        }
         if (key == 0ull) {                      // nothing in this rank covers anything needed (:522-526)
             cur_rank++;
             prev = -1;
@@ -334,7 +348,18 @@ greedy_kernel(const GreedyParams G)
             grid_barrier(G.barrier, bar_target);
             continue;
         }
-        const long long w = (long long)(0xffffffffu - (uint32_t)(key & 0xffffffffull));
+        long long w = (long long)(0xffffffffu - (uint32_t)(key & 0xffffffffull));
+        if (G.costs) {
+            // second pass: smallest id among the sets whose ratio equals the minimum
+            uint32_t mine = 0xffffffffu;
+            for (int64_t p = gtid; p < G.n_probes; p += gsize) {
+                const uint32_t g = __ldcg(&G.gain[p]);
+                if (g && G.rank_idx[p] == (uint32_t)cur_rank && ratio_key(p, g) == key) { mine = (uint32_t)p; break; }
+            }
+            if (mine != 0xffffffffu) atomicMin(&G.idmin[it & 1], mine);
+            grid_barrier(G.barrier, bar_target);
+            w = (long long)__ldcg(&G.idmin[it & 1]);
+        }
         if (gtid == 0) G.sel[n_picks] = w;
         n_picks++;
         prev = w;
@@ -1216,8 +1241,8 @@ greedy_par_kernel(const GreedyParams G)
 
 }  // namespace
 
-int cb_setcover_impl(cb_ctx *ctx, const cb_cover *cover, const int32_t *ranks, const double *universe_p,
-                     int64_t *sel_ids, int64_t *n_sel, cb_stats *stats)
+int cb_setcover_impl(cb_ctx *ctx, const cb_cover *cover, const double *costs, const int32_t *ranks,
+                     const double *universe_p, int64_t *sel_ids, int64_t *n_sel, cb_stats *stats)
 {
     if (!cover || !sel_ids || !n_sel) return cb_fail(ctx, CB_ERR_ARG, "null argument");
     cudaStream_t st = ctx->stream;
@@ -1328,8 +1353,16 @@ int cb_setcover_impl(cb_ctx *ctx, const cb_cover *cover, const int32_t *ranks, c
     G.phase_ns = d_barrier.p + 1;
     // which kernel: parallel rounds (default), one pick per rendezvous ("inc"), or the two-barrier
     // kernel that recomputes clamped gains ("legacy"; the only one that handles p_u < 1)
+    // non-unit costs (never produced by SetCoverFilter, set_cover_filter.py:759, but part of
+    // approx_multiuniverse's contract): the two-barrier kernel with ratio keys
+    bool use_costs = false;
+    if (costs)
+        for (int64_t p = 0; p < P; p++) {
+            if (!(costs[p] > 0.0) || costs[p] > 1e300) return cb_fail(ctx, CB_ERR_ARG, "costs must be positive and finite");
+            if (costs[p] != 1.0) use_costs = true;
+        }
     const char *mode_env = getenv("CB_GREEDY");
-    const bool legacy = full_mode || (mode_env && !strcmp(mode_env, "legacy")) ||
+    const bool legacy = full_mode || use_costs || (mode_env && !strcmp(mode_env, "legacy")) ||
                         (getenv("CB_GREEDY_LEGACY") && getenv("CB_GREEDY_LEGACY")[0] == '1');
     const bool par = !legacy && !(mode_env && !strcmp(mode_env, "inc"));
     uint32_t list_cap = par ? 2048u : 4096u;          // par: <= PAR_LIST_CAP; 2048 leaves room for 3 CTAs per SM
@@ -1346,6 +1379,17 @@ int cb_setcover_impl(cb_ctx *ctx, const cb_cover *cover, const int32_t *ranks, c
     G.list_cap = list_cap;
     G.pub = d_pub.p;
     G.ctr = d_pub.p + 4;
+    DevBuf<double> d_costs;
+    DevBuf<uint32_t> d_idmin;
+    if (use_costs) {
+        const uint32_t init[2] = {0xffffffffu, 0xffffffffu};
+        CB_CUDA(ctx, d_costs.alloc((size_t)P));
+        CB_CUDA(ctx, d_idmin.alloc(2));
+        CB_CUDA(ctx, cudaMemcpyAsync(d_costs.p, costs, sizeof(double) * (size_t)P, cudaMemcpyHostToDevice, st));
+        CB_CUDA(ctx, cudaMemcpyAsync(d_idmin.p, init, sizeof init, cudaMemcpyHostToDevice, st));
+        G.costs = d_costs.p;
+        G.idmin = d_idmin.p;
+    }
     if (par) {
         CB_CUDA(ctx, d_mark.alloc((size_t)u_words + 1));
         CB_CUDA(ctx, cudaMemsetAsync(d_mark.p, 0, sizeof(unsigned long long) * ((size_t)u_words + 1), st));

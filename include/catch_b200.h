@@ -203,6 +203,12 @@ int cb_cover_import(cb_ctx *ctx, int64_t n_probes, int32_t n_genomes, const int6
 int cb_setcover(cb_ctx *ctx, const cb_cover *cover, const int32_t *ranks, const double *universe_p,
                 int64_t *sel_ids, int64_t *n_sel, cb_stats *stats);
 
+/* The same with per-set costs (approx_multiuniverse's `costs`, utils/set_cover.py:147,426: each pick
+ * minimises float(cost) / gain, smallest id on ties).  costs: one positive finite double per probe, or
+ * NULL (all 1).  SetCoverFilter itself only ever passes unit costs (filter/set_cover_filter.py:759). */
+int cb_setcover_costs(cb_ctx *ctx, const cb_cover *cover, const double *costs, const int32_t *ranks,
+                      const double *universe_p, int64_t *sel_ids, int64_t *n_sel, cb_stats *stats);
+
 /* ---- multi-GPU: probe sharding inside one grouping ------------------------------------------
  * One process per GPU.  Rank 0 obtains an NCCL unique id, the host distributes the 128 bytes to all
  * ranks (any side channel), every rank joins with cb_comm_init.  Each rank then runs cb_coverage

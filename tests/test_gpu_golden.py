@@ -45,13 +45,14 @@ def test_find_probe_covers_in_sequence(ctx, ref_tests):
 
 
 def test_approx_multiuniverse(ctx, ref_tests):
-    """utils/tests/test_set_cover.py instances with unit costs (the only costs SetCoverFilter
-    ever passes, filter/set_cover_filter.py:759) through cb_cover_import + cb_setcover."""
-    n = 0
+    """Every utils/tests/test_set_cover.py instance (ranks, float costs, partial cover,
+    multi-universe) through cb_cover_import + cb_setcover[_costs]."""
+    n = n_costs = 0
     for r in ref_tests['setcover']:
         quads, n_sets, n_u, costs, up, ranks, set_ids = golden_io.setcover_case_to_quads(r)
-        if costs is not None and any(c != 1 for c in costs):
-            continue
+        if costs is not None and any(not (c > 0) for c in costs):
+            continue                                 # zero / negative costs: outside the device envelope
+        n_costs += costs is not None and any(c != 1 for c in costs)
         q = np.array(quads, dtype=np.int64).reshape(-1, 4)
         glen = np.zeros(n_u, dtype=np.int64)
         for u in range(n_u):
@@ -60,11 +61,12 @@ def test_approx_multiuniverse(ctx, ref_tests):
         cover = ctx.cover_import(n_sets, glen, q[:, 0], q[:, 1], q[:, 2], q[:, 3])
         picks, _ = ctx.setcover(cover, n_sets,
                                 None if ranks is None else np.array(ranks, dtype=np.int32),
-                                None if up is None else np.array(up, dtype=np.float64))
+                                None if up is None else np.array(up, dtype=np.float64),
+                                costs=None if costs is None else np.array(costs, dtype=np.float64))
         cover.free()
         assert sorted(set_ids[p] for p in picks.tolist()) == r['out'], r
         n += 1
-    assert n >= 15
+    assert n >= 15 and n_costs >= 1
 
 
 def _run_scf(ctx, r):

@@ -368,3 +368,25 @@ def test_baseline_config2_full_size_properties(ctx, monkeypatch):
     out = f.filter([[probe.Probe.from_str(c) for c in cands]], helpers.to_genomes([[[x] for x in seqs]]),
                    input_is_grouped=True)
     assert sorted(p.seq_str for p in out[0]) == sorted(cands[i] for i in sel.tolist())
+
+
+def test_setcover_with_costs_matches_oracle(ctx):
+    """approx_multiuniverse with per-set float costs (utils/set_cover.py:426: min cost/gain, smallest id
+    on ties), with and without ranks and partial cover: pick SEQUENCE against the oracle."""
+    O = _oracle()
+    rng = random.Random(41)
+    for case in (1, 2, 5, 7):
+        groups, cands, params = helpers.random_case(case)
+        probe_strs, genomes = cands[0], groups[0]
+        if not probe_strs:
+            continue
+        np.random.seed(3)
+        got, cover, _ = _device_quads(ctx, probe_strs, genomes, params)
+        for trial in range(4):
+            costs = np.array([rng.choice([1.0, 1.0, 0.5, 2.0, 3.25, 0.1]) for _ in probe_strs])
+            ranks = None if trial % 2 == 0 else np.array([rng.choice([0, 0, 3]) for _ in probe_strs], dtype=np.int32)
+            up = None if trial < 2 else np.array([rng.choice([1.0, 0.7, 0.3]) for _ in genomes])
+            want = O.set_cover_quads(got, len(probe_strs), len(genomes), costs, up, ranks)
+            picks, _ = ctx.setcover(cover, len(probe_strs), ranks, up, costs=costs)
+            assert picks.tolist() == want
+        cover.free()
