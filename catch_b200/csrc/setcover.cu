@@ -1358,7 +1358,7 @@ int cb_setcover_impl(cb_ctx *ctx, const cb_cover *cover, const double *costs, co
     bool use_costs = false;
     if (costs)
         for (int64_t p = 0; p < P; p++) {
-            if (!(costs[p] > 0.0) || costs[p] > 1e300) return cb_fail(ctx, CB_ERR_ARG, "costs must be positive and finite");
+            if (!(costs[p] >= 0.0) || costs[p] > 1e300) return cb_fail(ctx, CB_ERR_ARG, "costs must be nonnegative and finite");
             if (costs[p] != 1.0) use_costs = true;
         }
     const char *mode_env = getenv("CB_GREEDY");

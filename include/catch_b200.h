@@ -204,7 +204,7 @@ int cb_setcover(cb_ctx *ctx, const cb_cover *cover, const int32_t *ranks, const 
                 int64_t *sel_ids, int64_t *n_sel, cb_stats *stats);
 
 /* The same with per-set costs (approx_multiuniverse's `costs`, utils/set_cover.py:147,426: each pick
- * minimises float(cost) / gain, smallest id on ties).  costs: one positive finite double per probe, or
+ * minimises float(cost) / gain, smallest id on ties).  costs: one nonnegative finite double per probe, or
  * NULL (all 1).  SetCoverFilter itself only ever passes unit costs (filter/set_cover_filter.py:759). */
 int cb_setcover_costs(cb_ctx *ctx, const cb_cover *cover, const double *costs, const int32_t *ranks,
                       const double *universe_p, int64_t *sel_ids, int64_t *n_sel, cb_stats *stats);

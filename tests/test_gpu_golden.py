@@ -183,3 +183,45 @@ def test_near_duplicate_filter_vs_oracle_larger(ctx):
         want = (O.near_duplicate_minhash(probes, d) if kind == 'minhash'
                 else O.near_duplicate_hamming(probes, d, L))
         assert sorted(got) == sorted(want)
+
+
+class _IvSet:
+    """Stand-in for catch.utils.interval.IntervalSet: the drop-in only reads `.intervals`."""
+
+    def __init__(self, intervals):
+        self.intervals = [tuple(i) for i in intervals]
+
+
+def test_set_cover_module_drop_in(ctx, ref_tests):
+    """catch_b200.utils.set_cover.approx_multiuniverse / approx called the way the reference's callers
+    and tests call them (dict in, Python set of ids out), in all three element representations
+    (interval sets, plain sets, arrays: utils/tests/test_set_cover.py:545-556 checks they agree)."""
+    import array
+    from catch_b200.utils import set_cover as sc
+    n = 0
+    for r in ref_tests['setcover'][::2]:
+        costs = None if r['costs'] is None else {int(k): v for k, v in r['costs'].items()}
+        ranks = None if r['ranks'] is None else {int(k): v for k, v in r['ranks'].items()}
+        up = None if r['universe_p'] is None else {int(k): v for k, v in r['universe_p'].items()}
+        if sum(len(iv) for by_u in r['sets'].values() for iv in by_u.values()) > 3000:
+            continue                                        # keep the pure-Python conversions short
+        iv_sets = {int(s): {int(u): (tuple(iv[0]) if len(iv) == 1 else _IvSet(iv)) for u, iv in by_u.items()}
+                   for s, by_u in r['sets'].items()}
+        assert sc.approx_multiuniverse(iv_sets, costs, up, ranks, use_intervalsets=True, ctx=ctx) == set(r['out'])
+        plain = {int(s): {int(u): set(x for a, b in iv for x in range(a, b)) for u, iv in by_u.items()}
+                 for s, by_u in r['sets'].items()}
+        assert sc.approx_multiuniverse(plain, costs, up, ranks, ctx=ctx) == set(r['out'])
+        arrays = {s: {u: array.array('q', sorted(v)) for u, v in by_u.items()} for s, by_u in plain.items()}
+        assert sc.approx_multiuniverse(arrays, costs, up, ranks, use_arrays=True, ctx=ctx) == set(r['out'])
+        n += 1
+    assert n >= 10
+    # single-universe form and the validation errors of the reference
+    sets = {0: {1, 2, 3, 4}, 1: {3, 4, 5}, 2: {5, 6}, 3: {1}}
+    assert sc.approx(sets, ctx=ctx) == {0, 2}
+    assert sc.approx(sets, costs={0: 10.0, 1: 1.0, 2: 1.0, 3: 1.0}, p=0.5, ctx=ctx) == {1}
+    with pytest.raises(ValueError):
+        sc.approx(sets, p=1.5, ctx=ctx)
+    with pytest.raises(ValueError):
+        sc.approx_multiuniverse({0: {0: {1}}}, costs={0: -1.0}, ctx=ctx)
+    with pytest.raises(ValueError):
+        sc.approx_multiuniverse({0: {0: {1}}}, use_arrays=True, use_intervalsets=True, ctx=ctx)
