@@ -226,3 +226,29 @@ def test_mt19937_simd_and_scalar_paths_agree_with_numpy():
             out8 = np.full(n + 32, 7, dtype=np.uint8)
             assert L.cb_mt19937_randint_u8(key.ctypes.data, C.byref(pos), bound, n, out8.ctypes.data) == 0
             assert np.array_equal(out8[:n], want.astype(np.uint8))
+
+
+def test_set_cover_drop_in_validates_like_the_reference():
+    """The argument checks of approx_multiuniverse / approx (utils/set_cover.py:270-340, :88-95) come
+    before any device work, so they can be exercised without a GPU."""
+    from catch_b200.utils import set_cover as sc
+    sets = {0: {0: {1, 2}}, 1: {0: {2, 3}}}
+    with pytest.raises(ValueError, match="both arrays and IntervalSets"):
+        sc.approx_multiuniverse(sets, use_arrays=True, use_intervalsets=True)
+    with pytest.raises(ValueError, match="nonnegative"):
+        sc.approx_multiuniverse(sets, costs={0: 1.0, 1: -2.0})
+    with pytest.raises(ValueError, match="costs is missing"):
+        sc.approx_multiuniverse(sets, costs={0: 1.0})
+    with pytest.raises(ValueError, match="coverage fraction"):
+        sc.approx_multiuniverse(sets, universe_p={0: 1.5})
+    with pytest.raises(ValueError, match="universe_p is missing"):
+        sc.approx_multiuniverse(sets, universe_p={7: 0.5})
+    with pytest.raises(ValueError, match="ranks is missing"):
+        sc.approx_multiuniverse(sets, ranks={0: 1})
+    with pytest.raises(ValueError, match=r"p must be in \[0,1\]"):
+        sc.approx({0: {1}}, p=-0.1)
+    assert sc.approx_multiuniverse({}) == set()
+    # elements -> intervals: runs of consecutive indices of the universe's element numbering
+    index_of = {v: i for i, v in enumerate(['a', 'b', 'c', 'd', 'e'])}
+    assert sc._as_intervals({'a', 'b', 'd'}, False, index_of) == [(0, 2), (3, 4)]
+    assert sc._as_intervals((5, 9), True, None) == [(5, 9)]
