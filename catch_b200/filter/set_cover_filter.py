@@ -255,92 +255,26 @@ class SetCoverFilter(BaseFilter):
             owner = [rank] * len(input)
         local = {}
         chain = _DrawChain(self, input, owner, rank) if sharded else None
+        failure = None
         for group_i, (possible_probes, target_genomes) in enumerate(zip(input, target_genomes_grouped)):
             # The seed draws consume numpy's global RNG per grouping, in grouping order
             # (set_cover_filter.py:824-827).  A sharded run gets them from the draw chain (every
             # grouping sees the stream of a single-process run, a rank only touches the groupings it
-            # owns); a single process draws here, in the background of the upload.
-            mine = owner[group_i] == rank
-            if sharded and not mine:
+            # owns); a single process draws in _filter_one_group, in the background of the upload.
+            if sharded and owner[group_i] != rank:
                 continue
-            if not isinstance(possible_probes, (list, tuple)):
-                possible_probes = list(possible_probes)
-            n_probes = len(possible_probes)
-            probe_strs = _LazyStrs(possible_probes)
-            group = None
-            lengths, dups = None, True
-            host_ms = {}
-            t_mark = time.perf_counter()
-
-            def mark(name):
-                nonlocal t_mark
-                now = time.perf_counter()
-                host_ms[name] = host_ms.get(name, 0.0) + (now - t_mark) * 1e3
-                t_mark = now
-            drawn = drawn_tol = None
-            guess = None
-            if sharded:
-                drawn, drawn_tol = chain.get(group_i)
-            elif n_probes:
-                # The seed draw needs only the probe lengths and runs on the library's worker thread
-                # while the sequences are gathered, copied to the device and packed.  It is started
-                # on the guess that all probes are as long as the first (candidate probes are);
-                # if the gathered lengths say otherwise the guess is dropped -- a background draw
-                # only touches numpy's RNG state when it is accepted -- and the draw is redone.
-                guess = len(possible_probes[0].seq_str)
-                try:
-                    drawn = cov.draw_seeds(np.full(n_probes, guess, dtype=np.int32), self.mismatches,
-                                           self.lcf_thres, self.kmer_probe_map_k, background=True)
-                except ValueError:          # e.g. k longer than the first probe: decided on the real lengths
-                    drawn = None
-            if n_probes:
-                # sequences of the whole list in one buffer (straight into page-locked staging memory
-                # when this rank is going to upload them)
-                try:
-                    gathered = cov.gather_staged(self._context(), 0, possible_probes) if mine else None
-                    if gathered is None:
-                        gathered = cov.gather_probes(possible_probes)
-                except BaseException:
-                    if drawn is not None:
-                        cov.cancel_draw(drawn)
+            if failure is not None:
+                continue                     # keep taking part in the collectives below, then raise
+            try:
+                local[group_i] = self._filter_one_group(group_i, len(input), possible_probes, target_genomes,
+                                                        target_genomes_grouped, chain)
+            except Exception as e:
+                if not sharded:
                     raise
-                lengths = gathered[1]
-                if not sharded and (drawn is None or not bool(np.all(lengths == guess))):
-                    if drawn is not None:
-                        cov.cancel_draw(drawn)
-                    drawn = cov.draw_seeds(lengths, self.mismatches, self.lcf_thres, self.kmer_probe_map_k,
-                                           background=True)
-                mark('gather')
-            if mine and n_probes:
-                # The tolerant draw (ranks) continues the same stream, so it follows once the first
-                # has finished.
-                try:
-                    group = cov.PackedGroup(self._context(), possible_probes, target_genomes, gathered=gathered)
-                    mark('pack_and_upload')
-                    dups = self._context().probes_have_duplicates(group.probes)
-                    mark('duplicate_check')
-                finally:
-                    if not sharded:
-                        drawn = cov.finish_draw(drawn)
-                if self._needs_ranks() and not sharded:
-                    drawn_tol = cov.draw_seeds(lengths, self.mismatches_tolerant, self.lcf_thres_tolerant,
-                                               self.kmer_probe_map_k)
-                mark('seed_draw_wait')
-            plan = plan_tol = None
-            if n_probes:
-                plan = cov.SeedPlan(probe_strs, self.mismatches, self.lcf_thres, self.kmer_probe_map_k,
-                                    lengths=lengths, may_have_dups=dups and mine, drawn=drawn)
-                if self._needs_ranks():
-                    plan_tol = cov.SeedPlan(probe_strs, self.mismatches_tolerant, self.lcf_thres_tolerant,
-                                            self.kmer_probe_map_k, lengths=lengths, may_have_dups=dups and mine,
-                                            drawn=drawn_tol)
-                mark('seed_plan')
-            self._host_ms = host_ms
-            local[group_i] = self._select_for_group(group_i, len(input), probe_strs, group, plan, plan_tol,
-                                                    target_genomes, target_genomes_grouped)
+                failure = e
         if sharded:
             chain.finish()
-        chosen_per_group = parallel.exchange_group_results(local, owner, rank) if sharded else \
+        chosen_per_group = parallel.exchange_group_results(local, owner, rank, failure) if sharded else \
             [local[i] for i in range(len(input))]
         selected = []
         for possible_probes, chosen in zip(input, chosen_per_group):
@@ -348,6 +282,87 @@ class SetCoverFilter(BaseFilter):
                 possible_probes = list(possible_probes)
             selected.append([possible_probes[i] for i in chosen])
         return selected
+
+    def _filter_one_group(self, group_i, n_groups, possible_probes, target_genomes, target_genomes_grouped, chain):
+        """One grouping this process owns: gather, upload, seed plan, both stages.  `chain` is the draw
+        chain of a group-sharded run (None in a single process, which draws here in the background of
+        the upload).  Returns the indices of the selected probes in the reference's output order."""
+        sharded = chain is not None
+        if not isinstance(possible_probes, (list, tuple)):
+            possible_probes = list(possible_probes)
+        n_probes = len(possible_probes)
+        probe_strs = _LazyStrs(possible_probes)
+        group = None
+        lengths, dups = None, True
+        host_ms = {}
+        t_mark = time.perf_counter()
+
+        def mark(name):
+            nonlocal t_mark
+            now = time.perf_counter()
+            host_ms[name] = host_ms.get(name, 0.0) + (now - t_mark) * 1e3
+            t_mark = now
+        drawn = drawn_tol = None
+        guess = None
+        if sharded:
+            drawn, drawn_tol = chain.get(group_i)
+        elif n_probes:
+            # The seed draw needs only the probe lengths and runs on the library's worker thread
+            # while the sequences are gathered, copied to the device and packed.  It is started
+            # on the guess that all probes are as long as the first (candidate probes are);
+            # if the gathered lengths say otherwise the guess is dropped -- a background draw
+            # only touches numpy's RNG state when it is accepted -- and the draw is redone.
+            guess = len(possible_probes[0].seq_str)
+            try:
+                drawn = cov.draw_seeds(np.full(n_probes, guess, dtype=np.int32), self.mismatches,
+                                       self.lcf_thres, self.kmer_probe_map_k, background=True)
+            except ValueError:          # e.g. k longer than the first probe: decided on the real lengths
+                drawn = None
+        if n_probes:
+            # sequences of the whole list in one buffer (straight into page-locked staging memory
+            # when this rank is going to upload them)
+            try:
+                gathered = cov.gather_staged(self._context(), 0, possible_probes)
+                if gathered is None:
+                    gathered = cov.gather_probes(possible_probes)
+            except BaseException:
+                if drawn is not None:
+                    cov.cancel_draw(drawn)
+                raise
+            lengths = gathered[1]
+            if not sharded and (drawn is None or not bool(np.all(lengths == guess))):
+                if drawn is not None:
+                    cov.cancel_draw(drawn)
+                drawn = cov.draw_seeds(lengths, self.mismatches, self.lcf_thres, self.kmer_probe_map_k,
+                                       background=True)
+            mark('gather')
+        if n_probes:
+            # The tolerant draw (ranks) continues the same stream, so it follows once the first
+            # has finished.
+            try:
+                group = cov.PackedGroup(self._context(), possible_probes, target_genomes, gathered=gathered)
+                mark('pack_and_upload')
+                dups = self._context().probes_have_duplicates(group.probes)
+                mark('duplicate_check')
+            finally:
+                if not sharded:
+                    drawn = cov.finish_draw(drawn)
+            if self._needs_ranks() and not sharded:
+                drawn_tol = cov.draw_seeds(lengths, self.mismatches_tolerant, self.lcf_thres_tolerant,
+                                           self.kmer_probe_map_k)
+            mark('seed_draw_wait')
+        plan = plan_tol = None
+        if n_probes:
+            plan = cov.SeedPlan(probe_strs, self.mismatches, self.lcf_thres, self.kmer_probe_map_k,
+                                lengths=lengths, may_have_dups=dups, drawn=drawn)
+            if self._needs_ranks():
+                plan_tol = cov.SeedPlan(probe_strs, self.mismatches_tolerant, self.lcf_thres_tolerant,
+                                        self.kmer_probe_map_k, lengths=lengths, may_have_dups=dups,
+                                        drawn=drawn_tol)
+            mark('seed_plan')
+        self._host_ms = host_ms
+        return self._select_for_group(group_i, n_groups, probe_strs, group, plan, plan_tol,
+                                      target_genomes, target_genomes_grouped)
 
     def _shard_probes(self, n_groups, world_size):
         mode = os.environ.get('CB_SHARD', 'auto')

@@ -41,17 +41,25 @@ def _dist():
     return dist if dist.is_available() and dist.is_initialized() else None
 
 
-def exchange_group_results(local, owner, rank):
+def exchange_group_results(local, owner, rank, failure=None):
     """local: {group index: result} for the groupings this rank owns.  Returns the list of all
-    results in grouping order on every rank."""
+    results in grouping order on every rank.  `failure`: the exception that stopped this rank, if any;
+    it is exchanged with the results so that EVERY rank raises instead of some of them waiting for
+    ever in a collective."""
     n = len(owner)
     dist = _dist()
     if dist is None or dist.get_world_size() == 1:
+        if failure is not None:
+            raise failure
         return [local[i] for i in range(n)]
     gathered = [None] * dist.get_world_size()
-    dist.all_gather_object(gathered, local)
+    dist.all_gather_object(gathered, (local, None if failure is None else repr(failure)))
+    if failure is not None:
+        raise failure
     merged = {}
-    for part in gathered:
+    for r, (part, err) in enumerate(gathered):
+        if err is not None:
+            raise RuntimeError("rank %d failed: %s" % (r, err))
         merged.update(part)
     missing = [i for i in range(n) if i not in merged]
     if missing:

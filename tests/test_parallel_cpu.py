@@ -22,7 +22,7 @@ def test_assign_groups_is_deterministic_and_balanced():
     assert parallel.assign_groups([], 4) == []
 
 
-def _worker(rank, world_size, port, out_path):
+def _worker(rank, world_size, port, out_path, fail_group=None):
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world_size), LOCAL_RANK=str(rank),
                       MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     sys.path.insert(0, ROOT)
@@ -35,6 +35,8 @@ def _worker(rank, world_size, port, out_path):
     computed = []
 
     def fake_select(self, group_i, n_groups, probe_strs, group, plan, plan_tol, target_genomes, all_genomes):
+        if group_i == fail_group:
+            raise ValueError("grouping %d cannot be designed" % group_i)
         computed.append(group_i)
         # deterministic stand-in for the device result: depends on the drawn seeds
         return [int(x) % max(1, len(probe_strs)) for x in plan.seed_pos[:3]]
@@ -64,6 +66,16 @@ def _worker(rank, world_size, port, out_path):
     probes = [[probe.Probe.from_str(s) for s in c] for c in cands]
     f = SetCoverFilter(mismatches=1, lcf_thres=20)          # random seed mode: consumes np.random
     np.random.seed(3)
+    if fail_group is not None:
+        try:
+            f.filter(probes, helpers.to_genomes(groups), input_is_grouped=True)
+            outcome = 'no exception'
+        except Exception as e:
+            outcome = type(e).__name__ + ': ' + str(e)
+        with open(out_path, 'w') as fh:
+            fh.write(outcome)
+        dist.destroy_process_group()
+        return
     out = f.filter(probes, helpers.to_genomes(groups), input_is_grouped=True)
     after = int(np.random.randint(0, 1 << 30))
     np.save(out_path, np.array([computed, [[p.seq_str for p in g] for g in out], after], dtype=object),
@@ -107,3 +119,21 @@ def test_group_sharding_over_gloo(tmp_path, world_size):
         assert p.exitcode == 0
         single = np.load(str(ref_path), allow_pickle=True)
         assert single[1] == res[0][1] and single[2] == res[0][2]
+
+
+def test_failure_on_one_rank_raises_on_every_rank(tmp_path):
+    """A grouping that fails on its owner must not leave the other ranks waiting in a collective:
+    the failure travels with the results and every rank raises."""
+    import multiprocessing as mp
+    ctxm = mp.get_context('spawn')
+    port = _free_port()
+    paths = [str(tmp_path / ('f%d.txt' % r)) for r in range(2)]
+    procs = [ctxm.Process(target=_worker, args=(r, 2, port, paths[r], 2)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    outcomes = [open(p).read() for p in paths]
+    assert sum(o.startswith('ValueError: grouping 2') for o in outcomes) == 1
+    assert sum(o.startswith('RuntimeError: rank') for o in outcomes) == 1
