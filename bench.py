@@ -233,7 +233,13 @@ def main():
     probes = [[probe.Probe.from_str(s) for s in c] for c in w['groups_cands']]
     scf = SetCoverFilter(**w['scf'])
     scf._ctx = ctx
-    my_group = rank if (world > 1 and not strong) else 0     # equal-size groupings: assign_groups gives g -> rank g
+    # group-sharded run: the grouping this rank owns, by the same assignment SetCoverFilter._filter makes (the
+    # deduplicated candidate counts differ per generator seed, so it is a permutation, not g -> rank g)
+    my_group = 0
+    if world > 1 and not strong:
+        from catch_b200 import parallel as _par
+        sizes = [len(p) * max(1, sum(g.size() for g in tg)) for p, tg in zip(probes, genomes)]
+        my_group = _par.assign_groups(sizes, world).index(rank)
 
     def barrier():
         if dist is not None:

@@ -18,15 +18,18 @@
 //      (cp.async.bulk + mbarrier);
 //   2. one seed-index lookup per target position gives a bucket of candidate (probe, seed) hits;
 //      a block-wide prefix sum spreads the hits evenly over the threads;
-//   3. per hit: mismatch mask M of the whole alignment = OR over planes of (probe XOR window);
-//      the set of selected seeds of that probe that match exactly and in bounds on this diagonal
-//      is A = runs_of_k_zeros(M) & seed_mask(probe), computed with log2(k) shift-AND steps.
-//      The hit that came through the LOWEST bit of A owns the diagonal; all others stop here;
-//   4. owners are compacted into a shared-memory queue and processed densely (no divergence
-//      between owners and non-owners): for every seed of A that starts a new mismatch-free run
-//      (seeds in one run give identical ranges) the anchored extension is evaluated with
-//      ffs/clz on the mask, and the resulting range is appended, warp-aggregated, to a global
-//      list that is later bucketed by probe.
+//   3. per hit, a CHEAP test decides whether the hit has to be evaluated at all.  Seeds inside one
+//      mismatch-free run of a diagonal see the same mismatches on both sides and therefore give the
+//      same range, so one seed per run is enough.  Every index entry carries the distance g to the
+//      probe's nearest lower selected seed and the g probe bases in between; if those bases also
+//      match the target (and the lower seed starts inside the sequence), the lower seed matches on
+//      this diagonal, lies in the same run and yields the same range: the hit is dropped after one
+//      16-byte entry load and a masked compare against the staged tile -- the probe record is never
+//      touched.  What survives is exactly one hit per (probe, diagonal, run that holds a seed);
+//   4. survivors are compacted into a shared-memory queue and processed densely: mismatch mask
+//      M = OR over planes of (probe XOR window), one anchored extension around the hit's own seed
+//      (ffs/clz walks over at most 2(m+1) mismatches), threshold/island tests, +-e, clip, universe
+//      offset, and a warp-aggregated append to a global range list that is later bucketed by probe.
 #include <cstdlib>
 #include <cstring>
 
@@ -40,10 +43,7 @@ constexpr int SCAN_THREADS = 256;
 #endif
 constexpr int POS_PER_THREAD = CB_TILE / SCAN_THREADS;
 constexpr int TW = CB_TILE_WORDS;
-constexpr int HITS_PER_THREAD = 4;
-constexpr int QUEUE_CAP = 1536;           // 12 KB: keeps the CTA under 32 KB so four fit beside a large L1
-constexpr int QUEUE_FLUSH = QUEUE_CAP - SCAN_THREADS * HITS_PER_THREAD;
-constexpr int MAX_LOCAL_REC = 4;
+constexpr int QUEUE_FLUSH = 512;          // the survivor queue is drained once it holds more than this
 
 struct ScanParams {
     // targets
@@ -60,7 +60,8 @@ struct ScanParams {
     const int32_t *plen;
     // seed index
     const int64_t *bucket_off;
-    const uint64_t *entries;
+    const ulonglong2 *entries;     // x: probe << 32 | pos << 24 | tag24; y: g | prefix fields (see seed_index_kernel)
+    int pw;                        // bases per prefix field = 56 / bits
     uint32_t bucket_mask;
     // hybridisation model
     int m, lcf, island, ext, k;
@@ -135,47 +136,6 @@ __device__ __forceinline__ bool test_bit(const uint64_t (&M)[NW], int b)
     for (int w = 0; w < NW; w++)
         if ((b >> 6) == w) v = M[w];
     return (v >> (b & 63)) & 1ull;
-}
-
-// R = X >> n over NW words (bit j of R = bit j+n of X), 0 <= n < 64*NW
-template <int NW>
-__device__ __forceinline__ void shr_multi(const uint64_t (&X)[NW], int n, uint64_t (&R)[NW])
-{
-    const int ws = n >> 6, bs = n & 63;
-#pragma unroll
-    for (int w = 0; w < NW; w++) {
-        uint64_t lo = 0, hi = 0;
-#pragma unroll
-        for (int v = 0; v < NW; v++) {
-            if (v == w + ws) lo = X[v];
-            if (v == w + ws + 1) hi = X[v];
-        }
-        R[w] = bs ? ((lo >> bs) | (hi << (64 - bs))) : lo;
-    }
-}
-
-// C[s] = 1 iff Z[s .. s+k) are all ones (runs of k ones), by doubling: log2(k) shift-AND steps
-template <int NW>
-__device__ __forceinline__ void runs_of_k(const uint64_t (&Z)[NW], int k, uint64_t (&C)[NW])
-{
-    uint64_t D[NW], T[NW];
-#pragma unroll
-    for (int w = 0; w < NW; w++) { D[w] = Z[w]; C[w] = ~0ull; }
-    int off = 0;
-    for (int len = 1; len <= k; len <<= 1) {
-        // D = runs of `len` ones
-        if (k & len) {
-            shr_multi<NW>(D, off, T);
-#pragma unroll
-            for (int w = 0; w < NW; w++) C[w] &= T[w];
-            off += len;
-        }
-        if ((len << 1) <= k) {
-            shr_multi<NW>(D, len, T);
-#pragma unroll
-            for (int w = 0; w < NW; w++) D[w] &= T[w];
-        }
-    }
 }
 
 __device__ __forceinline__ uint64_t mix64(uint64_t h, uint64_t v)
@@ -288,27 +248,57 @@ __global__ void seed_expand_kernel(const uint64_t *__restrict__ precs, int prec_
     }
 }
 
+// Entry layout (16 bytes):
+//   x = probe << 32 | pos << 24 | tag24 (bits 40.. of the k-mer hash)
+//   y = g | field_0 << 8 | field_1 << (8 + pw) | ...   with pw = 56 / bits bases per field:
+//       g = distance from this seed down to the probe's nearest lower selected seed (0 when there is
+//       none within min(pw, k) bases), field_b = bits [pos - g, pos) of probe plane b.  The scan uses it
+//       to drop hits whose lower neighbour seed matches on the same diagonal (see scan_kernel).
 template <bool SCATTER>
 __global__ void seed_index_kernel(const uint32_t *__restrict__ entry_probe,
                                   const uint8_t *__restrict__ seed_pos, int64_t n_entries,
                                   const uint64_t *__restrict__ precs, int prec_words, int bits, int nw, int k,
                                   uint32_t bucket_mask, uint32_t *__restrict__ bucket_count,
                                   const int64_t *__restrict__ bucket_off, uint32_t *__restrict__ cursor,
-                                  uint64_t *__restrict__ entries)
+                                  ulonglong2 *__restrict__ entries)
 {
+    const int pw = 56 / bits;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_entries;
          e += (int64_t)gridDim.x * blockDim.x) {
         const uint32_t p = entry_probe[e];
         const int pos = seed_pos[e];
-        const uint64_t *pw = precs + (int64_t)p * prec_words;
-        const uint64_t h = kmer_hash(bits, k, [&](int b, int o) { return read64_bounded(pw + b * nw, nw, pos + o); });
+        const uint64_t *pwd = precs + (int64_t)p * prec_words;
+        const uint64_t h = kmer_hash(bits, k, [&](int b, int o) { return read64_bounded(pwd + b * nw, nw, pos + o); });
         const uint32_t bucket = (uint32_t)h & bucket_mask;
         if (!SCATTER) {
             atomicAdd(&bucket_count[bucket], 1u);
         } else {
+            // nearest selected seed below pos (seed mask = last nw words of the record)
+            const uint64_t *sm = pwd + bits * nw;
+            int prev = -1;
+            {
+                int w = pos >> 6;
+                uint64_t m = sm[w] & ((1ull << (pos & 63)) - 1ull);
+                for (;;) {
+                    if (m) { prev = w * 64 + 63 - __clzll((long long)m); break; }
+                    if (--w < 0) break;
+                    m = sm[w];
+                }
+            }
+            uint64_t y = 0ull;
+            if (prev >= 0) {
+                const int g = pos - prev;
+                if (g <= pw && g <= k) {
+                    y = (uint64_t)g;
+                    for (int b = 0; b < bits; b++)
+                        y |= (read64_bounded(pwd + b * nw, nw, prev) & ((1ull << g) - 1ull)) << (8 + b * pw);
+                }
+            }
             const uint32_t slot = atomicAdd(&cursor[bucket], 1u);
-            entries[bucket_off[bucket] + slot] =
-                ((uint64_t)p << 32) | ((uint64_t)pos << 24) | (uint64_t)(h >> 40);
+            ulonglong2 ent;
+            ent.x = ((uint64_t)p << 32) | ((uint64_t)pos << 24) | (uint64_t)(h >> 40);
+            ent.y = y;
+            entries[bucket_off[bucket] + slot] = ent;
         }
     }
 }
@@ -413,12 +403,10 @@ __device__ __forceinline__ int anchored_extend(const uint64_t (&M)[NW], int a, i
     return best_len;
 }
 
-// Mismatch mask of probe p aligned at target coordinate d, clipped to the sequence [qs, qe),
-// and the mask A of its selected seeds that match exactly and in bounds on this diagonal.
+// Mismatch mask of probe p aligned at target coordinate d (not yet clipped to the sequence).
 template <int NW>
-__device__ __forceinline__ void align_probe(const ScanParams &P, const uint64_t *s_tile, int64_t t0, int64_t d,
-                                            int64_t qs, int64_t qe, uint32_t p, int L, uint64_t (&M)[NW],
-                                            uint64_t (&A)[NW], int &a, int &bnd)
+__device__ __forceinline__ void mismatch_mask(const ScanParams &P, const uint64_t *s_tile, int64_t t0, int64_t d,
+                                              uint32_t p, uint64_t (&M)[NW])
 {
     const int off = (int)(d - t0) + CB_FRONT_PAD;    // bit offset in the staged tile
     const uint64_t *pw = P.precs + (int64_t)p * P.prec_words;
@@ -428,54 +416,13 @@ __device__ __forceinline__ void align_probe(const ScanParams &P, const uint64_t 
 #pragma unroll
         for (int w = 0; w < NW; w++) M[w] |= __ldg(pw + b * NW + w) ^ read64(s_tile + b * TW, off + 64 * w);
     }
-    // probe.py:1075-1094: the alignment is clipped to the sequence on both sides
-    a = (int)max((int64_t)0, qs - d);
-    bnd = (int)min((int64_t)L, qe - d);
-    uint64_t Z[NW];
-#pragma unroll
-    for (int w = 0; w < NW; w++) Z[w] = ~M[w] & range_word(a, bnd, w);
-    runs_of_k<NW>(Z, P.k, A);
-#pragma unroll
-    for (int w = 0; w < NW; w++) A[w] &= __ldg(pw + P.bits * NW + w);
 }
 
 // ---------------------------------------------------------------------------------------
-// Fast path for probes of up to 128 bases (NW == 2) and a compile-time seed length KC: masks are
-// two scalar 64-bit registers, every shift amount of the run detection is a constant.
+// Fast path for probes of up to 128 bases (NW == 2, every shipped probe length): masks are two
+// scalar 64-bit registers.
 // ---------------------------------------------------------------------------------------
 struct U128 { uint64_t lo, hi; };
-
-__device__ __forceinline__ U128 shr128(U128 x, int n)      // n is a compile-time constant after unrolling
-{
-    U128 r;
-    if (n == 0) return x;
-    if (n < 64) { r.lo = (x.lo >> n) | (x.hi << (64 - n)); r.hi = x.hi >> n; }
-    else if (n == 64) { r.lo = x.hi; r.hi = 0; }
-    else if (n < 128) { r.lo = x.hi >> (n - 64); r.hi = 0; }
-    else { r.lo = 0; r.hi = 0; }
-    return r;
-}
-
-template <int KC>
-__device__ __forceinline__ U128 runs_of_k_const(U128 Z)
-{
-    U128 D = Z, C;
-    C.lo = ~0ull; C.hi = ~0ull;
-    int off = 0;
-#pragma unroll
-    for (int len = 1; len <= KC; len <<= 1) {
-        if (KC & len) {
-            const U128 t = shr128(D, off);
-            C.lo &= t.lo; C.hi &= t.hi;
-            off += len;
-        }
-        if ((len << 1) <= KC) {
-            const U128 t = shr128(D, len);
-            D.lo &= t.lo; D.hi &= t.hi;
-        }
-    }
-    return C;
-}
 
 // bits [a, b) of a 128-bit mask, 0 <= a <= b <= 128
 __device__ __forceinline__ U128 range128(int a, int b)
@@ -490,14 +437,13 @@ __device__ __forceinline__ U128 range128(int a, int b)
     return r;
 }
 
-template <int KC>
-__device__ __forceinline__ void align_probe_fast(const ScanParams &P, const uint64_t *s_tile, int64_t t0, int64_t d,
-                                                 int64_t qs, int64_t qe, uint32_t p, int L, U128 &M, U128 &A,
-                                                 int &a, int &bnd)
+__device__ __forceinline__ U128 mismatch_mask_fast(const ScanParams &P, const uint64_t *s_tile, int64_t t0, int64_t d,
+                                                   uint32_t p)
 {
     const int off = (int)(d - t0) + CB_FRONT_PAD;
     const int idx = off >> 6, sh = off & 63;
     const ulonglong2 *pr = reinterpret_cast<const ulonglong2 *>(P.precs + (int64_t)p * P.prec_words);
+    U128 M;
     M.lo = 0ull;
     M.hi = 0ull;
     for (int b = 0; b < P.bits; b++) {
@@ -510,25 +456,7 @@ __device__ __forceinline__ void align_probe_fast(const ScanParams &P, const uint
         M.lo |= pw.x ^ w0;
         M.hi |= pw.y ^ w1;
     }
-    const ulonglong2 seeds = __ldg(pr + P.bits);
-    a = (int)max((int64_t)0, qs - d);
-    bnd = (int)min((int64_t)L, qe - d);
-    const U128 R = range128(a, bnd);
-    U128 Z;
-    Z.lo = ~M.lo & R.lo;
-    Z.hi = ~M.hi & R.hi;
-    const U128 C = runs_of_k_const<KC>(Z);
-    A.lo = C.lo & seeds.x;
-    A.hi = C.hi & seeds.y;
-}
-
-// is bit `pos` the lowest set bit of A?
-__device__ __forceinline__ bool lowest_is(U128 A, int pos)
-{
-    const uint64_t below = pos < 64 ? (A.lo & ((1ull << pos) - 1ull))
-                                    : (A.lo | (A.hi & ((1ull << (pos - 64)) - 1ull)));
-    const uint64_t bit = pos < 64 ? (A.lo >> pos) : (A.hi >> (pos - 64));
-    return below == 0ull && (bit & 1ull);
+    return M;
 }
 
 __device__ __forceinline__ int ffs128(U128 x)
@@ -591,156 +519,75 @@ __device__ __forceinline__ int anchored_extend_fast(U128 ML, U128 MR, int a, int
     return best_len;
 }
 
-struct OutRec { uint32_t s, e; };
-
-// Owner of a (probe, diagonal): evaluate the anchored extension for every matching seed that
-// starts a new mismatch-free run; returns the number of ranges written to `out`.
-template <int NW>
-__device__ __forceinline__ int run_owner_task(const ScanParams &P, const uint64_t (&M)[NW], uint64_t (&A)[NW],
-                                              int a, int bnd, int L, int64_t d, int64_t qs, int64_t qe,
-                                              uint32_t q_ubase, uint32_t p, OutRec (&out)[MAX_LOCAL_REC])
-{
-    const int k = P.k;
-    const int64_t qlen = qe - qs;
-    int thres = P.lcf;                                // probe.py:1332
-    if (L < thres) thres = L;
-    if (qlen < (int64_t)thres) thres = (int)qlen;
-    uint32_t cur_s = 0, cur_e = 0;
-    bool have = false;
-    int n_out = 0;
-    auto flush = [&]() {
-        if (n_out < MAX_LOCAL_REC) {
-#pragma unroll
-            for (int r = 0; r < MAX_LOCAL_REC; r++)
-                if (r == n_out) { out[r].s = cur_s; out[r].e = cur_e; }
-        } else {                                      // rare: spill straight to the global list
-            const unsigned long long slot = atomicAdd(P.rec_cursor, 1ull);
-            if (slot < P.rec_cap) P.rec[slot] = make_uint4(p, cur_s, cur_e, 0u);
-        }
-        n_out++;
-    };
-    int prev_s = -1;
-    for (;;) {
-        const int s = lowest_set<NW>(A);
-        if (s < 0) break;
-        clear_bit<NW>(A, s);
-        // seeds inside one mismatch-free run see the same mismatches on both sides and give the
-        // same range; only the first seed of a run is evaluated
-        if (prev_s >= 0 && !any_in_range<NW>(M, prev_s + k, s)) { prev_s = s; continue; }
-        prev_s = s;
-        int start, exact_len;
-        const int len = anchored_extend<NW>(M, a, bnd, s, k, P.m, start, exact_len);
-        if (len < thres) continue;
-        if (P.island > 0) {                           // probe.py:1335-1342
-            const int ex = (P.m == 0) ? len : exact_len;
-            if (ex < P.island) continue;
-        }
-        // sequence-local range, then +-cover_extension, clip, universe offset
-        // (filter/set_cover_filter.py:429-439)
-        int64_t rs = d + start - qs, re = rs + len;
-        rs -= P.ext;
-        re += P.ext;
-        if (rs < 0) rs = 0;
-        if (re > qlen) re = qlen;
-        const uint32_t us = q_ubase + (uint32_t)rs, ue = q_ubase + (uint32_t)re;
-        if (have && us <= cur_e && ue >= cur_s) {     // overlaps or touches the pending range
-            cur_s = min(cur_s, us);
-            cur_e = max(cur_e, ue);
-        } else {
-            if (have) flush();
-            cur_s = us;
-            cur_e = ue;
-            have = true;
-        }
-    }
-    if (have) flush();
-    return n_out;
-}
-
-// Fast-path owner: one anchored extension per mismatch-free run that holds a matching seed.
-// All seeds of A below the first mismatch (or the clip boundary) to the right of the current seed
-// lie in the same run -- a seed overlapping that mismatch would not be in A -- and give the same
-// range, so they are dropped together.
-template <int KC>
-__device__ __forceinline__ int run_owner_task_fast(const ScanParams &P, U128 M, U128 A, int a, int bnd, int L,
-                                                   int64_t d, int64_t qs, int64_t qe, uint32_t q_ubase, uint32_t p,
-                                                   OutRec (&out)[MAX_LOCAL_REC])
+// probe.py:1328-1344 (thresholds) and filter/set_cover_filter.py:429-439 (+-cover_extension, clip to
+// the sequence, universe offset) for an anchored range [start, start+len) in probe coordinates.
+__device__ __forceinline__ bool finish_range(const ScanParams &P, int len, int start, int exact_len, int L, int64_t d,
+                                             int64_t qs, int64_t qe, uint32_t q_ubase, uint32_t &us, uint32_t &ue)
 {
     const int64_t qlen = qe - qs;
     int thres = P.lcf;                                // probe.py:1332
     if (L < thres) thres = L;
     if (qlen < (int64_t)thres) thres = (int)qlen;
-    const U128 R = range128(a, bnd);
-    U128 mism;
-    mism.lo = M.lo & R.lo;
-    mism.hi = M.hi & R.hi;
-    uint32_t cur_s = 0, cur_e = 0;
-    bool have = false;
-    int n_out = 0;
-    auto flush = [&]() {
-        if (n_out < MAX_LOCAL_REC) {
-#pragma unroll
-            for (int r = 0; r < MAX_LOCAL_REC; r++)
-                if (r == n_out) { out[r].s = cur_s; out[r].e = cur_e; }
-        } else {
-            const unsigned long long slot = atomicAdd(P.rec_cursor, 1ull);
-            if (slot < P.rec_cap) P.rec[slot] = make_uint4(p, cur_s, cur_e, 0u);
-        }
-        n_out++;
-    };
-    while (A.lo | A.hi) {
-        const int s = ffs128(A);
-        const U128 right = range128(s + KC, 128);
-        U128 MR;
-        MR.lo = mism.lo & right.lo;
-        MR.hi = mism.hi & right.hi;
-        int run_end = ffs128(MR);
-        if (run_end < 0) run_end = bnd;
-        const U128 gone = range128(0, run_end);
-        A.lo &= ~gone.lo;
-        A.hi &= ~gone.hi;
-        const U128 left = range128(0, s);
-        U128 ML;
-        ML.lo = mism.lo & left.lo;
-        ML.hi = mism.hi & left.hi;
-        int start, exact_len;
-        const int len = anchored_extend_fast(ML, MR, a, bnd, s, KC, P.m, start, exact_len);
-        if (len < thres) continue;
-        if (P.island > 0) {                           // probe.py:1335-1342
-            const int ex = (P.m == 0) ? len : exact_len;
-            if (ex < P.island) continue;
-        }
-        int64_t rs = d + start - qs, re = rs + len;   // filter/set_cover_filter.py:429-439
-        rs -= P.ext;
-        re += P.ext;
-        if (rs < 0) rs = 0;
-        if (re > qlen) re = qlen;
-        const uint32_t us = q_ubase + (uint32_t)rs, ue = q_ubase + (uint32_t)re;
-        if (have && us <= cur_e && ue >= cur_s) {
-            cur_s = min(cur_s, us);
-            cur_e = max(cur_e, ue);
-        } else {
-            if (have) flush();
-            cur_s = us;
-            cur_e = ue;
-            have = true;
-        }
+    if (len < thres) return false;
+    if (P.island > 0) {                               // probe.py:1335-1342
+        const int ex = (P.m == 0) ? len : exact_len;
+        if (ex < P.island) return false;
     }
-    if (have) flush();
-    return n_out;
+    int64_t rs = d + start - qs, re = rs + len;
+    rs -= P.ext;
+    re += P.ext;
+    if (rs < 0) rs = 0;
+    if (re > qlen) re = qlen;
+    us = q_ubase + (uint32_t)rs;
+    ue = q_ubase + (uint32_t)re;
+    return true;
 }
 
-template <int NW, int KC>
+// One surviving hit: probe p, its seed at probe position `pos`, aligned on diagonal d of sequence
+// [qs, qe).  False when the seed does not match after all (bucket/tag collision) or the range fails
+// the thresholds.
+template <int NW, bool FAST>
+__device__ __forceinline__ bool eval_hit(const ScanParams &P, const uint64_t *s_tile, int64_t t0, int64_t d, int pos,
+                                         uint32_t p, int64_t qs, int64_t qe, uint32_t q_ubase, uint32_t &us,
+                                         uint32_t &ue)
+{
+    const int L = P.plen[p];
+    // probe.py:1075-1094: the alignment is clipped to the sequence on both sides
+    const int a = (int)max((int64_t)0, qs - d);
+    const int bnd = (int)min((int64_t)L, qe - d);
+    int start, exact_len, len;
+    if constexpr (FAST) {
+        static_assert(NW == 2, "the scalar 128-bit path is for two-word probes");
+        const int k = P.k;
+        const U128 M = mismatch_mask_fast(P, s_tile, t0, d, p);
+        const U128 S = range128(pos, pos + k);
+        if ((M.lo & S.lo) | (M.hi & S.hi)) return false;
+        const U128 RL = range128(a, pos), RR = range128(pos + k, bnd);
+        U128 ML, MR;
+        ML.lo = M.lo & RL.lo; ML.hi = M.hi & RL.hi;
+        MR.lo = M.lo & RR.lo; MR.hi = M.hi & RR.hi;
+        len = anchored_extend_fast(ML, MR, a, bnd, pos, k, P.m, start, exact_len);
+    } else {
+        uint64_t M[NW];
+        mismatch_mask<NW>(P, s_tile, t0, d, p, M);
+        if (any_in_range<NW>(M, pos, pos + P.k)) return false;
+        len = anchored_extend<NW>(M, a, bnd, pos, P.k, P.m, start, exact_len);
+    }
+    return finish_range(P, len, start, exact_len, L, d, qs, qe, q_ubase, us, ue);
+}
+
+template <int NW, bool FAST, int HITS_PER_THREAD>
 __global__ void __launch_bounds__(SCAN_THREADS, SCAN_MIN_BLOCKS)
 scan_kernel(const ScanParams P)
 {
+    constexpr int QUEUE_CAP = QUEUE_FLUSH + SCAN_THREADS * HITS_PER_THREAD;   // 12 KB at 4 hits per thread
     __shared__ __align__(128) uint64_t s_tile[CB_MAX_SYMBOL_BITS * TW];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ uint32_t s_begin_lo[CB_TILE];       // bucket begin (entries < 2^32)
     __shared__ uint32_t s_cum[CB_TILE + 1];
-    __shared__ uint32_t s_tag[CB_TILE];
+    __shared__ uint32_t s_tag[CB_TILE];            // tag24 | min(distance to the sequence start, 255) << 24
     __shared__ uint32_t s_seq[CB_TILE];
-    __shared__ uint64_t s_queue[QUEUE_CAP];        // owner tasks: j << 40 | pos << 32 | probe
+    __shared__ uint64_t s_queue[QUEUE_CAP];        // surviving hits: j << 40 | probe << 8 | pos
     __shared__ uint32_t s_warp[SCAN_THREADS / 32];
     __shared__ uint32_t s_qcount;
     __shared__ long long s_tile_id;
@@ -755,7 +602,8 @@ scan_kernel(const ScanParams P)
     }
     __syncthreads();
     uint32_t phase = 0;
-    unsigned long long local_hits = 0, local_lookups = 0, local_owners = 0;
+    unsigned long long local_hits = 0, local_lookups = 0, local_surv = 0;
+    const int pw = P.pw;
 
     for (;;) {
         if (tid == 0) s_tile_id = (long long)atomicAdd(P.tile_counter, 1ull);
@@ -799,7 +647,7 @@ scan_kernel(const ScanParams P)
                     const int64_t mid = (lo + hi) >> 1;
                     if (P.seq_start[mid] <= g) lo = mid; else hi = mid;
                 }
-                const int64_t qe = P.seq_start[lo + 1];
+                const int64_t qs = P.seq_start[lo], qe = P.seq_start[lo + 1];
                 s_seq[j] = (uint32_t)lo;
                 if (g + P.k <= qe) {                 // probe.py:1062 i in [0, len-k]
                     const uint64_t h = kmer_hash(P.bits, P.k, [&](int b, int o) {
@@ -807,8 +655,9 @@ scan_kernel(const ScanParams P)
                     });
                     const uint32_t bucket = (uint32_t)h & P.bucket_mask;
                     const int64_t b0 = P.bucket_off[bucket], b1 = P.bucket_off[bucket + 1];
+                    const int64_t dist = g - qs;
                     s_begin_lo[j] = (uint32_t)b0;
-                    s_tag[j] = (uint32_t)(h >> 40);
+                    s_tag[j] = (uint32_t)(h >> 40) | ((uint32_t)(dist < 255 ? dist : 255) << 24);
                     cnt[r] = (uint32_t)(b1 - b0);
                     local_lookups++;
                 }
@@ -846,7 +695,8 @@ scan_kernel(const ScanParams P)
         local_hits += (tid == 0) ? total : 0;
         if (P.count_only) continue;
 
-        // ---- phase 2: candidate hits in chunks; owners are queued, the queue is drained densely
+        // ---- phase 2: candidate hits in chunks; survivors of the cheap test are queued, the queue is
+        // drained densely
         for (uint32_t base = 0; base < total; base += SCAN_THREADS * HITS_PER_THREAD) {
             const uint32_t h0 = base + tid * HITS_PER_THREAD;
             // warp-uniform guard: the whole warp enters or skips, lanes past `total` are predicated
@@ -860,40 +710,34 @@ scan_kernel(const ScanParams P)
                     }
                     j = lo;
                 }
-                // the HITS_PER_THREAD alignments of a thread are independent instruction chains: they are
-                // all evaluated before any result is pushed, so the scheduler can interleave them
-                bool owner_v[HITS_PER_THREAD];
+                bool surv_v[HITS_PER_THREAD];
                 uint64_t task_v[HITS_PER_THREAD];
 #pragma unroll
                 for (int u = 0; u < HITS_PER_THREAD; u++) {
                     const uint32_t h = h0 + u;
-                    bool owner = false;
+                    bool surv = false;
                     uint64_t task = 0;
                     if (h < total) {
                         while (s_cum[j + 1] <= h) j++;
-                        const uint64_t ent = __ldg(P.entries + (int64_t)s_begin_lo[j] + (h - s_cum[j]));
-                        if ((uint32_t)(ent & 0xffffffull) == s_tag[j]) {
-                            const uint32_t p = (uint32_t)(ent >> 32);
-                            const int pos = (int)((ent >> 24) & 0xff);
-                            const uint32_t q = s_seq[j];
-                            const int L = P.plen[p];
-                            int a, bnd;
-                            // A has bit `pos` set unless the bucket/tag matched a different k-mer
-                            if constexpr (NW == 2 && KC > 0) {
-                                U128 M, A;
-                                align_probe_fast<KC>(P, s_tile, t0, t0 + j - pos, P.seq_start[q], P.seq_start[q + 1],
-                                                     p, L, M, A, a, bnd);
-                                owner = lowest_is(A, pos);
-                            } else {
-                                uint64_t M[NW], A[NW];
-                                align_probe<NW>(P, s_tile, t0, t0 + j - pos, P.seq_start[q], P.seq_start[q + 1], p,
-                                                L, M, A, a, bnd);
-                                owner = lowest_set<NW>(A) == pos;
+                        const ulonglong2 ent = __ldg(P.entries + (int64_t)s_begin_lo[j] + (h - s_cum[j]));
+                        const uint32_t tg = s_tag[j];
+                        if ((uint32_t)(ent.x & 0xffffffull) == (tg & 0xffffffu)) {
+                            surv = true;
+                            // nearest lower selected seed of the probe: g bases before this seed.  If it
+                            // starts inside the sequence and those g bases match too, it matches on this
+                            // diagonal, shares the mismatch-free run and gives the same range.
+                            const uint32_t g = (uint32_t)(ent.y & 0xffull);
+                            if (g != 0u && g <= (tg >> 24)) {
+                                const int off = j + CB_FRONT_PAD - (int)g;
+                                uint64_t diff = 0ull;
+                                for (int b = 0; b < P.bits; b++)
+                                    diff |= read64(s_tile + b * TW, off) ^ (ent.y >> (8 + b * pw));
+                                surv = (diff << (64 - g)) != 0ull;
                             }
-                            task = ((uint64_t)j << 40) | ((uint64_t)pos << 32) | (uint64_t)p;
+                            task = ((uint64_t)j << 40) | (ent.x >> 24);      // j | probe << 8 | pos
                         }
                     }
-                    owner_v[u] = owner;
+                    surv_v[u] = surv;
                     task_v[u] = task;
                 }
                 __syncwarp();
@@ -902,7 +746,7 @@ scan_kernel(const ScanParams P)
                 uint32_t n_push = 0;
 #pragma unroll
                 for (int u = 0; u < HITS_PER_THREAD; u++) {
-                    ow[u] = __ballot_sync(0xffffffffu, owner_v[u]);
+                    ow[u] = __ballot_sync(0xffffffffu, surv_v[u]);
                     n_push += __popc(ow[u]);
                 }
                 if (n_push) {
@@ -912,7 +756,7 @@ scan_kernel(const ScanParams P)
                     uint32_t before = 0;
 #pragma unroll
                     for (int u = 0; u < HITS_PER_THREAD; u++) {
-                        if (owner_v[u]) s_queue[qb + before + __popc(ow[u] & ((1u << lane) - 1u))] = task_v[u];
+                        if (surv_v[u]) s_queue[qb + before + __popc(ow[u] & ((1u << lane) - 1u))] = task_v[u];
                         before += __popc(ow[u]);
                     }
                 }
@@ -923,47 +767,29 @@ scan_kernel(const ScanParams P)
             if (qn > (uint32_t)QUEUE_FLUSH || (last && qn > 0)) {
                 for (uint32_t tb = 0; tb < qn; tb += SCAN_THREADS) {
                     const uint32_t ti = tb + tid;
-                    OutRec out[MAX_LOCAL_REC];
-                    int n_out = 0;
-                    uint32_t p = 0;
+                    bool emit = false;
+                    uint32_t p = 0, us = 0, ue = 0;
                     if (ti < qn) {
                         const uint64_t task = s_queue[ti];
                         const int j = (int)(task >> 40);
-                        const int pos = (int)((task >> 32) & 0xff);
-                        p = (uint32_t)task;
+                        const int pos = (int)(task & 0xffull);
+                        p = (uint32_t)(task >> 8);
                         const uint32_t q = s_seq[j];
-                        const int64_t qs = P.seq_start[q], qe = P.seq_start[q + 1];
-                        const int L = P.plen[p];
-                        const int64_t d = t0 + j - pos;
-                        int a, bnd;
-                        if constexpr (NW == 2 && KC > 0) {
-                            U128 M, A;
-                            align_probe_fast<KC>(P, s_tile, t0, d, qs, qe, p, L, M, A, a, bnd);
-                            n_out = run_owner_task_fast<KC>(P, M, A, a, bnd, L, d, qs, qe, P.seq_ubase[q], p, out);
-                        } else {
-                            uint64_t M[NW], A[NW];
-                            align_probe<NW>(P, s_tile, t0, d, qs, qe, p, L, M, A, a, bnd);
-                            n_out = run_owner_task<NW>(P, M, A, a, bnd, L, d, qs, qe, P.seq_ubase[q], p, out);
-                        }
-                        if (n_out) atomicAdd(&P.rec_count[p], (uint32_t)n_out);
-                        local_owners++;
+                        emit = eval_hit<NW, FAST>(P, s_tile, t0, t0 + j - pos, pos, p, P.seq_start[q], P.seq_start[q + 1],
+                                                P.seq_ubase[q], us, ue);
+                        local_surv++;
                     }
-                    // warp-aggregated append of the (up to MAX_LOCAL_REC) ranges held in registers
-                    const int n_loc = n_out < MAX_LOCAL_REC ? n_out : MAX_LOCAL_REC;
-                    int incl = n_loc;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const int t = __shfl_up_sync(0xffffffffu, incl, o);
-                        if (lane >= o) incl += t;
-                    }
-                    const int wtotal = __shfl_sync(0xffffffffu, incl, 31);
-                    if (wtotal) {
+                    // warp-aggregated append
+                    const unsigned em = __ballot_sync(0xffffffffu, emit);
+                    if (em) {
                         unsigned long long wb = 0;
-                        if (lane == 0) wb = atomicAdd(P.rec_cursor, (unsigned long long)wtotal);
-                        wb = __shfl_sync(0xffffffffu, wb, 0) + (unsigned long long)(incl - n_loc);
-#pragma unroll
-                        for (int r = 0; r < MAX_LOCAL_REC; r++)
-                            if (r < n_loc && wb + r < P.rec_cap) P.rec[wb + r] = make_uint4(p, out[r].s, out[r].e, 0u);
+                        if (lane == 0) wb = atomicAdd(P.rec_cursor, (unsigned long long)__popc(em));
+                        wb = __shfl_sync(0xffffffffu, wb, 0);
+                        if (emit) {
+                            const unsigned long long slot = wb + __popc(em & ((1u << lane) - 1u));
+                            if (slot < P.rec_cap) P.rec[slot] = make_uint4(p, us, ue, 0u);
+                            atomicAdd(&P.rec_count[p], 1u);
+                        }
                     }
                 }
                 __syncthreads();
@@ -975,7 +801,7 @@ scan_kernel(const ScanParams P)
     }
     if (local_hits) atomicAdd(P.stat_hits, local_hits);
     if (local_lookups) atomicAdd(P.stat_lookups, local_lookups);
-    if (local_owners) atomicAdd(P.stat_owners, local_owners);
+    if (local_surv) atomicAdd(P.stat_owners, local_surv);
 }
 
 // bucket the global range list by probe: rec_sorted[rec_off[p] + slot] = (start << 32 | end)
@@ -1214,10 +1040,10 @@ int launch_merge(cb_ctx *ctx, const int64_t *d_roff, uint64_t *d_sorted, int64_t
     return CB_OK;
 }
 
-template <int NW, int KC>
+template <int NW, bool FAST, int HPT>
 int launch_scan(cb_ctx *ctx, const ScanParams &P, int grid)
 {
-    scan_kernel<NW, KC><<<grid, SCAN_THREADS, 0, ctx->stream>>>(P);
+    scan_kernel<NW, FAST, HPT><<<grid, SCAN_THREADS, 0, ctx->stream>>>(P);
     ctx->launches++;
     CB_CUDA(ctx, cudaGetLastError());
     return CB_OK;
@@ -1225,24 +1051,17 @@ int launch_scan(cb_ctx *ctx, const ScanParams &P, int grid)
 
 int launch_scan_nw(cb_ctx *ctx, int nw, const ScanParams &P, int grid)
 {
-    const bool generic = getenv("CB_SCAN_GENERIC") != nullptr;     // testing: force the generic path
-    if (nw == 2 && !generic) {
-        // specialised seed lengths: the random-mode default (20) and the pigeonhole lengths of
-        // 75/100-nt probes (probe.py:473-491)
-        switch (P.k) {
-        case 20: return launch_scan<2, 20>(ctx, P, grid);
-        case 25: return launch_scan<2, 25>(ctx, P, grid);
-        case 50: return launch_scan<2, 50>(ctx, P, grid);
-        case 75: return launch_scan<2, 75>(ctx, P, grid);
-        case 100: return launch_scan<2, 100>(ctx, P, grid);
-        default: break;
-        }
-    }
+    const bool generic = getenv("CB_SCAN_GENERIC") != nullptr;     // testing: force the multi-word path
+    const char *hpt = getenv("CB_SCAN_HPT");                        // tuning: candidate hits per thread and chunk
     switch (nw) {
-    case 1: return launch_scan<1, 0>(ctx, P, grid);
-    case 2: return launch_scan<2, 0>(ctx, P, grid);
-    case 3: return launch_scan<3, 0>(ctx, P, grid);
-    case 4: return launch_scan<4, 0>(ctx, P, grid);
+    case 1: return launch_scan<1, false, 4>(ctx, P, grid);
+    case 2:
+        if (generic) return launch_scan<2, false, 4>(ctx, P, grid);
+        if (hpt && atoi(hpt) == 8) return launch_scan<2, true, 8>(ctx, P, grid);
+        if (hpt && atoi(hpt) == 2) return launch_scan<2, true, 2>(ctx, P, grid);
+        return launch_scan<2, true, 4>(ctx, P, grid);
+    case 3: return launch_scan<3, false, 4>(ctx, P, grid);
+    case 4: return launch_scan<4, false, 4>(ctx, P, grid);
     }
     return cb_fail(ctx, CB_ERR_UNSUPPORTED, "probe longer than CB_MAX_PROBE_LEN");
 }
@@ -1316,7 +1135,8 @@ int cb_coverage_impl(cb_ctx *ctx, const cb_probes *probes, const cb_targets *tar
     DevBuf<uint32_t> d_eprobe, d_bcount, d_bcursor, d_ndist;
     DevBuf<uint8_t> d_spos, d_epos;
     DevBuf<int64_t> d_boff, d_soff, d_eoff;
-    DevBuf<uint64_t> d_entries, d_precs;
+    DevBuf<ulonglong2> d_entries;
+    DevBuf<uint64_t> d_precs;
     DevBuf<int> d_bad;
     DevBuf<unsigned long long> d_ctr;        // [0] tile counter, [1] hits, [2] lookups, [3] owners, [4] range cursor
     if (!uniform) CB_CUDA(ctx, d_soff.alloc((size_t)P + 1));
@@ -1391,6 +1211,7 @@ int cb_coverage_impl(cb_ctx *ctx, const cb_probes *probes, const cb_targets *tar
     sp.plen = probes->d_len;
     sp.bucket_off = d_boff.p;
     sp.entries = d_entries.p;
+    sp.pw = 56 / bits;
     sp.bucket_mask = (uint32_t)(nb - 1);
     sp.m = hp->mismatches;
     sp.lcf = hp->lcf_thres;
@@ -1419,11 +1240,9 @@ int cb_coverage_impl(cb_ctx *ctx, const cb_probes *probes, const cb_targets *tar
     CB_CUDA(ctx, cudaMemcpyAsync(h_ctr, d_ctr.p, sizeof h_ctr, cudaMemcpyDeviceToHost, st));
     CB_CUDA(ctx, cudaStreamSynchronize(st));
     const unsigned long long hits_ub = h_ctr[1];
-    // a diagonal is emitted once, by its lowest matching seed: expect about hits / seeds-per-probe
-    // ranges; start with twice that and fall back to the hard bound if it overflows
-    const double distinct_per_probe = (double)n_entries / (double)P;
-    unsigned long long cap = (unsigned long long)(2.0 * (double)hits_ub / (distinct_per_probe > 1.0 ? distinct_per_probe : 1.0)) + 4096;
-    if (cap > hits_ub + 4096) cap = hits_ub + 4096;
+    // one range at most per surviving hit (one hit per mismatch-free run that holds a seed): start with a
+    // third of the candidate hits and fall back to the hard bound if the list overflows
+    unsigned long long cap = hits_ub / 3 + 4096;
 
     // ---- K3 scan
     DevBuf<uint4> d_rec;
@@ -1488,7 +1307,7 @@ int cb_coverage_impl(cb_ctx *ctx, const cb_probes *probes, const cb_targets *tar
         stats->n_raw_ranges = (int64_t)n_raw;
         stats->n_intervals = n_iv;
         stats->n_kernel_launches = ctx->launches;
-        stats->reserved[0] = (int64_t)h_ctr[3];     // diagonals owned (anchored extensions run)
+        stats->reserved[0] = (int64_t)h_ctr[3];     // hits that survived the cheap test (anchored extensions run)
     }
     guard.c = nullptr;
     *out = cov;
