@@ -48,6 +48,8 @@ EXPORTED_SYMBOLS = [
     'cb_coverage', 'cb_coverage_uniform', 'cb_cover_free', 'cb_cover_num_intervals', 'cb_cover_export', 'cb_cover_import',
     'cb_setcover', 'cb_setcover_costs', 'cb_minhash_neardup', 'cb_hamming_neardup', 'cb_neardup_filter', 'cb_group_duplicates',
     'cb_comm_unique_id', 'cb_comm_init', 'cb_comm_destroy', 'cb_cover_allgather',
+    'cb_coverage_range', 'cb_exchange_alloc', 'cb_exchange_bytes', 'cb_exchange_handle', 'cb_exchange_attach',
+    'cb_exchange_required', 'cb_setcover_sharded',
 ]
 
 _lib = None
@@ -90,6 +92,15 @@ def load():
     L.cb_mt19937_randint.argtypes = [vp, C.POINTER(i32), C.c_uint32, i64, vp]
     L.cb_coverage.argtypes = [vp, vp, vp, C.POINTER(HybParams), vp, vp, C.POINTER(vp), C.POINTER(Stats)]
     L.cb_coverage_uniform.argtypes = [vp, vp, vp, C.POINTER(HybParams), vp, i32, C.POINTER(vp), C.POINTER(Stats)]
+    L.cb_coverage_range.argtypes = [vp, vp, vp, C.POINTER(HybParams), vp, vp, vp, i32, i64, i64, C.POINTER(vp),
+                                    C.POINTER(Stats)]
+    L.cb_exchange_alloc.argtypes = [vp, i64]
+    L.cb_exchange_bytes.argtypes = [vp]
+    L.cb_exchange_bytes.restype = i64
+    L.cb_exchange_handle.argtypes = [vp, vp, C.POINTER(C.c_uint64)]
+    L.cb_exchange_attach.argtypes = [vp, i32, i32, vp, vp, i32]
+    L.cb_exchange_required.argtypes = [vp, vp, C.POINTER(i64)]
+    L.cb_setcover_sharded.argtypes = [vp, vp, i64, i64, vp, C.POINTER(i64), C.POINTER(Stats)]
     L.cb_cover_free.argtypes = [vp]
     L.cb_cover_free.restype = None
     L.cb_cover_num_intervals.argtypes = [vp]
@@ -217,6 +228,23 @@ class Context:
                                                C.byref(out), C.byref(st)))
         return Handle(self.L.cb_cover_free, out), st
 
+    def coverage_range(self, probes, targets, mismatches, lcf_thres, island, cover_extension, k, lo, hi,
+                       seeds_u8=None, seed_off=None, seed_pos=None):
+        """cb_coverage_range: stage A for the probes [lo, hi) only (a rank's shard); the cover keeps global
+        probe ids.  `seeds_u8`: uint8 [hi - lo, s] matrix, first row for probe lo; or the CSR pair."""
+        hp = HybParams(mismatches, lcf_thres, island, cover_extension, k)
+        out, st = C.c_void_p(), Stats()
+        if seeds_u8 is not None:
+            seeds_u8 = np.ascontiguousarray(seeds_u8, dtype=np.uint8)
+            s = seeds_u8.shape[1] if seeds_u8.ndim == 2 else 0
+            self._check(self.L.cb_coverage_range(self.h, probes.h, targets.h, C.byref(hp), None, None,
+                                                 seeds_u8.ctypes.data if seeds_u8.size else _ONE_BYTE.ctypes.data, s,
+                                                 lo, hi, C.byref(out), C.byref(st)))
+        else:
+            self._check(self.L.cb_coverage_range(self.h, probes.h, targets.h, C.byref(hp), _ptr(seed_off),
+                                                 _ptr(seed_pos), None, 0, lo, hi, C.byref(out), C.byref(st)))
+        return Handle(self.L.cb_cover_free, out), st
+
     def cover_export(self, cover):
         n = self.L.cb_cover_num_intervals(cover.h)
         pid = np.zeros(n, dtype=np.int64)
@@ -255,6 +283,44 @@ class Context:
         out = C.c_void_p()
         self._check(self.L.cb_cover_allgather(self.h, local_cover.h, probe_lo, n_probes_total, C.byref(out)))
         return Handle(self.L.cb_cover_free, out)
+
+    # ---- multi-GPU: sharded set cover through peer-mapped exchange areas
+    def exchange_alloc(self, nbytes):
+        self._check(self.L.cb_exchange_alloc(self.h, int(nbytes)))
+        self.exchange_ready = False
+
+    def exchange_bytes(self):
+        return int(self.L.cb_exchange_bytes(self.h))
+
+    def exchange_handle(self):
+        """(64-byte CUDA IPC handle, device address) of this context's exchange area."""
+        buf = (C.c_uint8 * 64)()
+        addr = C.c_uint64()
+        self._check(self.L.cb_exchange_handle(self.h, buf, C.byref(addr)))
+        return bytes(buf), int(addr.value)
+
+    def exchange_attach(self, rank, n_ranks, handles=None, addresses=None, grid_limit=0):
+        hb = ab = None
+        if handles is not None:
+            hb = (C.c_uint8 * (64 * n_ranks)).from_buffer_copy(b''.join(handles))
+        if addresses is not None:
+            ab = (C.c_uint64 * n_ranks)(*addresses)
+        self._check(self.L.cb_exchange_attach(self.h, rank, n_ranks, hb, ab, grid_limit))
+        self.exchange_ready = True
+        self.exchange_rank, self.exchange_n_ranks = rank, n_ranks
+
+    def exchange_required(self, cover):
+        n = C.c_int64()
+        self._check(self.L.cb_exchange_required(self.h, cover.h, C.byref(n)))
+        return int(n.value)
+
+    def setcover_sharded(self, cover, n_probes, lo, hi, ranks=None):
+        """cb_setcover_sharded (collective over the attached ranks): picks in pick order, the same on
+        every rank."""
+        sel = np.zeros(max(n_probes, 1), dtype=np.int64)
+        n, st = C.c_int64(), Stats()
+        self._check(self.L.cb_setcover_sharded(self.h, cover.h, lo, hi, _ptr(ranks), _ptr(sel), C.byref(n), C.byref(st)))
+        return sel[:n.value].copy(), st
 
     # ---- stage B
     def setcover(self, cover, n_probes, ranks=None, universe_p=None, costs=None):

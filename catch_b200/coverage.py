@@ -223,6 +223,16 @@ def compute_cover(ctx, group, plan, mismatches, lcf_thres, island, cover_extensi
                         plan.k, plan.seed_off, plan.seed_pos)
 
 
+def compute_cover_range(ctx, group, plan, mismatches, lcf_thres, island, cover_extension, lo, hi):
+    """Stage A for the probes [lo, hi) of a packed group (a rank's shard of a probe-sharded run); the
+    cover keeps the global probe ids.  `plan` is the seed plan of the WHOLE probe list."""
+    if plan.uniform is not None:
+        return ctx.coverage_range(group.probes, group.targets, mismatches, lcf_thres, island, cover_extension,
+                                  plan.k, lo, hi, seeds_u8=plan.uniform[lo:hi])
+    return ctx.coverage_range(group.probes, group.targets, mismatches, lcf_thres, island, cover_extension,
+                              plan.k, lo, hi, seed_off=plan.seed_off, seed_pos=plan.seed_pos)
+
+
 def cover_with_seeds(ctx, group, seeds_per_probe, k, mismatches, lcf_thres, island, cover_extension):
     """Stage A with explicitly given seed positions (a list of position lists, one per probe):
     the device counterpart of probe.find_probe_covers_in_sequence over a prebuilt

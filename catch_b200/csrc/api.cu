@@ -204,6 +204,7 @@ void cb_destroy(cb_ctx *ctx)
 {
     if (!ctx) return;
     cb_comm_destroy(ctx);
+    cb_exchange_alloc(ctx, 0);
     if (ctx->flush_buf) cudaFree(ctx->flush_buf);
     for (int i = 0; i < 2; i++)
         if (ctx->pinned[i]) cudaFreeHost(ctx->pinned[i]);
@@ -438,7 +439,7 @@ int cb_coverage(cb_ctx *ctx, const cb_probes *probes, const cb_targets *targets,
     ctx->launches = 0;
     CB_CUDA(ctx, cudaSetDevice(ctx->device));
     cb_tls_stream = ctx->stream;
-    return cb_coverage_impl(ctx, probes, targets, params, seed_off, seed_pos, nullptr, 0, out, stats);
+    return cb_coverage_impl(ctx, probes, targets, params, seed_off, seed_pos, nullptr, 0, 0, -1, out, stats);
 }
 
 int cb_coverage_uniform(cb_ctx *ctx, const cb_probes *probes, const cb_targets *targets, const cb_hyb_params *params,
@@ -450,7 +451,20 @@ int cb_coverage_uniform(cb_ctx *ctx, const cb_probes *probes, const cb_targets *
     ctx->launches = 0;
     CB_CUDA(ctx, cudaSetDevice(ctx->device));
     cb_tls_stream = ctx->stream;
-    return cb_coverage_impl(ctx, probes, targets, params, nullptr, nullptr, seed_pos, seeds_per_probe, out, stats);
+    return cb_coverage_impl(ctx, probes, targets, params, nullptr, nullptr, seed_pos, seeds_per_probe, 0, -1, out, stats);
+}
+
+int cb_coverage_range(cb_ctx *ctx, const cb_probes *probes, const cb_targets *targets, const cb_hyb_params *params,
+                      const int64_t *seed_off, const int32_t *seed_pos, const uint8_t *seed_pos_u8,
+                      int32_t seeds_per_probe, int64_t probe_lo, int64_t probe_hi, cb_cover **out, cb_stats *stats)
+{
+    if (!ctx) return CB_ERR_ARG;
+    if (stats) memset(stats, 0, sizeof *stats);
+    ctx->launches = 0;
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cb_tls_stream = ctx->stream;
+    return cb_coverage_impl(ctx, probes, targets, params, seed_off, seed_pos, seed_pos_u8, seeds_per_probe, probe_lo,
+                            probe_hi, out, stats);
 }
 
 void cb_cover_free(cb_cover *c)

@@ -192,10 +192,11 @@ __device__ __forceinline__ uint64_t kmer_hash(int bits, int k, Reader rd)
 // Seed positions arrive as a CSR that may hold repeats in any order (the reference draws with
 // replacement and keeps a set, probe.py:393-398).  One warp per probe ORs them into the probe's
 // seed mask (the last NW words of its record) and counts the distinct positions.
-// seed_off == nullptr: every probe has exactly `uniform` positions, probe p at [p*uniform, (p+1)*uniform).
+// seed_off == nullptr: every probe has exactly `uniform` positions, probe p at [(p-lo)*uniform, (p-lo+1)*uniform).
+// Probes outside [lo, hi) get an empty mask: they belong to another rank's shard.
 __global__ void seed_mask_kernel(const int64_t *__restrict__ seed_off, int uniform,
                                  const uint8_t *__restrict__ seed_pos,
-                                 const int32_t *__restrict__ plen, int k, int64_t n_probes,
+                                 const int32_t *__restrict__ plen, int k, int64_t n_probes, int64_t lo, int64_t hi,
                                  uint64_t *__restrict__ precs, int prec_words, int nw,
                                  uint32_t *__restrict__ n_distinct, int *__restrict__ bad)
 {
@@ -205,7 +206,11 @@ __global__ void seed_mask_kernel(const int64_t *__restrict__ seed_off, int unifo
     for (int64_t p = warp; p < n_probes; p += n_warps) {
         uint64_t mask[4] = {0, 0, 0, 0};
         const int limit = plen[p] - k;             // last admissible seed start
-        const int64_t e0 = seed_off ? seed_off[p] : p * uniform, e1 = seed_off ? seed_off[p + 1] : e0 + uniform;
+        int64_t e0 = 0, e1 = 0;
+        if (p >= lo && p < hi) {
+            e0 = seed_off ? seed_off[p] : (p - lo) * uniform;
+            e1 = seed_off ? seed_off[p + 1] : e0 + uniform;
+        }
         for (int64_t e = e0 + lane; e < e1; e += 32) {
             const int s = seed_pos[e];
             if (s > limit) { *bad = 1; continue; }
@@ -1070,9 +1075,13 @@ int launch_scan_nw(cb_ctx *ctx, int nw, const ScanParams &P, int grid)
 
 int cb_coverage_impl(cb_ctx *ctx, const cb_probes *probes, const cb_targets *targets,
                      const cb_hyb_params *hp, const int64_t *seed_off, const int32_t *seed_pos,
-                     const uint8_t *seed_pos_u8, int32_t seeds_per_probe, cb_cover **out, cb_stats *stats)
+                     const uint8_t *seed_pos_u8, int32_t seeds_per_probe, int64_t probe_lo, int64_t probe_hi,
+                     cb_cover **out, cb_stats *stats)
 {
     if (!probes || !targets || !hp || !out) return cb_fail(ctx, CB_ERR_ARG, "null argument");
+    // [probe_lo, probe_hi): the probes this call scans (a rank's shard); the cover keeps global probe ids
+    if (probe_hi < 0) probe_hi = probes->n_probes;
+    if (probe_lo < 0 || probe_lo > probe_hi || probe_hi > probes->n_probes) return cb_fail(ctx, CB_ERR_ARG, "bad probe range");
     const bool uniform = seed_pos_u8 != nullptr;        // [n_probes][seeds_per_probe] bytes, no CSR
     if (uniform ? seeds_per_probe < 0 : (probes->n_probes > 0 && (!seed_off || !seed_pos)))
         return cb_fail(ctx, CB_ERR_ARG, "bad seed arguments");
@@ -1101,8 +1110,8 @@ int cb_coverage_impl(cb_ctx *ctx, const cb_probes *probes, const cb_targets *tar
                                  cudaMemcpyDeviceToDevice, st));
     CB_CUDA(ctx, cb_dev_alloc(st, (void **)&cov->d_iv_off, sizeof(int64_t) * (size_t)(P + 1)));
 
-    const int64_t n_raw_seeds = !P ? 0 : uniform ? P * (int64_t)seeds_per_probe : seed_off[P] - seed_off[0];
-    const bool empty = (P == 0 || targets->total_bases == 0 || n_raw_seeds == 0);
+    const int64_t n_raw_seeds = !P ? 0 : uniform ? (probe_hi - probe_lo) * (int64_t)seeds_per_probe : seed_off[P] - seed_off[0];
+    const bool empty = (P == 0 || probe_hi == probe_lo || targets->total_bases == 0 || n_raw_seeds == 0);
     if (empty) {
         CB_CUDA(ctx, cudaMemsetAsync(cov->d_iv_off, 0, sizeof(int64_t) * (size_t)(P + 1), st));
         CB_CUDA(ctx, cudaStreamSynchronize(st));
@@ -1155,8 +1164,8 @@ int cb_coverage_impl(cb_ctx *ctx, const cb_probes *probes, const cb_targets *tar
     t_idx.start();
     const int wide = ctx->sm_count * 8;
     build_precs_kernel<<<wide, 256, 0, st>>>(probes->d_words, P, plane_words, prec_words, d_precs.p);
-    seed_mask_kernel<<<wide, 256, 0, st>>>(uniform ? nullptr : d_soff.p, (int)seeds_per_probe, d_spos.p, probes->d_len, hp->k, P, d_precs.p, prec_words, nw,
-                                           d_ndist.p, d_bad.p);
+    seed_mask_kernel<<<wide, 256, 0, st>>>(uniform ? nullptr : d_soff.p, (int)seeds_per_probe, d_spos.p, probes->d_len, hp->k, P,
+                                           probe_lo, probe_hi, d_precs.p, prec_words, nw, d_ndist.p, d_bad.p);
     ctx->launches += 2;
     CB_CUDA(ctx, cudaGetLastError());
     int64_t n_entries = 0;

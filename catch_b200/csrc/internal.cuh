@@ -40,6 +40,15 @@ struct cb_ctx {
     size_t pinned_bytes[2] = {0, 0};
     void *comm = nullptr;         // ncclComm_t once cb_comm_init has run
     int rank = 0, n_ranks = 1;
+    // exchange area of the sharded set cover (cb_exchange_*): this context's own area and the areas of
+    // the other ranks as they are mapped in this process
+    unsigned char *xarea = nullptr;
+    size_t xarea_bytes = 0;
+    unsigned char *xpeer[CB_MAX_RANKS] = {};
+    bool xpeer_ipc[CB_MAX_RANKS] = {};
+    int xrank = 0, xn_ranks = 1;
+    int xgrid_limit = 0;          // > 0: cap on the persistent kernel's grid (several ranks sharing one device)
+    bool xarea_poisoned = false;
 };
 
 struct cb_targets {
@@ -177,7 +186,8 @@ int cb_probes_have_duplicates_impl(cb_ctx *ctx, const cb_probes *probes, int32_t
 // coverage.cu
 int cb_coverage_impl(cb_ctx *ctx, const cb_probes *probes, const cb_targets *targets,
                      const cb_hyb_params *params, const int64_t *seed_off, const int32_t *seed_pos,
-                     const uint8_t *seed_pos_u8, int32_t seeds_per_probe, cb_cover **out, cb_stats *stats);
+                     const uint8_t *seed_pos_u8, int32_t seeds_per_probe, int64_t probe_lo, int64_t probe_hi,
+                     cb_cover **out, cb_stats *stats);
 
 int cb_cover_import_impl(cb_ctx *ctx, int64_t n_probes, int32_t n_genomes, const int64_t *genome_len,
                          int64_t n_intervals, const int64_t *probe_id, const int32_t *genome,
@@ -186,6 +196,11 @@ int cb_cover_import_impl(cb_ctx *ctx, int64_t n_probes, int32_t n_genomes, const
 // setcover.cu
 int cb_setcover_impl(cb_ctx *ctx, const cb_cover *cover, const double *costs, const int32_t *ranks,
                      const double *universe_p, int64_t *sel_ids, int64_t *n_sel, cb_stats *stats);
+
+// rounds.cu
+int64_t cb_rounds_exchange_bytes(const cb_cover *cover);
+int cb_setcover_rounds_impl(cb_ctx *ctx, const cb_cover *cover, int64_t lo, int64_t hi, const int32_t *ranks,
+                            bool sharded, int64_t *sel_ids, int64_t *n_sel, cb_stats *stats);
 
 // neardup.cu
 int cb_minhash_neardup_impl(cb_ctx *ctx, const uint8_t *ascii, const int64_t *probe_off, int64_t n_probes,

@@ -1,0 +1,1004 @@
+// Stage B, default path: exact greedy multi-universe set cover in PARALLEL ROUNDS, on one GPU or
+// with the candidate probes sharded over the GPUs of one box.
+//
+// Replaces utils/set_cover.py:147-615 approx_multiuniverse(use_intervalsets=True) for the case every
+// caller of SetCoverFilter produces by default: unit costs and p_u == 1 (coverage 1.0), with or
+// without ranks.  (p_u < 1 and non-unit costs take the two-barrier kernel of setcover.cu.)
+//
+// Why rounds are exact.  Sequential greedy picks the probe with the largest key = (gain, smallest
+// id) again and again (:393-433, :483-526).  Call two probes in conflict when they share a
+// still-uncovered universe bit.  A probe whose key is larger than the key of every probe it
+// conflicts with keeps its gain until it is picked -- a conflicting neighbour would have to become
+// the global maximum first, and it cannot while the probe is there -- and it IS picked in the end,
+// because nobody else can cover its bits before it.  So all such local maxima can be applied at
+// once: the selected SET and every probe's gain at pick time are those of the sequential loop.
+// Keys at pick time are strictly decreasing along the sequential pick sequence, therefore sorting
+// the picks by that key (host part below) restores the sequential pick ORDER, which the reference's
+// output order depends on (set.add() in pick order, filter/set_cover_filter.py:893-900).
+//
+// Local maxima are searched among a candidate list: every probe (of the current rank) with gain
+// >= tau, i.e. a prefix of the global key order, so every probe with a larger key than a list
+// member is itself a list member.  One round:
+//   exchange: every GPU compacts its still-active list entries (gain >= tau) and PUSHES
+//            (probe, gain, first interval, #intervals) into the exchange area of every GPU
+//            (stores over NVLink into peer-mapped memory), then a cross-GPU barrier;
+//   mark:    every GPU runs the conflict detection for ALL active candidates: one thread per
+//            (candidate, interval), intervals of a remote candidate are read straight from the
+//            owner's memory, atomicMax(mark[w], key) for each universe word with uncovered bits;
+//   check:   a candidate is accepted iff mark[w] == its key in all of those words (word
+//            granularity: false conflicts only postpone a pick);
+//   apply:   every GPU applies ALL accepted probes to ITS OWN copy of the universe bit set and to
+//            the gains of ITS OWN probes (interval index of the local probes only).
+// The universe bit set, the marks and the accepted list are replicated (every GPU computes the
+// same values from the same inputs); gains, the interval index and the candidate search -- the
+// parts whose cost grows with the number of probes -- are sharded.  The only cross-GPU traffic per
+// round is the candidate push (a few KB) and the interval reads of the active candidates.  On one
+// GPU the same kernel runs with n_ranks = 1 and the exchange degenerates to a grid barrier.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+#include "internal.cuh"
+
+namespace {
+
+constexpr int RT = 256;                     // threads per CTA
+constexpr int NWARP = RT / 32;
+constexpr int GAIN_LEVELS = 14;
+constexpr int ID_LEVELS = 33;
+constexpr int LIST_CAP_MAX = 4096;
+constexpr int PER = LIST_CAP_MAX / RT;
+constexpr int APPLY_WORDS = 64;             // winner intervals up to 64 words are staged in shared memory
+constexpr unsigned long long WAIT_NS = 30ull * 1000000000ull;   // a wait longer than this aborts the call
+
+// Exchange area of one rank (cb_exchange_*): header, candidate slots, universe bit set, intervals.
+struct XHeader {
+    unsigned long long flag[CB_MAX_RANKS];        // flag[r]: last barrier epoch rank r announced to this rank
+    unsigned long long epoch;                     // barrier epoch this rank has reached (persists across calls)
+    unsigned long long pad[7];
+    unsigned long long key[2][CB_MAX_RANKS];      // list rebuild: best key among rank r's probes
+    uint32_t hist[2][CB_MAX_RANKS][64];           // list rebuild: level histogram of rank r's probes
+    uint32_t cand_n[2][CB_MAX_RANKS];             // active candidates of rank r this round
+};
+
+struct RParams {
+    int64_t n_probes;               // probes of the whole grouping (ids are global)
+    int64_t lo, hi;                 // this rank's probes
+    const int64_t *iv_off;          // [n_probes+1] local CSR (rows outside [lo, hi) are empty)
+    const uint32_t *rank_idx;       // [n_probes] dense rank of every probe (only [lo, hi) is read)
+    int32_t n_ranks_cover;          // number of distinct ranks (set_cover.py:349)
+    uint32_t *gain;                 // [n_probes]
+    unsigned long long *U;          // universe bit set of this rank (inside its exchange area)
+    unsigned long long *mark;       // [u_words+1]
+    int64_t u_words;
+    // interval index of the LOCAL probes: items bucketed by the 64-position block of their start
+    const int64_t *blk_off;         // [n_blocks+1]
+    const uint2 *items;             // x = start, y = len << pbits | probe
+    int64_t n_blocks;
+    uint32_t max_item_len;
+    int pbits;
+    // control
+    unsigned long long *remaining;  // uncovered bits still to cover (replicated)
+    unsigned long long *barrier;    // local arrival counter
+    unsigned long long *release;    // local release word of the cross-GPU barrier
+    unsigned long long *key_local;  // [2]
+    uint32_t *hist_local;           // [2][64]
+    uint32_t *list, *list_n, list_cap;
+    uint32_t *flag;                 // [list_cap]
+    long long *sel, *n_sel;
+    int *status;
+    unsigned long long *phase_ns;   // [4]
+    unsigned long long *ctr;        // [3]
+    // the ranks
+    int rank, n_ranks;
+    unsigned char *xa[CB_MAX_RANKS];       // exchange area of every rank, as mapped HERE
+    const uint2 *iv[CB_MAX_RANKS];         // cover intervals of every rank (inside its exchange area)
+    int64_t cand_off;                      // byte offset of the candidate slots in an exchange area
+};
+
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Spin until pred() holds; gives up (and flags the call as failed) after WAIT_NS, so that a rank that
+// never arrives turns into an error on the others instead of a hang.
+template <typename Pred>
+__device__ __forceinline__ bool spin_until(const RParams &G, Pred pred)
+{
+    if (pred()) return true;
+    const unsigned long long t0 = globaltimer_ns();
+    for (unsigned it = 1;; it++) {
+        if (pred()) return true;
+        if ((it & 0xfffu) == 0u) {
+            if (*(volatile int *)G.status != 0) return false;
+            if (globaltimer_ns() - t0 > WAIT_NS) {
+                atomicCAS(G.status, 0, CB_ERR_COMM);
+                return false;
+            }
+        }
+    }
+}
+
+// Grid barrier of this GPU: monotone arrival counter, one arrival per CTA.
+__device__ __forceinline__ void grid_barrier(const RParams &G, unsigned long long &target)
+{
+    __syncthreads();
+    target += gridDim.x;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(G.barrier, 1ull);
+        const unsigned long long want = target;
+        spin_until(G, [&] { return *(volatile unsigned long long *)G.barrier >= want; });
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// Cross-GPU barrier with a payload.  All CTAs of this GPU arrive; CTA 0 then runs payload()
+// (which stores this rank's contribution into the exchange area of every rank), announces the new
+// epoch to every peer and waits for theirs, and releases the other CTAs.  After the call the
+// contributions of ALL ranks for this epoch are visible in the local exchange area (read them with
+// __ldcg).  Slots are double-buffered by epoch parity: a rank can be at most one barrier ahead of
+// the slowest reader.
+template <typename Payload>
+__device__ __forceinline__ void xbarrier(const RParams &G, unsigned long long &target, unsigned long long &epoch,
+                                         Payload payload)
+{
+    __syncthreads();
+    target += gridDim.x;
+    epoch++;
+    const unsigned long long e = epoch;
+    if (blockIdx.x != 0) {
+        if (threadIdx.x == 0) {
+            __threadfence();
+            atomicAdd(G.barrier, 1ull);
+            spin_until(G, [&] { return ld_acquire_gpu(G.release) >= e; });
+        }
+        __syncthreads();
+        return;
+    }
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(G.barrier, 1ull);
+        const unsigned long long want = target;
+        spin_until(G, [&] { return *(volatile unsigned long long *)G.barrier >= want; });
+        __threadfence();
+    }
+    __syncthreads();
+    payload();
+    if (G.n_ranks > 1) {
+        __threadfence_system();
+        __syncthreads();
+        if ((int)threadIdx.x < G.n_ranks && (int)threadIdx.x != G.rank) {
+            XHeader *peer = reinterpret_cast<XHeader *>(G.xa[threadIdx.x]);
+            XHeader *mine = reinterpret_cast<XHeader *>(G.xa[G.rank]);
+            st_release_sys(&peer->flag[G.rank], e);
+            spin_until(G, [&] { return ld_acquire_sys(&mine->flag[threadIdx.x]) >= e; });
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        st_release_gpu(G.release, e);
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ uint4 *cand_slot(const RParams &G, int on_rank, unsigned slot, int from_rank)
+{
+    return reinterpret_cast<uint4 *>(G.xa[on_rank] + G.cand_off) + ((size_t)slot * CB_MAX_RANKS + from_rank) * G.list_cap;
+}
+
+template <typename F>
+__device__ __forceinline__ void for_each_word(uint2 r, F f)
+{
+    if (r.x >= r.y) return;
+    const uint32_t w0 = r.x >> 6, w1 = (r.y - 1) >> 6;
+    for (uint32_t w = w0; w <= w1; w++) {
+        unsigned long long m = ~0ull;
+        if (w == w0) m &= ~0ull << (r.x & 63);
+        if (w == w1) m &= ~0ull >> (63 - ((r.y - 1) & 63));
+        f(w, m);
+    }
+}
+
+__device__ __forceinline__ uint32_t popcount_range_cg(const unsigned long long *U, uint32_t s, uint32_t e)
+{
+    uint32_t c = 0;
+    for_each_word(make_uint2(s, e), [&](uint32_t w, unsigned long long m) { c += __popcll(__ldcg(U + w) & m); });
+    return c;
+}
+
+// apply() of ONE accepted interval r by ONE WARP: stage the interval's still-uncovered bits in the
+// warp's slice of shared memory, subtract the uncovered bits of every overlap from the gain of the
+// overlapping (local) interval's probe, then clear exactly the staged bits in this GPU's universe.
+// The indexed items that can overlap r are ONE contiguous range: every item whose start lies in
+// (r.x - max_item_len, r.y).  Reads stay inside the accepted interval and accepted intervals share no
+// word with uncovered bits, so no barrier separates "update gains" from "clear U".
+__device__ __forceinline__ void apply_interval_warp(const RParams &G, uint2 r, unsigned long long *s_uw, int lane)
+{
+    if (r.x >= r.y) return;
+    const uint32_t w0 = r.x >> 6, w1 = (r.y - 1) >> 6;
+    const uint32_t nwords = w1 - w0 + 1;
+    const int64_t lo_pos = (int64_t)r.x - (int64_t)G.max_item_len + 1;
+    const int64_t b_lo = (lo_pos > 0 ? lo_pos : 0) >> 6;
+    int64_t b_hi = ((int64_t)r.y - 1) >> 6;
+    if (b_hi >= G.n_blocks) b_hi = G.n_blocks - 1;
+    const uint32_t pmask = (1u << G.pbits) - 1u;
+    if (nwords > (uint32_t)APPLY_WORDS) {          // very long interval: count against L2, no staging
+        const int64_t x0 = __ldg(G.blk_off + b_lo), x1 = __ldg(G.blk_off + b_hi + 1);
+        for (int64_t x = x0 + lane; x < x1; x += 32) {
+            const uint2 item = __ldg(G.items + x);
+            const uint32_t os = max(item.x, r.x), oe = min(item.x + (item.y >> G.pbits), r.y);
+            if (os < oe) {
+                const uint32_t dlt = popcount_range_cg(G.U, os, oe);
+                if (dlt) atomicSub(&G.gain[item.y & pmask], dlt);
+            }
+        }
+        __syncwarp();
+        uint32_t c = 0;
+        for (uint32_t wd = w0 + lane; wd <= w1; wd += 32) {
+            unsigned long long m = ~0ull;
+            if (wd == w0) m &= ~0ull << (r.x & 63);
+            if (wd == w1) m &= ~0ull >> (63 - ((r.y - 1) & 63));
+            const unsigned long long old = atomicAnd(&G.U[wd], ~m);
+            c += __popcll(old & m);
+        }
+        if (c) atomicAdd(G.remaining, (unsigned long long)(-(long long)c));
+        __syncwarp();
+        return;
+    }
+    unsigned long long mine[APPLY_WORDS / 32];
+#pragma unroll
+    for (int h = 0; h < APPLY_WORDS / 32; h++) {
+        const uint32_t q = (uint32_t)lane + 32u * h;
+        mine[h] = 0ull;
+        if (q < nwords) {
+            unsigned long long m = ~0ull;
+            const uint32_t wd = w0 + q;
+            if (wd == w0) m &= ~0ull << (r.x & 63);
+            if (wd == w1) m &= ~0ull >> (63 - ((r.y - 1) & 63));
+            mine[h] = __ldcg(G.U + wd) & m;
+            s_uw[q] = mine[h];
+        }
+    }
+    bool have = false;
+#pragma unroll
+    for (int h = 0; h < APPLY_WORDS / 32; h++) have |= mine[h] != 0ull;
+    __syncwarp();                                   // the staged words are read by the other lanes below
+    if (!__any_sync(0xffffffffu, have)) return;    // everything here is covered already
+    const int64_t x0 = __ldg(G.blk_off + b_lo), x1 = __ldg(G.blk_off + b_hi + 1);
+    constexpr int BATCH = 8;
+    for (int64_t xb = x0 + lane; xb - lane < x1; xb += 32 * BATCH) {     // warp-uniform trip count
+        uint2 item[BATCH];
+#pragma unroll
+        for (int u = 0; u < BATCH; u++) {
+            const int64_t x = xb + (int64_t)u * 32;
+            item[u] = x < x1 ? __ldg(G.items + x) : make_uint2(0u, 0u);
+        }
+#pragma unroll
+        for (int u = 0; u < BATCH; u++) {
+            const uint32_t os = max(item[u].x, r.x), oe = min(item[u].x + (item[u].y >> G.pbits), r.y);
+            if (os < oe) {
+                const uint32_t wa = (os >> 6) - w0, wb = ((oe - 1) >> 6) - w0;
+                uint32_t dlt = 0;
+                for (uint32_t q = wa; q <= wb; q++) {
+                    unsigned long long m = ~0ull;
+                    if (q == wa) m &= ~0ull << (os & 63);
+                    if (q == wb) m &= ~0ull >> (63 - ((oe - 1) & 63));
+                    dlt += __popcll(s_uw[q] & m);
+                }
+                if (dlt) atomicSub(&G.gain[item[u].y & pmask], dlt);
+            }
+        }
+    }
+    // clear exactly the bits that were set (nobody else touches them)
+    uint32_t c = 0;
+#pragma unroll
+    for (int h = 0; h < APPLY_WORDS / 32; h++)
+        if (mine[h]) {
+            atomicAnd(&G.U[w0 + lane + 32u * h], ~mine[h]);
+            c += __popcll(mine[h]);
+        }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0 && c) atomicAdd(G.remaining, (unsigned long long)(-(long long)c));
+    __syncwarp();                                   // s_uw is reused by the warp's next interval
+}
+
+// ---- set-up, pass 1 over the local intervals: universe bits, block counts of the index, gains
+// (every bit of every interval is uncovered at the start, so gain = total length).  An interval
+// longer than max_piece is indexed as several consecutive pieces (gains are additive over pieces).
+template <bool SCATTER>
+__global__ void index_kernel(const int64_t *__restrict__ iv_off, const uint2 *__restrict__ iv, int64_t lo, int64_t hi,
+                             uint32_t max_piece, int pbits, unsigned long long *U, uint32_t *__restrict__ gain,
+                             uint32_t *__restrict__ count, const int64_t *__restrict__ blk_off,
+                             uint32_t *__restrict__ cursor, uint2 *__restrict__ items)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t p = lo + warp; p < hi; p += n_warps) {
+        uint32_t c = 0;
+        for (int64_t i = iv_off[p] + lane; i < iv_off[p + 1]; i += 32) {
+            const uint2 r = iv[i];
+            if (r.x >= r.y) continue;
+            if (!SCATTER) {
+                c += r.y - r.x;
+                for_each_word(r, [&](uint32_t w, unsigned long long m) {
+                    if ((U[w] & m) != m) atomicOr(&U[w], m);
+                });
+            }
+            for (uint32_t s = r.x; s < r.y; s += max_piece) {
+                const uint32_t len = min(max_piece, r.y - s);
+                const uint32_t b = s >> 6;
+                if (!SCATTER) atomicAdd(&count[b], 1u);
+                else {
+                    const uint32_t slot = atomicAdd(&cursor[b], 1u);
+                    items[blk_off[b] + slot] = make_uint2(s, (len << pbits) | (uint32_t)p);
+                }
+            }
+        }
+        if (!SCATTER) {
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+            if (lane == 0) gain[p] = c;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(RT, 3)
+greedy_rounds_kernel(const RParams G)
+{
+    __shared__ unsigned long long s_key[NWARP];
+    __shared__ unsigned long long s_u[NWARP * APPLY_WORDS];   // one staging area per warp
+    __shared__ uint32_t s_part[NWARP];
+    __shared__ uint32_t s_hist[64];                  // level histogram of a list rebuild
+    __shared__ uint32_t s_rn[CB_MAX_RANKS + 1];      // prefix of the per-rank candidate counts
+    extern __shared__ uint32_t s_dyn[];
+    // per CTA, list_cap entries each: active candidates (probe, gain, first interval, exclusive prefix
+    // of the interval counts, owner rank) and the winners among them (first interval, prefix, owner)
+    uint32_t *s_p = s_dyn, *s_g = s_p + G.list_cap, *s_i0 = s_g + G.list_cap, *s_base = s_i0 + G.list_cap,
+             *s_wi0 = s_base + G.list_cap + 1, *s_wbase = s_wi0 + G.list_cap;
+    unsigned char *s_own = reinterpret_cast<unsigned char *>(s_wbase + G.list_cap + 1), *s_wown = s_own + G.list_cap;
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t gsize = (int64_t)gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    XHeader *xh = reinterpret_cast<XHeader *>(G.xa[G.rank]);
+    const int R = G.n_ranks, me = G.rank;
+
+    // exclusive prefix of v over the CTA (thread order); adds the CTA total to `total`
+    auto block_scan = [&](uint32_t v, uint32_t &total) -> uint32_t {
+        uint32_t inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        __syncthreads();                 // s_part may still be read from the previous scan
+        if (lane == 31) s_part[warp] = inc;
+        __syncthreads();
+        uint32_t before = 0, all = 0;
+#pragma unroll
+        for (int q = 0; q < NWARP; q++) {
+            const uint32_t t = s_part[q];
+            if (q < warp) before += t;
+            all += t;
+        }
+        total += all;
+        return before + inc - v;
+    };
+    auto block_max = [&](unsigned long long best) -> unsigned long long {
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            const unsigned long long t = __shfl_xor_sync(0xffffffffu, best, o);
+            best = t > best ? t : best;
+        }
+        if (lane == 0) s_key[warp] = best;
+        __syncthreads();
+        best = lane < NWARP ? s_key[lane] : 0ull;
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            const unsigned long long t = __shfl_xor_sync(0xffffffffu, best, o);
+            best = t > best ? t : best;
+        }
+        __syncthreads();
+        return best;
+    };
+
+    int cur_rank = 0;
+    long long n_picks = 0;
+    unsigned long long bar_target = 0, n_rebuilds = 0, n_rounds = 0, n_active_sum = 0;
+    unsigned long long epoch = __ldcg(&xh->epoch);
+    uint32_t tau = 1, id_thr = 0xffffffffu;
+    unsigned rb = 0;
+    bool need_rebuild = true;
+    unsigned long long t_phase[4] = {0, 0, 0, 0}, t_last = 0;
+    const bool timing = (gtid == 0);
+    if (timing) t_last = globaltimer_ns();
+    auto lap = [&](int i) {
+        if (timing) {
+            const unsigned long long t = globaltimer_ns();
+            t_phase[i] += t - t_last;
+            t_last = t;
+        }
+    };
+    // CTA-uniform (a barrier inside): every thread of the CTA takes the same branch even if the status changes
+    // while it is being read
+    auto failed = [&]() -> bool { return __syncthreads_or(*(volatile int *)G.status != 0) != 0; };
+
+    // ---- prologue: the universe is the union of every rank's intervals (utils/set_cover.py:302-320).
+    // The set-up kernel ORed the local intervals into this rank's bit set; OR in the peers' words
+    // (monotone, so reading a word a peer is still completing is harmless) and count the bits.
+    xbarrier(G, bar_target, epoch, [] {});
+    {
+        unsigned long long c = 0;
+        for (int64_t w = gtid; w < G.u_words; w += gsize) {
+            unsigned long long v = __ldcg(G.U + w), mine = v;
+            for (int r = 0; r < R; r++)
+                if (r != me) v |= *(volatile const unsigned long long *)(G.xa[r] + ((const unsigned char *)G.U - G.xa[me]) + 8 * w);
+            if (v != mine) G.U[w] = v;
+            c += __popcll(v);
+        }
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if (lane == 0 && c) atomicAdd(G.remaining, c);
+    }
+    xbarrier(G, bar_target, epoch, [] {});           // nobody clears a bit while a peer may still read it
+
+    for (;;) {
+        if (failed()) break;
+        if (need_rebuild) {
+            // ---- largest key among the probes of the current rank, over all GPUs
+            unsigned long long best = 0;
+            for (int64_t p = G.lo + gtid; p < G.hi; p += gsize) {
+                const uint32_t g = __ldcg(&G.gain[p]);
+                if (g && G.rank_idx[p] == (uint32_t)cur_rank) {
+                    const unsigned long long key = ((unsigned long long)g << 32) | (unsigned long long)(0xffffffffu - (uint32_t)p);
+                    best = key > best ? key : best;
+                }
+            }
+            best = block_max(best);
+            const unsigned ks = rb & 1u;
+            rb++;
+            if (threadIdx.x == 0 && best) atomicMax(&G.key_local[ks], best);
+            if (gtid == 0) *G.list_n = 0;
+            xbarrier(G, bar_target, epoch, [&] {
+                if ((int)threadIdx.x < R) {
+                    XHeader *peer = reinterpret_cast<XHeader *>(G.xa[threadIdx.x]);
+                    peer->key[epoch & 1ull][me] = __ldcg(&G.key_local[ks]);
+                }
+            });
+            if (failed() || __ldcg(G.remaining) == 0ull) break;
+            unsigned long long key = 0ull;
+            for (int r = 0; r < R; r++) {
+                const unsigned long long k2 = __ldcg(&xh->key[epoch & 1ull][r]);
+                key = k2 > key ? k2 : key;
+            }
+            if (gtid == 0) G.key_local[ks ^ 1u] = 0ull;
+            if (key == 0ull) {                  // rank exhausted (:522-526)
+                cur_rank++;
+                if (cur_rank >= G.n_ranks_cover) {
+                    if (gtid == 0) atomicCAS(G.status, 0, CB_ERR_STATE);
+                    break;
+                }
+                grid_barrier(G, bar_target);
+                continue;
+            }
+            const uint32_t wmax = 0xffffffffu - (uint32_t)(key & 0xffffffffull);
+            const uint32_t gmax = (uint32_t)(key >> 32);
+            // ---- choose the list threshold from a histogram, so that the list holds as many of the
+            // top candidates as fit: gain levels tau_0 = 1, tau_s = gmax - (gmax >> s) (s = 1..12),
+            // tau_13 = gmax; and, should more probes than fit TIE at gmax, id levels
+            // "id < wmax + ceil((P - wmax) / 2^j)" among those ties (sequential greedy consumes ties from
+            // the low ids upwards, so the remaining ones sit in [wmax, P)).  Either way the list is a
+            // prefix of the key order.
+            auto tau_of = [&](int lv) -> uint32_t {
+                if (lv == 0) return 1u;
+                if (lv >= GAIN_LEVELS - 1) return gmax;
+                const uint32_t t = gmax - (gmax >> lv);
+                return t < 1u ? 1u : t;
+            };
+            auto idthr_of = [&](int j) -> unsigned long long {
+                const unsigned long long span = (unsigned long long)G.n_probes - (unsigned long long)wmax;
+                return (unsigned long long)wmax + ((span + (1ull << j) - 1ull) >> j);
+            };
+            if (threadIdx.x < 64) s_hist[threadIdx.x] = 0u;
+            __syncthreads();
+            for (int64_t p = G.lo + gtid; p < G.hi; p += gsize) {
+                const uint32_t g = __ldcg(&G.gain[p]);
+                if (g && G.rank_idx[p] == (uint32_t)cur_rank) {
+                    int lv = GAIN_LEVELS - 1;
+                    while (lv > 0 && g < tau_of(lv)) lv--;          // largest level the probe qualifies for
+                    atomicAdd(&s_hist[lv], 1u);
+                    if (g == gmax) {
+                        int j = 0;
+                        while (j + 1 < ID_LEVELS && (unsigned long long)p < idthr_of(j + 1)) j++;
+                        atomicAdd(&s_hist[GAIN_LEVELS + j], 1u);
+                    }
+                }
+            }
+            __syncthreads();
+            uint32_t *hist_now = G.hist_local + 64 * ks, *hist_next = G.hist_local + 64 * (ks ^ 1u);
+            if (threadIdx.x < 64 && s_hist[threadIdx.x]) atomicAdd(&hist_now[threadIdx.x], s_hist[threadIdx.x]);
+            xbarrier(G, bar_target, epoch, [&] {
+                if (threadIdx.x < 64) {
+                    const uint32_t v = __ldcg(&hist_now[threadIdx.x]);
+                    for (int r = 0; r < R; r++)
+                        reinterpret_cast<XHeader *>(G.xa[r])->hist[epoch & 1ull][me][threadIdx.x] = v;
+                }
+            });
+            if (failed()) break;
+            if (gtid < 64) hist_next[gtid] = 0u;                    // last read one rebuild ago
+            id_thr = 0xffffffffu;
+            {
+                auto level_count = [&](int i) -> uint32_t {
+                    uint32_t c = 0;
+                    for (int r = 0; r < R; r++) c += __ldcg(&xh->hist[epoch & 1ull][r][i]);
+                    return c;
+                };
+                // counts are suffix sums: a probe at level lv also qualifies for every wider level
+                uint32_t c = 0;
+                int pick = -1;
+                for (int lv = GAIN_LEVELS - 1; lv >= 0; lv--) {
+                    c += level_count(lv);
+                    if (c <= G.list_cap) pick = lv; else break;
+                }
+                if (pick >= 0) {
+                    tau = tau_of(pick);
+                } else {                                            // more ties at gmax than the list holds
+                    tau = gmax;
+                    c = 0;
+                    int pj = -1;
+                    for (int j = ID_LEVELS - 1; j >= 0; j--) {
+                        c += level_count(GAIN_LEVELS + j);
+                        if (c <= G.list_cap) pj = j; else break;
+                    }
+                    // the smallest tied id is wmax; an id level that holds no tie at all (or none that
+                    // fits) leaves the argmax alone in the list
+                    unsigned long long thr = pj >= 0 ? idthr_of(pj) : 0ull;
+                    if (thr <= (unsigned long long)wmax) thr = (unsigned long long)wmax + 1ull;
+                    id_thr = thr > 0xffffffffull ? 0xffffffffu : (uint32_t)thr;
+                }
+            }
+            for (int64_t p = G.lo + gtid; p < G.hi; p += gsize) {
+                const uint32_t g = __ldcg(&G.gain[p]);
+                if (g >= tau && (uint32_t)p < id_thr && G.rank_idx[p] == (uint32_t)cur_rank) {
+                    const uint32_t slot = atomicAdd(G.list_n, 1u);
+                    if (slot < G.list_cap) G.list[slot] = (uint32_t)p;      // always true, by the counts
+                }
+            }
+            need_rebuild = false;
+            n_rebuilds++;
+            lap(0);
+        }
+
+        // ---- exchange: CTA 0 compacts this rank's active candidates (list entries whose gain is still
+        // >= tau; gains are final, every CTA has arrived) and pushes them to every rank
+        xbarrier(G, bar_target, epoch, [&] {
+            const unsigned slot = (unsigned)(epoch & 1ull);
+            const uint32_t n_list = min(__ldcg(G.list_n), G.list_cap);
+            uint32_t n_mine = 0;
+            for (uint32_t c0 = 0; c0 < n_list; c0 += RT) {          // CTA-uniform
+                const uint32_t c = c0 + threadIdx.x;
+                uint32_t p = 0xffffffffu, g = 0;
+                if (c < n_list) {
+                    p = __ldcg(&G.list[c]);
+                    g = __ldcg(&G.gain[p]);
+                }
+                const bool act = p != 0xffffffffu && g >= tau;
+                const uint32_t before = n_mine;
+                const uint32_t pos = before + block_scan(act ? 1u : 0u, n_mine);
+                if (act) {
+                    const int64_t x = G.iv_off[p], y = G.iv_off[p + 1];
+                    const uint4 rec = make_uint4(p, g, (uint32_t)x, (uint32_t)(y - x));
+                    for (int r = 0; r < R; r++) cand_slot(G, r, slot, me)[pos] = rec;
+                }
+            }
+            if (threadIdx.x == 0)
+                for (int r = 0; r < R; r++) reinterpret_cast<XHeader *>(G.xa[r])->cand_n[slot][me] = n_mine;
+        });
+        if (failed() || __ldcg(G.remaining) == 0ull) break;
+        const unsigned slot = (unsigned)(epoch & 1ull);
+
+        // ---- every CTA loads the active candidates of ALL ranks (rank order, then list order) into
+        // its own shared memory: same inputs, same arrays everywhere
+        if (threadIdx.x == 0) {
+            uint32_t acc = 0;
+            for (int r = 0; r < R; r++) {
+                s_rn[r] = acc;
+                acc += min(__ldcg(&xh->cand_n[slot][r]), G.list_cap);
+            }
+            s_rn[R] = acc;
+        }
+        __syncthreads();
+        const uint32_t n_act = min(s_rn[R], G.list_cap);
+        if (n_act == 0u) {                       // the list is used up
+            need_rebuild = true;
+            continue;
+        }
+        uint32_t total_pairs = 0;
+        {
+            uint32_t cntv[PER];
+#pragma unroll
+            for (int u = 0; u < PER; u++) {
+                const uint32_t a = (uint32_t)u * RT + threadIdx.x;
+                cntv[u] = 0;
+                if (a < n_act) {
+                    int r = 0;
+                    while (r + 1 < R && s_rn[r + 1] <= a) r++;
+                    const uint4 rec = __ldcg(cand_slot(G, me, slot, r) + (a - s_rn[r]));
+                    s_p[a] = rec.x;
+                    s_g[a] = rec.y;
+                    s_i0[a] = rec.z;
+                    s_own[a] = (unsigned char)r;
+                    cntv[u] = rec.w;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < PER; u++) {
+                if ((uint32_t)u * RT >= n_act) break;           // CTA-uniform
+                const uint32_t a = (uint32_t)u * RT + threadIdx.x;
+                const uint32_t before = total_pairs;
+                const uint32_t pos = before + block_scan(cntv[u], total_pairs);
+                if (a < n_act) s_base[a] = pos;
+            }
+            if (threadIdx.x == 0) s_base[n_act] = total_pairs;
+            // the conflict flags of the previous round have been read by everybody (barrier since)
+            if (blockIdx.x == 0)
+                for (uint32_t a = threadIdx.x; a < G.list_cap; a += RT) G.flag[a] = 0u;
+            __syncthreads();
+        }
+        auto pair_of = [&](uint32_t f, uint32_t &a) -> uint2 {
+            uint32_t lo = 0, hi = n_act;
+            while (hi - lo > 1) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (s_base[mid] <= f) lo = mid; else hi = mid;
+            }
+            a = lo;
+            return G.iv[s_own[lo]][(int64_t)s_i0[lo] + (f - s_base[lo])];      // peer memory when the owner is remote
+        };
+        auto key_of = [&](uint32_t a) -> unsigned long long {
+            return ((unsigned long long)s_g[a] << 32) | (unsigned long long)(0xffffffffu - s_p[a]);
+        };
+
+        // ---- mark: one thread per (candidate, interval)
+        for (int64_t f = gtid; f < (int64_t)total_pairs; f += gsize) {
+            uint32_t a;
+            const uint2 r = pair_of((uint32_t)f, a);
+            const unsigned long long key = key_of(a);
+            for_each_word(r, [&](uint32_t w, unsigned long long m) {
+                if (__ldcg(G.U + w) & m) atomicMax(&G.mark[w], key);
+            });
+        }
+        grid_barrier(G, bar_target);
+
+        // ---- check
+        for (int64_t f = gtid; f < (int64_t)total_pairs; f += gsize) {
+            uint32_t a;
+            const uint2 r = pair_of((uint32_t)f, a);
+            const unsigned long long key = key_of(a);
+            bool conflict = false;
+            for_each_word(r, [&](uint32_t w, unsigned long long m) {
+                if ((__ldcg(G.U + w) & m) && __ldcg(G.mark + w) != key) conflict = true;
+            });
+            if (conflict) G.flag[a] = 1u;
+        }
+        grid_barrier(G, bar_target);
+        if (failed()) break;
+
+        // ---- winners = active candidates without a conflict (same compaction in every CTA)
+        uint32_t n_win = 0;
+        {
+            uint32_t fl[PER];
+#pragma unroll
+            for (int u = 0; u < PER; u++) {
+                const uint32_t a = (uint32_t)u * RT + threadIdx.x;
+                fl[u] = a < n_act ? __ldcg(&G.flag[a]) : 1u;
+            }
+            uint32_t wsum = 0;
+#pragma unroll
+            for (int u = 0; u < PER; u++) {
+                if ((uint32_t)u * RT >= n_act) break;           // CTA-uniform
+                const uint32_t a = (uint32_t)u * RT + threadIdx.x;
+                const bool win = fl[u] == 0u;
+                const uint32_t cnt = win ? s_base[a + 1] - s_base[a] : 0u;
+                const uint32_t before_n = n_win, before_s = wsum;
+                const uint32_t j = before_n + block_scan(win ? 1u : 0u, n_win);
+                const uint32_t base = before_s + block_scan(cnt, wsum);
+                if (win) {
+                    s_wi0[j] = s_i0[a];
+                    s_wown[j] = s_own[a];
+                    s_wbase[j] = base;
+                    if (blockIdx.x == 0) G.sel[n_picks + j] = (long long)key_of(a);
+                }
+            }
+            if (threadIdx.x == 0) s_wbase[n_win] = wsum;
+            __syncthreads();
+        }
+        lap(1);
+        n_rounds++;
+        n_active_sum += n_act;
+        n_picks += n_win;
+
+        // ---- reset the marks of this round
+        for (int64_t f = gtid; f < (int64_t)total_pairs; f += gsize) {
+            uint32_t a;
+            const uint2 r = pair_of((uint32_t)f, a);
+            for_each_word(r, [&](uint32_t w, unsigned long long) { G.mark[w] = 0ull; });
+        }
+        // ---- apply every accepted probe: (winner, interval) pairs are dealt round-robin to the warps
+        {
+            const uint32_t total = s_wbase[n_win];
+            for (uint32_t f = (uint32_t)warp * gridDim.x + blockIdx.x; f < total; f += gridDim.x * NWARP) {
+                uint32_t lo = 0, hi = n_win;
+                while (hi - lo > 1) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (s_wbase[mid] <= f) lo = mid; else hi = mid;
+                }
+                const uint2 r = G.iv[s_wown[lo]][(int64_t)s_wi0[lo] + (f - s_wbase[lo])];
+                apply_interval_warp(G, r, s_u + warp * APPLY_WORDS, lane);
+            }
+        }
+        lap(2);
+    }
+    if (gtid == 0) {
+        xh->epoch = epoch;
+        *G.n_sel = n_picks;
+        for (int i = 0; i < 4; i++) G.phase_ns[i] = t_phase[i];
+        G.ctr[0] = n_rebuilds;
+        G.ctr[1] = n_rounds;
+        G.ctr[2] = n_active_sum;
+    }
+}
+
+size_t cand_bytes(uint32_t list_cap) { return sizeof(uint4) * 2 * CB_MAX_RANKS * (size_t)list_cap; }
+size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace
+
+// Bytes of exchange area the set cover over `cover` needs on this rank.
+int64_t cb_rounds_exchange_bytes(const cb_cover *cover)
+{
+    const size_t u_words = (size_t)(cover->universe_bits >> 6) + 1;
+    return (int64_t)(align_up(sizeof(XHeader)) + align_up(cand_bytes(LIST_CAP_MAX)) + align_up(8 * u_words) +
+                     align_up(sizeof(uint2) * (size_t)(cover->n_intervals ? cover->n_intervals : 1)));
+}
+
+// `cover` holds the intervals of probes [lo, hi) of a grouping of cover->n_probes probes (rows outside
+// are empty).  With ctx->xn_ranks > 1 every rank of the exchange group must make this call with its
+// own shard; all of them receive the same picks.
+int cb_setcover_rounds_impl(cb_ctx *ctx, const cb_cover *cover, int64_t lo, int64_t hi, const int32_t *ranks,
+                            bool sharded, int64_t *sel_ids, int64_t *n_sel, cb_stats *stats)
+{
+    cudaStream_t st = ctx->stream;
+    const int64_t P = cover->n_probes, E = cover->n_intervals;
+    const int R = sharded ? ctx->xn_ranks : 1, me = sharded ? ctx->xrank : 0;
+    if (lo < 0 || hi < lo || hi > P) return cb_fail(ctx, CB_ERR_ARG, "bad probe range");
+    if (sharded && ctx->xarea_poisoned)
+        return cb_fail(ctx, CB_ERR_STATE, "an earlier sharded call failed; attach the exchange areas again");
+    if (P >= (1ll << 25)) return cb_fail(ctx, CB_ERR_UNSUPPORTED, "more than 2^25 probes in one grouping");
+    if (E >= 0xfffffff0ll) return cb_fail(ctx, CB_ERR_UNSUPPORTED, "more than 2^32 intervals in one grouping");
+    EventTimer t_all(st), t_uni(st), t_greedy(st);
+    t_all.start();
+    t_uni.start();
+    const int wide = ctx->sm_count * 8;
+    const int64_t u_words = cover->universe_bits >> 6;
+    const int64_t n_blocks = u_words + 1;
+
+    uint32_t list_cap = 2048u;                    // <= LIST_CAP_MAX; 2048 leaves room for 3 CTAs per SM
+    if (const char *e = getenv("CB_GREEDY_LIST_CAP")) {
+        const int v = atoi(e);
+        if (v >= 1 && v <= LIST_CAP_MAX) list_cap = (uint32_t)v;
+    }
+
+    // ---- exchange area: the context's shared one when sharded, a work buffer otherwise
+    const size_t off_cand = align_up(sizeof(XHeader));
+    const size_t off_U = off_cand + align_up(cand_bytes(LIST_CAP_MAX));
+    const size_t off_iv = off_U + align_up(8 * ((size_t)u_words + 1));
+    const size_t need = off_iv + align_up(sizeof(uint2) * (size_t)(E ? E : 1));
+    DevBuf<unsigned char> d_area;
+    unsigned char *area = nullptr;
+    if (sharded) {
+        if (R < 2 || !ctx->xarea) return cb_fail(ctx, CB_ERR_STATE, "cb_exchange_attach has not been called");
+        if (need > ctx->xarea_bytes) return cb_fail(ctx, CB_ERR_STATE, "exchange area too small (cb_exchange_alloc)");
+        area = ctx->xarea;
+    } else {
+        CB_CUDA(ctx, d_area.alloc(off_iv));            // intervals stay where they are
+        area = d_area.p;
+        CB_CUDA(ctx, cudaMemsetAsync(area, 0, sizeof(XHeader), st));
+    }
+    unsigned long long *d_U = reinterpret_cast<unsigned long long *>(area + off_U);
+    CB_CUDA(ctx, cudaMemsetAsync(d_U, 0, 8 * ((size_t)u_words + 1), st));
+    const uint2 *d_iv_mine = cover->d_iv;
+    if (sharded) {
+        if (E) CB_CUDA(ctx, cudaMemcpyAsync(area + off_iv, cover->d_iv, sizeof(uint2) * (size_t)E, cudaMemcpyDeviceToDevice, st));
+        d_iv_mine = reinterpret_cast<const uint2 *>(area + off_iv);
+    }
+
+    // ---- ranks -> dense indices in ascending order of rank value (:349)
+    std::vector<uint32_t> h_rank;
+    int32_t n_ranks = 1;
+    DevBuf<uint32_t> d_rank;
+    CB_CUDA(ctx, d_rank.alloc((size_t)(P ? P : 1)));
+    if (ranks) {
+        h_rank.assign((size_t)P, 0u);
+        std::vector<int32_t> vals(ranks, ranks + P);
+        std::sort(vals.begin(), vals.end());
+        vals.erase(std::unique(vals.begin(), vals.end()), vals.end());
+        n_ranks = (int32_t)vals.size();
+        for (int64_t p = 0; p < P; p++)
+            h_rank[(size_t)p] = (uint32_t)(std::lower_bound(vals.begin(), vals.end(), ranks[p]) - vals.begin());
+        CB_CUDA(ctx, cudaMemcpyAsync(d_rank.p, h_rank.data(), sizeof(uint32_t) * (size_t)P, cudaMemcpyHostToDevice, st));
+    } else {
+        CB_CUDA(ctx, cudaMemsetAsync(d_rank.p, 0, sizeof(uint32_t) * (size_t)(P ? P : 1), st));
+    }
+
+    // ---- work buffers
+    int pbits = 1;
+    while ((1ll << pbits) < P) pbits++;
+    const uint32_t max_piece = (1u << (32 - pbits)) - 1u;
+    DevBuf<uint32_t> d_gain, d_bcount, d_bcursor, d_small;
+    DevBuf<unsigned long long> d_mark, d_ctl;
+    DevBuf<long long> d_sel;
+    DevBuf<int64_t> d_boff;
+    DevBuf<uint2> d_items;
+    CB_CUDA(ctx, d_gain.alloc((size_t)(P ? P : 1)));
+    CB_CUDA(ctx, cudaMemsetAsync(d_gain.p, 0, sizeof(uint32_t) * (size_t)(P ? P : 1), st));
+    CB_CUDA(ctx, d_bcount.alloc((size_t)n_blocks));
+    CB_CUDA(ctx, d_bcursor.alloc((size_t)n_blocks));
+    CB_CUDA(ctx, d_boff.alloc((size_t)n_blocks + 1));
+    CB_CUDA(ctx, cudaMemsetAsync(d_bcount.p, 0, sizeof(uint32_t) * (size_t)n_blocks, st));
+    CB_CUDA(ctx, cudaMemsetAsync(d_bcursor.p, 0, sizeof(uint32_t) * (size_t)n_blocks, st));
+    CB_CUDA(ctx, d_mark.alloc((size_t)u_words + 1));
+    CB_CUDA(ctx, cudaMemsetAsync(d_mark.p, 0, 8 * ((size_t)u_words + 1), st));
+    // control block: [0] remaining, [1] barrier, [2] release, [3..4] key_local, [5..8] phase ns, [9..11] counters,
+    // [12] n_sel, [13] status
+    CB_CUDA(ctx, d_ctl.alloc(16));
+    CB_CUDA(ctx, cudaMemsetAsync(d_ctl.p, 0, 8 * 16, st));
+    // small u32 block: list[list_cap], list_n, flag[list_cap], hist_local[128]
+    CB_CUDA(ctx, d_small.alloc(2 * (size_t)list_cap + 1 + 128));
+    CB_CUDA(ctx, cudaMemsetAsync(d_small.p, 0, sizeof(uint32_t) * (2 * (size_t)list_cap + 1 + 128), st));
+    CB_CUDA(ctx, d_sel.alloc((size_t)(P ? P : 1)));
+
+    // ---- set-up: universe bits + block counts + gains, offsets, index items
+    index_kernel<false><<<wide, 256, 0, st>>>(cover->d_iv_off, cover->d_iv, lo, hi, max_piece, pbits, d_U, d_gain.p,
+                                              d_bcount.p, nullptr, nullptr, nullptr);
+    ctx->launches++;
+    int64_t n_items = 0;
+    CB_TRY(cb_exclusive_scan_u32_to_i64(ctx, d_bcount.p, d_boff.p, n_blocks, &n_items));
+    if (n_items >= 0xfffffff0ll) return cb_fail(ctx, CB_ERR_UNSUPPORTED, "more than 2^32 index items");
+    CB_CUDA(ctx, d_items.alloc((size_t)(n_items ? n_items : 1)));
+    index_kernel<true><<<wide, 256, 0, st>>>(cover->d_iv_off, cover->d_iv, lo, hi, max_piece, pbits, nullptr, nullptr,
+                                             nullptr, d_boff.p, d_bcursor.p, d_items.p);
+    ctx->launches++;
+    CB_CUDA(ctx, cudaGetLastError());
+    t_uni.stop();
+
+    RParams G;
+    memset(&G, 0, sizeof G);
+    G.n_probes = P;
+    G.lo = lo;
+    G.hi = hi;
+    G.iv_off = cover->d_iv_off;
+    G.rank_idx = d_rank.p;
+    G.n_ranks_cover = n_ranks;
+    G.gain = d_gain.p;
+    G.U = d_U;
+    G.mark = d_mark.p;
+    G.u_words = u_words;
+    G.blk_off = d_boff.p;
+    G.items = d_items.p;
+    G.n_blocks = n_blocks;
+    G.max_item_len = std::min(cover->max_interval_len, max_piece);
+    G.pbits = pbits;
+    G.remaining = d_ctl.p;
+    G.barrier = d_ctl.p + 1;
+    G.release = d_ctl.p + 2;
+    G.key_local = d_ctl.p + 3;
+    G.phase_ns = d_ctl.p + 5;
+    G.ctr = d_ctl.p + 9;
+    G.n_sel = reinterpret_cast<long long *>(d_ctl.p + 12);
+    G.status = reinterpret_cast<int *>(d_ctl.p + 13);
+    G.list = d_small.p;
+    G.list_n = d_small.p + list_cap;
+    G.list_cap = list_cap;
+    G.flag = d_small.p + list_cap + 1;
+    G.hist_local = d_small.p + 2 * list_cap + 1;
+    G.sel = d_sel.p;
+    G.rank = me;
+    G.n_ranks = R;
+    G.cand_off = (int64_t)off_cand;
+    for (int r = 0; r < R; r++) {
+        G.xa[r] = sharded ? ctx->xpeer[r] : area;
+        G.iv[r] = sharded ? reinterpret_cast<const uint2 *>(ctx->xpeer[r] + off_iv) : d_iv_mine;
+    }
+    G.xa[me] = area;
+    G.iv[me] = d_iv_mine;
+
+    // ---- persistent cooperative launch
+    const size_t dyn_smem = sizeof(uint32_t) * (6 * (size_t)list_cap + 2) + 2 * (size_t)list_cap;
+    int per_sm = 0;
+    CB_CUDA(ctx, cudaFuncSetAttribute(greedy_rounds_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+    CB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, greedy_rounds_kernel, RT, dyn_smem));
+    if (per_sm < 1) return cb_fail(ctx, CB_ERR_CUDA, "greedy kernel does not fit on an SM");
+    int want = 3;
+    if (const char *e = getenv("CB_GREEDY_BLOCKS_PER_SM")) want = atoi(e) > 0 ? atoi(e) : want;
+    if (per_sm > want) per_sm = want;
+    int grid = per_sm * ctx->sm_count;
+    if (ctx->xgrid_limit > 0 && grid > ctx->xgrid_limit) grid = ctx->xgrid_limit;   // several ranks on one device (tests)
+    void *args[] = {(void *)&G};
+    t_greedy.start();
+    CB_CUDA(ctx, cudaLaunchCooperativeKernel((void *)greedy_rounds_kernel, dim3(grid), dim3(RT), args, dyn_smem, st));
+    ctx->launches++;
+    t_greedy.stop();
+    t_all.stop();
+
+    unsigned long long h_ctl[16];
+    CB_CUDA(ctx, cudaMemcpyAsync(h_ctl, d_ctl.p, sizeof h_ctl, cudaMemcpyDeviceToHost, st));
+    CB_CUDA(ctx, cudaStreamSynchronize(st));
+    const long long h_nsel = (long long)h_ctl[12];
+    const int h_status = (int)(uint32_t)h_ctl[13];
+    if (h_status == CB_ERR_COMM) {
+        ctx->xarea_poisoned = sharded;
+        return cb_fail(ctx, CB_ERR_COMM, "set cover: a rank did not arrive at a barrier within the time limit");
+    }
+    if (h_status != 0) return cb_fail(ctx, CB_ERR_STATE, "set cover ran out of ranks before reaching the requested coverage");
+    *n_sel = 0;
+    if (h_nsel > 0) {
+        static_assert(sizeof(long long) == sizeof(int64_t), "int64");
+        CB_CUDA(ctx, cudaMemcpyAsync(sel_ids, d_sel.p, sizeof(int64_t) * (size_t)h_nsel, cudaMemcpyDeviceToHost, st));
+        CB_CUDA(ctx, cudaStreamSynchronize(st));
+        // the kernel reports each pick's key at pick time, (gain << 32) | (2^32-1 - id), in no
+        // particular order inside a round; the sequential loop picks rank by rank and, inside a
+        // rank, in strictly decreasing key order
+        uint64_t *keys = reinterpret_cast<uint64_t *>(sel_ids);
+        auto id_of = [](uint64_t k) { return (int64_t)(0xffffffffu - (uint32_t)(k & 0xffffffffull)); };
+        if (n_ranks > 1)
+            std::sort(keys, keys + h_nsel, [&](uint64_t a, uint64_t b) {
+                const uint32_t ra = h_rank[(size_t)id_of(a)], rb = h_rank[(size_t)id_of(b)];
+                return ra != rb ? ra < rb : a > b;
+            });
+        else
+            std::sort(keys, keys + h_nsel, [](uint64_t a, uint64_t b) { return a > b; });
+        for (long long i = 0; i < h_nsel; i++) sel_ids[i] = id_of(keys[i]);
+    }
+    *n_sel = h_nsel;
+    if (stats) {
+        stats->ms_universe = t_uni.ms();
+        stats->ms_greedy = t_greedy.ms();
+        stats->ms_total = t_all.ms();
+        stats->n_picks = h_nsel;
+        stats->n_intervals = E;
+        stats->n_kernel_launches = ctx->launches;
+        for (int i = 0; i < 4; i++) stats->reserved[i] = (int64_t)h_ctl[5 + i];   // ns: list rebuilds, exchange+mark+check, apply, -
+        stats->reserved[4] = (int64_t)h_ctl[9];      // candidate-list rebuilds
+        stats->reserved[5] = (int64_t)h_ctl[10];     // rounds
+        stats->reserved[6] = (int64_t)h_ctl[11];     // active candidates summed over the rounds
+        stats->reserved[7] = n_items;
+    }
+    return CB_OK;
+}

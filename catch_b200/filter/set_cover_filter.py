@@ -371,46 +371,95 @@ class SetCoverFilter(BaseFilter):
         return mode == 'probes' or n_groups < world_size
 
     def _filter_probe_sharded(self, input, target_genomes_grouped, rank, world_size):
-        """Every rank works on every grouping: stage A on its block of the probes, all-gather of the
-        coverage over NCCL, then the (identical) greedy selection on every rank."""
+        """Every rank works on every grouping: stage A on its block of the probes, then the
+        greedy loop with gains and interval index sharded and one exchange per round between the GPUs
+        (cb_setcover_sharded); every rank ends up with the same picks.  Groupings that need p_u < 1 take
+        the all-gather of the coverage and a replicated greedy instead."""
         ctx = self._context()
-        parallel.ensure_comm(ctx)
         selected = []
         for group_i, (possible_probes, target_genomes) in enumerate(zip(input, target_genomes_grouped)):
-            possible_probes = list(possible_probes)
-            probe_strs = [p.seq_str for p in possible_probes]
+            if not isinstance(possible_probes, (list, tuple)):
+                possible_probes = list(possible_probes)
+            n_probes = len(possible_probes)
             t0 = time.perf_counter()
-            stats = {'group': group_i, 'n_probes': len(probe_strs), 'shard': 'probes',
+            stats = {'group': group_i, 'n_probes': n_probes, 'shard': 'probes',
                      'target_bp': sum(g.size() for g in target_genomes)}
             self.last_stats[group_i] = stats
-            if not probe_strs:
+            if n_probes == 0:
                 selected.append([])
                 continue
-            plan = cov.SeedPlan(probe_strs, self.mismatches, self.lcf_thres, self.kmer_probe_map_k)
-            lo, hi = parallel.shard_bounds(len(probe_strs), world_size, rank)
-            group = cov.PackedGroup(ctx, probe_strs[lo:hi], target_genomes)
+            lo, hi = parallel.shard_bounds(n_probes, world_size, rank)
+            token = parallel.rng_state_token()
+            local = group = None
+            failure = None
+            universe_p = self._make_universe_p(target_genomes)
+            sharded_b = bool(np.all(universe_p == 1.0))
             try:
-                so = plan.seed_off[lo:hi + 1] - plan.seed_off[lo]
-                sp = plan.seed_pos[plan.seed_off[lo]:max(plan.seed_off[hi], plan.seed_off[lo] + 1)]
-                local, st_a = ctx.coverage(group.probes, group.targets, self.mismatches, self.lcf_thres,
-                                           self.island_of_exact_match, self.cover_extension, plan.k,
-                                           np.ascontiguousarray(so), np.ascontiguousarray(sp))
+                # the draw consumes the RNG for ALL probes on every rank (same stream everywhere, and the
+                # stream ends where a single process would leave it); each rank uses its own rows
+                guess = len(possible_probes[0].seq_str)
+                try:
+                    drawn = cov.draw_seeds(np.full(n_probes, guess, dtype=np.int32), self.mismatches,
+                                           self.lcf_thres, self.kmer_probe_map_k, background=True)
+                except ValueError:
+                    drawn = None
+                try:
+                    gathered = cov.gather_staged(ctx, 0, possible_probes)
+                    if gathered is None:
+                        gathered = cov.gather_probes(possible_probes)
+                except BaseException:
+                    if drawn is not None:
+                        cov.cancel_draw(drawn)
+                    raise
+                lengths = gathered[1]
+                if drawn is None or not bool(np.all(lengths == guess)):
+                    if drawn is not None:
+                        cov.cancel_draw(drawn)
+                    drawn = cov.draw_seeds(lengths, self.mismatches, self.lcf_thres, self.kmer_probe_map_k,
+                                           background=True)
+                try:
+                    group = cov.PackedGroup(ctx, possible_probes, target_genomes, gathered=gathered)
+                    dups = ctx.probes_have_duplicates(group.probes)
+                finally:
+                    drawn = cov.finish_draw(drawn)
+                plan = cov.SeedPlan(_LazyStrs(possible_probes), self.mismatches, self.lcf_thres,
+                                    self.kmer_probe_map_k, lengths=lengths, may_have_dups=dups, drawn=drawn)
+                local, st_a = cov.compute_cover_range(ctx, group, plan, self.mismatches, self.lcf_thres,
+                                                      self.island_of_exact_match, self.cover_extension, lo, hi)
+            except Exception as e:
+                failure = e
             finally:
-                group.free()
+                if group is not None:
+                    group.free()
             try:
-                cover = ctx.cover_allgather(local, lo, len(probe_strs))
+                # collective from here on; a rank that failed above says so and everybody raises
+                need = ctx.exchange_required(local) if (failure is None and sharded_b) else 0
+                try:
+                    parallel.ensure_exchange(ctx, need, token, failed=failure is not None)
+                except RuntimeError:
+                    if failure is not None:
+                        raise failure
+                    raise
+                if sharded_b:
+                    picks, st_b = ctx.setcover_sharded(local, n_probes, lo, hi)
+                else:
+                    parallel.ensure_comm(ctx)
+                    cover = ctx.cover_allgather(local, lo, n_probes)
+                    try:
+                        picks, st_b = ctx.setcover(cover, n_probes, None, universe_p)
+                    finally:
+                        cover.free()
             finally:
-                local.free()
-            try:
-                picks, st_b = ctx.setcover(cover, len(probe_strs), None, self._make_universe_p(target_genomes))
-            finally:
-                cover.free()
+                if local is not None:
+                    local.free()
             chosen = set()
             for i in picks.tolist():
                 chosen.add(i)
             chosen = pickle.loads(pickle.dumps(chosen))
             selected.append([possible_probes[i] for i in chosen])
-            stats.update(seed_mode=plan.mode, k=plan.k, bits=group.bits, h2d_bytes=group.h2d_bytes,
+            seed_bytes = int(plan.uniform[lo:hi].nbytes) if plan.uniform is not None else \
+                int(plan.seed_pos.nbytes + plan.seed_off.nbytes)
+            stats.update(seed_mode=plan.mode, k=plan.k, bits=group.bits, h2d_bytes=group.h2d_bytes + seed_bytes,
                          d2h_bytes=int(picks.nbytes), picks=picks, upload_targets=group.st_targets.as_dict(),
                          upload_probes=group.st_probes.as_dict(), coverage=st_a.as_dict(),
                          setcover=st_b.as_dict(), wall_s=time.perf_counter() - t0)

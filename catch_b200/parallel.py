@@ -141,3 +141,45 @@ def ensure_comm(ctx):
     box = [ctx.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(box, src=0)
     ctx.comm_init(box[0], rank, world_size)
+
+
+def ensure_exchange(ctx, need_bytes, token=0, failed=False):
+    """Collective over all ranks, once per sharded set cover: make every rank's exchange area (the
+    peer-mapped memory of cb_setcover_sharded) at least as large as the largest `need_bytes` of any
+    rank, mapping all areas again when one had to grow.  The same small all-reduce carries two
+    checks: `token` (a checksum of host state that must be identical on every rank, e.g. of numpy's
+    RNG state the seed draws came from) and `failed` (this rank hit an error and will raise after
+    the exchange), so that a rank-local problem turns into an exception on EVERY rank instead of
+    leaving the others waiting in the kernel's barrier."""
+    dist = _dist()
+    if dist is None:
+        raise RuntimeError("probe sharding needs an initialised torch.distributed process group")
+    torch = sys.modules['torch']
+    rank, world_size = dist.get_rank(), dist.get_world_size()
+    token = int(token) & 0x3fffffffffffffff
+    t = torch.tensor([int(need_bytes), token, -token, 1 if failed else 0], dtype=torch.int64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)          # CPU tensor: gloo
+    need, tmax, tmin, any_failed = int(t[0]), int(t[1]), -int(t[2]), int(t[3])
+    if any_failed:
+        raise RuntimeError("a rank failed before the sharded set cover" + (" (this one)" if failed else ""))
+    if tmax != tmin:
+        raise RuntimeError("ranks disagree on the host state the seed draws depend on (numpy RNG state); "
+                           "seed np.random identically on every rank before calling the filter")
+    if getattr(ctx, 'exchange_ready', False) and ctx.exchange_bytes() >= need and \
+            getattr(ctx, 'exchange_n_ranks', 0) == world_size:
+        return
+    ctx.exchange_alloc(max(need + need // 2, 64 << 20))
+    handle, _ = ctx.exchange_handle()
+    handles = [None] * world_size
+    dist.all_gather_object(handles, handle)
+    ctx.exchange_attach(rank, world_size, handles=handles)
+    # nobody launches a sharded kernel before every rank has zeroed and mapped its area
+    dist.barrier()
+
+
+def rng_state_token():
+    """64-bit checksum of numpy's legacy global RNG state (see ensure_exchange)."""
+    import zlib
+    import numpy as np
+    name, key, pos, has_gauss, cached = np.random.get_state()
+    return (zlib.crc32(key.tobytes()) << 20) ^ (int(pos) << 1) ^ int(has_gauss)

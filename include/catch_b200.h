@@ -41,6 +41,7 @@ enum cb_status {
 #define CB_MAX_PROBE_LEN 256     /* bases per probe */
 #define CB_MAX_SYMBOL_BITS 8     /* bit planes per base */
 #define CB_MAX_MISMATCHES 31
+#define CB_MAX_RANKS 8           /* GPUs of one box that can share a sharded set cover */
 
 /* Hybridisation model parameters: probe.py:1274-1346
  * probe_covers_sequence_by_longest_common_substring(mismatches, lcf_thres, island). */
@@ -175,6 +176,14 @@ int cb_coverage(cb_ctx *ctx, const cb_probes *probes, const cb_targets *targets,
 int cb_coverage_uniform(cb_ctx *ctx, const cb_probes *probes, const cb_targets *targets,
                         const cb_hyb_params *params, const uint8_t *seed_pos, int32_t seeds_per_probe,
                         cb_cover **out, cb_stats *stats);
+/* The general form, used by the probe-sharded multi-GPU path: exactly one of (seed_off, seed_pos) and
+ * seed_pos_u8 is given, and only the probes [probe_lo, probe_hi) are scanned (probe_hi < 0: all).  The
+ * uniform byte matrix then holds probe_hi - probe_lo rows, the first one for probe_lo; the CSR form keeps
+ * its n_probes + 1 offsets.  The cover keeps GLOBAL probe ids: rows outside the range are empty. */
+int cb_coverage_range(cb_ctx *ctx, const cb_probes *probes, const cb_targets *targets,
+                      const cb_hyb_params *params, const int64_t *seed_off, const int32_t *seed_pos,
+                      const uint8_t *seed_pos_u8, int32_t seeds_per_probe, int64_t probe_lo, int64_t probe_hi,
+                      cb_cover **out, cb_stats *stats);
 void cb_cover_free(cb_cover *c);
 
 /* Number of merged (probe, genome, start, end) intervals held by a cover. */
@@ -221,6 +230,35 @@ int cb_comm_init(cb_ctx *ctx, const uint8_t id[128], int32_t rank, int32_t n_ran
 int cb_comm_destroy(cb_ctx *ctx);
 int cb_cover_allgather(cb_ctx *ctx, const cb_cover *local, int64_t probe_lo, int64_t n_probes_total,
                        cb_cover **out);
+
+/* ---- multi-GPU: sharded set cover (the reference loop is utils/set_cover.py:448-613) --
+ * The candidate probes of ONE grouping are sharded over the GPUs of a box; every rank holds the cover
+ * of its own probes only (cb_coverage_range), its gains and its interval index, plus a replica of
+ * the universe bit set.  The greedy loop runs as one persistent kernel per GPU; once per round the
+ * kernels exchange their active candidates through peer-mapped memory (stores and loads over
+ * NVLink inside the kernel, no host involvement), see csrc/rounds.cu.
+ *
+ * Set-up, once per process group (or whenever a larger area is needed):
+ *   cb_exchange_alloc    (re)allocates this rank's exchange area (cudaMalloc, zeroed);
+ *   cb_exchange_handle   returns its CUDA IPC handle (64 bytes) and its device address;
+ *   cb_exchange_attach   maps the areas of all ranks: `handles` = n_ranks * 64 bytes gathered from all
+ *                        ranks (one process per GPU), or `addresses` = n_ranks device pointers when the
+ *                        ranks are contexts of ONE process (tests: several ranks on one device; then
+ *                        grid_limit > 0 caps each rank's persistent grid so that all fit together).
+ *                        The caller must put a barrier between the attach calls and the first
+ *                        cb_setcover_sharded.
+ *   cb_exchange_required bytes a cover needs in the area (the maximum over ranks must fit everywhere).
+ * cb_setcover_sharded is collective: every rank calls it with the cover of its own probes
+ * [probe_lo, probe_hi) (global ids, universe_p == 1, unit costs) and receives the same picks in pick
+ * order.  A rank that does not arrive within 30 s makes the others fail with CB_ERR_COMM. */
+int cb_exchange_alloc(cb_ctx *ctx, int64_t bytes);
+int64_t cb_exchange_bytes(cb_ctx *ctx);
+int cb_exchange_handle(cb_ctx *ctx, uint8_t out[64], uint64_t *address);
+int cb_exchange_attach(cb_ctx *ctx, int32_t rank, int32_t n_ranks, const uint8_t *handles,
+                       const uint64_t *addresses, int32_t grid_limit);
+int cb_exchange_required(cb_ctx *ctx, const cb_cover *cover, int64_t *bytes);
+int cb_setcover_sharded(cb_ctx *ctx, const cb_cover *cover, int64_t probe_lo, int64_t probe_hi,
+                        const int32_t *ranks, int64_t *sel_ids, int64_t *n_sel, cb_stats *stats);
 
 /* ---- near-duplicate filter (K9-K12) --------------------------------------------------
  * Replaces NearDuplicateFilter._filter (filter/near_duplicate_filter.py:47-103) with

@@ -182,9 +182,9 @@ def test_limits_are_reported(ctx):
         SetCoverFilter(40, 30).filter([[probe.Probe.from_str('ACGT' * 25)]], g, input_is_grouped=True)
 
 
-@pytest.mark.parametrize('mode,cap', [('par', None), ('par', '1'), ('par', '3'), ('inc', None), ('legacy', None)])
+@pytest.mark.parametrize('mode,cap', [('par', None), ('par', '1'), ('par', '3'), ('legacy', None)])
 def test_greedy_kernels_agree_with_oracle(ctx, monkeypatch, mode, cap):
-    """The three greedy kernels (parallel rounds, one pick per rendezvous, recompute-everything) give
+    """Both greedy kernels (parallel rounds, csrc/rounds.cu; one pick per iteration, csrc/setcover.cu) give
     the oracle's pick SEQUENCE; a tiny candidate list forces the overflow and rebuild paths of the
     parallel-rounds kernel."""
     O = _oracle()
@@ -208,7 +208,7 @@ def test_greedy_kernels_agree_with_oracle(ctx, monkeypatch, mode, cap):
 
 def test_parallel_rounds_at_scale(ctx, monkeypatch):
     """Size-independent check at a size the oracle would take minutes for: the parallel-rounds
-    kernel and the one-pick-per-rendezvous kernel give the same pick sequence, and the selection
+    kernel and the one-pick-per-iteration kernel give the same pick sequence, and the selection
     covers every universe bit."""
     from catch_b200 import coverage as cov
     seqs = helpers.synthetic_genomes(120, 6000, 0.03, seed=5)
@@ -219,11 +219,11 @@ def test_parallel_rounds_at_scale(ctx, monkeypatch):
     cover, _ = cov.compute_cover(ctx, group, plan, 2, 60, 0, 50)
     group.free()
     res = {}
-    for mode in ('par', 'inc'):
+    for mode in ('par', 'legacy'):
         monkeypatch.setenv('CB_GREEDY', mode)
         res[mode], st = ctx.setcover(cover, len(cands), None, None)
     assert len(res['par']) > 50
-    assert res['par'].tolist() == res['inc'].tolist()
+    assert res['par'].tolist() == res['legacy'].tolist()
     pid, gen, s, e = ctx.cover_export(cover)
     cover.free()
     chosen = np.zeros(len(cands), dtype=bool)
@@ -278,7 +278,7 @@ def test_parallel_rounds_tie_heavy_regime(ctx, monkeypatch):
     assert plan.mode == 'pigeonhole'
     cover, _ = cov.compute_cover(ctx, group, plan, 0, 100, 0, 50)
     group.free()
-    monkeypatch.setenv('CB_GREEDY', 'inc')
+    monkeypatch.setenv('CB_GREEDY', 'legacy')
     want, _ = ctx.setcover(cover, len(cands), None, None)
     assert len(want) > 1000
     for cap in ('64', '2048', '2048'):
@@ -329,11 +329,11 @@ def test_baseline_config2_full_size_properties(ctx, monkeypatch):
     cover, st = cov.compute_cover(ctx, group, plan, 2, 60, 0, 50)
     group.free()
     picks = {}
-    for mode in ('par', 'inc'):
+    for mode in ('par', 'legacy'):
         monkeypatch.setenv('CB_GREEDY', mode)
         picks[mode], _ = ctx.setcover(cover, len(cands), None, None)
     monkeypatch.delenv('CB_GREEDY')
-    assert picks['par'].tolist() == picks['inc'].tolist()
+    assert picks['par'].tolist() == picks['legacy'].tolist()
     sel = picks['par']
     assert len(set(sel.tolist())) == len(sel) > 100
     pid, gen, s, e = ctx.cover_export(cover)

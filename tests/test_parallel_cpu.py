@@ -137,3 +137,83 @@ def test_failure_on_one_rank_raises_on_every_rank(tmp_path):
     outcomes = [open(p).read() for p in paths]
     assert sum(o.startswith('ValueError: grouping 2') for o in outcomes) == 1
     assert sum(o.startswith('RuntimeError: rank') for o in outcomes) == 1
+
+
+# ---- probe-sharded path: the host-side collective that precedes cb_setcover_sharded ----------------
+def _exchange_worker(rank, world, port, out_path, scenario):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank),
+                      MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    import torch.distributed as dist
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from catch_b200 import parallel
+
+    class FakeCtx:
+        """Stands in for _lib.Context: records what the collective asks of the exchange area."""
+
+        def __init__(self):
+            self.bytes, self.exchange_ready, self.log = 0, False, []
+
+        def exchange_bytes(self):
+            return self.bytes
+
+        def exchange_alloc(self, n):
+            self.bytes = n
+            self.log.append(('alloc', n))
+
+        def exchange_handle(self):
+            return bytes([rank]) * 64, 0
+
+        def exchange_attach(self, r, n, handles=None, addresses=None, grid_limit=0):
+            self.log.append(('attach', r, n, [h[0] for h in handles]))
+            self.exchange_ready, self.exchange_rank, self.exchange_n_ranks = True, r, n
+
+    ctx = FakeCtx()
+    res = []
+    try:
+        if scenario == 'grow':
+            # sizes differ per rank: everyone must end up with the largest; a second, smaller request keeps the area
+            parallel.ensure_exchange(ctx, (100 << 20) * (rank + 1), token=5)
+            parallel.ensure_exchange(ctx, 1 << 20, token=6)
+            parallel.ensure_exchange(ctx, (400 << 20) + rank, token=7)
+            res = ctx.log
+        elif scenario == 'token':
+            parallel.ensure_exchange(ctx, 1 << 20, token=11 + rank)        # ranks disagree on host state
+        elif scenario == 'failed':
+            parallel.ensure_exchange(ctx, 1 << 20, token=3, failed=(rank == 1))
+        outcome = 'ok'
+    except Exception as e:
+        outcome = type(e).__name__ + ': ' + str(e)
+    np.save(out_path, np.array([outcome, res], dtype=object), allow_pickle=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('scenario', ['grow', 'token', 'failed'])
+def test_ensure_exchange_over_gloo(tmp_path, scenario):
+    """World size 2 over gloo: the exchange areas grow to the largest need of any rank and are mapped
+    again only then; a rank-local failure or diverging RNG state raises on EVERY rank."""
+    import multiprocessing as mp
+    ctxm = mp.get_context('spawn')
+    port = _free_port()
+    paths = [str(tmp_path / ('x%d.npy' % r)) for r in range(2)]
+    procs = [ctxm.Process(target=_exchange_worker, args=(r, 2, port, paths[r], scenario)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    res = [np.load(p, allow_pickle=True) for p in paths]
+    if scenario == 'grow':
+        for r, (outcome, log) in enumerate(res):
+            assert outcome == 'ok'
+            allocs = [e[1] for e in log if e[0] == 'alloc']
+            attaches = [e for e in log if e[0] == 'attach']
+            assert len(allocs) == 2 and len(attaches) == 2          # the 1 MiB request reused the area
+            assert allocs[0] >= (200 << 20) and allocs[1] >= (400 << 20) + 1
+            assert attaches[0][1:] == (r, 2, [0, 1])
+        assert [e[1] for e in res[0][1] if e[0] == 'alloc'] == [e[1] for e in res[1][1] if e[0] == 'alloc']
+    elif scenario == 'token':
+        assert all(o[0].startswith('RuntimeError: ranks disagree') for o in res)
+    else:
+        assert all(o[0].startswith('RuntimeError: a rank failed') for o in res)
+        assert '(this one)' in res[1][0] and '(this one)' not in res[0][0]
