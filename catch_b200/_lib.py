@@ -100,7 +100,7 @@ def load():
     L.cb_exchange_handle.argtypes = [vp, vp, C.POINTER(C.c_uint64)]
     L.cb_exchange_attach.argtypes = [vp, i32, i32, vp, vp, i32]
     L.cb_exchange_required.argtypes = [vp, vp, C.POINTER(i64)]
-    L.cb_setcover_sharded.argtypes = [vp, vp, i64, i64, vp, C.POINTER(i64), C.POINTER(Stats)]
+    L.cb_setcover_sharded.argtypes = [vp, vp, i64, i64, vp, vp, C.POINTER(i64), C.POINTER(Stats)]
     L.cb_cover_free.argtypes = [vp]
     L.cb_cover_free.restype = None
     L.cb_cover_num_intervals.argtypes = [vp]

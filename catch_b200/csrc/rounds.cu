@@ -157,7 +157,8 @@ __device__ __forceinline__ void grid_barrier(const RParams &G, unsigned long lon
     __syncthreads();
 }
 
-// Cross-GPU barrier with a payload.  All CTAs of this GPU arrive; CTA 0 then runs payload()
+// Cross-GPU barrier with a payload (n_ranks > 1; with one rank it is the plain grid barrier and the
+// payload is NOT run: callers read their local copies instead).  All CTAs of this GPU arrive; CTA 0 then runs payload()
 // (which stores this rank's contribution into the exchange area of every rank), announces the new
 // epoch to every peer and waits for theirs, and releases the other CTAs.  After the call the
 // contributions of ALL ranks for this epoch are visible in the local exchange area (read them with
@@ -167,6 +168,11 @@ template <typename Payload>
 __device__ __forceinline__ void xbarrier(const RParams &G, unsigned long long &target, unsigned long long &epoch,
                                          Payload payload)
 {
+    if (G.n_ranks == 1) {                         // nothing to exchange: the symmetric barrier is cheaper
+        epoch++;
+        grid_barrier(G, target);
+        return;
+    }
     __syncthreads();
     target += gridDim.x;
     epoch++;
@@ -189,15 +195,13 @@ __device__ __forceinline__ void xbarrier(const RParams &G, unsigned long long &t
     }
     __syncthreads();
     payload();
-    if (G.n_ranks > 1) {
-        __threadfence_system();
-        __syncthreads();
-        if ((int)threadIdx.x < G.n_ranks && (int)threadIdx.x != G.rank) {
-            XHeader *peer = reinterpret_cast<XHeader *>(G.xa[threadIdx.x]);
-            XHeader *mine = reinterpret_cast<XHeader *>(G.xa[G.rank]);
-            st_release_sys(&peer->flag[G.rank], e);
-            spin_until(G, [&] { return ld_acquire_sys(&mine->flag[threadIdx.x]) >= e; });
-        }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < G.n_ranks && (int)threadIdx.x != G.rank) {
+        XHeader *peer = reinterpret_cast<XHeader *>(G.xa[threadIdx.x]);
+        XHeader *mine = reinterpret_cast<XHeader *>(G.xa[G.rank]);
+        st_release_sys(&peer->flag[G.rank], e);
+        spin_until(G, [&] { return ld_acquire_sys(&mine->flag[threadIdx.x]) >= e; });
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -493,8 +497,8 @@ greedy_rounds_kernel(const RParams G)
                 }
             });
             if (failed() || __ldcg(G.remaining) == 0ull) break;
-            unsigned long long key = 0ull;
-            for (int r = 0; r < R; r++) {
+            unsigned long long key = R == 1 ? __ldcg(&G.key_local[ks]) : 0ull;
+            for (int r = 0; r < R && R > 1; r++) {
                 const unsigned long long k2 = __ldcg(&xh->key[epoch & 1ull][r]);
                 key = k2 > key ? k2 : key;
             }
@@ -556,6 +560,7 @@ greedy_rounds_kernel(const RParams G)
             id_thr = 0xffffffffu;
             {
                 auto level_count = [&](int i) -> uint32_t {
+                    if (R == 1) return __ldcg(&hist_now[i]);
                     uint32_t c = 0;
                     for (int r = 0; r < R; r++) c += __ldcg(&xh->hist[epoch & 1ull][r][i]);
                     return c;
@@ -596,52 +601,99 @@ greedy_rounds_kernel(const RParams G)
             lap(0);
         }
 
-        // ---- exchange: CTA 0 compacts this rank's active candidates (list entries whose gain is still
-        // >= tau; gains are final, every CTA has arrived) and pushes them to every rank
-        xbarrier(G, bar_target, epoch, [&] {
-            const unsigned slot = (unsigned)(epoch & 1ull);
+        uint32_t n_act = 0, total_pairs = 0;
+        if (R == 1) {
+            // ---- one GPU: every CTA derives the active candidates (list entries whose gain is still >= tau)
+            // itself, from the same inputs with the same deterministic scan -- no global list of actives,
+            // no counters, one plain grid barrier (gains are final after it)
+            grid_barrier(G, bar_target);
+            if (failed() || __ldcg(G.remaining) == 0ull) break;
             const uint32_t n_list = min(__ldcg(G.list_n), G.list_cap);
-            uint32_t n_mine = 0;
-            for (uint32_t c0 = 0; c0 < n_list; c0 += RT) {          // CTA-uniform
-                const uint32_t c = c0 + threadIdx.x;
-                uint32_t p = 0xffffffffu, g = 0;
-                if (c < n_list) {
-                    p = __ldcg(&G.list[c]);
-                    g = __ldcg(&G.gain[p]);
-                }
-                const bool act = p != 0xffffffffu && g >= tau;
-                const uint32_t before = n_mine;
-                const uint32_t pos = before + block_scan(act ? 1u : 0u, n_mine);
-                if (act) {
+            uint32_t pv[PER], gv[PER];
+#pragma unroll
+            for (int u = 0; u < PER; u++) {
+                const uint32_t c = (uint32_t)u * RT + threadIdx.x;
+                pv[u] = c < n_list ? __ldcg(&G.list[c]) : 0xffffffffu;
+            }
+#pragma unroll
+            for (int u = 0; u < PER; u++) gv[u] = pv[u] != 0xffffffffu ? __ldcg(&G.gain[pv[u]]) : 0u;
+#pragma unroll
+            for (int u = 0; u < PER; u++) {
+                if ((uint32_t)u * RT >= n_list) break;          // CTA-uniform
+                const bool act = gv[u] >= tau && pv[u] != 0xffffffffu;
+                const uint32_t before = n_act;
+                const uint32_t pos = before + block_scan(act ? 1u : 0u, n_act);
+                if (act) { s_p[pos] = pv[u]; s_g[pos] = gv[u]; }
+            }
+            __syncthreads();
+            if (n_act == 0u) {                       // the list is used up
+                need_rebuild = true;
+                continue;
+            }
+            uint32_t i0v[PER], cntv[PER];
+#pragma unroll
+            for (int u = 0; u < PER; u++) {
+                const uint32_t a = (uint32_t)u * RT + threadIdx.x;
+                i0v[u] = cntv[u] = 0;
+                if (a < n_act) {
+                    const uint32_t p = s_p[a];
                     const int64_t x = G.iv_off[p], y = G.iv_off[p + 1];
-                    const uint4 rec = make_uint4(p, g, (uint32_t)x, (uint32_t)(y - x));
-                    for (int r = 0; r < R; r++) cand_slot(G, r, slot, me)[pos] = rec;
+                    i0v[u] = (uint32_t)x;
+                    cntv[u] = (uint32_t)(y - x);
                 }
             }
-            if (threadIdx.x == 0)
-                for (int r = 0; r < R; r++) reinterpret_cast<XHeader *>(G.xa[r])->cand_n[slot][me] = n_mine;
-        });
-        if (failed() || __ldcg(G.remaining) == 0ull) break;
-        const unsigned slot = (unsigned)(epoch & 1ull);
-
-        // ---- every CTA loads the active candidates of ALL ranks (rank order, then list order) into
-        // its own shared memory: same inputs, same arrays everywhere
-        if (threadIdx.x == 0) {
-            uint32_t acc = 0;
-            for (int r = 0; r < R; r++) {
-                s_rn[r] = acc;
-                acc += min(__ldcg(&xh->cand_n[slot][r]), G.list_cap);
+#pragma unroll
+            for (int u = 0; u < PER; u++) {
+                if ((uint32_t)u * RT >= n_act) break;           // CTA-uniform
+                const uint32_t a = (uint32_t)u * RT + threadIdx.x;
+                const uint32_t before = total_pairs;
+                const uint32_t pos = before + block_scan(cntv[u], total_pairs);
+                if (a < n_act) { s_i0[a] = i0v[u]; s_base[a] = pos; s_own[a] = 0; }
             }
-            s_rn[R] = acc;
-        }
-        __syncthreads();
-        const uint32_t n_act = min(s_rn[R], G.list_cap);
-        if (n_act == 0u) {                       // the list is used up
-            need_rebuild = true;
-            continue;
-        }
-        uint32_t total_pairs = 0;
-        {
+        } else {
+            // ---- several GPUs: CTA 0 compacts this rank's active candidates (gains are final, every CTA has
+            // arrived) and pushes (probe, gain, first interval, #intervals) to every rank
+            xbarrier(G, bar_target, epoch, [&] {
+                const unsigned slot = (unsigned)(epoch & 1ull);
+                const uint32_t n_list = min(__ldcg(G.list_n), G.list_cap);
+                uint32_t n_mine = 0;
+                for (uint32_t c0 = 0; c0 < n_list; c0 += RT) {          // CTA-uniform
+                    const uint32_t c = c0 + threadIdx.x;
+                    uint32_t p = 0xffffffffu, g = 0;
+                    if (c < n_list) {
+                        p = __ldcg(&G.list[c]);
+                        g = __ldcg(&G.gain[p]);
+                    }
+                    const bool act = p != 0xffffffffu && g >= tau;
+                    const uint32_t before = n_mine;
+                    const uint32_t pos = before + block_scan(act ? 1u : 0u, n_mine);
+                    if (act) {
+                        const int64_t x = G.iv_off[p], y = G.iv_off[p + 1];
+                        const uint4 rec = make_uint4(p, g, (uint32_t)x, (uint32_t)(y - x));
+                        for (int r = 0; r < R; r++) cand_slot(G, r, slot, me)[pos] = rec;
+                    }
+                }
+                if (threadIdx.x == 0)
+                    for (int r = 0; r < R; r++) reinterpret_cast<XHeader *>(G.xa[r])->cand_n[slot][me] = n_mine;
+            });
+            if (failed() || __ldcg(G.remaining) == 0ull) break;
+            const unsigned slot = (unsigned)(epoch & 1ull);
+            // every CTA loads the active candidates of ALL ranks (rank order, then list order) into its own
+            // shared memory: same inputs, same arrays everywhere
+            if (threadIdx.x == 0) {
+                uint32_t acc = 0;
+                for (int r = 0; r < R; r++) {
+                    s_rn[r] = acc;
+                    acc += min(__ldcg(&xh->cand_n[slot][r]), G.list_cap);
+                }
+                s_rn[R] = acc;
+            }
+            __syncthreads();
+            n_act = min(s_rn[R], G.list_cap);
+            if (n_act == 0u) {                       // the list is used up
+                need_rebuild = true;
+                continue;
+            }
             uint32_t cntv[PER];
 #pragma unroll
             for (int u = 0; u < PER; u++) {
@@ -666,12 +718,12 @@ greedy_rounds_kernel(const RParams G)
                 const uint32_t pos = before + block_scan(cntv[u], total_pairs);
                 if (a < n_act) s_base[a] = pos;
             }
-            if (threadIdx.x == 0) s_base[n_act] = total_pairs;
-            // the conflict flags of the previous round have been read by everybody (barrier since)
-            if (blockIdx.x == 0)
-                for (uint32_t a = threadIdx.x; a < G.list_cap; a += RT) G.flag[a] = 0u;
-            __syncthreads();
         }
+        if (threadIdx.x == 0) s_base[n_act] = total_pairs;
+        // the conflict flags of the previous round have been read by everybody (barrier since)
+        if (blockIdx.x == 0)
+            for (uint32_t a = threadIdx.x; a < G.list_cap; a += RT) G.flag[a] = 0u;
+        __syncthreads();
         auto pair_of = [&](uint32_t f, uint32_t &a) -> uint2 {
             uint32_t lo = 0, hi = n_act;
             while (hi - lo > 1) {
