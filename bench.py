@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Benchmark of the SetCoverFilter hot path (BASELINE.json metric: candidate-probe x target-bp / s).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload zika] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload zika|plumbing|influenza|vall|sweep]
+                    [--shard probes|groups] [--impl reference] [--no-extras] [--no-cpu-baseline]
 
 A step is one pass of the hot path (stage A coverage + stage B greedy set cover) over one batch
 of synthetic genomes.  Two numbers per run:
@@ -10,7 +11,18 @@ of synthetic genomes.  Two numbers per run:
   e2e   : the same metric through the plugin call a user makes, SetCoverFilter.filter(), with
           host Probe/Genome objects; host packing, host->device copies, both stages and the
           device->host read of the selection are all inside the timed region.
-The CPU oracle (oracle/) is executed only for `cpu_baseline` and `--impl reference`.
+With N > 1 (torchrun, one process per GPU) the default is STRONG scaling on the same single
+grouping: the candidate probes are sharded over the GPUs, stage A runs on each shard, and stage B
+runs with sharded gains and one exchange per greedy round through peer-mapped memory
+(csrc/rounds.cu).  `--shard groups` gives one independent grouping per GPU instead (weak scaling).
+
+The default line (workload zika = BASELINE config 2) also carries, unless --no-extras:
+  like_for_like : SetCoverFilter.filter() on the SAME 60-genome sample the CPU leg runs, with the
+                  selection compared to the oracle's (bit-exact, order included);
+  configs       : compact results for BASELINE configs 3 (influenza shape, MinHash near-duplicate
+                  filter on), 4 (V-All shape, a stated number of taxa) and 5 (m x l sweep);
+  with N > 1: vall_groups, the V-All-shape e2e with the SAME taxa sharded over the N GPUs.
+The CPU oracle (oracle/) is executed only for `cpu_baseline`, `like_for_like` and `--impl reference`.
 """
 import argparse
 import json
@@ -29,9 +41,10 @@ sys.path.insert(0, ROOT)
 from tests import helpers  # noqa: E402  (synthetic generators of SURVEY.md section 8d)
 
 RNG_SEED = 7
+METRIC = 'candidate-probe x target-bp / s through SetCoverFilter'
 
 WORKLOADS = {
-    # name: (n_genomes, genome_len, divergence, generator seed, probe_length, probe_stride, filter kwargs)
+    # single-grouping set-cover workloads: n_genomes, genome_len, divergence, generator seed, probe length / stride
     'plumbing': dict(n_genomes=20, length=5000, div=0.03, seed=1, pl=75, ps=50,
                      scf=dict(mismatches=0, lcf_thres=75, cover_extension=0),
                      desc='config 1: 20 x 5 kb, -pl 75 -m 0 -e 0'),
@@ -39,12 +52,11 @@ WORKLOADS = {
                  scf=dict(mismatches=2, lcf_thres=60, cover_extension=50),
                  desc='config 2 (Zika-scale): 500 x 11 kb, -pl 75 -m 2 -l 60 -e 50'),
 }
+OTHER_WORKLOADS = ('influenza', 'vall', 'sweep')
 
 
 def make_workload(name, n_genomes=None, n_groups=1):
-    """n_groups independent groupings of the named shape (generator seeds seed, seed+1, ...):
-    one grouping per GPU in the multi-GPU runs (weak scaling over independent set-cover instances,
-    the V-All structure of many taxa)."""
+    """n_groups independent groupings of the named shape (generator seeds seed, seed+1, ...)."""
     w = dict(WORKLOADS[name])
     if n_genomes is not None:
         w['n_genomes'] = n_genomes
@@ -60,6 +72,10 @@ def make_workload(name, n_genomes=None, n_groups=1):
     w['seqs'], w['cands'] = w['groups_seqs'][0], w['groups_cands'][0]
     w['pairs'] = pairs
     return w
+
+
+def sample_desc(w, name):
+    return 'first %d genomes of %s (P=%d, T=%d bp)' % (w['n_genomes'], name, len(w['cands']), sum(map(len, w['seqs'])))
 
 
 # ------------------------------------------------------------------------------------------
@@ -122,57 +138,239 @@ def measured_peak_gbs():
         return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
+def host_threads():
+    """Host threads the CPU leg may use.  torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU leg
+    is a reported baseline on 'all the host threads it can use', so it sizes itself from the machine."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 # ------------------------------------------------------------------------------------------
+def oracle_scf(w, threads):
+    """One SetCoverFilter pass of the CPU restatement of the reference on workload w; returns
+    (seconds, selected indices in the reference's output order)."""
+    from oracle import oracle as O
+    np.random.seed(RNG_SEED)
+    random.seed(RNG_SEED)
+    t0 = time.perf_counter()
+    sel = O.set_cover_filter([w['cands']], [[[s] for s in w['seqs']]], w['scf']['mismatches'],
+                             w['scf']['lcf_thres'], 0, 1.0, w['scf']['cover_extension'], 20, n_threads=threads)
+    return time.perf_counter() - t0, sel[0]
+
+
 def run_reference_arm(args, rank, world):
     """`--impl reference`: the CPU restatement of the reference path (oracle port -- the reference
-    itself is Python and does not travel to the GPU box) on the host cores, bounded sample."""
+    itself is Python and does not travel to the GPU box) on the host cores, bounded sample.  Rank 0
+    alone runs it, with every host thread of the box, whatever N is."""
     if rank != 0:
         return
-    from oracle import oracle as O
-    w = make_workload(args.workload, n_genomes=args.cpu_sample_genomes)
-    threads = O.num_threads()
-    groups = [[[s] for s in w['seqs']]]
-
-    def step():
-        np.random.seed(RNG_SEED)
-        random.seed(RNG_SEED)
-        t0 = time.perf_counter()
-        O.set_cover_filter([w['cands']], groups, w['scf']['mismatches'], w['scf']['lcf_thres'], 0, 1.0,
-                           w['scf']['cover_extension'], 20, n_threads=threads)
-        return time.perf_counter() - t0
-
+    name = args.workload if args.workload in WORKLOADS else 'zika'
+    w = make_workload(name, n_genomes=args.cpu_sample_genomes)
+    threads = host_threads()
     for _ in range(args.warmup):
-        step()
-    times = [step() for _ in range(args.steps)]
+        oracle_scf(w, threads)
+    times = [oracle_scf(w, threads)[0] for _ in range(args.steps)]
     t = sum(times) / len(times)
     v = w['pairs'] / t
-    sample = 'first %d genomes of %s (P=%d, T=%d bp)' % (w['n_genomes'], args.workload, len(w['cands']),
-                                                          sum(map(len, w['seqs'])))
+    sample = sample_desc(w, name)
     print(json.dumps({
-        'impl': 'reference', 'metric': 'candidate-probe x target-bp / s through SetCoverFilter',
+        'impl': 'reference', 'metric': METRIC,
         'value': v, 'unit': 'pairs/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': t * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'u8', 'data': 'synthetic',
-        'config': {'workload': WORKLOADS[args.workload]['desc'], 'sample': sample},
+        'ms_per_step': t * 1e3, 'higher_is_better': True, 'scaling': 'strong',
+        'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
+        'config': {'workload': WORKLOADS[name]['desc'], 'sample': sample},
         'cpu_baseline': {'value': v, 'unit': 'pairs/s', 'cores': threads, 'kind': 'port', 'sample': sample},
         'e2e': {'value': v, 'unit': 'pairs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }))
 
 
-def cpu_baseline(args):
-    from oracle import oracle as O
-    w = make_workload(args.workload, n_genomes=args.cpu_sample_genomes)
-    threads = O.num_threads()
-    np.random.seed(RNG_SEED)
-    random.seed(RNG_SEED)
+def cpu_and_like_for_like(args, ctx, name):
+    """The CPU leg and the GPU path on the SAME bounded sample: the oracle port on all
+    host threads, SetCoverFilter.filter() on the device, the two selections compared element by element."""
+    from catch_b200 import probe
+    from catch_b200.filter.set_cover_filter import SetCoverFilter
+    w = make_workload(name, n_genomes=args.cpu_sample_genomes)
+    threads = host_threads()
+    t_cpu, want = oracle_scf(w, threads)
+    sample = sample_desc(w, name)
+    cpu = {'value': w['pairs'] / t_cpu, 'unit': 'pairs/s', 'cores': threads, 'kind': 'port',
+           'sample': '%s, %.1f s; stage A on %d threads, stage B on 1 (as the reference: one process per grouping)'
+                     % (sample, t_cpu, threads)}
+    genomes = helpers.to_genomes([[[s] for s in w['seqs']]])
+    probes = [[probe.Probe.from_str(s) for s in w['cands']]]
+    scf = SetCoverFilter(**w['scf'])
+    scf._ctx = ctx
+    os.environ['CB_SHARD'] = 'groups'
+    times, got = [], None
+    for i in range(5):
+        np.random.seed(RNG_SEED)
+        random.seed(RNG_SEED)
+        ctx.flush_l2()
+        t0 = time.perf_counter()
+        out = scf.filter(probes, genomes, input_is_grouped=True)
+        times.append(time.perf_counter() - t0)
+        ids = {id(p): i for i, p in enumerate(probes[0])}
+        got = [ids[id(p)] for p in out[0]]
+    t_gpu = float(np.mean(times[2:]))
+    lfl = {'sample': sample, 'gpu_ms': t_gpu * 1e3, 'cpu_ms': t_cpu * 1e3, 'ratio': t_cpu / t_gpu,
+           'gpu_pairs_per_s': w['pairs'] / t_gpu, 'cpu_pairs_per_s': w['pairs'] / t_cpu, 'cpu_cores': threads,
+           'selected': len(got), 'identical': got == list(want),
+           'what': 'SetCoverFilter.filter() end to end on host objects vs the CPU port of the reference on the same '
+                   'input and RNG seed; identical = same probes in the same output order'}
+    return cpu, lfl
+
+
+# ------------------------------------------------------------------------------------------
+def config3_influenza(ctx, n_genomes, reps=3):
+    """BASELINE config 3: influenza shape, MinHash near-duplicate filter, then SetCoverFilter on what it keeps
+    (-m 5 -l 30 -e 50, pl 100).  Returns (compact result, kept probes, genomes, T)."""
+    from catch_b200 import probe
+    from catch_b200.filter.near_duplicate_filter import NearDuplicateFilterWithMinHash
+    from catch_b200.filter.set_cover_filter import SetCoverFilter
+    gens = helpers.synthetic_influenza(n_genomes, seed=3)
+    groups = [[[seg] for g in gens for seg in g]]
+    genomes = helpers.to_genomes(groups)
+    cands = helpers.tile_candidates([s for g in groups[0] for s in g], 100, 50)
+    T = sum(len(s) for g in groups[0] for s in g)
+    raw = [[probe.Probe.from_str(s) for s in cands]]
+    ndf_wall, ndf_dev, kept, st = [], [], None, None
+    for _ in range(reps):
+        np.random.seed(RNG_SEED)
+        random.seed(RNG_SEED)
+        ndf = NearDuplicateFilterWithMinHash(0.6)
+        ndf._ctx = ctx
+        t = time.perf_counter()
+        kept = ndf.filter(raw, genomes, input_is_grouped=True)
+        ndf_wall.append(time.perf_counter() - t)
+        st = ndf.last_stats
+        ndf_dev.append(st['ms_total'])
+    scf = SetCoverFilter(mismatches=5, lcf_thres=30, cover_extension=50)
+    scf._ctx = ctx
+    os.environ['CB_SHARD'] = 'groups'
+    scf_wall, n_sel = [], 0
+    for _ in range(reps):
+        np.random.seed(RNG_SEED)
+        ctx.flush_l2()
+        t = time.perf_counter()
+        out = scf.filter(kept, genomes, input_is_grouped=True)
+        scf_wall.append(time.perf_counter() - t)
+        n_sel = len(out[0])
+    s = scf.last_stats[0]
+    P = len(kept[0])
+    t_ndf, t_scf = min(ndf_wall[1:] or ndf_wall), min(scf_wall[1:] or scf_wall)
+    dev_ms = s['coverage']['ms_total'] + s['setcover']['ms_total']
+    res = {
+        'workload': 'config 3 (influenza shape): %d genomes x 8 segments (T=%d bp), pl 100 ps 50, MinHash near-duplicate '
+                    'filter 0.6, then -m 5 -l 30 -e 50' % (n_genomes, T),
+        'P_raw': len(cands), 'P_distinct': int(st['n_distinct']), 'P_after_ndf': P,
+        'ndf': {'wall_ms': t_ndf * 1e3, 'device_ms': min(ndf_dev), 'probes_per_s_e2e': len(cands) / t_ndf,
+                'probes_per_s_device': len(cands) / (min(ndf_dev) / 1e3), 'decision_rounds': int(st['n_picks']),
+                'device_split_ms': {'grouping': st['ms_pack'], 'signatures': st['ms_seed_index'], 'decisions': st['ms_greedy']}},
+        'scf': {'e2e_ms': t_scf * 1e3, 'device_ms': dev_ms, 'pairs_per_s_e2e': P * T / t_scf,
+                'pairs_per_s_device': P * T / (dev_ms / 1e3), 'selected': n_sel,
+                'scan_ms': s['coverage']['ms_scan_emit'], 'merge_ms': s['coverage']['ms_merge'],
+                'greedy_ms': s['setcover']['ms_greedy'], 'rounds': int(s['setcover']['reserved'][5])},
+    }
+    return res, kept, genomes, T
+
+
+def config5_sweep(ctx, kept, genomes, T, cells=None, reps=2):
+    """BASELINE config 5: hybridisation sweep on the config-3 input (after the near-duplicate filter)."""
+    from catch_b200.filter.set_cover_filter import SetCoverFilter
+    os.environ['CB_SHARD'] = 'groups'
+    P = len(kept[0])
+    out = []
+    for m in (0, 2, 5, 10):
+        for l in (30, 60, 100):
+            if cells is not None and (m, l) not in cells:
+                continue
+            scf = SetCoverFilter(mismatches=m, lcf_thres=l, cover_extension=50)
+            scf._ctx = ctx
+            best = None
+            for _ in range(reps):
+                np.random.seed(RNG_SEED)
+                ctx.flush_l2()
+                t = time.perf_counter()
+                sel = scf.filter(kept, genomes, input_is_grouped=True)
+                dt = time.perf_counter() - t
+                if best is None or dt < best[0]:
+                    best = (dt, dict(scf.last_stats[0]), len(sel[0]))
+            dt, s, n_sel = best
+            ca, cb = s['coverage'], s['setcover']
+            dev_ms = ca['ms_total'] + cb['ms_total']
+            out.append({'m': m, 'l': l, 'seeds': '%s k=%d' % (s['seed_mode'], s['k']), 'selected': n_sel,
+                        'e2e_ms': round(dt * 1e3, 2), 'device_ms': round(dev_ms, 2),
+                        'scan_ms': round(ca['ms_scan_emit'], 2), 'merge_ms': round(ca['ms_merge'], 2),
+                        'greedy_ms': round(cb['ms_greedy'], 2), 'rounds': int(cb['reserved'][5]),
+                        'pairs_per_s_e2e': P * T / dt, 'pairs_per_s_device': P * T / (dev_ms / 1e3)})
+    return out
+
+
+def config4_vall(ctx, n_taxa, n_genomes, dist=None, local_rank=0, reps=2):
+    """BASELINE config 4 shape (V-All): n_taxa independent taxa = groupings, -pl 100 -m 5 -l 30 -e 0, through
+    SetCoverFilter.filter(); with a process group the groupings are sharded over the ranks (largest first)."""
+    from catch_b200 import probe
+    from catch_b200.filter.set_cover_filter import SetCoverFilter
+    groups = helpers.synthetic_taxa(n_taxa, n_genomes, seed=4)
+    genomes = helpers.to_genomes([[[s] for s in g] for g in groups])
+    cands = [list(dict.fromkeys(helpers.tile_candidates(g, 100, 50))) for g in groups]
+    probes = [[probe.Probe.from_str(s) for s in c] for c in cands]
+    pairs = sum(len(c) * sum(map(len, g)) for c, g in zip(cands, groups))
+    scf = SetCoverFilter(mismatches=5, lcf_thres=30, cover_extension=0)
+    scf._ctx = ctx
+    os.environ['CB_SHARD'] = 'groups'
+    best, n_sel = None, 0
+    for rep in range(reps + 1):                        # first repetition is the warm-up
+        np.random.seed(RNG_SEED)
+        random.seed(RNG_SEED)
+        if dist is not None:
+            dist.barrier(device_ids=[local_rank])
+        t = time.perf_counter()
+        out = scf.filter(probes, genomes, input_is_grouped=True)
+        dt = time.perf_counter() - t
+        if dist is not None:
+            import torch
+            tt = torch.tensor([dt], dtype=torch.float64, device='cuda')
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+        if rep > 0 and (best is None or dt < best):
+            best = dt
+        n_sel = sum(len(o) for o in out)
+    dev_ms = sum((s['coverage']['ms_total'] + s['setcover']['ms_total']) for s in scf.last_stats if s and 'coverage' in s)
+    world = dist.get_world_size() if dist is not None else 1
+    return {'workload': 'config 4 shape (V-All): %d of 300 taxa x %d genomes of 10-30 kb, -pl 100 -m 5 -l 30 -e 0'
+                        % (n_taxa, n_genomes),
+            'n_gpus': world, 'groupings': n_taxa, 'P_total': sum(map(len, cands)),
+            'T_total_bp': sum(sum(map(len, g)) for g in groups), 'pairs': pairs, 'selected': n_sel,
+            'e2e_ms': best * 1e3, 'pairs_per_s_e2e': pairs / best, 'this_rank_device_ms': round(dev_ms, 1),
+            'sharding': 'single GPU' if world == 1 else
+                        'groupings over ranks, largest first; no data-path collective; same taxa at every N (strong)'}
+
+
+def emit_other_workload(args, ctx):
+    """--workload influenza | vall | sweep as the main line (single GPU)."""
     t0 = time.perf_counter()
-    O.set_cover_filter([w['cands']], [[[s] for s in w['seqs']]], w['scf']['mismatches'],
-                       w['scf']['lcf_thres'], 0, 1.0, w['scf']['cover_extension'], 20, n_threads=threads)
-    t = time.perf_counter() - t0
-    return {'value': w['pairs'] / t, 'unit': 'pairs/s', 'cores': threads, 'kind': 'port',
-            'sample': 'first %d genomes of %s (P=%d, T=%d bp), %.1f s; stage A on %d threads, stage B on 1 '
-                      '(as the reference: one process per grouping)' % (
-                          w['n_genomes'], args.workload, len(w['cands']), sum(map(len, w['seqs'])), t, threads)}
+    line = {'metric': METRIC, 'unit': 'pairs/s', 'n_gpus': 1, 'steps': args.steps, 'warmup': args.warmup,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic'}
+    sampler = ClockSampler(0)
+    sampler.start()
+    if args.workload == 'vall':
+        r = config4_vall(ctx, args.vall_taxa, args.vall_genomes, reps=max(1, args.steps))
+        line.update(value=r['pairs_per_s_e2e'], ms_per_step=r['e2e_ms'], config={'workload': r['workload'], 'l2': 'inputs >> L2'},
+                    e2e={'value': r['pairs_per_s_e2e'], 'unit': 'pairs/s', 'ms_per_step': r['e2e_ms']}, detail=r)
+    else:
+        r, kept, genomes, T = config3_influenza(ctx, args.influenza_genomes, reps=max(2, args.steps))
+        line.update(value=r['scf']['pairs_per_s_device'], ms_per_step=r['scf']['device_ms'],
+                    config={'workload': r['workload'], 'l2': 'flushed between steps (256 MiB memset)'},
+                    e2e={'value': r['scf']['pairs_per_s_e2e'], 'unit': 'pairs/s', 'ms_per_step': r['scf']['e2e_ms']},
+                    detail=r)
+        if args.workload == 'sweep':
+            line['sweep'] = config5_sweep(ctx, kept, genomes, T, reps=max(2, args.steps))
+    line['clocks'] = sampler.stop()
+    line['wall_s'] = round(time.perf_counter() - t0, 1)
+    print(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------
@@ -182,12 +380,16 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--workload', default='zika', choices=sorted(WORKLOADS))
+    ap.add_argument('--workload', default='zika', choices=sorted(WORKLOADS) + list(OTHER_WORKLOADS))
     ap.add_argument('--cpu-sample-genomes', type=int, default=60)
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--shard', default='groups', choices=['groups', 'probes'],
-                    help='multi-GPU mode: one grouping per GPU (weak scaling, default) or the probes of ONE '
-                         'grouping split over the GPUs with an NCCL all-gather of the coverage (strong scaling)')
+    ap.add_argument('--no-extras', action='store_true', help='skip like_for_like and the config 3/4/5 sub-objects')
+    ap.add_argument('--shard', default='probes', choices=['groups', 'probes'],
+                    help='multi-GPU mode: the probes of ONE grouping split over the GPUs, sharded set cover with one '
+                         'exchange per round (strong scaling, default), or one grouping per GPU (weak scaling)')
+    ap.add_argument('--influenza-genomes', type=int, default=5000)
+    ap.add_argument('--vall-taxa', type=int, default=16)
+    ap.add_argument('--vall-genomes', type=int, default=333)
     args = ap.parse_args()
     if args.impl == 'b200' and not os.environ.get('CB_BENCH_PROFILING'):
         args.warmup = max(args.warmup, 3)      # timing rule: at least 3 warm-up steps
@@ -205,8 +407,7 @@ def main():
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
-        # plumbing only: barrier, max-over-ranks of the timings (NCCL), exchange of the selected
-        # ids between ranks (gloo, a few KB of Python objects)
+        # plumbing only: barrier, max-over-ranks of the timings (NCCL), small host-side exchanges (gloo)
         dist.init_process_group('cpu:gloo,cuda:nccl')
         # NCCL announces its version on stdout when the communicator is first used; the contract is ONE
         # JSON line on stdout, so the first collective runs with fd 1 pointed at stderr
@@ -221,14 +422,21 @@ def main():
             os.dup2(saved_fd, 1)
             os.close(saved_fd)
 
-    from catch_b200 import _lib, probe
+    from catch_b200 import _lib, parallel, probe
     from catch_b200 import coverage as cov
     from catch_b200.filter.set_cover_filter import SetCoverFilter
 
-    strong = world > 1 and args.shard == 'probes'
-    os.environ['CB_SHARD'] = args.shard
-    w = make_workload(args.workload, n_groups=1 if strong else world)
     ctx = _lib.Context(local_rank)
+    if args.workload in OTHER_WORKLOADS:
+        if world > 1:
+            raise SystemExit('--workload %s is a single-GPU line; its multi-GPU form is the vall_groups object of the '
+                             'default workload' % args.workload)
+        emit_other_workload(args, ctx)
+        return
+
+    strong = world > 1 and args.shard == 'probes'
+    os.environ['CB_SHARD'] = args.shard if world > 1 else 'groups'
+    w = make_workload(args.workload, n_groups=1 if (strong or world == 1) else world)
     genomes = helpers.to_genomes([[[s] for s in seqs] for seqs in w['groups_seqs']])
     probes = [[probe.Probe.from_str(s) for s in c] for c in w['groups_cands']]
     scf = SetCoverFilter(**w['scf'])
@@ -237,9 +445,8 @@ def main():
     # deduplicated candidate counts differ per generator seed, so it is a permutation, not g -> rank g)
     my_group = 0
     if world > 1 and not strong:
-        from catch_b200 import parallel as _par
         sizes = [len(p) * max(1, sum(g.size() for g in tg)) for p, tg in zip(probes, genomes)]
-        my_group = _par.assign_groups(sizes, world).index(rank)
+        my_group = parallel.assign_groups(sizes, world).index(rank)
 
     def barrier():
         if dist is not None:
@@ -256,36 +463,26 @@ def main():
         out = scf.filter(probes, genomes, input_is_grouped=True)
         return time.perf_counter() - t0, out
 
-    # ---- resident: this rank's grouping (or its block of the probes) packed in HBM before the timed region
+    # ---- resident: this rank's grouping (all probes uploaded; a rank of a probe-sharded run SCANS only its block)
     my_cands = w['groups_cands'][my_group]
-    if strong:
-        from catch_b200 import parallel
-        parallel.ensure_comm(ctx)
-        lo, hi = parallel.shard_bounds(len(my_cands), world, rank)
-        group = cov.PackedGroup(ctx, my_cands[lo:hi], genomes[my_group])
-    else:
-        lo, hi = 0, len(my_cands)
-        group = cov.PackedGroup(ctx, my_cands, genomes[my_group])
+    P = len(my_cands)
+    group = cov.PackedGroup(ctx, my_cands, genomes[my_group])
+    lo, hi = parallel.shard_bounds(P, world, rank) if strong else (0, P)
+    m, lcf, ext = w['scf']['mismatches'], w['scf']['lcf_thres'], w['scf']['cover_extension']
 
     def resident_step():
         np.random.seed(RNG_SEED)
         ctx.flush_l2()
-        plan = cov.SeedPlan(my_cands, w['scf']['mismatches'], w['scf']['lcf_thres'], 20)
+        plan = cov.SeedPlan(my_cands, m, lcf, 20, may_have_dups=False)
         if strong:
-            t0 = time.perf_counter()
-            so = np.ascontiguousarray(plan.seed_off[lo:hi + 1] - plan.seed_off[lo])
-            sp = np.ascontiguousarray(plan.seed_pos[plan.seed_off[lo]:max(plan.seed_off[hi], plan.seed_off[lo] + 1)])
-            local, st_a = ctx.coverage(group.probes, group.targets, w['scf']['mismatches'], w['scf']['lcf_thres'], 0,
-                                       w['scf']['cover_extension'], plan.k, so, sp)
-            tg = time.perf_counter()
-            cover = ctx.cover_allgather(local, lo, len(my_cands))
-            st_a.ms_total += (time.perf_counter() - tg) * 1e3        # the exchange is part of the step
+            local, st_a = cov.compute_cover_range(ctx, group, plan, m, lcf, 0, ext, lo, hi)
+            parallel.ensure_exchange(ctx, ctx.exchange_required(local), parallel.rng_state_token())
+            picks, st_b = ctx.setcover_sharded(local, P, lo, hi)
             local.free()
         else:
-            cover, st_a = cov.compute_cover(ctx, group, plan, w['scf']['mismatches'], w['scf']['lcf_thres'], 0,
-                                            w['scf']['cover_extension'])
-        picks, st_b = ctx.setcover(cover, len(my_cands), None, None)
-        cover.free()
+            cover, st_a = cov.compute_cover(ctx, group, plan, m, lcf, 0, ext)
+            picks, st_b = ctx.setcover(cover, P, None, None)
+            cover.free()
         return st_a, st_b, picks
 
     for _ in range(args.warmup):
@@ -295,20 +492,38 @@ def main():
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
-    res = [resident_step() for _ in range(args.steps)]
+    res = []
+    for _ in range(args.steps):
+        if dist is not None:
+            dist.barrier(device_ids=[local_rank])   # ranks of a sharded step start together
+        res.append(resident_step())
     barrier()
-    e2e = [e2e_step() for _ in range(args.steps)]
+    e2e = []
+    for _ in range(args.steps):
+        if dist is not None:
+            dist.barrier(device_ids=[local_rank])
+        e2e.append(e2e_step())
     barrier()
     clocks = sampler.stop()
 
     ms_res = [a.ms_total + b.ms_total for a, b, _ in res]
     t_res = float(np.mean(ms_res)) / 1e3
     t_e2e = float(np.mean([t for t, _ in e2e]))
+    identical_across_ranks = None
     if dist is not None:
         import torch
         t = torch.tensor([t_res, t_e2e], dtype=torch.float64, device='cuda')
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_res, t_e2e = t.tolist()
+        if strong:
+            # every rank must hold the same picks (resident step) and return the same probes (e2e)
+            sel = [p.seq_str for p in e2e[-1][1][0]]
+            mine = (res[-1][2].tolist(), sel)
+            everyone = [None] * world
+            dist.all_gather_object(everyone, mine)
+            identical_across_ranks = all(x == everyone[0] for x in everyone)
+            if not identical_across_ranks:
+                raise SystemExit('ranks disagree on the selection')
     st_a, st_b, picks = res[-1]
     launches = sum(int(a.n_kernel_launches + b.n_kernel_launches) for a, b, _ in res)
     ls = scf.last_stats[my_group]
@@ -318,83 +533,125 @@ def main():
     # ---- roofline of the dominant kernel
     kern = {
         'scan_kernel (K3, count+emit)': (st_a.ms_scan_count + st_a.ms_scan_emit),
-        'greedy_kernel (K6-K8)': st_b.ms_greedy,
+        'greedy_rounds_kernel (K6-K8)': st_b.ms_greedy,
         'merge_kernel (K4)': st_a.ms_merge,
         'seed_index (K2)': st_a.ms_seed_index,
+        'set-up of stage B (K5: universe, gains, interval index)': st_b.ms_universe,
     }
     dom = max(kern, key=kern.get)
-    P, T = len(my_cands), sum(len(s) for s in w['groups_seqs'][my_group])
+    T = sum(len(s) for s in w['groups_seqs'][my_group])
     E, S = int(st_a.n_intervals), int(st_b.n_picks)
     bits = group.bits
     n_seed_entries = int(st_a.n_seed_entries)
+    nw = (w['pl'] + 63) // 64
+    hits, surv, lookups = int(st_a.n_candidate_hits), int(st_a.reserved[0]), int(st_a.n_seed_lookups)
     l2_operand_bytes = None
+    int_ops = None
     if dom.startswith('scan'):
         # SURVEY.md 8(d), stage A compulsory bytes: target planes (read by the counting pre-pass and by
-        # the scan) + one probe record per probe + one seed-index entry per distinct seed + 16 B per
-        # emitted range.  Everything else the kernel touches (index entries and probe records per
-        # candidate hit) is re-use served by L1/L2 and is reported separately as l2_operand_bytes.
-        nw = (w['pl'] + 63) // 64
-        alg_bytes = 2 * T * bits / 8 + P * (bits + 1) * nw * 8 + n_seed_entries * 8 + st_a.n_raw_ranges * 16
-        l2_operand_bytes = st_a.n_candidate_hits * (8 + (bits + 1) * nw * 8)
+        # the scan) + one probe record per probe + one 16-byte seed-index entry per distinct seed + 16 B per
+        # emitted range.  Everything else the kernel touches (an index entry per candidate hit, a probe
+        # record per surviving hit) is re-use served by L1/L2 and is reported as l2_operand_bytes.
+        alg_bytes = 2 * T * bits / 8 + (hi - lo) * (bits + 1) * nw * 8 + n_seed_entries * 16 + st_a.n_raw_ranges * 16
+        l2_operand_bytes = hits * 16 + surv * (bits * nw * 8 + 8)
         dur = kern[dom] / 1e3
+        # integer-op roofline (SURVEY 8d asks for int-op throughput beside HBM): algorithmic 32-bit integer
+        # operations of the scan (per looked-up position, per candidate hit, per surviving
+        # hit) over the kernel time, against the rate this GPU sustains on independent LOP3/LEA chains, measured now
+        kc = (20 + 63) // 64
+        ops = lookups * (15 * bits * kc + 8) + hits * (4 + 6 * bits) + \
+            surv * (8 * bits * nw + 16 + 22 * (m + 1) + 12)
+        peak_ops = ctx.intop_rate()
+        int_ops = {'achieved_gops': ops / dur / 1e9, 'peak_gops': peak_ops / 1e9, 'frac': ops / dur / peak_ops,
+                   'algorithmic_ops': ops, 'candidate_hits': hits, 'surviving_hits': surv, 'lookups': lookups,
+                   'raw_ranges': int(st_a.n_raw_ranges),
+                   'peak_source': 'cb_intop_rate measured in this run (independent LOP3/LEA chains on all SMs)'}
     elif dom.startswith('greedy'):
-        # SURVEY 8(d), stage B: S*P*4 (gain vector per pick) + E*16 (index items touched at least once) + 2*U/8
-        alg_bytes = S * P * 4 + E * 16 + 2 * (T / 8)
+        # SURVEY 8(d), stage B: S*P*4 (gain vector per pick) + E*8 (index items touched at least once) + 2*U/8
+        alg_bytes = S * P * 4 + E * 8 + 2 * (T / 8)
         dur = kern[dom] / 1e3
     else:
         alg_bytes = st_a.n_raw_ranges * 16 * 3
         dur = kern[dom] / 1e3
-    # measured DRAM traffic of the same kernel on the same workload (one `ncu --set full` capture,
-    # profiles/traffic_r01b.json); None for other workloads
-    traffic, ncu_facts = None, None
-    try:
-        with open(os.path.join(ROOT, 'profiles', 'traffic_r01b.json')) as f:
-            tj = json.load(f)
-        if tj.get('workload') == args.workload:
-            key = 'scan_kernel' if dom.startswith('scan') else 'greedy_kernel'
-            traffic = tj['dram_bytes_per_launch'].get(key)
-            ncu_facts = tj.get('ncu', {}).get(key)
-    except Exception:
-        pass
     peak, peak_src = measured_peak_gbs()
     achieved = alg_bytes / dur / 1e9 if dur > 0 else 0.0
     roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                'frac': achieved / peak, 'traffic': traffic, 'algorithmic_bytes': alg_bytes, 'peak_source': peak_src,
+                'frac': achieved / peak, 'traffic': None, 'algorithmic_bytes': alg_bytes, 'peak_source': peak_src,
                 'kernel_ms': {k: round(v, 3) for k, v in kern.items()},
                 'l2_operand_gbs': (l2_operand_bytes / dur / 1e9) if l2_operand_bytes else None,
-                'ncu': ncu_facts,
-                'note': 'HBM is not what binds this integer path: the scan is bound by the integer ALU pipe '
-                        '(ncu: ALU pipe 70 %, issue slots 63 %, operands L2-resident per grouping), the greedy loop '
-                        'by grid-barrier and dependent-load latency; frac is reported against HBM as the contract '
-                        'asks, see DESIGN.md section 5 and profiles/README_r01.md'}
+                'int_ops': int_ops,
+                'traffic_note': 'DRAM bytes per launch cannot be measured inside the run (null here rather than a stale '
+                                'constant); the ncu --set full capture of this kernel on this workload is summarised in '
+                                'profiles/README_r02.md',
+                'note': 'HBM is not what binds this integer path: the scan is bound by the integer ALU pipe (see int_ops '
+                        'and the ncu pipe utilisation in profiles/), the greedy loop by grid-barrier and dependent-load '
+                        'latency per round; frac is reported against HBM as the contract asks'}
 
+    if strong:
+        par = ('probes of ONE grouping split over the GPUs: stage A per shard, stage B with sharded gains / interval '
+               'index, replicated universe and one exchange per round through peer-mapped memory (csrc/rounds.cu); '
+               'torch.distributed carries only control data')
+    elif world > 1:
+        par = 'one grouping per GPU (independent set-cover instances), no data-path collective'
+    else:
+        par = 'single GPU'
     out = {
-        'metric': 'candidate-probe x target-bp / s through SetCoverFilter',
+        'metric': METRIC,
         'value': w['pairs'] / t_res, 'unit': 'pairs/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': t_res * 1e3, 'higher_is_better': True,
-        'scaling': 'strong' if strong else 'weak', 'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
+        'scaling': 'strong' if (strong or world == 1) else 'weak', 'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
         'config': {'workload': w['desc'] + ('' if (world == 1 or strong) else ' x %d independent groupings' % world),
                    'P_per_group': P, 'T_bp_per_group': T, 'pairs': w['pairs'], 'intervals': E,
                    'picks': S, 'l2': 'flushed between steps (256 MiB memset)',
-                   'parallelism': 'single GPU' if world == 1 else
-                   ('probes of one grouping split over the GPUs, NCCL all-gather of the coverage, greedy replicated'
-                    if strong else
-                    'one grouping per GPU (independent set-cover instances), no data-path collective')},
+                   'parallelism': par},
         'e2e': {'value': w['pairs'] / t_e2e, 'unit': 'pairs/s', 'ms_per_step': t_e2e * 1e3,
-                'h2d_bytes_per_step': int(scf.last_stats[my_group]['h2d_bytes']) * world,
-                'd2h_bytes_per_step': int(scf.last_stats[my_group]['d2h_bytes']) * world},
+                'h2d_bytes_per_step': int(ls['h2d_bytes']) * world,
+                'd2h_bytes_per_step': int(ls['d2h_bytes']) * world},
         'gpu_launches': launches * world,
         'clocks': clocks,
         'roofline': roofline,
         'stages_ms': {'coverage': st_a.as_dict(), 'setcover': st_b.as_dict(),
-                      'e2e_host': {k: round(v, 2) for k, v in scf.last_stats[my_group].get('host_ms', {}).items()},
-                      'e2e_group_wall_ms': round(scf.last_stats[my_group].get('wall_s', 0) * 1e3, 2)},
+                      'e2e_host': {k: round(v, 2) for k, v in ls.get('host_ms', {}).items()},
+                      'e2e_group_wall_ms': round(ls.get('wall_s', 0) * 1e3, 2)},
     }
-    if rank == 0:
-        if world == 1 and not args.no_cpu_baseline:
-            out['cpu_baseline'] = cpu_baseline(args)
-        print(json.dumps(out))
+    if strong:
+        out['multi_gpu'] = {'exchange_ranks_seen': int(getattr(ctx, 'exchange_n_ranks', 0)),
+                            'selection_identical_on_every_rank': identical_across_ranks,
+                            'greedy_rounds': int(st_b.reserved[5]), 'list_rebuilds': int(st_b.reserved[4]),
+                            'this_rank_probes': [int(lo), int(hi)], 'this_rank_intervals': E}
     group.free()
+
+    # ---- extras: same-input comparison with the CPU leg, the other BASELINE configs
+    extras_ok = args.workload == 'zika' and not args.no_extras
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            cpu, lfl = cpu_and_like_for_like(args, ctx, args.workload)
+            out['cpu_baseline'] = cpu
+            if not args.no_extras:
+                out['like_for_like'] = lfl
+        except Exception as e:                      # the main line must survive a failing extra
+            out['cpu_baseline_error'] = repr(e)
+    if extras_ok and world == 1:
+        configs = {}
+        try:
+            r3, kept, g3, T3 = config3_influenza(ctx, args.influenza_genomes)
+            configs['config3_influenza'] = r3
+            configs['config5_sweep'] = config5_sweep(ctx, kept, g3, T3, cells={(0, 100), (2, 60), (5, 30), (10, 30)})
+            del kept, g3
+        except Exception as e:
+            configs['config3_error'] = repr(e)
+        try:
+            configs['config4_vall'] = config4_vall(ctx, args.vall_taxa, args.vall_genomes)
+        except Exception as e:
+            configs['config4_error'] = repr(e)
+        out['configs'] = configs
+    if extras_ok and world > 1:
+        try:
+            out['vall_groups'] = config4_vall(ctx, args.vall_taxa, args.vall_genomes, dist=dist, local_rank=local_rank)
+        except Exception as e:
+            out['vall_groups_error'] = repr(e)
+    if rank == 0:
+        print(json.dumps(out))
     if dist is not None:
         dist.barrier(device_ids=[local_rank])
         dist.destroy_process_group()

@@ -244,6 +244,14 @@ int cb_flush_l2(cb_ctx *ctx)
     return CB_OK;
 }
 
+int cb_intop_rate(cb_ctx *ctx, double *ops_per_s)
+{
+    if (!ctx || !ops_per_s) return cb_fail(ctx, CB_ERR_ARG, "null argument");
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cb_tls_stream = ctx->stream;
+    return cb_intop_rate_impl(ctx, ops_per_s);
+}
+
 int cb_upload_targets(cb_ctx *ctx, const uint8_t *ascii, const int64_t *seq_off, int64_t n_seqs,
                       const int32_t *seq_genome, int32_t n_genomes, const uint8_t lut[256], int32_t bits,
                       cb_targets **out, cb_stats *stats)

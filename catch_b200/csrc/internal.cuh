@@ -182,6 +182,7 @@ int cb_launch_pack_probes(cb_ctx *ctx, const uint8_t *d_ascii, const int64_t *d_
 int cb_launch_byte_presence(cb_ctx *ctx, const uint8_t *d_buf, int64_t n, uint32_t *d_present);
 
 int cb_probes_have_duplicates_impl(cb_ctx *ctx, const cb_probes *probes, int32_t *has_dup);
+int cb_intop_rate_impl(cb_ctx *ctx, double *ops_per_s);
 
 // coverage.cu
 int cb_coverage_impl(cb_ctx *ctx, const cb_probes *probes, const cb_targets *targets,

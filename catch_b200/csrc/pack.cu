@@ -193,3 +193,51 @@ int cb_probes_have_duplicates_impl(cb_ctx *ctx, const cb_probes *probes, int32_t
     *has_dup = h;
     return CB_OK;
 }
+
+
+// ---------------------------------------------------------------------------------------
+// Integer-throughput calibration for the roofline of the scan kernel (which is bound by the integer
+// ALU pipe, not by HBM): every thread runs eight independent chains of LOP3 / SHF / IADD3 -- the
+// instructions the mismatch-mask and extension code is made of -- and the achieved rate is reported
+// as 32-bit integer operations per second over the whole chip.
+// ---------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) intop_kernel(uint32_t *out, int iters, uint32_t seed)
+{
+    uint32_t x[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) x[c] = seed + threadIdx.x * 8u + c + blockIdx.x * 2048u;
+    const uint32_t y = seed ^ 0x9e3779b9u;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int c = 0; c < 8; c++) x[c] = (x[c] ^ y) + (x[c] >> 7);      // LOP3, SHF, IADD3
+    }
+    uint32_t acc = 0;
+#pragma unroll
+    for (int c = 0; c < 8; c++) acc ^= x[c];
+    if (acc == 0x12345u) out[0] = acc;                                     // keeps the chains alive
+}
+}  // namespace
+
+int cb_intop_rate_impl(cb_ctx *ctx, double *ops_per_s)
+{
+    cudaStream_t st = ctx->stream;
+    DevBuf<uint32_t> d_out;
+    CB_CUDA(ctx, d_out.alloc(1));
+    const int iters = 4096, grid = ctx->sm_count * 8;
+    intop_kernel<<<grid, 256, 0, st>>>(d_out.p, 64, 1u);                   // warm-up
+    EventTimer t(st);
+    double best = 0.0;
+    for (int rep = 0; rep < 3; rep++) {
+        t.start();
+        intop_kernel<<<grid, 256, 0, st>>>(d_out.p, iters, 2u + rep);
+        t.stop();
+        CB_CUDA(ctx, cudaGetLastError());
+        const double ms = t.ms();
+        const double ops = 3.0 * 8.0 * (double)iters * 256.0 * (double)grid;
+        if (ms > 0 && ops / (ms * 1e-3) > best) best = ops / (ms * 1e-3);
+    }
+    ctx->launches += 4;
+    *ops_per_s = best;
+    return CB_OK;
+}

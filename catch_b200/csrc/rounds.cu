@@ -1004,7 +1004,14 @@ int cb_setcover_rounds_impl(cb_ctx *ctx, const cb_cover *cover, int64_t lo, int6
     if (ctx->xgrid_limit > 0 && grid > ctx->xgrid_limit) grid = ctx->xgrid_limit;   // several ranks on one device (tests)
     void *args[] = {(void *)&G};
     t_greedy.start();
-    CB_CUDA(ctx, cudaLaunchCooperativeKernel((void *)greedy_rounds_kernel, dim3(grid), dim3(RT), args, dyn_smem, st));
+    if (ctx->xgrid_limit > 0 && sharded) {
+        // several ranks share this device (tests): cooperative launches of different streams do not overlap,
+        // so the kernels go out as plain launches; the caller's grid limit keeps all of them co-resident
+        greedy_rounds_kernel<<<grid, RT, dyn_smem, st>>>(G);
+        CB_CUDA(ctx, cudaGetLastError());
+    } else {
+        CB_CUDA(ctx, cudaLaunchCooperativeKernel((void *)greedy_rounds_kernel, dim3(grid), dim3(RT), args, dyn_smem, st));
+    }
     ctx->launches++;
     t_greedy.stop();
     t_all.stop();

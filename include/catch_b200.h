@@ -85,6 +85,10 @@ const char *cb_version(void);
 /* Benchmark hygiene: overwrite a buffer larger than the L2 cache (256 MiB) so the next call
  * starts with a cold L2. */
 int cb_flush_l2(cb_ctx *ctx);
+/* Benchmark calibration: the rate (32-bit integer operations per second, whole chip) at which this GPU
+ * executes independent chains of LOP3 / SHF / IADD3, the instruction mix the scan kernel is bound by.
+ * The denominator of the integer-op roofline bench.py reports beside the HBM one. */
+int cb_intop_rate(cb_ctx *ctx, double *ops_per_s);
 
 /* Page-locked host staging memory owned by the context: slot 0 or 1, at least `bytes` bytes, valid
  * until the next cb_host_buffer call for the same slot with a larger size (or cb_destroy).  Filling
