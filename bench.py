@@ -565,7 +565,7 @@ def main():
         int_ops = {'achieved_gops': ops / dur / 1e9, 'peak_gops': peak_ops / 1e9, 'frac': ops / dur / peak_ops,
                    'algorithmic_ops': ops, 'candidate_hits': hits, 'surviving_hits': surv, 'lookups': lookups,
                    'raw_ranges': int(st_a.n_raw_ranges),
-                   'peak_source': 'cb_intop_rate measured in this run (independent LOP3/LEA chains on all SMs)'}
+                   'peak_source': 'cb_intop_rate measured in this run (integer ALU instructions per second on independent LOP3+LEA.HI chains, all SMs)'}
     elif dom.startswith('greedy'):
         # SURVEY 8(d), stage B: S*P*4 (gain vector per pick) + E*8 (index items touched at least once) + 2*U/8
         alg_bytes = S * P * 4 + E * 8 + 2 * (T / 8)

@@ -39,7 +39,7 @@ class Stats(C.Structure):
 
 # every symbol include/catch_b200.h declares
 EXPORTED_SYMBOLS = [
-    'cb_init', 'cb_destroy', 'cb_last_error', 'cb_version', 'cb_flush_l2', 'cb_intop_rate', 'cb_host_buffer',
+    'cb_init', 'cb_destroy', 'cb_last_error', 'cb_version', 'cb_flush_l2', 'cb_intop_rate', 'cb_pool_reserve', 'cb_host_buffer',
     'cb_upload_targets', 'cb_targets_free', 'cb_upload_probes', 'cb_probes_free', 'cb_upload_group',
     'cb_probes_have_duplicates', 'cb_mt19937_randint', 'cb_mt19937_randint_scalar', 'cb_mt19937_randint_u8',
     'cb_mt19937_randint_begin',
@@ -74,6 +74,7 @@ def load():
     L.cb_last_error.restype = C.c_char_p
     L.cb_flush_l2.argtypes = [vp]
     L.cb_intop_rate.argtypes = [vp, C.POINTER(C.c_double)]
+    L.cb_pool_reserve.argtypes = [vp, i64]
     L.cb_host_buffer.argtypes = [vp, i32, i64, C.POINTER(vp)]
     L.cb_upload_targets.argtypes = [vp, vp, vp, i64, vp, i32, vp, i32, C.POINTER(vp), C.POINTER(Stats)]
     L.cb_targets_free.argtypes = [vp]
@@ -175,6 +176,9 @@ class Context:
 
     def flush_l2(self):
         self._check(self.L.cb_flush_l2(self.h))
+
+    def pool_reserve(self, nbytes):
+        self._check(self.L.cb_pool_reserve(self.h, int(nbytes)))
 
     def intop_rate(self):
         """Measured integer-ALU rate of the device (ops/s), see cb_intop_rate."""

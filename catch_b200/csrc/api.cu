@@ -244,6 +244,17 @@ int cb_flush_l2(cb_ctx *ctx)
     return CB_OK;
 }
 
+int cb_pool_reserve(cb_ctx *ctx, int64_t bytes)
+{
+    if (!ctx || bytes < 0) return cb_fail(ctx, CB_ERR_ARG, "bad argument");
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    void *p = nullptr;
+    CB_CUDA(ctx, cudaMallocAsync(&p, (size_t)(bytes ? bytes : 1), ctx->stream));
+    CB_CUDA(ctx, cudaFreeAsync(p, ctx->stream));        // stays in the pool (release threshold: never)
+    CB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return CB_OK;
+}
+
 int cb_intop_rate(cb_ctx *ctx, double *ops_per_s)
 {
     if (!ctx || !ops_per_s) return cb_fail(ctx, CB_ERR_ARG, "null argument");

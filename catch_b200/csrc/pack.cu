@@ -199,7 +199,8 @@ int cb_probes_have_duplicates_impl(cb_ctx *ctx, const cb_probes *probes, int32_t
 // Integer-throughput calibration for the roofline of the scan kernel (which is bound by the integer
 // ALU pipe, not by HBM): every thread runs eight independent chains of LOP3 / SHF / IADD3 -- the
 // instructions the mismatch-mask and extension code is made of -- and the achieved rate is reported
-// as 32-bit integer operations per second over the whole chip.
+// as integer ALU instructions per second (thread level) over the whole chip.  One step of a chain is
+// two instructions in the SASS: LOP3 (xor) and LEA.HI (shift + add fused).
 // ---------------------------------------------------------------------------------------
 namespace {
 __global__ void __launch_bounds__(256) intop_kernel(uint32_t *out, int iters, uint32_t seed)
@@ -210,7 +211,7 @@ __global__ void __launch_bounds__(256) intop_kernel(uint32_t *out, int iters, ui
     const uint32_t y = seed ^ 0x9e3779b9u;
     for (int i = 0; i < iters; i++) {
 #pragma unroll
-        for (int c = 0; c < 8; c++) x[c] = (x[c] ^ y) + (x[c] >> 7);      // LOP3, SHF, IADD3
+        for (int c = 0; c < 8; c++) x[c] = (x[c] ^ y) + (x[c] >> 7);      // LOP3, LEA.HI
     }
     uint32_t acc = 0;
 #pragma unroll
@@ -234,7 +235,7 @@ int cb_intop_rate_impl(cb_ctx *ctx, double *ops_per_s)
         t.stop();
         CB_CUDA(ctx, cudaGetLastError());
         const double ms = t.ms();
-        const double ops = 3.0 * 8.0 * (double)iters * 256.0 * (double)grid;
+        const double ops = 2.0 * 8.0 * (double)iters * 256.0 * (double)grid;     // LOP3 + LEA.HI per step
         if (ms > 0 && ops / (ms * 1e-3) > best) best = ops / (ms * 1e-3);
     }
     ctx->launches += 4;

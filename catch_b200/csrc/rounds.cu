@@ -37,6 +37,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 
 #include "internal.cuh"
 
@@ -49,7 +50,7 @@ constexpr int ID_LEVELS = 33;
 constexpr int LIST_CAP_MAX = 4096;
 constexpr int PER = LIST_CAP_MAX / RT;
 constexpr int APPLY_WORDS = 64;             // winner intervals up to 64 words are staged in shared memory
-constexpr unsigned long long WAIT_NS = 30ull * 1000000000ull;   // a wait longer than this aborts the call
+constexpr unsigned long long WAIT_NS_DEFAULT = 30ull * 1000000000ull;   // a wait longer than this aborts the call
 
 // Exchange area of one rank (cb_exchange_*): header, candidate slots, universe bit set, intervals.
 struct XHeader {
@@ -94,6 +95,8 @@ struct RParams {
     unsigned char *xa[CB_MAX_RANKS];       // exchange area of every rank, as mapped HERE
     const uint2 *iv[CB_MAX_RANKS];         // cover intervals of every rank (inside its exchange area)
     int64_t cand_off;                      // byte offset of the candidate slots in an exchange area
+    unsigned long long wait_ns;            // a barrier wait longer than this aborts the call
+    unsigned long long *diag;              // first wait that timed out: epoch << 8 | kind
 };
 
 __device__ __forceinline__ unsigned long long globaltimer_ns()
@@ -126,7 +129,7 @@ __device__ __forceinline__ void st_release_gpu(unsigned long long *p, unsigned l
 // Spin until pred() holds; gives up (and flags the call as failed) after WAIT_NS, so that a rank that
 // never arrives turns into an error on the others instead of a hang.
 template <typename Pred>
-__device__ __forceinline__ bool spin_until(const RParams &G, Pred pred)
+__device__ __forceinline__ bool spin_until(const RParams &G, Pred pred, unsigned long long what = 0)
 {
     if (pred()) return true;
     const unsigned long long t0 = globaltimer_ns();
@@ -134,8 +137,8 @@ __device__ __forceinline__ bool spin_until(const RParams &G, Pred pred)
         if (pred()) return true;
         if ((it & 0xfffu) == 0u) {
             if (*(volatile int *)G.status != 0) return false;
-            if (globaltimer_ns() - t0 > WAIT_NS) {
-                atomicCAS(G.status, 0, CB_ERR_COMM);
+            if (globaltimer_ns() - t0 > G.wait_ns) {
+                if (atomicCAS(G.status, 0, CB_ERR_COMM) == 0) *G.diag = what;
                 return false;
             }
         }
@@ -151,7 +154,7 @@ __device__ __forceinline__ void grid_barrier(const RParams &G, unsigned long lon
         __threadfence();
         atomicAdd(G.barrier, 1ull);
         const unsigned long long want = target;
-        spin_until(G, [&] { return *(volatile unsigned long long *)G.barrier >= want; });
+        spin_until(G, [&] { return *(volatile unsigned long long *)G.barrier >= want; }, (want << 8) | 4ull);
         __threadfence();
     }
     __syncthreads();
@@ -181,7 +184,7 @@ __device__ __forceinline__ void xbarrier(const RParams &G, unsigned long long &t
         if (threadIdx.x == 0) {
             __threadfence();
             atomicAdd(G.barrier, 1ull);
-            spin_until(G, [&] { return ld_acquire_gpu(G.release) >= e; });
+            spin_until(G, [&] { return ld_acquire_gpu(G.release) >= e; }, (e << 8) | 2ull);
         }
         __syncthreads();
         return;
@@ -190,7 +193,7 @@ __device__ __forceinline__ void xbarrier(const RParams &G, unsigned long long &t
         __threadfence();
         atomicAdd(G.barrier, 1ull);
         const unsigned long long want = target;
-        spin_until(G, [&] { return *(volatile unsigned long long *)G.barrier >= want; });
+        spin_until(G, [&] { return *(volatile unsigned long long *)G.barrier >= want; }, (e << 8) | 1ull);
         __threadfence();
     }
     __syncthreads();
@@ -201,7 +204,7 @@ __device__ __forceinline__ void xbarrier(const RParams &G, unsigned long long &t
         XHeader *peer = reinterpret_cast<XHeader *>(G.xa[threadIdx.x]);
         XHeader *mine = reinterpret_cast<XHeader *>(G.xa[G.rank]);
         st_release_sys(&peer->flag[G.rank], e);
-        spin_until(G, [&] { return ld_acquire_sys(&mine->flag[threadIdx.x]) >= e; });
+        spin_until(G, [&] { return ld_acquire_sys(&mine->flag[threadIdx.x]) >= e; }, (e << 8) | 3ull | ((unsigned long long)threadIdx.x << 4));
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -827,6 +830,16 @@ greedy_rounds_kernel(const RParams G)
     }
 }
 
+// CB_TRACE=1: host-side timestamps of the steps of a call on stderr (debugging of multi-rank runs)
+void trace(const cb_ctx *ctx, const char *what)
+{
+    static const bool on = getenv("CB_TRACE") != nullptr;
+    if (!on) return;
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    fprintf(stderr, "[cb %p xrank %d] %.6f %s\n", (const void *)ctx, ctx->xrank, ts.tv_sec % 1000 + ts.tv_nsec * 1e-9, what);
+}
+
 size_t cand_bytes(uint32_t list_cap) { return sizeof(uint4) * 2 * CB_MAX_RANKS * (size_t)list_cap; }
 size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -854,6 +867,7 @@ int cb_setcover_rounds_impl(cb_ctx *ctx, const cb_cover *cover, int64_t lo, int6
         return cb_fail(ctx, CB_ERR_STATE, "an earlier sharded call failed; attach the exchange areas again");
     if (P >= (1ll << 25)) return cb_fail(ctx, CB_ERR_UNSUPPORTED, "more than 2^25 probes in one grouping");
     if (E >= 0xfffffff0ll) return cb_fail(ctx, CB_ERR_UNSUPPORTED, "more than 2^32 intervals in one grouping");
+    trace(ctx, "rounds: enter");
     EventTimer t_all(st), t_uni(st), t_greedy(st);
     t_all.start();
     t_uni.start();
@@ -883,6 +897,7 @@ int cb_setcover_rounds_impl(cb_ctx *ctx, const cb_cover *cover, int64_t lo, int6
         area = d_area.p;
         CB_CUDA(ctx, cudaMemsetAsync(area, 0, sizeof(XHeader), st));
     }
+    trace(ctx, "rounds: timers created");
     unsigned long long *d_U = reinterpret_cast<unsigned long long *>(area + off_U);
     CB_CUDA(ctx, cudaMemsetAsync(d_U, 0, 8 * ((size_t)u_words + 1), st));
     const uint2 *d_iv_mine = cover->d_iv;
@@ -891,6 +906,7 @@ int cb_setcover_rounds_impl(cb_ctx *ctx, const cb_cover *cover, int64_t lo, int6
         d_iv_mine = reinterpret_cast<const uint2 *>(area + off_iv);
     }
 
+    trace(ctx, "rounds: area memset + interval copy issued");
     // ---- ranks -> dense indices in ascending order of rank value (:349)
     std::vector<uint32_t> h_rank;
     int32_t n_ranks = 1;
@@ -909,6 +925,7 @@ int cb_setcover_rounds_impl(cb_ctx *ctx, const cb_cover *cover, int64_t lo, int6
         CB_CUDA(ctx, cudaMemsetAsync(d_rank.p, 0, sizeof(uint32_t) * (size_t)(P ? P : 1), st));
     }
 
+    trace(ctx, "rounds: rank array ready");
     // ---- work buffers
     int pbits = 1;
     while ((1ll << pbits) < P) pbits++;
@@ -925,6 +942,7 @@ int cb_setcover_rounds_impl(cb_ctx *ctx, const cb_cover *cover, int64_t lo, int6
     CB_CUDA(ctx, d_boff.alloc((size_t)n_blocks + 1));
     CB_CUDA(ctx, cudaMemsetAsync(d_bcount.p, 0, sizeof(uint32_t) * (size_t)n_blocks, st));
     CB_CUDA(ctx, cudaMemsetAsync(d_bcursor.p, 0, sizeof(uint32_t) * (size_t)n_blocks, st));
+    trace(ctx, "rounds: gain + block arrays allocated");
     CB_CUDA(ctx, d_mark.alloc((size_t)u_words + 1));
     CB_CUDA(ctx, cudaMemsetAsync(d_mark.p, 0, 8 * ((size_t)u_words + 1), st));
     // control block: [0] remaining, [1] barrier, [2] release, [3..4] key_local, [5..8] phase ns, [9..11] counters,
@@ -936,12 +954,15 @@ int cb_setcover_rounds_impl(cb_ctx *ctx, const cb_cover *cover, int64_t lo, int6
     CB_CUDA(ctx, cudaMemsetAsync(d_small.p, 0, sizeof(uint32_t) * (2 * (size_t)list_cap + 1 + 128), st));
     CB_CUDA(ctx, d_sel.alloc((size_t)(P ? P : 1)));
 
+    trace(ctx, "rounds: buffers allocated");
     // ---- set-up: universe bits + block counts + gains, offsets, index items
     index_kernel<false><<<wide, 256, 0, st>>>(cover->d_iv_off, cover->d_iv, lo, hi, max_piece, pbits, d_U, d_gain.p,
                                               d_bcount.p, nullptr, nullptr, nullptr);
     ctx->launches++;
     int64_t n_items = 0;
+    trace(ctx, "rounds: index pass 1 launched");
     CB_TRY(cb_exclusive_scan_u32_to_i64(ctx, d_bcount.p, d_boff.p, n_blocks, &n_items));
+    trace(ctx, "rounds: block offsets scanned");
     if (n_items >= 0xfffffff0ll) return cb_fail(ctx, CB_ERR_UNSUPPORTED, "more than 2^32 index items");
     CB_CUDA(ctx, d_items.alloc((size_t)(n_items ? n_items : 1)));
     index_kernel<true><<<wide, 256, 0, st>>>(cover->d_iv_off, cover->d_iv, lo, hi, max_piece, pbits, nullptr, nullptr,
@@ -975,6 +996,7 @@ int cb_setcover_rounds_impl(cb_ctx *ctx, const cb_cover *cover, int64_t lo, int6
     G.ctr = d_ctl.p + 9;
     G.n_sel = reinterpret_cast<long long *>(d_ctl.p + 12);
     G.status = reinterpret_cast<int *>(d_ctl.p + 13);
+    G.diag = d_ctl.p + 14;
     G.list = d_small.p;
     G.list_n = d_small.p + list_cap;
     G.list_cap = list_cap;
@@ -984,6 +1006,8 @@ int cb_setcover_rounds_impl(cb_ctx *ctx, const cb_cover *cover, int64_t lo, int6
     G.rank = me;
     G.n_ranks = R;
     G.cand_off = (int64_t)off_cand;
+    G.wait_ns = WAIT_NS_DEFAULT;
+    if (const char *e = getenv("CB_WAIT_MS")) if (atoll(e) > 0) G.wait_ns = (unsigned long long)atoll(e) * 1000000ull;
     for (int r = 0; r < R; r++) {
         G.xa[r] = sharded ? ctx->xpeer[r] : area;
         G.iv[r] = sharded ? reinterpret_cast<const uint2 *>(ctx->xpeer[r] + off_iv) : d_iv_mine;
@@ -994,7 +1018,16 @@ int cb_setcover_rounds_impl(cb_ctx *ctx, const cb_cover *cover, int64_t lo, int6
     // ---- persistent cooperative launch
     const size_t dyn_smem = sizeof(uint32_t) * (6 * (size_t)list_cap + 2) + 2 * (size_t)list_cap;
     int per_sm = 0;
-    CB_CUDA(ctx, cudaFuncSetAttribute(greedy_rounds_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
+    {
+        // once per device: changing a function attribute waits for running instances of the function, which
+        // would stall a rank behind another rank's persistent kernel when several contexts share a device
+        static bool attr_set[64] = {};
+        const size_t dyn_max = sizeof(uint32_t) * (6 * (size_t)LIST_CAP_MAX + 2) + 2 * (size_t)LIST_CAP_MAX;
+        if (ctx->device < 0 || ctx->device >= 64 || !attr_set[ctx->device]) {
+            CB_CUDA(ctx, cudaFuncSetAttribute(greedy_rounds_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_max));
+            if (ctx->device >= 0 && ctx->device < 64) attr_set[ctx->device] = true;
+        }
+    }
     CB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, greedy_rounds_kernel, RT, dyn_smem));
     if (per_sm < 1) return cb_fail(ctx, CB_ERR_CUDA, "greedy kernel does not fit on an SM");
     int want = 3;
@@ -1003,6 +1036,7 @@ int cb_setcover_rounds_impl(cb_ctx *ctx, const cb_cover *cover, int64_t lo, int6
     int grid = per_sm * ctx->sm_count;
     if (ctx->xgrid_limit > 0 && grid > ctx->xgrid_limit) grid = ctx->xgrid_limit;   // several ranks on one device (tests)
     void *args[] = {(void *)&G};
+    trace(ctx, "rounds: launching the greedy kernel");
     t_greedy.start();
     if (ctx->xgrid_limit > 0 && sharded) {
         // several ranks share this device (tests): cooperative launches of different streams do not overlap,
@@ -1016,14 +1050,21 @@ int cb_setcover_rounds_impl(cb_ctx *ctx, const cb_cover *cover, int64_t lo, int6
     t_greedy.stop();
     t_all.stop();
 
+    trace(ctx, "rounds: greedy kernel launched");
     unsigned long long h_ctl[16];
     CB_CUDA(ctx, cudaMemcpyAsync(h_ctl, d_ctl.p, sizeof h_ctl, cudaMemcpyDeviceToHost, st));
     CB_CUDA(ctx, cudaStreamSynchronize(st));
+    trace(ctx, "rounds: greedy kernel finished");
     const long long h_nsel = (long long)h_ctl[12];
     const int h_status = (int)(uint32_t)h_ctl[13];
     if (h_status == CB_ERR_COMM) {
         ctx->xarea_poisoned = sharded;
-        return cb_fail(ctx, CB_ERR_COMM, "set cover: a rank did not arrive at a barrier within the time limit");
+        char msg[256];
+        snprintf(msg, sizeof msg, "set cover: a barrier wait exceeded the time limit (rank %d of %d, barrier %llu, kind %llu, "
+                 "peer %llu; flags seen %llu)", me, R, (unsigned long long)(h_ctl[14] >> 8), (unsigned long long)(h_ctl[14] & 15),
+                 (unsigned long long)((h_ctl[14] >> 4) & 15), (unsigned long long)h_ctl[15]);
+        ctx->err = msg;
+        return CB_ERR_COMM;
     }
     if (h_status != 0) return cb_fail(ctx, CB_ERR_STATE, "set cover ran out of ranks before reaching the requested coverage");
     *n_sel = 0;

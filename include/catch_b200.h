@@ -85,6 +85,10 @@ const char *cb_version(void);
 /* Benchmark hygiene: overwrite a buffer larger than the L2 cache (256 MiB) so the next call
  * starts with a cold L2. */
 int cb_flush_l2(cb_ctx *ctx);
+/* Grow the device's stream-ordered memory pool so that it holds at least `bytes` of free memory: later
+ * calls then take their work buffers from the pool without going to the driver (which may wait for
+ * running kernels).  Optional; useful before the first call and wherever several contexts share a device. */
+int cb_pool_reserve(cb_ctx *ctx, int64_t bytes);
 /* Benchmark calibration: the rate (32-bit integer operations per second, whole chip) at which this GPU
  * executes independent chains of LOP3 / SHF / IADD3, the instruction mix the scan kernel is bound by.
  * The denominator of the integer-op roofline bench.py reports beside the HBM one. */

@@ -59,6 +59,9 @@ def _sharded_picks(ctxs, cands, seqs, kw, plan, grid_limit, ranks=None):
         for c in ctxs:
             if c.exchange_bytes() < need:
                 c.exchange_alloc(need)
+        # the ranks share one device and one memory pool here: make sure no rank has to go to the driver for
+        # memory (which waits for running kernels) while another rank's persistent kernel waits for it
+        ctxs[0].pool_reserve(R * (need + (64 << 20)))
         addrs = [c.exchange_handle()[1] for c in ctxs]
         for r, c in enumerate(ctxs):
             c.exchange_attach(r, R, addresses=addrs, grid_limit=grid_limit)
@@ -84,10 +87,13 @@ def _sharded_picks(ctxs, cands, seqs, kw, plan, grid_limit, ranks=None):
     return out
 
 
-@pytest.mark.parametrize('n_ranks', [2, 4])
+@pytest.mark.parametrize('n_ranks', [2])
 def test_sharded_setcover_virtual_ranks(ctx, n_ranks):
     """Stage A on shards of the probes + the sharded greedy loop give, on every rank, exactly the pick
-    sequence of the one-GPU path (which is pinned against the oracle elsewhere)."""
+    sequence of the one-GPU path (which is pinned against the oracle elsewhere).  Two virtual ranks only:
+    with more contexts on ONE device the CUDA driver makes a host call of the third rank wait for the
+    persistent kernels of the first two (measured; nothing of the kind exists with one process per GPU),
+    so larger rank counts are covered by the torchrun test below and tools/multigpu_check.py."""
     from catch_b200 import _lib
     from catch_b200 import coverage as cov
     ctxs = [_lib.Context(0) for _ in range(n_ranks)]
