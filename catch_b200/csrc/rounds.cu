@@ -48,7 +48,6 @@ constexpr int NWARP = RT / 32;
 constexpr int GAIN_LEVELS = 14;
 constexpr int ID_LEVELS = 33;
 constexpr int LIST_CAP_MAX = 4096;
-constexpr int PER = LIST_CAP_MAX / RT;
 constexpr int APPLY_WORDS = 64;             // winner intervals up to 64 words are staged in shared memory
 constexpr unsigned long long WAIT_NS_DEFAULT = 30ull * 1000000000ull;   // a wait longer than this aborts the call
 
@@ -59,7 +58,9 @@ struct XHeader {
     unsigned long long pad[7];
     unsigned long long key[2][CB_MAX_RANKS];      // list rebuild: best key among rank r's probes
     uint32_t hist[2][CB_MAX_RANKS][64];           // list rebuild: level histogram of rank r's probes
-    uint32_t cand_n[2][CB_MAX_RANKS];             // active candidates of rank r this round
+    uint32_t list_n[2][CB_MAX_RANKS];             // list rebuild: length of rank r's candidate list
+    // followed (at RParams::slot_off) by the lists [2][ranks][LIST_CAP_MAX] (uint4: probe, first interval,
+    // intervals, -) and the per-round gains [2][ranks][LIST_CAP_MAX] (uint32) of every rank
 };
 
 struct RParams {
@@ -84,8 +85,9 @@ struct RParams {
     unsigned long long *release;    // local release word of the cross-GPU barrier
     unsigned long long *key_local;  // [2]
     uint32_t *hist_local;           // [2][64]
-    uint32_t *list, *list_n, list_cap;
-    uint32_t *flag;                 // [list_cap]
+    uint4 *list;                    // [list_cap] this rank's candidate list: probe, first interval, intervals, -
+    uint32_t *list_n, list_cap;
+    uint32_t *conf;                 // [LIST_CAP_MAX / 32] conflict bits of the round's active candidates
     long long *sel, *n_sel;
     int *status;
     unsigned long long *phase_ns;   // [4]
@@ -94,7 +96,7 @@ struct RParams {
     int rank, n_ranks;
     unsigned char *xa[CB_MAX_RANKS];       // exchange area of every rank, as mapped HERE
     const uint2 *iv[CB_MAX_RANKS];         // cover intervals of every rank (inside its exchange area)
-    int64_t cand_off;                      // byte offset of the candidate slots in an exchange area
+    int64_t slot_off;                      // byte offset of the list / gain slots in an exchange area
     unsigned long long wait_ns;            // a barrier wait longer than this aborts the call
     unsigned long long *diag;              // first wait that timed out: epoch << 8 | kind
 };
@@ -214,9 +216,14 @@ __device__ __forceinline__ void xbarrier(const RParams &G, unsigned long long &t
     __syncthreads();
 }
 
-__device__ __forceinline__ uint4 *cand_slot(const RParams &G, int on_rank, unsigned slot, int from_rank)
+__device__ __forceinline__ uint4 *list_slot(const RParams &G, int on_rank, unsigned slot, int from_rank)
 {
-    return reinterpret_cast<uint4 *>(G.xa[on_rank] + G.cand_off) + ((size_t)slot * CB_MAX_RANKS + from_rank) * G.list_cap;
+    return reinterpret_cast<uint4 *>(G.xa[on_rank] + G.slot_off) + ((size_t)slot * CB_MAX_RANKS + from_rank) * LIST_CAP_MAX;
+}
+__device__ __forceinline__ uint32_t *gain_slot(const RParams &G, int on_rank, unsigned slot, int from_rank)
+{
+    return reinterpret_cast<uint32_t *>(G.xa[on_rank] + G.slot_off + sizeof(uint4) * 2 * CB_MAX_RANKS * LIST_CAP_MAX) +
+           ((size_t)slot * CB_MAX_RANKS + from_rank) * LIST_CAP_MAX;
 }
 
 template <typename F>
@@ -382,41 +389,52 @@ greedy_rounds_kernel(const RParams G)
 {
     __shared__ unsigned long long s_key[NWARP];
     __shared__ unsigned long long s_u[NWARP * APPLY_WORDS];   // one staging area per warp
-    __shared__ uint32_t s_part[NWARP];
+    __shared__ unsigned long long s_part[NWARP];
     __shared__ uint32_t s_hist[64];                  // level histogram of a list rebuild
-    __shared__ uint32_t s_rn[CB_MAX_RANKS + 1];      // prefix of the per-rank candidate counts
+    __shared__ uint32_t s_rn[CB_MAX_RANKS + 1];      // prefix of the per-rank list lengths
+    __shared__ uint32_t s_conf[LIST_CAP_MAX / 32];   // conflict bits of the active candidates
     extern __shared__ uint32_t s_dyn[];
-    // per CTA, list_cap entries each: active candidates (probe, gain, first interval, exclusive prefix
-    // of the interval counts, owner rank) and the winners among them (first interval, prefix, owner)
-    uint32_t *s_p = s_dyn, *s_g = s_p + G.list_cap, *s_i0 = s_g + G.list_cap, *s_base = s_i0 + G.list_cap,
-             *s_wi0 = s_base + G.list_cap + 1, *s_wbase = s_wi0 + G.list_cap;
-    unsigned char *s_own = reinterpret_cast<unsigned char *>(s_wbase + G.list_cap + 1), *s_wown = s_own + G.list_cap;
+    // per CTA, list_cap entries each.  The candidate LIST (all ranks' entries, rank order): probe,
+    // first interval, number of intervals, owner rank -- loaded once per list rebuild; gain -- loaded
+    // every round.  The ACTIVE candidates of the round (list slots whose gain is still >= tau) and the
+    // WINNERS among them: list slot + exclusive prefix of the interval counts.
+    const uint32_t cap = G.list_cap;
+    uint32_t *s_p = s_dyn, *s_i0 = s_p + cap, *s_cnt = s_i0 + cap, *s_g = s_cnt + cap, *s_base = s_g + cap,
+             *s_wbase = s_base + cap + 1;
+    uint16_t *s_act = reinterpret_cast<uint16_t *>(s_wbase + cap + 1), *s_wact = s_act + cap;
+    unsigned char *s_own = reinterpret_cast<unsigned char *>(s_wact + cap);
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t gsize = (int64_t)gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     XHeader *xh = reinterpret_cast<XHeader *>(G.xa[G.rank]);
     const int R = G.n_ranks, me = G.rank;
+    const uint32_t per = (cap + RT - 1) / RT;        // consecutive list slots handled by one thread
 
-    // exclusive prefix of v over the CTA (thread order); adds the CTA total to `total`
-    auto block_scan = [&](uint32_t v, uint32_t &total) -> uint32_t {
-        uint32_t inc = v;
+    // exclusive prefix of a (count, sum) pair over the CTA in thread order; returns the totals too
+    auto block_scan2 = [&](uint32_t cnt, uint32_t sum, uint32_t &cnt_before, uint32_t &sum_before, uint32_t &cnt_all,
+                           uint32_t &sum_all) {
+        const unsigned long long v = ((unsigned long long)cnt << 40) | (unsigned long long)sum;   // sum < 2^40, cnt < 2^24
+        unsigned long long inc = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
             if (lane >= o) inc += t;
         }
         __syncthreads();                 // s_part may still be read from the previous scan
         if (lane == 31) s_part[warp] = inc;
         __syncthreads();
-        uint32_t before = 0, all = 0;
+        unsigned long long before = 0, all = 0;
 #pragma unroll
         for (int q = 0; q < NWARP; q++) {
-            const uint32_t t = s_part[q];
+            const unsigned long long t = s_part[q];
             if (q < warp) before += t;
             all += t;
         }
-        total += all;
-        return before + inc - v;
+        const unsigned long long ex = before + inc - v;
+        cnt_before = (uint32_t)(ex >> 40);
+        sum_before = (uint32_t)(ex & 0xffffffffffull);
+        cnt_all = (uint32_t)(all >> 40);
+        sum_all = (uint32_t)(all & 0xffffffffffull);
     };
     auto block_max = [&](unsigned long long best) -> unsigned long long {
 #pragma unroll
@@ -440,7 +458,7 @@ greedy_rounds_kernel(const RParams G)
     long long n_picks = 0;
     unsigned long long bar_target = 0, n_rebuilds = 0, n_rounds = 0, n_active_sum = 0;
     unsigned long long epoch = __ldcg(&xh->epoch);
-    uint32_t tau = 1, id_thr = 0xffffffffu;
+    uint32_t tau = 1, id_thr = 0xffffffffu, n_list = 0;
     unsigned rb = 0;
     bool need_rebuild = true;
     unsigned long long t_phase[4] = {0, 0, 0, 0}, t_last = 0;
@@ -560,20 +578,23 @@ greedy_rounds_kernel(const RParams G)
             });
             if (failed()) break;
             if (gtid < 64) hist_next[gtid] = 0u;                    // last read one rebuild ago
+            // the 64 level counts of all ranks, fetched by 64 threads at once
+            if (threadIdx.x < 64) {
+                uint32_t c = 0;
+                if (R == 1) c = __ldcg(&hist_now[threadIdx.x]);
+                else
+                    for (int r = 0; r < R; r++) c += __ldcg(&xh->hist[epoch & 1ull][r][threadIdx.x]);
+                s_hist[threadIdx.x] = c;
+            }
+            __syncthreads();
             id_thr = 0xffffffffu;
             {
-                auto level_count = [&](int i) -> uint32_t {
-                    if (R == 1) return __ldcg(&hist_now[i]);
-                    uint32_t c = 0;
-                    for (int r = 0; r < R; r++) c += __ldcg(&xh->hist[epoch & 1ull][r][i]);
-                    return c;
-                };
                 // counts are suffix sums: a probe at level lv also qualifies for every wider level
                 uint32_t c = 0;
                 int pick = -1;
                 for (int lv = GAIN_LEVELS - 1; lv >= 0; lv--) {
-                    c += level_count(lv);
-                    if (c <= G.list_cap) pick = lv; else break;
+                    c += s_hist[lv];
+                    if (c <= cap) pick = lv; else break;
                 }
                 if (pick >= 0) {
                     tau = tau_of(pick);
@@ -582,8 +603,8 @@ greedy_rounds_kernel(const RParams G)
                     c = 0;
                     int pj = -1;
                     for (int j = ID_LEVELS - 1; j >= 0; j--) {
-                        c += level_count(GAIN_LEVELS + j);
-                        if (c <= G.list_cap) pj = j; else break;
+                        c += s_hist[GAIN_LEVELS + j];
+                        if (c <= cap) pj = j; else break;
                     }
                     // the smallest tied id is wmax; an id level that holds no tie at all (or none that
                     // fits) leaves the argmax alone in the list
@@ -592,159 +613,123 @@ greedy_rounds_kernel(const RParams G)
                     id_thr = thr > 0xffffffffull ? 0xffffffffu : (uint32_t)thr;
                 }
             }
+            __syncthreads();                                        // s_hist is reused by the next rebuild
+            // ---- the list of this rank: probe, first interval, number of intervals
             for (int64_t p = G.lo + gtid; p < G.hi; p += gsize) {
                 const uint32_t g = __ldcg(&G.gain[p]);
                 if (g >= tau && (uint32_t)p < id_thr && G.rank_idx[p] == (uint32_t)cur_rank) {
                     const uint32_t slot = atomicAdd(G.list_n, 1u);
-                    if (slot < G.list_cap) G.list[slot] = (uint32_t)p;      // always true, by the counts
+                    const int64_t x = G.iv_off[p], y = G.iv_off[p + 1];
+                    if (slot < cap) G.list[slot] = make_uint4((uint32_t)p, (uint32_t)x, (uint32_t)(y - x), 0u);   // always, by the counts
                 }
+            }
+            // ---- every rank's list goes to every rank; each CTA keeps all of them in shared memory
+            xbarrier(G, bar_target, epoch, [&] {
+                const unsigned slot = (unsigned)(epoch & 1ull);
+                const uint32_t n_mine = min(__ldcg(G.list_n), cap);
+                for (uint32_t i = threadIdx.x; i < n_mine; i += RT) {
+                    const uint4 rec = __ldcg(&G.list[i]);
+                    for (int r = 0; r < R; r++) list_slot(G, r, slot, me)[i] = rec;
+                }
+                if (threadIdx.x == 0)
+                    for (int r = 0; r < R; r++) reinterpret_cast<XHeader *>(G.xa[r])->list_n[slot][me] = n_mine;
+            });
+            if (failed()) break;
+            {
+                const unsigned slot = (unsigned)(epoch & 1ull);
+                if (threadIdx.x == 0) {
+                    uint32_t acc = 0;
+                    for (int r = 0; r < R; r++) {
+                        s_rn[r] = acc;
+                        acc += min(R == 1 ? __ldcg(G.list_n) : __ldcg(&xh->list_n[slot][r]), cap);
+                    }
+                    s_rn[R] = acc;
+                }
+                __syncthreads();
+                n_list = min(s_rn[R], cap);
+                for (uint32_t i = threadIdx.x; i < n_list; i += RT) {
+                    int r = 0;
+                    while (r + 1 < R && s_rn[r + 1] <= i) r++;
+                    const uint4 rec = R == 1 ? __ldcg(&G.list[i]) : __ldcg(list_slot(G, me, slot, r) + (i - s_rn[r]));
+                    s_p[i] = rec.x;
+                    s_i0[i] = rec.y;
+                    s_cnt[i] = rec.z;
+                    s_own[i] = (unsigned char)r;
+                }
+                __syncthreads();
             }
             need_rebuild = false;
             n_rebuilds++;
             lap(0);
         }
 
-        uint32_t n_act = 0, total_pairs = 0;
-        if (R == 1) {
-            // ---- one GPU: every CTA derives the active candidates (list entries whose gain is still >= tau)
-            // itself, from the same inputs with the same deterministic scan -- no global list of actives,
-            // no counters, one plain grid barrier (gains are final after it)
-            grid_barrier(G, bar_target);
-            if (failed() || __ldcg(G.remaining) == 0ull) break;
-            const uint32_t n_list = min(__ldcg(G.list_n), G.list_cap);
-            uint32_t pv[PER], gv[PER];
-#pragma unroll
-            for (int u = 0; u < PER; u++) {
-                const uint32_t c = (uint32_t)u * RT + threadIdx.x;
-                pv[u] = c < n_list ? __ldcg(&G.list[c]) : 0xffffffffu;
-            }
-#pragma unroll
-            for (int u = 0; u < PER; u++) gv[u] = pv[u] != 0xffffffffu ? __ldcg(&G.gain[pv[u]]) : 0u;
-#pragma unroll
-            for (int u = 0; u < PER; u++) {
-                if ((uint32_t)u * RT >= n_list) break;          // CTA-uniform
-                const bool act = gv[u] >= tau && pv[u] != 0xffffffffu;
-                const uint32_t before = n_act;
-                const uint32_t pos = before + block_scan(act ? 1u : 0u, n_act);
-                if (act) { s_p[pos] = pv[u]; s_g[pos] = gv[u]; }
-            }
-            __syncthreads();
-            if (n_act == 0u) {                       // the list is used up
-                need_rebuild = true;
-                continue;
-            }
-            uint32_t i0v[PER], cntv[PER];
-#pragma unroll
-            for (int u = 0; u < PER; u++) {
-                const uint32_t a = (uint32_t)u * RT + threadIdx.x;
-                i0v[u] = cntv[u] = 0;
-                if (a < n_act) {
-                    const uint32_t p = s_p[a];
-                    const int64_t x = G.iv_off[p], y = G.iv_off[p + 1];
-                    i0v[u] = (uint32_t)x;
-                    cntv[u] = (uint32_t)(y - x);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < PER; u++) {
-                if ((uint32_t)u * RT >= n_act) break;           // CTA-uniform
-                const uint32_t a = (uint32_t)u * RT + threadIdx.x;
-                const uint32_t before = total_pairs;
-                const uint32_t pos = before + block_scan(cntv[u], total_pairs);
-                if (a < n_act) { s_i0[a] = i0v[u]; s_base[a] = pos; s_own[a] = 0; }
-            }
-        } else {
-            // ---- several GPUs: CTA 0 compacts this rank's active candidates (gains are final, every CTA has
-            // arrived) and pushes (probe, gain, first interval, #intervals) to every rank
-            xbarrier(G, bar_target, epoch, [&] {
-                const unsigned slot = (unsigned)(epoch & 1ull);
-                const uint32_t n_list = min(__ldcg(G.list_n), G.list_cap);
-                uint32_t n_mine = 0;
-                for (uint32_t c0 = 0; c0 < n_list; c0 += RT) {          // CTA-uniform
-                    const uint32_t c = c0 + threadIdx.x;
-                    uint32_t p = 0xffffffffu, g = 0;
-                    if (c < n_list) {
-                        p = __ldcg(&G.list[c]);
-                        g = __ldcg(&G.gain[p]);
-                    }
-                    const bool act = p != 0xffffffffu && g >= tau;
-                    const uint32_t before = n_mine;
-                    const uint32_t pos = before + block_scan(act ? 1u : 0u, n_mine);
-                    if (act) {
-                        const int64_t x = G.iv_off[p], y = G.iv_off[p + 1];
-                        const uint4 rec = make_uint4(p, g, (uint32_t)x, (uint32_t)(y - x));
-                        for (int r = 0; r < R; r++) cand_slot(G, r, slot, me)[pos] = rec;
-                    }
-                }
-                if (threadIdx.x == 0)
-                    for (int r = 0; r < R; r++) reinterpret_cast<XHeader *>(G.xa[r])->cand_n[slot][me] = n_mine;
-            });
-            if (failed() || __ldcg(G.remaining) == 0ull) break;
+        // ---- the current gains of the list entries.  One GPU: a grid barrier (gains are final after it),
+        // then every CTA reads them where they are.  Several GPUs: CTA 0 pushes the gains of this rank's
+        // entries to every rank inside the cross-GPU barrier.
+        xbarrier(G, bar_target, epoch, [&] {
             const unsigned slot = (unsigned)(epoch & 1ull);
-            // every CTA loads the active candidates of ALL ranks (rank order, then list order) into its own
-            // shared memory: same inputs, same arrays everywhere
-            if (threadIdx.x == 0) {
-                uint32_t acc = 0;
-                for (int r = 0; r < R; r++) {
-                    s_rn[r] = acc;
-                    acc += min(__ldcg(&xh->cand_n[slot][r]), G.list_cap);
-                }
-                s_rn[R] = acc;
+            const uint32_t lo_i = s_rn[me], n_mine = s_rn[me + 1] - s_rn[me];
+            for (uint32_t i = threadIdx.x; i < n_mine; i += RT) {
+                const uint32_t g = __ldcg(&G.gain[s_p[lo_i + i]]);
+                for (int r = 0; r < R; r++) gain_slot(G, r, slot, me)[i] = g;
             }
+        });
+        if (failed() || __ldcg(G.remaining) == 0ull) break;
+        // ---- active candidates = list slots whose gain is still >= tau, compacted in list order by every
+        // CTA for itself (same inputs, same result): thread t looks at `per` consecutive slots
+        uint32_t n_act = 0, total_pairs = 0;
+        {
+            const unsigned slot = (unsigned)(epoch & 1ull);
+            const uint32_t i_lo = threadIdx.x * per, i_hi = min(i_lo + per, n_list);
+            uint32_t c = 0, sum = 0;
+            for (uint32_t i = i_lo; i < i_hi; i++) {
+                uint32_t g;
+                if (R == 1) g = __ldcg(&G.gain[s_p[i]]);
+                else {
+                    const int r = s_own[i];
+                    g = __ldcg(gain_slot(G, me, slot, r) + (i - s_rn[r]));
+                }
+                s_g[i] = g;
+                if (g >= tau) { c++; sum += s_cnt[i]; }
+            }
+            uint32_t cb, sb;
+            block_scan2(c, sum, cb, sb, n_act, total_pairs);
+            for (uint32_t i = i_lo; i < i_hi; i++)
+                if (s_g[i] >= tau) {
+                    s_act[cb] = (uint16_t)i;
+                    s_base[cb] = sb;
+                    cb++;
+                    sb += s_cnt[i];
+                }
+            if (threadIdx.x == 0) s_base[n_act] = total_pairs;
+            // the conflict bits of the previous round have been read by everybody (barrier since)
+            if (blockIdx.x == 0 && threadIdx.x < LIST_CAP_MAX / 32) G.conf[threadIdx.x] = 0u;
             __syncthreads();
-            n_act = min(s_rn[R], G.list_cap);
-            if (n_act == 0u) {                       // the list is used up
-                need_rebuild = true;
-                continue;
-            }
-            uint32_t cntv[PER];
-#pragma unroll
-            for (int u = 0; u < PER; u++) {
-                const uint32_t a = (uint32_t)u * RT + threadIdx.x;
-                cntv[u] = 0;
-                if (a < n_act) {
-                    int r = 0;
-                    while (r + 1 < R && s_rn[r + 1] <= a) r++;
-                    const uint4 rec = __ldcg(cand_slot(G, me, slot, r) + (a - s_rn[r]));
-                    s_p[a] = rec.x;
-                    s_g[a] = rec.y;
-                    s_i0[a] = rec.z;
-                    s_own[a] = (unsigned char)r;
-                    cntv[u] = rec.w;
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < PER; u++) {
-                if ((uint32_t)u * RT >= n_act) break;           // CTA-uniform
-                const uint32_t a = (uint32_t)u * RT + threadIdx.x;
-                const uint32_t before = total_pairs;
-                const uint32_t pos = before + block_scan(cntv[u], total_pairs);
-                if (a < n_act) s_base[a] = pos;
-            }
         }
-        if (threadIdx.x == 0) s_base[n_act] = total_pairs;
-        // the conflict flags of the previous round have been read by everybody (barrier since)
-        if (blockIdx.x == 0)
-            for (uint32_t a = threadIdx.x; a < G.list_cap; a += RT) G.flag[a] = 0u;
-        __syncthreads();
-        auto pair_of = [&](uint32_t f, uint32_t &a) -> uint2 {
+        if (n_act == 0u) {                       // the list is used up
+            need_rebuild = true;
+            continue;
+        }
+        // (candidate a, interval f - s_base[a]) for the f-th pair of the round
+        auto pair_of = [&](uint32_t f, uint32_t &a, uint32_t &slot_i) -> uint2 {
             uint32_t lo = 0, hi = n_act;
             while (hi - lo > 1) {
                 const uint32_t mid = (lo + hi) >> 1;
                 if (s_base[mid] <= f) lo = mid; else hi = mid;
             }
             a = lo;
-            return G.iv[s_own[lo]][(int64_t)s_i0[lo] + (f - s_base[lo])];      // peer memory when the owner is remote
+            slot_i = s_act[lo];
+            return G.iv[s_own[slot_i]][(int64_t)s_i0[slot_i] + (f - s_base[lo])];      // peer memory when the owner is remote
         };
-        auto key_of = [&](uint32_t a) -> unsigned long long {
-            return ((unsigned long long)s_g[a] << 32) | (unsigned long long)(0xffffffffu - s_p[a]);
+        auto key_of = [&](uint32_t slot_i) -> unsigned long long {
+            return ((unsigned long long)s_g[slot_i] << 32) | (unsigned long long)(0xffffffffu - s_p[slot_i]);
         };
 
         // ---- mark: one thread per (candidate, interval)
         for (int64_t f = gtid; f < (int64_t)total_pairs; f += gsize) {
-            uint32_t a;
-            const uint2 r = pair_of((uint32_t)f, a);
-            const unsigned long long key = key_of(a);
+            uint32_t a, si;
+            const uint2 r = pair_of((uint32_t)f, a, si);
+            const unsigned long long key = key_of(si);
             for_each_word(r, [&](uint32_t w, unsigned long long m) {
                 if (__ldcg(G.U + w) & m) atomicMax(&G.mark[w], key);
             });
@@ -753,45 +738,40 @@ greedy_rounds_kernel(const RParams G)
 
         // ---- check
         for (int64_t f = gtid; f < (int64_t)total_pairs; f += gsize) {
-            uint32_t a;
-            const uint2 r = pair_of((uint32_t)f, a);
-            const unsigned long long key = key_of(a);
+            uint32_t a, si;
+            const uint2 r = pair_of((uint32_t)f, a, si);
+            const unsigned long long key = key_of(si);
             bool conflict = false;
             for_each_word(r, [&](uint32_t w, unsigned long long m) {
                 if ((__ldcg(G.U + w) & m) && __ldcg(G.mark + w) != key) conflict = true;
             });
-            if (conflict) G.flag[a] = 1u;
+            if (conflict) atomicOr(&G.conf[a >> 5], 1u << (a & 31));
         }
         grid_barrier(G, bar_target);
         if (failed()) break;
 
         // ---- winners = active candidates without a conflict (same compaction in every CTA)
-        uint32_t n_win = 0;
+        uint32_t n_win = 0, win_pairs = 0;
         {
-            uint32_t fl[PER];
-#pragma unroll
-            for (int u = 0; u < PER; u++) {
-                const uint32_t a = (uint32_t)u * RT + threadIdx.x;
-                fl[u] = a < n_act ? __ldcg(&G.flag[a]) : 1u;
-            }
-            uint32_t wsum = 0;
-#pragma unroll
-            for (int u = 0; u < PER; u++) {
-                if ((uint32_t)u * RT >= n_act) break;           // CTA-uniform
-                const uint32_t a = (uint32_t)u * RT + threadIdx.x;
-                const bool win = fl[u] == 0u;
-                const uint32_t cnt = win ? s_base[a + 1] - s_base[a] : 0u;
-                const uint32_t before_n = n_win, before_s = wsum;
-                const uint32_t j = before_n + block_scan(win ? 1u : 0u, n_win);
-                const uint32_t base = before_s + block_scan(cnt, wsum);
-                if (win) {
-                    s_wi0[j] = s_i0[a];
-                    s_wown[j] = s_own[a];
-                    s_wbase[j] = base;
-                    if (blockIdx.x == 0) G.sel[n_picks + j] = (long long)key_of(a);
+            if (threadIdx.x < LIST_CAP_MAX / 32) s_conf[threadIdx.x] = __ldcg(&G.conf[threadIdx.x]);
+            __syncthreads();
+            const uint32_t pa = (n_act + RT - 1) / RT;
+            const uint32_t a_lo = min(threadIdx.x * pa, n_act), a_hi = min(a_lo + pa, n_act);
+            uint32_t c = 0, sum = 0;
+            for (uint32_t a = a_lo; a < a_hi; a++)
+                if (!((s_conf[a >> 5] >> (a & 31)) & 1u)) { c++; sum += s_cnt[s_act[a]]; }
+            uint32_t cb, sb;
+            block_scan2(c, sum, cb, sb, n_win, win_pairs);
+            for (uint32_t a = a_lo; a < a_hi; a++)
+                if (!((s_conf[a >> 5] >> (a & 31)) & 1u)) {
+                    const uint32_t si = s_act[a];
+                    s_wact[cb] = (uint16_t)si;
+                    s_wbase[cb] = sb;
+                    if (blockIdx.x == 0) G.sel[n_picks + cb] = (long long)key_of(si);
+                    cb++;
+                    sb += s_cnt[si];
                 }
-            }
-            if (threadIdx.x == 0) s_wbase[n_win] = wsum;
+            if (threadIdx.x == 0) s_wbase[n_win] = win_pairs;
             __syncthreads();
         }
         lap(1);
@@ -801,22 +781,20 @@ greedy_rounds_kernel(const RParams G)
 
         // ---- reset the marks of this round
         for (int64_t f = gtid; f < (int64_t)total_pairs; f += gsize) {
-            uint32_t a;
-            const uint2 r = pair_of((uint32_t)f, a);
+            uint32_t a, si;
+            const uint2 r = pair_of((uint32_t)f, a, si);
             for_each_word(r, [&](uint32_t w, unsigned long long) { G.mark[w] = 0ull; });
         }
         // ---- apply every accepted probe: (winner, interval) pairs are dealt round-robin to the warps
-        {
-            const uint32_t total = s_wbase[n_win];
-            for (uint32_t f = (uint32_t)warp * gridDim.x + blockIdx.x; f < total; f += gridDim.x * NWARP) {
-                uint32_t lo = 0, hi = n_win;
-                while (hi - lo > 1) {
-                    const uint32_t mid = (lo + hi) >> 1;
-                    if (s_wbase[mid] <= f) lo = mid; else hi = mid;
-                }
-                const uint2 r = G.iv[s_wown[lo]][(int64_t)s_wi0[lo] + (f - s_wbase[lo])];
-                apply_interval_warp(G, r, s_u + warp * APPLY_WORDS, lane);
+        for (uint32_t f = (uint32_t)warp * gridDim.x + blockIdx.x; f < win_pairs; f += gridDim.x * NWARP) {
+            uint32_t lo = 0, hi = n_win;
+            while (hi - lo > 1) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (s_wbase[mid] <= f) lo = mid; else hi = mid;
             }
+            const uint32_t si = s_wact[lo];
+            const uint2 r = G.iv[s_own[si]][(int64_t)s_i0[si] + (f - s_wbase[lo])];
+            apply_interval_warp(G, r, s_u + warp * APPLY_WORDS, lane);
         }
         lap(2);
     }
@@ -840,7 +818,7 @@ void trace(const cb_ctx *ctx, const char *what)
     fprintf(stderr, "[cb %p xrank %d] %.6f %s\n", (const void *)ctx, ctx->xrank, ts.tv_sec % 1000 + ts.tv_nsec * 1e-9, what);
 }
 
-size_t cand_bytes(uint32_t list_cap) { return sizeof(uint4) * 2 * CB_MAX_RANKS * (size_t)list_cap; }
+size_t slot_bytes() { return (sizeof(uint4) + sizeof(uint32_t)) * 2 * CB_MAX_RANKS * (size_t)LIST_CAP_MAX; }
 size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
 }  // namespace
@@ -849,7 +827,7 @@ size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 int64_t cb_rounds_exchange_bytes(const cb_cover *cover)
 {
     const size_t u_words = (size_t)(cover->universe_bits >> 6) + 1;
-    return (int64_t)(align_up(sizeof(XHeader)) + align_up(cand_bytes(LIST_CAP_MAX)) + align_up(8 * u_words) +
+    return (int64_t)(align_up(sizeof(XHeader)) + align_up(slot_bytes()) + align_up(8 * u_words) +
                      align_up(sizeof(uint2) * (size_t)(cover->n_intervals ? cover->n_intervals : 1)));
 }
 
@@ -883,7 +861,7 @@ int cb_setcover_rounds_impl(cb_ctx *ctx, const cb_cover *cover, int64_t lo, int6
 
     // ---- exchange area: the context's shared one when sharded, a work buffer otherwise
     const size_t off_cand = align_up(sizeof(XHeader));
-    const size_t off_U = off_cand + align_up(cand_bytes(LIST_CAP_MAX));
+    const size_t off_U = off_cand + align_up(slot_bytes());
     const size_t off_iv = off_U + align_up(8 * ((size_t)u_words + 1));
     const size_t need = off_iv + align_up(sizeof(uint2) * (size_t)(E ? E : 1));
     DevBuf<unsigned char> d_area;
@@ -949,9 +927,10 @@ int cb_setcover_rounds_impl(cb_ctx *ctx, const cb_cover *cover, int64_t lo, int6
     // [12] n_sel, [13] status
     CB_CUDA(ctx, d_ctl.alloc(16));
     CB_CUDA(ctx, cudaMemsetAsync(d_ctl.p, 0, 8 * 16, st));
-    // small u32 block: list[list_cap], list_n, flag[list_cap], hist_local[128]
-    CB_CUDA(ctx, d_small.alloc(2 * (size_t)list_cap + 1 + 128));
-    CB_CUDA(ctx, cudaMemsetAsync(d_small.p, 0, sizeof(uint32_t) * (2 * (size_t)list_cap + 1 + 128), st));
+    // small u32 block: list[4 * list_cap] (uint4 entries), conf[LIST_CAP_MAX / 32], hist_local[128], list_n
+    const size_t n_small = 4 * (size_t)list_cap + LIST_CAP_MAX / 32 + 128 + 4;
+    CB_CUDA(ctx, d_small.alloc(n_small));
+    CB_CUDA(ctx, cudaMemsetAsync(d_small.p, 0, sizeof(uint32_t) * n_small, st));
     CB_CUDA(ctx, d_sel.alloc((size_t)(P ? P : 1)));
 
     trace(ctx, "rounds: buffers allocated");
@@ -997,15 +976,15 @@ int cb_setcover_rounds_impl(cb_ctx *ctx, const cb_cover *cover, int64_t lo, int6
     G.n_sel = reinterpret_cast<long long *>(d_ctl.p + 12);
     G.status = reinterpret_cast<int *>(d_ctl.p + 13);
     G.diag = d_ctl.p + 14;
-    G.list = d_small.p;
-    G.list_n = d_small.p + list_cap;
+    G.list = reinterpret_cast<uint4 *>(d_small.p);           // cudaMallocAsync blocks are 256-byte aligned
     G.list_cap = list_cap;
-    G.flag = d_small.p + list_cap + 1;
-    G.hist_local = d_small.p + 2 * list_cap + 1;
+    G.conf = d_small.p + 4 * (size_t)list_cap;
+    G.hist_local = G.conf + LIST_CAP_MAX / 32;
+    G.list_n = G.hist_local + 128;
     G.sel = d_sel.p;
     G.rank = me;
     G.n_ranks = R;
-    G.cand_off = (int64_t)off_cand;
+    G.slot_off = (int64_t)off_cand;
     G.wait_ns = WAIT_NS_DEFAULT;
     if (const char *e = getenv("CB_WAIT_MS")) if (atoll(e) > 0) G.wait_ns = (unsigned long long)atoll(e) * 1000000ull;
     for (int r = 0; r < R; r++) {
@@ -1016,13 +995,13 @@ int cb_setcover_rounds_impl(cb_ctx *ctx, const cb_cover *cover, int64_t lo, int6
     G.iv[me] = d_iv_mine;
 
     // ---- persistent cooperative launch
-    const size_t dyn_smem = sizeof(uint32_t) * (6 * (size_t)list_cap + 2) + 2 * (size_t)list_cap;
+    const size_t dyn_smem = sizeof(uint32_t) * (6 * (size_t)list_cap + 2) + 5 * (size_t)list_cap;
     int per_sm = 0;
     {
         // once per device: changing a function attribute waits for running instances of the function, which
         // would stall a rank behind another rank's persistent kernel when several contexts share a device
         static bool attr_set[64] = {};
-        const size_t dyn_max = sizeof(uint32_t) * (6 * (size_t)LIST_CAP_MAX + 2) + 2 * (size_t)LIST_CAP_MAX;
+        const size_t dyn_max = sizeof(uint32_t) * (6 * (size_t)LIST_CAP_MAX + 2) + 5 * (size_t)LIST_CAP_MAX;
         if (ctx->device < 0 || ctx->device >= 64 || !attr_set[ctx->device]) {
             CB_CUDA(ctx, cudaFuncSetAttribute(greedy_rounds_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_max));
             if (ctx->device >= 0 && ctx->device < 64) attr_set[ctx->device] = true;
