@@ -49,7 +49,7 @@ EXPORTED_SYMBOLS = [
     'cb_setcover', 'cb_setcover_costs', 'cb_minhash_neardup', 'cb_hamming_neardup', 'cb_neardup_filter', 'cb_group_duplicates',
     'cb_comm_unique_id', 'cb_comm_init', 'cb_comm_destroy', 'cb_cover_allgather',
     'cb_coverage_range', 'cb_exchange_alloc', 'cb_exchange_bytes', 'cb_exchange_handle', 'cb_exchange_attach',
-    'cb_exchange_required', 'cb_setcover_sharded',
+    'cb_exchange_required', 'cb_setcover_sharded', 'cb_setcover_sharded_begin', 'cb_setcover_sharded_end',
 ]
 
 _lib = None
@@ -103,6 +103,8 @@ def load():
     L.cb_exchange_attach.argtypes = [vp, i32, i32, vp, vp, i32]
     L.cb_exchange_required.argtypes = [vp, vp, C.POINTER(i64)]
     L.cb_setcover_sharded.argtypes = [vp, vp, i64, i64, vp, vp, C.POINTER(i64), C.POINTER(Stats)]
+    L.cb_setcover_sharded_begin.argtypes = [vp, vp, i64, i64, vp, C.POINTER(vp)]
+    L.cb_setcover_sharded_end.argtypes = [vp, vp, vp, C.POINTER(i64), C.POINTER(Stats)]
     L.cb_cover_free.argtypes = [vp]
     L.cb_cover_free.restype = None
     L.cb_cover_num_intervals.argtypes = [vp]
@@ -331,6 +333,18 @@ class Context:
         sel = np.zeros(max(n_probes, 1), dtype=np.int64)
         n, st = C.c_int64(), Stats()
         self._check(self.L.cb_setcover_sharded(self.h, cover.h, lo, hi, _ptr(ranks), _ptr(sel), C.byref(n), C.byref(st)))
+        return sel[:n.value].copy(), st
+
+    def setcover_sharded_begin(self, cover, lo, hi, ranks=None):
+        """cb_setcover_sharded_begin: the rank-local set-up; returns a job for setcover_sharded_end."""
+        job = C.c_void_p()
+        self._check(self.L.cb_setcover_sharded_begin(self.h, cover.h, lo, hi, _ptr(ranks), C.byref(job)))
+        return job
+
+    def setcover_sharded_end(self, job, n_probes):
+        sel = np.zeros(max(n_probes, 1), dtype=np.int64)
+        n, st = C.c_int64(), Stats()
+        self._check(self.L.cb_setcover_sharded_end(self.h, job, _ptr(sel), C.byref(n), C.byref(st)))
         return sel[:n.value].copy(), st
 
     # ---- stage B

@@ -295,4 +295,30 @@ int cb_setcover_sharded(cb_ctx *ctx, const cb_cover *cover, int64_t probe_lo, in
     return cb_setcover_rounds_impl(ctx, cover, probe_lo, probe_hi, ranks, true, sel_ids, n_sel, stats);
 }
 
+int cb_setcover_sharded_begin(cb_ctx *ctx, const cb_cover *cover, int64_t probe_lo, int64_t probe_hi,
+                              const int32_t *ranks, cb_job **job)
+{
+    if (!ctx) return CB_ERR_ARG;
+    if (!cover || !job) return cb_fail(ctx, CB_ERR_ARG, "null argument");
+    *job = nullptr;
+    ctx->launches = 0;
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cb_tls_stream = ctx->stream;
+    cb_rounds_job *j = nullptr;
+    const int rc = cb_rounds_begin_impl(ctx, cover, probe_lo, probe_hi, ranks, &j);
+    *job = reinterpret_cast<cb_job *>(j);
+    return rc;
+}
+
+int cb_setcover_sharded_end(cb_ctx *ctx, cb_job *job, int64_t *sel_ids, int64_t *n_sel, cb_stats *stats)
+{
+    if (!ctx) return CB_ERR_ARG;
+    if (!job || !sel_ids || !n_sel) return cb_fail(ctx, CB_ERR_ARG, "null argument");
+    if (stats) memset(stats, 0, sizeof *stats);
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cb_tls_stream = ctx->stream;
+    *n_sel = 0;
+    return cb_rounds_end_impl(reinterpret_cast<cb_rounds_job *>(job), sel_ids, n_sel, stats);
+}
+
 }  // extern "C"

@@ -202,6 +202,10 @@ int cb_setcover_impl(cb_ctx *ctx, const cb_cover *cover, const double *costs, co
 int64_t cb_rounds_exchange_bytes(const cb_cover *cover);
 int cb_setcover_rounds_impl(cb_ctx *ctx, const cb_cover *cover, int64_t lo, int64_t hi, const int32_t *ranks,
                             bool sharded, int64_t *sel_ids, int64_t *n_sel, cb_stats *stats);
+struct cb_rounds_job;
+int cb_rounds_begin_impl(cb_ctx *ctx, const cb_cover *cover, int64_t lo, int64_t hi, const int32_t *ranks,
+                         cb_rounds_job **out);
+int cb_rounds_end_impl(cb_rounds_job *job, int64_t *sel_ids, int64_t *n_sel, cb_stats *stats);
 
 // neardup.cu
 int cb_minhash_neardup_impl(cb_ctx *ctx, const uint8_t *ascii, const int64_t *probe_off, int64_t n_probes,

@@ -87,7 +87,8 @@ struct RParams {
     uint32_t *hist_local;           // [2][64]
     uint4 *list;                    // [list_cap] this rank's candidate list: probe, first interval, intervals, -
     uint32_t *list_n, list_cap;
-    uint32_t *conf;                 // [LIST_CAP_MAX / 32] conflict bits of the round's active candidates
+    uint32_t *conf;                 // [LIST_CAP_MAX / 4] conflict flags (bytes) of the round's active candidates
+    unsigned int *work;             // [2] next (winner, interval) pair to apply, alternating between rounds
     long long *sel, *n_sel;
     int *status;
     unsigned long long *phase_ns;   // [4]
@@ -392,7 +393,7 @@ greedy_rounds_kernel(const RParams G)
     __shared__ unsigned long long s_part[NWARP];
     __shared__ uint32_t s_hist[64];                  // level histogram of a list rebuild
     __shared__ uint32_t s_rn[CB_MAX_RANKS + 1];      // prefix of the per-rank list lengths
-    __shared__ uint32_t s_conf[LIST_CAP_MAX / 32];   // conflict bits of the active candidates
+    __shared__ uint32_t s_conf[LIST_CAP_MAX / 4];    // conflict flags (one byte each) of the active candidates
     extern __shared__ uint32_t s_dyn[];
     // per CTA, list_cap entries each.  The candidate LIST (all ranks' entries, rank order): probe,
     // first interval, number of intervals, owner rank -- loaded once per list rebuild; gain -- loaded
@@ -682,7 +683,7 @@ greedy_rounds_kernel(const RParams G)
             const unsigned slot = (unsigned)(epoch & 1ull);
             const uint32_t i_lo = threadIdx.x * per, i_hi = min(i_lo + per, n_list);
             uint32_t c = 0, sum = 0;
-            for (uint32_t i = i_lo; i < i_hi; i++) {
+            for (uint32_t i = i_lo; i < i_hi; i++) {              // independent loads: all in flight together
                 uint32_t g;
                 if (R == 1) g = __ldcg(&G.gain[s_p[i]]);
                 else {
@@ -690,8 +691,9 @@ greedy_rounds_kernel(const RParams G)
                     g = __ldcg(gain_slot(G, me, slot, r) + (i - s_rn[r]));
                 }
                 s_g[i] = g;
-                if (g >= tau) { c++; sum += s_cnt[i]; }
             }
+            for (uint32_t i = i_lo; i < i_hi; i++)
+                if (s_g[i] >= tau) { c++; sum += s_cnt[i]; }
             uint32_t cb, sb;
             block_scan2(c, sum, cb, sb, n_act, total_pairs);
             for (uint32_t i = i_lo; i < i_hi; i++)
@@ -703,7 +705,8 @@ greedy_rounds_kernel(const RParams G)
                 }
             if (threadIdx.x == 0) s_base[n_act] = total_pairs;
             // the conflict bits of the previous round have been read by everybody (barrier since)
-            if (blockIdx.x == 0 && threadIdx.x < LIST_CAP_MAX / 32) G.conf[threadIdx.x] = 0u;
+            if (blockIdx.x == 0)
+                for (uint32_t q = threadIdx.x; q < LIST_CAP_MAX / 4; q += RT) G.conf[q] = 0u;
             __syncthreads();
         }
         if (n_act == 0u) {                       // the list is used up
@@ -745,7 +748,7 @@ greedy_rounds_kernel(const RParams G)
             for_each_word(r, [&](uint32_t w, unsigned long long m) {
                 if ((__ldcg(G.U + w) & m) && __ldcg(G.mark + w) != key) conflict = true;
             });
-            if (conflict) atomicOr(&G.conf[a >> 5], 1u << (a & 31));
+            if (conflict) reinterpret_cast<volatile unsigned char *>(G.conf)[a] = 1;     // plain byte store: no contention
         }
         grid_barrier(G, bar_target);
         if (failed()) break;
@@ -753,17 +756,18 @@ greedy_rounds_kernel(const RParams G)
         // ---- winners = active candidates without a conflict (same compaction in every CTA)
         uint32_t n_win = 0, win_pairs = 0;
         {
-            if (threadIdx.x < LIST_CAP_MAX / 32) s_conf[threadIdx.x] = __ldcg(&G.conf[threadIdx.x]);
+            for (uint32_t q = threadIdx.x; q < (n_act + 3) / 4; q += RT) s_conf[q] = __ldcg(&G.conf[q]);
             __syncthreads();
+            const unsigned char *s_cf = reinterpret_cast<const unsigned char *>(s_conf);
             const uint32_t pa = (n_act + RT - 1) / RT;
             const uint32_t a_lo = min(threadIdx.x * pa, n_act), a_hi = min(a_lo + pa, n_act);
             uint32_t c = 0, sum = 0;
             for (uint32_t a = a_lo; a < a_hi; a++)
-                if (!((s_conf[a >> 5] >> (a & 31)) & 1u)) { c++; sum += s_cnt[s_act[a]]; }
+                if (!s_cf[a]) { c++; sum += s_cnt[s_act[a]]; }
             uint32_t cb, sb;
             block_scan2(c, sum, cb, sb, n_win, win_pairs);
             for (uint32_t a = a_lo; a < a_hi; a++)
-                if (!((s_conf[a >> 5] >> (a & 31)) & 1u)) {
+                if (!s_cf[a]) {
                     const uint32_t si = s_act[a];
                     s_wact[cb] = (uint16_t)si;
                     s_wbase[cb] = sb;
@@ -785,16 +789,27 @@ greedy_rounds_kernel(const RParams G)
             const uint2 r = pair_of((uint32_t)f, a, si);
             for_each_word(r, [&](uint32_t w, unsigned long long) { G.mark[w] = 0ull; });
         }
-        // ---- apply every accepted probe: (winner, interval) pairs are dealt round-robin to the warps
-        for (uint32_t f = (uint32_t)warp * gridDim.x + blockIdx.x; f < win_pairs; f += gridDim.x * NWARP) {
-            uint32_t lo = 0, hi = n_win;
-            while (hi - lo > 1) {
-                const uint32_t mid = (lo + hi) >> 1;
-                if (s_wbase[mid] <= f) lo = mid; else hi = mid;
+        // ---- apply every accepted probe.  The cost of a (winner, interval) pair varies a lot (number of indexed
+        // items it overlaps, contention on the gains), so the pairs are handed out dynamically: a warp takes the
+        // next one from a global counter when it is done with its own.  Two counters alternate between rounds; the
+        // idle one is reset here, a full round (three barriers) before it is used again.
+        {
+            unsigned int *work = G.work + (n_rounds & 1ull);
+            if (gtid == 0) G.work[(n_rounds & 1ull) ^ 1ull] = 0u;
+            for (;;) {
+                uint32_t f = 0;
+                if (lane == 0) f = atomicAdd(work, 1u);
+                f = __shfl_sync(0xffffffffu, f, 0);
+                if (f >= win_pairs) break;
+                uint32_t lo = 0, hi = n_win;
+                while (hi - lo > 1) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (s_wbase[mid] <= f) lo = mid; else hi = mid;
+                }
+                const uint32_t si = s_wact[lo];
+                const uint2 r = G.iv[s_own[si]][(int64_t)s_i0[si] + (f - s_wbase[lo])];
+                apply_interval_warp(G, r, s_u + warp * APPLY_WORDS, lane);
             }
-            const uint32_t si = s_wact[lo];
-            const uint2 r = G.iv[s_own[si]][(int64_t)s_i0[si] + (f - s_wbase[lo])];
-            apply_interval_warp(G, r, s_u + warp * APPLY_WORDS, lane);
         }
         lap(2);
     }
@@ -831,40 +846,59 @@ int64_t cb_rounds_exchange_bytes(const cb_cover *cover)
                      align_up(sizeof(uint2) * (size_t)(cover->n_intervals ? cover->n_intervals : 1)));
 }
 
-// `cover` holds the intervals of probes [lo, hi) of a grouping of cover->n_probes probes (rows outside
-// are empty).  With ctx->xn_ranks > 1 every rank of the exchange group must make this call with its
-// own shard; all of them receive the same picks.
-int cb_setcover_rounds_impl(cb_ctx *ctx, const cb_cover *cover, int64_t lo, int64_t hi, const int32_t *ranks,
-                            bool sharded, int64_t *sel_ids, int64_t *n_sel, cb_stats *stats)
+// One set cover in two steps.  prepare(): everything that is local to this rank (work buffers, universe
+// bits, gains, interval index) -- it never waits for another rank.  run(): the persistent kernel and the
+// read-back of the picks -- with several ranks this is the collective part.
+struct cb_rounds_job {
+    cb_ctx *ctx = nullptr;
+    bool sharded = false;
+    int64_t P = 0, E = 0, n_items = 0;
+    int32_t n_ranks = 1;
+    uint32_t list_cap = 2048u;
+    std::vector<uint32_t> h_rank;
+    DevBuf<unsigned char> d_area;
+    DevBuf<uint32_t> d_rank, d_gain, d_bcount, d_bcursor, d_small;
+    DevBuf<unsigned long long> d_mark, d_ctl;
+    DevBuf<long long> d_sel;
+    DevBuf<int64_t> d_boff;
+    DevBuf<uint2> d_items;
+    RParams G;
+    EventTimer t_all, t_uni, t_greedy;
+    explicit cb_rounds_job(cb_ctx *c) : ctx(c), t_all(c->stream), t_uni(c->stream), t_greedy(c->stream) {}
+    int prepare(const cb_cover *cover, int64_t lo, int64_t hi, const int32_t *ranks, bool sharded_);
+    int run(int64_t *sel_ids, int64_t *n_sel, cb_stats *stats);
+};
+
+int cb_rounds_job::prepare(const cb_cover *cover, int64_t lo, int64_t hi, const int32_t *ranks, bool sharded_)
 {
     cudaStream_t st = ctx->stream;
-    const int64_t P = cover->n_probes, E = cover->n_intervals;
+    sharded = sharded_;
+    P = cover->n_probes;
+    E = cover->n_intervals;
     const int R = sharded ? ctx->xn_ranks : 1, me = sharded ? ctx->xrank : 0;
     if (lo < 0 || hi < lo || hi > P) return cb_fail(ctx, CB_ERR_ARG, "bad probe range");
     if (sharded && ctx->xarea_poisoned)
         return cb_fail(ctx, CB_ERR_STATE, "an earlier sharded call failed; attach the exchange areas again");
     if (P >= (1ll << 25)) return cb_fail(ctx, CB_ERR_UNSUPPORTED, "more than 2^25 probes in one grouping");
     if (E >= 0xfffffff0ll) return cb_fail(ctx, CB_ERR_UNSUPPORTED, "more than 2^32 intervals in one grouping");
-    trace(ctx, "rounds: enter");
-    EventTimer t_all(st), t_uni(st), t_greedy(st);
+    trace(ctx, "rounds: prepare");
     t_all.start();
     t_uni.start();
     const int wide = ctx->sm_count * 8;
     const int64_t u_words = cover->universe_bits >> 6;
     const int64_t n_blocks = u_words + 1;
 
-    uint32_t list_cap = 2048u;                    // <= LIST_CAP_MAX; 2048 leaves room for 3 CTAs per SM
+    list_cap = 2048u;                             // <= LIST_CAP_MAX; 2048 leaves room for 3 CTAs per SM
     if (const char *e = getenv("CB_GREEDY_LIST_CAP")) {
         const int v = atoi(e);
         if (v >= 1 && v <= LIST_CAP_MAX) list_cap = (uint32_t)v;
     }
 
     // ---- exchange area: the context's shared one when sharded, a work buffer otherwise
-    const size_t off_cand = align_up(sizeof(XHeader));
-    const size_t off_U = off_cand + align_up(slot_bytes());
+    const size_t off_slots = align_up(sizeof(XHeader));
+    const size_t off_U = off_slots + align_up(slot_bytes());
     const size_t off_iv = off_U + align_up(8 * ((size_t)u_words + 1));
     const size_t need = off_iv + align_up(sizeof(uint2) * (size_t)(E ? E : 1));
-    DevBuf<unsigned char> d_area;
     unsigned char *area = nullptr;
     if (sharded) {
         if (R < 2 || !ctx->xarea) return cb_fail(ctx, CB_ERR_STATE, "cb_exchange_attach has not been called");
@@ -875,7 +909,6 @@ int cb_setcover_rounds_impl(cb_ctx *ctx, const cb_cover *cover, int64_t lo, int6
         area = d_area.p;
         CB_CUDA(ctx, cudaMemsetAsync(area, 0, sizeof(XHeader), st));
     }
-    trace(ctx, "rounds: timers created");
     unsigned long long *d_U = reinterpret_cast<unsigned long long *>(area + off_U);
     CB_CUDA(ctx, cudaMemsetAsync(d_U, 0, 8 * ((size_t)u_words + 1), st));
     const uint2 *d_iv_mine = cover->d_iv;
@@ -884,11 +917,8 @@ int cb_setcover_rounds_impl(cb_ctx *ctx, const cb_cover *cover, int64_t lo, int6
         d_iv_mine = reinterpret_cast<const uint2 *>(area + off_iv);
     }
 
-    trace(ctx, "rounds: area memset + interval copy issued");
     // ---- ranks -> dense indices in ascending order of rank value (:349)
-    std::vector<uint32_t> h_rank;
-    int32_t n_ranks = 1;
-    DevBuf<uint32_t> d_rank;
+    n_ranks = 1;
     CB_CUDA(ctx, d_rank.alloc((size_t)(P ? P : 1)));
     if (ranks) {
         h_rank.assign((size_t)P, 0u);
@@ -903,16 +933,10 @@ int cb_setcover_rounds_impl(cb_ctx *ctx, const cb_cover *cover, int64_t lo, int6
         CB_CUDA(ctx, cudaMemsetAsync(d_rank.p, 0, sizeof(uint32_t) * (size_t)(P ? P : 1), st));
     }
 
-    trace(ctx, "rounds: rank array ready");
     // ---- work buffers
     int pbits = 1;
     while ((1ll << pbits) < P) pbits++;
     const uint32_t max_piece = (1u << (32 - pbits)) - 1u;
-    DevBuf<uint32_t> d_gain, d_bcount, d_bcursor, d_small;
-    DevBuf<unsigned long long> d_mark, d_ctl;
-    DevBuf<long long> d_sel;
-    DevBuf<int64_t> d_boff;
-    DevBuf<uint2> d_items;
     CB_CUDA(ctx, d_gain.alloc((size_t)(P ? P : 1)));
     CB_CUDA(ctx, cudaMemsetAsync(d_gain.p, 0, sizeof(uint32_t) * (size_t)(P ? P : 1), st));
     CB_CUDA(ctx, d_bcount.alloc((size_t)n_blocks));
@@ -920,28 +944,24 @@ int cb_setcover_rounds_impl(cb_ctx *ctx, const cb_cover *cover, int64_t lo, int6
     CB_CUDA(ctx, d_boff.alloc((size_t)n_blocks + 1));
     CB_CUDA(ctx, cudaMemsetAsync(d_bcount.p, 0, sizeof(uint32_t) * (size_t)n_blocks, st));
     CB_CUDA(ctx, cudaMemsetAsync(d_bcursor.p, 0, sizeof(uint32_t) * (size_t)n_blocks, st));
-    trace(ctx, "rounds: gain + block arrays allocated");
     CB_CUDA(ctx, d_mark.alloc((size_t)u_words + 1));
     CB_CUDA(ctx, cudaMemsetAsync(d_mark.p, 0, 8 * ((size_t)u_words + 1), st));
     // control block: [0] remaining, [1] barrier, [2] release, [3..4] key_local, [5..8] phase ns, [9..11] counters,
-    // [12] n_sel, [13] status
+    // [12] n_sel, [13] status, [14] diagnostics
     CB_CUDA(ctx, d_ctl.alloc(16));
     CB_CUDA(ctx, cudaMemsetAsync(d_ctl.p, 0, 8 * 16, st));
-    // small u32 block: list[4 * list_cap] (uint4 entries), conf[LIST_CAP_MAX / 32], hist_local[128], list_n
-    const size_t n_small = 4 * (size_t)list_cap + LIST_CAP_MAX / 32 + 128 + 4;
+    // small u32 block: list[4 * list_cap] (uint4 entries), conf[LIST_CAP_MAX / 4], hist_local[128], list_n[4], work[4]
+    const size_t n_small = 4 * (size_t)list_cap + LIST_CAP_MAX / 4 + 128 + 4 + 4;
     CB_CUDA(ctx, d_small.alloc(n_small));
     CB_CUDA(ctx, cudaMemsetAsync(d_small.p, 0, sizeof(uint32_t) * n_small, st));
     CB_CUDA(ctx, d_sel.alloc((size_t)(P ? P : 1)));
 
-    trace(ctx, "rounds: buffers allocated");
     // ---- set-up: universe bits + block counts + gains, offsets, index items
     index_kernel<false><<<wide, 256, 0, st>>>(cover->d_iv_off, cover->d_iv, lo, hi, max_piece, pbits, d_U, d_gain.p,
                                               d_bcount.p, nullptr, nullptr, nullptr);
     ctx->launches++;
-    int64_t n_items = 0;
-    trace(ctx, "rounds: index pass 1 launched");
+    n_items = 0;
     CB_TRY(cb_exclusive_scan_u32_to_i64(ctx, d_bcount.p, d_boff.p, n_blocks, &n_items));
-    trace(ctx, "rounds: block offsets scanned");
     if (n_items >= 0xfffffff0ll) return cb_fail(ctx, CB_ERR_UNSUPPORTED, "more than 2^32 index items");
     CB_CUDA(ctx, d_items.alloc((size_t)(n_items ? n_items : 1)));
     index_kernel<true><<<wide, 256, 0, st>>>(cover->d_iv_off, cover->d_iv, lo, hi, max_piece, pbits, nullptr, nullptr,
@@ -950,7 +970,6 @@ int cb_setcover_rounds_impl(cb_ctx *ctx, const cb_cover *cover, int64_t lo, int6
     CB_CUDA(ctx, cudaGetLastError());
     t_uni.stop();
 
-    RParams G;
     memset(&G, 0, sizeof G);
     G.n_probes = P;
     G.lo = lo;
@@ -979,12 +998,13 @@ int cb_setcover_rounds_impl(cb_ctx *ctx, const cb_cover *cover, int64_t lo, int6
     G.list = reinterpret_cast<uint4 *>(d_small.p);           // cudaMallocAsync blocks are 256-byte aligned
     G.list_cap = list_cap;
     G.conf = d_small.p + 4 * (size_t)list_cap;
-    G.hist_local = G.conf + LIST_CAP_MAX / 32;
+    G.hist_local = G.conf + LIST_CAP_MAX / 4;
     G.list_n = G.hist_local + 128;
+    G.work = G.list_n + 4;
     G.sel = d_sel.p;
     G.rank = me;
     G.n_ranks = R;
-    G.slot_off = (int64_t)off_cand;
+    G.slot_off = (int64_t)off_slots;
     G.wait_ns = WAIT_NS_DEFAULT;
     if (const char *e = getenv("CB_WAIT_MS")) if (atoll(e) > 0) G.wait_ns = (unsigned long long)atoll(e) * 1000000ull;
     for (int r = 0; r < R; r++) {
@@ -993,10 +1013,6 @@ int cb_setcover_rounds_impl(cb_ctx *ctx, const cb_cover *cover, int64_t lo, int6
     }
     G.xa[me] = area;
     G.iv[me] = d_iv_mine;
-
-    // ---- persistent cooperative launch
-    const size_t dyn_smem = sizeof(uint32_t) * (6 * (size_t)list_cap + 2) + 5 * (size_t)list_cap;
-    int per_sm = 0;
     {
         // once per device: changing a function attribute waits for running instances of the function, which
         // would stall a rank behind another rank's persistent kernel when several contexts share a device
@@ -1007,6 +1023,17 @@ int cb_setcover_rounds_impl(cb_ctx *ctx, const cb_cover *cover, int64_t lo, int6
             if (ctx->device >= 0 && ctx->device < 64) attr_set[ctx->device] = true;
         }
     }
+    trace(ctx, "rounds: prepared");
+    return CB_OK;
+}
+
+int cb_rounds_job::run(int64_t *sel_ids, int64_t *n_sel, cb_stats *stats)
+{
+    cudaStream_t st = ctx->stream;
+    const int R = G.n_ranks, me = G.rank;
+    // ---- persistent launch: cooperative (co-residency guaranteed), as many blocks as the device holds (<= 3 per SM)
+    const size_t dyn_smem = sizeof(uint32_t) * (6 * (size_t)list_cap + 2) + 5 * (size_t)list_cap;
+    int per_sm = 0;
     CB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, greedy_rounds_kernel, RT, dyn_smem));
     if (per_sm < 1) return cb_fail(ctx, CB_ERR_CUDA, "greedy kernel does not fit on an SM");
     int want = 3;
@@ -1029,7 +1056,6 @@ int cb_setcover_rounds_impl(cb_ctx *ctx, const cb_cover *cover, int64_t lo, int6
     t_greedy.stop();
     t_all.stop();
 
-    trace(ctx, "rounds: greedy kernel launched");
     unsigned long long h_ctl[16];
     CB_CUDA(ctx, cudaMemcpyAsync(h_ctl, d_ctl.p, sizeof h_ctl, cudaMemcpyDeviceToHost, st));
     CB_CUDA(ctx, cudaStreamSynchronize(st));
@@ -1040,8 +1066,8 @@ int cb_setcover_rounds_impl(cb_ctx *ctx, const cb_cover *cover, int64_t lo, int6
         ctx->xarea_poisoned = sharded;
         char msg[256];
         snprintf(msg, sizeof msg, "set cover: a barrier wait exceeded the time limit (rank %d of %d, barrier %llu, kind %llu, "
-                 "peer %llu; flags seen %llu)", me, R, (unsigned long long)(h_ctl[14] >> 8), (unsigned long long)(h_ctl[14] & 15),
-                 (unsigned long long)((h_ctl[14] >> 4) & 15), (unsigned long long)h_ctl[15]);
+                 "peer %llu)", me, R, (unsigned long long)(h_ctl[14] >> 8), (unsigned long long)(h_ctl[14] & 15),
+                 (unsigned long long)((h_ctl[14] >> 4) & 15));
         ctx->err = msg;
         return CB_ERR_COMM;
     }
@@ -1080,4 +1106,36 @@ int cb_setcover_rounds_impl(cb_ctx *ctx, const cb_cover *cover, int64_t lo, int6
         stats->reserved[7] = n_items;
     }
     return CB_OK;
+}
+
+// `cover` holds the intervals of probes [lo, hi) of a grouping of cover->n_probes probes (rows outside
+// are empty).  With sharded = true every rank of the exchange group must make this call with its
+// own shard; all of them receive the same picks.
+int cb_setcover_rounds_impl(cb_ctx *ctx, const cb_cover *cover, int64_t lo, int64_t hi, const int32_t *ranks,
+                            bool sharded, int64_t *sel_ids, int64_t *n_sel, cb_stats *stats)
+{
+    cb_rounds_job job(ctx);
+    CB_TRY(job.prepare(cover, lo, hi, ranks, sharded));
+    return job.run(sel_ids, n_sel, stats);
+}
+
+int cb_rounds_begin_impl(cb_ctx *ctx, const cb_cover *cover, int64_t lo, int64_t hi, const int32_t *ranks,
+                         cb_rounds_job **out)
+{
+    cb_rounds_job *job = new cb_rounds_job(ctx);
+    const int rc = job->prepare(cover, lo, hi, ranks, true);
+    if (rc == CB_OK) {
+        cudaStreamSynchronize(ctx->stream);           // nothing of the set-up is still queued when run() starts
+        *out = job;
+    } else {
+        delete job;
+    }
+    return rc;
+}
+
+int cb_rounds_end_impl(cb_rounds_job *job, int64_t *sel_ids, int64_t *n_sel, cb_stats *stats)
+{
+    const int rc = job->run(sel_ids, n_sel, stats);
+    delete job;
+    return rc;
 }

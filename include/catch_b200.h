@@ -267,6 +267,15 @@ int cb_exchange_attach(cb_ctx *ctx, int32_t rank, int32_t n_ranks, const uint8_t
 int cb_exchange_required(cb_ctx *ctx, const cb_cover *cover, int64_t *bytes);
 int cb_setcover_sharded(cb_ctx *ctx, const cb_cover *cover, int64_t probe_lo, int64_t probe_hi,
                         const int32_t *ranks, int64_t *sel_ids, int64_t *n_sel, cb_stats *stats);
+/* The same in two steps: _begin does everything that is local to the rank (work buffers, universe bits,
+ * gains, interval index; it never waits for another rank and returns with the stream idle), _end is the
+ * collective part (the persistent kernel, the picks) and releases the job.  Lets a caller overlap the
+ * set-up with other work, and lets ranks that share one device (tests) finish all host-side set-up
+ * before the first persistent kernel starts. */
+typedef struct cb_job cb_job;
+int cb_setcover_sharded_begin(cb_ctx *ctx, const cb_cover *cover, int64_t probe_lo, int64_t probe_hi,
+                              const int32_t *ranks, cb_job **job);
+int cb_setcover_sharded_end(cb_ctx *ctx, cb_job *job, int64_t *sel_ids, int64_t *n_sel, cb_stats *stats);
 
 /* ---- near-duplicate filter (K9-K12) --------------------------------------------------
  * Replaces NearDuplicateFilter._filter (filter/near_duplicate_filter.py:47-103) with

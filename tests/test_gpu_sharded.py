@@ -66,10 +66,16 @@ def _sharded_picks(ctxs, cands, seqs, kw, plan, grid_limit, ranks=None):
         for r, c in enumerate(ctxs):
             c.exchange_attach(r, R, addresses=addrs, grid_limit=grid_limit)
 
+        # all host-side set-up first, then the persistent kernels: with the ranks sharing ONE device, a driver
+        # call of one rank's set-up (memory, module state) can otherwise wait for another rank's running kernel
+        jobs = [None] * R
+        for r, c in enumerate(ctxs):
+            lo, hi = parallel.shard_bounds(P, R, r)
+            jobs[r] = c.setcover_sharded_begin(covers[r], lo, hi, ranks)
+
         def run(r):
             try:
-                lo, hi = parallel.shard_bounds(P, R, r)
-                out[r] = ctxs[r].setcover_sharded(covers[r], P, lo, hi, ranks)
+                out[r] = ctxs[r].setcover_sharded_end(jobs[r], P)
             except BaseException as e:      # noqa: BLE001 -- reported by the main thread
                 err[r] = e
         threads = [threading.Thread(target=run, args=(r,)) for r in range(R)]
@@ -87,13 +93,10 @@ def _sharded_picks(ctxs, cands, seqs, kw, plan, grid_limit, ranks=None):
     return out
 
 
-@pytest.mark.parametrize('n_ranks', [2])
+@pytest.mark.parametrize('n_ranks', [2, 4])
 def test_sharded_setcover_virtual_ranks(ctx, n_ranks):
     """Stage A on shards of the probes + the sharded greedy loop give, on every rank, exactly the pick
-    sequence of the one-GPU path (which is pinned against the oracle elsewhere).  Two virtual ranks only:
-    with more contexts on ONE device the CUDA driver makes a host call of the third rank wait for the
-    persistent kernels of the first two (measured; nothing of the kind exists with one process per GPU),
-    so larger rank counts are covered by the torchrun test below and tools/multigpu_check.py."""
+    sequence of the one-GPU path (which is pinned against the oracle elsewhere)."""
     from catch_b200 import _lib
     from catch_b200 import coverage as cov
     ctxs = [_lib.Context(0) for _ in range(n_ranks)]
