@@ -460,9 +460,10 @@ greedy_rounds_kernel(const RParams G)
     unsigned long long bar_target = 0, n_rebuilds = 0, n_rounds = 0, n_active_sum = 0;
     unsigned long long epoch = __ldcg(&xh->epoch);
     uint32_t tau = 1, id_thr = 0xffffffffu, n_list = 0;
+    unsigned long long stamp = 0;                   // round stamp of the marks, < 2^(32 - pbits)
     unsigned rb = 0;
     bool need_rebuild = true;
-    unsigned long long t_phase[4] = {0, 0, 0, 0}, t_last = 0;
+    unsigned long long t_phase[4] = {0, 0, 0, 0}, t_last = 0, t_fine[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, t_f = 0;
     const bool timing = (gtid == 0);
     if (timing) t_last = globaltimer_ns();
     auto lap = [&](int i) {
@@ -470,6 +471,15 @@ greedy_rounds_kernel(const RParams G)
             const unsigned long long t = globaltimer_ns();
             t_phase[i] += t - t_last;
             t_last = t;
+        }
+    };
+    // finer split of a round for CB_TRACE: [0] gain exchange barrier, [1] compaction, [2] mark, [3] barrier, [4] check,
+    // [5] barrier, [6] winners, [7] mark reset, [8] apply
+    auto fine = [&](int i) {
+        if (timing) {
+            const unsigned long long t = globaltimer_ns();
+            t_fine[i] += t - t_f;
+            t_f = t;
         }
     };
     // CTA-uniform (a barrier inside): every thread of the CTA takes the same branch even if the status changes
@@ -664,6 +674,14 @@ greedy_rounds_kernel(const RParams G)
             lap(0);
         }
 
+        if (timing) t_f = globaltimer_ns();
+        // ---- next round stamp; when it is about to wrap, every mark is wiped (visible to all after the
+        // barrier that follows)
+        stamp++;
+        if (stamp >= (1ull << (32 - G.pbits)) - 1ull) {
+            for (int64_t w = gtid; w <= G.u_words; w += gsize) G.mark[w] = 0ull;
+            stamp = 1;
+        }
         // ---- the current gains of the list entries.  One GPU: a grid barrier (gains are final after it),
         // then every CTA reads them where they are.  Several GPUs: CTA 0 pushes the gains of this rank's
         // entries to every rank inside the cross-GPU barrier.
@@ -676,6 +694,7 @@ greedy_rounds_kernel(const RParams G)
             }
         });
         if (failed() || __ldcg(G.remaining) == 0ull) break;
+        fine(0);
         // ---- active candidates = list slots whose gain is still >= tau, compacted in list order by every
         // CTA for itself (same inputs, same result): thread t looks at `per` consecutive slots
         uint32_t n_act = 0, total_pairs = 0;
@@ -683,17 +702,28 @@ greedy_rounds_kernel(const RParams G)
             const unsigned slot = (unsigned)(epoch & 1ull);
             const uint32_t i_lo = threadIdx.x * per, i_hi = min(i_lo + per, n_list);
             uint32_t c = 0, sum = 0;
-            for (uint32_t i = i_lo; i < i_hi; i++) {              // independent loads: all in flight together
-                uint32_t g;
-                if (R == 1) g = __ldcg(&G.gain[s_p[i]]);
-                else {
-                    const int r = s_own[i];
-                    g = __ldcg(gain_slot(G, me, slot, r) + (i - s_rn[r]));
+            constexpr int PER_MAX = LIST_CAP_MAX / RT;
+            uint32_t gv[PER_MAX];
+#pragma unroll
+            for (int j = 0; j < PER_MAX; j++) {                  // independent loads: all in flight together
+                const uint32_t i = i_lo + (uint32_t)j;
+                gv[j] = 0u;
+                if ((uint32_t)j < per && i < i_hi) {
+                    if (R == 1) gv[j] = __ldcg(&G.gain[s_p[i]]);
+                    else {
+                        const int r = s_own[i];
+                        gv[j] = __ldcg(gain_slot(G, me, slot, r) + (i - s_rn[r]));
+                    }
                 }
-                s_g[i] = g;
             }
-            for (uint32_t i = i_lo; i < i_hi; i++)
-                if (s_g[i] >= tau) { c++; sum += s_cnt[i]; }
+#pragma unroll
+            for (int j = 0; j < PER_MAX; j++) {
+                const uint32_t i = i_lo + (uint32_t)j;
+                if ((uint32_t)j < per && i < i_hi) {
+                    s_g[i] = gv[j];
+                    if (gv[j] >= tau) { c++; sum += s_cnt[i]; }
+                }
+            }
             uint32_t cb, sb;
             block_scan2(c, sum, cb, sb, n_act, total_pairs);
             for (uint32_t i = i_lo; i < i_hi; i++)
@@ -713,6 +743,7 @@ greedy_rounds_kernel(const RParams G)
             need_rebuild = true;
             continue;
         }
+        fine(1);
         // (candidate a, interval f - s_base[a]) for the f-th pair of the round
         auto pair_of = [&](uint32_t f, uint32_t &a, uint32_t &slot_i) -> uint2 {
             uint32_t lo = 0, hi = n_act;
@@ -727,31 +758,105 @@ greedy_rounds_kernel(const RParams G)
         auto key_of = [&](uint32_t slot_i) -> unsigned long long {
             return ((unsigned long long)s_g[slot_i] << 32) | (unsigned long long)(0xffffffffu - s_p[slot_i]);
         };
+        // Mark value of a candidate: round stamp | gain | (2^pbits - 1 - probe).  Within a round the order is
+        // the key order; a newer round beats every older mark, so marks are never reset between rounds (they
+        // are wiped when the stamp is about to wrap, see below).
+        const int pbits = G.pbits;
+        auto mkey_of = [&](uint32_t slot_i) -> unsigned long long {
+            return (stamp << (32 + pbits)) | ((unsigned long long)s_g[slot_i] << pbits) |
+                   (unsigned long long)(((1u << pbits) - 1u) - s_p[slot_i]);
+        };
 
-        // ---- mark: one thread per (candidate, interval)
-        for (int64_t f = gtid; f < (int64_t)total_pairs; f += gsize) {
+        // ---- mark: one thread per (candidate, interval).  The first MC pairs of a thread stay in registers
+        // (interval, candidate, which of its words still hold uncovered bits) for the check phase; all loads
+        // of a step are issued before any is used.
+        constexpr int MC = 3, MW = 8;
+        uint2 c_r[MC];
+        uint32_t c_a[MC], c_si[MC], c_live[MC];
+#pragma unroll
+        for (int k = 0; k < MC; k++) {
+            const int64_t f = gtid + (int64_t)k * gsize;
+            c_r[k] = make_uint2(0u, 0u);
+            c_a[k] = c_si[k] = c_live[k] = 0u;
+            if (f < (int64_t)total_pairs) c_r[k] = pair_of((uint32_t)f, c_a[k], c_si[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < MC; k++) {
+            const uint2 r = c_r[k];
+            if (r.x >= r.y) continue;
+            const uint32_t w0 = r.x >> 6, w1 = (r.y - 1) >> 6;
+            if (w1 - w0 < (uint32_t)MW) {
+                unsigned long long u[MW];
+#pragma unroll
+                for (int j = 0; j < MW; j++) u[j] = (w0 + j <= w1) ? __ldcg(G.U + w0 + j) : 0ull;
+                uint32_t live = 0;
+#pragma unroll
+                for (int j = 0; j < MW; j++) {
+                    unsigned long long m = ~0ull;
+                    if (j == 0) m &= ~0ull << (r.x & 63);
+                    if (w0 + j == w1) m &= ~0ull >> (63 - ((r.y - 1) & 63));
+                    if (w0 + j <= w1 && (u[j] & m)) live |= 1u << j;
+                }
+                c_live[k] = live;
+                const unsigned long long mk = mkey_of(c_si[k]);
+#pragma unroll
+                for (int j = 0; j < MW; j++)
+                    if ((live >> j) & 1u) atomicMax(&G.mark[w0 + j], mk);
+            } else {                                    // long interval: word by word, re-read in the check phase
+                c_live[k] = 0x80000000u;
+                const unsigned long long mk = mkey_of(c_si[k]);
+                for_each_word(r, [&](uint32_t w, unsigned long long m) {
+                    if (__ldcg(G.U + w) & m) atomicMax(&G.mark[w], mk);
+                });
+            }
+        }
+        for (int64_t f = gtid + (int64_t)MC * gsize; f < (int64_t)total_pairs; f += gsize) {     // rarely: more pairs
             uint32_t a, si;
             const uint2 r = pair_of((uint32_t)f, a, si);
-            const unsigned long long key = key_of(si);
+            const unsigned long long mk = mkey_of(si);
             for_each_word(r, [&](uint32_t w, unsigned long long m) {
-                if (__ldcg(G.U + w) & m) atomicMax(&G.mark[w], key);
+                if (__ldcg(G.U + w) & m) atomicMax(&G.mark[w], mk);
             });
         }
+        fine(2);
         grid_barrier(G, bar_target);
+        fine(3);
 
-        // ---- check
-        for (int64_t f = gtid; f < (int64_t)total_pairs; f += gsize) {
+        // ---- check: accepted iff the candidate holds the mark of every word it marked
+#pragma unroll
+        for (int k = 0; k < MC; k++) {
+            const uint2 r = c_r[k];
+            if (r.x >= r.y) continue;
+            const unsigned long long mk = mkey_of(c_si[k]);
+            const uint32_t w0 = r.x >> 6;
+            bool conflict = false;
+            if (!(c_live[k] & 0x80000000u)) {
+                unsigned long long mv[MW];
+#pragma unroll
+                for (int j = 0; j < MW; j++) mv[j] = ((c_live[k] >> j) & 1u) ? __ldcg(G.mark + w0 + j) : mk;
+#pragma unroll
+                for (int j = 0; j < MW; j++) conflict |= mv[j] != mk;
+            } else {
+                for_each_word(r, [&](uint32_t w, unsigned long long m) {
+                    if ((__ldcg(G.U + w) & m) && __ldcg(G.mark + w) != mk) conflict = true;
+                });
+            }
+            if (conflict) reinterpret_cast<volatile unsigned char *>(G.conf)[c_a[k]] = 1;     // plain byte store: no contention
+        }
+        for (int64_t f = gtid + (int64_t)MC * gsize; f < (int64_t)total_pairs; f += gsize) {
             uint32_t a, si;
             const uint2 r = pair_of((uint32_t)f, a, si);
-            const unsigned long long key = key_of(si);
+            const unsigned long long mk = mkey_of(si);
             bool conflict = false;
             for_each_word(r, [&](uint32_t w, unsigned long long m) {
-                if ((__ldcg(G.U + w) & m) && __ldcg(G.mark + w) != key) conflict = true;
+                if ((__ldcg(G.U + w) & m) && __ldcg(G.mark + w) != mk) conflict = true;
             });
-            if (conflict) reinterpret_cast<volatile unsigned char *>(G.conf)[a] = 1;     // plain byte store: no contention
+            if (conflict) reinterpret_cast<volatile unsigned char *>(G.conf)[a] = 1;
         }
+        fine(4);
         grid_barrier(G, bar_target);
         if (failed()) break;
+        fine(5);
 
         // ---- winners = active candidates without a conflict (same compaction in every CTA)
         uint32_t n_win = 0, win_pairs = 0;
@@ -779,16 +884,12 @@ greedy_rounds_kernel(const RParams G)
             __syncthreads();
         }
         lap(1);
+        fine(6);
         n_rounds++;
         n_active_sum += n_act;
         n_picks += n_win;
 
-        // ---- reset the marks of this round
-        for (int64_t f = gtid; f < (int64_t)total_pairs; f += gsize) {
-            uint32_t a, si;
-            const uint2 r = pair_of((uint32_t)f, a, si);
-            for_each_word(r, [&](uint32_t w, unsigned long long) { G.mark[w] = 0ull; });
-        }
+        fine(7);
         // ---- apply every accepted probe.  The cost of a (winner, interval) pair varies a lot (number of indexed
         // items it overlaps, contention on the gains), so the pairs are handed out dynamically: a warp takes the
         // next one from a global counter when it is done with its own.  Two counters alternate between rounds; the
@@ -812,8 +913,10 @@ greedy_rounds_kernel(const RParams G)
             }
         }
         lap(2);
+        fine(8);
     }
     if (gtid == 0) {
+        for (int i = 0; i < 12; i++) G.ctr[8 + i] = t_fine[i];
         xh->epoch = epoch;
         *G.n_sel = n_picks;
         for (int i = 0; i < 4; i++) G.phase_ns[i] = t_phase[i];
@@ -948,8 +1051,8 @@ int cb_rounds_job::prepare(const cb_cover *cover, int64_t lo, int64_t hi, const 
     CB_CUDA(ctx, cudaMemsetAsync(d_mark.p, 0, 8 * ((size_t)u_words + 1), st));
     // control block: [0] remaining, [1] barrier, [2] release, [3..4] key_local, [5..8] phase ns, [9..11] counters,
     // [12] n_sel, [13] status, [14] diagnostics
-    CB_CUDA(ctx, d_ctl.alloc(16));
-    CB_CUDA(ctx, cudaMemsetAsync(d_ctl.p, 0, 8 * 16, st));
+    CB_CUDA(ctx, d_ctl.alloc(40));
+    CB_CUDA(ctx, cudaMemsetAsync(d_ctl.p, 0, 8 * 40, st));
     // small u32 block: list[4 * list_cap] (uint4 entries), conf[LIST_CAP_MAX / 4], hist_local[128], list_n[4], work[4]
     const size_t n_small = 4 * (size_t)list_cap + LIST_CAP_MAX / 4 + 128 + 4 + 4;
     CB_CUDA(ctx, d_small.alloc(n_small));
@@ -1056,10 +1159,14 @@ int cb_rounds_job::run(int64_t *sel_ids, int64_t *n_sel, cb_stats *stats)
     t_greedy.stop();
     t_all.stop();
 
-    unsigned long long h_ctl[16];
+    unsigned long long h_ctl[40];
     CB_CUDA(ctx, cudaMemcpyAsync(h_ctl, d_ctl.p, sizeof h_ctl, cudaMemcpyDeviceToHost, st));
     CB_CUDA(ctx, cudaStreamSynchronize(st));
     trace(ctx, "rounds: greedy kernel finished");
+    if (getenv("CB_TRACE"))
+        fprintf(stderr, "[cb] round phases (us, CTA 0): xchg %.0f compact %.0f mark %.0f bar %.0f check %.0f bar %.0f winners %.0f reset %.0f "
+                        "apply %.0f | rebuilds %llu rounds %llu\n", h_ctl[17] / 1e3, h_ctl[18] / 1e3, h_ctl[19] / 1e3, h_ctl[20] / 1e3,
+                h_ctl[21] / 1e3, h_ctl[22] / 1e3, h_ctl[23] / 1e3, h_ctl[24] / 1e3, h_ctl[25] / 1e3, h_ctl[9], h_ctl[10]);
     const long long h_nsel = (long long)h_ctl[12];
     const int h_status = (int)(uint32_t)h_ctl[13];
     if (h_status == CB_ERR_COMM) {
