@@ -385,7 +385,7 @@ __global__ void index_kernel(const int64_t *__restrict__ iv_off, const uint2 *__
     }
 }
 
-__global__ void __launch_bounds__(RT, 3)
+__global__ void __launch_bounds__(RT, 2)
 greedy_rounds_kernel(const RParams G)
 {
     __shared__ unsigned long long s_key[NWARP];
@@ -957,7 +957,7 @@ struct cb_rounds_job {
     bool sharded = false;
     int64_t P = 0, E = 0, n_items = 0;
     int32_t n_ranks = 1;
-    uint32_t list_cap = 2048u;
+    uint32_t list_cap = 3072u;
     std::vector<uint32_t> h_rank;
     DevBuf<unsigned char> d_area;
     DevBuf<uint32_t> d_rank, d_gain, d_bcount, d_bcursor, d_small;
@@ -991,7 +991,7 @@ int cb_rounds_job::prepare(const cb_cover *cover, int64_t lo, int64_t hi, const 
     const int64_t u_words = cover->universe_bits >> 6;
     const int64_t n_blocks = u_words + 1;
 
-    list_cap = 2048u;                             // <= LIST_CAP_MAX; 2048 leaves room for 3 CTAs per SM
+    list_cap = 3072u;                             // <= LIST_CAP_MAX; with 2 CTAs per SM the measured optimum (profiles/README_r02.md)
     if (const char *e = getenv("CB_GREEDY_LIST_CAP")) {
         const int v = atoi(e);
         if (v >= 1 && v <= LIST_CAP_MAX) list_cap = (uint32_t)v;
@@ -1134,12 +1134,12 @@ int cb_rounds_job::run(int64_t *sel_ids, int64_t *n_sel, cb_stats *stats)
 {
     cudaStream_t st = ctx->stream;
     const int R = G.n_ranks, me = G.rank;
-    // ---- persistent launch: cooperative (co-residency guaranteed), as many blocks as the device holds (<= 3 per SM)
+    // ---- persistent launch: cooperative (co-residency guaranteed), as many blocks as the device holds (<= 2 per SM)
     const size_t dyn_smem = sizeof(uint32_t) * (6 * (size_t)list_cap + 2) + 5 * (size_t)list_cap;
     int per_sm = 0;
     CB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, greedy_rounds_kernel, RT, dyn_smem));
     if (per_sm < 1) return cb_fail(ctx, CB_ERR_CUDA, "greedy kernel does not fit on an SM");
-    int want = 3;
+    int want = 2;
     if (const char *e = getenv("CB_GREEDY_BLOCKS_PER_SM")) want = atoi(e) > 0 ? atoi(e) : want;
     if (per_sm > want) per_sm = want;
     int grid = per_sm * ctx->sm_count;

@@ -300,3 +300,64 @@ def test_set_cover_module_drop_in(ctx, ref_tests):
         sc.approx_multiuniverse({0: {0: {1}}}, costs={0: -1.0}, ctx=ctx)
     with pytest.raises(ValueError):
         sc.approx_multiuniverse({0: {0: {1}}}, use_arrays=True, use_intervalsets=True, ctx=ctx)
+
+
+def test_scale_goldens_config2_and_config3_shapes(ctx):
+    """Oracle-generated goldens at BASELINE shapes (tests/golden/make_scale_golden.py): 120 genomes of the
+    config-2 generator (-pl 75 -m 2 -l 60 -e 50) and 40 influenza-shaped genomes of the config-3 generator with
+    the MinHash near-duplicate filter on (-m 5 -l 30 -e 50).  Interval counts, the greedy pick SEQUENCE, the
+    filter's output order and the near-duplicate filter's kept set are all compared bit for bit."""
+    import hashlib
+    from catch_b200 import coverage as cov
+    from catch_b200 import probe
+    from catch_b200.filter import near_duplicate_filter as ndf
+    from catch_b200.filter.set_cover_filter import SetCoverFilter
+    gold = golden_io.load('scale_oracle.json.gz')
+
+    def md5(strs):
+        return hashlib.md5('\n'.join(strs).encode()).hexdigest()
+
+    def check_scf(cands, seq_groups, c):
+        genomes = helpers.to_genomes([seq_groups])
+        # stage by stage: number of merged intervals and the pick sequence
+        group = cov.PackedGroup(ctx, cands, seq_groups)
+        np.random.seed(c['np_seed'])
+        plan = cov.SeedPlan(cands, c['scf']['mismatches'], c['scf']['lcf_thres'], 20)
+        cover, st = cov.compute_cover(ctx, group, plan, c['scf']['mismatches'], c['scf']['lcf_thres'], 0,
+                                      c['scf']['cover_extension'])
+        group.free()
+        assert int(st.n_intervals) == c['n_intervals']
+        picks, _ = ctx.setcover(cover, len(cands))
+        cover.free()
+        assert picks.tolist() == c['picks']
+        # the plugin call on host objects, output order included
+        f = SetCoverFilter(**c['scf'])
+        f._ctx = ctx
+        probes = [probe.Probe.from_str(s) for s in cands]
+        np.random.seed(c['np_seed'])
+        random.seed(c['np_seed'])
+        out = f.filter([probes], genomes, input_is_grouped=True)
+        ids = {id(p): i for i, p in enumerate(probes)}
+        assert [ids[id(p)] for p in out[0]] == c['selected']
+
+    c = gold['config2_120']
+    seqs = helpers.synthetic_genomes(c['n_genomes'], c['length'], c['div'], c['gen_seed'])
+    cands = list(dict.fromkeys(helpers.tile_candidates(seqs, c['pl'], c['ps'])))
+    assert len(cands) == c['n_cands'] and md5(cands) == c['cands_md5']
+    check_scf(cands, [[s] for s in seqs], c)
+
+    c = gold['config3_40']
+    gens = helpers.synthetic_influenza(c['n_genomes'], seed=c['gen_seed'])
+    segs = [seg for g in gens for seg in g]
+    c3 = helpers.tile_candidates(segs, c['pl'], c['ps'])
+    assert len(c3) == c['n_cands'] and md5(c3) == c['cands_md5']
+    flt = ndf.NearDuplicateFilterWithMinHash(c['ndf']['dist_thres'])
+    flt._ctx = ctx
+    random.seed(c['ndf']['random_seed'])
+    kept = flt.filter([probe.Probe.from_str(s) for s in c3])
+    first = {}
+    for i, s in enumerate(c3):
+        first.setdefault(s, i)
+    kept_idx = sorted(first[p.seq_str] for p in kept)
+    assert kept_idx == c['kept_idx']
+    check_scf([c3[i] for i in kept_idx], [[s] for s in segs], c)

@@ -115,3 +115,21 @@ def test_cpython_str_hash(rnd_cases):
     """abs(hash(str)) under PYTHONHASHSEED=0 == SipHash-1-3, zero key (utils/lsh.py:103)."""
     for s, h in rnd_cases['hash']:
         assert O.abs_pyhash(s) == h
+
+
+def test_scale_golden_inputs_match_the_generators():
+    """tests/golden/scale_oracle.json.gz stores generator parameters, not sequences: the inputs the GPU test
+    regenerates must be the ones the oracle saw when the fixture was made."""
+    import hashlib
+    from tests import helpers
+    gold = golden_io.load('scale_oracle.json.gz')
+    c = gold['config2_120']
+    seqs = helpers.synthetic_genomes(c['n_genomes'], c['length'], c['div'], c['gen_seed'])
+    cands = list(dict.fromkeys(helpers.tile_candidates(seqs, c['pl'], c['ps'])))
+    assert hashlib.md5('\n'.join(cands).encode()).hexdigest() == c['cands_md5']
+    assert len(c['picks']) == len(c['selected']) > 300 and sorted(c['picks']) == sorted(c['selected'])
+    c = gold['config3_40']
+    segs = [seg for g in helpers.synthetic_influenza(c['n_genomes'], seed=c['gen_seed']) for seg in g]
+    c3 = helpers.tile_candidates(segs, c['pl'], c['ps'])
+    assert hashlib.md5('\n'.join(c3).encode()).hexdigest() == c['cands_md5']
+    assert 0 < len(c['kept_idx']) < len(c3) and len(c['picks']) > 300
