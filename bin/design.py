@@ -2,9 +2,10 @@
 """Design probes: same command line as the reference's bin/design.py (:448-980), with the
 near-duplicate and set-cover filters running on the GPU (catch_b200).
 
-Flags that only configure parts of CATCH outside the accelerated hot path (NCBI download, genome
-clustering, adapters, poly-A / N-expansion / reverse-complement filters, coverage analysis reports)
-are parsed for compatibility and rejected with a clear message when used.
+The near-duplicate, set-cover and adapter filters and the coverage analysis run on the GPU
+(catch_b200).  Flags that only configure parts of CATCH outside the accelerated path (NCBI download,
+poly-A / N-expansion filters, --filter-from-fasta) are parsed for compatibility
+and rejected with a clear message when used.
 """
 import argparse
 import logging
@@ -15,18 +16,16 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 from catch_b200 import __version__  # noqa: E402
-from catch_b200.filter import duplicate_filter, near_duplicate_filter, probe_designer, set_cover_filter  # noqa: E402
+from catch_b200 import coverage_analysis  # noqa: E402
+from catch_b200.filter import (adapter_filter, duplicate_filter, near_duplicate_filter, probe_designer,  # noqa: E402
+                                reverse_complement_filter, set_cover_filter)
 from catch_b200.utils import seq_io  # noqa: E402
 
 logger = logging.getLogger(__name__)
 
 UNSUPPORTED = {
     'filter_from_fasta': '--filter-from-fasta', 'filter_polya': '--filter-polya',
-    'add_adapters': '--add-adapters', 'adapter_a': '--adapter-a', 'adapter_b': '--adapter-b',
-    'expand_n': '--expand-n', 'add_reverse_complements': '--add-reverse-complements',
-    'print_analysis': '--print-analysis', 'write_analysis_to_tsv': '--write-analysis-to-tsv',
-    'write_sliding_window_coverage': '--write-sliding-window-coverage',
-    'write_probe_map_counts_to_tsv': '--write-probe-map-counts-to-tsv',
+    'expand_n': '--expand-n',
     'cluster_from_fragments': '--cluster-from-fragments',
     'custom_hybridization_fn': '--custom-hybridization-fn',
     'custom_hybridization_fn_tolerant': '--custom-hybridization-fn-tolerant',
@@ -45,12 +44,14 @@ def main(args):
         logger.warning("design_large.py: genome clustering is not available; designing without it")
 
     genomes_grouped = []
+    genomes_grouped_names = []
     for ds in args.dataset:
         if ds.startswith('download:') or ds.startswith('collection:'):
             raise ValueError("Only FASTA files are accepted as input (no network access for 'download:')")
         if not os.path.isfile(ds):
             raise ValueError("Please check that the path to '%s' is valid" % ds)
         genomes_grouped.append(seq_io.read_genomes_from_fasta(ds))
+        genomes_grouped_names.append(os.path.basename(ds))
 
     if args.limit_target_genomes and args.limit_target_genomes_randomly_with_replacement:
         raise Exception("Cannot --limit-target-genomes and --limit-target-genomes-randomly-with-replacement "
@@ -77,9 +78,17 @@ def main(args):
         if args.kmer_probe_map_k > args.probe_length:
             raise Exception("KMER_PROBE_MAP_K (%d) exceeds PROBE_LENGTH (%d), which is not permitted" %
                             (args.kmer_probe_map_k, args.probe_length))
-        k_scf = args.kmer_probe_map_k
+        k_scf = k_af = k_analyzer = args.kmer_probe_map_k
     else:
-        k_scf = 20
+        # bin/design.py:199-205: 20 for the set cover and adapter filters, 10 for the (more sensitive) analyzer
+        k_scf, k_af, k_analyzer = 20, 20, 10
+    if args.add_adapters:
+        if not (args.adapter_a or args.adapter_b):
+            logger.warning("Adapter sequences will be added, but default sequences will be used; to provide "
+                           "adapter sequences, use --adapter-a and --adapter-b")
+    elif args.adapter_a or args.adapter_b:
+        raise Exception("Adapter sequences were provided with --adapter-a and --adapter-b, but --add-adapters is "
+                        "required to add adapter sequences onto the ends of probes")
     if args.small_seq_skip is not None and args.small_seq_min is not None:
         raise Exception("Both --small-seq-skip and --small-seq-min were specified, but both cannot be used together")
 
@@ -104,12 +113,40 @@ def main(args):
             identify=args.identify, avoided_genomes=avoided, coverage=args.coverage,
             cover_extension=args.cover_extension, kmer_probe_map_k=k_scf))
 
+    if args.add_adapters:                           # bin/design.py:343-365
+        adapter_a = tuple(args.adapter_a) if args.adapter_a else ('ATACGCCATGCTGGGTCTCC', 'CGTACTTGGGAGTCGGCCAT')
+        adapter_b = tuple(args.adapter_b) if args.adapter_b else ('AGGCCCTGGCTGCTGATATG', 'GACCTTTTGGGACAGCGGTG')
+        filters.append(adapter_filter.AdapterFilter(adapter_a, adapter_b, mismatches=args.mismatches,
+                                                    lcf_thres=args.lcf_thres,
+                                                    island_of_exact_match=args.island_of_exact_match,
+                                                    kmer_probe_map_k=k_af))
+
+    if args.add_reverse_complements:               # bin/design.py:375-380
+        filters.append(reverse_complement_filter.ReverseComplementFilter())
+
     pd = probe_designer.ProbeDesigner(genomes_grouped, filters, probe_length=args.probe_length,
                                       probe_stride=args.probe_stride, allow_small_seqs=args.small_seq_min,
                                       seq_length_to_skip=args.small_seq_skip)
     pd.design()
     seq_io.write_probe_fasta(pd.final_probes, args.output_probes)
-    print(len(pd.final_probes))
+    if (args.print_analysis or args.write_analysis_to_tsv or args.write_sliding_window_coverage or
+            args.write_probe_map_counts_to_tsv):                          # bin/design.py:417-443
+        analyzer = coverage_analysis.Analyzer(pd.final_probes, args.mismatches, args.lcf_thres, genomes_grouped,
+                                              genomes_grouped_names,
+                                              island_of_exact_match=args.island_of_exact_match,
+                                              cover_extension=args.cover_extension, kmer_probe_map_k=k_analyzer,
+                                              rc_too=bool(args.add_reverse_complements))
+        analyzer.run()
+        if args.write_analysis_to_tsv:
+            analyzer.write_data_matrix_as_tsv(args.write_analysis_to_tsv)
+        if args.write_sliding_window_coverage:
+            analyzer.write_sliding_window_coverage(args.write_sliding_window_coverage)
+        if args.write_probe_map_counts_to_tsv:
+            analyzer.write_probe_map_counts(args.write_probe_map_counts_to_tsv)
+        if args.print_analysis:
+            analyzer.print_analysis()
+    else:
+        print(len(pd.final_probes))
 
 
 def init_and_parse_args(args_type='basic', argv=None):

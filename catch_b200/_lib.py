@@ -48,7 +48,7 @@ EXPORTED_SYMBOLS = [
     'cb_coverage', 'cb_coverage_uniform', 'cb_cover_free', 'cb_cover_num_intervals', 'cb_cover_export', 'cb_cover_import',
     'cb_setcover', 'cb_setcover_costs', 'cb_minhash_neardup', 'cb_hamming_neardup', 'cb_neardup_filter', 'cb_group_duplicates',
     'cb_comm_unique_id', 'cb_comm_init', 'cb_comm_destroy', 'cb_cover_allgather',
-    'cb_coverage_range', 'cb_exchange_alloc', 'cb_exchange_bytes', 'cb_exchange_handle', 'cb_exchange_attach',
+    'cb_coverage_range', 'cb_coverage_records', 'cb_free_host', 'cb_exchange_alloc', 'cb_exchange_bytes', 'cb_exchange_handle', 'cb_exchange_attach',
     'cb_exchange_required', 'cb_setcover_sharded', 'cb_setcover_sharded_begin', 'cb_setcover_sharded_end',
 ]
 
@@ -96,6 +96,10 @@ def load():
     L.cb_coverage_uniform.argtypes = [vp, vp, vp, C.POINTER(HybParams), vp, i32, C.POINTER(vp), C.POINTER(Stats)]
     L.cb_coverage_range.argtypes = [vp, vp, vp, C.POINTER(HybParams), vp, vp, vp, i32, i64, i64, C.POINTER(vp),
                                     C.POINTER(Stats)]
+    L.cb_coverage_records.argtypes = [vp, vp, vp, C.POINTER(HybParams), vp, vp, C.POINTER(i64), C.POINTER(vp),
+                                      C.POINTER(Stats)]
+    L.cb_free_host.argtypes = [vp]
+    L.cb_free_host.restype = None
     L.cb_exchange_alloc.argtypes = [vp, i64]
     L.cb_exchange_bytes.argtypes = [vp]
     L.cb_exchange_bytes.restype = i64
@@ -257,6 +261,22 @@ class Context:
             self._check(self.L.cb_coverage_range(self.h, probes.h, targets.h, C.byref(hp), _ptr(seed_off),
                                                  _ptr(seed_pos), None, 0, lo, hi, C.byref(out), C.byref(st)))
         return Handle(self.L.cb_cover_free, out), st
+
+    def coverage_records(self, probes, targets, mismatches, lcf_thres, island, k, seed_off, seed_pos):
+        """cb_coverage_records: the unmerged ranges of the scan as an int64 [n, 5] array
+        (probe, sequence, start, end, position of the seed hit), in no particular order."""
+        hp = HybParams(mismatches, lcf_thres, island, 0, k)
+        n, buf, st = C.c_int64(), C.c_void_p(), Stats()
+        self._check(self.L.cb_coverage_records(self.h, probes.h, targets.h, C.byref(hp), _ptr(seed_off), _ptr(seed_pos),
+                                               C.byref(n), C.byref(buf), C.byref(st)))
+        try:
+            if n.value == 0:
+                return np.zeros((0, 5), dtype=np.int64), st
+            raw = np.ctypeslib.as_array(C.cast(buf, C.POINTER(C.c_uint32)), shape=(n.value, 5))
+            return raw.astype(np.int64), st
+        finally:
+            if buf.value:
+                self.L.cb_free_host(buf)
 
     def cover_export(self, cover):
         n = self.L.cb_cover_num_intervals(cover.h)

@@ -233,6 +233,93 @@ def compute_cover_range(ctx, group, plan, mismatches, lcf_thres, island, cover_e
                               plan.k, lo, hi, seed_off=plan.seed_off, seed_pos=plan.seed_pos)
 
 
+class KmerMapOrder:
+    """Order in which the reference's k-mer map lists the probes that share one k-mer.  The map's values
+    are Python SETS of (probe, position) tuples (probe.py:385, :497), filled probe by probe in list order
+    and k-mer by k-mer in draw order, and find_probe_covers_in_sequence aligns the probes of a k-mer in the
+    iteration order of that set (probe.py:756-760, :1067).  That order decides which of several probes first
+    seen at the SAME sequence position comes first in the scan's result dict, which the consumers with
+    order-dependent output inherit (interval.schedule ties in the adapter filter, the row order of the
+    analyzer's probe-map-counts file).  It is reproduced with the real thing: the same insertions into real
+    sets of (Probe, position) tuples -- Probe hashes by its sequence, so like the reference this is
+    reproducible across processes only under a fixed PYTHONHASHSEED.  Built lazily: ties are rare."""
+
+    def __init__(self, probes, plan):
+        self.probes, self.plan, self.sets = probes, plan, None
+
+    def _build(self):
+        k, seeds = self.plan.k, np.asarray(self.plan._seeds)
+        sets = {}
+        for i, p in enumerate(self.probes):
+            s = p.seq_str
+            for pos in seeds[i].tolist():
+                sets.setdefault(s[pos:pos + k], set()).add((p, pos))
+        self.sets = sets
+
+    def rank(self, kmer, probe):
+        """Index of `probe`'s first entry in the iteration order of the k-mer's set (large if absent)."""
+        if self.sets is None:
+            self._build()
+        for r, (q, _pos) in enumerate(self.sets.get(kmer, ())):
+            if q == probe:
+                return r
+        return 1 << 30
+
+
+def listing_tie_ranks(g_probe, g_hit, sequence, kmer_order):
+    """Secondary sort key of the listing order: 0 everywhere except for probes whose first hit is at the same
+    sequence position as another probe's; those get their rank in the k-mer map's set of that position's k-mer."""
+    tie = np.zeros(len(g_probe), dtype=np.int64)
+    if kmer_order is None or sequence is None or len(g_probe) < 2:
+        return tie
+    probes_u, first = np.unique(g_probe, return_index=True)
+    hits_u = g_hit[first]
+    vals, counts = np.unique(hits_u, return_counts=True)
+    for h in vals[counts > 1].tolist():
+        kmer = sequence[h:h + kmer_order.plan.k]
+        for pi in probes_u[hits_u == h].tolist():
+            tie[g_probe == pi] = kmer_order.rank(kmer, kmer_order.probes[pi])
+    return tie
+
+
+def sequence_batches(sequences, max_bases=1 << 30):
+    """Split an iterable of sequences into lists whose total length stays below max_bases, so that a
+    grouping of any size goes through the device in bounded pieces (a universe is limited to 2^32 bits,
+    cb_upload_targets).  A single sequence longer than max_bases forms its own batch."""
+    batch, total = [], 0
+    for s in sequences:
+        if batch and total + len(s) > max_bases:
+            yield batch
+            batch, total = [], 0
+        batch.append(s)
+        total += len(s)
+    if batch:
+        yield batch
+
+
+def scan_records(ctx, probe_strs, sequences, plan, mismatches, lcf_thres, island, max_bases=1 << 30):
+    """The device counterpart of probe.find_probe_covers_in_sequence() over every sequence of `sequences`
+    BEFORE any merging (probe.py:1008-1119): an int64 array [n, 5] of (probe index, sequence index, start,
+    end, position of the seed hit) with one row per emitted range, in no particular order.  The two uses
+    in the reference: merge_overlapping=False callers take sorted(set(ranges)) per probe and sequence
+    (probe.py:1262-1270), merge_overlapping=True callers merge them (utils/interval.py:288-316); the hit
+    position gives the order in which the reference's result dict first sees each probe."""
+    out, base = [], 0
+    seqs = list(sequences)
+    for batch in sequence_batches(seqs, max_bases):
+        group = PackedGroup(ctx, probe_strs, [[s] for s in batch])
+        try:
+            rec, _ = ctx.coverage_records(group.probes, group.targets, mismatches, lcf_thres, island, plan.k,
+                                          plan.seed_off, plan.seed_pos)
+        finally:
+            group.free()
+        if len(rec):
+            rec[:, 1] += base
+            out.append(rec)
+        base += len(batch)
+    return np.concatenate(out) if out else np.zeros((0, 5), dtype=np.int64)
+
+
 def cover_with_seeds(ctx, group, seeds_per_probe, k, mismatches, lcf_thres, island, cover_extension):
     """Stage A with explicitly given seed positions (a list of position lists, one per probe):
     the device counterpart of probe.find_probe_covers_in_sequence over a prebuilt

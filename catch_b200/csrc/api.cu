@@ -1,6 +1,7 @@
 // C ABI of libcatchb200.so (see include/catch_b200.h): context, packing (uploads), exports and
 // the thin wrappers around the stage implementations.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "internal.cuh"
@@ -485,6 +486,50 @@ int cb_coverage_range(cb_ctx *ctx, const cb_probes *probes, const cb_targets *ta
     return cb_coverage_impl(ctx, probes, targets, params, seed_off, seed_pos, seed_pos_u8, seeds_per_probe, probe_lo,
                             probe_hi, out, stats);
 }
+
+int cb_coverage_records(cb_ctx *ctx, const cb_probes *probes, const cb_targets *targets, const cb_hyb_params *params,
+                        const int64_t *seed_off, const int32_t *seed_pos, int64_t *n_records, uint32_t **records,
+                        cb_stats *stats)
+{
+    if (!ctx) return CB_ERR_ARG;
+    if (!n_records || !records || !targets) return cb_fail(ctx, CB_ERR_ARG, "null argument");
+    *n_records = 0;
+    *records = nullptr;
+    if (stats) memset(stats, 0, sizeof *stats);
+    ctx->launches = 0;
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cb_tls_stream = ctx->stream;
+    if (targets->total_bases >= 0xffffffffll) return cb_fail(ctx, CB_ERR_UNSUPPORTED, "target group exceeds 2^32 bases");
+    std::vector<uint32_t> raw;
+    cb_cover *cov = nullptr;
+    const int rc = cb_coverage_impl(ctx, probes, targets, params, seed_off, seed_pos, nullptr, 0, 0, -1, &cov, stats, &raw);
+    if (cov) cb_cover_free(cov);
+    if (rc != CB_OK) return rc;
+    const size_t n = raw.size() / 4;
+    if (n) {
+        uint32_t *buf = (uint32_t *)malloc(n * 5 * sizeof(uint32_t));
+        if (!buf) return cb_fail(ctx, CB_ERR_NOMEM, "out of host memory");
+        // records -> (probe, sequence, start, end, hit position): universe and target coordinates become
+        // positions inside the sequence the range lies in
+        const std::vector<int64_t> &ss = targets->h_seq_start;
+        std::vector<uint32_t> seq_ubase((size_t)targets->n_seqs);
+        CB_CUDA(ctx, cudaMemcpy(seq_ubase.data(), targets->d_seq_ubase, sizeof(uint32_t) * (size_t)targets->n_seqs, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < n; i++) {
+            const uint32_t hit = raw[4 * i + 3];
+            const size_t q = (size_t)(std::upper_bound(ss.begin(), ss.end(), (int64_t)hit) - ss.begin()) - 1;
+            buf[5 * i] = raw[4 * i];
+            buf[5 * i + 1] = (uint32_t)q;
+            buf[5 * i + 2] = raw[4 * i + 1] - seq_ubase[q];
+            buf[5 * i + 3] = raw[4 * i + 2] - seq_ubase[q];
+            buf[5 * i + 4] = (uint32_t)((int64_t)hit - ss[q]);
+        }
+        *records = buf;
+    }
+    *n_records = (int64_t)n;
+    return CB_OK;
+}
+
+void cb_free_host(void *p) { free(p); }
 
 void cb_cover_free(cb_cover *c)
 {

@@ -773,12 +773,13 @@ scan_kernel(const ScanParams P)
                 for (uint32_t tb = 0; tb < qn; tb += SCAN_THREADS) {
                     const uint32_t ti = tb + tid;
                     bool emit = false;
-                    uint32_t p = 0, us = 0, ue = 0;
+                    uint32_t p = 0, us = 0, ue = 0, hit = 0;
                     if (ti < qn) {
                         const uint64_t task = s_queue[ti];
                         const int j = (int)(task >> 40);
                         const int pos = (int)(task & 0xffull);
                         p = (uint32_t)(task >> 8);
+                        hit = (uint32_t)(t0 + j);                  // target coordinate of the seed hit (probe.py:1062 `i`)
                         const uint32_t q = s_seq[j];
                         emit = eval_hit<NW, FAST>(P, s_tile, t0, t0 + j - pos, pos, p, P.seq_start[q], P.seq_start[q + 1],
                                                 P.seq_ubase[q], us, ue);
@@ -792,7 +793,7 @@ scan_kernel(const ScanParams P)
                         wb = __shfl_sync(0xffffffffu, wb, 0);
                         if (emit) {
                             const unsigned long long slot = wb + __popc(em & ((1u << lane) - 1u));
-                            if (slot < P.rec_cap) P.rec[slot] = make_uint4(p, us, ue, 0u);
+                            if (slot < P.rec_cap) P.rec[slot] = make_uint4(p, us, ue, hit);
                             atomicAdd(&P.rec_count[p], 1u);
                         }
                     }
@@ -1076,7 +1077,7 @@ int launch_scan_nw(cb_ctx *ctx, int nw, const ScanParams &P, int grid)
 int cb_coverage_impl(cb_ctx *ctx, const cb_probes *probes, const cb_targets *targets,
                      const cb_hyb_params *hp, const int64_t *seed_off, const int32_t *seed_pos,
                      const uint8_t *seed_pos_u8, int32_t seeds_per_probe, int64_t probe_lo, int64_t probe_hi,
-                     cb_cover **out, cb_stats *stats)
+                     cb_cover **out, cb_stats *stats, std::vector<uint32_t> *raw_records)
 {
     if (!probes || !targets || !hp || !out) return cb_fail(ctx, CB_ERR_ARG, "null argument");
     // [probe_lo, probe_hi): the probes this call scans (a rank's shard); the cover keeps global probe ids
@@ -1274,6 +1275,27 @@ int cb_coverage_impl(cb_ctx *ctx, const cb_probes *probes, const cb_targets *tar
     }
     t_emit.stop();
     if (n_raw >= 0xfffffff0ull * 16ull) return cb_fail(ctx, CB_ERR_UNSUPPORTED, "too many cover ranges");
+    if (raw_records) {
+        // the caller wants the emitted ranges themselves (probe, start, end, hit position), unmerged: the
+        // consumers with merge_overlapping=False semantics (coverage_analysis.py:228-231) and the adapter
+        // filter's interval scheduling (adapter_filter.py:191-238) take it from here on the host
+        raw_records->resize((size_t)n_raw * 4);
+        if (n_raw) CB_CUDA(ctx, cudaMemcpyAsync(raw_records->data(), d_rec.p, sizeof(uint4) * (size_t)n_raw, cudaMemcpyDeviceToHost, st));
+        CB_CUDA(ctx, cudaMemsetAsync(cov->d_iv_off, 0, sizeof(int64_t) * (size_t)(P + 1), st));
+        CB_CUDA(ctx, cudaStreamSynchronize(st));
+        if (stats) {
+            stats->ms_seed_index = t_idx.ms();
+            stats->ms_scan_count = t_cnt.ms();
+            stats->ms_scan_emit = t_emit.ms();
+            stats->n_seed_entries = n_entries;
+            stats->n_candidate_hits = (int64_t)h_ctr[1];
+            stats->n_raw_ranges = (int64_t)n_raw;
+            stats->n_kernel_launches = ctx->launches;
+        }
+        guard.c = nullptr;
+        *out = cov;
+        return CB_OK;
+    }
 
     // ---- bucket by probe, K4 merge
     t_merge.start();

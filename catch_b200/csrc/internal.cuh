@@ -188,7 +188,7 @@ int cb_intop_rate_impl(cb_ctx *ctx, double *ops_per_s);
 int cb_coverage_impl(cb_ctx *ctx, const cb_probes *probes, const cb_targets *targets,
                      const cb_hyb_params *params, const int64_t *seed_off, const int32_t *seed_pos,
                      const uint8_t *seed_pos_u8, int32_t seeds_per_probe, int64_t probe_lo, int64_t probe_hi,
-                     cb_cover **out, cb_stats *stats);
+                     cb_cover **out, cb_stats *stats, std::vector<uint32_t> *raw_records = nullptr);
 
 int cb_cover_import_impl(cb_ctx *ctx, int64_t n_probes, int32_t n_genomes, const int64_t *genome_len,
                          int64_t n_intervals, const int64_t *probe_id, const int32_t *genome,

@@ -192,6 +192,18 @@ int cb_coverage_range(cb_ctx *ctx, const cb_probes *probes, const cb_targets *ta
                       const cb_hyb_params *params, const int64_t *seed_off, const int32_t *seed_pos,
                       const uint8_t *seed_pos_u8, int32_t seeds_per_probe, int64_t probe_lo, int64_t probe_hi,
                       cb_cover **out, cb_stats *stats);
+/* The ranges the scan emits, one record per (probe, diagonal, mismatch-free run that holds a selected seed)
+ * that passes the predicate, NOT merged and NOT extended by cover_extension (params->cover_extension must be
+ * 0): five uint32 per record = probe index, sequence index, start and end inside that sequence
+ * (probe.py:1095-1106 cover_start / cover_end), and the sequence position of the seed hit that produced it
+ * (probe.py:1062 `i`); records come in no particular order.  This is what find_probe_covers_in_sequence(merge_overlapping=False)
+ * consumers (coverage_analysis.py:228-231, `sorted(set(...))` per probe and sequence) and the adapter
+ * filter's interval scheduling (adapter_filter.py:191-238, which also needs the order in which probes are
+ * first found) are built on.  *records is allocated by the library (cb_free_host), *n_records records. */
+int cb_coverage_records(cb_ctx *ctx, const cb_probes *probes, const cb_targets *targets,
+                        const cb_hyb_params *params, const int64_t *seed_off, const int32_t *seed_pos,
+                        int64_t *n_records, uint32_t **records, cb_stats *stats);
+void cb_free_host(void *p);
 void cb_cover_free(cb_cover *c);
 
 /* Number of merged (probe, genome, start, end) intervals held by a cover. */

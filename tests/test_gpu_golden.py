@@ -75,7 +75,7 @@ def test_find_probe_covers_in_sequence(ctx, ref_tests):
     n = 0
     for r in ref_tests['scan']:
         if not r['merge']:
-            continue          # merge_overlapping=False is only used by the adapter filter (out of scope)
+            continue          # merge_overlapping=False vectors: tests/test_gpu_f1.py (cb_coverage_records)
         group = cov.PackedGroup(ctx, r['probes'], [[r['seq']]])
         cover, st = cov.cover_with_seeds(ctx, group, r['seeds'], r['k'], r['m'], r['lcf'], r['island'], 0)
         pid, gen, s, e = ctx.cover_export(cover)
