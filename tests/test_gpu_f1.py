@@ -78,17 +78,16 @@ def test_adapter_filter_and_analyzer_against_the_reference():
     assert out['bad'] == {'adapter': [], 'analyzer': []}, out
 
 
-def test_unmerged_scan_records_match_reference_scans(ctx):
-    """find_probe_covers_in_sequence(merge_overlapping=False) vectors of the reference's test_probe.py:
-    sorted distinct ranges per probe (probe.py:1262-1270) from cb_coverage_records."""
+def test_scan_records_match_reference_scans(ctx):
+    """cb_coverage_records (the unmerged ranges of the scan) against every find_probe_covers_in_sequence vector
+    of the reference's test_probe.py: merged on the host the way probe.py:1262-1270 does for
+    merge_overlapping=True (interval.merge_overlapping) and as sorted distinct ranges for False."""
     import numpy as np
     from catch_b200 import coverage as cov
     from tests import golden_io
     ref = golden_io.load('reference_tests.json.gz')
     n = 0
     for r in ref['scan']:
-        if r['merge']:
-            continue
         group = cov.PackedGroup(ctx, r['probes'], [[r['seq']]])
         off = np.zeros(len(r['seeds']) + 1, dtype=np.int64)
         off[1:] = np.cumsum([len(x) for x in r['seeds']])
@@ -96,11 +95,22 @@ def test_unmerged_scan_records_match_reference_scans(ctx):
         pos = np.array(flat if flat else [0], dtype=np.int32)
         rec, _ = ctx.coverage_records(group.probes, group.targets, r['m'], r['lcf'], r['island'], r['k'], off, pos)
         group.free()
-        got = {}
+        per_probe = {}
         for p, q, s, e, h in sorted(set(map(tuple, rec.tolist()))):
-            assert q == 0
-            got.setdefault(r['probes'][p], set()).add((s, e))
-        got = {k: [list(x) for x in sorted(v)] for k, v in got.items()}
+            assert q == 0 and 0 <= h <= len(r['seq']) - r['k']
+            per_probe.setdefault(r['probes'][p], []).append([s, e])
+        got = {}
+        for k, ranges in per_probe.items():
+            ranges = sorted(map(list, set(map(tuple, ranges))))
+            if r['merge']:
+                merged = []
+                for s, e in ranges:
+                    if merged and s <= merged[-1][1]:
+                        merged[-1][1] = max(merged[-1][1], e)
+                    else:
+                        merged.append([s, e])
+                ranges = merged
+            got[k] = ranges
         assert got == r['out'], (r['probes'], r['seq'][:80])
         n += 1
-    assert n >= 1
+    assert n >= 100
