@@ -6,9 +6,9 @@
 //   utils/lsh.py:16-45     HammingDistanceFamily             -> hamming_signature_kernel
 //   utils/lsh.py:218-300   HashConcatenation, NearNeighborLookup.add -> bucket_kernel (hash-bucket CSR)
 //   utils/lsh.py:302-320   NearNeighborLookup.query + filter/near_duplicate_filter.py:107,148-157
-//                          (exact Hamming / Jaccard distance)  -> inside decide_kernel
+//                          (exact Hamming / Jaccard distance)  -> inside decide_probe
 //   filter/near_duplicate_filter.py:81-96  sequential greedy in priority order -> rounds of
-//                          group_min_kernel / decide_kernel / append_kernel
+//                          decide_rounds_kernel (persistent; all rounds of the fix point)
 //
 // The sequential loop of the reference keeps probe p iff no EARLIER-priority KEPT probe reports p
 // as a neighbour (same key in some table and exact distance <= threshold).  That is the
@@ -217,17 +217,6 @@ __global__ void bucket_kernel(const uint32_t *__restrict__ sig, int64_t n_probes
     }
 }
 
-// ---- K12 round, step 1: smallest undecided probe of every bucket
-__global__ void group_min_kernel(const uint8_t *__restrict__ state, const uint32_t *__restrict__ pg,
-                                 int64_t n_probes, int n_tables, uint32_t *__restrict__ grp_min)
-{
-    const int64_t n = n_probes * n_tables;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t p = i / n_tables;
-        if (state[p] == 0) atomicMin(&grp_min[pg[i]], (uint32_t)p);
-    }
-}
-
 struct DecideParams {
     int64_t n_probes;
     int n_tables, k_concat, family;      // family 0 = MinHash/Jaccard, 1 = Hamming
@@ -281,87 +270,148 @@ __device__ __forceinline__ bool is_near(const DecideParams &D, int64_t p, int64_
     return (double)mm <= D.dist_thres;
 }
 
-// ---- K11 + K12 round, step 2: one warp per undecided probe
+// ---- K11 + K12, one probe of one round, by one warp: 2 = dropped (a kept earlier bucket-mate is within the
+// exact distance), 3 = kept (every earlier bucket-mate is decided), 0 = still undecided
+__device__ __forceinline__ int decide_probe(const DecideParams &D, int64_t p, int lane, unsigned long long &dists)
+{
+    const int n_fn = D.n_tables * D.k_concat;
+    bool blocked = false, dropped = false;
+    for (int tb = 0; tb < D.n_tables && !dropped; tb += 32) {
+        const int t = tb + lane;
+        const bool have_t = t < D.n_tables;
+        uint32_t b = 0, j = 0, jn = 0;
+        if (have_t) {
+            b = D.pg[p * D.n_tables + t];
+            if (__ldcg(&D.grp_min[b]) < (uint32_t)p) blocked = true;
+            j = __ldcg(&D.checked[p * D.n_tables + t]);
+            jn = __ldcg(&D.inc_count[b]);
+        }
+        // walk the kept members of the probe's buckets, 32 tables abreast
+        while (!dropped) {
+            uint32_t q = 0xffffffffu;
+            bool cand = false;
+            if (have_t && j < jn) {
+                q = __ldcg(&D.inc_list[D.boff[b] + j]);
+                j++;
+                if (q < (uint32_t)p) {             // kept earlier; same key (not just same bucket)?
+                    cand = true;
+                    const uint32_t *kp = D.sig + p * n_fn + (int64_t)t * D.k_concat;
+                    const uint32_t *kq = D.sig + (int64_t)q * n_fn + (int64_t)t * D.k_concat;
+                    for (int c = 0; c < D.k_concat; c++) cand = cand && (kp[c] == kq[c]);
+                }
+            }
+            const unsigned more = __ballot_sync(0xffffffffu, have_t && j < jn);
+            unsigned cands = __ballot_sync(0xffffffffu, cand);
+            // the same q usually shows up in many tables at once: evaluate it once
+            const unsigned same = __match_any_sync(0xffffffffu, cand ? q : 0xffffffffu - lane);
+            if (cand && (__ffs(same) - 1) != lane) cand = false;
+            cands = __ballot_sync(0xffffffffu, cand);
+            while (cands && !dropped) {
+                const int src = __ffs(cands) - 1;
+                cands &= cands - 1;
+                const uint32_t qq = __shfl_sync(0xffffffffu, q, src);
+                dists++;
+                if (is_near(D, p, (int64_t)qq, lane)) dropped = true;
+            }
+            if (!more) break;
+        }
+        if (have_t) __stcg(&D.checked[p * D.n_tables + t], j);
+    }
+    blocked = __any_sync(0xffffffffu, blocked);
+    return dropped ? 2 : (blocked ? 0 : 3);
+}
+
+// The sequential keep/drop loop of filter/near_duplicate_filter.py:81-96 as rounds to its fix point, ALL rounds
+// in one persistent cooperative kernel.  A round only touches the probes that are still undecided (compact
+// list, rebuilt every round), so the cost follows the number of undecided probes, not rounds x probes:
+//   A  every undecided probe writes its index into grp_min of its buckets (atomicMin);
+//   B  one warp per undecided probe decides: dropped / kept / still undecided (-> next list);
+//   C  probes kept this round join the kept lists of their buckets; grp_min of the touched buckets is reset.
+struct RoundsCtl {
+    uint32_t *list[2];            // undecided probes, ping-pong
+    uint32_t *n_list;             // [2]
+    uint32_t *kept;               // probes kept in the current round
+    uint32_t *n_kept;
+    uint32_t *grp_min;
+    uint32_t *inc_count;
+    uint32_t *inc_list;
+    unsigned long long *barrier;
+    unsigned long long *rounds;
+};
+
+__device__ __forceinline__ void nd_grid_barrier(unsigned long long *counter, unsigned long long &target)
+{
+    __syncthreads();
+    target += gridDim.x;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1ull);
+        while (*(volatile unsigned long long *)counter < target) { }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(ND_THREADS)
-decide_kernel(const DecideParams D)
+decide_rounds_kernel(const DecideParams D, const RoundsCtl C)
 {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const int n_fn = D.n_tables * D.k_concat;
-    unsigned long long undecided = 0, dists = 0;
-    for (int64_t p = warp; p < D.n_probes; p += n_warps) {
-        if (D.state[p] != 0) continue;
-        bool blocked = false, dropped = false;
-        for (int tb = 0; tb < D.n_tables && !dropped; tb += 32) {
-            const int t = tb + lane;
-            const bool have_t = t < D.n_tables;
-            uint32_t b = 0, j = 0, jn = 0;
-            if (have_t) {
-                b = D.pg[p * D.n_tables + t];
-                if (D.grp_min[b] < (uint32_t)p) blocked = true;
-                j = D.checked[p * D.n_tables + t];
-                jn = D.inc_count[b];
-            }
-            // walk the kept members of the probe's buckets, 32 tables abreast
-            while (!dropped) {
-                uint32_t q = 0xffffffffu;
-                bool cand = false;
-                if (have_t && j < jn) {
-                    q = D.inc_list[D.boff[b] + j];
-                    j++;
-                    if (q < (uint32_t)p) {             // kept earlier; same key (not just same bucket)?
-                        cand = true;
-                        const uint32_t *kp = D.sig + p * n_fn + (int64_t)t * D.k_concat;
-                        const uint32_t *kq = D.sig + (int64_t)q * n_fn + (int64_t)t * D.k_concat;
-                        for (int c = 0; c < D.k_concat; c++) cand = cand && (kp[c] == kq[c]);
-                    }
-                }
-                const unsigned more = __ballot_sync(0xffffffffu, have_t && j < jn);
-                unsigned cands = __ballot_sync(0xffffffffu, cand);
-                // the same q usually shows up in many tables at once: evaluate it once
-                const unsigned same = __match_any_sync(0xffffffffu, cand ? q : 0xffffffffu - lane);
-                if (cand && (__ffs(same) - 1) != lane) cand = false;
-                cands = __ballot_sync(0xffffffffu, cand);
-                while (cands && !dropped) {
-                    const int src = __ffs(cands) - 1;
-                    cands &= cands - 1;
-                    const uint32_t qq = __shfl_sync(0xffffffffu, q, src);
-                    dists++;
-                    if (is_near(D, p, (int64_t)qq, lane)) dropped = true;
-                }
-                if (!more) break;
-            }
-            if (have_t) D.checked[p * D.n_tables + t] = j;
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long bar = 0, dists = 0, rounds = 0;
+    int cur = 0;
+    uint32_t n_cur = (uint32_t)D.n_probes;
+    for (;;) {
+        const uint32_t *list = C.list[cur];
+        // A: smallest undecided index of every bucket
+        if (gtid == 0) *C.n_kept = 0u;
+        for (int64_t i = warp; i < (int64_t)n_cur; i += n_warps) {
+            const uint32_t p = list[i];
+            for (int t = lane; t < D.n_tables; t += 32) atomicMin(&C.grp_min[D.pg[(int64_t)p * D.n_tables + t]], p);
         }
-        blocked = __any_sync(0xffffffffu, blocked);
-        if (lane == 0) {
-            if (dropped) D.state[p] = 2;
-            else if (!blocked) D.state[p] = 3;
-            else undecided++;
+        nd_grid_barrier(C.barrier, bar);
+        // B: decide
+        for (int64_t i = warp; i < (int64_t)n_cur; i += n_warps) {
+            const uint32_t p = list[i];
+            const int r = decide_probe(D, (int64_t)p, lane, dists);
+            if (lane == 0) {
+                if (r == 2) D.state[p] = 2;
+                else if (r == 3) C.kept[atomicAdd(C.n_kept, 1u)] = p;
+                else C.list[cur ^ 1][atomicAdd(&C.n_list[cur ^ 1], 1u)] = p;
+            }
         }
+        nd_grid_barrier(C.barrier, bar);
+        // C: kept probes join the kept lists of their buckets; grp_min entries used this round are reset
+        const uint32_t n_kept = __ldcg(C.n_kept);
+        for (int64_t i = warp; i < (int64_t)n_kept; i += n_warps) {
+            const uint32_t p = __ldcg(&C.kept[i]);
+            for (int t = lane; t < D.n_tables; t += 32) {
+                const uint32_t b = D.pg[(int64_t)p * D.n_tables + t];
+                const uint32_t slot = atomicAdd(&C.inc_count[b], 1u);
+                C.inc_list[D.boff[b] + slot] = p;
+            }
+            if (lane == 0) D.state[p] = 1;
+        }
+        for (int64_t i = warp; i < (int64_t)n_cur; i += n_warps) {
+            const uint32_t p = list[i];
+            for (int t = lane; t < D.n_tables; t += 32) C.grp_min[D.pg[(int64_t)p * D.n_tables + t]] = 0xffffffffu;
+        }
+        if (gtid == 0) C.n_list[cur] = 0u;
+        rounds++;
+        nd_grid_barrier(C.barrier, bar);
+        cur ^= 1;
+        n_cur = __ldcg(&C.n_list[cur]);
+        if (n_cur == 0u) break;
     }
-    if (lane == 0) {
-        if (undecided) atomicAdd(D.n_undecided, undecided);
-        if (dists) atomicAdd(D.n_dist, dists);
-    }
+    if (lane == 0 && dists) atomicAdd(D.n_dist, dists);
+    if (gtid == 0) *C.rounds = rounds;
 }
 
-// ---- K12 round, step 3: probes kept this round join the kept lists of their buckets
-__global__ void append_kernel(uint8_t *__restrict__ state, const uint32_t *__restrict__ pg, int64_t n_probes,
-                              int n_tables, const int64_t *__restrict__ boff, uint32_t *__restrict__ inc_count,
-                              uint32_t *__restrict__ inc_list)
+__global__ void iota_kernel(uint32_t *out, int64_t n)
 {
-    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_probes;
-         p += (int64_t)gridDim.x * blockDim.x) {
-        if (state[p] != 3) continue;
-        for (int t = 0; t < n_tables; t++) {
-            const uint32_t b = pg[p * n_tables + t];
-            const uint32_t slot = atomicAdd(&inc_count[b], 1u);
-            inc_list[boff[b] + slot] = (uint32_t)p;
-        }
-        state[p] = 1;
-    }
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (uint32_t)i;
 }
 
 __global__ void finish_kernel(const uint8_t *__restrict__ state, int64_t n, uint8_t *__restrict__ keep)
@@ -502,24 +552,41 @@ int neardup_run(cb_ctx *ctx, const uint8_t *d_ascii_in, const std::vector<int64_
     D.n_undecided = d_ctr.p;
     D.n_dist = d_ctr.p + 1;
 
-    // K12 rounds
+    // K12 rounds: one persistent cooperative kernel
     t_rounds.start();
-    int64_t rounds = 0;
-    unsigned long long h_ctr[2] = {0, 0};
-    for (;;) {
-        CB_CUDA(ctx, cudaMemsetAsync(d_grpmin.p, 0xff, sizeof(uint32_t) * (size_t)n_buckets, st));
-        CB_CUDA(ctx, cudaMemsetAsync(d_ctr.p, 0, sizeof(unsigned long long), st));
-        group_min_kernel<<<wide, ND_THREADS, 0, st>>>(d_state.p, d_pg.p, P, n_tables, d_grpmin.p);
-        decide_kernel<<<wide, ND_THREADS, 0, st>>>(D);
-        append_kernel<<<wide, ND_THREADS, 0, st>>>(d_state.p, d_pg.p, P, n_tables, d_boff.p, d_inccount.p, d_inclist.p);
-        ctx->launches += 3;
-        CB_CUDA(ctx, cudaGetLastError());
-        CB_CUDA(ctx, cudaMemcpyAsync(h_ctr, d_ctr.p, sizeof h_ctr, cudaMemcpyDeviceToHost, st));
-        CB_CUDA(ctx, cudaStreamSynchronize(st));
-        rounds++;
-        if (h_ctr[0] == 0) break;
-        if (rounds > P + 2) return cb_fail(ctx, CB_ERR_STATE, "near-duplicate rounds did not converge");
-    }
+    DevBuf<uint32_t> d_lists, d_small;
+    DevBuf<unsigned long long> d_bar;
+    CB_CUDA(ctx, d_lists.alloc((size_t)P * 3));                 // undecided (ping-pong) + kept-this-round
+    CB_CUDA(ctx, d_small.alloc(8));
+    CB_CUDA(ctx, d_bar.alloc(2));
+    CB_CUDA(ctx, cudaMemsetAsync(d_small.p, 0, sizeof(uint32_t) * 8, st));
+    CB_CUDA(ctx, cudaMemsetAsync(d_bar.p, 0, sizeof(unsigned long long) * 2, st));
+    CB_CUDA(ctx, cudaMemsetAsync(d_grpmin.p, 0xff, sizeof(uint32_t) * (size_t)n_buckets, st));
+    iota_kernel<<<wide, ND_THREADS, 0, st>>>(d_lists.p, P);
+    ctx->launches++;
+    RoundsCtl C;
+    C.list[0] = d_lists.p;
+    C.list[1] = d_lists.p + P;
+    C.kept = d_lists.p + 2 * P;
+    C.n_list = d_small.p;
+    C.n_kept = d_small.p + 2;
+    C.grp_min = d_grpmin.p;
+    C.inc_count = d_inccount.p;
+    C.inc_list = d_inclist.p;
+    C.barrier = d_bar.p;
+    C.rounds = d_bar.p + 1;
+    int per_sm = 0;
+    CB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decide_rounds_kernel, ND_THREADS, 0));
+    if (per_sm < 1) return cb_fail(ctx, CB_ERR_CUDA, "near-duplicate kernel does not fit on an SM");
+    if (per_sm > 4) per_sm = 4;
+    void *args[] = {(void *)&D, (void *)&C};
+    CB_CUDA(ctx, cudaLaunchCooperativeKernel((void *)decide_rounds_kernel, dim3(per_sm * ctx->sm_count), dim3(ND_THREADS),
+                                             args, 0, st));
+    ctx->launches++;
+    unsigned long long h_ctr[2] = {0, 0}, h_rounds = 0;
+    CB_CUDA(ctx, cudaMemcpyAsync(h_ctr, d_ctr.p, sizeof h_ctr, cudaMemcpyDeviceToHost, st));
+    CB_CUDA(ctx, cudaMemcpyAsync(&h_rounds, d_bar.p + 1, sizeof h_rounds, cudaMemcpyDeviceToHost, st));
+    const int64_t rounds = 0;
     finish_kernel<<<wide, ND_THREADS, 0, st>>>(d_state.p, P, d_keep.p);
     ctx->launches++;
     t_rounds.stop();
@@ -530,7 +597,7 @@ int neardup_run(cb_ctx *ctx, const uint8_t *d_ascii_in, const std::vector<int64_
         stats->ms_seed_index += t_sig.ms();      // signatures + buckets
         stats->ms_greedy += t_rounds.ms();       // decision rounds
         stats->ms_total += t_all.ms();
-        stats->n_picks = rounds;
+        stats->n_picks = (int64_t)h_rounds + rounds;
         stats->n_candidate_hits = (int64_t)h_ctr[1];   // exact distance evaluations
         stats->n_kernel_launches = ctx->launches;
     }

@@ -185,25 +185,29 @@ class SetCoverFilter(BaseFilter):
         return p
 
     def _tolerant_bp_covered(self, ctx, probe_strs, plan, sequences):
-        """Sum over `sequences` and their reverse complements of the bp each probe covers under
-        the tolerant parameters (set_cover_filter.py:472-529): ranges merged per sequence, no
-        cover extension.  Each sequence and each reverse complement is packed as its own
-        'genome' so merging stays per sequence."""
-        seqs = []
-        for s in sequences:
-            seqs.append([s])
-            seqs.append([_reverse_complement(s)])
-        group = cov.PackedGroup(ctx, probe_strs, seqs)
-        try:
-            cover, st = cov.compute_cover(ctx, group, plan, self.mismatches_tolerant,
-                                          self.lcf_thres_tolerant, self.island_of_exact_match_tolerant, 0)
-            pid, _, start, end = ctx.cover_export(cover)
-            cover.free()
-        finally:
-            group.free()
+        """Sum over `sequences` (any iterable, consumed as a stream) and their reverse complements of the bp
+        each probe covers under the tolerant parameters (set_cover_filter.py:472-529): ranges merged per
+        sequence, no cover extension.  Each sequence and each reverse complement is packed as its own
+        'genome' so merging stays per sequence.  The sequences go through the device in batches of bounded
+        size (a host genome given to --avoid-genomes is gigabases long; the reference, too, looks at one
+        sequence at a time, :700-707), so neither the 2^32-bit universe limit nor memory depends on the size
+        of the FASTA."""
         bp = np.zeros(len(probe_strs), dtype=np.int64)
-        if len(pid):
-            np.add.at(bp, pid, end - start)
+        for batch in cov.sequence_batches(sequences, max_bases=1 << 29):
+            seqs = []
+            for s in batch:
+                seqs.append([s])
+                seqs.append([_reverse_complement(s)])
+            group = cov.PackedGroup(ctx, probe_strs, seqs)
+            try:
+                cover, st = cov.compute_cover(ctx, group, plan, self.mismatches_tolerant,
+                                              self.lcf_thres_tolerant, self.island_of_exact_match_tolerant, 0)
+                pid, _, start, end = ctx.cover_export(cover)
+                cover.free()
+            finally:
+                group.free()
+            if len(pid):
+                np.add.at(bp, pid, end - start)
         return bp
 
     def _needs_ranks(self):
@@ -218,14 +222,12 @@ class SetCoverFilter(BaseFilter):
         if self.identify:
             hits = np.zeros(n, dtype=np.int64)
             for genomes in target_genomes_grouped:
-                seqs = [s for g in genomes for s in g.seqs]
-                bp = self._tolerant_bp_covered(ctx, probe_strs, plan, seqs)
+                bp = self._tolerant_bp_covered(ctx, probe_strs, plan, (s for g in genomes for s in g.seqs))
                 hits += (bp >= 1)
             second = hits
         avoided_bp = np.zeros(n, dtype=np.int64)
         for path in self.avoided_genomes:
-            seqs = list(seq_io.iterate_fasta(path))
-            avoided_bp += self._tolerant_bp_covered(ctx, probe_strs, plan, seqs)
+            avoided_bp += self._tolerant_bp_covered(ctx, probe_strs, plan, seq_io.iterate_fasta(path))
         if plan.rep is not None:
             # dicts keyed by sequence: all duplicates share the values of their representative
             rep = np.asarray(plan.rep)
