@@ -41,6 +41,16 @@ def gather_staged(ctx, slot, items):
     return addr, np.frombuffer(lens, dtype=np.int32, count=n), total
 
 
+def offsets_from_lengths(lens):
+    """int64 offsets [n + 1] of sequences of the given lengths laid back to back."""
+    n = len(lens)
+    if n and int(lens[0]) > 0 and bool((lens == lens[0]).all()):       # candidate probes: one length
+        return np.arange(n + 1, dtype=np.int64) * int(lens[0])
+    off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(lens, dtype=np.int64, out=off[1:])
+    return off
+
+
 def probe_lengths(probes):
     """int32 lengths of the sequences of `probes` (str or objects with .seq_str), nothing copied."""
     n = len(probes)

@@ -28,6 +28,23 @@ def _num_tables(P1, k, reporting_prob):
     return int(math.ceil(math.log(1.0 - reporting_prob, 1.0 - math.pow(P1, k))))
 
 
+def set_ordered(probes):
+    """list(set built by .add() in list order) for DISTINCT probes, without a Python-level __hash__ / __eq__ call per
+    element: a set of the sequences (str: hashed and compared in C) filled in the same order has the same table
+    layout, hence the same iteration order, as the set of Probe objects -- a Probe hashes as its sequence
+    (probe.py:324-329) and set insertion depends on nothing but the hashes and the insertion order."""
+    strs = [p.seq_str for p in probes]
+    by_str = dict(zip(strs, probes))
+    if len(by_str) != len(strs):                      # equal sequences: keep the plain construction
+        out = set()
+        for p in probes:
+            out.add(p)
+        return list(out)
+    order = set()
+    order.update(strs)
+    return [by_str[s] for s in order]
+
+
 class NearDuplicateFilter(BaseFilter):
     def __init__(self, k, reporting_prob=0.80):
         self.k = k
@@ -61,15 +78,11 @@ class NearDuplicateFilter(BaseFilter):
         if gathered is None:
             gathered = cov.gather_probes(input)
         raw, lens = gathered[0], gathered[1]
-        off = np.zeros(len(input) + 1, dtype=np.int64)
-        np.cumsum(lens, out=off[1:])
+        off = cov.offsets_from_lengths(lens)
         kept, n_distinct, st = self._draw_and_run(ctx, raw, off, lens)
         self.last_stats = st.as_dict()
         self.last_stats['n_distinct'] = n_distinct
-        to_include = set()
-        for i in kept.tolist():
-            to_include.add(input[i])
-        return list(to_include)                                   # :103
+        return set_ordered([input[i] for i in kept.tolist()])     # :96-103: to_include.add(p) ..., list(to_include)
 
 
 class NearDuplicateFilterWithHammingDistance(NearDuplicateFilter):

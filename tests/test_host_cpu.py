@@ -252,3 +252,23 @@ def test_set_cover_drop_in_validates_like_the_reference():
     index_of = {v: i for i, v in enumerate(['a', 'b', 'c', 'd', 'e'])}
     assert sc._as_intervals({'a', 'b', 'd'}, False, index_of) == [(0, 2), (3, 4)]
     assert sc._as_intervals((5, 9), True, None) == [(5, 9)]
+
+
+def test_set_ordered_equals_set_of_probes():
+    """near_duplicate_filter.set_ordered (set of sequences, C-level hashing) iterates in the order of the
+    reference's set of Probe objects built by .add() in the same order (near_duplicate_filter.py:96-103)."""
+    import random
+    from catch_b200 import probe
+    from catch_b200.filter.near_duplicate_filter import set_ordered
+    rng = random.Random(4)
+    for n in (0, 1, 5, 8, 9, 100, 5000, 70000):
+        probes = [probe.Probe.from_str(''.join(rng.choice('ACGT') for _ in range(rng.choice([20, 40, 100]))))
+                  for _ in range(n)]
+        probes = list(dict.fromkeys(probes))
+        want = set()
+        for p in probes:
+            want.add(p)
+        got = set_ordered(probes)
+        assert len(got) == len(probes) and all(a is b for a, b in zip(got, list(want)))
+    dup = [probe.Probe.from_str('ACGT'), probe.Probe.from_str('ACGT'), probe.Probe.from_str('TTTT')]
+    assert [p.seq_str for p in set_ordered(dup)] == [p.seq_str for p in list(set(dup))]
