@@ -76,42 +76,51 @@ def gather_probes(probes):
     return data, lens
 
 
+def stage_targets(ctx, slot, genomes):
+    """Gather the sequences of a grouping's genomes into staging buffer `slot` (or a bytes object when the C
+    helper is not built) and derive the tables cb_upload_group needs.  No library call is made when the
+    buffer is already large enough, so a helper thread may run this while the context is busy."""
+    # sequences of all genomes in order, and the genome each belongs to (no per-sequence Python loop:
+    # an influenza-shaped grouping has 40 000 single-sequence genomes)
+    seq_lists = [g.seqs if hasattr(g, 'seqs') else g for g in genomes]
+    n_genomes = len(genomes)
+    counts = np.fromiter(map(len, seq_lists), dtype=np.int64, count=n_genomes)
+    seqs = list(itertools.chain.from_iterable(seq_lists))
+    sg = np.repeat(np.arange(n_genomes, dtype=np.int32), counts) if len(seqs) else np.zeros(1, np.int32)
+    staged_t = gather_staged(ctx, slot, seqs)
+    if staged_t is not None:
+        t_raw, t_lens, t_total = staged_t
+        seq_off = np.zeros(len(seqs) + 1, dtype=np.int64)
+        np.cumsum(t_lens, dtype=np.int64, out=seq_off[1:])
+    else:
+        _, seq_off, t_raw = _concat_ascii(seqs)
+        t_total = len(t_raw)
+    return dict(raw=t_raw, seq_off=seq_off, seq_genome=sg, n_genomes=n_genomes, total=int(t_total))
+
+
 class PackedGroup:
     """Probes + targets of one grouping, resident on the device (one cb_upload_group call: both
     host->device copies, the code table derived on the device, both packings)."""
 
-    def __init__(self, ctx, probe_strs, genomes, gathered=None):
+    def __init__(self, ctx, probe_strs, genomes, gathered=None, targets_staged=None):
         """`probe_strs`: list of str (or of objects with .seq_str).  `gathered`: the result of
-        gather_probes() on it, if the caller already has that."""
+        gather_probes() / gather_staged() on it, `targets_staged`: the result of stage_targets() on
+        `genomes`, if the caller already has them (prefetched while the previous grouping was on the device)."""
         self.ctx = ctx
         self.n_probes = len(probe_strs)
-        # sequences of all genomes in order, and the genome each belongs to (no per-sequence Python loop:
-        # an influenza-shaped grouping has 40 000 single-sequence genomes)
-        seq_lists = [g.seqs if hasattr(g, 'seqs') else g for g in genomes]
-        self.n_genomes = len(genomes)
-        counts = np.fromiter(map(len, seq_lists), dtype=np.int64, count=self.n_genomes)
-        seqs = list(itertools.chain.from_iterable(seq_lists))
-        sg = np.repeat(np.arange(self.n_genomes, dtype=np.int32), counts) if len(seqs) else np.zeros(1, np.int32)
-        staged_t = gather_staged(ctx, 1, seqs)
-        if staged_t is not None:
-            t_raw, t_lens, t_total = staged_t
-            seq_off = np.zeros(len(seqs) + 1, dtype=np.int64)
-            np.cumsum(t_lens, out=seq_off[1:])
-        else:
-            _, seq_off, t_raw = _concat_ascii(seqs)
-            t_total = len(t_raw)
-        self.target_bases = int(seq_off[-1])
+        ts = targets_staged if targets_staged is not None else stage_targets(ctx, 1, genomes)
+        self.n_genomes = ts['n_genomes']
+        self.target_bases = int(ts['seq_off'][-1])
         if gathered is None:
             gathered = gather_staged(ctx, 0, probe_strs)
             if gathered is None:
                 gathered = gather_probes(probe_strs)
         p_raw, lens = gathered[0], gathered[1]
-        off = np.zeros(self.n_probes + 1, dtype=np.int64)
-        np.cumsum(lens, out=off[1:])
+        off = offsets_from_lengths(lens)
         self.probes, self.targets, self.probe_len, self.bits, st = ctx.upload_group(
-            p_raw, self.n_probes, t_raw, seq_off, sg, self.n_genomes, probe_off=off)
+            p_raw, self.n_probes, ts['raw'], ts['seq_off'], ts['seq_genome'], self.n_genomes, probe_off=off)
         self.st_targets, self.st_probes = st, _lib.Stats()
-        self.h2d_bytes = int(off[-1]) + int(t_total)
+        self.h2d_bytes = int(off[-1]) + ts['total']
 
     @property
     def probe_off(self):

@@ -126,6 +126,62 @@ class _DrawChain:
             parallel.rng_broadcast(self.owner[-1])            # everyone ends where a single process would
 
 
+class _Prefetch:
+    """Host work of the NEXT grouping while the current one is on the device.  A helper thread gathers the
+    probe sequences and the target sequences of the groupings this process owns, in order, into a second
+    pair of page-locked staging buffers (cb_host_buffer slots 2k and 2k+1 of pair k); the filter loop picks
+    each grouping up when it gets there.  The device calls of the loop release the GIL (ctypes), so the
+    gather of grouping g+1 overlaps the scan and set cover of g.  A pair is reused only after the upload
+    that reads it has returned (release()).  The staging buffers are sized up front on the calling thread,
+    so the helper never calls into the library."""
+
+    def __init__(self, ctx, groups):
+        """groups: list of (group index, probe list, genomes) in processing order."""
+        import queue
+        self.ctx, self.groups = ctx, groups
+        p_max = t_max = 0
+        for _g, probes, genomes in groups:
+            if len(probes):
+                p_max = max(p_max, int(cov.probe_lengths(probes).sum(dtype=np.int64)))
+            t_max = max(t_max, sum(g.size() for g in genomes))
+        for pair in (0, 1):
+            ctx.host_buffer(2 * pair, p_max + 64)
+            ctx.host_buffer(2 * pair + 1, t_max + 64)
+        self.free = [threading.Semaphore(1), threading.Semaphore(1)]
+        self.q = queue.Queue()
+        self.stop = False
+        self.thread = threading.Thread(target=self._run, name='cb-prefetch', daemon=True)
+        self.thread.start()
+
+    def _run(self):
+        for k, (g, probes, genomes) in enumerate(self.groups):
+            self.free[k % 2].acquire()
+            if self.stop:
+                return
+            try:
+                gathered = cov.gather_staged(self.ctx, 2 * (k % 2), probes) if len(probes) else None
+                staged = cov.stage_targets(self.ctx, 2 * (k % 2) + 1, genomes) if len(probes) else None
+                self.q.put((g, gathered, staged, None))
+            except BaseException as e:          # noqa: BLE001 -- re-raised by the consumer
+                self.q.put((g, None, None, e))
+
+    def get(self, g):
+        got, gathered, staged, err = self.q.get()
+        assert got == g
+        if err is not None:
+            raise err
+        return gathered, staged
+
+    def release(self, k):
+        self.free[k % 2].release()
+
+    def close(self):
+        self.stop = True
+        for s in self.free:
+            s.release()
+        self.thread.join()
+
+
 class SetCoverFilter(BaseFilter):
     def __init__(self, mismatches, lcf_thres, island_of_exact_match=0, mismatches_tolerant=None,
                  lcf_thres_tolerant=None, island_of_exact_match_tolerant=None,
@@ -258,22 +314,38 @@ class SetCoverFilter(BaseFilter):
         local = {}
         chain = _DrawChain(self, input, owner, rank) if sharded else None
         failure = None
-        for group_i, (possible_probes, target_genomes) in enumerate(zip(input, target_genomes_grouped)):
-            # The seed draws consume numpy's global RNG per grouping, in grouping order
-            # (set_cover_filter.py:824-827).  A sharded run gets them from the draw chain (every
-            # grouping sees the stream of a single-process run, a rank only touches the groupings it
-            # owns); a single process draws in _filter_one_group, in the background of the upload.
-            if sharded and owner[group_i] != rank:
-                continue
-            if failure is not None:
-                continue                     # keep taking part in the collectives below, then raise
-            try:
-                local[group_i] = self._filter_one_group(group_i, len(input), possible_probes, target_genomes,
-                                                        target_genomes_grouped, chain)
-            except Exception as e:
-                if not sharded:
-                    raise
-                failure = e
+        mine = [g for g in range(len(input)) if owner[g] == rank]
+        prefetch = None
+        if len(mine) >= 2 and cov._fastpack is not None and hasattr(self._context(), 'host_buffer') and \
+                os.environ.get('CB_PREFETCH', '1') != '0':
+            as_lists = {g: (input[g] if isinstance(input[g], (list, tuple)) else list(input[g])) for g in mine}
+            prefetch = _Prefetch(self._context(), [(g, as_lists[g], target_genomes_grouped[g]) for g in mine])
+        try:
+            for k, group_i in enumerate(mine):
+                # The seed draws consume numpy's global RNG per grouping, in grouping order
+                # (set_cover_filter.py:824-827).  A sharded run gets them from the draw chain (every
+                # grouping sees the stream of a single-process run, a rank only touches the groupings it
+                # owns); a single process draws in _filter_one_group, in the background of the upload.
+                possible_probes = as_lists[group_i] if prefetch is not None else input[group_i]
+                if failure is not None:
+                    if prefetch is not None:
+                        prefetch.get(group_i)
+                        prefetch.release(k)
+                    continue                     # keep taking part in the collectives below, then raise
+                try:
+                    pre = None
+                    if prefetch is not None:
+                        pre = prefetch.get(group_i) + (lambda k=k: prefetch.release(k),)
+                    local[group_i] = self._filter_one_group(group_i, len(input), possible_probes,
+                                                            target_genomes_grouped[group_i], target_genomes_grouped,
+                                                            chain, pre)
+                except Exception as e:
+                    if not sharded:
+                        raise
+                    failure = e
+        finally:
+            if prefetch is not None:
+                prefetch.close()
         if sharded:
             chain.finish()
         chosen_per_group = parallel.exchange_group_results(local, owner, rank, failure) if sharded else \
@@ -285,10 +357,13 @@ class SetCoverFilter(BaseFilter):
             selected.append([possible_probes[i] for i in chosen])
         return selected
 
-    def _filter_one_group(self, group_i, n_groups, possible_probes, target_genomes, target_genomes_grouped, chain):
+    def _filter_one_group(self, group_i, n_groups, possible_probes, target_genomes, target_genomes_grouped, chain,
+                          pre=None):
         """One grouping this process owns: gather, upload, seed plan, both stages.  `chain` is the draw
         chain of a group-sharded run (None in a single process, which draws here in the background of
-        the upload).  Returns the indices of the selected probes in the reference's output order."""
+        the upload).  `pre`: (gathered probes, staged targets, release callback) when the prefetch thread
+        already gathered this grouping.  Returns the indices of the selected probes in the reference's
+        output order."""
         sharded = chain is not None
         if not isinstance(possible_probes, (list, tuple)):
             possible_probes = list(possible_probes)
@@ -306,53 +381,67 @@ class SetCoverFilter(BaseFilter):
             t_mark = now
         drawn = drawn_tol = None
         guess = None
-        if sharded:
-            drawn, drawn_tol = chain.get(group_i)
-        elif n_probes:
-            # The seed draw needs only the probe lengths and runs on the library's worker thread
-            # while the sequences are gathered, copied to the device and packed.  It is started
-            # on the guess that all probes are as long as the first (candidate probes are);
-            # if the gathered lengths say otherwise the guess is dropped -- a background draw
-            # only touches numpy's RNG state when it is accepted -- and the draw is redone.
-            guess = len(possible_probes[0].seq_str)
-            try:
-                drawn = cov.draw_seeds(np.full(n_probes, guess, dtype=np.int32), self.mismatches,
-                                       self.lcf_thres, self.kmer_probe_map_k, background=True)
-            except ValueError:          # e.g. k longer than the first probe: decided on the real lengths
-                drawn = None
-        if n_probes:
-            # sequences of the whole list in one buffer (straight into page-locked staging memory
-            # when this rank is going to upload them)
-            try:
-                gathered = cov.gather_staged(self._context(), 0, possible_probes)
-                if gathered is None:
-                    gathered = cov.gather_probes(possible_probes)
-            except BaseException:
-                if drawn is not None:
-                    cov.cancel_draw(drawn)
-                raise
-            lengths = gathered[1]
-            if not sharded and (drawn is None or not bool(np.all(lengths == guess))):
-                if drawn is not None:
-                    cov.cancel_draw(drawn)
-                drawn = cov.draw_seeds(lengths, self.mismatches, self.lcf_thres, self.kmer_probe_map_k,
+        gathered = staged = release = None
+        if pre is not None:
+            gathered, staged, release = pre
+        try:
+            if sharded:
+                drawn, drawn_tol = chain.get(group_i)
+            elif n_probes and gathered is not None:
+                # prefetched: the lengths are known, the draw runs on the library's worker thread during the upload
+                drawn = cov.draw_seeds(gathered[1], self.mismatches, self.lcf_thres, self.kmer_probe_map_k,
                                        background=True)
-            mark('gather')
-        if n_probes:
-            # The tolerant draw (ranks) continues the same stream, so it follows once the first
-            # has finished.
-            try:
-                group = cov.PackedGroup(self._context(), possible_probes, target_genomes, gathered=gathered)
-                mark('pack_and_upload')
-                dups = self._context().probes_have_duplicates(group.probes)
-                mark('duplicate_check')
-            finally:
-                if not sharded:
-                    drawn = cov.finish_draw(drawn)
-            if self._needs_ranks() and not sharded:
-                drawn_tol = cov.draw_seeds(lengths, self.mismatches_tolerant, self.lcf_thres_tolerant,
-                                           self.kmer_probe_map_k)
-            mark('seed_draw_wait')
+            elif n_probes:
+                # The seed draw needs only the probe lengths and runs on the library's worker thread
+                # while the sequences are gathered, copied to the device and packed.  It is started
+                # on the guess that all probes are as long as the first (candidate probes are);
+                # if the gathered lengths say otherwise the guess is dropped -- a background draw
+                # only touches numpy's RNG state when it is accepted -- and the draw is redone.
+                guess = len(possible_probes[0].seq_str)
+                try:
+                    drawn = cov.draw_seeds(np.full(n_probes, guess, dtype=np.int32), self.mismatches,
+                                           self.lcf_thres, self.kmer_probe_map_k, background=True)
+                except ValueError:          # e.g. k longer than the first probe: decided on the real lengths
+                    drawn = None
+            if n_probes:
+                if gathered is None:
+                    # sequences of the whole list in one buffer (straight into page-locked staging memory
+                    # when this rank is going to upload them)
+                    try:
+                        gathered = cov.gather_staged(self._context(), 0, possible_probes)
+                        if gathered is None:
+                            gathered = cov.gather_probes(possible_probes)
+                    except BaseException:
+                        if drawn is not None:
+                            cov.cancel_draw(drawn)
+                        raise
+                    lengths = gathered[1]
+                    if not sharded and (drawn is None or not bool(np.all(lengths == guess))):
+                        if drawn is not None:
+                            cov.cancel_draw(drawn)
+                        drawn = cov.draw_seeds(lengths, self.mismatches, self.lcf_thres, self.kmer_probe_map_k,
+                                               background=True)
+                lengths = gathered[1]
+                mark('gather')
+            if n_probes:
+                # The tolerant draw (ranks) continues the same stream, so it follows once the first
+                # has finished.
+                try:
+                    group = cov.PackedGroup(self._context(), possible_probes, target_genomes, gathered=gathered,
+                                            targets_staged=staged)
+                    mark('pack_and_upload')
+                    dups = self._context().probes_have_duplicates(group.probes)
+                    mark('duplicate_check')
+                finally:
+                    if not sharded:
+                        drawn = cov.finish_draw(drawn)
+                if self._needs_ranks() and not sharded:
+                    drawn_tol = cov.draw_seeds(lengths, self.mismatches_tolerant, self.lcf_thres_tolerant,
+                                               self.kmer_probe_map_k)
+                mark('seed_draw_wait')
+        finally:
+            if release is not None:
+                release()                        # the staging pair may take the next grouping
         plan = plan_tol = None
         if n_probes:
             plan = cov.SeedPlan(probe_strs, self.mismatches, self.lcf_thres, self.kmer_probe_map_k,

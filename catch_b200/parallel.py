@@ -42,29 +42,46 @@ def _dist():
 
 
 def exchange_group_results(local, owner, rank, failure=None):
-    """local: {group index: result} for the groupings this rank owns.  Returns the list of all
-    results in grouping order on every rank.  `failure`: the exception that stopped this rank, if any;
-    it is exchanged with the results so that EVERY rank raises instead of some of them waiting for
-    ever in a collective."""
+    """local: {group index: list of selected indices} for the groupings this rank owns.  Returns the list of all
+    results in grouping order on every rank.  Two fixed-shape all-reduces over the control backend (gloo,
+    CPU tensors): the lengths of every grouping's result plus one failure slot per rank, then one flat
+    index tensor that each rank fills in at its groupings' offsets -- no pickling, no per-object
+    collectives.  `failure`: the exception that stopped this rank, if any; its presence is exchanged
+    with the lengths so that EVERY rank raises instead of some of them waiting for ever in a collective."""
     n = len(owner)
     dist = _dist()
     if dist is None or dist.get_world_size() == 1:
         if failure is not None:
             raise failure
         return [local[i] for i in range(n)]
-    gathered = [None] * dist.get_world_size()
-    dist.all_gather_object(gathered, (local, None if failure is None else repr(failure)))
+    torch = sys.modules['torch']
+    world_size = dist.get_world_size()
+    head = torch.zeros(n + world_size, dtype=torch.int64)
+    for i, res in local.items():
+        head[i] = len(res) + 1                       # +1: "computed", so that an empty result is told from a missing one
+    if failure is not None:
+        head[n + rank] = 1
+    dist.all_reduce(head)
+    failed = [r for r in range(world_size) if int(head[n + r])]
     if failure is not None:
         raise failure
-    merged = {}
-    for r, (part, err) in enumerate(gathered):
-        if err is not None:
-            raise RuntimeError("rank %d failed: %s" % (r, err))
-        merged.update(part)
-    missing = [i for i in range(n) if i not in merged]
+    if failed:
+        raise RuntimeError("rank %d failed: see that rank's log for the exception" % failed[0])
+    counts = head[:n].tolist()
+    missing = [i for i in range(n) if counts[i] == 0]
     if missing:
         raise RuntimeError("groupings %s were not computed by any rank" % missing)
-    return [merged[i] for i in range(n)]
+    lens = [c - 1 for c in counts]
+    offs = [0] * (n + 1)
+    for i in range(n):
+        offs[i + 1] = offs[i] + lens[i]
+    flat = torch.zeros(max(offs[n], 1), dtype=torch.int64)
+    for i, res in local.items():
+        if lens[i]:
+            flat[offs[i]:offs[i + 1]] = torch.as_tensor(list(res), dtype=torch.int64)
+    dist.all_reduce(flat)
+    out = flat.tolist()
+    return [out[offs[i]:offs[i + 1]] for i in range(n)]
 
 
 # ---- numpy's global RNG state as a token passed along the groupings ------------------------------

@@ -47,7 +47,7 @@ def _worker(rank, world_size, port, out_path, fail_group=None):
     from catch_b200 import coverage as cov
 
     class FakeGroup:
-        def __init__(self, ctx, probe_strs, genomes, gathered=None):
+        def __init__(self, ctx, probe_strs, genomes, gathered=None, targets_staged=None):
             self.probe_len = np.array([len(s) for s in probe_strs], dtype=np.int32)
             self.probes = None
 
