@@ -4,8 +4,11 @@ import itertools
 
 import numpy as np
 
+import ctypes
+
 from catch_b200 import _lib
 from catch_b200 import probe as probe_mod
+from catch_b200.probe_batch import ProbeBatch
 
 try:                                    # host-side glue built next to libcatchb200.so (csrc/fastpack.c)
     from catch_b200 import _fastpack
@@ -30,6 +33,14 @@ def gather_staged(ctx, slot, items):
     """Gather the sequences of `items` (str or objects with .seq_str) straight into the context's
     page-locked staging buffer `slot`.  Returns (address, int32 lengths, total bytes), or None when
     the C helper is not built (callers then use gather_probes)."""
+    if isinstance(items, ProbeBatch):             # already one buffer: a single copy into the staging memory
+        if not hasattr(ctx, 'host_buffer'):
+            return None
+        total = int(items.data.size)
+        addr, cap = ctx.host_buffer(slot, total)
+        if total:
+            ctypes.memmove(addr, items.data.ctypes.data, total)
+        return addr, items.lengths(), total
     if _fastpack is None or not hasattr(ctx, 'host_buffer'):
         return None
     n = len(items)
@@ -53,6 +64,8 @@ def offsets_from_lengths(lens):
 
 def probe_lengths(probes):
     """int32 lengths of the sequences of `probes` (str or objects with .seq_str), nothing copied."""
+    if isinstance(probes, ProbeBatch):
+        return probes.lengths()
     n = len(probes)
     if _fastpack is not None:
         _, lens = _fastpack.lengths(probes, 'seq_str')
@@ -63,6 +76,8 @@ def probe_lengths(probes):
 def gather_probes(probes):
     """(bytes of all sequences back to back, int32 lengths) for a list of Probe objects (or str).
     One C pass over the list when the _fastpack helper is built."""
+    if isinstance(probes, ProbeBatch):
+        return probes.data.tobytes(), probes.lengths()
     n = len(probes)
     if _fastpack is not None:
         data, lens = _fastpack.gather(probes, 'seq_str')

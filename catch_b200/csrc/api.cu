@@ -207,7 +207,7 @@ void cb_destroy(cb_ctx *ctx)
     cb_comm_destroy(ctx);
     cb_exchange_alloc(ctx, 0);
     if (ctx->flush_buf) cudaFree(ctx->flush_buf);
-    for (int i = 0; i < 4; i++)
+    for (int i = 0; i < 6; i++)
         if (ctx->pinned[i]) cudaFreeHost(ctx->pinned[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -217,7 +217,7 @@ const char *cb_last_error(cb_ctx *ctx) { return ctx ? ctx->err.c_str() : "null c
 
 int cb_host_buffer(cb_ctx *ctx, int32_t slot, int64_t bytes, void **out)
 {
-    if (!ctx || !out || slot < 0 || slot > 3 || bytes < 0) return cb_fail(ctx, CB_ERR_ARG, "bad argument");
+    if (!ctx || !out || slot < 0 || slot > 5 || bytes < 0) return cb_fail(ctx, CB_ERR_ARG, "bad argument");
     CB_CUDA(ctx, cudaSetDevice(ctx->device));
     if ((size_t)bytes > ctx->pinned_bytes[slot]) {
         // the previous buffer may still feed an asynchronous copy

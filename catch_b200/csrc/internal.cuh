@@ -36,8 +36,8 @@ struct cb_ctx {
     int64_t launches = 0;         // kernels launched since the counter was last reset
     void *flush_buf = nullptr;    // cb_flush_l2 scratch
     unsigned flush_val = 0;
-    void *pinned[4] = {nullptr, nullptr, nullptr, nullptr};   // cb_host_buffer staging (page-locked), grown on demand
-    size_t pinned_bytes[4] = {0, 0, 0, 0};
+    void *pinned[6] = {};         // cb_host_buffer staging (page-locked), grown on demand
+    size_t pinned_bytes[6] = {};
     void *comm = nullptr;         // ncclComm_t once cb_comm_init has run
     int rank = 0, n_ranks = 1;
     // exchange area of the sharded set cover (cb_exchange_*): this context's own area and the areas of

@@ -10,6 +10,7 @@ import numpy as np
 from catch_b200 import _lib
 from catch_b200 import coverage as cov
 from catch_b200.filter.base_filter import BaseFilter
+from catch_b200.probe_batch import ProbeBatch
 
 
 class DuplicateFilter(BaseFilter):
@@ -23,16 +24,17 @@ class DuplicateFilter(BaseFilter):
         return self._ctx
 
     def _filter(self, input):
-        if not isinstance(input, (list, tuple)):
+        if not isinstance(input, (list, tuple, ProbeBatch)):
             input = list(input)
-        if not input:
+        if not len(input):
             return []
         ctx = self._context()
         gathered = cov.gather_staged(ctx, 0, input)
         if gathered is None:
             gathered = cov.gather_probes(input)
-        off = np.zeros(len(input) + 1, dtype=np.int64)
-        np.cumsum(gathered[1], out=off[1:])
+        off = cov.offsets_from_lengths(gathered[1])
         first, _, st = ctx.group_duplicates(gathered[0], off)
         self.last_stats = st.as_dict()
+        if isinstance(input, ProbeBatch):
+            return input.take(first)                # still one buffer; no Probe objects
         return [input[i] for i in first.tolist()]

@@ -19,6 +19,7 @@ import numpy as np
 from catch_b200 import _lib
 from catch_b200 import coverage as cov
 from catch_b200.filter.base_filter import BaseFilter
+from catch_b200.probe_batch import ProbeBatch
 
 
 def _num_tables(P1, k, reporting_prob):
@@ -68,8 +69,9 @@ class NearDuplicateFilter(BaseFilter):
         the sequential keep/drop loop (:81-96) all run in cb_neardup_filter.  It returns, in priority
         order, the list index of the first occurrence of every kept sequence -- the Probe object the
         reference's dict keyed by Probe keeps."""
-        input = list(input)
-        if not input:
+        if not isinstance(input, ProbeBatch):
+            input = list(input)
+        if not len(input):
             # the reference still builds the lookup (and draws its parameters) for empty input
             self._draw_only()
             return []
@@ -82,6 +84,13 @@ class NearDuplicateFilter(BaseFilter):
         kept, n_distinct, st = self._draw_and_run(ctx, raw, off, lens)
         self.last_stats = st.as_dict()
         self.last_stats['n_distinct'] = n_distinct
+        if isinstance(input, ProbeBatch):
+            # same order as the reference's list(set(...)): the set order of the kept SEQUENCES (see set_ordered)
+            strs = input.strs(kept)
+            rank = {s: i for i, s in enumerate(strs)}
+            order = set()
+            order.update(strs)
+            return input.take(kept[np.fromiter((rank[s] for s in order), dtype=np.int64, count=len(strs))])
         return set_ordered([input[i] for i in kept.tolist()])     # :96-103: to_include.add(p) ..., list(to_include)
 
 

@@ -9,6 +9,7 @@ import itertools
 import logging
 
 from catch_b200.filter import candidate_probes
+from catch_b200.probe_batch import ProbeBatch
 
 logger = logging.getLogger(__name__)
 
@@ -30,17 +31,39 @@ class ProbeDesigner:
     def design(self):
         candidates = []
         for genomes_from_group in self.genomes:
-            group = []
-            for g in genomes_from_group:
-                group += candidate_probes.make_candidate_probes_from_sequences(
-                    g.seqs, probe_length=self.probe_length, probe_stride=self.probe_stride,
-                    allow_small_seqs=self.allow_small_seqs, seq_length_to_skip=self.seq_length_to_skip)
-            if not group:
+            group = self._candidates_as_batch(genomes_from_group)
+            if group is None:                   # small sequences in play: the per-object path knows those rules
+                group = []
+                for g in genomes_from_group:
+                    group += candidate_probes.make_candidate_probes_from_sequences(
+                        g.seqs, probe_length=self.probe_length, probe_stride=self.probe_stride,
+                        allow_small_seqs=self.allow_small_seqs, seq_length_to_skip=self.seq_length_to_skip)
+            if not len(group):
                 logger.warning("There are no candidate probes for a grouping of genomes")
             candidates.append(group)
         probes = candidates
         for f in self.filters:
             logger.info("Starting filter %s", f.__class__.__name__)
             probes = f.filter(probes, self.genomes, input_is_grouped=True)
-        self.candidate_probes = list(itertools.chain(*candidates))
+        self._candidates = candidates
         self.final_probes = list(set(itertools.chain(*probes)))
+
+    @property
+    def candidate_probes(self):
+        """All candidates as Probe objects (probe_designer.py:268); materialised on demand only."""
+        return list(itertools.chain(*self._candidates))
+
+    def _candidates_as_batch(self, genomes_from_group):
+        """The candidates of one grouping as one buffer (catch_b200/probe_batch.py), or None when a sequence is
+        shorter than the probe length (then --small-seq-min / the error of candidate_probes.py:53-70 applies)."""
+        batches = []
+        for g in genomes_from_group:
+            if not isinstance(g.seqs, list) or len(g.seqs) == 0 or not all(isinstance(s, str) for s in g.seqs):
+                return None
+            b = ProbeBatch.from_sequences(g.seqs, self.probe_length, self.probe_stride,
+                                          seq_length_to_skip=self.seq_length_to_skip)
+            if b is None:
+                return None
+            batches.append(b)
+        out = ProbeBatch.concat(batches)
+        return out if out is not None else []

@@ -22,6 +22,7 @@ from catch_b200 import _lib
 from catch_b200 import coverage as cov
 from catch_b200 import parallel
 from catch_b200.filter.base_filter import BaseFilter
+from catch_b200.probe_batch import ProbeBatch
 from catch_b200.utils import seq_io
 
 logger = logging.getLogger(__name__)
@@ -54,7 +55,8 @@ class _LazyStrs:
 
     def _get(self):
         if self._strs is None:
-            self._strs = [p.seq_str for p in self._probes]
+            self._strs = self._probes.strs() if isinstance(self._probes, ProbeBatch) else \
+                [p.seq_str for p in self._probes]
         return self._strs
 
     def __len__(self):
@@ -81,7 +83,7 @@ class _DrawChain:
         self.mine = [g for g in range(len(input)) if owner[g] == rank]
         # lengths first, on the calling thread and on all ranks at once, so that a hop of the chain
         # is nothing but the draw itself
-        self.lengths = {g: cov.probe_lengths(input[g] if isinstance(input[g], (list, tuple)) else list(input[g]))
+        self.lengths = {g: cov.probe_lengths(input[g] if isinstance(input[g], (list, tuple, ProbeBatch)) else list(input[g]))
                         for g in self.mine}
         self.events = {g: threading.Event() for g in self.mine}
         self.results, self.sends, self.error = {}, [], None
@@ -129,11 +131,15 @@ class _DrawChain:
 class _Prefetch:
     """Host work of the NEXT grouping while the current one is on the device.  A helper thread gathers the
     probe sequences and the target sequences of the groupings this process owns, in order, into a second
-    pair of page-locked staging buffers (cb_host_buffer slots 2k and 2k+1 of pair k); the filter loop picks
+    pair of page-locked staging buffers (cb_host_buffer slots 2 + 2k and 3 + 2k of pair k = 0, 1; slots 0 and 1
+    stay with the calls the loop itself makes, e.g. the scans behind the ranks); the filter loop picks
     each grouping up when it gets there.  The device calls of the loop release the GIL (ctypes), so the
     gather of grouping g+1 overlaps the scan and set cover of g.  A pair is reused only after the upload
     that reads it has returned (release()).  The staging buffers are sized up front on the calling thread,
-    so the helper never calls into the library."""
+    so the helper never calls into the library.
+    OFF by default (CB_PREFETCH=1 turns it on): measured on the V-All shape it does not pay -- gathering a list
+    of Probe objects holds the GIL for its whole attribute pass, so the two threads mostly take turns
+    (profiles/README_r02.md).  The remedy for that host cost is not to have the objects at all: ProbeBatch."""
 
     def __init__(self, ctx, groups):
         """groups: list of (group index, probe list, genomes) in processing order."""
@@ -145,8 +151,8 @@ class _Prefetch:
                 p_max = max(p_max, int(cov.probe_lengths(probes).sum(dtype=np.int64)))
             t_max = max(t_max, sum(g.size() for g in genomes))
         for pair in (0, 1):
-            ctx.host_buffer(2 * pair, p_max + 64)
-            ctx.host_buffer(2 * pair + 1, t_max + 64)
+            ctx.host_buffer(2 + 2 * pair, p_max + 64)
+            ctx.host_buffer(3 + 2 * pair, t_max + 64)
         self.free = [threading.Semaphore(1), threading.Semaphore(1)]
         self.q = queue.Queue()
         self.stop = False
@@ -159,8 +165,8 @@ class _Prefetch:
             if self.stop:
                 return
             try:
-                gathered = cov.gather_staged(self.ctx, 2 * (k % 2), probes) if len(probes) else None
-                staged = cov.stage_targets(self.ctx, 2 * (k % 2) + 1, genomes) if len(probes) else None
+                gathered = cov.gather_staged(self.ctx, 2 + 2 * (k % 2), probes) if len(probes) else None
+                staged = cov.stage_targets(self.ctx, 3 + 2 * (k % 2), genomes) if len(probes) else None
                 self.q.put((g, gathered, staged, None))
             except BaseException as e:          # noqa: BLE001 -- re-raised by the consumer
                 self.q.put((g, None, None, e))
@@ -317,8 +323,8 @@ class SetCoverFilter(BaseFilter):
         mine = [g for g in range(len(input)) if owner[g] == rank]
         prefetch = None
         if len(mine) >= 2 and cov._fastpack is not None and hasattr(self._context(), 'host_buffer') and \
-                os.environ.get('CB_PREFETCH', '1') != '0':
-            as_lists = {g: (input[g] if isinstance(input[g], (list, tuple)) else list(input[g])) for g in mine}
+                os.environ.get('CB_PREFETCH', '0') == '1':
+            as_lists = {g: (input[g] if isinstance(input[g], (list, tuple, ProbeBatch)) else list(input[g])) for g in mine}
             prefetch = _Prefetch(self._context(), [(g, as_lists[g], target_genomes_grouped[g]) for g in mine])
         try:
             for k, group_i in enumerate(mine):
@@ -352,7 +358,7 @@ class SetCoverFilter(BaseFilter):
             [local[i] for i in range(len(input))]
         selected = []
         for possible_probes, chosen in zip(input, chosen_per_group):
-            if not isinstance(possible_probes, (list, tuple)):
+            if not isinstance(possible_probes, (list, tuple, ProbeBatch)):
                 possible_probes = list(possible_probes)
             selected.append([possible_probes[i] for i in chosen])
         return selected
@@ -365,7 +371,7 @@ class SetCoverFilter(BaseFilter):
         already gathered this grouping.  Returns the indices of the selected probes in the reference's
         output order."""
         sharded = chain is not None
-        if not isinstance(possible_probes, (list, tuple)):
+        if not isinstance(possible_probes, (list, tuple, ProbeBatch)):
             possible_probes = list(possible_probes)
         n_probes = len(possible_probes)
         probe_strs = _LazyStrs(possible_probes)
@@ -397,7 +403,8 @@ class SetCoverFilter(BaseFilter):
                 # on the guess that all probes are as long as the first (candidate probes are);
                 # if the gathered lengths say otherwise the guess is dropped -- a background draw
                 # only touches numpy's RNG state when it is accepted -- and the draw is redone.
-                guess = len(possible_probes[0].seq_str)
+                guess = possible_probes.probe_length if isinstance(possible_probes, ProbeBatch) else \
+                    len(possible_probes[0].seq_str)
                 try:
                     drawn = cov.draw_seeds(np.full(n_probes, guess, dtype=np.int32), self.mismatches,
                                            self.lcf_thres, self.kmer_probe_map_k, background=True)
@@ -469,7 +476,7 @@ class SetCoverFilter(BaseFilter):
         ctx = self._context()
         selected = []
         for group_i, (possible_probes, target_genomes) in enumerate(zip(input, target_genomes_grouped)):
-            if not isinstance(possible_probes, (list, tuple)):
+            if not isinstance(possible_probes, (list, tuple, ProbeBatch)):
                 possible_probes = list(possible_probes)
             n_probes = len(possible_probes)
             t0 = time.perf_counter()
@@ -488,7 +495,8 @@ class SetCoverFilter(BaseFilter):
             try:
                 # the draw consumes the RNG for ALL probes on every rank (same stream everywhere, and the
                 # stream ends where a single process would leave it); each rank uses its own rows
-                guess = len(possible_probes[0].seq_str)
+                guess = possible_probes.probe_length if isinstance(possible_probes, ProbeBatch) else \
+                    len(possible_probes[0].seq_str)
                 try:
                     drawn = cov.draw_seeds(np.full(n_probes, guess, dtype=np.int32), self.mismatches,
                                            self.lcf_thres, self.kmer_probe_map_k, background=True)

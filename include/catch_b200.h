@@ -94,8 +94,8 @@ int cb_pool_reserve(cb_ctx *ctx, int64_t bytes);
  * The denominator of the integer-op roofline bench.py reports beside the HBM one. */
 int cb_intop_rate(cb_ctx *ctx, double *ops_per_s);
 
-/* Page-locked host staging memory owned by the context: slot 0..3 (two probe/target pairs, so that the next
- * grouping can be gathered while the current one is on the device), at least `bytes` bytes, valid
+/* Page-locked host staging memory owned by the context: slot 0..5 (0/1: probes and targets of the call in progress; 2/3 and 4/5: two more
+ * pairs, so that the next groupings can be gathered while the current one is on the device), at least `bytes` bytes, valid
  * until the next cb_host_buffer call for the same slot with a larger size (or cb_destroy).  Filling
  * the sequences straight into it lets the uploads below run as true asynchronous DMA instead of
  * going through the driver's bounce buffer. */

@@ -1,4 +1,5 @@
 """Parity of the CUDA path (through the C ABI) against the CPU oracle.  Needs a B200."""
+import os
 import random
 
 import numpy as np
@@ -390,3 +391,39 @@ def test_setcover_with_costs_matches_oracle(ctx):
             picks, _ = ctx.setcover(cover, len(probe_strs), ranks, up, costs=costs)
             assert picks.tolist() == want
         cover.free()
+
+
+def test_probe_batch_filter_chain_equals_probe_lists(ctx):
+    """candidates kept as one buffer (catch_b200/probe_batch.py) through DuplicateFilter /
+    NearDuplicateFilter / SetCoverFilter give exactly the output of the same chain on lists of Probe objects
+    (same probes, same order); Probe objects only appear for the selected ones."""
+    from catch_b200 import probe
+    from catch_b200.filter.duplicate_filter import DuplicateFilter
+    from catch_b200.filter.near_duplicate_filter import NearDuplicateFilterWithMinHash
+    from catch_b200.filter.set_cover_filter import SetCoverFilter
+    from catch_b200.probe_batch import ProbeBatch
+    groups = [helpers.synthetic_genomes(25, 2500, 0.04, seed=21), helpers.synthetic_genomes(12, 1800, 0.02, seed=22)]
+    groups[0][3] = groups[0][3][:700] + 'NNNN' + groups[0][3][704:]            # an N run: flanking probes
+    genomes = helpers.to_genomes([[[s] for s in g] for g in groups])
+    batches = [ProbeBatch.from_sequences(g, 100, 50) for g in groups]
+    lists = [[probe.Probe.from_str(s) for s in b.strs()] for b in batches]
+    for first in ('dup', 'minhash'):
+        outs = []
+        for inp in (lists, batches):
+            f1 = DuplicateFilter() if first == 'dup' else NearDuplicateFilterWithMinHash(0.5)
+            f2 = SetCoverFilter(mismatches=3, lcf_thres=60, cover_extension=20)
+            f1._ctx = f2._ctx = ctx
+            np.random.seed(5)
+            random.seed(5)
+            mid = f1.filter(inp, genomes, input_is_grouped=True)
+            if inp is batches:
+                assert all(isinstance(m, ProbeBatch) for m in mid)
+            out = f2.filter(mid, genomes, input_is_grouped=True)
+            outs.append(([[p.seq_str for p in g] for g in mid], [[p.seq_str for p in g] for g in out]))
+        if first == 'dup' or os.environ.get('PYTHONHASHSEED') == '0':
+            assert outs[0] == outs[1]
+        else:
+            # the near-duplicate filter's output ORDER follows the interpreter's string hash seed on both
+            # paths alike (list(set(...))); both are in THIS process, so the orders agree here too
+            assert outs[0] == outs[1]
+        assert sum(map(len, outs[0][1])) > 10

@@ -272,3 +272,37 @@ def test_set_ordered_equals_set_of_probes():
         assert len(got) == len(probes) and all(a is b for a, b in zip(got, list(want)))
     dup = [probe.Probe.from_str('ACGT'), probe.Probe.from_str('ACGT'), probe.Probe.from_str('TTTT')]
     assert [p.seq_str for p in set_ordered(dup)] == [p.seq_str for p in list(set(dup))]
+
+
+def test_probe_batch_tiling_equals_candidate_probes():
+    """ProbeBatch.from_sequences (one strided buffer) yields exactly the probes of
+    filter/candidate_probes.py:21-182 in the same order, N-run handling and flanking flags included."""
+    import random
+    from catch_b200.filter import candidate_probes as cp
+    from catch_b200.probe_batch import ProbeBatch
+    rng = random.Random(9)
+    n_cases = 0
+    for case in range(60):
+        pl = rng.choice([20, 50, 100])
+        ps = rng.choice([7, 10, 25, 50, 100, 130])
+        seqs = []
+        for _ in range(rng.randint(1, 4)):
+            n = rng.randint(pl, 6 * pl + rng.randint(0, 40))
+            s = [rng.choice('ACGT') for _ in range(n)]
+            for _ in range(rng.choice([0, 0, 1, 3])):            # N runs of length 1..6, sometimes at the ends
+                a = rng.choice([0, rng.randrange(n), n - 1])
+                for i in range(a, min(n, a + rng.randint(1, 6))):
+                    s[i] = 'N'
+            seqs.append(''.join(s))
+        skip = rng.choice([None, None, pl + 5])
+        want = cp.make_candidate_probes_from_sequences(seqs, pl, ps, seq_length_to_skip=skip)
+        got = ProbeBatch.from_sequences(seqs, pl, ps, seq_length_to_skip=skip)
+        assert got is not None
+        assert got.strs() == [p.seq_str for p in want]
+        assert [p.is_flanking_n_string for p in got] == [p.is_flanking_n_string for p in want]
+        assert [p.seq_str for p in got[1:4]] == [p.seq_str for p in want[1:4]]
+        n_cases += len(want) > 0
+    assert n_cases > 40
+    assert ProbeBatch.from_sequences(['ACGT'], 10, 5) is None        # shorter than a probe: per-object path
+    b = ProbeBatch.from_sequences(['ACGTACGTAC', 'TTTTTTTTTTTT'], 10, 5)
+    assert b.take([1, 0]).strs() == ['TTTTTTTTTT', 'ACGTACGTAC'] and len(b) == 3
