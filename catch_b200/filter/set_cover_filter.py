@@ -360,7 +360,8 @@ class SetCoverFilter(BaseFilter):
         for possible_probes, chosen in zip(input, chosen_per_group):
             if not isinstance(possible_probes, (list, tuple, ProbeBatch)):
                 possible_probes = list(possible_probes)
-            selected.append([possible_probes[i] for i in chosen])
+            selected.append(possible_probes.probes(list(chosen)) if isinstance(possible_probes, ProbeBatch) else
+                            [possible_probes[i] for i in chosen])
         return selected
 
     def _filter_one_group(self, group_i, n_groups, possible_probes, target_genomes, target_genomes_grouped, chain,
@@ -555,7 +556,8 @@ class SetCoverFilter(BaseFilter):
             for i in picks.tolist():
                 chosen.add(i)
             chosen = pickle.loads(pickle.dumps(chosen))
-            selected.append([possible_probes[i] for i in chosen])
+            selected.append(possible_probes.probes(list(chosen)) if isinstance(possible_probes, ProbeBatch) else
+                            [possible_probes[i] for i in chosen])
             seed_bytes = int(plan.uniform[lo:hi].nbytes) if plan.uniform is not None else \
                 int(plan.seed_pos.nbytes + plan.seed_off.nbytes)
             stats.update(seed_mode=plan.mode, k=plan.k, bits=group.bits, h2d_bytes=group.h2d_bytes + seed_bytes,

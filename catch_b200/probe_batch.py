@@ -66,6 +66,16 @@ class ProbeBatch:
         flat = rows.tobytes().decode('latin-1')
         return [flat[i * L:(i + 1) * L] for i in range(n)]
 
+    def probes(self, idx):
+        """Probe objects of the rows `idx`, built from one decode of the gathered rows."""
+        idx = np.asarray(idx, dtype=np.int64)
+        out = [probe.Probe(s) for s in self.strs(idx)]
+        if self.flanking is not None:
+            for p, fl in zip(out, self.flanking[idx].tolist()):
+                if fl:
+                    p.is_flanking_n_string = True
+        return out
+
     def lengths(self):
         return np.full(len(self), self.data.shape[1], dtype=np.int32)
 
