@@ -947,8 +947,8 @@ merge_kernel(const int64_t *__restrict__ rec_off, uint64_t *__restrict__ rec, in
 // Probes with at most MERGE_WARP_CAP ranges (all of them in the usual one-range-per-genome case):
 // one WARP per probe, the same normalised bitonic network in the warp's slice of shared memory
 // with __syncwarp between the steps -- no block barrier anywhere, eight probes in flight per CTA.
-constexpr int MERGE_WARP_CAP = 512;
-constexpr int MERGE_WARPS = 8;
+constexpr int MERGE_WARP_CAP = 1024;     // the scan emits one range per (probe, diagonal, run): ~260 per probe at Zika scale,
+constexpr int MERGE_WARPS = 4;           // a few probes several hundred; 4 x 1024 x 8 B = 32 KB of shared memory per CTA
 
 __global__ void __launch_bounds__(MERGE_WARPS * 32)
 merge_warp_kernel(const int64_t *__restrict__ rec_off, uint64_t *__restrict__ rec, int64_t n_probes,

@@ -241,13 +241,13 @@ def test_parallel_rounds_at_scale(ctx, monkeypatch):
 
 
 def test_merge_paths_small_and_large_range_lists(ctx):
-    """Probes with a handful of ranges take the warp-per-probe merge, probes with more than 512
-    ranges (here: ~700 near-identical genomes) the block-per-probe merge; both against the oracle."""
+    """Probes with a handful of ranges take the warp-per-probe merge, probes with more than 1024
+    ranges (here: ~1300 near-identical genomes) the block-per-probe merge; both against the oracle."""
     O = _oracle()
     rng = random.Random(23)
     anc = ''.join(rng.choice('ACGT') for _ in range(260))
     anc_b = ''.join(rng.choice('ACGT') for _ in range(260))
-    genomes = [[helpers.mutate(rng, anc, 0.01)] for _ in range(700)] + \
+    genomes = [[helpers.mutate(rng, anc, 0.01)] for _ in range(1300)] + \
               [[helpers.mutate(rng, anc_b, 0.01)] for _ in range(4)]
     probe_strs = list(dict.fromkeys(helpers.tile_candidates([g[0] for g in genomes[:6] + genomes[-2:]], 60, 20)))
     params = dict(mismatches=3, lcf_thres=40, island_of_exact_match=0, cover_extension=5, kmer_probe_map_k=15)
@@ -257,7 +257,7 @@ def test_merge_paths_small_and_large_range_lists(ctx):
     np.random.seed(5)
     got, cover, st = _device_quads(ctx, probe_strs, genomes, params)
     counts = np.bincount(want[:, 0], minlength=len(probe_strs))
-    assert counts.max() > 512 and counts.min() < 512
+    assert counts.max() > 1024 and counts.min() < 512
     assert np.array_equal(got, want)
     picks, _ = ctx.setcover(cover, len(probe_strs), None, None)
     assert picks.tolist() == O.set_cover_quads(want, len(probe_strs), len(genomes))
