@@ -26,7 +26,6 @@ logger = logging.getLogger(__name__)
 UNSUPPORTED = {
     'filter_from_fasta': '--filter-from-fasta', 'filter_polya': '--filter-polya',
     'expand_n': '--expand-n',
-    'cluster_from_fragments': '--cluster-from-fragments',
     'custom_hybridization_fn': '--custom-hybridization-fn',
     'custom_hybridization_fn_tolerant': '--custom-hybridization-fn-tolerant',
 }
@@ -38,10 +37,11 @@ def main(args):
         if getattr(args, attr, None):
             raise SystemExit("%s configures a part of CATCH outside the GPU hot path and is not available "
                              "in this build" % flag)
-    if args.cluster_and_design_separately and args.args_type != 'large':
-        raise SystemExit("--cluster-and-design-separately (genome clustering) is not available in this build")
-    if args.cluster_and_design_separately:
-        logger.warning("design_large.py: genome clustering is not available; designing without it")
+    if args.cluster_and_design_separately and args.identify:              # bin/design.py:237-243
+        raise Exception("Cannot use --cluster-and-design-separately with --identify, because clustering collapses "
+                        "genome groupings into one")
+    if args.cluster_from_fragments and not args.cluster_and_design_separately:
+        raise Exception("Cannot use --cluster-from-fragments without also setting --cluster-and-design-separately")
 
     genomes_grouped = []
     genomes_grouped_names = []
@@ -124,9 +124,18 @@ def main(args):
     if args.add_reverse_complements:               # bin/design.py:375-380
         filters.append(reverse_complement_filter.ReverseComplementFilter())
 
+    if args.skip_set_cover:                         # bin/design.py:382-385 (the filter before the set cover)
+        filter_before_scf = filters[0]
+    if args.cluster_and_design_separately:          # bin/design.py:387-400
+        cluster_kw = dict(cluster_threshold=args.cluster_and_design_separately,
+                          cluster_merge_after=filter_before_scf if args.skip_set_cover else filters[1],
+                          cluster_method=args.cluster_and_design_separately_method,
+                          cluster_fragment_length=args.cluster_from_fragments)
+    else:
+        cluster_kw = {}
     pd = probe_designer.ProbeDesigner(genomes_grouped, filters, probe_length=args.probe_length,
                                       probe_stride=args.probe_stride, allow_small_seqs=args.small_seq_min,
-                                      seq_length_to_skip=args.small_seq_skip)
+                                      seq_length_to_skip=args.small_seq_skip, **cluster_kw)
     pd.design()
     seq_io.write_probe_fasta(pd.final_probes, args.output_probes)
     if (args.print_analysis or args.write_analysis_to_tsv or args.write_sliding_window_coverage or
@@ -200,7 +209,7 @@ def init_and_parse_args(args_type='basic', argv=None):
                     default={'basic': None, 'large': 0.15}[args_type])
     ap.add_argument('--cluster-and-design-separately-method', choices=['choose', 'simple', 'hierarchical'],
                     default='choose')
-    ap.add_argument('--cluster-from-fragments', type=int, default=None)
+    ap.add_argument('--cluster-from-fragments', type=int, default={'basic': None, 'large': 50000}[args_type])
     ap.add_argument('--filter-with-lsh-hamming', type=int)
 
     def jaccard(val):

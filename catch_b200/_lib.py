@@ -50,6 +50,8 @@ EXPORTED_SYMBOLS = [
     'cb_comm_unique_id', 'cb_comm_init', 'cb_comm_destroy', 'cb_cover_allgather',
     'cb_coverage_range', 'cb_coverage_records', 'cb_free_host', 'cb_exchange_alloc', 'cb_exchange_bytes', 'cb_exchange_handle', 'cb_exchange_attach',
     'cb_exchange_required', 'cb_setcover_sharded', 'cb_setcover_sharded_begin', 'cb_setcover_sharded_end',
+    'cb_sketch_sequences', 'cb_sketches_import', 'cb_sketches_export', 'cb_sketches_free', 'cb_sketch_dist_rows',
+    'cb_sketch_dist_condensed',
 ]
 
 _lib = None
@@ -126,6 +128,13 @@ def load():
                                     C.POINTER(i64), C.POINTER(Stats)]
     L.cb_group_duplicates.argtypes = [vp, vp, vp, i64, vp, vp, C.POINTER(i64), C.POINTER(Stats)]
     L.cb_hamming_neardup.argtypes = [vp, vp, vp, i64, vp, i32, i32, i32, vp, C.POINTER(Stats)]
+    L.cb_sketch_sequences.argtypes = [vp, vp, vp, i64, i32, i32, C.c_uint64, C.c_uint64, C.POINTER(vp), C.POINTER(Stats)]
+    L.cb_sketches_import.argtypes = [vp, vp, i64, i32, C.POINTER(vp)]
+    L.cb_sketches_export.argtypes = [vp, vp, vp]
+    L.cb_sketches_free.argtypes = [vp]
+    L.cb_sketches_free.restype = None
+    L.cb_sketch_dist_rows.argtypes = [vp, vp, vp, i64, vp]
+    L.cb_sketch_dist_condensed.argtypes = [vp, vp, vp]
     _lib = L
     return L
 
@@ -421,6 +430,40 @@ class Context:
         self._check(self.L.cb_hamming_neardup(self.h, _ptr(ascii_u8), _ptr(probe_off), n, _ptr(positions),
                                               n_tables, k_concat, int(dist_thres), _ptr(keep), C.byref(st)))
         return keep[:n], st
+
+
+    # ---- genome clustering: MinHash sketches
+    def sketch_sequences(self, raw, seq_off, kmer_size, N, a, b):
+        """cb_sketch_sequences: `raw` holds the sequences back to back (bytes), seq_off their int64 offsets.
+        Returns (sketches handle, stats)."""
+        out, st = C.c_void_p(), Stats()
+        self._check(self.L.cb_sketch_sequences(self.h, raw, _ptr(seq_off), len(seq_off) - 1, kmer_size, N,
+                                               int(a), int(b), C.byref(out), C.byref(st)))
+        return Handle(self.L.cb_sketches_free, out), st
+
+    def sketches_import(self, sig):
+        out = C.c_void_p()
+        self._check(self.L.cb_sketches_import(self.h, _ptr(sig), sig.shape[0], sig.shape[1], C.byref(out)))
+        return Handle(self.L.cb_sketches_free, out)
+
+    def sketches_export(self, sketches, n, N):
+        sig = np.zeros((n, N), dtype=np.uint32)
+        if n:
+            self._check(self.L.cb_sketches_export(self.h, sketches.h, _ptr(sig)))
+        return sig
+
+    def sketch_dist_rows(self, sketches, rows, n):
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        out = np.zeros((len(rows), n), dtype=np.float64)
+        if out.size:
+            self._check(self.L.cb_sketch_dist_rows(self.h, sketches.h, _ptr(rows), len(rows), _ptr(out)))
+        return out
+
+    def sketch_dist_condensed(self, sketches, n):
+        out = np.zeros(n * (n - 1) // 2, dtype=np.float32)
+        if out.size:
+            self._check(self.L.cb_sketch_dist_condensed(self.h, sketches.h, _ptr(out)))
+        return out
 
 
 class Handle:

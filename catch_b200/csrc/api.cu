@@ -650,4 +650,48 @@ int cb_hamming_neardup(cb_ctx *ctx, const uint8_t *ascii, const int64_t *probe_o
                                    dist_thres, keep, stats);
 }
 
+int cb_sketch_sequences(cb_ctx *ctx, const uint8_t *ascii, const int64_t *seq_off, int64_t n_seqs, int32_t kmer_size,
+                        int32_t N, uint64_t a, uint64_t b, cb_sketches **out, cb_stats *stats)
+{
+    if (!ctx) return CB_ERR_ARG;
+    if (stats) memset(stats, 0, sizeof *stats);
+    ctx->launches = 0;
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cb_tls_stream = ctx->stream;
+    return cb_sketch_sequences_impl(ctx, ascii, seq_off, n_seqs, kmer_size, N, a, b, out, stats);
+}
+
+int cb_sketches_import(cb_ctx *ctx, const uint32_t *sig, int64_t n_seqs, int32_t N, cb_sketches **out)
+{
+    if (!ctx) return CB_ERR_ARG;
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cb_tls_stream = ctx->stream;
+    return cb_sketch_import_impl(ctx, sig, n_seqs, N, out);
+}
+
+int cb_sketches_export(cb_ctx *ctx, const cb_sketches *sk, uint32_t *sig)
+{
+    if (!ctx) return CB_ERR_ARG;
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    return cb_sketches_export_impl(ctx, sk, sig);
+}
+
+int cb_sketch_dist_rows(cb_ctx *ctx, const cb_sketches *sk, const int64_t *rows, int64_t n_rows, double *out)
+{
+    if (!ctx) return CB_ERR_ARG;
+    ctx->launches = 0;
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cb_tls_stream = ctx->stream;
+    return cb_sketch_dist_rows_impl(ctx, sk, rows, n_rows, out);
+}
+
+int cb_sketch_dist_condensed(cb_ctx *ctx, const cb_sketches *sk, float *out)
+{
+    if (!ctx) return CB_ERR_ARG;
+    ctx->launches = 0;
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cb_tls_stream = ctx->stream;
+    return cb_sketch_dist_condensed_impl(ctx, sk, out);
+}
+
 }  // extern "C"

@@ -146,7 +146,112 @@ static PyObject *gather(PyObject *self, PyObject *args) { return gather_impl(arg
 static PyObject *gather_into(PyObject *self, PyObject *args) { return gather_impl(args, 1); }
 static PyObject *lengths(PyObject *self, PyObject *args) { return gather_impl(args, 2); }
 
+
+/* ---- FASTA wire format ---------------------------------------------------------------------
+ * parse_fasta(data, make_uppercase, replace_degenerate, skip_gaps) -> (list of names, list of sequences)
+ * The record loop of the reference's seq_io.read_fasta (catch/utils/seq_io.py:104-175) over the raw bytes of an
+ * ASCII file, one pass, GIL released: lines end at '\n', '\r\n' or a lone '\r' (Python's universal newlines);
+ * every line is right-stripped of ASCII whitespace (str.rstrip: 0x09-0x0d, 0x1c-0x20); an empty line closes the
+ * current record, and the next non-empty line must then be a header (AssertionError otherwise, :141-143); a line
+ * that starts with '>' opens a record named by the rest of the line; any other line is appended to the current
+ * record after upper-casing, [YRWSMKBDHV] -> N and removal of '-' (:149-154), each switchable like the
+ * reference's keyword arguments.  Records come back in file order, repeated names included: the caller's
+ * `m[name] = seq` in that order gives the reference's OrderedDict (a repeated header restarts the entry but
+ * keeps its first position, :145-146).  The caller guarantees that `data` holds no byte above 0x7f. */
+typedef struct { size_t name_b, name_e, seq_b, seq_e; } fasta_rec;
+
+static int is_py_space(unsigned char c) { return (c >= 0x09 && c <= 0x0d) || (c >= 0x1c && c <= 0x20); }
+
+static PyObject *parse_fasta(PyObject *self, PyObject *args)
+{
+    Py_buffer view;
+    int make_upper = 1, replace_degenerate = 1, skip_gaps = 1;
+    if (!PyArg_ParseTuple(args, "y*|ppp", &view, &make_upper, &replace_degenerate, &skip_gaps)) return NULL;
+    const unsigned char *p = (const unsigned char *)view.buf;
+    const size_t n = (size_t)view.len;
+    unsigned char map[256], keep[256];
+    for (int c = 0; c < 256; c++) {
+        unsigned char o = (unsigned char)c;
+        if (make_upper && o >= 'a' && o <= 'z') o = (unsigned char)(o - 32);
+        if (replace_degenerate && strchr("YRWSMKBDHV", o) && o) o = 'N';
+        map[c] = o;
+        keep[c] = !(skip_gaps && c == '-');
+    }
+    unsigned char *out = (unsigned char *)malloc(n ? n : 1);
+    size_t cap = 1024, n_rec = 0, bad_at = (size_t)-1;
+    fasta_rec *rec = (fasta_rec *)malloc(cap * sizeof(fasta_rec));
+    if (!out || !rec) { free(out); free(rec); PyBuffer_Release(&view); return PyErr_NoMemory(); }
+    int oom = 0;
+    Py_BEGIN_ALLOW_THREADS
+    size_t pos = 0, w = 0;
+    int in_record = 0;
+    while (pos < n) {
+        /* one line [pos, e), terminator consumed */
+        const unsigned char *nl = (const unsigned char *)memchr(p + pos, '\n', n - pos);
+        size_t e = nl ? (size_t)(nl - p) : n, next = nl ? e + 1 : n;
+        const unsigned char *cr = (const unsigned char *)memchr(p + pos, '\r', e - pos);
+        if (cr && !((size_t)(cr - p) + 1 == e && nl)) {      /* a lone '\r' ends the line too */
+            e = (size_t)(cr - p);
+            next = e + 1;
+            if (next < n && p[next] == '\n') next++;
+        }
+        size_t b = pos;
+        pos = next;
+        while (e > b && is_py_space(p[e - 1])) e--;
+        if (e == b) { in_record = 0; continue; }
+        if (!in_record && p[b] != '>') { bad_at = b; break; }
+        if (p[b] == '>') {
+            if (n_rec == cap) {
+                cap *= 2;
+                fasta_rec *r2 = (fasta_rec *)realloc(rec, cap * sizeof(fasta_rec));
+                if (!r2) { oom = 1; break; }
+                rec = r2;
+            }
+            if (n_rec) rec[n_rec - 1].seq_e = w;
+            rec[n_rec].name_b = b + 1; rec[n_rec].name_e = e; rec[n_rec].seq_b = w; rec[n_rec].seq_e = w;
+            n_rec++;
+            in_record = e - b > 1;      /* an empty name is the reference's "no record" marker (:137-143) */
+            continue;
+        }
+        for (size_t i = b; i < e; i++) {
+            const unsigned char c = p[i];
+            out[w] = map[c];
+            w += keep[c];
+        }
+    }
+    if (n_rec) rec[n_rec - 1].seq_e = w;
+    Py_END_ALLOW_THREADS
+    PyObject *names = NULL, *seqs = NULL, *ret = NULL;
+    if (oom) { PyErr_NoMemory(); goto done; }
+    if (bad_at != (size_t)-1) {
+        PyErr_Format(PyExc_AssertionError, "FASTA: sequence data without a header at byte %zu", bad_at);
+        goto done;
+    }
+    names = PyList_New((Py_ssize_t)n_rec);
+    seqs = PyList_New((Py_ssize_t)n_rec);
+    if (!names || !seqs) goto done;
+    for (size_t i = 0; i < n_rec; i++) {
+        PyObject *nm = PyUnicode_New((Py_ssize_t)(rec[i].name_e - rec[i].name_b), 127);
+        PyObject *sq = PyUnicode_New((Py_ssize_t)(rec[i].seq_e - rec[i].seq_b), 127);
+        if (!nm || !sq) { Py_XDECREF(nm); Py_XDECREF(sq); goto done; }
+        memcpy(PyUnicode_1BYTE_DATA(nm), p + rec[i].name_b, rec[i].name_e - rec[i].name_b);
+        memcpy(PyUnicode_1BYTE_DATA(sq), out + rec[i].seq_b, rec[i].seq_e - rec[i].seq_b);
+        PyList_SET_ITEM(names, (Py_ssize_t)i, nm);
+        PyList_SET_ITEM(seqs, (Py_ssize_t)i, sq);
+    }
+    ret = PyTuple_Pack(2, names, seqs);
+done:
+    Py_XDECREF(names);
+    Py_XDECREF(seqs);
+    free(out);
+    free(rec);
+    PyBuffer_Release(&view);
+    return ret;
+}
+
 static PyMethodDef methods[] = {
+    {"parse_fasta", parse_fasta, METH_VARARGS,
+     "parse_fasta(data, make_uppercase=True, replace_degenerate=True, skip_gaps=True) -> (names, sequences)"},
     {"gather", gather, METH_VARARGS, "gather(seq, attr) -> (bytes data, bytes int32 lengths)"},
     {"lengths", lengths, METH_VARARGS, "lengths(seq, attr) -> (int total_bytes, bytes int32 lengths); nothing is copied"},
     {"gather_into", gather_into, METH_VARARGS,

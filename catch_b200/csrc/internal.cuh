@@ -220,3 +220,11 @@ int cb_group_duplicates_impl(cb_ctx *ctx, const uint8_t *ascii, const int64_t *p
 int cb_hamming_neardup_impl(cb_ctx *ctx, const uint8_t *ascii, const int64_t *probe_off, int64_t n_probes,
                             const int32_t *positions, int32_t n_tables, int32_t k_concat,
                             int32_t dist_thres, uint8_t *keep, cb_stats *stats);
+
+// cluster.cu
+int cb_sketch_sequences_impl(cb_ctx *ctx, const uint8_t *ascii, const int64_t *seq_off, int64_t n, int32_t k,
+                             int32_t N, uint64_t a, uint64_t b, cb_sketches **out, cb_stats *stats);
+int cb_sketch_import_impl(cb_ctx *ctx, const uint32_t *sig, int64_t n, int32_t N, cb_sketches **out);
+int cb_sketches_export_impl(cb_ctx *ctx, const cb_sketches *sk, uint32_t *sig);
+int cb_sketch_dist_rows_impl(cb_ctx *ctx, const cb_sketches *sk, const int64_t *rows, int64_t n_rows, double *out);
+int cb_sketch_dist_condensed_impl(cb_ctx *ctx, const cb_sketches *sk, float *out);

@@ -1,0 +1,250 @@
+"""Clustering sequences by MinHash sketches before design: drop-in for catch/utils/cluster.py.
+
+Same functions and arguments as the reference (`cluster_with_minhash_signatures(seqs, k=12, N=100,
+threshold=0.1, cluster_method='simple')` :358-430 is what ProbeDesigner calls).  The two expensive parts run on
+the device: the sketches of all sequences (`make_signatures_with_minhash` :29-46 -> cb_sketch_sequences: one md5
+per k-mer, bottom-N selection per sequence) and every pairwise distance estimate (`estimate_jaccard_dist`,
+utils/lsh.py:166-214 -> cb_sketch_dist_rows / cb_sketch_dist_condensed), which the reference spreads over a
+process pool (:103-195, :270-290).
+
+Host work kept here, because it is interpreter state or third-party code the reference calls as well:
+  * the two parameters of the hash function come from Python's `random` (utils/lsh.py:95-96);
+  * the depth-first search of find_connected_components (:198-355) keeps the reference's set operations, so that
+    the order in which neighbours are pushed -- and with it the effect of the early-stop heuristic -- is the same;
+  * average-linkage clustering is scipy's (`hierarchy.linkage` / `fcluster`, :213-214).
+"""
+import logging
+import operator
+import random
+from collections import defaultdict
+
+import numpy as np
+
+from catch_b200 import _lib
+
+logger = logging.getLogger(__name__)
+
+_P31 = 2 ** 31 - 1
+
+
+class MinHashFamily:
+    """lsh.MinHashFamily (utils/lsh.py:47-214) with the deterministic md5 inner hash, which is what clustering
+    uses (:386); the hash function it makes runs on the device."""
+
+    def __init__(self, kmer_size, N=1, use_fast_str_hash=False):
+        if use_fast_str_hash:
+            raise NotImplementedError("sketches use the md5 inner hash (use_fast_str_hash=False), as cluster.py does")
+        self.kmer_size = kmer_size
+        self.N = N
+        self.use_fast_str_hash = False
+
+    def make_h(self):
+        a = random.randint(1, _P31)          # utils/lsh.py:95
+        b = random.randint(0, _P31)          # utils/lsh.py:96
+        return SketchFunction(self.kmer_size, self.N, a, b)
+
+    def P1(self, dist):
+        return 1.0 - dist
+
+    def estimate_jaccard_dist(self, hA, hB):
+        """Distance estimate of two signature tuples (utils/lsh.py:166-214), evaluated by the same kernel as the
+        batched forms."""
+        sk = SketchSet.from_signatures(np.array([hA, hB], dtype=np.uint32))
+        return float(sk.rows([0])[0, 1])
+
+
+class SketchFunction:
+    """The `h` of MinHashFamily.make_h(): h(s) is the signature tuple of one sequence; h.sketch(seqs) does many
+    sequences in one library call and leaves the sketches on the device."""
+
+    def __init__(self, kmer_size, N, a, b):
+        self.kmer_size, self.N, self.a, self.b = kmer_size, N, a, b
+
+    def sketch(self, seqs, ctx=None):
+        seqs = list(seqs)
+        for s in seqs:
+            assert self.kmer_size <= len(s)                  # utils/lsh.py:117
+            _warn_short(self.kmer_size, self.N, len(s))
+        ctx = ctx or _lib.default_context()
+        lens = np.fromiter((len(s) for s in seqs), dtype=np.int64, count=len(seqs))
+        off = np.zeros(len(seqs) + 1, dtype=np.int64)
+        np.cumsum(lens, out=off[1:])
+        raw = ''.join(seqs).encode('utf-8')
+        if len(raw) != int(off[-1]):
+            raise ValueError("sequences must be ASCII")
+        h, st = ctx.sketch_sequences(raw, off, self.kmer_size, self.N, self.a, self.b)
+        return SketchSet(ctx, h, len(seqs), self.N, st)
+
+    def __call__(self, s):
+        return tuple(int(v) for v in self.sketch([s]).signatures()[0])
+
+
+def _warn_short(kmer_size, N, length):
+    if kmer_size >= length / 2:                              # utils/lsh.py:118-122
+        logger.warning("The k-mer size %d is large (> (1/2)x) compared to the size of a sequence to hash (%d), "
+                       "which might make it difficult for MinHash to find similar sequence", kmer_size, length)
+    if length - kmer_size + 1 < N:                           # utils/lsh.py:124-130
+        logger.warning("The number of k-mers (%d) in a given sequence is too small to produce a signature of size "
+                       "%d; the MinHash family might provide unreliable distances against the sequence. This might "
+                       "be fine, or specify --small-seq-skip to skip the sequence.", length - kmer_size + 1, N)
+
+
+class SketchSet:
+    """Sketches of n sequences on the device, and distances between them.  Calling it as dist_fn(i, j) gives one
+    distance (what the reference's `jaccard_dist` closure does, cluster.py:397-401); rows() gives whole rows."""
+
+    def __init__(self, ctx, handle, n, N, stats=None):
+        self.ctx, self.h, self.n, self.N = ctx, handle, n, N
+        self.last_stats = stats.as_dict() if stats is not None else None
+        self._row_cache = {}
+
+    @classmethod
+    def from_signatures(cls, sig, ctx=None):
+        ctx = ctx or _lib.default_context()
+        sig = np.ascontiguousarray(sig, dtype=np.uint32)
+        return cls(ctx, ctx.sketches_import(sig), sig.shape[0], sig.shape[1])
+
+    def signatures(self):
+        return self.ctx.sketches_export(self.h, self.n, self.N)
+
+    def rows(self, idx):
+        """float64 [len(idx), n]: estimated Jaccard distance of each sketch in idx to every sketch."""
+        return self.ctx.sketch_dist_rows(self.h, np.asarray(idx, dtype=np.int64), self.n)
+
+    def row(self, j):
+        return self.rows([j])[0]
+
+    def condensed(self):
+        return self.ctx.sketch_dist_condensed(self.h, self.n)
+
+    def __call__(self, i, j):
+        r = self._row_cache.get(i)
+        if r is None:
+            if len(self._row_cache) > 64:
+                self._row_cache.clear()
+            r = self._row_cache[i] = self.row(i)
+        return float(r[j])
+
+
+def make_signatures_with_minhash(family, seqs):
+    """dict header -> signature (cluster.py:29-46): ONE hash function for all sequences."""
+    h = family.make_h()
+    sig = h.sketch(seqs.values()).signatures()
+    return {name: tuple(int(v) for v in sig[i]) for i, name in enumerate(seqs)}
+
+
+def _jaccard_dist_from_mash_dist(mash_dist, k):
+    """cluster.py:49-71: j = 1 / (2 exp(kD) - 1)."""
+    return 1.0 - 1.0 / (2.0 * np.exp(k * mash_dist) - 1)
+
+
+def set_max_num_processes_for_computing_distances(max_num_processes=8):
+    """Kept for interface compatibility (cluster.py:74-88); distances are computed on the device."""
+    global _cdm_max_num_processes
+    _cdm_max_num_processes = max_num_processes
+
+
+set_max_num_processes_for_computing_distances()
+
+
+def create_condensed_dist_matrix(n, dist_fn, num_processes=None):
+    """1d condensed distance matrix for scipy, float32 like the reference's shared array (cluster.py:103-195).
+    A SketchSet is evaluated on the device in one call; any other callable is the caller's own function and is
+    simply called for every pair."""
+    if isinstance(dist_fn, SketchSet):
+        assert dist_fn.n == n
+        return dist_fn.condensed()
+    out = np.zeros(int(n * (n - 1) / 2), dtype=np.float32)
+    for j in range(n):
+        for i in range(j):
+            out[i * n - i * (i + 3) // 2 + j - 1] = dist_fn(i, j)
+    return out
+
+
+def cluster_hierarchically_from_dist_matrix(dist_matrix, threshold):
+    """cluster.py:198-236: average linkage, clusters in descending order of size."""
+    from scipy.cluster import hierarchy
+    if len(dist_matrix) == 0:
+        return [[0]]
+    linkage = hierarchy.linkage(dist_matrix, method='average')
+    clusters = hierarchy.fcluster(linkage, threshold, criterion='distance')
+    first_clust_num = min(clusters)
+    num_clusters = max(clusters) + 1 - first_clust_num
+    elements_in_cluster = defaultdict(list)
+    for i, clust_num in enumerate(clusters):
+        elements_in_cluster[clust_num].append(i)
+    cluster_sizes = {c: len(elements_in_cluster[c]) for c in range(first_clust_num, num_clusters + first_clust_num)}
+    return [elements_in_cluster[c] for c, _ in sorted(cluster_sizes.items(), key=operator.itemgetter(1), reverse=True)]
+
+
+def find_connected_components(n, dist_fn, threshold, early_stop_threshold=_jaccard_dist_from_mash_dist(0.02, 12)):
+    """Connected components under `dist <= threshold` by the reference's depth-first search (cluster.py:239-355),
+    including its early-stop heuristic (a neighbour within early_stop_threshold is marked visited, not explored).
+    The Python set operations are the reference's own, so neighbours are pushed in the same order; the distances of
+    one search step (vertex j against everything not yet seen) are one row from the device."""
+    by_row = isinstance(dist_fn, SketchSet)
+    indices_to_consider = set(range(n))
+
+    def dfs(i):
+        visited_indices = set()
+        indices_to_visit = [i]
+        indices_to_visit_or_already_visited = {i}
+        while len(indices_to_visit) > 0:
+            j = indices_to_visit.pop()
+            if j in visited_indices:
+                continue
+            visited_indices.add(j)
+            possible_neighborhood = list(indices_to_consider - indices_to_visit_or_already_visited)
+            if not possible_neighborhood:
+                continue
+            ks = np.array(possible_neighborhood, dtype=np.int64)
+            if by_row:
+                dists = dist_fn.row(j)[ks]
+            else:
+                dists = np.array([dist_fn(j, k) for k in possible_neighborhood])
+            adjacent = dists <= threshold
+            early = adjacent & (dists <= early_stop_threshold)
+            marked = ks[early].tolist()
+            visited_indices.update(marked)
+            later = ks[adjacent & ~early].tolist()           # in the order of possible_neighborhood
+            indices_to_visit.extend(later)
+            indices_to_visit_or_already_visited.update(marked)
+            indices_to_visit_or_already_visited.update(later)
+        return visited_indices
+
+    previously_visited_indices = set()
+    connected_components = []
+    for i in range(n):
+        if i in previously_visited_indices:
+            continue
+        cc = dfs(i)
+        previously_visited_indices.update(cc)
+        indices_to_consider -= cc
+        connected_components.append(sorted(list(cc)))
+    connected_components.sort(key=len, reverse=True)
+    return connected_components
+
+
+def cluster_with_minhash_signatures(seqs, k=12, N=100, threshold=0.1, cluster_method='simple'):
+    """Clusters of sequence headers, largest first (cluster.py:358-430)."""
+    num_seqs = len(seqs)
+    logger.info("Producing signatures of %d sequences", num_seqs)
+    family = MinHashFamily(k, N=N)
+    h = family.make_h()
+    seq_headers = list(seqs.keys())
+    sketches = h.sketch(seqs.values())
+    jaccard_dist_threshold = _jaccard_dist_from_mash_dist(threshold, k)
+    if cluster_method == 'simple':
+        logger.info("Clustering %d sequences at Jaccard distance threshold of %f based on connected components",
+                    num_seqs, jaccard_dist_threshold)
+        clusters = find_connected_components(num_seqs, sketches, jaccard_dist_threshold)
+    elif cluster_method == 'hierarchical':
+        logger.info("Creating condensed distance matrix of %d sequences", num_seqs)
+        dist_matrix = create_condensed_dist_matrix(num_seqs, sketches)
+        logger.info("Clustering %d sequences at Jaccard distance threshold of %f using hierarchical method",
+                    num_seqs, jaccard_dist_threshold)
+        clusters = cluster_hierarchically_from_dist_matrix(dist_matrix, jaccard_dist_threshold)
+    else:
+        raise ValueError(f"Unknown cluster_method '{cluster_method}'")
+    cluster_with_minhash_signatures.last_stats = sketches.last_stats
+    return [[seq_headers[i] for i in cluster_idxs] for cluster_idxs in clusters]

@@ -329,6 +329,32 @@ int cb_neardup_filter(cb_ctx *ctx, const uint8_t *ascii, const int64_t *probe_of
                       int32_t n_tables, int32_t k_concat, int32_t kmer_size, double dist_thres,
                       int64_t *kept_first_idx, int64_t *n_kept, int64_t *n_distinct, cb_stats *stats);
 
+/* ---- genome clustering: MinHash sketches of whole sequences ---------------
+ * Replaces cluster.make_signatures_with_minhash (utils/cluster.py:29-46) with the hash function of
+ * lsh.MinHashFamily(kmer_size, N).make_h() (utils/lsh.py:74-148, md5 inner hash :106-111): for every k-mer x
+ * of a sequence, v = (a * int(md5(x).hexdigest(), 16) + b) mod (2^31 - 1); the sketch is the N smallest v in
+ * sorted order, as a multiset, and a sequence with fewer than N k-mers counts each of its k-mers
+ * ceil(N / num_kmers) times (:131-139).  a, b are the two draws of make_h (random.randint(1, p),
+ * random.randint(0, p)); the host makes them because they come from Python's `random`.
+ * Sequence i is ascii[seq_off[i] .. seq_off[i+1]); CB_ERR_ARG if one is shorter than kmer_size (the
+ * reference asserts, :117).  kmer_size <= 55, N <= 1024.
+ * stats: ms_scan_emit = hashing kernel, ms_merge = selection kernel, n_seed_lookups = bases hashed. */
+typedef struct cb_sketches cb_sketches;
+int cb_sketch_sequences(cb_ctx *ctx, const uint8_t *ascii, const int64_t *seq_off, int64_t n_seqs, int32_t kmer_size,
+                        int32_t N, uint64_t a, uint64_t b, cb_sketches **out, cb_stats *stats);
+/* Sketches computed elsewhere (n_seqs rows of N sorted values) as a device object. */
+int cb_sketches_import(cb_ctx *ctx, const uint32_t *sig, int64_t n_seqs, int32_t N, cb_sketches **out);
+/* Copy the sketches out: sig holds n_seqs * N values, row i = the signature tuple h(seq_i). */
+int cb_sketches_export(cb_ctx *ctx, const cb_sketches *sk, uint32_t *sig);
+void cb_sketches_free(cb_sketches *sk);
+/* MinHashFamily.estimate_jaccard_dist (utils/lsh.py:166-214) of sketch rows[r] against EVERY sketch:
+ * out[r * n_seqs + c], the double the reference's Python arithmetic gives (1.0 - intersect / union).  One call
+ * serves one step of find_connected_components' search (utils/cluster.py:270-290). */
+int cb_sketch_dist_rows(cb_ctx *ctx, const cb_sketches *sk, const int64_t *rows, int64_t n_rows, double *out);
+/* cluster.create_condensed_dist_matrix (utils/cluster.py:103-195): all n(n-1)/2 distances in scipy's condensed
+ * order, rounded to float32 as the reference's shared c_float array does (:141-142). */
+int cb_sketch_dist_condensed(cb_ctx *ctx, const cb_sketches *sk, float *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -426,3 +426,127 @@ def abs_pyhash(s):
 
 def minhash(s, kmer, a, b):
     return lib().orc_minhash(_b(s), len(s), kmer, a, b)
+
+
+# ---- genome clustering by MinHash sketches -- small cases only (one hashlib call per k-mer) -------
+def sketch_params():
+    """The two draws of MinHashFamily.make_h (utils/lsh.py:95-96)."""
+    p = 2 ** 31 - 1
+    a = random.randint(1, p)
+    b = random.randint(0, p)
+    return a, b
+
+
+def sketch(s, kmer_size, N, a, b):
+    """h(s) of MinHashFamily(kmer_size, N).make_h() with the md5 inner hash (utils/lsh.py:106-148): the N smallest
+    values of (a * int(md5(kmer).hexdigest(), 16) + b) mod (2^31 - 1) over the k-mer list, which is run through
+    repeatedly until at least N values have been produced; sorted, repeats kept."""
+    import hashlib
+    import heapq
+    p = 2 ** 31 - 1
+    assert kmer_size <= len(s)
+    num_kmers = len(s) - kmer_size + 1
+    one_pass = [(a * int(hashlib.md5(s[i:i + kmer_size].encode('utf-8')).hexdigest(), 16) + b) % p
+                for i in range(num_kmers)]
+    values = []
+    while len(values) < N:                       # :131-139
+        values += one_pass
+    if N == 1:
+        return (min(values),)
+    return tuple(sorted(heapq.nsmallest(N, values)))
+
+
+def sketch_jaccard_dist(hA, hB, N):
+    """MinHashFamily.estimate_jaccard_dist (utils/lsh.py:166-214)."""
+    ia = ib = inter = union = 0
+    while ia < len(hA) and ib < len(hB):
+        if union == N:
+            break
+        if hA[ia] < hB[ib]:
+            ia += 1
+        elif hA[ia] > hB[ib]:
+            ib += 1
+        else:
+            inter += 1
+            ia += 1
+            ib += 1
+        union += 1
+    return 1.0 - float(inter) / union
+
+
+def jaccard_dist_from_mash_dist(mash_dist, k):
+    """utils/cluster.py:49-71."""
+    return 1.0 - 1.0 / (2.0 * np.exp(k * mash_dist) - 1)
+
+
+def condensed_dist_matrix(sigs, N):
+    """utils/cluster.py:103-195 (float32 storage, scipy's condensed order)."""
+    n = len(sigs)
+    out = np.zeros(n * (n - 1) // 2, dtype=np.float32)
+    for j in range(n):
+        for i in range(j):
+            out[int((-1 * i * i) / 2 + i * n - 3 * i / 2 + j - 1)] = sketch_jaccard_dist(sigs[i], sigs[j], N)
+    return out
+
+
+def connected_components(n, dist_fn, threshold, early_stop_threshold=None):
+    """utils/cluster.py:239-355 without the process pool: same search, same set operations."""
+    if early_stop_threshold is None:
+        early_stop_threshold = jaccard_dist_from_mash_dist(0.02, 12)
+    indices_to_consider = set(range(n))
+
+    def dfs(i):
+        visited = set()
+        to_visit = [i]
+        seen = {i}
+        while len(to_visit) > 0:
+            j = to_visit.pop()
+            if j in visited:
+                continue
+            visited.add(j)
+            possible = list(indices_to_consider - seen)
+            for k in possible:
+                dist = dist_fn(j, k)
+                if dist <= threshold:
+                    if dist <= early_stop_threshold:
+                        visited.add(k)
+                        seen.add(k)
+                    else:
+                        to_visit.append(k)
+                        seen.add(k)
+        return visited
+
+    previously = set()
+    ccs = []
+    for i in range(n):
+        if i in previously:
+            continue
+        cc = dfs(i)
+        previously.update(cc)
+        indices_to_consider -= cc
+        ccs.append(sorted(list(cc)))
+    ccs.sort(key=len, reverse=True)
+    return ccs
+
+
+def cluster_with_minhash_signatures(seqs, k=12, N=100, threshold=0.1, cluster_method='simple'):
+    """utils/cluster.py:358-430; `seqs` is an ordered dict header -> sequence."""
+    a, b = sketch_params()
+    headers = list(seqs.keys())
+    sigs = [sketch(seqs[h], k, N, a, b) for h in headers]
+    thr = jaccard_dist_from_mash_dist(threshold, k)
+    if cluster_method == 'simple':
+        clusters = connected_components(len(sigs), lambda i, j: sketch_jaccard_dist(sigs[i], sigs[j], N), thr)
+    else:
+        from scipy.cluster import hierarchy
+        dm = condensed_dist_matrix(sigs, N)
+        if len(dm) == 0:
+            clusters = [[0]]
+        else:
+            lab = hierarchy.fcluster(hierarchy.linkage(dm, method='average'), thr, criterion='distance')
+            by = {}
+            for i, c in enumerate(lab):
+                by.setdefault(int(c), []).append(i)
+            sizes = {c: len(by[c]) for c in range(int(min(lab)), int(max(lab)) + 1)}
+            clusters = [by[c] for c, _ in sorted(sizes.items(), key=lambda t: t[1], reverse=True)]
+    return [[headers[i] for i in c] for c in clusters]

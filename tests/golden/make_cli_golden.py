@@ -42,18 +42,23 @@ CASES = {
                            ['-m', '5', '-l', '30', '-e', '50', '--filter-with-lsh-minhash', '0.6']),
     'identify': ([(6, 1500, 0.05, 8), (6, 1500, 0.05, 9)],
                  ['-pl', '60', '-m', '1', '-l', '40', '-i', '-c', '0.2', '-mt', '3', '-lt', '30']),
+    # genome clustering: a FASTA given as a LIST of generator calls holds several families
+    'cluster_simple': ([[(6, 2000, 0.03, 21), (5, 2000, 0.03, 22), (4, 2500, 0.03, 23)]],
+                       ['-pl', '75', '-m', '2', '-l', '60', '-e', '50', '--cluster-and-design-separately', '0.15']),
+    'cluster_fragments': ([[(5, 2400, 0.03, 24), (4, 2400, 0.03, 25)], (3, 1600, 0.02, 26)],
+                          ['-pl', '75', '-m', '1', '-l', '60', '--cluster-and-design-separately', '0.1',
+                           '--cluster-from-fragments', '800']),
+    'cluster_skip_set_cover': ([[(4, 1500, 0.03, 27), (4, 1500, 0.03, 28)]],
+                               ['-pl', '75', '-ps', '25', '--skip-set-cover', '--cluster-and-design-separately', '0.2',
+                                '--cluster-and-design-separately-method', 'hierarchical']),
+    'cluster_adapters': ([[(5, 1800, 0.04, 29), (5, 1800, 0.04, 30)]],
+                         ['-pl', '75', '-m', '2', '-l', '60', '--cluster-and-design-separately', '0.15',
+                          '--add-adapters']),
 }
 
 
 def write_inputs(tmp, spec):
-    paths = []
-    for gi, (n, length, div, seed) in enumerate(spec):
-        fn = os.path.join(tmp, 'g%d.fasta' % gi)
-        with open(fn, 'w') as f:
-            for i, s in enumerate(helpers.synthetic_genomes(n, length, div, seed)):
-                f.write('>g%d\n%s\n' % (i, s))
-        paths.append(fn)
-    return paths
+    return helpers.write_cli_inputs(tmp, spec)
 
 
 def main():
@@ -61,7 +66,12 @@ def main():
     ref_design = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(ref_design)
     out = {}
+    only = sys.argv[1:]
+    if only:                                       # re-record the named cases only, keep the others
+        out = json.load(open(os.path.join(HERE, 'cli.json')))
     for name, (gen, cli) in CASES.items():
+        if only and name not in only:
+            continue
         with tempfile.TemporaryDirectory() as tmp:
             paths = write_inputs(tmp, gen)
             fasta = os.path.join(tmp, 'out.fasta')

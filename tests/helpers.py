@@ -149,3 +149,21 @@ def synthetic_taxa(n_taxa, genomes_per_taxon, seed=4, n_clades=10, clade_div=0.0
         groups.append([letters[diverge(clades[i % n_clades], strain_div)].tobytes().decode()
                        for i in range(genomes_per_taxon)])
     return groups
+
+
+def write_cli_inputs(tmp, spec):
+    """FASTA files for a command-line case: one file per entry of `spec`; an entry is one generator call
+    (n_genomes, length, divergence, seed) or a list of them (several families in one file)."""
+    import os
+    paths = []
+    for gi, entry in enumerate(spec):
+        calls = entry if isinstance(entry[0], (list, tuple)) else [entry]
+        fn = os.path.join(str(tmp), 'g%d.fasta' % gi)
+        with open(fn, 'w') as f:
+            i = 0
+            for n, length, div, seed in calls:
+                for s in synthetic_genomes(n, length, div, seed):
+                    f.write('>g%d\n%s\n' % (i, s))
+                    i += 1
+        paths.append(fn)
+    return paths

@@ -25,16 +25,11 @@ design.main(args)
 '''
 
 
-@pytest.mark.parametrize('name', ['config1', 'zika_small', 'two_groups_minhash', 'identify'])
+@pytest.mark.parametrize('name', ['config1', 'zika_small', 'two_groups_minhash', 'identify', 'cluster_simple',
+                                  'cluster_fragments', 'cluster_skip_set_cover', 'cluster_adapters'])
 def test_design_cli_matches_reference_fasta(tmp_path, name):
     want = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'cli.json')))[name]
-    paths = []
-    for gi, (n, length, div, seed) in enumerate(want['gen']):
-        fn = tmp_path / ('g%d.fasta' % gi)
-        with open(fn, 'w') as f:
-            for i, s in enumerate(helpers.synthetic_genomes(n, length, div, seed)):
-                f.write('>g%d\n%s\n' % (i, s))
-        paths.append(str(fn))
+    paths = helpers.write_cli_inputs(tmp_path, want['gen'])
     out = str(tmp_path / 'out.fasta')
     argv = paths + want['cli'] + ['-o', out]
     env = dict(os.environ, PYTHONHASHSEED='0')

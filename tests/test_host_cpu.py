@@ -306,3 +306,61 @@ def test_probe_batch_tiling_equals_candidate_probes():
     assert ProbeBatch.from_sequences(['ACGT'], 10, 5) is None        # shorter than a probe: per-object path
     b = ProbeBatch.from_sequences(['ACGTACGTAC', 'TTTTTTTTTTTT'], 10, 5)
     assert b.take([1, 0]).strs() == ['TTTTTTTTTT', 'ACGTACGTAC'] and len(b) == 3
+
+
+def test_cluster_host_logic_on_the_reference_test_vectors():
+    """The toy distance functions of the reference's catch/utils/tests/test_cluster.py (its expected values restated
+    as data): connected components, condensed matrix layout, hierarchical clustering.  No device involved: a plain
+    callable is the caller's own distance function."""
+    from catch_b200.utils import cluster
+    seqs = ['a', 'b', 'x', 'm', 'c', 'o', 'n', 'z', 'w', 'y', 'v', 'd', 'k']
+
+    def dist(i, j):
+        return abs(ord(seqs[i]) - ord(seqs[j]))
+    assert cluster.find_connected_components(len(seqs), dist, 1) == [[2, 7, 8, 9, 10], [0, 1, 4, 11], [3, 5, 6], [12]]
+    seqs = ['a', 'c', 'b', 'c']
+    assert cluster.find_connected_components(4, dist, 1) == [[0, 1, 2, 3]]
+    seqs = ['a', 'z', 'm']
+    assert sorted(cluster.find_connected_components(3, dist, 1)) == [[0], [1], [2]]
+    assert cluster.find_connected_components(0, dist, 1) == []
+    m2 = np.array([[0, 1, 100], [1, 0, 2], [100, 2, 0]])
+    cond = cluster.create_condensed_dist_matrix(3, lambda i, j: m2[i][j])
+    assert cond.dtype == np.float32 and cond.tolist() == [1.0, 100.0, 2.0]
+    assert cluster.cluster_hierarchically_from_dist_matrix(cond, 10) == [[0, 1], [2]]
+    d = {(0, 1): 100, (0, 2): 100, (1, 2): 1}
+    cond = cluster.create_condensed_dist_matrix(3, lambda i, j: d[(i, j)])
+    assert cluster.cluster_hierarchically_from_dist_matrix(cond, 10) == [[1, 2], [0]]
+    assert cluster.cluster_hierarchically_from_dist_matrix(cluster.create_condensed_dist_matrix(1, None), 10) == [[0]]
+    assert cluster._jaccard_dist_from_mash_dist(0.1, 12) == 1.0 - 1.0 / (2.0 * np.exp(12 * 0.1) - 1)
+
+
+def test_fasta_reader_matches_reference_fixtures(tmp_path):
+    """the native FASTA parser (and the Python line loop behind it) against outputs of the reference's
+    seq_io.read_fasta recorded by tests/golden/make_f4_golden.py."""
+    import base64
+    import gzip
+    from collections import OrderedDict
+    from catch_b200.utils import seq_io
+    from tests import golden_io
+    assert seq_io._fastpack is not None and hasattr(seq_io._fastpack, 'parse_fasta')
+    n_ok = 0
+    for c in golden_io.load('f4_reference.json.gz'):
+        fn = str(tmp_path / ('t.fasta.gz' if c['gz'] else 't.fasta'))
+        with (gzip.open(fn, 'wb') if c['gz'] else open(fn, 'wb')) as f:
+            f.write(base64.b64decode(c['data']))
+        for reader in (seq_io.read_fasta, seq_io._read_fasta_lines):
+            if c['out'] == 'AssertionError':
+                with pytest.raises(AssertionError):
+                    reader(fn, **c['kw'])
+            else:
+                got = reader(fn, **c['kw'])
+                assert isinstance(got, OrderedDict)
+                assert [[n, s] for n, s in got.items()] == c['out']
+                n_ok += 1
+    assert n_ok > 300
+    # non-ASCII bytes take the line loop; one Genome per record
+    fn = str(tmp_path / 'u.fasta')
+    with open(fn, 'w', encoding='utf-8') as f:
+        f.write('>g\u00e9nome\nacgt-y\n>b\nAC\nGT\n')
+    assert list(seq_io.read_fasta(fn).items()) == [('g\u00e9nome', 'ACGTN'), ('b', 'ACGT')]
+    assert [g.seqs for g in seq_io.read_genomes_from_fasta(fn)] == [['ACGTN'], ['ACGT']]

@@ -133,3 +133,25 @@ def test_scale_golden_inputs_match_the_generators():
     c3 = helpers.tile_candidates(segs, c['pl'], c['ps'])
     assert hashlib.md5('\n'.join(c3).encode()).hexdigest() == c['cands_md5']
     assert 0 < len(c['kept_idx']) < len(c3) and len(c['picks']) > 300
+
+
+def test_cluster_oracle_matches_reference_fixtures():
+    """sketches (md5 inner hash), distance estimates, condensed matrix and clusters of the oracle against
+    the outputs of the reference recorded by tests/golden/make_f3_golden.py."""
+    gold = golden_io.load('f3_reference.json.gz')
+    for c in gold['sketches']:
+        sigs = [list(O.sketch(s, c['k'], c['N'], c['a'], c['b'])) for s in c['seqs'].values()]
+        assert sigs == c['sigs'], c['name']
+        n = len(sigs)
+        if n <= 12:
+            for i in range(n):
+                for j in range(n):
+                    assert O.sketch_jaccard_dist(sigs[i], sigs[j], c['N']) == c['dist'][i][j]
+            assert O.condensed_dist_matrix(sigs, c['N']).tolist() == c['condensed']
+    for c in gold['clusters']:
+        if len(c['seqs']) > 40:
+            continue
+        random.seed(c['seed'])
+        got = O.cluster_with_minhash_signatures(c['seqs'], k=c['k'], N=c['N'], threshold=c['threshold'],
+                                                     cluster_method=c['method'])
+        assert got == c['clusters'], (c['name'], c['method'], c['threshold'])
