@@ -371,6 +371,51 @@ def config4_vall(ctx, n_taxa, n_genomes, dist=None, local_rank=0, reps=2):
                         'groupings over ranks, largest first; no data-path collective; same taxa at every N (strong)'}
 
 
+def cluster_f3(ctx, n_taxa=4, n_genomes=333, reps=3, sm_mhz=None):
+    """cluster_with_minhash_signatures (the pre-partitioner of design_large.py) on the genomes of a few
+    V-All-shape taxa thrown together: sketches (md5 per 12-mer, bottom-100 per genome) and distance rows on the
+    device, the search on the host.  The oracle's sketch (hashlib + heapq, one core) is timed on a few genomes."""
+    from catch_b200.utils import cluster
+    from oracle import oracle
+    groups = helpers.synthetic_taxa(n_taxa, n_genomes, seed=4)
+    seqs = {'t%d_%d' % (t, i): s for t, g in enumerate(groups) for i, s in enumerate(g)}
+    bases = sum(map(len, seqs.values()))
+    best, st, clusters = None, None, None
+    for _ in range(reps):
+        random.seed(RNG_SEED)
+        t = time.perf_counter()
+        clusters = cluster.cluster_with_minhash_signatures(seqs, threshold=0.15)
+        dt = time.perf_counter() - t
+        if best is None or dt < best:
+            best, st = dt, cluster.cluster_with_minhash_signatures.last_stats
+    # md5 of one 12-byte block + the affine map mod 2^31 - 1: 365 SASS instructions per k-mer in
+    # sketch_hash_kernel<12> (cuobjdump -sass: 78 IADD3, 75 LEA.HI = rotate-and-add, 74 LOP3, 29 IMAD, ...; 64 md5
+    # steps at ~3.6 instructions each), all on the integer pipe.  Ceilings: the rate the same GPU sustains on
+    # LOP3 + LEA.HI chains (cb_intop_rate, the scan kernel's ceiling) and the issue limit of 128 lanes per SM-clock
+    ops = bases * 365
+    hash_s = st['ms_scan_emit'] / 1e3
+    peak_ops = ctx.intop_rate()
+    issue = 148 * 128 * (sm_mhz or 1965.0) * 1e6
+    sample = list(seqs.values())[:8]
+    random.seed(RNG_SEED)
+    a, b = oracle.sketch_params()
+    t = time.perf_counter()
+    want = [oracle.sketch(s, 12, 100, a, b) for s in sample]
+    cpu_s = time.perf_counter() - t
+    got = cluster.SketchFunction(12, 100, a, b).sketch(sample, ctx).signatures().tolist()
+    return {'workload': 'genomes of %d V-All-shape taxa x %d (%d sequences, %d bp), k=12 N=100 threshold 0.15, method simple'
+                        % (n_taxa, n_genomes, len(seqs), bases),
+            'clusters': [len(c) for c in clusters], 'wall_ms': best * 1e3, 'device_ms': st['ms_total'],
+            'hash_kernel_ms': st['ms_scan_emit'], 'select_kernel_ms': st['ms_merge'],
+            'bases_per_s_e2e': bases / best, 'bases_per_s_hash_kernel': bases / hash_s,
+            'int_ops': {'achieved_gops': ops / hash_s / 1e9, 'peak_gops': peak_ops / 1e9, 'frac': ops / hash_s / peak_ops,
+                        'issue_limit_gops': issue / 1e9, 'frac_of_issue_limit': ops / hash_s / issue,
+                        'instructions_per_kmer': 365},
+            'cpu_port': {'bases_per_s': sum(map(len, sample)) / cpu_s, 'cores': 1,
+                         'sample': 'first %d genomes (hashlib.md5 + heapq)' % len(sample),
+                         'identical': got == [list(x) for x in want]}}
+
+
 def emit_other_workload(args, ctx):
     """--workload influenza | vall | sweep as the main line (single GPU)."""
     t0 = time.perf_counter()
@@ -666,6 +711,10 @@ def main():
             configs['config4_vall'] = config4_vall(ctx, args.vall_taxa, args.vall_genomes)
         except Exception as e:
             configs['config4_error'] = repr(e)
+        try:
+            configs['cluster_f3'] = cluster_f3(ctx, sm_mhz=(clocks or {}).get('sm_mhz'))
+        except Exception as e:
+            configs['cluster_f3_error'] = repr(e)
         out['configs'] = configs
     if extras_ok and world > 1:
         try:

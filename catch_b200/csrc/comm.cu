@@ -7,12 +7,19 @@
 //
 // NCCL is resolved at run time (dlopen of libnccl.so.2) so that single-GPU use neither needs nor
 // loads it, and so that a process that already carries an NCCL (e.g. torch's) shares that copy.
+// The handful of NCCL types the calls below need are declared here (their layout and values are
+// part of NCCL 2's stable ABI), so building the library does not need the NCCL headers either.
 #include <dlfcn.h>
-#include <nccl.h>
 
 #include <cstring>
 
 #include "internal.cuh"
+
+typedef struct { char internal[128]; } ncclUniqueId;      // NCCL_UNIQUE_ID_BYTES
+typedef struct ncclComm *ncclComm_t;
+typedef int ncclResult_t;                                   // ncclSuccess == 0
+typedef int ncclDataType_t;
+enum { ncclSuccess = 0, ncclInt64 = 4, ncclUint64 = 5 };
 
 namespace {
 

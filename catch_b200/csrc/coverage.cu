@@ -835,22 +835,26 @@ constexpr int MERGE_SMEM_CAP = 4096;
 
 __device__ __forceinline__ void bitonic_sort(uint64_t *a, uint32_t n)
 {
-    uint32_t n2 = 1;
-    while (n2 < n) n2 <<= 1;
-    for (uint32_t size = 2; size <= n2; size <<= 1) {
+    // all sizes and strides are powers of two: indices come from shifts and masks (ls = log2 size, lt = log2 stride)
+    int ln2 = 0;
+    while ((1u << ln2) < n) ln2++;
+    const uint32_t half = (1u << ln2) >> 1;
+    for (int ls = 1; ls <= ln2; ls++) {
         // first step of each merge: compare i with its mirror inside the block of `size`
-        for (uint32_t t = threadIdx.x; t < n2 / 2; t += blockDim.x) {
-            const uint32_t blk = t / (size / 2), o = t % (size / 2);
-            const uint32_t i = blk * size + o, j = blk * size + size - 1 - o;
+        const uint32_t size = 1u << ls;
+        for (uint32_t t = threadIdx.x; t < half; t += blockDim.x) {
+            const uint32_t base = (t >> (ls - 1)) << ls, o = t & ((size >> 1) - 1u);
+            const uint32_t i = base + o, j = base + size - 1u - o;
             if (j < n) {
                 const uint64_t x = a[i], y = a[j];
                 if (x > y) { a[i] = y; a[j] = x; }
             }
         }
         __syncthreads();
-        for (uint32_t stride = size / 4; stride >= 1; stride >>= 1) {
-            for (uint32_t t = threadIdx.x; t < n2 / 2; t += blockDim.x) {
-                const uint32_t i = (t / stride) * stride * 2 + (t % stride), j = i + stride;
+        for (int lt = ls - 2; lt >= 0; lt--) {
+            const uint32_t stride = 1u << lt;
+            for (uint32_t t = threadIdx.x; t < half; t += blockDim.x) {
+                const uint32_t i = ((t >> lt) << (lt + 1)) + (t & (stride - 1u)), j = i + stride;
                 if (j < n) {
                     const uint64_t x = a[i], y = a[j];
                     if (x > y) { a[i] = y; a[j] = x; }
@@ -914,9 +918,11 @@ __device__ __forceinline__ uint32_t warp_merge_sorted(const uint64_t *a, uint64_
 // Probes with more than MERGE_WARP_CAP ranges: one block per probe (see above).
 __global__ void __launch_bounds__(MERGE_THREADS)
 merge_kernel(const int64_t *__restrict__ rec_off, uint64_t *__restrict__ rec, int64_t n_probes,
-             uint32_t *__restrict__ n_merged, uint32_t *__restrict__ max_len, uint32_t min_n)
+             uint32_t *__restrict__ n_merged, uint32_t *__restrict__ max_len, uint32_t min_n,
+             const unsigned int *__restrict__ n_large)
 {
     __shared__ uint64_t s_rec[MERGE_SMEM_CAP];
+    if (n_large && *n_large == 0u) return;          // the warp kernel took every probe (the usual case)
     uint32_t local_max = 0;
     for (int64_t p = blockIdx.x; p < n_probes; p += gridDim.x) {
         const int64_t o0 = rec_off[p];
@@ -969,21 +975,24 @@ merge_warp_kernel(const int64_t *__restrict__ rec_off, uint64_t *__restrict__ re
         uint64_t *g = rec + o0;
         for (uint32_t i = lane; i < n; i += 32) a[i] = g[i];
         __syncwarp();
-        uint32_t n2 = 1;
-        while (n2 < n) n2 <<= 1;
-        for (uint32_t size = 2; size <= n2; size <<= 1) {
-            for (uint32_t t = lane; t < n2 / 2; t += 32) {
-                const uint32_t blk = t / (size / 2), o = t % (size / 2);
-                const uint32_t i = blk * size + o, j = blk * size + size - 1 - o;
+        int ln2 = 0;
+        while ((1u << ln2) < n) ln2++;
+        const uint32_t half = (1u << ln2) >> 1;
+        for (int ls = 1; ls <= ln2; ls++) {
+            const uint32_t size = 1u << ls;
+            for (uint32_t t = lane; t < half; t += 32) {
+                const uint32_t base = (t >> (ls - 1)) << ls, o = t & ((size >> 1) - 1u);
+                const uint32_t i = base + o, j = base + size - 1u - o;
                 if (j < n) {
                     const uint64_t x = a[i], y = a[j];
                     if (x > y) { a[i] = y; a[j] = x; }
                 }
             }
             __syncwarp();
-            for (uint32_t stride = size / 4; stride >= 1; stride >>= 1) {
-                for (uint32_t t = lane; t < n2 / 2; t += 32) {
-                    const uint32_t i = (t / stride) * stride * 2 + (t % stride), j = i + stride;
+            for (int lt = ls - 2; lt >= 0; lt--) {
+                const uint32_t stride = 1u << lt;
+                for (uint32_t t = lane; t < half; t += 32) {
+                    const uint32_t i = ((t >> lt) << (lt + 1)) + (t & (stride - 1u)), j = i + stride;
                     if (j < n) {
                         const uint64_t x = a[i], y = a[j];
                         if (x > y) { a[i] = y; a[j] = x; }
@@ -1033,16 +1042,14 @@ int launch_merge(cb_ctx *ctx, const int64_t *d_roff, uint64_t *d_sorted, int64_t
     merge_warp_kernel<<<(unsigned)g, MERGE_WARPS * 32, 0, st>>>(d_roff, d_sorted, P, d_nmerged, d_maxlen, d_large.p);
     ctx->launches++;
     CB_CUDA(ctx, cudaGetLastError());
-    unsigned int h_large = 0;
-    CB_CUDA(ctx, cudaMemcpyAsync(&h_large, d_large.p, sizeof h_large, cudaMemcpyDeviceToHost, st));
-    CB_CUDA(ctx, cudaStreamSynchronize(st));
-    if (h_large) {
-        int64_t gb = P < (int64_t)ctx->sm_count * 8 ? P : (int64_t)ctx->sm_count * 8;
-        merge_kernel<<<(unsigned)gb, MERGE_THREADS, 0, st>>>(d_roff, d_sorted, P, d_nmerged, d_maxlen,
-                                                            (uint32_t)MERGE_WARP_CAP + 1u);
-        ctx->launches++;
-        CB_CUDA(ctx, cudaGetLastError());
-    }
+    // probes with more ranges than the warp kernel takes: decided on the device (no host round trip in the
+    // middle of stage A); the blocks leave at once when there is none
+    int64_t gb = P < (int64_t)ctx->sm_count * 8 ? P : (int64_t)ctx->sm_count * 8;
+    if (gb < 1) gb = 1;
+    merge_kernel<<<(unsigned)gb, MERGE_THREADS, 0, st>>>(d_roff, d_sorted, P, d_nmerged, d_maxlen,
+                                                        (uint32_t)MERGE_WARP_CAP + 1u, d_large.p);
+    ctx->launches++;
+    CB_CUDA(ctx, cudaGetLastError());
     return CB_OK;
 }
 
@@ -1240,19 +1247,38 @@ int cb_coverage_impl(cb_ctx *ctx, const cb_probes *probes, const cb_targets *tar
     int64_t grid64 = sp.n_tiles < (int64_t)ctx->sm_count * per_sm ? sp.n_tiles : (int64_t)ctx->sm_count * per_sm;
     const int grid = (int)grid64;
 
-    // ---- K3 pre-pass: upper bound on the number of candidate hits (sizes the range list)
+    // ---- K3 pre-pass: upper bound on the number of candidate hits (sizes the range list).  Skipped when the
+    // previous scan of this context ran with the same parameters: then the list gets twice the room its density of
+    // ranges per (probe x target base) asks for, and the pre-pass only runs if that overflows.
     unsigned long long h_ctr[8];
-    t_cnt.start();
-    CB_CUDA(ctx, cudaMemsetAsync(d_ctr.p, 0, sizeof(unsigned long long) * 8, st));
-    sp.count_only = 1;
-    CB_TRY(launch_scan_nw(ctx, nw, sp, grid));
-    t_cnt.stop();
-    CB_CUDA(ctx, cudaMemcpyAsync(h_ctr, d_ctr.p, sizeof h_ctr, cudaMemcpyDeviceToHost, st));
-    CB_CUDA(ctx, cudaStreamSynchronize(st));
-    const unsigned long long hits_ub = h_ctr[1];
-    // one range at most per surviving hit (one hit per mismatch-free run that holds a seed): start with a
-    // third of the candidate hits and fall back to the hard bound if the list overflows
-    unsigned long long cap = hits_ub / 3 + 4096;
+    unsigned long long hits_ub = 0;
+    bool counted = false;
+    auto count_pass = [&]() -> int {
+        t_cnt.start();
+        CB_CUDA(ctx, cudaMemsetAsync(d_ctr.p, 0, sizeof(unsigned long long) * 8, st));
+        sp.count_only = 1;
+        CB_TRY(launch_scan_nw(ctx, nw, sp, grid));
+        t_cnt.stop();
+        CB_CUDA(ctx, cudaMemcpyAsync(h_ctr, d_ctr.p, sizeof h_ctr, cudaMemcpyDeviceToHost, st));
+        CB_CUDA(ctx, cudaStreamSynchronize(st));
+        hits_ub = h_ctr[1];
+        counted = true;
+        return CB_OK;
+    };
+    const int32_t dkey[5] = {hp->mismatches, hp->lcf_thres, hp->island_of_exact_match, hp->k,
+                             (int32_t)probes->max_len};
+    const double pairs_scanned = (double)(probe_hi - probe_lo) * (double)targets->total_bases;
+    const bool hinted = ctx->range_density > 0.0 && memcmp(dkey, ctx->range_density_key, sizeof dkey) == 0 &&
+                        !getenv("CB_SCAN_PREPASS");
+    unsigned long long cap;
+    if (hinted) {
+        cap = (unsigned long long)(2.0 * ctx->range_density * pairs_scanned) + 65536ull;
+    } else {
+        CB_TRY(count_pass());
+        // one range at most per surviving hit (one hit per mismatch-free run that holds a seed): start with a
+        // third of the candidate hits and fall back to the hard bound if the list overflows
+        cap = hits_ub / 3 + 4096;
+    }
 
     // ---- K3 scan
     DevBuf<uint4> d_rec;
@@ -1271,7 +1297,12 @@ int cb_coverage_impl(cb_ctx *ctx, const cb_probes *probes, const cb_targets *tar
         n_raw = h_ctr[4];
         if (n_raw <= cap) break;
         if (attempt == 1) return cb_fail(ctx, CB_ERR_STATE, "range list overflow after retry");
+        if (!counted) CB_TRY(count_pass());
         cap = hits_ub + 4096;
+    }
+    if (pairs_scanned > 0) {
+        ctx->range_density = (double)n_raw / pairs_scanned;
+        memcpy(ctx->range_density_key, dkey, sizeof dkey);
     }
     t_emit.stop();
     if (n_raw >= 0xfffffff0ull * 16ull) return cb_fail(ctx, CB_ERR_UNSUPPORTED, "too many cover ranges");
@@ -1285,7 +1316,7 @@ int cb_coverage_impl(cb_ctx *ctx, const cb_probes *probes, const cb_targets *tar
         CB_CUDA(ctx, cudaStreamSynchronize(st));
         if (stats) {
             stats->ms_seed_index = t_idx.ms();
-            stats->ms_scan_count = t_cnt.ms();
+            stats->ms_scan_count = counted ? t_cnt.ms() : 0.0;
             stats->ms_scan_emit = t_emit.ms();
             stats->n_seed_entries = n_entries;
             stats->n_candidate_hits = (int64_t)h_ctr[1];
@@ -1299,9 +1330,7 @@ int cb_coverage_impl(cb_ctx *ctx, const cb_probes *probes, const cb_targets *tar
 
     // ---- bucket by probe, K4 merge
     t_merge.start();
-    int64_t n_raw_chk = 0;
-    CB_TRY(cb_exclusive_scan_u32_to_i64(ctx, d_rcount.p, d_roff.p, P, &n_raw_chk));
-    if ((unsigned long long)n_raw_chk != n_raw) return cb_fail(ctx, CB_ERR_STATE, "range count mismatch");
+    CB_TRY(cb_exclusive_scan_u32_to_i64(ctx, d_rcount.p, d_roff.p, P, nullptr));
     DevBuf<uint64_t> d_sorted;
     DevBuf<uint32_t> d_nmerged, d_maxlen;
     CB_CUDA(ctx, d_sorted.alloc((size_t)n_raw));
@@ -1328,7 +1357,7 @@ int cb_coverage_impl(cb_ctx *ctx, const cb_probes *probes, const cb_targets *tar
     CB_CUDA(ctx, cudaStreamSynchronize(st));
     if (stats) {
         stats->ms_seed_index = t_idx.ms();
-        stats->ms_scan_count = t_cnt.ms();
+        stats->ms_scan_count = counted ? t_cnt.ms() : 0.0;
         stats->ms_scan_emit = t_emit.ms();
         stats->ms_merge = t_merge.ms();
         stats->ms_total = t_all.ms();

@@ -49,6 +49,10 @@ struct cb_ctx {
     int xrank = 0, xn_ranks = 1;
     int xgrid_limit = 0;          // > 0: cap on the persistent kernel's grid (several ranks sharing one device)
     bool xarea_poisoned = false;
+    // stage A: ranges emitted per (probe x target base) by the last scan and the parameters it ran with; sizes the
+    // range list of the next scan with the same parameters without the counting pre-pass (see cb_coverage_impl)
+    double range_density = 0.0;
+    int32_t range_density_key[5] = {-1, -1, -1, -1, -1};
 };
 
 struct cb_targets {

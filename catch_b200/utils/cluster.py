@@ -13,6 +13,7 @@ Host work kept here, because it is interpreter state or third-party code the ref
     the order in which neighbours are pushed -- and with it the effect of the early-stop heuristic -- is the same;
   * average-linkage clustering is scipy's (`hierarchy.linkage` / `fcluster`, :213-214).
 """
+import ctypes
 import logging
 import operator
 import random
@@ -21,6 +22,7 @@ from collections import defaultdict
 import numpy as np
 
 from catch_b200 import _lib
+from catch_b200 import coverage as cov
 
 logger = logging.getLogger(__name__)
 
@@ -66,12 +68,18 @@ class SketchFunction:
             assert self.kmer_size <= len(s)                  # utils/lsh.py:117
             _warn_short(self.kmer_size, self.N, len(s))
         ctx = ctx or _lib.default_context()
-        lens = np.fromiter((len(s) for s in seqs), dtype=np.int64, count=len(seqs))
+        # the sequences go back to back into the context's page-locked staging memory (one threaded copy pass,
+        # true asynchronous DMA afterwards); without the C helper, through one bytes object
+        staged = cov.gather_staged(ctx, 0, seqs)
+        if staged is not None:
+            raw, lens, total = staged
+            if total and int(np.ctypeslib.as_array(ctypes.cast(raw, ctypes.POINTER(ctypes.c_uint8)), shape=(total,)).max()) > 127:
+                raise ValueError("sequences must be ASCII")      # md5 is taken over the UTF-8 bytes (utils/lsh.py:110)
+        else:
+            raw = ''.join(seqs).encode('ascii')
+            lens = np.fromiter((len(s) for s in seqs), dtype=np.int64, count=len(seqs))
         off = np.zeros(len(seqs) + 1, dtype=np.int64)
-        np.cumsum(lens, out=off[1:])
-        raw = ''.join(seqs).encode('utf-8')
-        if len(raw) != int(off[-1]):
-            raise ValueError("sequences must be ASCII")
+        np.cumsum(lens, dtype=np.int64, out=off[1:])
         h, st = ctx.sketch_sequences(raw, off, self.kmer_size, self.N, self.a, self.b)
         return SketchSet(ctx, h, len(seqs), self.N, st)
 
@@ -113,6 +121,22 @@ class SketchSet:
 
     def row(self, j):
         return self.rows([j])[0]
+
+    def row_cached(self, j, soon=()):
+        """Row j for a search that asks for every row at most once: a miss fetches j together with the rows of
+        `soon` (vertices the caller expects to ask for next) in ONE library call; a row leaves the cache when
+        it is handed out."""
+        r = self._row_cache.pop(j, None)
+        if r is None:
+            if len(self._row_cache) > 256:           # rows fetched ahead for vertices that were never visited
+                self._row_cache.clear()
+            want = [j] + [k for k in soon if k != j and k not in self._row_cache]
+            budget = max(1, min(len(want), (64 << 20) // max(8 * self.n, 1)))      # at most 64 MB of rows per call
+            got = self.rows(want[:budget])
+            for k, row in zip(want[1:budget], got[1:]):
+                self._row_cache[k] = row
+            r = got[0]
+        return r
 
     def condensed(self):
         return self.ctx.sketch_dist_condensed(self.h, self.n)
@@ -199,7 +223,10 @@ def find_connected_components(n, dist_fn, threshold, early_stop_threshold=_jacca
                 continue
             ks = np.array(possible_neighborhood, dtype=np.int64)
             if by_row:
-                dists = dist_fn.row(j)[ks]
+                # the rows of the vertices on top of the stack come along (they are asked for next, unless a
+                # neighbour marks them visited first); an empty stack means the outer loop picks the next start
+                soon = indices_to_visit[:-65:-1] or [k for k in range(j + 1, min(n, j + 65)) if k in indices_to_consider]
+                dists = dist_fn.row_cached(j, soon)[ks]
             else:
                 dists = np.array([dist_fn(j, k) for k in possible_neighborhood])
             adjacent = dists <= threshold
