@@ -922,7 +922,7 @@ merge_kernel(const int64_t *__restrict__ rec_off, uint64_t *__restrict__ rec, in
              const unsigned int *__restrict__ n_large)
 {
     __shared__ uint64_t s_rec[MERGE_SMEM_CAP];
-    if (n_large && *n_large == 0u) return;          // the warp kernel took every probe (the usual case)
+    if (n_large && (*n_large & 1u) == 0u) return;   // the warp kernels took every probe (the usual case)
     uint32_t local_max = 0;
     for (int64_t p = blockIdx.x; p < n_probes; p += gridDim.x) {
         const int64_t o0 = rec_off[p];
@@ -950,65 +950,170 @@ merge_kernel(const int64_t *__restrict__ rec_off, uint64_t *__restrict__ rec, in
     }
 }
 
-// Probes with at most MERGE_WARP_CAP ranges (all of them in the usual one-range-per-genome case):
-// one WARP per probe, the same normalised bitonic network in the warp's slice of shared memory
-// with __syncwarp between the steps -- no block barrier anywhere, eight probes in flight per CTA.
-constexpr int MERGE_WARP_CAP = 1024;     // the scan emits one range per (probe, diagonal, run): ~260 per probe at Zika scale,
-constexpr int MERGE_WARPS = 4;           // a few probes several hundred; 4 x 1024 x 8 B = 32 KB of shared memory per CTA
+// Probes with at most MERGE_WARP_CAP ranges (all of them in the usual one-range-per-genome case): one WARP per
+// probe, everything in registers.  Element i of the probe's list lives in register i % EPL of lane i / EPL (padded
+// with +inf to 32 * EPL elements): the steps of the bitonic network with a stride below EPL are compare-exchanges
+// between registers of the same lane, only the strides of EPL and more (15 of the 45 steps of a 512-element list)
+// go through warp shuffles; the merge of the sorted list is a sequential pass of every lane over its own EPL
+// consecutive ranges with three warp scans in between.  No shared memory, no barrier.
+constexpr int MERGE_WARP_CAP = 1024;     // the scan emits one range per (probe, diagonal, run): ~260 per probe at Zika scale
+constexpr int MERGE_WARPS = 4;
 
-__global__ void __launch_bounds__(MERGE_WARPS * 32)
+// The size loop stays rolled -- fully unrolled, the network of a 512-element list is ~100 KB of straight-line code
+// per variant and the warps of an SM, each at a different place in it, starve on instruction fetch (measured: 3.6x
+// slower) -- only the loops over a lane's registers are unrolled.
+template <int EPL>
+__device__ __forceinline__ void warp_bitonic_regs(uint64_t (&v)[EPL], int lane)
+{
+#pragma unroll 1
+    for (int k = 2; k <= 32 * EPL; k <<= 1) {
+        // ascending iff bit k of the element index is clear; for k >= EPL that is a property of the lane
+#pragma unroll 1
+        for (int j = k >> 1; j >= EPL; j >>= 1) {
+            const int jl = j / EPL;
+            const bool keep_min = ((lane & jl) == 0) == (((lane * EPL) & k) == 0);
+#pragma unroll
+            for (int r = 0; r < EPL; r++) {
+                const uint64_t mine = v[r];
+                const uint64_t other = __shfl_xor_sync(0xffffffffu, mine, jl);
+                v[r] = (keep_min == (other < mine)) ? other : mine;
+            }
+        }
+#pragma unroll
+        for (int J = EPL / 2; J >= 1; J >>= 1) {
+            if (J < k) {
+#pragma unroll
+                for (int r = 0; r < EPL; r++) {
+                    if ((r & J) == 0) {
+                        const bool up = ((lane * EPL + r) & k) == 0;
+                        const uint64_t a = v[r], b = v[r | J];
+                        const bool sw = up == (a > b);
+                        v[r] = sw ? b : a;
+                        v[r | J] = sw ? a : b;
+                    }
+                }
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t warp_excl_max(uint32_t x, int lane)
+{
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x = max(x, t);
+    }
+    x = __shfl_up_sync(0xffffffffu, x, 1);
+    return lane == 0 ? 0u : x;
+}
+
+// Sort + merge of one probe's n ranges (n <= 32 * EPL) by one warp; the merged ranges are written to the front of
+// g (utils/interval.py:304-314: a range joins the current one iff start <= curr_end).  Returns their number.
+template <int EPL>
+__device__ __forceinline__ uint32_t warp_sort_merge(uint64_t *__restrict__ g, uint32_t n, int lane, uint32_t &local_max)
+{
+    uint64_t v[EPL];
+#pragma unroll
+    for (int r = 0; r < EPL; r++) {                  // any element may start in any slot: coalesced loads
+        const uint32_t i = (uint32_t)(r * 32 + lane);
+        v[r] = i < n ? g[i] : ~0ull;
+    }
+    warp_bitonic_regs<EPL>(v, lane);
+    // lane L now holds the elements [L * EPL, (L + 1) * EPL) of the sorted list; starts of ranges are < 2^32 - 1
+    const uint32_t first = (uint32_t)(lane * EPL);
+    // largest end before this lane's elements
+    uint32_t lane_max = 0;
+#pragma unroll
+    for (int r = 0; r < EPL; r++)
+        if (first + r < n) lane_max = max(lane_max, (uint32_t)v[r]);
+    const uint32_t max_in = warp_excl_max(lane_max, lane);
+    // heads (a range that starts beyond everything before it) and the start of the last head in this lane
+    uint32_t run = max_in, last_head = 0;
+    unsigned heads = 0;
+#pragma unroll
+    for (int r = 0; r < EPL; r++) {
+        const uint32_t s = (uint32_t)(v[r] >> 32);
+        if (first + r < n) {
+            if (first + r == 0 || s > run) { heads |= 1u << r; last_head = s; }
+            run = max(run, (uint32_t)v[r]);
+        }
+    }
+    // start of the group that is open when this lane begins (starts ascend, so the latest head is the largest)
+    uint32_t gs = warp_excl_max(last_head, lane);
+    // a range closes its group iff the next range of the list is a head (or there is none)
+    const unsigned next_heads = __shfl_down_sync(0xffffffffu, heads, 1);
+    const bool next_lane_head = lane < 31 && (next_heads & 1u);
+    unsigned tails = 0;
+#pragma unroll
+    for (int r = 0; r < EPL; r++) {
+        if (first + r < n) {
+            const bool last = first + r + 1 == n;
+            const bool nh = r + 1 < EPL ? ((heads >> (r + 1 < EPL ? r + 1 : 0)) & 1u) : next_lane_head;
+            if (last || nh) tails |= 1u << r;
+        }
+    }
+    uint32_t before = (uint32_t)__popc(tails);
+    uint32_t total = before;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, total, o);
+        if (lane >= o) total += t;
+    }
+    uint32_t k_out = total - before;                 // merged ranges that end in earlier lanes
+    const uint32_t n_out = __shfl_sync(0xffffffffu, total, 31);
+    run = max_in;
+#pragma unroll
+    for (int r = 0; r < EPL; r++) {
+        if (first + r < n) {
+            if ((heads >> r) & 1u) gs = (uint32_t)(v[r] >> 32);
+            run = max(run, (uint32_t)v[r]);
+            if ((tails >> r) & 1u) {
+                g[k_out++] = ((uint64_t)gs << 32) | (uint64_t)run;
+                local_max = max(local_max, run - gs);
+            }
+        }
+    }
+    return n_out;
+}
+
+// WIDE = false: probes with at most 512 ranges (16 registers of ranges per lane: 64 registers per thread, eight
+// CTAs per SM); WIDE = true: the probes with 513..1024 ranges, which the first kernel flags in n_large bit 1.
+// Probes with more than MERGE_WARP_CAP ranges set bit 0 and go to the block-per-probe kernel.
+template <bool WIDE>
+__global__ void __launch_bounds__(MERGE_WARPS * 32, WIDE ? 3 : 8)
 merge_warp_kernel(const int64_t *__restrict__ rec_off, uint64_t *__restrict__ rec, int64_t n_probes,
                   uint32_t *__restrict__ n_merged, uint32_t *__restrict__ max_len, unsigned int *__restrict__ n_large)
 {
-    __shared__ uint64_t s_all[MERGE_WARPS * MERGE_WARP_CAP];
+    if (WIDE && (*n_large & 2u) == 0u) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint64_t *a = s_all + warp * MERGE_WARP_CAP;
     uint32_t local_max = 0, large = 0;
     for (int64_t p = (int64_t)blockIdx.x * MERGE_WARPS + warp; p < n_probes; p += (int64_t)gridDim.x * MERGE_WARPS) {
         const int64_t o0 = rec_off[p];
         const uint32_t n = (uint32_t)(rec_off[p + 1] - o0);
-        if (n == 0) {
-            if (lane == 0) n_merged[p] = 0;
-            continue;
-        }
-        if (n > (uint32_t)MERGE_WARP_CAP) { large = 1; continue; }
         uint64_t *g = rec + o0;
-        for (uint32_t i = lane; i < n; i += 32) a[i] = g[i];
-        __syncwarp();
-        int ln2 = 0;
-        while ((1u << ln2) < n) ln2++;
-        const uint32_t half = (1u << ln2) >> 1;
-        for (int ls = 1; ls <= ln2; ls++) {
-            const uint32_t size = 1u << ls;
-            for (uint32_t t = lane; t < half; t += 32) {
-                const uint32_t base = (t >> (ls - 1)) << ls, o = t & ((size >> 1) - 1u);
-                const uint32_t i = base + o, j = base + size - 1u - o;
-                if (j < n) {
-                    const uint64_t x = a[i], y = a[j];
-                    if (x > y) { a[i] = y; a[j] = x; }
-                }
+        uint32_t n_out;
+        if (WIDE) {
+            if (n <= 512u || n > (uint32_t)MERGE_WARP_CAP) continue;
+            n_out = warp_sort_merge<32>(g, n, lane, local_max);
+        } else {
+            if (n == 0) {
+                if (lane == 0) n_merged[p] = 0;
+                continue;
             }
-            __syncwarp();
-            for (int lt = ls - 2; lt >= 0; lt--) {
-                const uint32_t stride = 1u << lt;
-                for (uint32_t t = lane; t < half; t += 32) {
-                    const uint32_t i = ((t >> lt) << (lt + 1)) + (t & (stride - 1u)), j = i + stride;
-                    if (j < n) {
-                        const uint64_t x = a[i], y = a[j];
-                        if (x > y) { a[i] = y; a[j] = x; }
-                    }
-                }
-                __syncwarp();
-            }
+            if (n > 512u) { large |= n > (uint32_t)MERGE_WARP_CAP ? 1u : 2u; continue; }
+            if (n <= 32) n_out = warp_sort_merge<1>(g, n, lane, local_max);
+            else if (n <= 64) n_out = warp_sort_merge<2>(g, n, lane, local_max);
+            else if (n <= 128) n_out = warp_sort_merge<4>(g, n, lane, local_max);
+            else if (n <= 256) n_out = warp_sort_merge<8>(g, n, lane, local_max);
+            else n_out = warp_sort_merge<16>(g, n, lane, local_max);
         }
-        const uint32_t n_out = warp_merge_sorted(a, g, n, lane, local_max);
         if (lane == 0) n_merged[p] = n_out;
-        __syncwarp();
     }
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, o));
     if (lane == 0 && local_max) atomicMax(max_len, local_max);
-    if (lane == 0 && large) atomicOr(n_large, 1u);
+    if (lane == 0 && large) atomicOr(n_large, large);
 }
 
 __global__ void compact_kernel(const int64_t *__restrict__ rec_off, const uint64_t *__restrict__ rec,
@@ -1039,8 +1144,9 @@ int launch_merge(cb_ctx *ctx, const int64_t *d_roff, uint64_t *d_sorted, int64_t
     const int64_t cap = (int64_t)ctx->sm_count * 16;
     if (g > cap) g = cap;
     if (g < 1) g = 1;
-    merge_warp_kernel<<<(unsigned)g, MERGE_WARPS * 32, 0, st>>>(d_roff, d_sorted, P, d_nmerged, d_maxlen, d_large.p);
-    ctx->launches++;
+    merge_warp_kernel<false><<<(unsigned)g, MERGE_WARPS * 32, 0, st>>>(d_roff, d_sorted, P, d_nmerged, d_maxlen, d_large.p);
+    merge_warp_kernel<true><<<(unsigned)g, MERGE_WARPS * 32, 0, st>>>(d_roff, d_sorted, P, d_nmerged, d_maxlen, d_large.p);
+    ctx->launches += 2;
     CB_CUDA(ctx, cudaGetLastError());
     // probes with more ranges than the warp kernel takes: decided on the device (no host round trip in the
     // middle of stage A); the blocks leave at once when there is none
