@@ -197,6 +197,31 @@ int cb_init(int device_id, cb_ctx **out)
         *out = ctx;
         return CB_ERR_UNSUPPORTED;
     }
+    {   // Work buffers of a call add up to a few hundred MB .. a few GB; growing the pool piecemeal in the middle of
+        // a call was measured to cost up to 400 ms (the driver maps new memory with the device idle), so the pool is
+        // grown once here: CB_POOL_RESERVE_MB (default 8192, 0 = leave it to the first calls), never more than a
+        // quarter of the device's free memory.
+        long long mb = 8192;
+        if (const char *e = getenv("CB_POOL_RESERVE_MB")) mb = atoll(e);
+        size_t free_b = 0, total_b = 0;
+        cudaMemPool_t pool;
+        unsigned long long have = 0;
+        if (mb > 0 && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess &&
+            cudaDeviceGetDefaultMemPool(&pool, device_id) == cudaSuccess &&
+            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &have) == cudaSuccess) {
+            unsigned long long want = (unsigned long long)mb << 20;
+            if (want > free_b / 4) want = free_b / 4;
+            if (have < want) {
+                void *p = nullptr;
+                if (cudaMallocAsync(&p, (size_t)(want - have), ctx->stream) == cudaSuccess) {
+                    cudaFreeAsync(p, ctx->stream);
+                    cudaStreamSynchronize(ctx->stream);
+                } else {
+                    cudaGetLastError();          // not fatal: the calls grow the pool as they go
+                }
+            }
+        }
+    }
     *out = ctx;
     return CB_OK;
 }
