@@ -61,6 +61,13 @@ static PyObject *gather_impl(PyObject *args, int into)
     Py_ssize_t got = 0;
     size_t total = 0;
     for (Py_ssize_t i = 0; i < n; i++) {
+        if ((i & 1023) == 1023) {
+            /* let a thread that waits for the interpreter lock have it: a helper thread gathering the next
+             * grouping must not keep the main thread from issuing its next device call for a whole pass.
+             * (The caller keeps the list alive and does not change it meanwhile.) */
+            Py_BEGIN_ALLOW_THREADS
+            Py_END_ALLOW_THREADS
+        }
         PyObject *s = items[i];
         if (PyUnicode_Check(s)) {
             Py_INCREF(s);

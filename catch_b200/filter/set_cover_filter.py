@@ -137,9 +137,11 @@ class _Prefetch:
     gather of grouping g+1 overlaps the scan and set cover of g.  A pair is reused only after the upload
     that reads it has returned (release()).  The staging buffers are sized up front on the calling thread,
     so the helper never calls into the library.
-    OFF by default (CB_PREFETCH=1 turns it on): measured on the V-All shape it does not pay -- gathering a list
-    of Probe objects holds the GIL for its whole attribute pass, so the two threads mostly take turns
-    (profiles/README_r02.md).  The remedy for that host cost is not to have the objects at all: ProbeBatch."""
+    ON by default (CB_PREFETCH=0 turns it off).  Measured on the V-All shape (16 taxa, one B200): lists of Probe
+    objects 262 -> 234 ms, ProbeBatch input 198 -> 176 ms.  The gather of a list of Probe objects needs the GIL
+    for its attribute pass; it hands the lock over every 1024 objects (csrc/fastpack.c), so the main thread is not
+    kept from issuing its next device call.  The larger remedy for that host cost is not to have the objects at
+    all: ProbeBatch."""
 
     def __init__(self, ctx, groups):
         """groups: list of (group index, probe list, genomes) in processing order."""
@@ -323,7 +325,7 @@ class SetCoverFilter(BaseFilter):
         mine = [g for g in range(len(input)) if owner[g] == rank]
         prefetch = None
         if len(mine) >= 2 and cov._fastpack is not None and hasattr(self._context(), 'host_buffer') and \
-                os.environ.get('CB_PREFETCH', '0') == '1':
+                os.environ.get('CB_PREFETCH', '1') == '1':
             as_lists = {g: (input[g] if isinstance(input[g], (list, tuple, ProbeBatch)) else list(input[g])) for g in mine}
             prefetch = _Prefetch(self._context(), [(g, as_lists[g], target_genomes_grouped[g]) for g in mine])
         try:

@@ -427,3 +427,25 @@ def test_probe_batch_filter_chain_equals_probe_lists(ctx):
             # paths alike (list(set(...))); both are in THIS process, so the orders agree here too
             assert outs[0] == outs[1]
         assert sum(map(len, outs[0][1])) > 10
+
+
+def test_prefetch_thread_does_not_change_the_output(ctx, monkeypatch):
+    """Several groupings in one filter() call: the helper thread that gathers the next grouping while the current
+    one is on the device (on by default) gives the same selection, in the same order, as the plain loop."""
+    import random as pyrandom
+    from catch_b200 import probe
+    from catch_b200.filter.set_cover_filter import SetCoverFilter
+    groups = helpers.synthetic_taxa(5, 12, seed=9, length_range=(1500, 3000))
+    genomes = helpers.to_genomes([[[s] for s in g] for g in groups])
+    cands = [list(dict.fromkeys(helpers.tile_candidates(g, 100, 50))) for g in groups]
+    probes = [[probe.Probe.from_str(s) for s in c] for c in cands]
+    outs = []
+    for flag in ('1', '0', '1'):
+        monkeypatch.setenv('CB_PREFETCH', flag)
+        scf = SetCoverFilter(mismatches=3, lcf_thres=40, cover_extension=10)
+        scf._ctx = ctx
+        np.random.seed(5)
+        pyrandom.seed(5)
+        outs.append([[p.seq_str for p in g] for g in scf.filter(probes, genomes, input_is_grouped=True)])
+    assert outs[0] == outs[1] == outs[2]
+    assert all(len(g) > 0 for g in outs[0])
