@@ -138,6 +138,28 @@ def measured_peak_gbs():
         return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
+def captured_traffic(kernel_label):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed `ncu --set
+    full` capture (profiles/traffic_r02.json, written by tools/ncu_summary.py --traffic).  DRAM bytes cannot be
+    measured inside the run; the capture is only quoted while the kernel source it was taken from is the source in
+    the tree (sha256 of the .cu file recorded with it) and the workload is config 2 -- otherwise null, never a stale
+    constant."""
+    import hashlib
+    path = os.path.join(ROOT, 'profiles', 'traffic_r02.json')
+    try:
+        rec = json.load(open(path))
+        for k in rec['kernels']:
+            if kernel_label.startswith(k['label']):
+                src = os.path.join(ROOT, k['source'])
+                if hashlib.sha256(open(src, 'rb').read()).hexdigest() != k['source_sha256']:
+                    return None, '%s changed since the ncu capture in %s was taken' % (k['source'], k['capture'])
+                return k['dram_read_bytes'] + k['dram_write_bytes'], \
+                    'ncu --set full capture %s (same kernel source, config 2), per launch' % k['capture']
+    except (OSError, KeyError, ValueError):
+        pass
+    return None, 'no ncu capture of this kernel recorded in profiles/traffic_r02.json'
+
+
 def host_threads():
     """Host threads the CPU leg may use.  torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU leg
     is a reported baseline on 'all the host threads it can use', so it sizes itself from the machine."""
@@ -642,14 +664,13 @@ def main():
         dur = kern[dom] / 1e3
     peak, peak_src = measured_peak_gbs()
     achieved = alg_bytes / dur / 1e9 if dur > 0 else 0.0
+    traffic, traffic_note = captured_traffic(dom)
     roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                'frac': achieved / peak, 'traffic': None, 'algorithmic_bytes': alg_bytes, 'peak_source': peak_src,
+                'frac': achieved / peak, 'traffic': traffic, 'algorithmic_bytes': alg_bytes, 'peak_source': peak_src,
                 'kernel_ms': {k: round(v, 3) for k, v in kern.items()},
                 'l2_operand_gbs': (l2_operand_bytes / dur / 1e9) if l2_operand_bytes else None,
                 'int_ops': int_ops,
-                'traffic_note': 'DRAM bytes per launch cannot be measured inside the run (null here rather than a stale '
-                                'constant); the ncu --set full capture of this kernel on this workload is summarised in '
-                                'profiles/README_r02.md',
+                'traffic_note': traffic_note,
                 'note': 'HBM is not what binds this integer path: the scan is bound by the integer ALU pipe (see int_ops '
                         'and the ncu pipe utilisation in profiles/), the greedy loop by grid-barrier and dependent-load '
                         'latency per round; frac is reported against HBM as the contract asks'}
