@@ -268,6 +268,21 @@ def config3_influenza(ctx, n_genomes, reps=3):
         ndf_wall.append(time.perf_counter() - t)
         st = ndf.last_stats
         ndf_dev.append(st['ms_total'])
+    # the same filter on the candidates as ONE buffer (ProbeBatch: what the tiling of design.py hands to the filter
+    # chain) instead of 1.3 M Probe objects
+    from catch_b200.probe_batch import ProbeBatch
+    batch = [ProbeBatch(np.frombuffer(''.join(cands).encode(), dtype=np.uint8).reshape(len(cands), 100))]
+    ndf_wall_b, kept_b = [], None
+    for _ in range(reps):
+        np.random.seed(RNG_SEED)
+        random.seed(RNG_SEED)
+        ndf = NearDuplicateFilterWithMinHash(0.6)
+        ndf._ctx = ctx
+        t = time.perf_counter()
+        kept_b = ndf.filter(batch, genomes, input_is_grouped=True)
+        ndf_wall_b.append(time.perf_counter() - t)
+    same_b = [p.seq_str for p in kept_b[0]] == [p.seq_str for p in kept[0]]
+    del batch, kept_b
     scf = SetCoverFilter(mismatches=5, lcf_thres=30, cover_extension=50)
     scf._ctx = ctx
     os.environ['CB_SHARD'] = 'groups'
@@ -287,7 +302,8 @@ def config3_influenza(ctx, n_genomes, reps=3):
         'workload': 'config 3 (influenza shape): %d genomes x 8 segments (T=%d bp), pl 100 ps 50, MinHash near-duplicate '
                     'filter 0.6, then -m 5 -l 30 -e 50' % (n_genomes, T),
         'P_raw': len(cands), 'P_distinct': int(st['n_distinct']), 'P_after_ndf': P,
-        'ndf': {'wall_ms': t_ndf * 1e3, 'device_ms': min(ndf_dev), 'probes_per_s_e2e': len(cands) / t_ndf,
+        'ndf': {'wall_ms': t_ndf * 1e3, 'wall_batch_ms': min(ndf_wall_b[1:] or ndf_wall_b) * 1e3, 'batch_output_identical': same_b,
+                'device_ms': min(ndf_dev), 'probes_per_s_e2e': len(cands) / t_ndf,
                 'probes_per_s_device': len(cands) / (min(ndf_dev) / 1e3), 'decision_rounds': int(st['n_picks']),
                 'device_split_ms': {'grouping': st['ms_pack'], 'signatures': st['ms_seed_index'], 'decisions': st['ms_greedy']}},
         'scf': {'e2e_ms': t_scf * 1e3, 'device_ms': dev_ms, 'pairs_per_s_e2e': P * T / t_scf,
