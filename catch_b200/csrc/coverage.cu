@@ -70,6 +70,7 @@ struct ScanParams {
     unsigned long long rec_cap;
     unsigned long long *rec_cursor;
     uint32_t *rec_count;
+    int keep_hit;                   // records carry the hit position (cb_coverage_records) instead of the per-probe sequence number
     // scheduling / stats
     int64_t n_tiles;
     unsigned long long *tile_counter;
@@ -793,8 +794,10 @@ scan_kernel(const ScanParams P)
                         wb = __shfl_sync(0xffffffffu, wb, 0);
                         if (emit) {
                             const unsigned long long slot = wb + __popc(em & ((1u << lane) - 1u));
-                            if (slot < P.rec_cap) P.rec[slot] = make_uint4(p, us, ue, hit);
-                            atomicAdd(&P.rec_count[p], 1u);
+                            // the range's number among the probe's ranges rides in the record (unless the caller
+                            // wants the hit positions): the bucketing pass then needs no atomics of its own
+                            const uint32_t nth = atomicAdd(&P.rec_count[p], 1u);
+                            if (slot < P.rec_cap) P.rec[slot] = make_uint4(p, us, ue, P.keep_hit ? hit : nth);
                         }
                     }
                 }
@@ -812,14 +815,12 @@ scan_kernel(const ScanParams P)
 
 // bucket the global range list by probe: rec_sorted[rec_off[p] + slot] = (start << 32 | end)
 __global__ void scatter_by_probe_kernel(const uint4 *__restrict__ rec, unsigned long long n,
-                                        const int64_t *__restrict__ rec_off, uint32_t *__restrict__ cursor,
-                                        uint64_t *__restrict__ rec_sorted)
+                                        const int64_t *__restrict__ rec_off, uint64_t *__restrict__ rec_sorted)
 {
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (unsigned long long)gridDim.x * blockDim.x) {
-        const uint4 r = rec[i];
-        const uint32_t slot = atomicAdd(&cursor[r.x], 1u);
-        rec_sorted[rec_off[r.x] + slot] = ((uint64_t)r.y << 32) | (uint64_t)r.z;
+        const uint4 r = rec[i];                      // probe, start, end, number among the probe's ranges
+        rec_sorted[rec_off[r.x] + r.w] = ((uint64_t)r.y << 32) | (uint64_t)r.z;
     }
 }
 
@@ -922,7 +923,7 @@ merge_kernel(const int64_t *__restrict__ rec_off, uint64_t *__restrict__ rec, in
              const unsigned int *__restrict__ n_large)
 {
     __shared__ uint64_t s_rec[MERGE_SMEM_CAP];
-    if (n_large && (*n_large & 1u) == 0u) return;   // the warp kernels took every probe (the usual case)
+    if (n_large && *n_large == 0u) return;          // the warp kernels took every probe (the usual case)
     uint32_t local_max = 0;
     for (int64_t p = blockIdx.x; p < n_probes; p += gridDim.x) {
         const int64_t o0 = rec_off[p];
@@ -1078,42 +1079,53 @@ __device__ __forceinline__ uint32_t warp_sort_merge(uint64_t *__restrict__ g, ui
 }
 
 // WIDE = false: probes with at most 512 ranges (16 registers of ranges per lane: 64 registers per thread, eight
-// CTAs per SM); WIDE = true: the probes with 513..1024 ranges, which the first kernel flags in n_large bit 1.
-// Probes with more than MERGE_WARP_CAP ranges set bit 0 and go to the block-per-probe kernel.
+// CTAs per SM); the probes with 513..1024 ranges are appended to wide_list and done by the WIDE = true launch, one
+// warp per list entry (few probes, each a long sort: spread over the whole grid instead of wherever they happen to
+// fall).  Probes with more than MERGE_WARP_CAP ranges set n_large and go to the block-per-probe kernel.
 template <bool WIDE>
 __global__ void __launch_bounds__(MERGE_WARPS * 32, WIDE ? 3 : 8)
 merge_warp_kernel(const int64_t *__restrict__ rec_off, uint64_t *__restrict__ rec, int64_t n_probes,
-                  uint32_t *__restrict__ n_merged, uint32_t *__restrict__ max_len, unsigned int *__restrict__ n_large)
+                  uint32_t *__restrict__ n_merged, uint32_t *__restrict__ max_len, unsigned int *__restrict__ n_large,
+                  uint32_t *__restrict__ wide_list, unsigned int *__restrict__ wide_count)
 {
-    if (WIDE && (*n_large & 2u) == 0u) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t local_max = 0, large = 0;
-    for (int64_t p = (int64_t)blockIdx.x * MERGE_WARPS + warp; p < n_probes; p += (int64_t)gridDim.x * MERGE_WARPS) {
-        const int64_t o0 = rec_off[p];
-        const uint32_t n = (uint32_t)(rec_off[p + 1] - o0);
-        uint64_t *g = rec + o0;
-        uint32_t n_out;
-        if (WIDE) {
-            if (n <= 512u || n > (uint32_t)MERGE_WARP_CAP) continue;
-            n_out = warp_sort_merge<32>(g, n, lane, local_max);
-        } else {
+    if (WIDE) {
+        const unsigned int n_wide = *wide_count;
+        for (unsigned int i = blockIdx.x * MERGE_WARPS + warp; i < n_wide; i += gridDim.x * MERGE_WARPS) {
+            const int64_t p = wide_list[i];
+            const int64_t o0 = rec_off[p];
+            const uint32_t n = (uint32_t)(rec_off[p + 1] - o0);
+            const uint32_t n_out = warp_sort_merge<32>(rec + o0, n, lane, local_max);
+            if (lane == 0) n_merged[p] = n_out;
+        }
+    } else {
+        for (int64_t p = (int64_t)blockIdx.x * MERGE_WARPS + warp; p < n_probes; p += (int64_t)gridDim.x * MERGE_WARPS) {
+            const int64_t o0 = rec_off[p];
+            const uint32_t n = (uint32_t)(rec_off[p + 1] - o0);
+            uint64_t *g = rec + o0;
+            uint32_t n_out;
             if (n == 0) {
                 if (lane == 0) n_merged[p] = 0;
                 continue;
             }
-            if (n > 512u) { large |= n > (uint32_t)MERGE_WARP_CAP ? 1u : 2u; continue; }
+            if (n > 512u) {
+                if (n > (uint32_t)MERGE_WARP_CAP) large = 1u;
+                else if (lane == 0) wide_list[atomicAdd(wide_count, 1u)] = (uint32_t)p;
+                continue;
+            }
             if (n <= 32) n_out = warp_sort_merge<1>(g, n, lane, local_max);
             else if (n <= 64) n_out = warp_sort_merge<2>(g, n, lane, local_max);
             else if (n <= 128) n_out = warp_sort_merge<4>(g, n, lane, local_max);
             else if (n <= 256) n_out = warp_sort_merge<8>(g, n, lane, local_max);
             else n_out = warp_sort_merge<16>(g, n, lane, local_max);
+            if (lane == 0) n_merged[p] = n_out;
         }
-        if (lane == 0) n_merged[p] = n_out;
     }
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, o));
     if (lane == 0 && local_max) atomicMax(max_len, local_max);
-    if (lane == 0 && large) atomicOr(n_large, large);
+    if (lane == 0 && large) atomicOr(n_large, 1u);
 }
 
 __global__ void compact_kernel(const int64_t *__restrict__ rec_off, const uint64_t *__restrict__ rec,
@@ -1137,15 +1149,19 @@ __global__ void compact_kernel(const int64_t *__restrict__ rec_off, const uint64
 int launch_merge(cb_ctx *ctx, const int64_t *d_roff, uint64_t *d_sorted, int64_t P, uint32_t *d_nmerged, uint32_t *d_maxlen)
 {
     cudaStream_t st = ctx->stream;
-    DevBuf<unsigned int> d_large;
-    CB_CUDA(ctx, d_large.alloc(1));
-    CB_CUDA(ctx, cudaMemsetAsync(d_large.p, 0, sizeof(unsigned int), st));
+    DevBuf<unsigned int> d_large;            // [0] some probe has more than MERGE_WARP_CAP ranges, [1] length of the wide list
+    DevBuf<uint32_t> d_wide;
+    CB_CUDA(ctx, d_large.alloc(2));
+    CB_CUDA(ctx, d_wide.alloc((size_t)(P > 0 ? P : 1)));
+    CB_CUDA(ctx, cudaMemsetAsync(d_large.p, 0, 2 * sizeof(unsigned int), st));
     int64_t g = (P + MERGE_WARPS - 1) / MERGE_WARPS;
     const int64_t cap = (int64_t)ctx->sm_count * 16;
     if (g > cap) g = cap;
     if (g < 1) g = 1;
-    merge_warp_kernel<false><<<(unsigned)g, MERGE_WARPS * 32, 0, st>>>(d_roff, d_sorted, P, d_nmerged, d_maxlen, d_large.p);
-    merge_warp_kernel<true><<<(unsigned)g, MERGE_WARPS * 32, 0, st>>>(d_roff, d_sorted, P, d_nmerged, d_maxlen, d_large.p);
+    merge_warp_kernel<false><<<(unsigned)g, MERGE_WARPS * 32, 0, st>>>(d_roff, d_sorted, P, d_nmerged, d_maxlen, d_large.p,
+                                                                       d_wide.p, d_large.p + 1);
+    merge_warp_kernel<true><<<(unsigned)g, MERGE_WARPS * 32, 0, st>>>(d_roff, d_sorted, P, d_nmerged, d_maxlen, d_large.p,
+                                                                      d_wide.p, d_large.p + 1);
     ctx->launches += 2;
     CB_CUDA(ctx, cudaGetLastError());
     // probes with more ranges than the warp kernel takes: decided on the device (no host round trip in the
@@ -1314,10 +1330,9 @@ int cb_coverage_impl(cb_ctx *ctx, const cb_probes *probes, const cb_targets *tar
     CB_CUDA(ctx, cudaGetLastError());
     t_idx.stop();
 
-    DevBuf<uint32_t> d_rcount, d_rcursor;
+    DevBuf<uint32_t> d_rcount;
     DevBuf<int64_t> d_roff;
     CB_CUDA(ctx, d_rcount.alloc((size_t)P));
-    CB_CUDA(ctx, d_rcursor.alloc((size_t)P));
     CB_CUDA(ctx, d_roff.alloc((size_t)P + 1));
 
     ScanParams sp;
@@ -1342,6 +1357,7 @@ int cb_coverage_impl(cb_ctx *ctx, const cb_probes *probes, const cb_targets *tar
     sp.ext = hp->cover_extension;
     sp.k = hp->k;
     sp.rec_count = d_rcount.p;
+    sp.keep_hit = raw_records ? 1 : 0;
     sp.n_tiles = (targets->total_bases + CB_TILE - 1) / CB_TILE;
     sp.tile_counter = d_ctr.p;
     sp.stat_hits = d_ctr.p + 1;
@@ -1442,10 +1458,9 @@ int cb_coverage_impl(cb_ctx *ctx, const cb_probes *probes, const cb_targets *tar
     CB_CUDA(ctx, d_sorted.alloc((size_t)n_raw));
     CB_CUDA(ctx, d_nmerged.alloc((size_t)P));
     CB_CUDA(ctx, d_maxlen.alloc(1));
-    CB_CUDA(ctx, cudaMemsetAsync(d_rcursor.p, 0, sizeof(uint32_t) * (size_t)P, st));
     CB_CUDA(ctx, cudaMemsetAsync(d_maxlen.p, 0, sizeof(uint32_t), st));
     if (n_raw) {
-        scatter_by_probe_kernel<<<wide, 256, 0, st>>>(d_rec.p, n_raw, d_roff.p, d_rcursor.p, d_sorted.p);
+        scatter_by_probe_kernel<<<wide, 256, 0, st>>>(d_rec.p, n_raw, d_roff.p, d_sorted.p);
         ctx->launches++;
     }
     CB_TRY(launch_merge(ctx, d_roff.p, d_sorted.p, P, d_nmerged.p, d_maxlen.p));
@@ -1514,7 +1529,7 @@ int cb_cover_import_impl(cb_ctx *ctx, int64_t P, int32_t NG, const int64_t *geno
             return cb_fail(ctx, CB_ERR_ARG, "interval out of range");
         const uint32_t b = cov->h_ubase[(size_t)genome[i]];
         h_rec[(size_t)i] = make_uint4((uint32_t)probe_id[i], b + (uint32_t)start[i], b + (uint32_t)end[i], 0u);
-        if (end[i] > start[i]) h_count[(size_t)probe_id[i]]++;
+        if (end[i] > start[i]) h_rec[(size_t)i].w = h_count[(size_t)probe_id[i]]++;   // number among the probe's ranges
         else h_rec[(size_t)i].x = 0xffffffffu;            // empty interval: dropped
     }
     // compact away empty intervals on the host
@@ -1531,23 +1546,21 @@ int cb_cover_import_impl(cb_ctx *ctx, int64_t P, int32_t NG, const int64_t *geno
         return CB_OK;
     }
     DevBuf<uint4> d_rec;
-    DevBuf<uint32_t> d_rcount, d_rcursor, d_nmerged, d_maxlen;
+    DevBuf<uint32_t> d_rcount, d_nmerged, d_maxlen;
     DevBuf<int64_t> d_roff;
     DevBuf<uint64_t> d_sorted;
     CB_CUDA(ctx, d_rec.alloc(m));
     CB_CUDA(ctx, d_rcount.alloc((size_t)P));
-    CB_CUDA(ctx, d_rcursor.alloc((size_t)P));
     CB_CUDA(ctx, d_roff.alloc((size_t)P + 1));
     CB_CUDA(ctx, d_sorted.alloc(m));
     CB_CUDA(ctx, d_nmerged.alloc((size_t)P));
     CB_CUDA(ctx, d_maxlen.alloc(1));
     CB_CUDA(ctx, cudaMemcpyAsync(d_rec.p, h_rec.data(), sizeof(uint4) * m, cudaMemcpyHostToDevice, st));
     CB_CUDA(ctx, cudaMemcpyAsync(d_rcount.p, h_count.data(), sizeof(uint32_t) * (size_t)P, cudaMemcpyHostToDevice, st));
-    CB_CUDA(ctx, cudaMemsetAsync(d_rcursor.p, 0, sizeof(uint32_t) * (size_t)P, st));
     CB_CUDA(ctx, cudaMemsetAsync(d_maxlen.p, 0, sizeof(uint32_t), st));
     CB_TRY(cb_exclusive_scan_u32_to_i64(ctx, d_rcount.p, d_roff.p, P, nullptr));
     const int wide = ctx->sm_count * 8;
-    scatter_by_probe_kernel<<<wide, 256, 0, st>>>(d_rec.p, (unsigned long long)m, d_roff.p, d_rcursor.p, d_sorted.p);
+    scatter_by_probe_kernel<<<wide, 256, 0, st>>>(d_rec.p, (unsigned long long)m, d_roff.p, d_sorted.p);
     ctx->launches++;
     CB_TRY(launch_merge(ctx, d_roff.p, d_sorted.p, P, d_nmerged.p, d_maxlen.p));
     CB_CUDA(ctx, cudaGetLastError());

@@ -449,3 +449,50 @@ def test_prefetch_thread_does_not_change_the_output(ctx, monkeypatch):
         outs.append([[p.seq_str for p in g] for g in scf.filter(probes, genomes, input_is_grouped=True)])
     assert outs[0] == outs[1] == outs[2]
     assert all(len(g) > 0 for g in outs[0])
+
+
+@pytest.mark.parametrize('n_genomes', [20, 45, 100, 200, 400, 800])
+def test_merge_every_list_length_class(ctx, n_genomes):
+    """The warp merge sorts a probe's ranges in registers with 1, 2, 4, 8 or 16 ranges per lane, lists of 513..1024
+    in a second kernel: one case per class (a probe hits every genome about once), against the oracle."""
+    O = _oracle()
+    rng = random.Random(100 + n_genomes)
+    anc = ''.join(rng.choice('ACGT') for _ in range(400))
+    genomes = [[helpers.mutate(rng, anc, 0.015)] for _ in range(n_genomes)]
+    probe_strs = list(dict.fromkeys(helpers.tile_candidates([g[0] for g in genomes[:5]], 60, 30)))
+    params = dict(mismatches=2, lcf_thres=45, island_of_exact_match=0, cover_extension=10, kmer_probe_map_k=15)
+    np.random.seed(9)
+    k, seeds, _ = O.choose_seeds(probe_strs, 2, 45, min_k=15, k=15)
+    want = O.make_sets_quads(O.SeedMap(probe_strs, seeds, k), genomes, 2, 45, 0, 10)
+    np.random.seed(9)
+    got, cover, st = _device_quads(ctx, probe_strs, genomes, params)
+    cover.free()
+    counts = np.bincount(want[:, 0], minlength=len(probe_strs))
+    assert counts.max() > n_genomes // 2
+    assert np.array_equal(got, want)
+
+
+def test_range_list_sized_from_previous_scan_overflows_gracefully(ctx):
+    """Stage A sizes its range list from the density of the previous scan with the same parameters and only counts
+    when that overflows: a scan that finds almost nothing followed by a dense one (and the other way round) must give
+    the same cover as a context that always counts first."""
+    O = _oracle()
+    rng = random.Random(77)
+    anc = ''.join(rng.choice('ACGT') for _ in range(3000))
+    dense = [[helpers.mutate(rng, anc, 0.01)] for _ in range(220)]
+    # almost nothing to find, but not nothing (a density of zero is not used as a hint)
+    sparse = [[''.join(rng.choice('ACGT') for _ in range(3000))] for _ in range(219)] + [dense[0]]
+    probe_strs = list(dict.fromkeys(helpers.tile_candidates([g[0] for g in dense[:4]], 75, 25)))
+    params = dict(mismatches=2, lcf_thres=60, island_of_exact_match=0, cover_extension=0, kmer_probe_map_k=20)
+    np.random.seed(3)
+    k, seeds, _ = O.choose_seeds(probe_strs, 2, 60, min_k=20, k=20)
+    want = O.make_sets_quads(O.SeedMap(probe_strs, seeds, k), dense, 2, 60, 0, 0)
+    for genomes in (sparse, dense, sparse, dense):
+        np.random.seed(3)
+        got, cover, st = _device_quads(ctx, probe_strs, genomes, params)
+        cover.free()
+        if genomes is dense:
+            assert np.array_equal(got, want)
+            assert st.n_raw_ranges > 70000              # more than the hint of the sparse scan allows for (~65.6 k)
+        else:
+            assert 0 < st.n_raw_ranges < 2000
