@@ -21,7 +21,8 @@ The default line (workload zika = BASELINE config 2) also carries, unless --no-e
                   selection compared to the oracle's (bit-exact, order included);
   configs       : compact results for BASELINE configs 3 (influenza shape, MinHash near-duplicate
                   filter on), 4 (V-All shape, a stated number of taxa) and 5 (m x l sweep);
-  with N > 1: vall_groups, the V-All-shape e2e with the SAME taxa sharded over the N GPUs.
+  with N > 1: vall_groups, the V-All-shape e2e with the SAME taxa sharded over the N GPUs, and influenza_shard, the
+  config-3 set cover (one grouping, 61 k probes x 68 Mbp) with its probes sharded over the N GPUs.
 The CPU oracle (oracle/) is executed only for `cpu_baseline`, `like_for_like` and `--impl reference`.
 """
 import argparse
@@ -312,6 +313,50 @@ def config3_influenza(ctx, n_genomes, reps=3):
                 'greedy_ms': s['setcover']['ms_greedy'], 'rounds': int(s['setcover']['reserved'][5])},
     }
     return res, kept, genomes, T
+
+
+def config3_sharded(ctx, n_genomes, dist, local_rank, reps=3):
+    """BASELINE config 3 (influenza shape), N > 1: the set cover filter on what the near-duplicate filter keeps
+    (-m 5 -l 30 -e 50), ONE grouping with its probes sharded over the GPUs (stage A per shard, stage B with one
+    exchange per round).  Every rank builds the same input and runs the same near-duplicate filter first."""
+    import torch
+    from catch_b200 import probe
+    from catch_b200.filter.near_duplicate_filter import NearDuplicateFilterWithMinHash
+    from catch_b200.filter.set_cover_filter import SetCoverFilter
+    gens = helpers.synthetic_influenza(n_genomes, seed=3)
+    groups = [[[seg] for g in gens for seg in g]]
+    genomes = helpers.to_genomes(groups)
+    cands = helpers.tile_candidates([s for g in groups[0] for s in g], 100, 50)
+    T = sum(len(s) for g in groups[0] for s in g)
+    np.random.seed(RNG_SEED)
+    random.seed(RNG_SEED)
+    ndf = NearDuplicateFilterWithMinHash(0.6)
+    ndf._ctx = ctx
+    kept = ndf.filter([[probe.Probe.from_str(s) for s in cands]], genomes, input_is_grouped=True)
+    P = len(kept[0])
+    scf = SetCoverFilter(mismatches=5, lcf_thres=30, cover_extension=50)
+    scf._ctx = ctx
+    os.environ['CB_SHARD'] = 'probes'
+    best, n_sel = None, 0
+    for rep in range(reps + 1):
+        np.random.seed(RNG_SEED)
+        dist.barrier(device_ids=[local_rank])
+        t = time.perf_counter()
+        out = scf.filter(kept, genomes, input_is_grouped=True)
+        tt = torch.tensor([time.perf_counter() - t], dtype=torch.float64, device='cuda')
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        if rep > 0 and (best is None or float(tt.item()) < best):
+            best = float(tt.item())
+        n_sel = len(out[0])
+    s = scf.last_stats[0]
+    dev = torch.tensor([s['coverage']['ms_total'] + s['setcover']['ms_total']], dtype=torch.float64, device='cuda')
+    dist.all_reduce(dev, op=dist.ReduceOp.MAX)
+    return {'workload': 'config 3 (influenza shape): %d genomes x 8 segments (T=%d bp), %d probes after the near-duplicate '
+                        'filter, -m 5 -l 30 -e 50, probes of the ONE grouping sharded over the GPUs' % (n_genomes, T, P),
+            'n_gpus': dist.get_world_size(), 'e2e_ms': best * 1e3, 'device_ms_max_over_ranks': float(dev.item()),
+            'pairs_per_s_e2e': P * T / best, 'pairs_per_s_device': P * T / (float(dev.item()) / 1e3), 'selected': n_sel,
+            'this_rank': {'scan_ms': s['coverage']['ms_scan_emit'], 'merge_ms': s['coverage']['ms_merge'],
+                          'greedy_ms': s['setcover']['ms_greedy'], 'rounds': int(s['setcover']['reserved'][5])}}
 
 
 def config5_sweep(ctx, kept, genomes, T, cells=None, reps=2):
@@ -758,6 +803,10 @@ def main():
             out['vall_groups'] = config4_vall(ctx, args.vall_taxa, args.vall_genomes, dist=dist, local_rank=local_rank)
         except Exception as e:
             out['vall_groups_error'] = repr(e)
+        try:
+            out['influenza_shard'] = config3_sharded(ctx, args.influenza_genomes, dist, local_rank)
+        except Exception as e:
+            out['influenza_shard_error'] = repr(e)
     if rank == 0:
         print(json.dumps(out))
     if dist is not None:
