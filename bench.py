@@ -333,6 +333,9 @@ def config3_sharded(ctx, n_genomes, dist, local_rank, reps=3):
     ndf = NearDuplicateFilterWithMinHash(0.6)
     ndf._ctx = ctx
     kept = ndf.filter([[probe.Probe.from_str(s) for s in cands]], genomes, input_is_grouped=True)
+    # the filter returns list(set(...)): an order that depends on the process's string hash seed.  Every rank must
+    # hand the SAME list to the sharded filter, so it is put into a process-independent order here
+    kept = [sorted(kept[0], key=lambda p: p.seq_str)]
     P = len(kept[0])
     scf = SetCoverFilter(mismatches=5, lcf_thres=30, cover_extension=50)
     scf._ctx = ctx

@@ -52,6 +52,24 @@ def gather_staged(ctx, slot, items):
     return addr, np.frombuffer(lens, dtype=np.int32, count=n), total
 
 
+def fingerprint(gathered, max_samples=64):
+    """Cheap checksum of a gathered probe list (number of probes, their lengths' sum and the bytes of up to
+    `max_samples` evenly spaced probes): ranks that are about to shard ONE probe list compare it, because a list whose
+    order came out of a Python set differs between processes unless PYTHONHASHSEED is pinned."""
+    import zlib
+    raw, lens = gathered[0], gathered[1]
+    n = len(lens)
+    if n == 0:
+        return 0
+    off = offsets_from_lengths(lens)
+    crc = zlib.crc32(b'%d:%d' % (n, int(off[-1])))
+    for i in np.unique(np.linspace(0, n - 1, num=min(n, max_samples)).astype(np.int64)).tolist():
+        a, b = int(off[i]), int(off[i + 1])
+        chunk = raw[a:b] if isinstance(raw, (bytes, bytearray)) else ctypes.string_at(raw + a, b - a)
+        crc = zlib.crc32(chunk, crc)
+    return crc
+
+
 def offsets_from_lengths(lens):
     """int64 offsets [n + 1] of sequences of the given lengths laid back to back."""
     n = len(lens)

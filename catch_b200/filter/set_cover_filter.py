@@ -514,6 +514,8 @@ class SetCoverFilter(BaseFilter):
                         cov.cancel_draw(drawn)
                     raise
                 lengths = gathered[1]
+                # every rank must hold the SAME list in the same order (it shards it by position)
+                token = (token * 1000003) ^ cov.fingerprint(gathered)
                 if drawn is None or not bool(np.all(lengths == guess)):
                     if drawn is not None:
                         cov.cancel_draw(drawn)

@@ -180,8 +180,9 @@ def ensure_exchange(ctx, need_bytes, token=0, failed=False):
     if any_failed:
         raise RuntimeError("a rank failed before the sharded set cover" + (" (this one)" if failed else ""))
     if tmax != tmin:
-        raise RuntimeError("ranks disagree on the host state the seed draws depend on (numpy RNG state); "
-                           "seed np.random identically on every rank before calling the filter")
+        raise RuntimeError("ranks disagree on the host state a sharded grouping depends on: numpy's RNG state (seed "
+                           "np.random identically on every rank before calling the filter) or the probe list itself "
+                           "(a list ordered by a Python set differs between processes unless PYTHONHASHSEED is pinned)")
     if getattr(ctx, 'exchange_ready', False) and ctx.exchange_bytes() >= need and \
             getattr(ctx, 'exchange_n_ranks', 0) == world_size:
         return

@@ -364,3 +364,17 @@ def test_fasta_reader_matches_reference_fixtures(tmp_path):
         f.write('>g\u00e9nome\nacgt-y\n>b\nAC\nGT\n')
     assert list(seq_io.read_fasta(fn).items()) == [('g\u00e9nome', 'ACGTN'), ('b', 'ACGT')]
     assert [g.seqs for g in seq_io.read_genomes_from_fasta(fn)] == [['ACGTN'], ['ACGT']]
+
+
+def test_probe_list_fingerprint_sees_order_and_content():
+    """The checksum ranks compare before sharding ONE probe list by position (catch_b200/coverage.py: fingerprint)."""
+    import ctypes
+    from catch_b200 import coverage as cov, probe
+    ps = [probe.Probe('ACGT' * 20 + str(i % 10) * 5) for i in range(1000)]
+    g = cov.gather_probes(ps)
+    assert cov.fingerprint(g) == cov.fingerprint(cov.gather_probes(list(ps)))
+    assert cov.fingerprint(g) != cov.fingerprint(cov.gather_probes(ps[::-1]))
+    assert cov.fingerprint(g) != cov.fingerprint(cov.gather_probes(ps[:-1]))
+    buf = ctypes.create_string_buffer(g[0], len(g[0]))                      # the same bytes behind an address
+    assert cov.fingerprint((ctypes.addressof(buf), g[1])) == cov.fingerprint(g)
+    assert cov.fingerprint((b'', np.zeros(0, np.int32))) == 0
