@@ -70,6 +70,28 @@ def fingerprint(gathered, max_samples=64):
     return crc
 
 
+def fingerprint_lists(groupings, per_list=16):
+    """The same idea for a list of probe lists that are NOT gathered on this rank (group-sharded runs gather only
+    the groupings a rank owns): lengths of the lists and up to `per_list` evenly spaced sequences of each."""
+    import zlib
+    crc = 0
+    for probes in groupings:
+        if not isinstance(probes, (list, tuple, ProbeBatch)):
+            continue                                     # some other iterable: nothing to sample without consuming it
+        n = len(probes)
+        crc = zlib.crc32(b'%d;' % n, crc)
+        if n == 0:
+            continue
+        idx = sorted(set(int(round(x)) for x in np.linspace(0, n - 1, num=min(n, per_list)).tolist()))
+        if isinstance(probes, ProbeBatch):
+            crc = zlib.crc32(probes.data[np.asarray(idx, dtype=np.int64)].tobytes(), crc)
+        else:
+            for i in idx:
+                p = probes[i]
+                crc = zlib.crc32((p if isinstance(p, str) else p.seq_str).encode('latin-1'), crc)
+    return crc
+
+
 def offsets_from_lengths(lens):
     """int64 offsets [n + 1] of sequences of the given lengths laid back to back."""
     n = len(lens)

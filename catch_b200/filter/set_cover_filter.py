@@ -356,7 +356,8 @@ class SetCoverFilter(BaseFilter):
                 prefetch.close()
         if sharded:
             chain.finish()
-        chosen_per_group = parallel.exchange_group_results(local, owner, rank, failure) if sharded else \
+        chosen_per_group = parallel.exchange_group_results(local, owner, rank, failure,
+                                                           token=cov.fingerprint_lists(input)) if sharded else \
             [local[i] for i in range(len(input))]
         selected = []
         for possible_probes, chosen in zip(input, chosen_per_group):

@@ -41,13 +41,15 @@ def _dist():
     return dist if dist.is_available() and dist.is_initialized() else None
 
 
-def exchange_group_results(local, owner, rank, failure=None):
+def exchange_group_results(local, owner, rank, failure=None, token=0):
     """local: {group index: list of selected indices} for the groupings this rank owns.  Returns the list of all
     results in grouping order on every rank.  Two fixed-shape all-reduces over the control backend (gloo,
     CPU tensors): the lengths of every grouping's result plus one failure slot per rank, then one flat
     index tensor that each rank fills in at its groupings' offsets -- no pickling, no per-object
     collectives.  `failure`: the exception that stopped this rank, if any; its presence is exchanged
-    with the lengths so that EVERY rank raises instead of some of them waiting for ever in a collective."""
+    with the lengths so that EVERY rank raises instead of some of them waiting for ever in a collective.
+    `token`: a checksum of the input lists (coverage.fingerprint_lists); the results are indices into those lists, so
+    every rank must hold the same lists in the same order -- compared here, in the same all-reduce."""
     n = len(owner)
     dist = _dist()
     if dist is None or dist.get_world_size() == 1:
@@ -56,17 +58,22 @@ def exchange_group_results(local, owner, rank, failure=None):
         return [local[i] for i in range(n)]
     torch = sys.modules['torch']
     world_size = dist.get_world_size()
-    head = torch.zeros(n + world_size, dtype=torch.int64)
+    head = torch.zeros(n + 2 * world_size, dtype=torch.int64)
     for i, res in local.items():
         head[i] = len(res) + 1                       # +1: "computed", so that an empty result is told from a missing one
     if failure is not None:
         head[n + rank] = 1
+    head[n + world_size + rank] = int(token) & 0x3fffffffffffffff
     dist.all_reduce(head)
     failed = [r for r in range(world_size) if int(head[n + r])]
     if failure is not None:
         raise failure
     if failed:
         raise RuntimeError("rank %d failed: see that rank's log for the exception" % failed[0])
+    if len(set(head[n + world_size:].tolist())) != 1:
+        raise RuntimeError("ranks hold different probe lists (or the same probes in a different order): the selected "
+                           "indices cannot be exchanged.  A list ordered by a Python set differs between processes "
+                           "unless PYTHONHASHSEED is pinned")
     counts = head[:n].tolist()
     missing = [i for i in range(n) if counts[i] == 0]
     if missing:
