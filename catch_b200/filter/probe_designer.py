@@ -110,14 +110,14 @@ class ProbeDesigner:
     def _candidates_as_batch(self, genomes_from_group):
         """The candidates of one grouping as one buffer (catch_b200/probe_batch.py), or None when a sequence is
         shorter than the probe length (then --small-seq-min / the error of candidate_probes.py:53-70 applies)."""
-        batches = []
+        seqs = []
         for g in genomes_from_group:
             if not isinstance(g.seqs, list) or len(g.seqs) == 0 or not all(isinstance(s, str) for s in g.seqs):
                 return None
-            b = ProbeBatch.from_sequences(g.seqs, self.probe_length, self.probe_stride,
-                                          seq_length_to_skip=self.seq_length_to_skip)
-            if b is None:
-                return None
-            batches.append(b)
-        out = ProbeBatch.concat(batches)
-        return out if out is not None else []
+            seqs.extend(g.seqs)
+        # all sequences of the grouping in one call (genome order, then sequence order, as :249-256 concatenates them)
+        out = ProbeBatch.from_sequences(seqs, self.probe_length, self.probe_stride,
+                                        seq_length_to_skip=self.seq_length_to_skip)
+        if out is None:
+            return None
+        return out if len(out) else []
