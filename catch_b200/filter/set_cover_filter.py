@@ -114,7 +114,7 @@ class _DrawChain:
                 self.error = e
             self.events[g].set()
 
-    def get(self, g):
+    def get(self, g, true_lengths=None):
         self.events[g].wait()
         if self.error is not None:
             raise self.error
@@ -126,6 +126,79 @@ class _DrawChain:
             req.wait()
         if self.n_groups:
             parallel.rng_broadcast(self.owner[-1])            # everyone ends where a single process would
+
+
+class _DrawReplay:
+    """Seed draws of a group-sharded run without any communication: EVERY rank makes the draws of ALL groupings,
+    in grouping order, on a helper thread, and keeps those of the groupings it owns.  numpy's stream is a chain
+    (grouping g continues where g-1 stopped, set_cover_filter.py:824-827), and the number of raw outputs a grouping
+    consumes is only known by generating them (rejection sampling) -- but generating them is cheap now (AVX-512
+    replay, ~1.6 ms for 128 k probes x 20 draws), cheaper than a hop of the token chain above (draw + send + wake-up),
+    and the draws of grouping g are ready on every rank g x 1.6 ms after the start instead of g hops later.  Every
+    rank ends with the state a single process would have: no broadcast.
+    Only the lengths of the probes enter the draws.  A rank does not look at the probes of groupings it does not own;
+    it takes them to be as long as a few evenly spaced samples of the list say (candidate probes are: one length),
+    and measures the whole list only when the samples disagree.  The owner checks the assumption against the lengths
+    it gathers and fails loudly if it does not hold (CB_DRAW=chain selects the token chain, which assumes nothing)."""
+
+    def __init__(self, flt, input, owner, rank):
+        self.flt, self.owner, self.rank, self.n_groups = flt, owner, rank, len(input)
+        self.mine = set(g for g in range(len(input)) if owner[g] == rank)
+        self.lengths = [self._lengths_of(p) for p in input]
+        self.events = {g: threading.Event() for g in self.mine}
+        self.results, self.error = {}, {}
+        self.thread = threading.Thread(target=self._run, name='cb-draw-replay', daemon=True)
+        self.thread.start()
+
+    @staticmethod
+    def _lengths_of(probes):
+        """(n, L) when all probes are taken to be L long, else the int32 array of all lengths."""
+        if isinstance(probes, ProbeBatch):
+            return len(probes), probes.probe_length
+        if not isinstance(probes, (list, tuple)):
+            probes = list(probes)
+        n = len(probes)
+        if n == 0:
+            return 0, 0
+        idx = sorted(set(int(round(x)) for x in np.linspace(0, n - 1, num=min(n, 48)).tolist()))
+        sample = cov.probe_lengths([probes[i] for i in idx])
+        if bool((sample == sample[0]).all()):
+            return n, int(sample[0])
+        return cov.probe_lengths(probes)
+
+    def assumed_lengths(self, g):
+        lens = self.lengths[g]
+        return np.full(lens[0], lens[1], dtype=np.int32) if isinstance(lens, tuple) else lens
+
+    def _run(self):
+        flt = self.flt
+        for g in range(self.n_groups):
+            drawn = drawn_tol = None
+            try:
+                lens = self.assumed_lengths(g)
+                if len(lens):
+                    drawn = cov.draw_seeds(lens, flt.mismatches, flt.lcf_thres, flt.kmer_probe_map_k)
+                    if flt._needs_ranks():
+                        drawn_tol = cov.draw_seeds(lens, flt.mismatches_tolerant, flt.lcf_thres_tolerant,
+                                                   flt.kmer_probe_map_k)
+            except BaseException as e:             # parameters rejected: raised where the grouping is processed
+                self.error[g] = e
+            if g in self.mine:
+                self.results[g] = (drawn, drawn_tol)
+                self.events[g].set()
+
+    def get(self, g, true_lengths=None):
+        self.events[g].wait()
+        if g in self.error:
+            raise self.error[g]
+        if true_lengths is not None and not np.array_equal(np.asarray(true_lengths, dtype=np.int64),
+                                                           self.assumed_lengths(g).astype(np.int64)):
+            raise RuntimeError("grouping %d: probes of different lengths were not seen by the length samples of the "
+                               "draw replay; run with CB_DRAW=chain" % g)
+        return self.results.pop(g)
+
+    def finish(self):
+        self.thread.join()
 
 
 class _Prefetch:
@@ -320,7 +393,9 @@ class SetCoverFilter(BaseFilter):
         else:
             owner = [rank] * len(input)
         local = {}
-        chain = _DrawChain(self, input, owner, rank) if sharded else None
+        chain = None
+        if sharded:
+            chain = (_DrawChain if os.environ.get('CB_DRAW', 'replay') == 'chain' else _DrawReplay)(self, input, owner, rank)
         failure = None
         mine = [g for g in range(len(input)) if owner[g] == rank]
         prefetch = None
@@ -396,7 +471,7 @@ class SetCoverFilter(BaseFilter):
             gathered, staged, release = pre
         try:
             if sharded:
-                drawn, drawn_tol = chain.get(group_i)
+                pass                             # the draws come from the chain / replay thread, fetched after the upload
             elif n_probes and gathered is not None:
                 # prefetched: the lengths are known, the draw runs on the library's worker thread during the upload
                 drawn = cov.draw_seeds(gathered[1], self.mismatches, self.lcf_thres, self.kmer_probe_map_k,
@@ -446,10 +521,16 @@ class SetCoverFilter(BaseFilter):
                 finally:
                     if not sharded:
                         drawn = cov.finish_draw(drawn)
+                if sharded:
+                    # only now: gather, upload and packing do not need the draws, and the wait for this grouping's
+                    # turn in the stream overlaps them
+                    drawn, drawn_tol = chain.get(group_i, lengths)
                 if self._needs_ranks() and not sharded:
                     drawn_tol = cov.draw_seeds(lengths, self.mismatches_tolerant, self.lcf_thres_tolerant,
                                                self.kmer_probe_map_k)
                 mark('seed_draw_wait')
+            elif sharded:
+                chain.get(group_i)
         finally:
             if release is not None:
                 release()                        # the staging pair may take the next grouping

@@ -32,7 +32,10 @@ from tests import helpers  # noqa: E402
 # so the MinHash parameters -- and the output -- differ from run to run even under a fixed seed.
 # That case is therefore recorded as non-deterministic: only the probe count (a statistical
 # reference point) is kept.
-NON_DETERMINISTIC = {'two_groups_minhash'}
+NON_DETERMINISTIC = {'two_groups_minhash', 'large_defaults'}
+# cases run through design_large.py's defaults (args_type 'large': -m 5 -e 50, MinHash near-duplicate filter 0.6,
+# --cluster-and-design-separately 0.15 --cluster-from-fragments 50000)
+LARGE = {'large_defaults'}
 
 CASES = {
     # name: (generator calls [(n_genomes, length, div, seed)] one per FASTA/grouping, CLI args)
@@ -54,6 +57,7 @@ CASES = {
     'cluster_adapters': ([[(5, 1800, 0.04, 29), (5, 1800, 0.04, 30)]],
                          ['-pl', '75', '-m', '2', '-l', '60', '--cluster-and-design-separately', '0.15',
                           '--add-adapters']),
+    'large_defaults': ([[(8, 2000, 0.03, 31), (8, 2000, 0.03, 32)]], ['-l', '60']),
 }
 
 
@@ -76,13 +80,13 @@ def main():
             paths = write_inputs(tmp, gen)
             fasta = os.path.join(tmp, 'out.fasta')
             sys.argv = ['design.py'] + paths + cli + ['-o', fasta, '--max-num-processes', '1']
-            args = ref_design.init_and_parse_args('basic')
+            args = ref_design.init_and_parse_args('large' if name in LARGE else 'basic')
             np.random.seed(7)
             random.seed(7)
             ref_design.main(args)
             data = open(fasta, 'rb').read()
             out[name] = dict(gen=gen, cli=cli, n_probes=data.count(b'>'), md5=hashlib.md5(data).hexdigest(),
-                             deterministic=name not in NON_DETERMINISTIC)
+                             deterministic=name not in NON_DETERMINISTIC, args_type='large' if name in LARGE else 'basic')
             print(name, out[name]['n_probes'], out[name]['md5'])
     with open(os.path.join(HERE, 'cli.json'), 'w') as f:
         json.dump(out, f, indent=1, sort_keys=True)

@@ -19,21 +19,21 @@ import sys, random
 sys.path.insert(0, %(bin)r)
 import numpy as np
 import design
-args = design.init_and_parse_args('basic', %(argv)r)
+args = design.init_and_parse_args(%(args_type)r, %(argv)r)
 np.random.seed(7); random.seed(7)
 design.main(args)
 '''
 
 
 @pytest.mark.parametrize('name', ['config1', 'zika_small', 'two_groups_minhash', 'identify', 'cluster_simple',
-                                  'cluster_fragments', 'cluster_skip_set_cover', 'cluster_adapters'])
+                                  'cluster_fragments', 'cluster_skip_set_cover', 'cluster_adapters', 'large_defaults'])
 def test_design_cli_matches_reference_fasta(tmp_path, name):
     want = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'cli.json')))[name]
     paths = helpers.write_cli_inputs(tmp_path, want['gen'])
     out = str(tmp_path / 'out.fasta')
     argv = paths + want['cli'] + ['-o', out]
     env = dict(os.environ, PYTHONHASHSEED='0')
-    code = RUNNER % dict(bin=os.path.join(ROOT, 'bin'), argv=argv)
+    code = RUNNER % dict(bin=os.path.join(ROOT, 'bin'), argv=argv, args_type=want.get('args_type', 'basic'))
     r = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     data = open(out, 'rb').read()

@@ -92,9 +92,12 @@ def _free_port():
     return port
 
 
-@pytest.mark.parametrize('world_size', [1, 2])
-def test_group_sharding_over_gloo(tmp_path, world_size):
+@pytest.mark.parametrize('world_size,draw', [(1, 'replay'), (2, 'replay'), (2, 'chain')])
+def test_group_sharding_over_gloo(tmp_path, monkeypatch, world_size, draw):
+    """draw: how a group-sharded run gets its seed draws -- every rank replays the whole stream (default) or the
+    RNG state travels from owner to owner (CB_DRAW=chain); both must reproduce the single-process stream."""
     import multiprocessing as mp
+    monkeypatch.setenv('CB_DRAW', draw)
     ctxm = mp.get_context('spawn')
     port = _free_port()
     paths = [str(tmp_path / ('r%d.npy' % r)) for r in range(world_size)]
