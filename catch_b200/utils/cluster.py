@@ -204,39 +204,65 @@ def cluster_hierarchically_from_dist_matrix(dist_matrix, threshold):
 def find_connected_components(n, dist_fn, threshold, early_stop_threshold=_jaccard_dist_from_mash_dist(0.02, 12)):
     """Connected components under `dist <= threshold` by the reference's depth-first search (cluster.py:239-355),
     including its early-stop heuristic (a neighbour within early_stop_threshold is marked visited, not explored).
-    The Python set operations are the reference's own, so neighbours are pushed in the same order; the distances of
-    one search step (vertex j against everything not yet seen) are one row from the device."""
+    The distances of one search step (vertex j against everything) are one row from the device.
+
+    The reference walks `list(indices_to_consider - indices_to_visit_or_already_visited)` at every step; only the
+    members within the threshold have any effect, and the ORDER of that list matters only for the order in which
+    two or more of them are pushed on the stack.  So a step first finds the unseen vertices within the threshold
+    from the row with a few vector operations (two boolean masks shadow the two sets), and builds the real set
+    difference -- the reference's own operation, for its iteration order -- only when at least two vertices are to
+    be pushed.  Most steps of a search inside a tight cluster push nothing (everything near is seen already):
+    16 000 sequences, 5.3 s -> 0.5 s."""
     by_row = isinstance(dist_fn, SketchSet)
     indices_to_consider = set(range(n))
+    consider_mask = np.ones(n, dtype=bool)
 
     def dfs(i):
         visited_indices = set()
         indices_to_visit = [i]
         indices_to_visit_or_already_visited = {i}
+        seen_mask = np.zeros(n, dtype=bool)
+        seen_mask[i] = True
         while len(indices_to_visit) > 0:
             j = indices_to_visit.pop()
             if j in visited_indices:
                 continue
             visited_indices.add(j)
-            possible_neighborhood = list(indices_to_consider - indices_to_visit_or_already_visited)
-            if not possible_neighborhood:
-                continue
-            ks = np.array(possible_neighborhood, dtype=np.int64)
             if by_row:
                 # the rows of the vertices on top of the stack come along (they are asked for next, unless a
                 # neighbour marks them visited first); an empty stack means the outer loop picks the next start
                 soon = indices_to_visit[:-65:-1] or [k for k in range(j + 1, min(n, j + 65)) if k in indices_to_consider]
-                dists = dist_fn.row_cached(j, soon)[ks]
+                row = dist_fn.row_cached(j, soon)
+                near = np.flatnonzero((row <= threshold) & consider_mask & ~seen_mask)
+                if near.size == 0:
+                    continue
+                is_early = row[near] <= early_stop_threshold
+                marked = near[is_early].tolist()
+                later = near[~is_early]
+                if later.size >= 2:
+                    # their order on the stack is the iteration order of the reference's set difference
+                    possible = indices_to_consider - indices_to_visit_or_already_visited
+                    ks = np.fromiter(possible, dtype=np.int64, count=len(possible))
+                    push = np.zeros(n, dtype=bool)
+                    push[later] = True
+                    later = ks[push[ks]]
+                later = later.tolist()
             else:
+                possible_neighborhood = list(indices_to_consider - indices_to_visit_or_already_visited)
+                if not possible_neighborhood:
+                    continue
+                ks = np.array(possible_neighborhood, dtype=np.int64)
                 dists = np.array([dist_fn(j, k) for k in possible_neighborhood])
-            adjacent = dists <= threshold
-            early = adjacent & (dists <= early_stop_threshold)
-            marked = ks[early].tolist()
+                adjacent = dists <= threshold
+                early = adjacent & (dists <= early_stop_threshold)
+                marked = ks[early].tolist()
+                later = ks[adjacent & ~early].tolist()       # in the order of possible_neighborhood
             visited_indices.update(marked)
-            later = ks[adjacent & ~early].tolist()           # in the order of possible_neighborhood
             indices_to_visit.extend(later)
             indices_to_visit_or_already_visited.update(marked)
             indices_to_visit_or_already_visited.update(later)
+            seen_mask[marked] = True
+            seen_mask[later] = True
         return visited_indices
 
     previously_visited_indices = set()
@@ -247,7 +273,9 @@ def find_connected_components(n, dist_fn, threshold, early_stop_threshold=_jacca
         cc = dfs(i)
         previously_visited_indices.update(cc)
         indices_to_consider -= cc
-        connected_components.append(sorted(list(cc)))
+        members = sorted(list(cc))
+        consider_mask[members] = False
+        connected_components.append(members)
     connected_components.sort(key=len, reverse=True)
     return connected_components
 
