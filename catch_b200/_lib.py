@@ -497,6 +497,18 @@ def default_context():
     return _default_ctx
 
 
+_extra_ctx = {}
+
+
+def extra_context(device_id, index):
+    """Further contexts (own stream, own staging buffers) on a device, created on first use and kept: a filter that
+    works on two groupings at a time gives each worker thread its own."""
+    key = (int(device_id), int(index))
+    if key not in _extra_ctx:
+        _extra_ctx[key] = Context(device_id)
+    return _extra_ctx[key]
+
+
 def split_lengths(raw, n, sep=10):
     """Lengths of the n strings joined with `sep` into the bytes object `raw`; None when the
     separator also occurs inside a string."""

@@ -128,6 +128,10 @@ class _DrawChain:
             parallel.rng_broadcast(self.owner[-1])            # everyone ends where a single process would
 
 
+class _LengthsNotUniform(RuntimeError):
+    """The length samples of a draw replay missed probes of another length (see _DrawReplay)."""
+
+
 class _DrawReplay:
     """Seed draws of a group-sharded run without any communication: EVERY rank makes the draws of ALL groupings,
     in grouping order, on a helper thread, and keeps those of the groupings it owns.  numpy's stream is a chain
@@ -193,8 +197,8 @@ class _DrawReplay:
             raise self.error[g]
         if true_lengths is not None and not np.array_equal(np.asarray(true_lengths, dtype=np.int64),
                                                            self.assumed_lengths(g).astype(np.int64)):
-            raise RuntimeError("grouping %d: probes of different lengths were not seen by the length samples of the "
-                               "draw replay; run with CB_DRAW=chain" % g)
+            raise _LengthsNotUniform("grouping %d: probes of different lengths were not seen by the length samples "
+                                     "of the draw replay; run with CB_DRAW=chain" % g)
         return self.results.pop(g)
 
     def finish(self):
@@ -303,10 +307,14 @@ class SetCoverFilter(BaseFilter):
         self.requires_probe_groupings = True
         self._force_num_processes = None       # accepted and ignored (tests set it)
         self._ctx = None
+        self._tls = threading.local()          # per worker thread: the context it drives, its host timings
         self.last_stats = []                   # one dict per grouping of the last _filter call
 
     # ------------------------------------------------------------------ helpers
     def _context(self):
+        ctx = getattr(self._tls, 'ctx', None)
+        if ctx is not None:
+            return ctx
         if self._ctx is None:
             self._ctx = _lib.default_context()
         return self._ctx
@@ -398,6 +406,20 @@ class SetCoverFilter(BaseFilter):
             chain = (_DrawChain if os.environ.get('CB_DRAW', 'replay') == 'chain' else _DrawReplay)(self, input, owner, rank)
         failure = None
         mine = [g for g in range(len(input)) if owner[g] == rank]
+        # Two groupings at a time (CB_PIPELINE=1: one): see _run_pipelined
+        n_workers = min(len(mine), max(1, int(os.environ.get('CB_PIPELINE', '2'))))
+        if n_workers >= 2 and isinstance(self._context(), _lib.Context):
+            state0 = np.random.get_state()
+            try:
+                local, failure = self._run_pipelined(input, target_genomes_grouped, mine, chain, n_workers)
+                mine = []                            # done
+            except _LengthsNotUniform:
+                if sharded:
+                    raise
+                np.random.set_state(state0)          # rare (mixed probe lengths): the plain loop measures every list
+                local, failure = {}, None
+            if failure is not None and not sharded:
+                raise failure
         prefetch = None
         if len(mine) >= 2 and cov._fastpack is not None and hasattr(self._context(), 'host_buffer') and \
                 os.environ.get('CB_PREFETCH', '1') == '1':
@@ -441,6 +463,53 @@ class SetCoverFilter(BaseFilter):
             selected.append(possible_probes.probes(list(chosen)) if isinstance(possible_probes, ProbeBatch) else
                             [possible_probes[i] for i in chosen])
         return selected
+
+    def _run_pipelined(self, input, target_genomes_grouped, mine, chain, n_workers):
+        """The groupings `mine` on n_workers threads, each driving its own context (stream, staging buffers) on the
+        device: while one grouping is in a library call (the GIL is released), the host work of the next -- gather,
+        seed plan, result lists -- runs on the other thread, and its uploads and kernels queue up behind on their own
+        stream.  The seed draws come from ONE helper thread in grouping order (a single process replays the stream
+        exactly like a rank of a group-sharded run does, _DrawReplay), so the workers never touch numpy's RNG.
+        Returns ({grouping: selected indices}, first exception or None)."""
+        import queue
+        own_chain = chain is None
+        if own_chain:
+            chain = _DrawReplay(self, input, [0] * len(input), 0)
+        main = self._context()
+        contexts = [main] + [_lib.extra_context(main.device_id, w) for w in range(1, n_workers)]
+        todo = queue.SimpleQueue()
+        for g in mine:
+            todo.put(g)
+        local, errors = {}, []
+
+        def work(ctx):
+            self._tls.ctx = ctx
+            try:
+                while not errors:
+                    try:
+                        g = todo.get_nowait()
+                    except queue.Empty:
+                        return
+                    probes = input[g] if isinstance(input[g], (list, tuple, ProbeBatch)) else list(input[g])
+                    local[g] = self._filter_one_group(g, len(input), probes, target_genomes_grouped[g],
+                                                      target_genomes_grouped, chain, None)
+            except BaseException as e:               # noqa: BLE001 -- handed to the caller
+                errors.append(e)
+            finally:
+                self._tls.ctx = None
+
+        threads = [threading.Thread(target=work, args=(c,), name='cb-group-worker') for c in contexts[1:]]
+        for t in threads:
+            t.start()
+        work(main)
+        for t in threads:
+            t.join()
+        if own_chain:
+            chain.finish()
+        for e in errors:
+            if isinstance(e, _LengthsNotUniform):
+                raise e
+        return local, (errors[0] if errors else None)
 
     def _filter_one_group(self, group_i, n_groups, possible_probes, target_genomes, target_genomes_grouped, chain,
                           pre=None):
@@ -543,7 +612,7 @@ class SetCoverFilter(BaseFilter):
                                         self.kmer_probe_map_k, lengths=lengths, may_have_dups=dups,
                                         drawn=drawn_tol)
             mark('seed_plan')
-        self._host_ms = host_ms
+        self._tls.host_ms = host_ms
         return self._select_for_group(group_i, n_groups, probe_strs, group, plan, plan_tol,
                                       target_genomes, target_genomes_grouped)
 
@@ -696,5 +765,5 @@ class SetCoverFilter(BaseFilter):
                      upload_targets=group.st_targets.as_dict(),
                      upload_probes=group.st_probes.as_dict(),
                      coverage=st_a.as_dict(), setcover=st_b.as_dict(),
-                     wall_s=time.perf_counter() - t0, host_ms=dict(getattr(self, '_host_ms', {})))
+                     wall_s=time.perf_counter() - t0, host_ms=dict(getattr(self._tls, 'host_ms', {})))
         return list(chosen)

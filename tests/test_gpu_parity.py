@@ -429,26 +429,58 @@ def test_probe_batch_filter_chain_equals_probe_lists(ctx):
         assert sum(map(len, outs[0][1])) > 10
 
 
-def test_prefetch_thread_does_not_change_the_output(ctx, monkeypatch):
-    """Several groupings in one filter() call: the helper thread that gathers the next grouping while the current
-    one is on the device (on by default) gives the same selection, in the same order, as the plain loop."""
+def test_pipelining_and_prefetch_do_not_change_the_output(ctx, monkeypatch):
+    """Several groupings in one filter() call: two groupings at a time on two contexts with the draws replayed by a
+    helper thread (default), one at a time with the helper thread that gathers the next grouping, and the plain loop
+    all give the same selection in the same order, and leave numpy's RNG in the same state."""
     import random as pyrandom
     from catch_b200 import probe
     from catch_b200.filter.set_cover_filter import SetCoverFilter
-    groups = helpers.synthetic_taxa(5, 12, seed=9, length_range=(1500, 3000))
+    from catch_b200.probe_batch import ProbeBatch
+    groups = helpers.synthetic_taxa(7, 12, seed=9, length_range=(1500, 3000))
     genomes = helpers.to_genomes([[[s] for s in g] for g in groups])
     cands = [list(dict.fromkeys(helpers.tile_candidates(g, 100, 50))) for g in groups]
     probes = [[probe.Probe.from_str(s) for s in c] for c in cands]
+    batches = [ProbeBatch(np.frombuffer(''.join(c).encode(), dtype=np.uint8).reshape(len(c), 100)) for c in cands]
     outs = []
-    for flag in ('1', '0', '1'):
-        monkeypatch.setenv('CB_PREFETCH', flag)
+    for pipeline, prefetch, inp in (('2', '1', probes), ('1', '1', probes), ('1', '0', probes), ('2', '1', batches),
+                                    ('3', '1', probes)):
+        monkeypatch.setenv('CB_PIPELINE', pipeline)
+        monkeypatch.setenv('CB_PREFETCH', prefetch)
         scf = SetCoverFilter(mismatches=3, lcf_thres=40, cover_extension=10)
         scf._ctx = ctx
         np.random.seed(5)
         pyrandom.seed(5)
-        outs.append([[p.seq_str for p in g] for g in scf.filter(probes, genomes, input_is_grouped=True)])
-    assert outs[0] == outs[1] == outs[2]
-    assert all(len(g) > 0 for g in outs[0])
+        out = scf.filter(inp, genomes, input_is_grouped=True)
+        outs.append(([[p.seq_str for p in g] for g in out], int(np.random.randint(0, 1 << 30))))
+        assert all(s is not None for s in scf.last_stats)
+    assert all(o == outs[0] for o in outs[1:])
+    assert all(len(g) > 0 for g in outs[0][0])
+
+
+def test_pipelining_falls_back_on_mixed_probe_lengths(ctx, monkeypatch):
+    """The draw replay takes a probe list to be as uniform as its length samples say; a list with a few probes of
+    another length that the samples miss makes the filter redo the call with the plain loop (which measures every
+    list) from the saved RNG state: same result as CB_PIPELINE=1."""
+    import random as pyrandom
+    from catch_b200 import probe
+    from catch_b200.filter.set_cover_filter import SetCoverFilter
+    groups = helpers.synthetic_taxa(3, 10, seed=11, length_range=(1500, 2500))
+    genomes = helpers.to_genomes([[[s] for s in g] for g in groups])
+    cands = [list(dict.fromkeys(helpers.tile_candidates(g, 100, 50))) for g in groups]
+    cands[1][7] = cands[1][7][:80]                        # one shorter probe, not at a sampled position
+    cands[1][-3] = cands[1][-3][:90]
+    probes = [[probe.Probe.from_str(s) for s in c] for c in cands]
+    outs = []
+    for pipeline in ('2', '1'):
+        monkeypatch.setenv('CB_PIPELINE', pipeline)
+        scf = SetCoverFilter(mismatches=3, lcf_thres=40, cover_extension=10)
+        scf._ctx = ctx
+        np.random.seed(6)
+        pyrandom.seed(6)
+        out = scf.filter(probes, genomes, input_is_grouped=True)
+        outs.append(([[p.seq_str for p in g] for g in out], int(np.random.randint(0, 1 << 30))))
+    assert outs[0] == outs[1]
 
 
 @pytest.mark.parametrize('n_genomes', [20, 45, 100, 200, 400, 800])
