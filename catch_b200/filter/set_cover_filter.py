@@ -406,8 +406,10 @@ class SetCoverFilter(BaseFilter):
             chain = (_DrawChain if os.environ.get('CB_DRAW', 'replay') == 'chain' else _DrawReplay)(self, input, owner, rank)
         failure = None
         mine = [g for g in range(len(input)) if owner[g] == rank]
-        # Two groupings at a time (CB_PIPELINE=1: one): see _run_pipelined
-        n_workers = min(len(mine), max(1, int(os.environ.get('CB_PIPELINE', '2'))))
+        # Up to three groupings at a time (CB_PIPELINE=1: one after the other): see _run_pipelined.  V-All shape, 16
+        # taxa, one B200: 1 / 2 / 3 workers = 219 / 212 / 188 ms from lists of Probe objects, 173 / 153 / 147 ms from
+        # ProbeBatch input
+        n_workers = min(len(mine), max(1, int(os.environ.get('CB_PIPELINE', '3'))))
         if n_workers >= 2 and isinstance(self._context(), _lib.Context):
             state0 = np.random.get_state()
             try:
