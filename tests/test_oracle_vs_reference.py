@@ -90,3 +90,48 @@ def test_set_cover_filter_random_vs_reference(ref):
                                  params['island_of_exact_match'], params['coverage'],
                                  params['cover_extension'], params['kmer_probe_map_k'])
         assert got == want
+
+
+def test_tiling_fasta_and_cluster_oracle_against_the_live_reference(ref, tmp_path):
+    """The callers in front of the filters, live: vectorised candidate tiling, the native FASTA
+    parser, and the oracle's sketch / clustering restatement against the reference's own modules."""
+    import catch.filter.candidate_probes as rcp
+    import catch.utils.cluster as rcluster
+    import catch.utils.seq_io as rseq_io
+    from catch_b200.probe_batch import ProbeBatch
+    from catch_b200.utils import seq_io
+    from oracle import oracle
+    import logging
+    logging.disable(logging.WARNING)
+    try:
+        rng = random.Random(31)
+        for _ in range(60):
+            seqs = []
+            for _ in range(rng.randint(1, 8)):
+                n = rng.randint(60, 400)
+                s = [rng.choice('ACGT') for _ in range(n)]
+                if rng.random() < 0.4:
+                    for _ in range(rng.randint(1, 3)):
+                        a = rng.randrange(n)
+                        for i in range(a, min(n, a + rng.choice([1, 2, 3, 10]))):
+                            s[i] = 'N'
+                seqs.append(''.join(s))
+            L, st = rng.choice([40, 60]), rng.choice([7, 20, 30, 60])
+            want = rcp.make_candidate_probes_from_sequences(seqs, probe_length=L, probe_stride=st)
+            got = ProbeBatch.from_sequences(seqs, L, st)
+            assert [(p.seq_str, p.is_flanking_n_string) for p in got] == [(p.seq_str, p.is_flanking_n_string) for p in want]
+        fn = str(tmp_path / 'x.fasta')
+        with open(fn, 'w') as f:
+            f.write('>a b\r\nacgt-ry\r\nNNtt\n\n>c\nAC GT\t\n>a b\nTTTT\n')
+        assert list(seq_io.read_fasta(fn).items()) == list(rseq_io.read_fasta(fn).items())
+        seqs = {}
+        for g in range(3):
+            for i, s in enumerate(helpers.synthetic_genomes(5, 1200, 0.05, 50 + g)):
+                seqs['g%d_%d' % (g, i)] = s
+        for method in ('simple', 'hierarchical'):
+            random.seed(2)
+            want = rcluster.cluster_with_minhash_signatures(seqs, threshold=0.12, cluster_method=method)
+            random.seed(2)
+            assert oracle.cluster_with_minhash_signatures(seqs, threshold=0.12, cluster_method=method) == want
+    finally:
+        logging.disable(logging.NOTSET)
