@@ -51,7 +51,7 @@ EXPORTED_SYMBOLS = [
     'cb_coverage_range', 'cb_coverage_records', 'cb_free_host', 'cb_exchange_alloc', 'cb_exchange_bytes', 'cb_exchange_handle', 'cb_exchange_attach',
     'cb_exchange_required', 'cb_setcover_sharded', 'cb_setcover_sharded_begin', 'cb_setcover_sharded_end',
     'cb_sketch_sequences', 'cb_sketches_import', 'cb_sketches_export', 'cb_sketches_free', 'cb_sketch_dist_rows',
-    'cb_sketch_dist_condensed',
+    'cb_sketch_dist_condensed', 'cb_sketch_near_rows',
 ]
 
 _lib = None
@@ -135,6 +135,7 @@ def load():
     L.cb_sketches_free.restype = None
     L.cb_sketch_dist_rows.argtypes = [vp, vp, vp, i64, vp]
     L.cb_sketch_dist_condensed.argtypes = [vp, vp, vp]
+    L.cb_sketch_near_rows.argtypes = [vp, vp, vp, i64, C.c_double, vp, C.POINTER(vp), C.POINTER(vp)]
     _lib = L
     return L
 
@@ -458,6 +459,26 @@ class Context:
         if out.size:
             self._check(self.L.cb_sketch_dist_rows(self.h, sketches.h, _ptr(rows), len(rows), _ptr(out)))
         return out
+
+    def sketch_near_rows(self, sketches, rows, threshold):
+        """cb_sketch_near_rows: (row_off int64 [len(rows) + 1], columns uint32, distances float64) of the sketches
+        within `threshold` of each row, columns ascending."""
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        off = np.zeros(len(rows) + 1, dtype=np.int64)
+        idx, dist = C.c_void_p(), C.c_void_p()
+        self._check(self.L.cb_sketch_near_rows(self.h, sketches.h, _ptr(rows), len(rows), float(threshold), _ptr(off),
+                                               C.byref(idx), C.byref(dist)))
+        total = int(off[-1])
+        try:
+            if total == 0:
+                return off, np.zeros(0, dtype=np.uint32), np.zeros(0, dtype=np.float64)
+            return (off, np.ctypeslib.as_array(C.cast(idx, C.POINTER(C.c_uint32)), shape=(total,)).copy(),
+                    np.ctypeslib.as_array(C.cast(dist, C.POINTER(C.c_double)), shape=(total,)).copy())
+        finally:
+            if idx.value:
+                self.L.cb_free_host(idx)
+            if dist.value:
+                self.L.cb_free_host(dist)
 
     def sketch_dist_condensed(self, sketches, n):
         out = np.zeros(n * (n - 1) // 2, dtype=np.float32)

@@ -710,6 +710,16 @@ int cb_sketch_dist_rows(cb_ctx *ctx, const cb_sketches *sk, const int64_t *rows,
     return cb_sketch_dist_rows_impl(ctx, sk, rows, n_rows, out);
 }
 
+int cb_sketch_near_rows(cb_ctx *ctx, const cb_sketches *sk, const int64_t *rows, int64_t n_rows, double threshold,
+                        int64_t *row_off, uint32_t **idx, double **dist)
+{
+    if (!ctx) return CB_ERR_ARG;
+    ctx->launches = 0;
+    CB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cb_tls_stream = ctx->stream;
+    return cb_sketch_near_rows_impl(ctx, sk, rows, n_rows, threshold, row_off, idx, dist);
+}
+
 int cb_sketch_dist_condensed(cb_ctx *ctx, const cb_sketches *sk, float *out)
 {
     if (!ctx) return CB_ERR_ARG;

@@ -342,7 +342,117 @@ sketch_condensed_kernel(const uint32_t *__restrict__ sig, int64_t n, int N, floa
     out[i * n - i * (i + 3) / 2 + j - 1] = (float)jaccard_dist(inter, uni);
 }
 
+// The sketches within `threshold` of each requested row, as compact (column, distance) lists in ascending column
+// order: what one step of the connected-components search needs (cluster.py:270-290 looks at every distance of the
+// row, but only those within the threshold have an effect).  Pass 1 counts per row, pass 2 writes at the row's offset.
+__global__ void __launch_bounds__(256)
+near_count_kernel(const double *__restrict__ d, int64_t n, double threshold, uint32_t *__restrict__ counts)
+{
+    const double *row = d + (int64_t)blockIdx.x * n;
+    uint32_t c = 0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) c += row[i] <= threshold;
+    __shared__ uint32_t s_w[8];
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < 8; w++) t += s_w[w];
+        counts[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+near_compact_kernel(const double *__restrict__ d, int64_t n, double threshold, const int64_t *__restrict__ row_off,
+                    uint32_t *__restrict__ idx_out, double *__restrict__ dist_out)
+{
+    const double *row = d + (int64_t)blockIdx.x * n;
+    __shared__ uint32_t s_w[8];
+    __shared__ uint32_t s_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    const int64_t out0 = row_off[blockIdx.x];
+    for (int64_t i0 = 0; i0 < n; i0 += blockDim.x) {
+        const int64_t i = i0 + threadIdx.x;
+        const double v = i < n ? row[i] : 2.0;
+        const bool hit = i < n && v <= threshold;
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0) s_w[warp] = __popc(m);
+        __syncthreads();
+        uint32_t before = s_base;
+        for (int w = 0; w < warp; w++) before += s_w[w];
+        if (hit) {
+            const int64_t o = out0 + before + __popc(m & ((1u << lane) - 1u));
+            idx_out[o] = (uint32_t)i;
+            dist_out[o] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t t = 0;
+            for (int w = 0; w < 8; w++) t += s_w[w];
+            s_base += t;
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace
+
+int cb_sketch_near_rows_impl(cb_ctx *ctx, const cb_sketches *sk, const int64_t *rows, int64_t n_rows, double threshold,
+                             int64_t *row_off, uint32_t **idx, double **dist)
+{
+    if (!sk || !row_off || !idx || !dist || (n_rows > 0 && !rows)) return cb_fail(ctx, CB_ERR_ARG, "cb_sketch_near_rows: NULL argument");
+    *idx = nullptr;
+    *dist = nullptr;
+    row_off[0] = 0;
+    for (int64_t r = 0; r < n_rows; r++) row_off[r + 1] = 0;
+    if (n_rows == 0 || sk->n == 0) return CB_OK;
+    for (int64_t r = 0; r < n_rows; r++)
+        if (rows[r] < 0 || rows[r] >= sk->n) return cb_fail(ctx, CB_ERR_ARG, "cb_sketch_near_rows: row out of range");
+    if (n_rows > 65535) return cb_fail(ctx, CB_ERR_ARG, "cb_sketch_near_rows: at most 65535 rows per call");
+    cudaStream_t st = ctx->stream;
+    cb_tls_stream = st;
+    const int64_t n = sk->n;
+    DevBuf<int64_t> d_rows, d_off;
+    DevBuf<double> d_full, d_dist;
+    DevBuf<uint32_t> d_counts, d_idx;
+    if (d_rows.alloc((size_t)n_rows) != cudaSuccess || d_full.alloc((size_t)n_rows * n) != cudaSuccess ||
+        d_counts.alloc((size_t)n_rows) != cudaSuccess || d_off.alloc((size_t)n_rows + 1) != cudaSuccess)
+        return cb_fail(ctx, CB_ERR_NOMEM, "cb_sketch_near_rows: out of device memory");
+    CB_CUDA(ctx, cudaMemcpyAsync(d_rows.p, rows, (size_t)n_rows * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    dim3 grid((unsigned)((n + 127) / 128), (unsigned)n_rows);
+    sketch_rows_kernel<<<grid, 128, 0, st>>>(sk->d_sig, n, sk->N, d_rows.p, d_full.p);
+    near_count_kernel<<<(unsigned)n_rows, 256, 0, st>>>(d_full.p, n, threshold, d_counts.p);
+    CB_CUDA(ctx, cudaGetLastError());
+    std::vector<uint32_t> h_counts((size_t)n_rows);
+    CB_CUDA(ctx, cudaMemcpyAsync(h_counts.data(), d_counts.p, (size_t)n_rows * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CB_CUDA(ctx, cudaStreamSynchronize(st));
+    for (int64_t r = 0; r < n_rows; r++) row_off[r + 1] = row_off[r] + (int64_t)h_counts[(size_t)r];
+    const int64_t total = row_off[n_rows];
+    ctx->launches += 2;
+    if (total == 0) return CB_OK;
+    if (d_idx.alloc((size_t)total) != cudaSuccess || d_dist.alloc((size_t)total) != cudaSuccess)
+        return cb_fail(ctx, CB_ERR_NOMEM, "cb_sketch_near_rows: out of device memory");
+    CB_CUDA(ctx, cudaMemcpyAsync(d_off.p, row_off, (size_t)(n_rows + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    near_compact_kernel<<<(unsigned)n_rows, 256, 0, st>>>(d_full.p, n, threshold, d_off.p, d_idx.p, d_dist.p);
+    CB_CUDA(ctx, cudaGetLastError());
+    ctx->launches++;
+    uint32_t *h_idx = (uint32_t *)malloc((size_t)total * sizeof(uint32_t));
+    double *h_dist = (double *)malloc((size_t)total * sizeof(double));
+    if (!h_idx || !h_dist) { free(h_idx); free(h_dist); return cb_fail(ctx, CB_ERR_NOMEM, "cb_sketch_near_rows: out of host memory"); }
+    if (cudaMemcpyAsync(h_idx, d_idx.p, (size_t)total * sizeof(uint32_t), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaMemcpyAsync(h_dist, d_dist.p, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess) {
+        free(h_idx);
+        free(h_dist);
+        return cb_fail(ctx, CB_ERR_CUDA, "cb_sketch_near_rows: copy failed");
+    }
+    *idx = h_idx;
+    *dist = h_dist;
+    return CB_OK;
+}
 
 int cb_sketch_sequences_impl(cb_ctx *ctx, const uint8_t *ascii, const int64_t *seq_off, int64_t n, int32_t k,
                              int32_t N, uint64_t a, uint64_t b, cb_sketches **out, cb_stats *stats)

@@ -232,3 +232,5 @@ int cb_sketch_import_impl(cb_ctx *ctx, const uint32_t *sig, int64_t n, int32_t N
 int cb_sketches_export_impl(cb_ctx *ctx, const cb_sketches *sk, uint32_t *sig);
 int cb_sketch_dist_rows_impl(cb_ctx *ctx, const cb_sketches *sk, const int64_t *rows, int64_t n_rows, double *out);
 int cb_sketch_dist_condensed_impl(cb_ctx *ctx, const cb_sketches *sk, float *out);
+int cb_sketch_near_rows_impl(cb_ctx *ctx, const cb_sketches *sk, const int64_t *rows, int64_t n_rows, double threshold,
+                             int64_t *row_off, uint32_t **idx, double **dist);

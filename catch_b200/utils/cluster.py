@@ -138,6 +138,28 @@ class SketchSet:
             r = got[0]
         return r
 
+    def near_cached(self, j, threshold, soon=()):
+        """(columns, distances) of the sketches within `threshold` of sketch j, columns ascending -- row_cached's
+        answer reduced on the device to the part a search step uses (cb_sketch_near_rows), with the same
+        fetch-ahead of the rows asked for next."""
+        cache = self.__dict__.setdefault('_near_cache', {})
+        if cache.get('threshold') != threshold:
+            cache.clear()
+            cache['threshold'] = threshold
+        r = cache.pop(j, None)
+        if r is None:
+            if len(cache) > 512:
+                cache.clear()
+                cache['threshold'] = threshold
+            want = [j] + [k for k in soon if k != j and k not in cache]
+            want = want[:max(1, min(len(want), (256 << 20) // max(8 * self.n, 1)))]   # <= 256 MB of full rows on the device
+            off, idx, dist = self.ctx.sketch_near_rows(self.h, want, threshold)
+            idx = idx.astype(np.int64)
+            for t, k in enumerate(want[1:], start=1):
+                cache[k] = (idx[off[t]:off[t + 1]], dist[off[t]:off[t + 1]])
+            r = (idx[off[0]:off[1]], dist[off[0]:off[1]])
+        return r
+
     def condensed(self):
         return self.ctx.sketch_dist_condensed(self.h, self.n)
 
@@ -204,12 +226,13 @@ def cluster_hierarchically_from_dist_matrix(dist_matrix, threshold):
 def find_connected_components(n, dist_fn, threshold, early_stop_threshold=_jaccard_dist_from_mash_dist(0.02, 12)):
     """Connected components under `dist <= threshold` by the reference's depth-first search (cluster.py:239-355),
     including its early-stop heuristic (a neighbour within early_stop_threshold is marked visited, not explored).
-    The distances of one search step (vertex j against everything) are one row from the device.
+    The distances of one search step (vertex j against everything) are one row on the device, of which the part
+    within the threshold comes back (cb_sketch_near_rows).
 
     The reference walks `list(indices_to_consider - indices_to_visit_or_already_visited)` at every step; only the
     members within the threshold have any effect, and the ORDER of that list matters only for the order in which
-    two or more of them are pushed on the stack.  So a step first finds the unseen vertices within the threshold
-    from the row with a few vector operations (two boolean masks shadow the two sets), and builds the real set
+    two or more of them are pushed on the stack.  So a step first picks the unseen vertices among those within the
+    threshold with a few vector operations (two boolean masks shadow the two sets), and builds the real set
     difference -- the reference's own operation, for its iteration order -- only when at least two vertices are to
     be pushed.  Most steps of a search inside a tight cluster push nothing (everything near is seen already):
     16 000 sequences, 5.3 s -> 0.5 s."""
@@ -232,11 +255,12 @@ def find_connected_components(n, dist_fn, threshold, early_stop_threshold=_jacca
                 # the rows of the vertices on top of the stack come along (they are asked for next, unless a
                 # neighbour marks them visited first); an empty stack means the outer loop picks the next start
                 soon = indices_to_visit[:-65:-1] or [k for k in range(j + 1, min(n, j + 65)) if k in indices_to_consider]
-                row = dist_fn.row_cached(j, soon)
-                near = np.flatnonzero((row <= threshold) & consider_mask & ~seen_mask)
+                cols, dists = dist_fn.near_cached(j, threshold, soon)
+                unseen = consider_mask[cols] & ~seen_mask[cols]
+                near = cols[unseen]
                 if near.size == 0:
                     continue
-                is_early = row[near] <= early_stop_threshold
+                is_early = dists[unseen] <= early_stop_threshold
                 marked = near[is_early].tolist()
                 later = near[~is_early]
                 if later.size >= 2:

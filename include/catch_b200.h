@@ -351,6 +351,13 @@ void cb_sketches_free(cb_sketches *sk);
  * out[r * n_seqs + c], the double the reference's Python arithmetic gives (1.0 - intersect / union).  One call
  * serves one step of find_connected_components' search (utils/cluster.py:270-290). */
 int cb_sketch_dist_rows(cb_ctx *ctx, const cb_sketches *sk, const int64_t *rows, int64_t n_rows, double *out);
+/* The same rows, reduced to what a search step uses: for each of rows[r] the sketches c with
+ * distance <= threshold, as (column, distance) pairs in ascending column order.  Row r's pairs are
+ * idx[row_off[r] .. row_off[r+1]) / dist[...]; row_off (n_rows + 1 entries) is caller-allocated, *idx and *dist are
+ * allocated by the library (cb_free_host; NULL when nothing is within the threshold).  The distances are the same
+ * doubles cb_sketch_dist_rows returns; only the copy back shrinks (a row of 40 000 doubles to a few thousand pairs). */
+int cb_sketch_near_rows(cb_ctx *ctx, const cb_sketches *sk, const int64_t *rows, int64_t n_rows, double threshold,
+                        int64_t *row_off, uint32_t **idx, double **dist);
 /* cluster.create_condensed_dist_matrix (utils/cluster.py:103-195): all n(n-1)/2 distances in scipy's condensed
  * order, rounded to float32 as the reference's shared c_float array does (:141-142). */
 int cb_sketch_dist_condensed(cb_ctx *ctx, const cb_sketches *sk, float *out);

@@ -105,3 +105,19 @@ def test_sequence_shorter_than_kmer_is_rejected(ctx):
         ctx.sketch_sequences(b'ACGTACGTACG', np.array([0, 11], dtype=np.int64), 12, 100, 5, 7)
     with pytest.raises(_lib.CatchB200Error):
         ctx.sketch_sequences(b'ACGTACGTACGTT', np.array([0, 13], dtype=np.int64), 12, 2000, 5, 7)
+
+
+def test_near_rows_are_the_thresholded_distance_rows(ctx, gold):
+    """cb_sketch_near_rows: the part of cb_sketch_dist_rows within the threshold, same doubles, ascending columns."""
+    for c in gold['sketches']:
+        n = len(c['sigs'])
+        sk = cluster.SketchSet.from_signatures(np.array(c['sigs'], dtype=np.uint32), ctx)
+        full = sk.rows(list(range(n)))
+        for thr in (0.0, 0.3, 0.8, 1.0):
+            rows = list(range(n - 1, -1, -1))
+            off, idx, dist = ctx.sketch_near_rows(sk.h, rows, thr)
+            assert off[0] == 0 and len(off) == n + 1 and off[-1] == len(idx) == len(dist)
+            for t, r in enumerate(rows):
+                want = np.flatnonzero(full[r] <= thr)
+                assert idx[off[t]:off[t + 1]].tolist() == want.tolist(), (c['name'], thr, r)
+                assert np.array_equal(dist[off[t]:off[t + 1]], full[r][want])
