@@ -734,11 +734,15 @@ scan_kernel(const ScanParams P)
                             // diagonal, shares the mismatch-free run and gives the same range.
                             const uint32_t g = (uint32_t)(ent.y & 0xffull);
                             if (g != 0u && g <= (tg >> 24)) {
+                                // g <= 28 bases per plane: 32-bit reads of the tile and one funnel shift each
                                 const int off = j + CB_FRONT_PAD - (int)g;
-                                uint64_t diff = 0ull;
+                                const uint32_t *t32 = reinterpret_cast<const uint32_t *>(s_tile) + (off >> 5);
+                                const int sh = off & 31;
+                                uint32_t diff = 0u;
                                 for (int b = 0; b < P.bits; b++)
-                                    diff |= read64(s_tile + b * TW, off) ^ (ent.y >> (8 + b * pw));
-                                surv = (diff << (64 - g)) != 0ull;
+                                    diff |= __funnelshift_r(t32[b * 2 * TW], t32[b * 2 * TW + 1], sh) ^
+                                            (uint32_t)(ent.y >> (8 + b * pw));
+                                surv = (diff << (32 - g)) != 0u;
                             }
                             task = ((uint64_t)j << 40) | (ent.x >> 24);      // j | probe << 8 | pos
                         }
