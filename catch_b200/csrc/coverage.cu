@@ -430,16 +430,13 @@ __device__ __forceinline__ void mismatch_mask(const ScanParams &P, const uint64_
 // ---------------------------------------------------------------------------------------
 struct U128 { uint64_t lo, hi; };
 
-// bits [a, b) of a 128-bit mask, 0 <= a <= b <= 128
-__device__ __forceinline__ U128 range128(int a, int b)
+// bits [0, x) of a 128-bit mask, 0 <= x <= 128
+__device__ __forceinline__ U128 below128(int x)
 {
     U128 r;
-    const uint64_t ge_lo = a < 64 ? (~0ull << a) : 0ull;
-    const uint64_t ge_hi = a <= 64 ? ~0ull : (~0ull << (a - 64));
-    const uint64_t lt_lo = b >= 64 ? ~0ull : ((1ull << b) - 1ull);
-    const uint64_t lt_hi = b <= 64 ? 0ull : (b >= 128 ? ~0ull : ((1ull << (b - 64)) - 1ull));
-    r.lo = ge_lo & lt_lo;
-    r.hi = ge_hi & lt_hi;
+    const int nl = x < 64 ? x : 64, nh = x > 64 ? x - 64 : 0;
+    r.lo = nl == 64 ? ~0ull : ((1ull << nl) - 1ull);
+    r.hi = nh == 64 ? ~0ull : ((1ull << nh) - 1ull);
     return r;
 }
 
@@ -465,19 +462,6 @@ __device__ __forceinline__ U128 mismatch_mask_fast(const ScanParams &P, const ui
     return M;
 }
 
-__device__ __forceinline__ int ffs128(U128 x)
-{
-    return x.lo ? (__ffsll((long long)x.lo) - 1) : (x.hi ? (64 + __ffsll((long long)x.hi) - 1) : -1);
-}
-__device__ __forceinline__ int fls128(U128 x)
-{
-    return x.hi ? (127 - __clzll((long long)x.hi)) : (x.lo ? (63 - __clzll((long long)x.lo)) : -1);
-}
-__device__ __forceinline__ void clear128(U128 &x, int b)
-{
-    if (b < 64) x.lo &= ~(1ull << b); else x.hi &= ~(1ull << (b - 64));
-}
-
 // anchored extension (utils/longest_common_substring.py:59-159) on scalar 128-bit masks.
 // ML / MR: mismatches strictly left of the anchor / at or right of its end, already clipped to [a, b).
 __device__ __forceinline__ int anchored_extend_fast(U128 ML, U128 MR, int a, int b, int s, int k, int m,
@@ -488,8 +472,11 @@ __device__ __forceinline__ int anchored_extend_fast(U128 ML, U128 MR, int a, int
     const int after_full = b - (s + k);
     int n_right = 0;
     for (int j = 0; j <= m; j++) {
-        const int pos = ffs128(MR);
-        if (pos < 0) break;
+        // lowest mismatch right of the anchor; it is cleared with w & (w - 1) on the word that holds it
+        const bool in_lo = MR.lo != 0ull;
+        const uint64_t w = in_lo ? MR.lo : MR.hi;
+        if (w == 0ull) break;
+        const int pos = (in_lo ? 0 : 64) + __ffsll((long long)w) - 1;
         const uint64_t v = (uint64_t)(pos - (s + k));
         if (j < 8) aft[0] |= v << (j * 8);
         else {
@@ -497,7 +484,7 @@ __device__ __forceinline__ int anchored_extend_fast(U128 ML, U128 MR, int a, int
             for (int q = 1; q < 4; q++)
                 if ((j >> 3) == q) aft[q] |= v << ((j & 7) * 8);
         }
-        clear128(MR, pos);
+        if (in_lo) MR.lo = w & (w - 1ull); else MR.hi = w & (w - 1ull);
         n_right++;
     }
     auto after = [&](int j) -> int {
@@ -512,13 +499,18 @@ __device__ __forceinline__ int anchored_extend_fast(U128 ML, U128 MR, int a, int
     };
     int best_len = -1, best_start = -1, bef0 = 0;
     for (int i = 0; i <= m; i++) {
-        const int hp = fls128(ML);
+        // highest mismatch left of the anchor
+        const bool in_hi = ML.hi != 0ull;
+        const uint64_t wl = in_hi ? ML.hi : ML.lo;
+        const int lz = __clzll((long long)wl);                           // 64 when wl == 0
+        const int hp = wl ? (in_hi ? 127 : 63) - lz : -1;
         const int bef = hp >= 0 ? (s - 1 - hp) : (s - a);
         if (i == 0) bef0 = bef;
         const int tot = bef + k + after(m - i);
         if (tot > best_len) { best_len = tot; best_start = s - bef; }     // strict '>' (:154)
         if (hp < 0) break;
-        clear128(ML, hp);
+        const uint64_t cleared = wl & ~(0x8000000000000000ull >> lz);
+        if (in_hi) ML.hi = cleared; else ML.lo = cleared;
     }
     start = best_start;
     exact_len = bef0 + k + after(0);
@@ -566,12 +558,12 @@ __device__ __forceinline__ bool eval_hit(const ScanParams &P, const uint64_t *s_
         static_assert(NW == 2, "the scalar 128-bit path is for two-word probes");
         const int k = P.k;
         const U128 M = mismatch_mask_fast(P, s_tile, t0, d, p);
-        const U128 S = range128(pos, pos + k);
-        if ((M.lo & S.lo) | (M.hi & S.hi)) return false;
-        const U128 RL = range128(a, pos), RR = range128(pos + k, bnd);
+        // the three ranges [pos, pos+k), [a, pos), [pos+k, bnd) from four "bits below x" masks
+        const U128 la = below128(a), lp = below128(pos), lk = below128(pos + k), lb = below128(bnd);
+        if ((M.lo & lk.lo & ~lp.lo) | (M.hi & lk.hi & ~lp.hi)) return false;
         U128 ML, MR;
-        ML.lo = M.lo & RL.lo; ML.hi = M.hi & RL.hi;
-        MR.lo = M.lo & RR.lo; MR.hi = M.hi & RR.hi;
+        ML.lo = M.lo & lp.lo & ~la.lo; ML.hi = M.hi & lp.hi & ~la.hi;
+        MR.lo = M.lo & lb.lo & ~lk.lo; MR.hi = M.hi & lb.hi & ~lk.hi;
         len = anchored_extend_fast(ML, MR, a, bnd, pos, k, P.m, start, exact_len);
     } else {
         uint64_t M[NW];
