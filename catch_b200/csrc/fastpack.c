@@ -27,13 +27,14 @@ static void *copy_worker(void *arg)
     copy_job *j = (copy_job *)arg;
     char *d = j->dst;
     for (Py_ssize_t i = j->begin; i < j->end; i++) {
+        if (i + 8 < j->end) __builtin_prefetch(j->src[i + 8]);      /* the strings are scattered over the heap */
         memcpy(d, j->src[i], (size_t)j->len[i]);
         d += j->len[i];
     }
     return NULL;
 }
 
-#define PAR_COPY_MIN_BYTES (8u << 20)
+#define PAR_COPY_MIN_BYTES (2u << 20)
 #define PAR_COPY_THREADS 6
 
 /* gather(seq, attr) -> (bytes data, bytes lengths_int32)
@@ -163,6 +164,7 @@ static PyObject *gather_impl(PyObject *args, int into)
             for (Py_ssize_t k = 0; k < n; k++) Py_DECREF(strs[k]);
         } else {
             for (Py_ssize_t i = 0; i < n; i++) {
+                if (copy && i + 8 < n) __builtin_prefetch(PyUnicode_1BYTE_DATA(strs[i + 8]));
                 if (copy) memcpy(dst, PyUnicode_1BYTE_DATA(strs[i]), (size_t)lens[i]);
                 dst += lens[i];
                 Py_DECREF(strs[i]);
