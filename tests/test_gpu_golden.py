@@ -361,3 +361,63 @@ def test_scale_goldens_config2_and_config3_shapes(ctx):
     kept_idx = sorted(first[p.seq_str] for p in kept)
     assert kept_idx == c['kept_idx']
     check_scf([c3[i] for i in kept_idx], [[s] for s in segs], c)
+
+
+def test_scale_goldens_config4_shape_and_config5_sweep(ctx):
+    """Oracle-generated goldens (tests/golden/make_scale_golden2.py).  Config-4 shape: 6 taxa x 40 genomes as six
+    groupings through ONE SetCoverFilter.filter() call seeded once -- the device path works on several groupings at a
+    time with the draws replayed by a helper thread, and must give the oracle's sequential result (selection, order,
+    and the state numpy's RNG is left in), from lists of Probe objects and from ProbeBatch input.  Config 5: nine
+    m x l cells on the config-3 input: interval counts, pick sequences and output order."""
+    import hashlib
+    from catch_b200 import coverage as cov
+    from catch_b200 import probe
+    from catch_b200.filter.set_cover_filter import SetCoverFilter
+    from catch_b200.probe_batch import ProbeBatch
+    gold = golden_io.load('scale_oracle2.json.gz')
+
+    def md5(strs):
+        return hashlib.md5('\n'.join(strs).encode()).hexdigest()
+
+    c = gold['config4_6x40']
+    groups = helpers.synthetic_taxa(c['n_taxa'], c['n_genomes'], seed=c['gen_seed'])
+    cands = [list(dict.fromkeys(helpers.tile_candidates(g, c['pl'], c['ps']))) for g in groups]
+    assert [len(x) for x in cands] == c['n_cands'] and [md5(x) for x in cands] == c['cands_md5']
+    genomes = helpers.to_genomes([[[s] for s in g] for g in groups])
+    inputs = {'lists': [[probe.Probe.from_str(s) for s in x] for x in cands],
+              'batch': [ProbeBatch(np.frombuffer(''.join(x).encode(), dtype=np.uint8).reshape(len(x), c['pl'])) for x in cands]}
+    for kind, inp in inputs.items():
+        f = SetCoverFilter(**c['scf'])
+        f._ctx = ctx
+        np.random.seed(c['np_seed'])
+        random.seed(c['np_seed'])
+        out = f.filter(inp, genomes, input_is_grouped=True)
+        for g in range(c['n_taxa']):
+            assert [p.seq_str for p in out[g]] == [cands[g][i] for i in c['selected'][g]], (kind, g)
+        assert int(np.random.randint(0, 1 << 30)) == c['rng_after'], kind
+
+    c3 = golden_io.load('scale_oracle.json.gz')['config3_40']
+    gens = helpers.synthetic_influenza(c3['n_genomes'], seed=c3['gen_seed'])
+    segs = [seg for g in gens for seg in g]
+    tiles = helpers.tile_candidates(segs, c3['pl'], c3['ps'])
+    scf_in = [tiles[i] for i in c3['kept_idx']]
+    seq_groups = [[s] for s in segs]
+    genomes = helpers.to_genomes([seq_groups])
+    probes = [probe.Probe.from_str(s) for s in scf_in]
+    ids = {id(p): i for i, p in enumerate(probes)}
+    c5 = gold['config5_40']
+    for cell in c5['cells']:
+        group = cov.PackedGroup(ctx, scf_in, seq_groups)
+        np.random.seed(c5['np_seed'])
+        plan = cov.SeedPlan(scf_in, cell['m'], cell['l'], 20)
+        cover, st = cov.compute_cover(ctx, group, plan, cell['m'], cell['l'], 0, c5['cover_extension'])
+        group.free()
+        assert int(st.n_intervals) == cell['n_intervals'], (cell['m'], cell['l'])
+        picks, _ = ctx.setcover(cover, len(scf_in))
+        cover.free()
+        assert picks.tolist() == cell['picks'], (cell['m'], cell['l'])
+        f = SetCoverFilter(mismatches=cell['m'], lcf_thres=cell['l'], cover_extension=c5['cover_extension'])
+        f._ctx = ctx
+        np.random.seed(c5['np_seed'])
+        out = f.filter([probes], genomes, input_is_grouped=True)
+        assert [ids[id(p)] for p in out[0]] == cell['selected'], (cell['m'], cell['l'])
