@@ -34,7 +34,7 @@ static void *copy_worker(void *arg)
     return NULL;
 }
 
-#define PAR_COPY_MIN_BYTES (2u << 20)
+#define PAR_COPY_MIN_BYTES (8u << 20)
 #define PAR_COPY_THREADS 6
 
 /* gather(seq, attr) -> (bytes data, bytes lengths_int32)
