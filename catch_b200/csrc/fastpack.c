@@ -34,7 +34,19 @@ static void *copy_worker(void *arg)
     return NULL;
 }
 
-#define PAR_COPY_MIN_BYTES (8u << 20)
+/* copies of at least this many bytes are spread over PAR_COPY_THREADS threads (CB_GATHER_PAR_MB overrides).  Measured on
+ * the B200 host (tools/gather_sweep.py, 100-byte strings): 7 MB 1.05 ms on one thread / 1.87 ms on six, 13 MB 2.2 / 2.8,
+ * 26 MB 6.1 / 5.3, 52 MB 27.8 / 17.3, 133 MB 73 / 48: the threads pay from about 20 MB on. */
+static size_t par_copy_min_bytes(void)
+{
+    static size_t v = 0;
+    if (!v) {
+        const char *e = getenv("CB_GATHER_PAR_MB");
+        long mb = e ? atol(e) : 24;
+        v = (size_t)(mb > 0 ? mb : 24) << 20;
+    }
+    return v;
+}
 #define PAR_COPY_THREADS 6
 
 /* gather(seq, attr) -> (bytes data, bytes lengths_int32)
@@ -136,7 +148,7 @@ static PyObject *gather_impl(PyObject *args, int into)
         char *dst = into ? (char *)(uintptr_t)address : PyBytes_AS_STRING(data);
         const int copy = !into || (into == 1 && total <= (size_t)capacity);
         const void **srcs = NULL;
-        if (copy && total >= PAR_COPY_MIN_BYTES && n >= 2 * PAR_COPY_THREADS)
+        if (copy && total >= par_copy_min_bytes() && n >= 2 * PAR_COPY_THREADS)
             srcs = (const void **)malloc(sizeof(void *) * (size_t)n);
         if (srcs) {
             copy_job jobs[PAR_COPY_THREADS];

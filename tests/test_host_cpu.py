@@ -183,14 +183,26 @@ def test_background_draw_can_be_cancelled_without_touching_the_rng():
 
 
 def test_gather_large_input_takes_the_threaded_copy():
-    """More than 8 MB in total: pass 2 of the gather runs on several threads with the GIL released."""
-    from catch_b200 import coverage as cov
-    rng = np.random.default_rng(1)
-    strs = [''.join('ACGT'[i] for i in rng.integers(0, 4, int(n))) for n in rng.integers(50_000, 150_000, 120)]
-    strs += ['', 'N', 'ACGT' * 3]
-    assert sum(map(len, strs)) > (8 << 20)
-    data, lens = cov.gather_probes(strs)
-    assert data == ''.join(strs).encode() and lens.tolist() == [len(s) for s in strs]
+    """Pass 2 of the gather runs on several threads with the GIL released above a size threshold (24 MB; the
+    threshold is read once per process, so the threaded path is exercised in a child with CB_GATHER_PAR_MB=1)."""
+    import subprocess
+    code = r'''
+import sys
+sys.path.insert(0, %r)
+import numpy as np
+from catch_b200 import coverage as cov
+rng = np.random.default_rng(1)
+strs = [''.join('ACGT'[i] for i in rng.integers(0, 4, int(n))) for n in rng.integers(50_000, 150_000, 40)]
+strs += ['', 'N', 'ACGT' * 3]
+assert sum(map(len, strs)) > (2 << 20)
+data, lens = cov.gather_probes(strs)
+assert data == ''.join(strs).encode() and lens.tolist() == [len(s) for s in strs]
+print('ok')
+''' % ROOT
+    for mb in ('1', '100000'):
+        r = subprocess.run([sys.executable, '-c', code], env=dict(os.environ, CB_GATHER_PAR_MB=mb), capture_output=True,
+                           text=True, timeout=120)
+        assert r.returncode == 0 and r.stdout.strip() == 'ok', r.stderr[-1500:]
 
 
 def test_mt19937_simd_and_scalar_paths_agree_with_numpy():
