@@ -311,6 +311,17 @@ class SetCoverFilter(BaseFilter):
         self.last_stats = []                   # one dict per grouping of the last _filter call
 
     # ------------------------------------------------------------------ helpers
+    def __getstate__(self):
+        # a filter travels without its device context and per-thread state (both are re-made on first use)
+        d = dict(self.__dict__)
+        d.pop('_tls', None)
+        d['_ctx'] = None
+        return d
+
+    def __setstate__(self, d):
+        self.__dict__.update(d)
+        self._tls = threading.local()
+
     def _context(self):
         ctx = getattr(self._tls, 'ctx', None)
         if ctx is not None:

@@ -390,3 +390,14 @@ def test_probe_list_fingerprint_sees_order_and_content():
     buf = ctypes.create_string_buffer(g[0], len(g[0]))                      # the same bytes behind an address
     assert cov.fingerprint((ctypes.addressof(buf), g[1])) == cov.fingerprint(g)
     assert cov.fingerprint((b'', np.zeros(0, np.int32))) == 0
+
+
+def test_set_cover_filter_survives_pickling():
+    """The filter object keeps per-thread state and a device context; neither travels through pickle / copy."""
+    import copy
+    import pickle
+    from catch_b200.filter.set_cover_filter import SetCoverFilter
+    f = SetCoverFilter(mismatches=2, lcf_thres=60, cover_extension=10, coverage=0.9)
+    for g in (pickle.loads(pickle.dumps(f)), copy.deepcopy(f)):
+        assert (g.mismatches, g.lcf_thres, g.cover_extension, g.coverage) == (2, 60, 10, 0.9)
+        assert g._ctx is None and getattr(g._tls, 'ctx', None) is None
