@@ -827,8 +827,8 @@ __global__ void scatter_by_probe_kernel(const uint4 *__restrict__ rec, unsigned 
 // probe's ranges fit, otherwise in place in global memory.  Then warp 0 merges overlapping or
 // touching ranges (utils/interval.py:304-314: start <= curr_end) in 32-wide chunks.
 // ---------------------------------------------------------------------------------------
-constexpr int MERGE_THREADS = 128;
-constexpr int MERGE_SMEM_CAP = 4096;
+constexpr int MERGE_THREADS = 512;
+constexpr int MERGE_SMEM_CAP = 12288;    // ranges sorted in (dynamic) shared memory: 96 KB, two CTAs per SM
 
 __device__ __forceinline__ void bitonic_sort(uint64_t *a, uint32_t n)
 {
@@ -912,24 +912,25 @@ __device__ __forceinline__ uint32_t warp_merge_sorted(const uint64_t *a, uint64_
     return n_out;
 }
 
-// Probes with more than MERGE_WARP_CAP ranges: one block per probe (see above).
+// Probes with more than MERGE_WARP_CAP ranges (a probe that hits thousands of genomes: the influenza shape): one block
+// per entry of the list the warp kernel left behind; sorted in shared memory up to MERGE_SMEM_CAP ranges, in place in
+// global memory beyond.
 __global__ void __launch_bounds__(MERGE_THREADS)
-merge_kernel(const int64_t *__restrict__ rec_off, uint64_t *__restrict__ rec, int64_t n_probes,
-             uint32_t *__restrict__ n_merged, uint32_t *__restrict__ max_len, uint32_t min_n,
-             const unsigned int *__restrict__ n_large)
+merge_kernel(const int64_t *__restrict__ rec_off, uint64_t *__restrict__ rec, uint32_t *__restrict__ n_merged,
+             uint32_t *__restrict__ max_len, const uint32_t *__restrict__ big_list, const unsigned int *__restrict__ n_big)
 {
-    __shared__ uint64_t s_rec[MERGE_SMEM_CAP];
-    if (n_large && *n_large == 0u) return;          // the warp kernels took every probe (the usual case)
+    extern __shared__ uint64_t s_rec[];
+    const unsigned int todo = *n_big;                // usually 0: the warp kernels took every probe
     uint32_t local_max = 0;
-    for (int64_t p = blockIdx.x; p < n_probes; p += gridDim.x) {
+    for (unsigned int i = blockIdx.x; i < todo; i += gridDim.x) {
+        const int64_t p = big_list[i];
         const int64_t o0 = rec_off[p];
         const uint32_t n = (uint32_t)(rec_off[p + 1] - o0);
-        if (n < min_n) continue;                    // done by merge_warp_kernel (block-uniform)
         uint64_t *g = rec + o0;
         uint64_t *a = g;
-        const bool in_smem = n <= MERGE_SMEM_CAP;
+        const bool in_smem = n <= (uint32_t)MERGE_SMEM_CAP;
         if (in_smem) {
-            for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) s_rec[i] = g[i];
+            for (uint32_t t = threadIdx.x; t < n; t += blockDim.x) s_rec[t] = g[t];
             a = s_rec;
         }
         __syncthreads();
@@ -1077,15 +1078,16 @@ __device__ __forceinline__ uint32_t warp_sort_merge(uint64_t *__restrict__ g, ui
 // WIDE = false: probes with at most 512 ranges (16 registers of ranges per lane: 64 registers per thread, eight
 // CTAs per SM); the probes with 513..1024 ranges are appended to wide_list and done by the WIDE = true launch, one
 // warp per list entry (few probes, each a long sort: spread over the whole grid instead of wherever they happen to
-// fall).  Probes with more than MERGE_WARP_CAP ranges set n_large and go to the block-per-probe kernel.
+// fall).  Probes with more than MERGE_WARP_CAP ranges are appended to big_list for the block-per-probe kernel.
 template <bool WIDE>
 __global__ void __launch_bounds__(MERGE_WARPS * 32, WIDE ? 3 : 8)
 merge_warp_kernel(const int64_t *__restrict__ rec_off, uint64_t *__restrict__ rec, int64_t n_probes,
-                  uint32_t *__restrict__ n_merged, uint32_t *__restrict__ max_len, unsigned int *__restrict__ n_large,
-                  uint32_t *__restrict__ wide_list, unsigned int *__restrict__ wide_count)
+                  uint32_t *__restrict__ n_merged, uint32_t *__restrict__ max_len, uint32_t *__restrict__ big_list,
+                  unsigned int *__restrict__ big_count, uint32_t *__restrict__ wide_list,
+                  unsigned int *__restrict__ wide_count)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t local_max = 0, large = 0;
+    uint32_t local_max = 0;
     if (WIDE) {
         const unsigned int n_wide = *wide_count;
         for (unsigned int i = blockIdx.x * MERGE_WARPS + warp; i < n_wide; i += gridDim.x * MERGE_WARPS) {
@@ -1106,8 +1108,10 @@ merge_warp_kernel(const int64_t *__restrict__ rec_off, uint64_t *__restrict__ re
                 continue;
             }
             if (n > 512u) {
-                if (n > (uint32_t)MERGE_WARP_CAP) large = 1u;
-                else if (lane == 0) wide_list[atomicAdd(wide_count, 1u)] = (uint32_t)p;
+                if (lane == 0) {
+                    if (n > (uint32_t)MERGE_WARP_CAP) big_list[atomicAdd(big_count, 1u)] = (uint32_t)p;
+                    else wide_list[atomicAdd(wide_count, 1u)] = (uint32_t)p;
+                }
                 continue;
             }
             if (n <= 32) n_out = warp_sort_merge<1>(g, n, lane, local_max);
@@ -1121,7 +1125,6 @@ merge_warp_kernel(const int64_t *__restrict__ rec_off, uint64_t *__restrict__ re
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, o));
     if (lane == 0 && local_max) atomicMax(max_len, local_max);
-    if (lane == 0 && large) atomicOr(n_large, 1u);
 }
 
 __global__ void compact_kernel(const int64_t *__restrict__ rec_off, const uint64_t *__restrict__ rec,
@@ -1145,27 +1148,34 @@ __global__ void compact_kernel(const int64_t *__restrict__ rec_off, const uint64
 int launch_merge(cb_ctx *ctx, const int64_t *d_roff, uint64_t *d_sorted, int64_t P, uint32_t *d_nmerged, uint32_t *d_maxlen)
 {
     cudaStream_t st = ctx->stream;
-    DevBuf<unsigned int> d_large;            // [0] some probe has more than MERGE_WARP_CAP ranges, [1] length of the wide list
-    DevBuf<uint32_t> d_wide;
+    DevBuf<unsigned int> d_large;            // [0] length of the big list, [1] length of the wide list
+    DevBuf<uint32_t> d_wide;                 // [0, P) wide list, [P, 2P) big list
+    const size_t Pn = (size_t)(P > 0 ? P : 1);
     CB_CUDA(ctx, d_large.alloc(2));
-    CB_CUDA(ctx, d_wide.alloc((size_t)(P > 0 ? P : 1)));
+    CB_CUDA(ctx, d_wide.alloc(2 * Pn));
     CB_CUDA(ctx, cudaMemsetAsync(d_large.p, 0, 2 * sizeof(unsigned int), st));
     int64_t g = (P + MERGE_WARPS - 1) / MERGE_WARPS;
     const int64_t cap = (int64_t)ctx->sm_count * 16;
     if (g > cap) g = cap;
     if (g < 1) g = 1;
-    merge_warp_kernel<false><<<(unsigned)g, MERGE_WARPS * 32, 0, st>>>(d_roff, d_sorted, P, d_nmerged, d_maxlen, d_large.p,
-                                                                       d_wide.p, d_large.p + 1);
-    merge_warp_kernel<true><<<(unsigned)g, MERGE_WARPS * 32, 0, st>>>(d_roff, d_sorted, P, d_nmerged, d_maxlen, d_large.p,
-                                                                      d_wide.p, d_large.p + 1);
+    merge_warp_kernel<false><<<(unsigned)g, MERGE_WARPS * 32, 0, st>>>(d_roff, d_sorted, P, d_nmerged, d_maxlen, d_wide.p + Pn,
+                                                                       d_large.p, d_wide.p, d_large.p + 1);
+    merge_warp_kernel<true><<<(unsigned)g, MERGE_WARPS * 32, 0, st>>>(d_roff, d_sorted, P, d_nmerged, d_maxlen, d_wide.p + Pn,
+                                                                      d_large.p, d_wide.p, d_large.p + 1);
     ctx->launches += 2;
     CB_CUDA(ctx, cudaGetLastError());
-    // probes with more ranges than the warp kernel takes: decided on the device (no host round trip in the
-    // middle of stage A); the blocks leave at once when there is none
-    int64_t gb = P < (int64_t)ctx->sm_count * 8 ? P : (int64_t)ctx->sm_count * 8;
-    if (gb < 1) gb = 1;
-    merge_kernel<<<(unsigned)gb, MERGE_THREADS, 0, st>>>(d_roff, d_sorted, P, d_nmerged, d_maxlen,
-                                                        (uint32_t)MERGE_WARP_CAP + 1u, d_large.p);
+    // probes with more ranges than the warp kernels take: listed on the device (no host round trip in the
+    // middle of stage A); the blocks leave at once when the list is empty
+    {
+        static bool attr_set[64] = {};
+        if (ctx->device < 0 || ctx->device >= 64 || !attr_set[ctx->device]) {
+            CB_CUDA(ctx, cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)(MERGE_SMEM_CAP * sizeof(uint64_t))));
+            if (ctx->device >= 0 && ctx->device < 64) attr_set[ctx->device] = true;
+        }
+    }
+    merge_kernel<<<(unsigned)(ctx->sm_count * 2), MERGE_THREADS, MERGE_SMEM_CAP * sizeof(uint64_t), st>>>(
+        d_roff, d_sorted, d_nmerged, d_maxlen, d_wide.p + Pn, d_large.p);
     ctx->launches++;
     CB_CUDA(ctx, cudaGetLastError());
     return CB_OK;

@@ -528,3 +528,27 @@ def test_range_list_sized_from_previous_scan_overflows_gracefully(ctx):
             assert st.n_raw_ranges > 70000              # more than the hint of the sparse scan allows for (~65.6 k)
         else:
             assert 0 < st.n_raw_ranges < 2000
+
+
+def test_merge_block_paths_on_tandem_repeats(ctx):
+    """A probe made of a short repeat unit against tandem-repeat genomes matches on thousands of diagonals: its range
+    list goes to the block-per-probe merge -- sorted in shared memory up to 12 288 ranges (the second case: ~4 600 per
+    probe), in place in global memory beyond (the first case: ~14 000 per probe).  All of them collapse to one
+    interval per genome."""
+    O = _oracle()
+    rng = random.Random(41)
+    unit = 'ACGGTCA'
+    flank = ''.join(rng.choice('ACGT') for _ in range(300))
+    probe_strs = [(unit * 12)[:60], (unit * 12)[3:63], flank[10:70], flank[100:160]]
+    params = dict(mismatches=1, lcf_thres=50, island_of_exact_match=0, cover_extension=0, kmer_probe_map_k=15)
+    for scale, at_least in ((3, 2 * 12288), (1, 2 * 4000)):
+        genomes = [[flank + unit * (720 * scale) + flank[::-1]], [unit * (1450 * scale) + flank],
+                   [flank + unit * (2450 * scale)]]
+        np.random.seed(2)
+        k, seeds, _ = O.choose_seeds(probe_strs, 1, 50, min_k=15, k=15)
+        want = O.make_sets_quads(O.SeedMap(probe_strs, seeds, k), genomes, 1, 50, 0, 0)
+        np.random.seed(2)
+        got, cover, st = _device_quads(ctx, probe_strs, genomes, params)
+        cover.free()
+        assert st.n_raw_ranges > at_least                      # the two repeat probes: one range per matching diagonal
+        assert np.array_equal(got, want)
