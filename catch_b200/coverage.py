@@ -39,7 +39,11 @@ def gather_staged(ctx, slot, items):
         total = int(items.data.size)
         addr, cap = ctx.host_buffer(slot, total)
         if total:
-            ctypes.memmove(addr, items.data.ctypes.data, total)
+            data = items.data if items.data.flags['C_CONTIGUOUS'] else np.ascontiguousarray(items.data)
+            if _fastpack is not None and hasattr(_fastpack, 'copy_into'):
+                _fastpack.copy_into(data, addr)          # threaded from 24 MB on, GIL released
+            else:
+                ctypes.memmove(addr, data.ctypes.data, total)
         return addr, items.lengths(), total
     if _fastpack is None or not hasattr(ctx, 'host_buffer'):
         return None

@@ -304,7 +304,51 @@ done:
     return ret;
 }
 
+
+/* copy_into(buffer, address) -> int bytes: one contiguous buffer (a ProbeBatch's byte matrix) into caller-owned memory
+ * (the library's page-locked staging buffer), on several threads from par_copy_min_bytes() on, GIL released. */
+typedef struct { const char *src; char *dst; size_t n; } span_job;
+static void *span_worker(void *arg)
+{
+    span_job *j = (span_job *)arg;
+    memcpy(j->dst, j->src, j->n);
+    return NULL;
+}
+
+static PyObject *copy_into(PyObject *self, PyObject *args)
+{
+    Py_buffer view;
+    unsigned long long address = 0;
+    if (!PyArg_ParseTuple(args, "y*K", &view, &address)) return NULL;
+    const size_t n = (size_t)view.len;
+    char *dst = (char *)(uintptr_t)address;
+    const char *src = (const char *)view.buf;
+    Py_BEGIN_ALLOW_THREADS
+    if (n >= par_copy_min_bytes()) {
+        span_job jobs[PAR_COPY_THREADS];
+        pthread_t th[PAR_COPY_THREADS];
+        int started[PAR_COPY_THREADS];
+        const size_t per = (n / PAR_COPY_THREADS + 4095) & ~(size_t)4095;
+        for (int t = 0; t < PAR_COPY_THREADS; t++) {
+            const size_t b = (size_t)t * per < n ? (size_t)t * per : n;
+            const size_t e = b + per < n ? b + per : n;
+            jobs[t].src = src + b; jobs[t].dst = dst + b; jobs[t].n = (t == PAR_COPY_THREADS - 1 ? n : e) - b;
+            started[t] = jobs[t].n > 0 && pthread_create(&th[t], NULL, span_worker, &jobs[t]) == 0;
+        }
+        for (int t = 0; t < PAR_COPY_THREADS; t++) {
+            if (started[t]) pthread_join(th[t], NULL);
+            else if (jobs[t].n > 0) span_worker(&jobs[t]);
+        }
+    } else {
+        memcpy(dst, src, n);
+    }
+    Py_END_ALLOW_THREADS
+    PyBuffer_Release(&view);
+    return PyLong_FromSize_t(n);
+}
+
 static PyMethodDef methods[] = {
+    {"copy_into", copy_into, METH_VARARGS, "copy_into(buffer, address) -> bytes copied (threaded for large buffers)"},
     {"parse_fasta", parse_fasta, METH_VARARGS,
      "parse_fasta(data, make_uppercase=True, replace_degenerate=True, skip_gaps=True) -> (names, sequences)"},
     {"gather", gather, METH_VARARGS, "gather(seq, attr) -> (bytes data, bytes int32 lengths)"},
