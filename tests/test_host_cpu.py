@@ -401,3 +401,57 @@ def test_set_cover_filter_survives_pickling():
     for g in (pickle.loads(pickle.dumps(f)), copy.deepcopy(f)):
         assert (g.mismatches, g.lcf_thres, g.cover_extension, g.coverage) == (2, 60, 10, 0.9)
         assert g._ctx is None and getattr(g._tls, 'ctx', None) is None
+
+
+def test_draw_replay_reproduces_the_sequential_stream():
+    """_DrawReplay (every rank / worker gets the seed draws of its groupings from one helper thread that replays ALL
+    groupings in order) against plain sequential draws: same draws for every grouping, same RNG state afterwards;
+    lists of Probe objects, str lists, ProbeBatch input, a list whose length samples disagree (measured in full) and
+    one whose odd-length probes the samples miss (the owner's check raises)."""
+    from catch_b200 import coverage as cov, probe
+    from catch_b200.filter import set_cover_filter as scf_mod
+    from catch_b200.probe_batch import ProbeBatch
+    rng = np.random.default_rng(3)
+    letters = np.frombuffer(b'ACGT', dtype=np.uint8)
+
+    def strs(n, L):
+        flat = letters[rng.integers(0, 4, (n, L), dtype=np.uint8)].tobytes().decode()
+        return [flat[i * L:(i + 1) * L] for i in range(n)]
+    g0 = [probe.Probe.from_str(s) for s in strs(300, 100)]
+    g1 = strs(120, 100)
+    g2 = ProbeBatch(letters[rng.integers(0, 4, (200, 100), dtype=np.uint8)])
+    g3 = [probe.Probe.from_str(s) for s in (strs(50, 100) + strs(50, 80) + strs(60, 100))]      # samples see both lengths
+    g4 = []
+    inputs = [g0, g1, g2, g3, g4]
+    flt = scf_mod.SetCoverFilter(mismatches=2, lcf_thres=60)
+
+    def lengths(g):
+        return cov.probe_lengths(g) if len(g) else np.zeros(0, dtype=np.int32)
+    np.random.seed(11)
+    want = []
+    for g in inputs:
+        lens = lengths(g)
+        want.append(np.asarray(cov.finish_draw(cov.draw_seeds(lens, 2, 60, 20))[1]) if len(lens) else None)
+    after = int(np.random.randint(0, 1 << 30))
+    for owner, rank in (([0] * 5, 0), ([0, 1, 0, 1, 0], 1), ([1, 1, 1, 1, 1], 0)):
+        np.random.seed(11)
+        rep = scf_mod._DrawReplay(flt, inputs, owner, rank)
+        for g in range(5):
+            if owner[g] != rank:
+                continue
+            drawn, drawn_tol = rep.get(g, lengths(inputs[g]) if len(inputs[g]) else None)
+            assert drawn_tol is None
+            if want[g] is None:
+                assert drawn is None
+            else:
+                assert np.array_equal(np.asarray(cov.finish_draw(drawn)[1]), want[g]), g
+        rep.finish()
+        assert int(np.random.randint(0, 1 << 30)) == after
+    # odd lengths that the 48 samples miss: the owner's check raises
+    odd = strs(400, 100)
+    odd[7] = odd[7][:80]
+    np.random.seed(11)
+    rep = scf_mod._DrawReplay(flt, [odd], [0], 0)
+    with pytest.raises(scf_mod._LengthsNotUniform):
+        rep.get(0, cov.probe_lengths(odd))
+    rep.finish()
