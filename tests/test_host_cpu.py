@@ -93,6 +93,54 @@ def test_cli_parser_matches_reference_defaults():
         (5, 50, 0.6, 75, 300)
     with pytest.raises(SystemExit):
         design.init_and_parse_args('basic', ['x.fasta', '-o', 'o', '-c', '1.5'])
+    # genome clustering: off in design.py, on in design_large.py (bin/design.py:753-813 of the reference)
+    assert (a.cluster_and_design_separately, a.cluster_from_fragments, a.cluster_and_design_separately_method) == \
+        (None, None, 'choose')
+    assert (b.cluster_and_design_separately, b.cluster_from_fragments, b.cluster_and_design_separately_method) == \
+        (0.15, 50000, 'choose')
+    with pytest.raises(SystemExit):
+        design.init_and_parse_args('basic', ['x.fasta', '-o', 'o', '--cluster-and-design-separately', '0.6'])
+
+
+def test_probe_designer_cluster_path_with_stub_filters(monkeypatch):
+    """ProbeDesigner.design() with cluster_threshold (probe_designer.py:291-315): clusters become the groupings of the
+    filters up to cluster_merge_after, the rest run ungrouped on the merged probes.  The clustering itself is stubbed
+    (it needs the device); fragments, the 'choose' rule and the skip rule are the host logic under test."""
+    from catch_b200 import genome
+    from catch_b200.filter import probe_designer
+    from catch_b200.filter.base_filter import BaseFilter
+    from catch_b200.utils import cluster
+    calls = {}
+
+    def fake_cluster(seqs, threshold=None, cluster_method=None, **kw):
+        calls['n'] = len(seqs)
+        calls['method'] = cluster_method
+        keys = list(seqs)
+        return [keys[0::2], keys[1::2]]
+    monkeypatch.setattr(cluster, 'cluster_with_minhash_signatures', fake_cluster)
+
+    class Keep(BaseFilter):
+        def __init__(self):
+            self.seen = []
+
+        def _filter(self, input):
+            self.seen.append(len(input))
+            return list(input)[:3]
+    rng = np.random.default_rng(0)
+    letters = np.frombuffer(b'ACGT', dtype=np.uint8)
+    seqs = [letters[rng.integers(0, 4, 400)].tobytes().decode() for _ in range(5)] + ['ACGT' * 10]
+    genomes = [[genome.Genome.from_one_seq(s) for s in seqs]]
+    first, second = Keep(), Keep()
+    pd = probe_designer.ProbeDesigner(genomes, [first, second], probe_length=100, probe_stride=50,
+                                      seq_length_to_skip=50, cluster_threshold=0.15, cluster_merge_after=first,
+                                      cluster_method='choose', cluster_fragment_length=150)
+    pd.design()
+    # 5 sequences of 400 nt in fragments of 150 (the last one flush with the end): 3 each; the 40-nt sequence is skipped
+    assert calls == {'n': 15, 'method': 'hierarchical'}           # fragments shorter than the average sequence
+    assert len(first.seen) == 2                                    # once per cluster
+    assert len(second.seen) == 1 and 0 < second.seen[0] <= 6       # once, ungrouped, on the merged probes
+    assert 0 < len(pd.final_probes) <= 3
+    assert len(pd.candidate_probes) == sum(first.seen)
 
 
 def test_filters_fail_loudly_without_a_gpu():
