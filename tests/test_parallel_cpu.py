@@ -183,6 +183,12 @@ def _exchange_worker(rank, world, port, out_path, scenario):
             parallel.ensure_exchange(ctx, 1 << 20, token=11 + rank)        # ranks disagree on host state
         elif scenario == 'failed':
             parallel.ensure_exchange(ctx, 1 << 20, token=3, failed=(rank == 1))
+        elif scenario == 'lists_agree':
+            # group-sharded result exchange: both ranks hold the same lists (same fingerprint)
+            res = parallel.exchange_group_results({rank: [3 + rank, 1]}, [0, 1], rank, None, token=77)
+        elif scenario == 'lists_differ':
+            # ... or lists in a different order (a set-ordered list without a pinned PYTHONHASHSEED)
+            parallel.exchange_group_results({rank: [3 + rank, 1]}, [0, 1], rank, None, token=77 + rank)
         outcome = 'ok'
     except Exception as e:
         outcome = type(e).__name__ + ': ' + str(e)
@@ -191,7 +197,7 @@ def _exchange_worker(rank, world, port, out_path, scenario):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('scenario', ['grow', 'token', 'failed'])
+@pytest.mark.parametrize('scenario', ['grow', 'token', 'failed', 'lists_agree', 'lists_differ'])
 def test_ensure_exchange_over_gloo(tmp_path, scenario):
     """World size 2 over gloo: the exchange areas grow to the largest need of any rank and are mapped
     again only then; a rank-local failure or diverging RNG state raises on EVERY rank."""
@@ -217,6 +223,10 @@ def test_ensure_exchange_over_gloo(tmp_path, scenario):
         assert [e[1] for e in res[0][1] if e[0] == 'alloc'] == [e[1] for e in res[1][1] if e[0] == 'alloc']
     elif scenario == 'token':
         assert all(o[0].startswith('RuntimeError: ranks disagree') for o in res)
+    elif scenario == 'lists_agree':
+        assert all(o[0] == 'ok' and o[1] == [[3, 1], [4, 1]] for o in res)
+    elif scenario == 'lists_differ':
+        assert all(o[0].startswith('RuntimeError: ranks hold different probe lists') for o in res)
     else:
         assert all(o[0].startswith('RuntimeError: a rank failed') for o in res)
         assert '(this one)' in res[1][0] and '(this one)' not in res[0][0]
