@@ -503,3 +503,49 @@ def test_draw_replay_reproduces_the_sequential_stream():
     with pytest.raises(scf_mod._LengthsNotUniform):
         rep.get(0, cov.probe_lengths(odd))
     rep.finish()
+
+
+def test_connected_components_search_equals_the_reference_walk():
+    """find_connected_components with a device-style distance provider (rows thresholded to neighbour lists, fetched
+    ahead in batches) against the oracle's plain restatement of the reference's walk over every pair: random planar
+    point sets, ties at both thresholds, the early-stop heuristic on and off.  The provider here is a numpy stand-in
+    for cb_sketch_near_rows, so the host logic is checked without a GPU."""
+    from catch_b200.utils import cluster
+    from oracle import oracle
+
+    class FakeSketches(cluster.SketchSet):
+        def __init__(self, D):
+            self.D, self.n, self._row_cache, self.calls = D, len(D), {}, 0
+            self.h = None
+
+        @property
+        def ctx(self):
+            return self
+
+        def sketch_near_rows(self, h, want, thr):
+            self.calls += 1
+            off, idx, dist = [0], [], []
+            for j in want:
+                c = np.flatnonzero(self.D[j] <= thr)
+                idx.append(c.astype(np.uint32))
+                dist.append(self.D[j][c])
+                off.append(off[-1] + len(c))
+            return np.array(off, dtype=np.int64), np.concatenate(idx), np.concatenate(dist)
+
+    rng = np.random.default_rng(0)
+    visited = calls = 0
+    for trial in range(150):
+        n = int(rng.integers(1, 250))
+        pts = rng.random((n, 2)) * rng.choice([1, 3, 10])
+        D = np.sqrt(((pts[:, None] - pts[None]) ** 2).sum(-1))
+        if trial % 3 == 0:
+            D = np.round(D, 1)                       # many distances exactly at a threshold
+        thr = float(rng.choice([0.1, 0.3, 0.6]))
+        early = float(rng.choice([0, 0.05, 0.1, 0.3]))
+        f = FakeSketches(D)
+        got = cluster.find_connected_components(n, f, thr, early)
+        want = oracle.connected_components(n, lambda i, j: D[i, j], thr, early)
+        assert got == want, trial
+        visited += n
+        calls += f.calls
+    assert calls < visited / 3                        # rows are fetched in batches, not one call per vertex
