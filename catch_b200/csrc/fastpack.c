@@ -217,6 +217,78 @@ typedef struct { size_t name_b, name_e, seq_b, seq_e; } fasta_rec;
 
 static int is_py_space(unsigned char c) { return (c >= 0x09 && c <= 0x0d) || (c >= 0x1c && c <= 0x20); }
 
+/* One span [begin, end) of the file that starts at the beginning of a line (the file start or a header line): its
+ * records, transformed sequence bytes written to out[begin ..) (never more than were read). */
+typedef struct {
+    const unsigned char *p;
+    size_t begin, end;
+    unsigned char *out;
+    const unsigned char *map, *keep;
+    fasta_rec *rec;
+    size_t n_rec, cap, bad_at;
+    int oom;
+} fasta_job;
+
+static void *fasta_worker(void *arg)
+{
+    fasta_job *J = (fasta_job *)arg;
+    const unsigned char *p = J->p;
+    const size_t n = J->end;
+    size_t pos = J->begin, w = J->begin;
+    int in_record = 0;
+    while (pos < n) {
+        /* one line [pos, e), terminator consumed */
+        const unsigned char *nl = (const unsigned char *)memchr(p + pos, '\n', n - pos);
+        size_t e = nl ? (size_t)(nl - p) : n, next = nl ? e + 1 : n;
+        const unsigned char *cr = (const unsigned char *)memchr(p + pos, '\r', e - pos);
+        if (cr && !((size_t)(cr - p) + 1 == e && nl)) {      /* a lone '\r' ends the line too */
+            e = (size_t)(cr - p);
+            next = e + 1;
+            if (next < n && p[next] == '\n') next++;
+        }
+        size_t b = pos;
+        pos = next;
+        while (e > b && is_py_space(p[e - 1])) e--;
+        if (e == b) { in_record = 0; continue; }
+        if (!in_record && p[b] != '>') { J->bad_at = b; break; }
+        if (p[b] == '>') {
+            if (J->n_rec == J->cap) {
+                const size_t cap2 = J->cap ? J->cap * 2 : 1024;
+                fasta_rec *r2 = (fasta_rec *)realloc(J->rec, cap2 * sizeof(fasta_rec));
+                if (!r2) { J->oom = 1; break; }
+                J->rec = r2;
+                J->cap = cap2;
+            }
+            if (J->n_rec) J->rec[J->n_rec - 1].seq_e = w;
+            fasta_rec *r = &J->rec[J->n_rec++];
+            r->name_b = b + 1; r->name_e = e; r->seq_b = w; r->seq_e = w;
+            in_record = e - b > 1;      /* an empty name is the reference's "no record" marker (:137-143) */
+            continue;
+        }
+        for (size_t i = b; i < e; i++) {
+            const unsigned char c = p[i];
+            J->out[w] = J->map[c];
+            w += J->keep[c];
+        }
+    }
+    if (J->n_rec) J->rec[J->n_rec - 1].seq_e = w;
+    return NULL;
+}
+
+#define FASTA_THREADS 6
+/* files of at least this many bytes are parsed on several threads (CB_FASTA_PAR_BYTES overrides: the tests set it to 1
+ * so that tiny files exercise the cutting) */
+static size_t fasta_par_min_bytes(void)
+{
+    static size_t v = 0;
+    if (!v) {
+        const char *e = getenv("CB_FASTA_PAR_BYTES");
+        long long b = e ? atoll(e) : 0;
+        v = b > 0 ? (size_t)b : ((size_t)8 << 20);
+    }
+    return v;
+}
+
 static PyObject *parse_fasta(PyObject *self, PyObject *args)
 {
     Py_buffer view;
@@ -233,73 +305,80 @@ static PyObject *parse_fasta(PyObject *self, PyObject *args)
         keep[c] = !(skip_gaps && c == '-');
     }
     unsigned char *out = (unsigned char *)malloc(n ? n : 1);
-    size_t cap = 1024, n_rec = 0, bad_at = (size_t)-1;
-    fasta_rec *rec = (fasta_rec *)malloc(cap * sizeof(fasta_rec));
-    if (!out || !rec) { free(out); free(rec); PyBuffer_Release(&view); return PyErr_NoMemory(); }
-    int oom = 0;
+    if (!out) { PyBuffer_Release(&view); return PyErr_NoMemory(); }
+    fasta_job jobs[FASTA_THREADS];
+    int n_jobs = 0;
     Py_BEGIN_ALLOW_THREADS
-    size_t pos = 0, w = 0;
-    int in_record = 0;
-    while (pos < n) {
-        /* one line [pos, e), terminator consumed */
-        const unsigned char *nl = (const unsigned char *)memchr(p + pos, '\n', n - pos);
-        size_t e = nl ? (size_t)(nl - p) : n, next = nl ? e + 1 : n;
-        const unsigned char *cr = (const unsigned char *)memchr(p + pos, '\r', e - pos);
-        if (cr && !((size_t)(cr - p) + 1 == e && nl)) {      /* a lone '\r' ends the line too */
-            e = (size_t)(cr - p);
-            next = e + 1;
-            if (next < n && p[next] == '\n') next++;
-        }
-        size_t b = pos;
-        pos = next;
-        while (e > b && is_py_space(p[e - 1])) e--;
-        if (e == b) { in_record = 0; continue; }
-        if (!in_record && p[b] != '>') { bad_at = b; break; }
-        if (p[b] == '>') {
-            if (n_rec == cap) {
-                cap *= 2;
-                fasta_rec *r2 = (fasta_rec *)realloc(rec, cap * sizeof(fasta_rec));
-                if (!r2) { oom = 1; break; }
-                rec = r2;
+    /* Large files are cut at header lines ('>' right after a line end) into spans that are parsed independently: a
+     * header line sets the parser's whole state, and a span's output never outgrows its input. */
+    size_t cuts[FASTA_THREADS + 1];
+    cuts[0] = 0;
+    n_jobs = 1;
+    if (n >= fasta_par_min_bytes()) {
+        for (int t = 1; t < FASTA_THREADS; t++) {
+            size_t i = n / FASTA_THREADS * (size_t)t;
+            if (i <= cuts[n_jobs - 1]) i = cuts[n_jobs - 1] + 1;
+            for (; i < n; i++) {
+                const unsigned char *g = (const unsigned char *)memchr(p + i, '>', n - i);
+                if (!g) { i = n; break; }
+                i = (size_t)(g - p);
+                if (i > 0 && (p[i - 1] == '\n' || p[i - 1] == '\r')) break;
             }
-            if (n_rec) rec[n_rec - 1].seq_e = w;
-            rec[n_rec].name_b = b + 1; rec[n_rec].name_e = e; rec[n_rec].seq_b = w; rec[n_rec].seq_e = w;
-            n_rec++;
-            in_record = e - b > 1;      /* an empty name is the reference's "no record" marker (:137-143) */
-            continue;
-        }
-        for (size_t i = b; i < e; i++) {
-            const unsigned char c = p[i];
-            out[w] = map[c];
-            w += keep[c];
+            if (i < n) cuts[n_jobs++] = i;
+            else break;
         }
     }
-    if (n_rec) rec[n_rec - 1].seq_e = w;
+    cuts[n_jobs] = n;
+    for (int t = 0; t < n_jobs; t++) {
+        jobs[t].p = p; jobs[t].begin = cuts[t]; jobs[t].end = cuts[t + 1]; jobs[t].out = out;
+        jobs[t].map = map; jobs[t].keep = keep; jobs[t].rec = NULL; jobs[t].n_rec = 0; jobs[t].cap = 0;
+        jobs[t].bad_at = (size_t)-1; jobs[t].oom = 0;
+    }
+    {
+        pthread_t th[FASTA_THREADS];
+        int started[FASTA_THREADS];
+        for (int t = 1; t < n_jobs; t++) started[t] = pthread_create(&th[t], NULL, fasta_worker, &jobs[t]) == 0;
+        fasta_worker(&jobs[0]);
+        for (int t = 1; t < n_jobs; t++) {
+            if (started[t]) pthread_join(th[t], NULL);
+            else fasta_worker(&jobs[t]);
+        }
+    }
     Py_END_ALLOW_THREADS
     PyObject *names = NULL, *seqs = NULL, *ret = NULL;
-    if (oom) { PyErr_NoMemory(); goto done; }
-    if (bad_at != (size_t)-1) {
-        PyErr_Format(PyExc_AssertionError, "FASTA: sequence data without a header at byte %zu", bad_at);
-        goto done;
+    size_t n_rec = 0;
+    for (int t = 0; t < n_jobs; t++) {
+        if (jobs[t].oom) { PyErr_NoMemory(); goto done; }
+        if (jobs[t].bad_at != (size_t)-1) {
+            PyErr_Format(PyExc_AssertionError, "FASTA: sequence data without a header at byte %zu", jobs[t].bad_at);
+            goto done;
+        }
+        n_rec += jobs[t].n_rec;
     }
     names = PyList_New((Py_ssize_t)n_rec);
     seqs = PyList_New((Py_ssize_t)n_rec);
     if (!names || !seqs) goto done;
-    for (size_t i = 0; i < n_rec; i++) {
-        PyObject *nm = PyUnicode_New((Py_ssize_t)(rec[i].name_e - rec[i].name_b), 127);
-        PyObject *sq = PyUnicode_New((Py_ssize_t)(rec[i].seq_e - rec[i].seq_b), 127);
-        if (!nm || !sq) { Py_XDECREF(nm); Py_XDECREF(sq); goto done; }
-        memcpy(PyUnicode_1BYTE_DATA(nm), p + rec[i].name_b, rec[i].name_e - rec[i].name_b);
-        memcpy(PyUnicode_1BYTE_DATA(sq), out + rec[i].seq_b, rec[i].seq_e - rec[i].seq_b);
-        PyList_SET_ITEM(names, (Py_ssize_t)i, nm);
-        PyList_SET_ITEM(seqs, (Py_ssize_t)i, sq);
+    {
+        Py_ssize_t at = 0;
+        for (int t = 0; t < n_jobs; t++)
+            for (size_t i = 0; i < jobs[t].n_rec; i++) {
+                const fasta_rec *r = &jobs[t].rec[i];
+                PyObject *nm = PyUnicode_New((Py_ssize_t)(r->name_e - r->name_b), 127);
+                PyObject *sq = PyUnicode_New((Py_ssize_t)(r->seq_e - r->seq_b), 127);
+                if (!nm || !sq) { Py_XDECREF(nm); Py_XDECREF(sq); goto done; }
+                memcpy(PyUnicode_1BYTE_DATA(nm), p + r->name_b, r->name_e - r->name_b);
+                memcpy(PyUnicode_1BYTE_DATA(sq), out + r->seq_b, r->seq_e - r->seq_b);
+                PyList_SET_ITEM(names, at, nm);
+                PyList_SET_ITEM(seqs, at, sq);
+                at++;
+            }
     }
     ret = PyTuple_Pack(2, names, seqs);
 done:
     Py_XDECREF(names);
     Py_XDECREF(seqs);
     free(out);
-    free(rec);
+    for (int t = 0; t < n_jobs; t++) free(jobs[t].rec);
     PyBuffer_Release(&view);
     return ret;
 }

@@ -549,3 +549,35 @@ def test_connected_components_search_equals_the_reference_walk():
         visited += n
         calls += f.calls
     assert calls < visited / 3                        # rows are fetched in batches, not one call per vertex
+
+
+def test_fasta_reader_multi_span_path_matches_reference_fixtures(tmp_path):
+    """The native parser cuts large files at header lines and parses the spans on several threads; with the size
+    threshold at one byte (read once per process: a child interpreter) the 400 reference-recorded files go through
+    that path, cuts included."""
+    import subprocess
+    code = r'''
+import base64, gzip, os, sys
+sys.path.insert(0, %r)
+from catch_b200.utils import seq_io
+from tests import golden_io
+tmp = %r
+n_ok = n_rejected = 0
+for c in golden_io.load('f4_reference.json.gz'):
+    fn = os.path.join(tmp, 't.fasta.gz' if c['gz'] else 't.fasta')
+    with (gzip.open(fn, 'wb') if c['gz'] else open(fn, 'wb')) as f:
+        f.write(base64.b64decode(c['data']))
+    try:
+        got = [[n, s] for n, s in seq_io.read_fasta(fn, **c['kw']).items()]
+    except AssertionError:
+        got = 'AssertionError'
+    assert got == c['out'], c
+    n_ok += got != 'AssertionError'
+    n_rejected += got == 'AssertionError'
+print(n_ok, n_rejected)
+''' % (ROOT, str(tmp_path))
+    r = subprocess.run([sys.executable, '-c', code], env=dict(os.environ, CB_FASTA_PAR_BYTES='1'), capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    n_ok, n_rejected = map(int, r.stdout.split())
+    assert n_ok > 150 and n_rejected > 50
