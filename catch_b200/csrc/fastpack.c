@@ -384,6 +384,82 @@ done:
 }
 
 
+/* fasta_stream_block(data, replace_degenerate) -> list
+ * One block of an ASCII FASTA file that ends at a line end, for the streaming reader (the reference's
+ * seq_io.iterate_fasta, catch/utils/seq_io.py:178-232: no upper-casing, no gap removal, blank lines skipped, header
+ * text ignored): the list holds, in file order, None for every header line and a bytes object for every run of
+ * sequence lines between two headers (lines right-stripped and concatenated, [YRWSMKBDHV] -> N when asked).  The caller
+ * joins the runs of a record across blocks and yields it at the next header. */
+static PyObject *fasta_stream_block(PyObject *self, PyObject *args)
+{
+    Py_buffer view;
+    int replace_degenerate = 1;
+    if (!PyArg_ParseTuple(args, "y*|p", &view, &replace_degenerate)) return NULL;
+    const unsigned char *p = (const unsigned char *)view.buf;
+    const size_t n = (size_t)view.len;
+    unsigned char map[256];
+    for (int c = 0; c < 256; c++) map[c] = (unsigned char)((replace_degenerate && c && strchr("YRWSMKBDHV", c)) ? 'N' : c);
+    unsigned char *out = (unsigned char *)malloc(n ? n : 1);
+    /* runs: [b, e) in out; a header is recorded as b == (size_t)-1 */
+    size_t cap = 256, n_items = 0;
+    size_t (*items)[2] = (size_t (*)[2])malloc(cap * sizeof *items);
+    if (!out || !items) { free(out); free(items); PyBuffer_Release(&view); return PyErr_NoMemory(); }
+    int oom = 0;
+    Py_BEGIN_ALLOW_THREADS
+    size_t pos = 0, w = 0, run_b = 0;
+    while (pos < n && !oom) {
+        const unsigned char *nl = (const unsigned char *)memchr(p + pos, '\n', n - pos);
+        size_t e = nl ? (size_t)(nl - p) : n, next = nl ? e + 1 : n;
+        const unsigned char *cr = (const unsigned char *)memchr(p + pos, '\r', e - pos);
+        if (cr && !((size_t)(cr - p) + 1 == e && nl)) {
+            e = (size_t)(cr - p);
+            next = e + 1;
+            if (next < n && p[next] == '\n') next++;
+        }
+        size_t b = pos;
+        pos = next;
+        while (e > b && is_py_space(p[e - 1])) e--;
+        if (e == b) continue;                                  /* blank line: skipped (:218-220) */
+        if (p[b] == '>') {
+            if (n_items + 2 > cap) {
+                cap *= 2;
+                size_t (*i2)[2] = (size_t (*)[2])realloc(items, cap * sizeof *items);
+                if (!i2) { oom = 1; break; }
+                items = i2;
+            }
+            if (w > run_b) { items[n_items][0] = run_b; items[n_items][1] = w; n_items++; }
+            items[n_items][0] = (size_t)-1; items[n_items][1] = 0; n_items++;
+            run_b = w;
+            continue;
+        }
+        for (size_t i = b; i < e; i++) out[w++] = map[p[i]];
+    }
+    if (!oom && w > run_b) {
+        if (n_items + 1 > cap) {
+            size_t (*i2)[2] = (size_t (*)[2])realloc(items, (cap + 1) * sizeof *items);
+            if (!i2) oom = 1; else items = i2;
+        }
+        if (!oom) { items[n_items][0] = run_b; items[n_items][1] = w; n_items++; }
+    }
+    Py_END_ALLOW_THREADS
+    PyObject *ret = NULL;
+    if (oom) { PyErr_NoMemory(); goto done; }
+    ret = PyList_New((Py_ssize_t)n_items);
+    if (!ret) goto done;
+    for (size_t i = 0; i < n_items; i++) {
+        PyObject *it;
+        if (items[i][0] == (size_t)-1) { it = Py_None; Py_INCREF(it); }
+        else it = PyBytes_FromStringAndSize((const char *)out + items[i][0], (Py_ssize_t)(items[i][1] - items[i][0]));
+        if (!it) { Py_CLEAR(ret); goto done; }
+        PyList_SET_ITEM(ret, (Py_ssize_t)i, it);
+    }
+done:
+    free(out);
+    free(items);
+    PyBuffer_Release(&view);
+    return ret;
+}
+
 /* copy_into(buffer, address) -> int bytes: one contiguous buffer (a ProbeBatch's byte matrix) into caller-owned memory
  * (the library's page-locked staging buffer), on several threads from par_copy_min_bytes() on, GIL released. */
 typedef struct { const char *src; char *dst; size_t n; } span_job;
@@ -427,6 +503,8 @@ static PyObject *copy_into(PyObject *self, PyObject *args)
 }
 
 static PyMethodDef methods[] = {
+    {"fasta_stream_block", fasta_stream_block, METH_VARARGS,
+     "fasta_stream_block(data, replace_degenerate=True) -> [None | bytes, ...] (headers and runs of sequence lines)"},
     {"copy_into", copy_into, METH_VARARGS, "copy_into(buffer, address) -> bytes copied (threaded for large buffers)"},
     {"parse_fasta", parse_fasta, METH_VARARGS,
      "parse_fasta(data, make_uppercase=True, replace_degenerate=True, skip_gaps=True) -> (names, sequences)"},

@@ -66,10 +66,64 @@ def _read_fasta_lines(fn, replace_degenerate=True, skip_gaps=True, make_uppercas
     return OrderedDict((k, ''.join(v)) for k, v in chunks.items())
 
 
-def iterate_fasta(fn, replace_degenerate=True):
-    """Yield sequences one at a time (no upper-casing, as reference :178-232)."""
-    cur = []
-    with _open(fn) as f:
+def iterate_fasta(fn, data_type='str', replace_degenerate=True, block_bytes=64 << 20):
+    """Yield sequences one at a time (no upper-casing, no gap removal, as the reference's seq_io.iterate_fasta
+    :178-232).  The file is read in blocks of `block_bytes` that are cut at a line end and scanned natively
+    (`_fastpack.fasta_stream_block`); a sequence is held in memory only until the header that follows it.  A block
+    with non-ASCII bytes hands the rest of the file to the Python line loop."""
+    if data_type != 'str':
+        raise ValueError("Unknown data_type " + data_type if data_type != 'np' else
+                         "data_type 'np' (arrays of single characters) is not provided; sequences are str")
+    if _fastpack is None or not hasattr(_fastpack, 'fasta_stream_block'):
+        yield from _iterate_fasta_lines(_open(fn), [], replace_degenerate)
+        return
+    pieces = []                                            # runs of the sequence being read (str)
+    with (gzip.open(fn, 'rb') if fn.endswith('.gz') else open(fn, 'rb')) as f:
+        tail = b''
+        while True:
+            block = f.read(block_bytes)
+            if not block:
+                break
+            block = tail + block
+            # cut at the last line end whose successor is known (a '\r' at the very end may be half of a '\r\n')
+            cut = block.rfind(b'\n') + 1
+            if cut == 0:
+                cut = block.rfind(b'\r', 0, len(block) - 1) + 1
+            tail, block = block[cut:], block[:cut]
+            if not block:
+                continue                                   # one line longer than the block: keep reading
+            if not block.isascii():
+                import io
+                rest = io.TextIOWrapper(io.BytesIO(block + tail + f.read()))
+                yield from _iterate_fasta_lines(rest, pieces, replace_degenerate)
+                return
+            for item in _fastpack.fasta_stream_block(block, replace_degenerate):
+                if item is None:
+                    if pieces:
+                        yield ''.join(pieces)
+                    pieces = []
+                else:
+                    pieces.append(item.decode('ascii'))
+        if tail:
+            if not tail.isascii():
+                import io
+                yield from _iterate_fasta_lines(io.TextIOWrapper(io.BytesIO(tail)), pieces, replace_degenerate)
+                return
+            for item in _fastpack.fasta_stream_block(tail, replace_degenerate):
+                if item is None:
+                    if pieces:
+                        yield ''.join(pieces)
+                    pieces = []
+                else:
+                    pieces.append(item.decode('ascii'))
+    if pieces:
+        yield ''.join(pieces)
+
+
+def _iterate_fasta_lines(f, cur, replace_degenerate=True):
+    """The line loop of iterate_fasta on an open text file, continuing a sequence whose first runs are in `cur`."""
+    cur = list(cur)
+    with f:
         for line in f:
             line = line.rstrip()
             if not line:

@@ -581,3 +581,28 @@ print(n_ok, n_rejected)
     assert r.returncode == 0, r.stderr[-2000:]
     n_ok, n_rejected = map(int, r.stdout.split())
     assert n_ok > 150 and n_rejected > 50
+
+
+def test_fasta_streaming_reader_matches_reference_fixtures(tmp_path):
+    """seq_io.iterate_fasta (blocks cut at line ends, scanned natively) against the reference's iterate_fasta outputs
+    recorded by tests/golden/make_f4_golden.py, with block sizes from a few bytes (every cut position) to one block."""
+    import base64
+    import gzip
+    from catch_b200.utils import seq_io
+    from tests import golden_io
+    assert hasattr(seq_io._fastpack, 'fasta_stream_block')
+    n = 0
+    for k, c in enumerate(golden_io.load('f4_reference.json.gz')):
+        fn = str(tmp_path / ('t.fasta.gz' if c['gz'] else 't.fasta'))
+        with (gzip.open(fn, 'wb') if c['gz'] else open(fn, 'wb')) as f:
+            f.write(base64.b64decode(c['data']))
+        for bs in (1 + k % 9, 50 + k % 40, 64 << 20):
+            got = list(seq_io.iterate_fasta(fn, replace_degenerate=c['kw']['replace_degenerate'], block_bytes=bs))
+            assert got == c['iter'], (k, bs)
+            n += len(got)
+    assert n > 1000
+    fn = str(tmp_path / 'u.fasta')
+    with open(fn, 'w', encoding='utf-8') as f:                                # non-ASCII: the line loop takes over
+        f.write('>a\nACGY\n>gé\nACéT\nyy\n')
+    for bs in (3, 64 << 20):
+        assert list(seq_io.iterate_fasta(fn, block_bytes=bs)) == ['ACGN', 'ACéTyy']
